@@ -1,0 +1,411 @@
+/*
+ * qsgpu.h -- C ABI of libqsgpu.so: the B200 (sm_100a) execution path for
+ * Quickstep's data-parallel relational operators.
+ *
+ * The reference (UWQuickstep/quickstep @ fee4c630) has no FFI: its seam is the
+ * pair of C++ virtuals RelationalOperator::getAllWorkOrders()
+ * (relational_operators/RelationalOperator.hpp:132) and WorkOrder::execute()
+ * (relational_operators/WorkOrder.hpp:251).  This header is what the bodies of
+ * GPU work orders call *under* execute(); every entry point cites the
+ * reference code it replaces.  Plain pointers and sizes only; every function
+ * returns 0 on success and a non-zero qsgpu_status otherwise (the C++ wrapper
+ * turns non-zero into LOG(FATAL), the reference's error convention,
+ * relational_operators/BuildHashOperator.cpp:205).
+ *
+ * Type ids, comparison ids and operation ids use the reference's own enum
+ * values (types/TypeID.hpp:33-45, types/operations/comparisons/ComparisonID.hpp,
+ * types/operations/binary_operations/BinaryOperationID.hpp) so that a
+ * serialization::Predicate / serialization::Scalar proto lowers 1:1 into a
+ * qs_node array.
+ *
+ * There is NO CPU fallback behind this ABI: with no CUDA device every compute
+ * entry point fails with QSGPU_ERR_NO_DEVICE.
+ */
+#ifndef QSGPU_H_
+#define QSGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+typedef enum qsgpu_status {
+  QSGPU_OK = 0,
+  QSGPU_ERR_NO_DEVICE = 1,      /* no CUDA device / init not called           */
+  QSGPU_ERR_CUDA = 2,           /* a CUDA runtime call failed                 */
+  QSGPU_ERR_INVALID = 3,        /* bad argument / malformed expression tree   */
+  QSGPU_ERR_UNSUPPORTED = 4,    /* valid in the reference, not lowered (yet)  */
+  QSGPU_ERR_CAPACITY = 5,       /* table / output relation capacity exceeded  */
+  QSGPU_ERR_OOM = 6
+} qsgpu_status;
+
+/* Thread-local text of the last error raised on the calling thread. */
+const char *qsgpu_last_error(void);
+
+/* ------------------------------------------------------------------- types */
+/* Values follow types/TypeID.hpp:33-45. */
+enum {
+  QS_INT = 0,      /* int32                                                    */
+  QS_LONG = 1,     /* int64                                                    */
+  QS_FLOAT = 2,    /* float                                                    */
+  QS_DOUBLE = 3,   /* double (SQL DECIMAL parses to this, SqlParser.ypp:791)   */
+  QS_CHAR = 4,     /* fixed width, NUL padded, strncmp order                   */
+  QS_VARCHAR = 5,  /* never staged on device (QSGPU_ERR_UNSUPPORTED)           */
+  QS_DATE = 6      /* DateLit {int32 year; u8 month; u8 day; 2 pad} = 8 bytes, */
+                   /* lexicographic order (types/DatetimeLit.hpp:38-93)        */
+};
+
+/* Comparison ids (types/operations/comparisons/ComparisonID.hpp). */
+enum { QS_EQ = 0, QS_NE = 1, QS_LT = 2, QS_LE = 3, QS_GT = 4, QS_GE = 5 };
+
+/* Binary operation ids (binary_operations/BinaryOperationID.hpp). */
+enum { QS_ADD = 0, QS_SUB = 1, QS_MUL = 2, QS_DIV = 3, QS_MOD = 4 };
+
+/* Unary operation ids used on the path. */
+enum { QS_NEGATE = 0, QS_CAST = 1 };
+
+/* Aggregate function ids (expressions/aggregation/AggregationID.hpp). */
+enum { QS_AGG_AVG = 0, QS_AGG_COUNT = 1, QS_AGG_MAX = 2, QS_AGG_MIN = 3, QS_AGG_SUM = 4 };
+
+/*
+ * Flattened expression tree: serialization::Predicate and
+ * serialization::Scalar (expressions/Expressions.proto:29-137) in one node
+ * array.  Children are referenced by index and must precede their parent.
+ */
+enum {
+  QS_N_LITERAL = 0,     /* Scalar LITERAL:  type/width, value in lit           */
+  QS_N_ATTRIBUTE = 1,   /* Scalar ATTRIBUTE: a = attribute id, b = join side   */
+                        /*   (0 none / probe side, 2 = build side, matching    */
+                        /*   ScalarAttribute::JoinSide RIGHT_SIDE)             */
+  QS_N_UNARY = 2,       /* op = QS_NEGATE | QS_CAST (to `type`), a = operand   */
+  QS_N_BINARY = 3,      /* op = QS_ADD.., a = left, b = right                  */
+  QS_N_SHARED = 5,      /* ScalarSharedExpression: a = operand, b = share id   */
+  QS_N_TRUE = 16,       /* Predicate TRUE                                      */
+  QS_N_FALSE = 17,
+  QS_N_COMPARISON = 18, /* op = QS_EQ.., a = left scalar, b = right scalar     */
+  QS_N_NEGATION = 19,   /* a = operand predicate                               */
+  QS_N_CONJUNCTION = 20,/* a, b = operand predicates (n-ary lists are folded   */
+  QS_N_DISJUNCTION = 21 /*   into left-deep binary chains by the caller)       */
+};
+
+typedef struct qs_node {
+  uint16_t kind;   /* QS_N_*                                                   */
+  uint16_t op;     /* comparison / binary / unary id                           */
+  uint16_t type;   /* result type of a scalar node (QS_INT..QS_DATE)           */
+  uint16_t width;  /* byte width for QS_CHAR (attribute or literal)            */
+  int32_t a;
+  int32_t b;
+  union {
+    int32_t i32;
+    int64_t i64;
+    float f32;
+    double f64;
+    struct { int32_t year; uint8_t month, day, pad[2]; } date;
+    uint64_t pool_offset; /* QS_CHAR literal: offset into the string pool      */
+  } lit;
+} qs_node;
+
+/* An expression "program": the node array plus the CHAR literal pool. */
+typedef struct qs_expr_set {
+  const qs_node *nodes;
+  uint32_t n_nodes;
+  const char *str_pool;
+  uint32_t str_pool_bytes;
+} qs_expr_set;
+
+/* --------------------------------------------------------- runtime/devices */
+/* Called once per process before anything else (cli/QuickstepCli.cpp:183-284
+ * is where the reference brings up its workers).  dev_ids == NULL means
+ * devices 0..n_dev-1; n_dev == 0 means "all visible". */
+int qsgpu_init(int n_dev, const int *dev_ids);
+int qsgpu_shutdown(void);
+int qsgpu_device_count(int *n_dev);
+/* Block until all work queued on `dev` by this library has completed. */
+int qsgpu_synchronize(int dev);
+/* Number of kernels this library has launched since init (bench.py's
+ * gpu_launches); never reset by the library. */
+int qsgpu_launch_count(uint64_t *n);
+
+/* Raw device memory (StorageManager-side allocations for staged columns). */
+int qsgpu_malloc(int dev, size_t bytes, void **dptr);
+int qsgpu_free(int dev, void *dptr);
+int qsgpu_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes);
+int qsgpu_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes);
+/* Pinned host memory for staging buffers. */
+int qsgpu_host_alloc(size_t bytes, void **hptr);
+int qsgpu_host_free(void *hptr);
+
+/* ---------------------------------------------- device-resident relations */
+/*
+ * A device relation is the HBM image of a CatalogRelation's blocks: one
+ * contiguous, 256-byte aligned, native-width buffer per attribute (the
+ * ColumnVector-equivalent the north star asks for), padded so that 16 bytes
+ * past the last row are always readable.  Temporary relations produced by
+ * Select / HashJoin / FinalizeAggregation are device relations too (the
+ * analogue of the temporary SplitRowStore relations written through
+ * InsertDestination, storage/InsertDestination.cpp:202-216).
+ */
+typedef struct qsgpu_relation *qsgpu_relation_t;
+
+typedef struct qs_attr {
+  uint16_t type;   /* QS_INT..QS_DATE */
+  uint16_t width;  /* bytes per value (4, 8, 4, 8, n, -, 8) */
+} qs_attr;
+
+int qsgpu_relation_create(int dev, uint32_t n_attrs, const qs_attr *attrs,
+                          uint64_t capacity_rows, qsgpu_relation_t *out);
+int qsgpu_relation_destroy(qsgpu_relation_t rel);
+int qsgpu_relation_num_rows(qsgpu_relation_t rel, uint64_t *n_rows);
+int qsgpu_relation_set_num_rows(qsgpu_relation_t rel, uint64_t n_rows);
+/* Device pointer of attribute `attr` (row 0). */
+int qsgpu_relation_column(qsgpu_relation_t rel, uint32_t attr, void **dptr);
+/* Wrap caller-owned device buffers (e.g. generated in place) without copy.
+ * Buffers must be 16-byte aligned and readable 16 bytes past the last row. */
+int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs,
+                        void *const *dptrs, uint64_t n_rows,
+                        qsgpu_relation_t *out);
+/* Copy rows [row_begin, row_begin+n_rows) of one attribute to the host
+ * (InsertDestination::bulkInsertTuples direction). */
+int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
+                        uint64_t n_rows, void *host_out);
+
+/*
+ * K0 -- staging of one storage block's attribute into a device relation,
+ * appended at the relation's current end.  Physical encodings of the
+ * reference's sub-blocks:
+ *   QS_ENC_PLAIN      BasicColumnStore stripe
+ *                     (storage/BasicColumnStoreTupleStorageSubBlock.cpp:100-183)
+ *   QS_ENC_STRIDED    fixed-width attribute inside SplitRowStore tuple slots
+ *                     (storage/SplitRowStoreTupleStorageSubBlock.cpp:103-179):
+ *                     value i at host + i*stride
+ *   QS_ENC_DICT       CompressedColumnStore stripe of 1/2/4-byte codes into an
+ *                     ordered dictionary (compression/CompressionDictionaryLite.hpp:40-51,
+ *                     storage/CompressedColumnStoreTupleStorageSubBlock.cpp:203-215)
+ *   QS_ENC_TRUNCATED  CompressedColumnStore stripe of a non-negative INT/LONG
+ *                     truncated to 1/2/4 bytes
+ *                     (storage/CompressedBlockBuilder.cpp:434-506)
+ * The block is decoded to native width on the device by the K0 kernels.
+ */
+enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3 };
+
+typedef struct qs_stage_desc {
+  uint32_t attr;         /* target attribute                                   */
+  uint32_t encoding;     /* QS_ENC_*                                           */
+  const void *host;      /* host stripe / first slot                           */
+  uint32_t code_width;   /* DICT/TRUNCATED: 1, 2 or 4                          */
+  uint32_t stride;       /* STRIDED: tuple slot bytes                          */
+  const void *dict;      /* DICT: values array (native width, sorted)          */
+  uint32_t dict_entries; /* DICT: number of codes                              */
+  uint32_t reserved;
+} qs_stage_desc;
+
+/* Stage `n_desc` attributes of one block of `n_rows` tuples; all attributes
+ * of the relation must be staged by the same call or by calls made before
+ * qsgpu_relation_commit_block(). */
+int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows,
+                      const qs_stage_desc *descs, uint32_t n_desc);
+
+/* ----------------------------------------------------------- LIP filters  */
+/*
+ * K4.  utility/lip_filter/BitVectorExactFilter.hpp:61-176 (bit v-min; probe
+ * out of range -> is_anti) and SingleIdentityHashFilter.hpp:62-171 (bit
+ * (uint64)v % cardinality).  Bits live in 64-bit words, MSB first, exactly as
+ * BarrieredReadWriteConcurrentBitVector (utility/
+ * BarrieredReadWriteConcurrentBitVector.hpp:128-147) so a device filter can be
+ * compared with (or handed to) the host structure bit for bit.
+ */
+typedef struct qsgpu_lip *qsgpu_lip_t;
+enum { QS_LIP_BITVECTOR_EXACT = 0, QS_LIP_SINGLE_IDENTITY_HASH = 1 };
+
+int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type /*QS_INT|QS_LONG*/,
+                     int64_t min_value, int64_t max_value, /* exact filter     */
+                     uint64_t cardinality,                 /* identity hash    */
+                     int is_anti, qsgpu_lip_t *out);
+int qsgpu_lip_destroy(qsgpu_lip_t lip);
+int qsgpu_lip_num_words(qsgpu_lip_t lip, uint64_t *n_words);
+int qsgpu_lip_read(qsgpu_lip_t lip, uint64_t *host_words);
+/* Device address of the bit words (for NCCL all-reduce(BOR) across GPUs). */
+int qsgpu_lip_device_words(qsgpu_lip_t lip, void **dptr);
+
+/* A filter bound to the attribute it is built from / probed with
+ * (LIPFilterDeployment, utility/lip_filter/LIPFilterDeployment.cpp). */
+typedef struct qs_lip_ref {
+  qsgpu_lip_t lip;
+  uint32_t attr;      /* attribute of the scanned relation */
+  uint32_t reserved;
+} qs_lip_ref;
+
+/* ------------------------------------------------------------ scan source */
+/* What every operator scans: a row range of a device relation, an optional
+ * predicate (root index into exprs, -1 = none) and LIP filters to probe. */
+typedef struct qs_scan {
+  qsgpu_relation_t input;
+  uint64_t row_begin, row_end;     /* row_end == UINT64_MAX -> all rows       */
+  const qs_expr_set *exprs;        /* may be NULL when nothing refers to it   */
+  int32_t predicate_root;          /* -1: no predicate                        */
+  uint32_t n_lip_probe;
+  const qs_lip_ref *lip_probe;     /* LIPFilterAdaptiveProber::filterValueAccessor */
+} qs_scan;
+
+/* --------------------------------------------------------- BuildLIPFilter */
+/* BuildLIPFilterWorkOrder::execute (relational_operators/
+ * BuildLIPFilterOperator.cpp:146-172): predicate -> probe upstream filters ->
+ * insert survivors into the target filters. */
+int qsgpu_build_lip_filter(const qs_scan *scan, uint32_t n_build,
+                           const qs_lip_ref *build);
+
+/* ------------------------------------------------------------------ Select */
+/*
+ * K3.  SelectWorkOrder::execute (relational_operators/SelectOperator.cpp:161-195):
+ * predicate -> LIP probe -> projection -> output relation.  Projection column
+ * j is the scalar rooted at project_roots[j] (a bare attribute node is the
+ * selectSimple path, StorageBlock.cpp:390-398).  Rows are appended to `output`
+ * (rows of one tile stay in input order; tiles interleave, like blocks of
+ * concurrent work orders do in the reference).
+ */
+int qsgpu_select(const qs_scan *scan, uint32_t n_project,
+                 const int32_t *project_roots, qsgpu_relation_t output);
+
+/* ------------------------------------------------------------- aggregation */
+/*
+ * AggregationOperationState (storage/AggregationOperationState.hpp:72-320):
+ * created once per query from the serialized description
+ * (query_execution/QueryContext.cpp:66-77), fed by one qsgpu_agg_run per work
+ * order (AggregationWorkOrder::execute -> aggregateBlock,
+ * storage/AggregationOperationState.cpp:428-474), finalized by
+ * FinalizeAggregationWorkOrder (…:641-948) and freed by
+ * DestroyAggregationStateWorkOrder.
+ *
+ * Strategy (ExecutionGenerator.cpp:1924-1965 decides in the reference):
+ *   QS_AGG_SINGLE_STATE     no GROUP BY        (K1; aggregateBlockSingleState)
+ *   QS_AGG_COMPACT_KEY      keys total <= 8 B  (K2; ThreadPrivateCompactKeyHashTable)
+ *   QS_AGG_SEPARATE_CHAINING generic keys <= 32 B (K7; PackedPayloadHashTable)
+ *   QS_AGG_COLLISION_FREE   one INT/LONG key used as the array index
+ *                                              (K7d; CollisionFreeVectorTable)
+ */
+enum {
+  QS_AGG_SINGLE_STATE = 0,
+  QS_AGG_COMPACT_KEY = 1,
+  QS_AGG_SEPARATE_CHAINING = 2,
+  QS_AGG_COLLISION_FREE = 3
+};
+
+typedef struct qs_aggregate {
+  uint32_t function;     /* QS_AGG_*                                           */
+  int32_t argument_root; /* scalar root in exprs; -1 for COUNT(*)              */
+} qs_aggregate;
+
+typedef struct qs_agg_spec {
+  int dev;
+  uint32_t strategy;
+  const qs_expr_set *exprs;          /* predicate + arguments + group-by      */
+  int32_t predicate_root;            /* -1: none                              */
+  uint32_t n_aggregates;
+  const qs_aggregate *aggregates;
+  uint32_t n_group_by;
+  const int32_t *group_by_roots;     /* attribute nodes                       */
+  uint64_t estimated_num_entries;    /* table sizing (proto field 5)          */
+  int64_t collision_free_max_key;    /* QS_AGG_COLLISION_FREE: num_entries-1  */
+} qs_agg_spec;
+
+typedef struct qsgpu_agg_state *qsgpu_agg_state_t;
+
+int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out);
+/* One work order: aggregate rows [row_begin,row_end) of `input`; the state's
+ * own predicate is applied, plus the LIP probes given here. */
+int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input,
+                  uint64_t row_begin, uint64_t row_end,
+                  uint32_t n_lip_probe, const qs_lip_ref *lip_probe);
+/* Number of groups currently in the state (1 for SINGLE_STATE). */
+int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups);
+/*
+ * Raw partial state for cross-GPU merging (AggregationHandle::mergeStates):
+ * a device array of n_groups x (n_aggregates + 1) 64-bit words, row-major,
+ * word 0 = row count of the group, word 1+j = value word of aggregate j
+ * (int64 for integer SUM / COUNT / integer MIN,MAX; double otherwise), and the
+ * packed group keys (n_groups x key_words 64-bit words).
+ */
+int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys,
+                      uint64_t *n_groups, uint32_t *words_per_group,
+                      uint32_t *key_words);
+/* Merge a partial state (device pointers on the state's device, same layout
+ * as qsgpu_agg_partial returns) into `state`. */
+int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states,
+                            const void *d_keys, uint64_t n_groups);
+/*
+ * finalizeAggregate: output relation gets one row per group: the group-by
+ * attributes in order, then one column per aggregate (SUM(int)->LONG,
+ * SUM(float/double)->DOUBLE, AVG->DOUBLE, COUNT->LONG, MIN/MAX->argument
+ * type).  `*out` is created by the call.  For an aggregate over zero rows
+ * (SQL NULL, AggregationHandleSum.cpp:134-143) the value is 0 and the
+ * matching bit of *null_mask (bit j = aggregate j, SINGLE_STATE only) is set.
+ */
+int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out,
+                       uint64_t *null_mask);
+int qsgpu_agg_destroy(qsgpu_agg_state_t state);
+
+/* --------------------------------------------------------------- hash join */
+/*
+ * K5/K6.  JoinHashTable (storage/HashTable.hpp:1284) keyed by one INT/LONG
+ * attribute, duplicates allowed.  The stored value is the build row id (the
+ * TupleReference of BuildHashOperator.cpp:48-61); projected build-side
+ * attributes are gathered through it at probe time.
+ */
+typedef struct qsgpu_join_table *qsgpu_join_table_t;
+enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };
+
+int qsgpu_join_create(int dev, uint32_t key_type /*QS_INT|QS_LONG*/,
+                      uint64_t estimated_num_entries, qsgpu_join_table_t *out);
+/* BuildHashWorkOrder::execute (BuildHashOperator.cpp:162-207): predicate ->
+ * LIP build -> put(key -> row id).  The build relation must outlive the table. */
+int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan,
+                     uint32_t key_attr, uint32_t n_lip_build,
+                     const qs_lip_ref *lip_build);
+int qsgpu_join_num_entries(qsgpu_join_table_t table, uint64_t *n);
+/*
+ * HashInnerJoinWorkOrder / Semi / Anti (HashJoinOperator.cpp:450-987): LIP
+ * probe -> hash probe -> residual predicate over both sides -> projection.
+ * In `exprs`, attribute nodes with b == 2 refer to the build relation.
+ * residual_root == -1: none.  Output rows are appended to `output`.
+ */
+int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe,
+                     uint32_t probe_key_attr, uint32_t join_type,
+                     int32_t residual_root, uint32_t n_project,
+                     const int32_t *project_roots, qsgpu_relation_t output);
+int qsgpu_join_destroy(qsgpu_join_table_t table);
+
+/* ----------------------------------------------------------------- top-k   */
+/* K9.  SortRunGeneration + SortMergeRun with LIMIT (§8f row 1): order rows of
+ * `input` by up to 4 sort attributes and keep the first `limit` rows. */
+typedef struct qs_sort_key { uint32_t attr; uint32_t descending; } qs_sort_key;
+int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
+               uint64_t limit, qsgpu_relation_t *out);
+
+/* ------------------------------------------------------- radix partition   */
+/*
+ * K8.  Partition rows of `input` by hash(key attr) mod n_parts into
+ * `output` (same schema, rows grouped by partition) and report the partition
+ * start offsets (n_parts + 1 entries, host).  The exchange that follows is an
+ * all-to-all over NVLink (PartitionAwareInsertDestination is the reference's
+ * repartitioning sink, storage/InsertDestination.cpp:471-722).
+ */
+int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr,
+                          uint32_t n_parts, qsgpu_relation_t output,
+                          uint64_t *host_offsets);
+
+/* ---------------------------------------------------------- instrumentation */
+/* CUDA-event time (ms) of the most recent kernel of the given family launched
+ * by the calling thread's last call, for bench.py's roofline block. */
+enum { QS_K_SCAN_AGG = 0, QS_K_SELECT = 1, QS_K_LIP = 2, QS_K_JOIN_BUILD = 3,
+       QS_K_JOIN_PROBE = 4, QS_K_GROUPBY = 5, QS_K_PARTITION = 6, QS_K_TOPK = 7,
+       QS_K_STAGE = 8, QS_K_FAMILIES = 9 };
+int qsgpu_set_timing(int enabled);
+int qsgpu_last_kernel_ms(uint32_t family, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* QSGPU_H_ */

@@ -1,0 +1,1124 @@
+// C-ABI of libqsgpu.so (include/qsgpu.h): runtime, device relations, staging
+// and the operator entry points.  Host code only; kernels live in k_*.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "qs_host.h"
+#include "qs_lower.h"
+
+namespace qs {
+
+static std::vector<Device> g_devices;
+static std::mutex g_mutex;
+static bool g_inited = false;
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<bool> g_timing{false};
+static thread_local std::string t_error;
+static thread_local float t_ms[QS_K_FAMILIES];
+
+void set_error(int status, const std::string &msg) {
+  char buf[32];
+  std::snprintf(buf, sizeof(buf), "[qsgpu %d] ", status);
+  t_error = std::string(buf) + msg;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error(QSGPU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? QSGPU_ERR_OOM : QSGPU_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
+bool timing_enabled() { return g_timing.load(); }
+void record_ms(uint32_t family, float ms) { if (family < QS_K_FAMILIES) t_ms[family] = ms; }
+
+Device *device(int dev) {
+  if (!g_inited) {
+    set_error(QSGPU_ERR_NO_DEVICE, "qsgpu_init has not been called (or found no CUDA device); there is no CPU fallback");
+    return nullptr;
+  }
+  for (auto &d : g_devices) if (d.id == dev) {
+    if (cudaSetDevice(dev) != cudaSuccess) { set_error(QSGPU_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    return &d;
+  }
+  set_error(QSGPU_ERR_INVALID, "device was not passed to qsgpu_init");
+  return nullptr;
+}
+
+// Times one kernel family with CUDA events on the launching stream.
+struct KernelTimer {
+  Device *d; uint32_t family; bool on;
+  KernelTimer(Device *dev, uint32_t fam) : d(dev), family(fam), on(timing_enabled()) {
+    if (on) cudaEventRecord(d->ev0, d->stream);
+  }
+  ~KernelTimer() {
+    if (!on) return;
+    cudaEventRecord(d->ev1, d->stream);
+    cudaEventSynchronize(d->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+    record_ms(family, ms);
+  }
+};
+
+// Picks ring depth, shared memory size and grid for a scan.
+int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
+  uint32_t stage = 0;
+  for (uint32_t c = 0; c < S->n_cols; ++c) {
+    S->cols[c].smem_off = stage;
+    stage += static_cast<uint32_t>(kTileRows) * S->cols[c].width;   // multiple of 16 by construction
+  }
+  stage = (stage + 127u) & ~127u;
+  if (stage == 0) stage = 128;
+  S->stage_bytes = stage;
+  const size_t fixed = kBarBytes + extra_smem + 256;
+  const size_t per_sm = d->smem_per_sm;                     // 228 KB on B200
+  const size_t per_block_max = d->smem_per_block_optin;     // 227 KB
+  // two CTAs per SM when two stages of each fit, else one
+  int ctas = 2;
+  size_t budget = per_sm / 2 - 1024;                        // 1 KB per CTA is reserved by the driver
+  if (fixed + 2ull * stage > budget) { ctas = 1; budget = per_block_max; }
+  if (fixed + 2ull * stage > budget) {
+    set_error(QSGPU_ERR_UNSUPPORTED, "scan references too many bytes per row for the shared-memory tile ring");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  uint32_t n_stages = static_cast<uint32_t>((budget - fixed) / stage);
+  if (n_stages > static_cast<uint32_t>(kMaxStages)) n_stages = kMaxStages;
+  S->n_stages = n_stages;
+  plan->smem = kBarBytes + static_cast<size_t>(n_stages) * stage + extra_smem + 64;
+  int grid = d->sm_count * ctas;
+  if (S->d_row_end == nullptr && S->n_tiles < static_cast<uint32_t>(grid)) grid = std::max<int>(1, S->n_tiles);
+  plan->grid = grid;
+  return QSGPU_OK;
+}
+
+static int check_device_error(Device *d) {
+  uint32_t flag = 0;
+  QS_CUDA(cudaMemcpyAsync(&flag, d->d_error, 4, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  if (flag != 0) {
+    uint32_t zero = 0;
+    cudaMemcpyAsync(d->d_error, &zero, 4, cudaMemcpyHostToDevice, d->stream);
+    set_error(static_cast<int>(flag), "a kernel reported a capacity overflow (hash table, group limit or output relation too small)");
+    return static_cast<int>(flag);
+  }
+  return QSGPU_OK;
+}
+
+static int sync_rows(qsgpu_relation *rel) {
+  if (!rel->dirty) return QSGPU_OK;
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  unsigned long long n = 0;
+  QS_CUDA(cudaMemcpyAsync(&n, rel->d_rows, 8, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  int st = check_device_error(d);
+  if (st) return st;
+  rel->host_rows = std::min<uint64_t>(n, rel->capacity);
+  rel->dirty = false;
+  return QSGPU_OK;
+}
+
+// Fills the row extent + staged columns of a ScanDesc from a lowering.
+static int fill_scan(const qsgpu_relation *rel, uint64_t row_begin, uint64_t row_end, const Lowering &L,
+                     ScanDesc *S) {
+  std::memset(S, 0, sizeof(*S));
+  uint64_t limit = rel->dirty ? rel->capacity : rel->host_rows;
+  if (row_end > limit) row_end = limit;
+  if (row_begin > row_end) row_begin = row_end;
+  S->row_begin = row_begin;
+  S->row_end = row_end;
+  S->first_row = row_begin & ~15ull;
+  S->d_row_end = rel->dirty ? rel->d_rows : nullptr;
+  const uint64_t span = row_end - S->first_row;
+  S->n_tiles = static_cast<uint32_t>((span + kTileRows - 1) / kTileRows);
+  S->n_cols = static_cast<uint32_t>(L.staged_attrs.size());
+  for (uint32_t c = 0; c < S->n_cols; ++c) {
+    const uint32_t a = L.staged_attrs[c];
+    S->cols[c].ptr = rel->cols[a];
+    S->cols[c].width = rel->attrs[a].width;
+  }
+  return QSGPU_OK;
+}
+
+static int fill_lips(uint32_t n, const qs_lip_ref *refs, const qsgpu_relation *rel, int dev, ScanDesc *S) {
+  if (n > static_cast<uint32_t>(kMaxLip)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxLip LIP filters on one scan"); return QSGPU_ERR_UNSUPPORTED; }
+  S->n_lip = n;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!refs[i].lip || refs[i].lip->dev != dev) { set_error(QSGPU_ERR_INVALID, "LIP filter missing or on another device"); return QSGPU_ERR_INVALID; }
+    S->lip[i] = refs[i].lip->d;
+  }
+  (void)rel;
+  return QSGPU_OK;
+}
+
+static uint16_t attr_width(uint16_t type, uint16_t width) {
+  switch (type) {
+    case QS_INT: case QS_FLOAT: return 4;
+    case QS_LONG: case QS_DOUBLE: case QS_DATE: return 8;
+    default: return width;
+  }
+}
+
+static size_t padded_bytes(uint64_t rows, uint32_t width) {
+  return ((rows * width + 255) & ~static_cast<uint64_t>(255)) + 256;   // 16+ readable bytes past the end
+}
+
+}  // namespace qs
+
+using namespace qs;
+
+extern "C" {
+
+const char *qsgpu_last_error(void) { return t_error.c_str(); }
+
+int qsgpu_init(int n_dev, const int *dev_ids) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  if (g_inited) return QSGPU_OK;
+  int visible = 0;
+  cudaError_t e = cudaGetDeviceCount(&visible);
+  if (e != cudaSuccess || visible == 0) {
+    cudaGetLastError();
+    set_error(QSGPU_ERR_NO_DEVICE, "no CUDA device visible; libqsgpu has no CPU fallback");
+    return QSGPU_ERR_NO_DEVICE;
+  }
+  std::vector<int> ids;
+  if (n_dev <= 0) for (int i = 0; i < visible; ++i) ids.push_back(i);
+  else for (int i = 0; i < n_dev; ++i) ids.push_back(dev_ids ? dev_ids[i] : i);
+  for (int id : ids) {
+    if (id < 0 || id >= visible) { set_error(QSGPU_ERR_INVALID, "device id out of range"); return QSGPU_ERR_INVALID; }
+    Device d;
+    d.id = id;
+    QS_CUDA(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    QS_CUDA(cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10) {
+      set_error(QSGPU_ERR_NO_DEVICE, "libqsgpu is built for sm_100a (B200) only");
+      return QSGPU_ERR_NO_DEVICE;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    d.smem_per_sm = prop.sharedMemPerMultiprocessor;
+    d.smem_per_block_optin = prop.sharedMemPerBlockOptin;
+    QS_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    QS_CUDA(cudaMalloc(&d.d_error, 256));
+    QS_CUDA(cudaMemset(d.d_error, 0, 256));
+    QS_CUDA(cudaEventCreate(&d.ev0));
+    QS_CUDA(cudaEventCreate(&d.ev1));
+    g_devices.push_back(d);
+  }
+  g_inited = true;
+  return QSGPU_OK;
+}
+
+int qsgpu_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  for (auto &d : g_devices) {
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    cudaFree(d.d_error);
+    cudaEventDestroy(d.ev0);
+    cudaEventDestroy(d.ev1);
+    cudaStreamDestroy(d.stream);
+  }
+  g_devices.clear();
+  g_inited = false;
+  return QSGPU_OK;
+}
+
+int qsgpu_device_count(int *n_dev) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *n_dev = n;
+  return QSGPU_OK;
+}
+
+int qsgpu_synchronize(int dev) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return check_device_error(d);
+}
+
+int qsgpu_launch_count(uint64_t *n) { *n = g_launches.load(); return QSGPU_OK; }
+
+int qsgpu_set_timing(int enabled) { g_timing.store(enabled != 0); return QSGPU_OK; }
+int qsgpu_last_kernel_ms(uint32_t family, float *ms) {
+  if (family >= QS_K_FAMILIES) { set_error(QSGPU_ERR_INVALID, "bad kernel family"); return QSGPU_ERR_INVALID; }
+  *ms = t_ms[family];
+  return QSGPU_OK;
+}
+
+int qsgpu_malloc(int dev, size_t bytes, void **dptr) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaMalloc(dptr, bytes ? bytes : 256));
+  return QSGPU_OK;
+}
+int qsgpu_free(int dev, void *dptr) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  QS_CUDA(cudaFree(dptr));
+  return QSGPU_OK;
+}
+int qsgpu_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return QSGPU_OK;
+}
+int qsgpu_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return QSGPU_OK;
+}
+int qsgpu_host_alloc(size_t bytes, void **hptr) {
+  if (!g_inited) { set_error(QSGPU_ERR_NO_DEVICE, "qsgpu_init has not been called"); return QSGPU_ERR_NO_DEVICE; }
+  QS_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocPortable));
+  return QSGPU_OK;
+}
+int qsgpu_host_free(void *hptr) {
+  QS_CUDA(cudaFreeHost(hptr));
+  return QSGPU_OK;
+}
+
+/* ------------------------------------------------------------- relations */
+static int relation_new(int dev, uint32_t n_attrs, const qs_attr *attrs, qsgpu_relation **out) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (n_attrs == 0 || !attrs) { set_error(QSGPU_ERR_INVALID, "relation needs at least one attribute"); return QSGPU_ERR_INVALID; }
+  std::unique_ptr<qsgpu_relation> r(new qsgpu_relation);
+  r->dev = dev;
+  for (uint32_t i = 0; i < n_attrs; ++i) {
+    qs_attr a = attrs[i];
+    if (a.type == QS_VARCHAR || a.type > QS_DATE) { set_error(QSGPU_ERR_UNSUPPORTED, "VARCHAR / non fixed-width attributes are not staged on the device"); return QSGPU_ERR_UNSUPPORTED; }
+    a.width = attr_width(a.type, a.width);
+    if (a.width == 0) { set_error(QSGPU_ERR_INVALID, "zero-width attribute"); return QSGPU_ERR_INVALID; }
+    r->attrs.push_back(a);
+  }
+  QS_CUDA(cudaMalloc(&r->d_rows, 256));
+  QS_CUDA(cudaMemsetAsync(r->d_rows, 0, 256, d->stream));
+  *out = r.release();
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_create(int dev, uint32_t n_attrs, const qs_attr *attrs, uint64_t capacity_rows,
+                          qsgpu_relation_t *out) {
+  qsgpu_relation *r = nullptr;
+  int st = relation_new(dev, n_attrs, attrs, &r);
+  if (st) return st;
+  r->capacity = capacity_rows;
+  r->owns_memory = true;
+  for (auto &a : r->attrs) {
+    char *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, padded_bytes(capacity_rows, a.width));
+    if (e != cudaSuccess) { qsgpu_relation_destroy(r); return cuda_fail(e, "cudaMalloc(relation column)"); }
+    r->cols.push_back(p);
+  }
+  *out = r;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs, void *const *dptrs, uint64_t n_rows,
+                        qsgpu_relation_t *out) {
+  qsgpu_relation *r = nullptr;
+  int st = relation_new(dev, n_attrs, attrs, &r);
+  if (st) return st;
+  r->capacity = n_rows;
+  r->host_rows = n_rows;
+  r->owns_memory = false;
+  for (uint32_t i = 0; i < n_attrs; ++i) {
+    if ((reinterpret_cast<uintptr_t>(dptrs[i]) & 15) != 0) {
+      qsgpu_relation_destroy(r);
+      set_error(QSGPU_ERR_INVALID, "wrapped column is not 16-byte aligned");
+      return QSGPU_ERR_INVALID;
+    }
+    r->cols.push_back(static_cast<char *>(dptrs[i]));
+  }
+  Device *d = device(dev);
+  unsigned long long n = n_rows;
+  QS_CUDA(cudaMemcpyAsync(r->d_rows, &n, 8, cudaMemcpyHostToDevice, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  *out = r;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_destroy(qsgpu_relation_t rel) {
+  if (!rel) return QSGPU_OK;
+  Device *d = device(rel->dev);
+  if (d) cudaStreamSynchronize(d->stream);
+  if (rel->owns_memory) for (char *p : rel->cols) cudaFree(p);
+  cudaFree(rel->d_rows);
+  delete rel;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_num_rows(qsgpu_relation_t rel, uint64_t *n_rows) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  *n_rows = rel->host_rows;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_set_num_rows(qsgpu_relation_t rel, uint64_t n_rows) {
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (n_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "row count above relation capacity"); return QSGPU_ERR_CAPACITY; }
+  unsigned long long n = n_rows;
+  QS_CUDA(cudaMemcpyAsync(rel->d_rows, &n, 8, cudaMemcpyHostToDevice, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  rel->host_rows = n_rows;
+  rel->dirty = false;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_column(qsgpu_relation_t rel, uint32_t attr, void **dptr) {
+  if (attr >= rel->cols.size()) { set_error(QSGPU_ERR_INVALID, "attribute id out of range"); return QSGPU_ERR_INVALID; }
+  *dptr = rel->cols[attr];
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin, uint64_t n_rows,
+                        void *host_out) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  if (attr >= rel->cols.size() || row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
+  Device *d = device(rel->dev);
+  const uint32_t w = rel->attrs[attr].width;
+  QS_CUDA(cudaMemcpyAsync(host_out, rel->cols[attr] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return QSGPU_OK;
+}
+
+int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc *descs, uint32_t n_desc) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (!rel->owns_memory) { set_error(QSGPU_ERR_INVALID, "cannot stage into a wrapped relation"); return QSGPU_ERR_INVALID; }
+  if (rel->host_rows + n_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "relation capacity exceeded while staging"); return QSGPU_ERR_CAPACITY; }
+  if (n_desc != rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "qsgpu_stage_block must stage every attribute of the relation"); return QSGPU_ERR_INVALID; }
+  KernelTimer timer(d, QS_K_STAGE);
+  std::vector<void *> scratch;
+  int rc = QSGPU_OK;
+  for (uint32_t i = 0; i < n_desc && rc == QSGPU_OK; ++i) {
+    const qs_stage_desc &s = descs[i];
+    if (s.attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "stage: attribute out of range"); rc = QSGPU_ERR_INVALID; break; }
+    const uint32_t w = rel->attrs[s.attr].width;
+    char *dst = rel->cols[s.attr] + rel->host_rows * w;
+    cudaError_t e = cudaSuccess;
+    switch (s.encoding) {
+      case QS_ENC_PLAIN:
+        e = cudaMemcpyAsync(dst, s.host, n_rows * w, cudaMemcpyHostToDevice, d->stream);
+        break;
+      case QS_ENC_STRIDED: {
+        void *tmp = nullptr;
+        const size_t bytes = n_rows ? (n_rows - 1) * s.stride + w : 0;
+        e = cudaMalloc(&tmp, bytes + 16);
+        if (e == cudaSuccess) { scratch.push_back(tmp); e = cudaMemcpyAsync(tmp, s.host, bytes, cudaMemcpyHostToDevice, d->stream); }
+        if (e == cudaSuccess) { e = launch_decode_strided(dst, tmp, n_rows, s.stride, w, d->stream); count_launch(); }
+        break;
+      }
+      case QS_ENC_DICT: {
+        if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; break; }
+        void *codes = nullptr, *dict = nullptr;
+        e = cudaMalloc(&codes, n_rows * s.code_width + 16);
+        if (e == cudaSuccess) { scratch.push_back(codes); e = cudaMalloc(&dict, static_cast<size_t>(s.dict_entries) * w + 16); }
+        if (e == cudaSuccess) { scratch.push_back(dict); e = cudaMemcpyAsync(codes, s.host, n_rows * s.code_width, cudaMemcpyHostToDevice, d->stream); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dict, s.dict, static_cast<size_t>(s.dict_entries) * w, cudaMemcpyHostToDevice, d->stream);
+        if (e == cudaSuccess) { e = launch_decode_dict(dst, codes, dict, n_rows, s.code_width, w, s.dict_entries, d->stream); count_launch(); }
+        break;
+      }
+      case QS_ENC_TRUNCATED: {
+        if ((w != 4 && w != 8) || (s.code_width != 1 && s.code_width != 2 && s.code_width != 4)) { set_error(QSGPU_ERR_INVALID, "truncation applies to INT/LONG with 1/2/4-byte codes"); rc = QSGPU_ERR_INVALID; break; }
+        void *codes = nullptr;
+        e = cudaMalloc(&codes, n_rows * s.code_width + 16);
+        if (e == cudaSuccess) { scratch.push_back(codes); e = cudaMemcpyAsync(codes, s.host, n_rows * s.code_width, cudaMemcpyHostToDevice, d->stream); }
+        if (e == cudaSuccess) { e = launch_decode_truncated(dst, codes, n_rows, s.code_width, w, d->stream); count_launch(); }
+        break;
+      }
+      default:
+        set_error(QSGPU_ERR_INVALID, "unknown staging encoding");
+        rc = QSGPU_ERR_INVALID;
+    }
+    if (rc == QSGPU_OK && e != cudaSuccess) rc = cuda_fail(e, "qsgpu_stage_block");
+  }
+  cudaStreamSynchronize(d->stream);     // host stripes may be unpinned / reused by the caller
+  for (void *p : scratch) cudaFree(p);
+  if (rc != QSGPU_OK) return rc;
+  return qsgpu_relation_set_num_rows(rel, rel->host_rows + n_rows);
+}
+
+/* ------------------------------------------------------------ LIP filters */
+int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type, int64_t min_value, int64_t max_value,
+                     uint64_t cardinality, int is_anti, qsgpu_lip_t *out) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (attr_type != QS_INT && attr_type != QS_LONG) { set_error(QSGPU_ERR_UNSUPPORTED, "LIP filters are defined over INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  uint64_t bits;
+  if (kind == QS_LIP_BITVECTOR_EXACT) {
+    if (max_value < min_value) { set_error(QSGPU_ERR_INVALID, "exact filter needs max >= min"); return QSGPU_ERR_INVALID; }
+    bits = static_cast<uint64_t>(max_value - min_value) + 1;
+  } else if (kind == QS_LIP_SINGLE_IDENTITY_HASH) {
+    if (cardinality == 0) { set_error(QSGPU_ERR_INVALID, "hash filter needs cardinality >= 1"); return QSGPU_ERR_INVALID; }
+    bits = cardinality;
+  } else { set_error(QSGPU_ERR_INVALID, "unknown LIP filter kind"); return QSGPU_ERR_INVALID; }
+  std::unique_ptr<qsgpu_lip> f(new qsgpu_lip);
+  f->dev = dev;
+  f->attr_type = attr_type;
+  f->n_words = (bits + 63) / 64;
+  f->d.kind = kind;
+  f->d.min_value = min_value;
+  f->d.max_value = max_value;
+  f->d.cardinality = cardinality;
+  f->d.is_anti = is_anti ? 1 : 0;
+  QS_CUDA(cudaMalloc(&f->d.words, f->n_words * 8 + 64));
+  QS_CUDA(cudaMemsetAsync(f->d.words, 0, f->n_words * 8 + 64, d->stream));
+  *out = f.release();
+  return QSGPU_OK;
+}
+int qsgpu_lip_destroy(qsgpu_lip_t lip) {
+  if (!lip) return QSGPU_OK;
+  Device *d = device(lip->dev);
+  if (d) cudaStreamSynchronize(d->stream);
+  cudaFree(lip->d.words);
+  delete lip;
+  return QSGPU_OK;
+}
+int qsgpu_lip_num_words(qsgpu_lip_t lip, uint64_t *n_words) { *n_words = lip->n_words; return QSGPU_OK; }
+int qsgpu_lip_read(qsgpu_lip_t lip, uint64_t *host_words) {
+  return qsgpu_memcpy_d2h(lip->dev, host_words, lip->d.words, lip->n_words * 8);
+}
+int qsgpu_lip_device_words(qsgpu_lip_t lip, void **dptr) { *dptr = lip->d.words; return QSGPU_OK; }
+
+/* --------------------------------------------- shared scan-side lowering */
+static int lower_scan_predicate(Lowering &L, const qs_scan *scan) {
+  bool have = false;
+  if (scan->predicate_root >= 0) { L.lower_pred(scan->predicate_root); have = true; }
+  for (uint32_t i = 0; i < scan->n_lip_probe; ++i) {
+    L.lower_lip_probe(i, scan->lip_probe[i].attr, have);
+    have = true;
+  }
+  L.mark_pred_end();
+  if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  return QSGPU_OK;
+}
+
+static int fill_lip_build(uint32_t n, const qs_lip_ref *refs, Lowering &L, const qsgpu_relation *rel, SinkDesc *K) {
+  if (n > static_cast<uint32_t>(kMaxLip)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxLip LIP filters built by one scan"); return QSGPU_ERR_UNSUPPORTED; }
+  K->n_lip_build = n;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!refs[i].lip || refs[i].lip->dev != rel->dev || refs[i].attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "bad LIP build reference"); return QSGPU_ERR_INVALID; }
+    const uint8_t lt = vtype_of(rel->attrs[refs[i].attr].type);
+    if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "LIP filters take INT/LONG attributes"); return QSGPU_ERR_UNSUPPORTED; }
+    K->lip_build[i] = refs[i].lip->d;
+    K->lip_build_col[i] = static_cast<uint16_t>(L.stage_attr(refs[i].attr));
+    K->lip_build_ltype[i] = lt;
+  }
+  if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  return QSGPU_OK;
+}
+
+// Lowers the projection list; an attribute root is a raw pass-through copy.
+static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *roots, qsgpu_relation *output, SinkDesc *K) {
+  if (n_project > static_cast<uint32_t>(kMaxOut)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxOut projected columns"); return QSGPU_ERR_UNSUPPORTED; }
+  if (n_project != output->attrs.size()) { set_error(QSGPU_ERR_INVALID, "projection list does not match the output relation"); return QSGPU_ERR_INVALID; }
+  K->n_out = n_project;
+  for (uint32_t j = 0; j < n_project; ++j) {
+    const qs_node *n = L.node(roots[j]);
+    if (!n) break;
+    K->out[j] = output->cols[j];
+    K->out_width[j] = static_cast<uint8_t>(output->attrs[j].width);
+    if (n->kind == QS_N_ATTRIBUTE) {
+      const qsgpu_relation *src = n->b == 2 ? L.build_rel : L.rel;
+      if (!src || static_cast<uint32_t>(n->a) >= src->attrs.size() ||
+          src->attrs[n->a].width != output->attrs[j].width) { set_error(QSGPU_ERR_INVALID, "projected attribute does not match the output column width"); return QSGPU_ERR_INVALID; }
+      Instr in{};
+      in.arg = static_cast<uint16_t>(j);
+      if (n->b == 2) { in.op = OP_EMIT_RAW_BUILD; in.flags = static_cast<uint8_t>(L.build_attr(static_cast<uint32_t>(n->a))); }
+      else { in.op = OP_EMIT_RAW; in.flags = static_cast<uint8_t>(L.stage_attr(static_cast<uint32_t>(n->a))); }
+      L.push(in);
+    } else {
+      const uint8_t t = L.lower_scalar(roots[j]);
+      uint8_t to = vtype_of(output->attrs[j].type);
+      if (to == 0xff || to == V_DATE) { set_error(QSGPU_ERR_INVALID, "expression projected into a CHAR/DATE column"); return QSGPU_ERR_INVALID; }
+      L.lower_cast_acc(t, to);
+      Instr in{};
+      in.op = OP_EMIT; in.type = to; in.arg = static_cast<uint16_t>(j);
+      L.push(in);
+    }
+  }
+  L.finish();
+  if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  return QSGPU_OK;
+}
+
+int qsgpu_build_lip_filter(const qs_scan *scan, uint32_t n_build, const qs_lip_ref *build) {
+  qsgpu_relation *rel = scan->input;
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  Lowering L(scan->exprs, rel);
+  int st = lower_scan_predicate(L, scan);
+  if (st) return st;
+  SinkDesc K{};
+  K.error_flag = d->d_error;
+  st = fill_lip_build(n_build, build, L, rel, &K);
+  if (st) return st;
+  L.finish();
+  ScanDesc S;
+  fill_scan(rel, scan->row_begin, scan->row_end, L, &S);
+  st = fill_lips(scan->n_lip_probe, scan->lip_probe, rel, rel->dev, &S);
+  if (st) return st;
+  ScanPlan plan;
+  st = plan_scan(d, &S, kCompactSmemBytes, &plan);
+  if (st) return st;
+  KernelTimer timer(d, QS_K_LIP);
+  QS_CUDA(launch_scan_select(S, L.P, K, plan.grid, plan.smem, d->stream));
+  count_launch();
+  return QSGPU_OK;
+}
+
+int qsgpu_select(const qs_scan *scan, uint32_t n_project, const int32_t *project_roots, qsgpu_relation_t output) {
+  qsgpu_relation *rel = scan->input;
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (output->dev != rel->dev) { set_error(QSGPU_ERR_INVALID, "output relation on another device"); return QSGPU_ERR_INVALID; }
+  Lowering L(scan->exprs, rel);
+  int st = lower_scan_predicate(L, scan);
+  if (st) return st;
+  SinkDesc K{};
+  K.error_flag = d->d_error;
+  K.capacity = output->capacity;
+  K.counter = output->d_rows;
+  st = lower_projection(L, n_project, project_roots, output, &K);
+  if (st) return st;
+  ScanDesc S;
+  fill_scan(rel, scan->row_begin, scan->row_end, L, &S);
+  st = fill_lips(scan->n_lip_probe, scan->lip_probe, rel, rel->dev, &S);
+  if (st) return st;
+  ScanPlan plan;
+  st = plan_scan(d, &S, kCompactSmemBytes, &plan);
+  if (st) return st;
+  KernelTimer timer(d, QS_K_SELECT);
+  QS_CUDA(launch_scan_select(S, L.P, K, plan.grid, plan.smem, d->stream));
+  count_launch();
+  output->dirty = true;
+  return QSGPU_OK;
+}
+
+/* ------------------------------------------------------------- aggregation */
+static bool is_fp(uint8_t v) { return v == V_F32 || v == V_F64; }
+
+int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
+  Device *d = device(spec->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  std::unique_ptr<qsgpu_agg_state> s(new qsgpu_agg_state);
+  s->dev = spec->dev;
+  s->strategy = spec->strategy;
+  if (spec->exprs) {
+    s->nodes.assign(spec->exprs->nodes, spec->exprs->nodes + spec->exprs->n_nodes);
+    s->str_pool.assign(spec->exprs->str_pool ? spec->exprs->str_pool : "", spec->exprs->str_pool ? spec->exprs->str_pool_bytes : 0);
+  }
+  s->exprs.nodes = s->nodes.data();
+  s->exprs.n_nodes = static_cast<uint32_t>(s->nodes.size());
+  s->exprs.str_pool = s->str_pool.data();
+  s->exprs.str_pool_bytes = static_cast<uint32_t>(s->str_pool.size());
+  s->predicate_root = spec->predicate_root;
+  s->aggregates.assign(spec->aggregates, spec->aggregates + spec->n_aggregates);
+  s->group_by_roots.assign(spec->group_by_roots, spec->group_by_roots + spec->n_group_by);
+  s->estimated = spec->estimated_num_entries;
+  if (spec->n_aggregates > static_cast<uint32_t>(kMaxOut)) { set_error(QSGPU_ERR_UNSUPPORTED, "too many aggregates"); return QSGPU_ERR_UNSUPPORTED; }
+
+  AggDesc &A = s->A;
+  A.strategy = spec->strategy;
+  A.error_flag = d->d_error;
+  // ---- value words: one per SUM/AVG/MIN/MAX, COUNT reads the row-count word
+  Lowering typer(&s->exprs, nullptr);
+  uint32_t n_agg = 0;
+  for (const qs_aggregate &a : s->aggregates) {
+    if (a.function == QS_AGG_COUNT) { s->value_word.push_back(0); s->arg_vtype.push_back(V_I64); continue; }
+    if (a.argument_root < 0) { set_error(QSGPU_ERR_INVALID, "aggregate without an argument"); return QSGPU_ERR_INVALID; }
+    if (n_agg >= static_cast<uint32_t>(kMaxAgg)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxAgg value aggregates in one state"); return QSGPU_ERR_UNSUPPORTED; }
+    const qs_node &root = s->nodes[a.argument_root];
+    uint8_t vt = typer.scalar_vtype(a.argument_root);
+    if (!typer.ok()) { set_error(typer.status, typer.err); return typer.status; }
+    if ((root.kind == QS_N_ATTRIBUTE || root.kind == QS_N_LITERAL) && root.type == QS_DATE) { set_error(QSGPU_ERR_UNSUPPORTED, "MIN/MAX over DATE is not lowered"); return QSGPU_ERR_UNSUPPORTED; }
+    uint8_t own = vt;
+    if (root.kind == QS_N_ATTRIBUTE || root.kind == QS_N_LITERAL) own = vtype_of(root.type);
+    uint8_t kind;
+    switch (a.function) {
+      case QS_AGG_SUM: case QS_AGG_AVG: kind = is_fp(vt) ? AK_SUM_F64 : AK_SUM_I64; break;
+      case QS_AGG_MIN: kind = is_fp(vt) ? AK_MIN_F64 : AK_MIN_I64; break;
+      case QS_AGG_MAX: kind = is_fp(vt) ? AK_MAX_F64 : AK_MAX_I64; break;
+      default: set_error(QSGPU_ERR_INVALID, "unknown aggregate function"); return QSGPU_ERR_INVALID;
+    }
+    A.kind[n_agg] = kind;
+    s->value_word.push_back(static_cast<int>(1 + n_agg));
+    s->arg_vtype.push_back(own);
+    ++n_agg;
+  }
+  A.n_agg = n_agg;
+  A.words = n_agg + 1;
+  // ---- group-by keys (attribute nodes)
+  uint32_t key_bytes = 0;
+  A.n_key_cols = static_cast<uint32_t>(s->group_by_roots.size());
+  if (A.n_key_cols > static_cast<uint32_t>(kMaxKeyCols)) { set_error(QSGPU_ERR_UNSUPPORTED, "too many group-by attributes"); return QSGPU_ERR_UNSUPPORTED; }
+  for (uint32_t k = 0; k < A.n_key_cols; ++k) {
+    const int32_t r = s->group_by_roots[k];
+    if (r < 0 || static_cast<size_t>(r) >= s->nodes.size() || s->nodes[r].kind != QS_N_ATTRIBUTE) { set_error(QSGPU_ERR_UNSUPPORTED, "group-by expressions must be attributes"); return QSGPU_ERR_UNSUPPORTED; }
+    qs_attr ka{s->nodes[r].type, attr_width(s->nodes[r].type, s->nodes[r].width)};
+    s->key_attrs.push_back(ka);
+    s->key_attr_ids.push_back(static_cast<uint32_t>(s->nodes[r].a));
+    A.key_width[k] = static_cast<uint8_t>(ka.width);
+    A.key_off[k] = static_cast<uint8_t>(key_bytes);
+    key_bytes += ka.width;
+  }
+  A.key_words = std::max<uint32_t>(1, (key_bytes + 7) / 8);
+
+  switch (spec->strategy) {
+    case QS_AGG_SINGLE_STATE:
+      if (A.n_key_cols != 0) { set_error(QSGPU_ERR_INVALID, "SINGLE_STATE with GROUP BY"); return QSGPU_ERR_INVALID; }
+      A.partial_rows = 1;
+      break;
+    case QS_AGG_COMPACT_KEY:
+      // ThreadPrivateCompactKeyHashTable: keys fit one 64-bit code (…CompactKeyHashTable.hpp:113-116)
+      if (A.n_key_cols == 0 || key_bytes > 8) { set_error(QSGPU_ERR_INVALID, "COMPACT_KEY needs 1..8 key bytes"); return QSGPU_ERR_INVALID; }
+      A.partial_rows = kCompactMaxGroups;
+      break;
+    case QS_AGG_SEPARATE_CHAINING:
+      if (A.n_key_cols == 0 || key_bytes > 8u * kMaxKeyWords) { set_error(QSGPU_ERR_UNSUPPORTED, "group-by key wider than 32 bytes"); return QSGPU_ERR_UNSUPPORTED; }
+      break;
+    case QS_AGG_COLLISION_FREE:
+      if (A.n_key_cols != 1 || (s->key_attrs[0].type != QS_INT && s->key_attrs[0].type != QS_LONG) || spec->collision_free_max_key < 0) {
+        set_error(QSGPU_ERR_INVALID, "COLLISION_FREE needs one INT/LONG key and a non-negative max key");
+        return QSGPU_ERR_INVALID;
+      }
+      for (const qs_aggregate &a : s->aggregates)
+        if (a.function != QS_AGG_SUM && a.function != QS_AGG_COUNT && a.function != QS_AGG_AVG) {
+          // reference restricts this table to COUNT/SUM (StarSchemaSimpleCostModel.cpp:614-709)
+          set_error(QSGPU_ERR_INVALID, "COLLISION_FREE supports COUNT/SUM/AVG only");
+          return QSGPU_ERR_INVALID;
+        }
+      break;
+    default: set_error(QSGPU_ERR_INVALID, "unknown aggregation strategy"); return QSGPU_ERR_INVALID;
+  }
+
+  QS_CUDA(cudaMalloc(&A.n_groups, 256));
+  QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 256, d->stream));
+  QS_CUDA(cudaMalloc(&s->d_done, 256));
+  QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
+  QS_CUDA(cudaMalloc(&s->d_idx_count, 256));
+  if (spec->strategy == QS_AGG_SINGLE_STATE || spec->strategy == QS_AGG_COMPACT_KEY) {
+    s->max_ctas = static_cast<uint32_t>(d->sm_count) * 2;
+    const size_t prow = static_cast<size_t>(A.partial_rows) * A.words * 8;
+    QS_CUDA(cudaMalloc(&A.partials, prow * s->max_ctas));
+    A.dir_cap = 1024;
+    QS_CUDA(cudaMalloc(&A.dir_keys, A.dir_cap * 8));
+    QS_CUDA(cudaMalloc(&A.dir_gid, A.dir_cap * 4));
+    QS_CUDA(cudaMemsetAsync(A.dir_gid, 0xff, A.dir_cap * 4, d->stream));
+    QS_CUDA(cudaMalloc(&A.gid_keys, kCompactMaxGroups * 8));
+    QS_CUDA(cudaMemsetAsync(A.gid_keys, 0, kCompactMaxGroups * 8, d->stream));
+    QS_CUDA(cudaMalloc(&A.states, prow));
+    A.cap = A.partial_rows;
+    QS_CUDA(launch_fill_identity(A.states, A.partial_rows, A, d->stream));
+    count_launch();
+  } else {
+    if (spec->strategy == QS_AGG_COLLISION_FREE) A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
+    else {
+      uint64_t want = std::max<uint64_t>(1024, spec->estimated_num_entries * 2);
+      uint64_t cap = 1024;
+      while (cap < want) cap <<= 1;
+      A.cap = cap;
+      QS_CUDA(cudaMalloc(&A.tags, cap * 4));
+      QS_CUDA(cudaMemsetAsync(A.tags, 0, cap * 4, d->stream));
+      QS_CUDA(cudaMalloc(&A.keys, cap * A.key_words * 8));
+    }
+    QS_CUDA(cudaMalloc(&A.states, A.cap * A.words * 8));
+    QS_CUDA(launch_fill_identity(A.states, A.cap, A, d->stream));
+    count_launch();
+  }
+  *out = s.release();
+  return QSGPU_OK;
+}
+
+// Grows a SEPARATE_CHAINING table so that `extra` more groups certainly fit
+// (the reference resizes PackedPayloadHashTable under an exclusive lock,
+// storage/PackedPayloadHashTable.hpp:856; here growth happens between work
+// orders, never inside a kernel).
+static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
+  AggDesc &A = s->A;
+  uint32_t n = 0;
+  QS_CUDA(cudaMemcpyAsync(&n, A.n_groups, 4, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  // worst case every row opens a group, but never plan for more than 8x the optimizer's estimate at once
+  uint64_t worst = n + std::min<uint64_t>(extra_rows, std::max<uint64_t>(8 * s->estimated, 1u << 20));
+  if (worst * 3 / 2 <= A.cap) return QSGPU_OK;
+  uint64_t cap = A.cap;
+  while (cap < worst * 2) cap <<= 1;
+  AggDesc B = A;
+  B.cap = cap;
+  QS_CUDA(cudaMalloc(&B.tags, cap * 4));
+  QS_CUDA(cudaMemsetAsync(B.tags, 0, cap * 4, d->stream));
+  QS_CUDA(cudaMalloc(&B.keys, cap * A.key_words * 8));
+  QS_CUDA(cudaMalloc(&B.states, cap * A.words * 8));
+  QS_CUDA(launch_fill_identity(B.states, cap, B, d->stream));
+  QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 4, d->stream));
+  QS_CUDA(launch_rehash(A, B, d->stream));
+  count_launch(2);
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  cudaFree(A.tags); cudaFree(A.keys); cudaFree(A.states);
+  A = B;
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_begin, uint64_t row_end,
+                  uint32_t n_lip_probe, const qs_lip_ref *lip_probe) {
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (input->dev != state->dev) { set_error(QSGPU_ERR_INVALID, "input relation on another device"); return QSGPU_ERR_INVALID; }
+  qs_scan scan{};
+  scan.input = input;
+  scan.exprs = &state->exprs;
+  scan.predicate_root = state->predicate_root;
+  scan.n_lip_probe = n_lip_probe;
+  scan.lip_probe = lip_probe;
+  Lowering L(&state->exprs, input);
+  int st = lower_scan_predicate(L, &scan);
+  if (st) return st;
+  AggDesc A = state->A;
+  for (uint32_t k = 0; k < A.n_key_cols; ++k) {
+    const uint32_t attr = state->key_attr_ids[k];
+    if (attr >= input->attrs.size() || input->attrs[attr].width != A.key_width[k]) { set_error(QSGPU_ERR_INVALID, "group-by attribute does not match the input relation"); return QSGPU_ERR_INVALID; }
+    A.key_col[k] = static_cast<uint16_t>(L.stage_attr(attr));
+  }
+  for (size_t i = 0; i < state->aggregates.size(); ++i) {
+    const int w = state->value_word[i];
+    if (w == 0) continue;
+    const uint8_t t = L.lower_scalar(state->aggregates[i].argument_root);
+    const uint8_t kind = A.kind[w - 1];
+    const uint8_t to = (kind == AK_SUM_F64 || kind == AK_MIN_F64 || kind == AK_MAX_F64) ? V_F64 : V_I64;
+    L.lower_cast_acc(t, to);
+    Instr in{};
+    in.op = OP_EMIT; in.type = to; in.arg = static_cast<uint16_t>(w - 1);
+    L.push(in);
+  }
+  L.finish();
+  if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  ScanDesc S;
+  fill_scan(input, row_begin, row_end, L, &S);
+  st = fill_lips(n_lip_probe, lip_probe, input, state->dev, &S);
+  if (st) return st;
+  ScanPlan plan;
+  if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
+    int hot, nt;
+    agg_template_shape(A, &hot, &nt);
+    st = plan_scan(d, &S, agg_smem_extra(hot, nt, A.n_key_cols > 0, A.words), &plan);
+    if (st) return st;
+    if (static_cast<uint32_t>(plan.grid) > state->max_ctas) plan.grid = static_cast<int>(state->max_ctas);
+    KernelTimer timer(d, QS_K_SCAN_AGG);
+    QS_CUDA(launch_scan_agg(S, L.P, A, plan.grid, plan.smem, d->stream));
+    QS_CUDA(launch_merge_partials(A, static_cast<uint32_t>(plan.grid), d->stream));
+    count_launch(2);
+  } else {
+    if (state->strategy == QS_AGG_SEPARATE_CHAINING) {
+      uint64_t rows = (row_end == UINT64_MAX ? input->capacity : row_end) - row_begin;
+      if (!input->dirty) rows = std::min<uint64_t>(rows, input->host_rows);
+      st = maybe_grow(state, d, rows);
+      if (st) return st;
+      A.tags = state->A.tags; A.keys = state->A.keys; A.states = state->A.states; A.cap = state->A.cap;
+    }
+    st = plan_scan(d, &S, 0, &plan);
+    if (st) return st;
+    KernelTimer timer(d, QS_K_GROUPBY);
+    QS_CUDA(launch_scan_groupby(S, L.P, A, plan.grid, plan.smem, d->stream));
+    count_launch();
+  }
+  return QSGPU_OK;
+}
+
+static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
+  AggDesc &A = s->A;
+  if (s->idx_cap < A.cap) {
+    if (s->d_idx) cudaFree(s->d_idx);
+    QS_CUDA(cudaMalloc(&s->d_idx, A.cap * 8 + 64));
+    s->idx_cap = A.cap;
+  }
+  QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
+  QS_CUDA(launch_collect_slots(A.states, A.words, A.cap, s->d_idx, s->d_idx_count, d->stream));
+  count_launch();
+  unsigned long long n = 0;
+  QS_CUDA(cudaMemcpyAsync(&n, s->d_idx_count, 8, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  *n_out = n;
+  return check_device_error(d);
+}
+
+int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups) {
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (state->strategy == QS_AGG_COLLISION_FREE) return collect_groups(state, d, n_groups);
+  uint32_t n = 0;
+  QS_CUDA(cudaMemcpyAsync(&n, state->A.n_groups, 4, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  int st = check_device_error(d);
+  if (st) return st;
+  *n_groups = state->strategy == QS_AGG_SINGLE_STATE ? 1 : n;
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys, uint64_t *n_groups,
+                      uint32_t *words_per_group, uint32_t *key_words) {
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  AggDesc &A = state->A;
+  *words_per_group = A.words;
+  *key_words = state->strategy == QS_AGG_COLLISION_FREE ? 1 : A.key_words;
+  if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
+    int st = qsgpu_agg_num_groups(state, n_groups);
+    if (st) return st;
+    *d_states = A.states;
+    *d_keys = A.gid_keys;
+    return QSGPU_OK;
+  }
+  uint64_t n = 0;
+  int st = collect_groups(state, d, &n);
+  if (st) return st;
+  if (state->exp_cap < n || !state->d_exp_states) {
+    if (state->d_exp_states) { cudaFree(state->d_exp_states); cudaFree(state->d_exp_keys); }
+    const uint64_t cap = std::max<uint64_t>(n, 1024);
+    QS_CUDA(cudaMalloc(&state->d_exp_states, cap * A.words * 8));
+    QS_CUDA(cudaMalloc(&state->d_exp_keys, cap * (*key_words) * 8));
+    state->exp_cap = cap;
+  }
+  QS_CUDA(launch_gather_rows(A.states, A.keys, A.words, A.key_words, state->d_idx, n, state->d_exp_states,
+                             state->d_exp_keys, state->strategy == QS_AGG_COLLISION_FREE, d->stream));
+  count_launch();
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  *d_states = state->d_exp_states;
+  *d_keys = state->d_exp_keys;
+  *n_groups = n;
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states, const void *d_keys, uint64_t n_groups) {
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  const AggDesc &A = state->A;
+  if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
+    QS_CUDA(launch_merge_foreign_compact(A, static_cast<const uint64_t *>(d_states), static_cast<const uint64_t *>(d_keys),
+                                         static_cast<uint32_t>(n_groups), d->stream));
+  } else {
+    if (state->strategy == QS_AGG_SEPARATE_CHAINING) {
+      int st = maybe_grow(state, d, n_groups);
+      if (st) return st;
+    }
+    QS_CUDA(launch_merge_foreign_table(state->A, static_cast<const uint64_t *>(d_states), static_cast<const uint64_t *>(d_keys),
+                                       n_groups, d->stream));
+  }
+  count_launch();
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t *null_mask) {
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  AggDesc &A = state->A;
+  const bool dense = state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY;
+  uint64_t n = 0;
+  int st = dense ? qsgpu_agg_num_groups(state, &n) : collect_groups(state, d, &n);
+  if (st) return st;
+  // output schema: group-by attributes, then one column per aggregate
+  std::vector<qs_attr> attrs = state->key_attrs;
+  FinalizeDesc F{};
+  F.n_key_cols = A.n_key_cols;
+  F.key_words = A.key_words;
+  F.keys_are_slots = state->strategy == QS_AGG_COLLISION_FREE;
+  for (uint32_t k = 0; k < A.n_key_cols; ++k) { F.key_width[k] = A.key_width[k]; F.key_off[k] = A.key_off[k]; }
+  F.n_out = static_cast<uint32_t>(state->aggregates.size());
+  for (size_t j = 0; j < state->aggregates.size(); ++j) {
+    const qs_aggregate &a = state->aggregates[j];
+    const int w = state->value_word[j];
+    F.function[j] = static_cast<uint8_t>(a.function);
+    F.word[j] = static_cast<uint8_t>(w);
+    uint8_t kind = w ? A.kind[w - 1] : AK_SUM_I64;
+    F.word_is_f64[j] = (kind == AK_SUM_F64 || kind == AK_MIN_F64 || kind == AK_MAX_F64) ? 1 : 0;
+    qs_attr oa{};
+    switch (a.function) {
+      case QS_AGG_COUNT: oa.type = QS_LONG; F.out_vtype[j] = V_I64; break;
+      case QS_AGG_AVG: oa.type = QS_DOUBLE; F.out_vtype[j] = V_F64; break;
+      case QS_AGG_SUM: oa.type = F.word_is_f64[j] ? QS_DOUBLE : QS_LONG; F.out_vtype[j] = F.word_is_f64[j] ? V_F64 : V_I64; break;
+      default: {   // MIN / MAX keep the argument type (AggregationHandleMin.hpp:101-207)
+        const uint8_t v = state->arg_vtype[j];
+        F.out_vtype[j] = v;
+        oa.type = v == V_I32 ? QS_INT : v == V_I64 ? QS_LONG : v == V_F32 ? QS_FLOAT : QS_DOUBLE;
+      }
+    }
+    oa.width = attr_width(oa.type, 0);
+    attrs.push_back(oa);
+  }
+  qsgpu_relation *rel = nullptr;
+  st = qsgpu_relation_create(state->dev, static_cast<uint32_t>(attrs.size()), attrs.data(), std::max<uint64_t>(n, 1), &rel);
+  if (st) return st;
+  for (uint32_t k = 0; k < A.n_key_cols; ++k) F.key_out[k] = rel->cols[k];
+  for (uint32_t j = 0; j < F.n_out; ++j) F.out[j] = rel->cols[A.n_key_cols + j];
+  const uint64_t *keys = dense ? A.gid_keys : A.keys;
+  KernelTimer timer(d, QS_K_GROUPBY);
+  cudaError_t e = launch_finalize(A.states, keys, A.words, dense ? nullptr : state->d_idx, n, F, d->stream);
+  count_launch();
+  if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "finalize"); }
+  if (null_mask) {
+    *null_mask = 0;
+    if (state->strategy == QS_AGG_SINGLE_STATE) {
+      uint64_t count = 0;
+      QS_CUDA(cudaMemcpyAsync(&count, A.states, 8, cudaMemcpyDeviceToHost, d->stream));
+      QS_CUDA(cudaStreamSynchronize(d->stream));
+      if (count == 0)
+        for (size_t j = 0; j < state->aggregates.size(); ++j)
+          if (state->aggregates[j].function != QS_AGG_COUNT) *null_mask |= 1ull << j;
+    }
+  }
+  st = qsgpu_relation_set_num_rows(rel, n);
+  if (st) { qsgpu_relation_destroy(rel); return st; }
+  *out = rel;
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_destroy(qsgpu_agg_state_t s) {
+  if (!s) return QSGPU_OK;
+  Device *d = device(s->dev);
+  if (d) cudaStreamSynchronize(d->stream);
+  AggDesc &A = s->A;
+  cudaFree(A.partials); cudaFree(A.dir_keys); cudaFree(A.dir_gid); cudaFree(A.n_groups); cudaFree(A.gid_keys);
+  cudaFree(A.tags); cudaFree(A.keys); cudaFree(A.states);
+  cudaFree(s->d_done); cudaFree(s->d_idx); cudaFree(s->d_idx_count); cudaFree(s->d_exp_states); cudaFree(s->d_exp_keys);
+  delete s;
+  return QSGPU_OK;
+}
+
+/* --------------------------------------------------------------- hash join */
+int qsgpu_join_create(int dev, uint32_t key_type, uint64_t estimated_num_entries, qsgpu_join_table_t *out) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (key_type != QS_INT && key_type != QS_LONG) { set_error(QSGPU_ERR_UNSUPPORTED, "join keys are single INT/LONG attributes"); return QSGPU_ERR_UNSUPPORTED; }
+  std::unique_ptr<qsgpu_join_table> t(new qsgpu_join_table);
+  t->dev = dev;
+  t->key_type = key_type;
+  uint64_t cap = 1024;
+  while (cap < estimated_num_entries * 2) cap <<= 1;
+  t->J.cap = cap;
+  t->J.error_flag = d->d_error;
+  t->J.key_ltype = key_type == QS_INT ? V_I32 : V_I64;
+  QS_CUDA(cudaMalloc(&t->J.slots, cap * sizeof(JoinSlot)));
+  QS_CUDA(cudaMalloc(&t->J.n_entries, 256));
+  QS_CUDA(cudaMemsetAsync(t->J.n_entries, 0, 256, d->stream));
+  QS_CUDA(launch_join_clear(t->J, d->stream));
+  count_launch();
+  *out = t.release();
+  return QSGPU_OK;
+}
+
+int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan, uint32_t key_attr, uint32_t n_lip_build,
+                     const qs_lip_ref *lip_build) {
+  qsgpu_relation *rel = scan->input;
+  Device *d = device(table->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (rel->dev != table->dev || key_attr >= rel->attrs.size() || rel->attrs[key_attr].type != table->key_type) { set_error(QSGPU_ERR_INVALID, "build key attribute does not match the table"); return QSGPU_ERR_INVALID; }
+  if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
+  table->build_rel = rel;
+  Lowering L(scan->exprs, rel);
+  int st = lower_scan_predicate(L, scan);
+  if (st) return st;
+  SinkDesc K{};
+  K.error_flag = d->d_error;
+  st = fill_lip_build(n_lip_build, lip_build, L, rel, &K);
+  if (st) return st;
+  JoinDesc J = table->J;
+  J.key_col = static_cast<uint16_t>(L.stage_attr(key_attr));
+  L.finish();
+  ScanDesc S;
+  fill_scan(rel, scan->row_begin, scan->row_end, L, &S);
+  st = fill_lips(scan->n_lip_probe, scan->lip_probe, rel, rel->dev, &S);
+  if (st) return st;
+  ScanPlan plan;
+  st = plan_scan(d, &S, 0, &plan);
+  if (st) return st;
+  KernelTimer timer(d, QS_K_JOIN_BUILD);
+  QS_CUDA(launch_join_build(S, L.P, K, J, plan.grid, plan.smem, d->stream));
+  count_launch();
+  return QSGPU_OK;
+}
+
+int qsgpu_join_num_entries(qsgpu_join_table_t table, uint64_t *n) {
+  Device *d = device(table->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  unsigned long long v = 0;
+  QS_CUDA(cudaMemcpyAsync(&v, table->J.n_entries, 8, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  *n = v;
+  return check_device_error(d);
+}
+
+int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t probe_key_attr, uint32_t join_type,
+                     int32_t residual_root, uint32_t n_project, const int32_t *project_roots,
+                     qsgpu_relation_t output) {
+  qsgpu_relation *rel = probe->input;
+  Device *d = device(table->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (join_type == QS_JOIN_LEFT_OUTER) { set_error(QSGPU_ERR_UNSUPPORTED, "outer joins need NULL-able output columns (not staged on the device yet)"); return QSGPU_ERR_UNSUPPORTED; }
+  if (join_type > QS_JOIN_LEFT_ANTI) { set_error(QSGPU_ERR_INVALID, "unknown join type"); return QSGPU_ERR_INVALID; }
+  if (rel->dev != table->dev || output->dev != table->dev || probe_key_attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "bad probe arguments"); return QSGPU_ERR_INVALID; }
+  const uint8_t klt = vtype_of(rel->attrs[probe_key_attr].type);
+  if (klt != V_I32 && klt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "probe key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  Lowering L(probe->exprs, rel, table->build_rel);
+  int st = lower_scan_predicate(L, probe);
+  if (st) return st;
+  if (residual_root >= 0) { L.lower_pred(residual_root); L.mark_mid_end(); }
+  SinkDesc K{};
+  K.error_flag = d->d_error;
+  K.capacity = output->capacity;
+  K.counter = output->d_rows;
+  const size_t builds_before = L.build_attrs.size();
+  st = lower_projection(L, n_project, project_roots, output, &K);
+  if (st) return st;
+  if (join_type != QS_JOIN_INNER && L.build_attrs.size() != builds_before) { set_error(QSGPU_ERR_INVALID, "semi/anti joins cannot project build-side attributes"); return QSGPU_ERR_INVALID; }
+  JoinDesc J = table->J;
+  J.join_type = static_cast<uint8_t>(join_type);
+  J.key_col = static_cast<uint16_t>(L.stage_attr(probe_key_attr));
+  J.key_ltype = klt;
+  J.n_build_cols = static_cast<uint32_t>(L.build_attrs.size());
+  for (uint32_t c = 0; c < J.n_build_cols; ++c) {
+    const uint32_t a = L.build_attrs[c];
+    J.build_cols[c].ptr = table->build_rel->cols[a];
+    J.build_cols[c].width = table->build_rel->attrs[a].width;
+  }
+  if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  ScanDesc S;
+  fill_scan(rel, probe->row_begin, probe->row_end, L, &S);
+  st = fill_lips(probe->n_lip_probe, probe->lip_probe, rel, rel->dev, &S);
+  if (st) return st;
+  ScanPlan plan;
+  st = plan_scan(d, &S, kCompactSmemBytes, &plan);
+  if (st) return st;
+  KernelTimer timer(d, QS_K_JOIN_PROBE);
+  QS_CUDA(launch_join_probe(S, L.P, K, J, plan.grid, plan.smem, d->stream));
+  count_launch();
+  output->dirty = true;
+  return QSGPU_OK;
+}
+
+int qsgpu_join_destroy(qsgpu_join_table_t t) {
+  if (!t) return QSGPU_OK;
+  Device *d = device(t->dev);
+  if (d) cudaStreamSynchronize(d->stream);
+  cudaFree(t->J.slots);
+  cudaFree(t->J.n_entries);
+  delete t;
+  return QSGPU_OK;
+}
+
+}  // extern "C"

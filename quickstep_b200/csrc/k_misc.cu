@@ -1,0 +1,397 @@
+// K8: radix (hash) partition of a device relation, K9: top-k.
+//
+//   K8  the reference repartitions through PartitionAwareInsertDestination
+//       (storage/InsertDestination.cpp:471-722, partition id =
+//       PartitionSchemeHeader::getPartitionId of the key); on the device the
+//       partition id is mix64(key) % n_parts and rows are regrouped so that
+//       each partition is one contiguous slice per column -- the send buffers
+//       of the NVLink all-to-all that follows.
+//   K9  SortRunGenerationOperator + SortMergeRunOperator with a LIMIT
+//       (relational_operators/SortRunGenerationOperator.hpp:76,
+//       SortMergeRunOperator.hpp:72; plan at ExecutionGenerator.cpp:2227-2351):
+//       radix-select the k-th primary sort key, gather the <= k + ties
+//       candidates, sort them with the full multi-attribute comparator in one CTA.
+#include <algorithm>
+#include <vector>
+
+#include "qs_host.h"
+#include "qs_lower.h"
+#include "qs_vm.cuh"
+
+namespace qs {
+
+// ------------------------------------------------------------------- K8
+struct PartDesc {
+  uint32_t n_cols;
+  ColDesc in[kMaxCols];
+  char *out[kMaxCols];
+  const char *key;
+  uint8_t key_ltype;
+  uint32_t n_parts;
+  uint64_t n_rows;
+  unsigned long long *hist;      // [n_parts]
+  unsigned long long *cursor;    // [n_parts] absolute write positions
+};
+
+__device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
+  const int64_t k = static_cast<int64_t>(load_native(D.key + row * native_width(D.key_ltype), D.key_ltype));
+  return static_cast<uint32_t>(mix64(static_cast<uint64_t>(k)) % D.n_parts);
+}
+
+__global__ void __launch_bounds__(kBlock) k_part_hist(const __grid_constant__ PartDesc D) {
+  extern __shared__ unsigned int s_hist[];
+  for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x) s_hist[p] = 0;
+  __syncthreads();
+  for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < D.n_rows;
+       row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&s_hist[part_of(D, row)], 1u);
+  __syncthreads();
+  for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x)
+    if (s_hist[p]) atomicAdd(&D.hist[p], static_cast<unsigned long long>(s_hist[p]));
+}
+
+__global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__ PartDesc D) {
+  extern __shared__ unsigned int s_mem[];
+  unsigned int *s_count = s_mem;                                            // [n_parts]
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_mem + ((D.n_parts + 1) & ~1u));
+  const uint64_t n_tiles = (D.n_rows + kTileRows - 1) / kTileRows;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x) s_count[p] = 0;
+    __syncthreads();
+    uint32_t part[kRows], rank[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const uint64_t row = tile * kTileRows + tile_row(r, threadIdx.x);
+      part[r] = 0xffffffffu;
+      if (row < D.n_rows) {
+        part[r] = part_of(D, row);
+        rank[r] = atomicAdd(&s_count[part[r]], 1u);
+      }
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x)
+      s_base[p] = s_count[p] ? atomicAdd(&D.cursor[p], static_cast<unsigned long long>(s_count[p])) : 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (part[r] == 0xffffffffu) continue;
+      const uint64_t row = tile * kTileRows + tile_row(r, threadIdx.x);
+      const uint64_t dst = s_base[part[r]] + rank[r];
+      for (uint32_t c = 0; c < D.n_cols; ++c) {
+        const uint32_t w = D.in[c].width;
+        const char *src = D.in[c].ptr + row * w;
+        char *o = D.out[c] + dst * w;
+        if (w == 8) *reinterpret_cast<uint64_t *>(o) = *reinterpret_cast<const uint64_t *>(src);
+        else if (w == 4) *reinterpret_cast<uint32_t *>(o) = *reinterpret_cast<const uint32_t *>(src);
+        else for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------- K9
+// Order-preserving map of a native value to an unsigned 64-bit key.
+__device__ __forceinline__ uint64_t sort_key(const char *p, uint8_t ltype, bool desc) {
+  uint64_t k;
+  switch (ltype) {
+    case V_F32: {
+      const double d = static_cast<double>(*reinterpret_cast<const float *>(p));
+      const uint64_t b = d2u(d);
+      k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+      break;
+    }
+    case V_F64: {
+      const uint64_t b = *reinterpret_cast<const uint64_t *>(p);
+      k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+      break;
+    }
+    default:
+      k = load_native(p, ltype) ^ 0x8000000000000000ull;   // I32 / I64 / DATE key
+  }
+  return desc ? ~k : k;
+}
+
+struct TopkDesc {
+  uint32_t n_keys;
+  ColDesc key_col[4];
+  uint8_t key_ltype[4];
+  uint8_t desc[4];
+  uint64_t n_rows;
+  uint32_t n_cols;
+  ColDesc in[kMaxCols];
+  char *out[kMaxCols];
+};
+
+__global__ void k_topk_primary(const __grid_constant__ TopkDesc D, uint64_t *pk) {
+  for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < D.n_rows;
+       row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    pk[row] = sort_key(D.key_col[0].ptr + row * D.key_col[0].width, D.key_ltype[0], D.desc[0] != 0);
+}
+
+// Histogram of byte `shift/8` among keys whose higher bytes equal `prefix`.
+__global__ void k_topk_hist(const uint64_t *pk, uint64_t n, uint64_t prefix, int shift, unsigned long long *hist) {
+  __shared__ unsigned int s[256];
+  s[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t k = pk[i];
+    if ((k & hi_mask) == (prefix & hi_mask)) atomicAdd(&s[(k >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  if (s[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(s[threadIdx.x]));
+}
+
+__global__ void k_topk_collect(const uint64_t *pk, uint64_t n, uint64_t threshold, uint64_t *cand,
+                               unsigned long long *count, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (pk[i] <= threshold) {
+      const unsigned long long pos = atomicAdd(count, 1ull);
+      if (pos < cap) cand[pos] = i;
+    }
+  }
+}
+
+constexpr int kTopkMaxCand = 2048;
+
+struct SortElem { uint64_t k[4]; uint64_t row; };
+
+__device__ __forceinline__ bool elem_less(const SortElem &a, const SortElem &b) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) if (a.k[i] != b.k[i]) return a.k[i] < b.k[i];
+  return a.row < b.row;
+}
+
+// One CTA: bitonic sort of <= kTopkMaxCand candidates, then gather the first `limit` rows.
+__global__ void __launch_bounds__(1024) k_topk_sort(const __grid_constant__ TopkDesc D, const uint64_t *cand,
+                                                    uint32_t m, uint32_t limit) {
+  extern __shared__ __align__(16) char s_raw[];
+  SortElem *e = reinterpret_cast<SortElem *>(s_raw);
+  uint32_t N = 1;
+  while (N < m) N <<= 1;
+  for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+    SortElem x;
+    if (i < m) {
+      x.row = cand[i];
+      for (uint32_t q = 0; q < 4; ++q)
+        x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + x.row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
+    } else {
+      x.row = ~0ull;
+      for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
+    }
+    e[i] = x;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const SortElem a = e[i], b = e[j];
+          if (elem_less(b, a) == up) { e[i] = b; e[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = min(limit, m);
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const uint64_t row = e[i].row;
+    for (uint32_t c = 0; c < D.n_cols; ++c) {
+      const uint32_t w = D.in[c].width;
+      const char *src = D.in[c].ptr + row * w;
+      char *o = D.out[c] + static_cast<uint64_t>(i) * w;
+      for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+    }
+  }
+}
+
+static int grid_for(uint64_t n) {
+  uint64_t g = (n + 255) / 256;
+  if (g > 148ull * 8) g = 148ull * 8;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace qs
+
+using namespace qs;
+
+extern "C" {
+
+int qsgpu_relation_create(int, uint32_t, const qs_attr *, uint64_t, qsgpu_relation_t *);
+int qsgpu_relation_destroy(qsgpu_relation_t);
+int qsgpu_relation_num_rows(qsgpu_relation_t, uint64_t *);
+int qsgpu_relation_set_num_rows(qsgpu_relation_t, uint64_t);
+
+int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
+                          uint64_t *host_offsets) {
+  Device *d = device(input->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  uint64_t n = 0;
+  int st = qsgpu_relation_num_rows(input, &n);
+  if (st) return st;
+  if (n_parts == 0 || n_parts > 1024 || key_attr >= input->attrs.size() || output->dev != input->dev ||
+      output->attrs.size() != input->attrs.size() || output->capacity < n || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
+    set_error(QSGPU_ERR_INVALID, "bad radix partition arguments");
+    return QSGPU_ERR_INVALID;
+  }
+  const uint8_t lt = vtype_of(input->attrs[key_attr].type);
+  if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "partition key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  PartDesc D{};
+  D.n_cols = static_cast<uint32_t>(input->attrs.size());
+  for (uint32_t c = 0; c < D.n_cols; ++c) {
+    if (input->attrs[c].width != output->attrs[c].width) { set_error(QSGPU_ERR_INVALID, "partition output schema differs"); return QSGPU_ERR_INVALID; }
+    D.in[c].ptr = input->cols[c];
+    D.in[c].width = input->attrs[c].width;
+    D.out[c] = output->cols[c];
+  }
+  D.key = input->cols[key_attr];
+  D.key_ltype = lt;
+  D.n_parts = n_parts;
+  D.n_rows = n;
+  unsigned long long *d_buf = nullptr;
+  QS_CUDA(cudaMalloc(&d_buf, 2ull * n_parts * 8 + 64));
+  QS_CUDA(cudaMemsetAsync(d_buf, 0, 2ull * n_parts * 8, d->stream));
+  D.hist = d_buf;
+  D.cursor = d_buf + n_parts;
+  const int grid = std::min(grid_for(n), d->sm_count * 8);
+  {
+    cudaEvent_t e0 = d->ev0, e1 = d->ev1;
+    const bool on = timing_enabled();
+    if (on) cudaEventRecord(e0, d->stream);
+    k_part_hist<<<grid, kBlock, n_parts * 4, d->stream>>>(D);
+    std::vector<unsigned long long> hist(n_parts), cur(n_parts);
+    cudaError_t e = cudaMemcpyAsync(hist.data(), D.hist, n_parts * 8, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { cudaFree(d_buf); return cuda_fail(e, "partition histogram"); }
+    uint64_t acc = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) { host_offsets[p] = acc; cur[p] = acc; acc += hist[p]; }
+    host_offsets[n_parts] = acc;
+    e = cudaMemcpyAsync(D.cursor, cur.data(), n_parts * 8, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) { cudaFree(d_buf); return cuda_fail(e, "partition cursors"); }
+    const size_t smem = ((n_parts + 1) & ~1u) * 4 + n_parts * 8;
+    k_part_scatter<<<grid, kBlock, smem, d->stream>>>(D);
+    count_launch(2);
+    if (on) {
+      cudaEventRecord(e1, d->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      record_ms(QS_K_PARTITION, ms);
+    }
+    e = cudaStreamSynchronize(d->stream);
+    cudaFree(d_buf);
+    if (e != cudaSuccess) return cuda_fail(e, "partition scatter");
+  }
+  return qsgpu_relation_set_num_rows(output, n);
+}
+
+int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys, uint64_t limit,
+               qsgpu_relation_t *out) {
+  Device *d = device(input->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  uint64_t n = 0;
+  int st = qsgpu_relation_num_rows(input, &n);
+  if (st) return st;
+  if (n_keys == 0 || n_keys > 4 || limit == 0 || limit > 1024 || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
+    set_error(QSGPU_ERR_UNSUPPORTED, "top-k supports 1..4 sort attributes and LIMIT <= 1024");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  TopkDesc D{};
+  D.n_keys = n_keys;
+  D.n_rows = n;
+  for (uint32_t q = 0; q < n_keys; ++q) {
+    if (keys[q].attr >= input->attrs.size()) { set_error(QSGPU_ERR_INVALID, "sort attribute out of range"); return QSGPU_ERR_INVALID; }
+    const uint8_t lt = vtype_of(input->attrs[keys[q].attr].type);
+    if (lt == 0xff) { set_error(QSGPU_ERR_UNSUPPORTED, "CHAR sort keys are not lowered"); return QSGPU_ERR_UNSUPPORTED; }
+    D.key_col[q].ptr = input->cols[keys[q].attr];
+    D.key_col[q].width = input->attrs[keys[q].attr].width;
+    D.key_ltype[q] = lt;
+    D.desc[q] = keys[q].descending ? 1 : 0;
+  }
+  qsgpu_relation *rel = nullptr;
+  st = qsgpu_relation_create(input->dev, static_cast<uint32_t>(input->attrs.size()), input->attrs.data(),
+                             std::max<uint64_t>(limit, 1), &rel);
+  if (st) return st;
+  D.n_cols = static_cast<uint32_t>(input->attrs.size());
+  for (uint32_t c = 0; c < D.n_cols; ++c) {
+    D.in[c].ptr = input->cols[c];
+    D.in[c].width = input->attrs[c].width;
+    D.out[c] = rel->cols[c];
+  }
+  if (n == 0) { *out = rel; return qsgpu_relation_set_num_rows(rel, 0); }
+
+  uint64_t *pk = nullptr, *cand = nullptr;
+  unsigned long long *hist = nullptr;
+  auto cleanup = [&]() { cudaFree(pk); cudaFree(cand); cudaFree(hist); };
+  cudaError_t e = cudaMalloc(&pk, n * 8 + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&cand, kTopkMaxCand * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&hist, 257 * 8);
+  if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k scratch"); }
+  const bool on = timing_enabled();
+  if (on) cudaEventRecord(d->ev0, d->stream);
+  const int grid = grid_for(n);
+  k_topk_primary<<<grid, 256, 0, d->stream>>>(D, pk);
+  count_launch();
+  // radix select of the k-th smallest primary key, one byte per pass
+  const uint64_t k = std::min<uint64_t>(limit, n);
+  uint64_t prefix = 0, remaining = k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    cudaMemsetAsync(hist, 0, 256 * 8, d->stream);
+    k_topk_hist<<<grid, 256, 0, d->stream>>>(pk, n, prefix, shift, hist);
+    count_launch();
+    unsigned long long h[256];
+    e = cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k select"); }
+    uint64_t acc = 0;
+    int b = 0;
+    for (; b < 256; ++b) {
+      if (acc + h[b] >= remaining) break;
+      acc += h[b];
+    }
+    if (b == 256) b = 255;
+    remaining -= acc;
+    prefix |= static_cast<uint64_t>(b) << shift;
+  }
+  cudaMemsetAsync(hist + 256, 0, 8, d->stream);
+  k_topk_collect<<<grid, 256, 0, d->stream>>>(pk, n, prefix, cand, hist + 256, kTopkMaxCand);
+  count_launch();
+  unsigned long long m = 0;
+  e = cudaMemcpyAsync(&m, hist + 256, 8, cudaMemcpyDeviceToHost, d->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k collect"); }
+  if (m > static_cast<unsigned long long>(kTopkMaxCand)) {
+    cleanup();
+    qsgpu_relation_destroy(rel);
+    set_error(QSGPU_ERR_UNSUPPORTED, "top-k: more than 2048 rows tie on the primary sort key at the cut");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  uint32_t N = 1;
+  while (N < m) N <<= 1;
+  const size_t smem = static_cast<size_t>(N) * sizeof(SortElem);
+  cudaFuncSetAttribute(k_topk_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  k_topk_sort<<<1, 1024, smem, d->stream>>>(D, cand, static_cast<uint32_t>(m), static_cast<uint32_t>(limit));
+  count_launch();
+  if (on) {
+    cudaEventRecord(d->ev1, d->stream);
+    cudaEventSynchronize(d->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+    record_ms(QS_K_TOPK, ms);
+  }
+  e = cudaStreamSynchronize(d->stream);
+  cleanup();
+  if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k sort"); }
+  st = qsgpu_relation_set_num_rows(rel, std::min<uint64_t>(limit, m));
+  if (st) { qsgpu_relation_destroy(rel); return st; }
+  *out = rel;
+  return QSGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,378 @@
+// Expression-tree -> VM program lowering (host code; see qs_lower.h).
+#include <cstring>
+
+#include "qs_host.h"
+#include "qs_lower.h"
+
+namespace qs {
+
+uint8_t vtype_of(uint16_t t) {
+  switch (t) {
+    case QS_INT: return V_I32;
+    case QS_LONG: return V_I64;
+    case QS_FLOAT: return V_F32;
+    case QS_DOUBLE: return V_F64;
+    case QS_DATE: return V_DATE;
+    default: return 0xff;
+  }
+}
+
+// TypeFactory::GetUnifyingType for numeric pairs (types/TypeFactory.cpp:159-180).
+uint8_t unify(uint8_t a, uint8_t b) {
+  if (a == V_DATE) a = V_I64;
+  if (b == V_DATE) b = V_I64;
+  if (a == b) return a;
+  if (a == V_F64 || b == V_F64) return V_F64;
+  if ((a == V_I64 && b == V_F32) || (a == V_F32 && b == V_I64)) return V_F64;
+  if (a == V_F32 || b == V_F32) return V_F32;   // INT with FLOAT
+  return V_I64;                                  // INT with LONG
+}
+
+static uint64_t host_cvt(uint64_t raw, uint8_t from, uint8_t to) {
+  if (from == V_DATE) from = V_I64;
+  if (from == to) return raw;
+  double d = 0;
+  int64_t i = 0;
+  bool is_fp = false;
+  switch (from) {
+    case V_I32: i = static_cast<int32_t>(raw); break;
+    case V_I64: i = static_cast<int64_t>(raw); break;
+    case V_F32: { uint32_t u = static_cast<uint32_t>(raw); float f; std::memcpy(&f, &u, 4); d = f; is_fp = true; break; }
+    default: { std::memcpy(&d, &raw, 8); is_fp = true; break; }
+  }
+  switch (to) {
+    case V_I32: return static_cast<uint64_t>(static_cast<int64_t>(is_fp ? static_cast<int32_t>(d) : static_cast<int32_t>(i)));
+    case V_I64: return static_cast<uint64_t>(is_fp ? static_cast<int64_t>(d) : i);
+    case V_F32: { float f = is_fp ? static_cast<float>(d) : static_cast<float>(i); uint32_t u; std::memcpy(&u, &f, 4); return u; }
+    default: { double x = is_fp ? d : static_cast<double>(i); uint64_t u; std::memcpy(&u, &x, 8); return u; }
+  }
+}
+
+Lowering::Lowering(const qs_expr_set *e, const qsgpu_relation *r, const qsgpu_relation *b)
+    : ex(e), rel(r), build_rel(b) {
+  std::memset(&P, 0, sizeof(P));
+  if (r) slot_of_attr.assign(r->attrs.size(), -1);
+  if (b) bslot_of_attr.assign(b->attrs.size(), -1);
+}
+
+const qs_node *Lowering::node(int i) {
+  if (!ex || i < 0 || static_cast<uint32_t>(i) >= ex->n_nodes) {
+    fail(QSGPU_ERR_INVALID, "expression node index out of range");
+    return nullptr;
+  }
+  return &ex->nodes[i];
+}
+
+int Lowering::stage_attr(uint32_t attr) {
+  if (!rel || attr >= rel->attrs.size()) { fail(QSGPU_ERR_INVALID, "attribute id out of range"); return 0; }
+  if (slot_of_attr[attr] >= 0) return slot_of_attr[attr];
+  if (staged_attrs.size() >= static_cast<size_t>(kMaxCols)) {
+    fail(QSGPU_ERR_UNSUPPORTED, "more than kMaxCols attributes referenced by one scan");
+    return 0;
+  }
+  slot_of_attr[attr] = static_cast<int>(staged_attrs.size());
+  staged_attrs.push_back(attr);
+  return slot_of_attr[attr];
+}
+
+int Lowering::build_attr(uint32_t attr) {
+  if (!build_rel || attr >= build_rel->attrs.size()) {
+    fail(QSGPU_ERR_INVALID, "build-side attribute without a build relation");
+    return 0;
+  }
+  if (bslot_of_attr[attr] >= 0) return bslot_of_attr[attr];
+  if (build_attrs.size() >= static_cast<size_t>(kMaxCols)) {
+    fail(QSGPU_ERR_UNSUPPORTED, "too many build-side attributes");
+    return 0;
+  }
+  bslot_of_attr[attr] = static_cast<int>(build_attrs.size());
+  build_attrs.push_back(attr);
+  return bslot_of_attr[attr];
+}
+
+void Lowering::push(Instr in) {
+  if (n_code >= static_cast<uint32_t>(kMaxInstr)) { fail(QSGPU_ERR_UNSUPPORTED, "expression program too long"); return; }
+  P.code[n_code++] = in;
+}
+
+int Lowering::add_lit(uint64_t v) {
+  for (uint32_t i = 0; i < n_lits; ++i) if (P.lits[i] == v) return static_cast<int>(i);
+  if (n_lits >= static_cast<uint32_t>(kMaxLits)) { fail(QSGPU_ERR_UNSUPPORTED, "too many literals"); return 0; }
+  P.lits[n_lits] = v;
+  return static_cast<int>(n_lits++);
+}
+
+uint8_t Lowering::scalar_vtype(int i) {
+  const qs_node *n = node(i);
+  if (!n) return V_I64;
+  switch (n->kind) {
+    case QS_N_LITERAL:
+    case QS_N_ATTRIBUTE: {
+      const uint8_t v = vtype_of(n->type);
+      if (v == 0xff) { fail(QSGPU_ERR_UNSUPPORTED, "CHAR/VARCHAR value in arithmetic context"); return V_I64; }
+      return v == V_DATE ? V_I64 : v;
+    }
+    case QS_N_UNARY:
+      if (n->op == QS_CAST) { const uint8_t v = vtype_of(n->type); return v == V_DATE ? V_I64 : v; }
+      return scalar_vtype(n->a);
+    case QS_N_BINARY: return unify(scalar_vtype(n->a), scalar_vtype(n->b));
+    case QS_N_SHARED: return scalar_vtype(n->a);
+    default: fail(QSGPU_ERR_INVALID, "predicate node used as scalar"); return V_I64;
+  }
+}
+
+bool Lowering::is_leaf(int i) {
+  const qs_node *n = node(i);
+  if (!n) return false;
+  if (n->kind == QS_N_LITERAL || n->kind == QS_N_ATTRIBUTE) return true;
+  if (n->kind == QS_N_SHARED) return shared.count(n->b) > 0;
+  return false;
+}
+
+static uint64_t literal_raw(const qs_node *n) {
+  switch (n->type) {
+    case QS_INT: return static_cast<uint64_t>(static_cast<int64_t>(n->lit.i32));
+    case QS_LONG: return static_cast<uint64_t>(n->lit.i64);
+    case QS_FLOAT: { uint32_t u; std::memcpy(&u, &n->lit.f32, 4); return u; }
+    case QS_DOUBLE: { uint64_t u; std::memcpy(&u, &n->lit.f64, 8); return u; }
+    case QS_DATE:
+      return static_cast<uint64_t>(static_cast<int64_t>(n->lit.date.year) * 65536 +
+                                   (static_cast<int64_t>(n->lit.date.month) << 8) + n->lit.date.day);
+    default: return 0;
+  }
+}
+
+bool Lowering::leaf_ref(int i, uint8_t want, Instr *in) {
+  const qs_node *n = node(i);
+  if (!n) return false;
+  if (n->kind == QS_N_LITERAL) {
+    const uint8_t own = vtype_of(n->type);
+    if (own == 0xff) return fail(QSGPU_ERR_UNSUPPORTED, "CHAR literal in arithmetic context");
+    in->leaf = LEAF_LIT;
+    in->ltype = want;
+    in->arg = static_cast<uint16_t>(add_lit(host_cvt(literal_raw(n), own, want)));
+    return true;
+  }
+  if (n->kind == QS_N_ATTRIBUTE) {
+    const uint8_t own = vtype_of(n->type);
+    if (own == 0xff) return fail(QSGPU_ERR_UNSUPPORTED, "CHAR attribute in arithmetic context");
+    in->ltype = own;
+    if (n->b == 2) { in->leaf = LEAF_BUILD; in->arg = static_cast<uint16_t>(build_attr(static_cast<uint32_t>(n->a))); }
+    else { in->leaf = LEAF_COL; in->arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(n->a))); }
+    return true;
+  }
+  if (n->kind == QS_N_SHARED) {
+    auto it = shared.find(n->b);
+    if (it == shared.end()) return fail(QSGPU_ERR_INVALID, "shared expression not materialised");
+    in->leaf = LEAF_TMP;
+    in->ltype = it->second.type;
+    in->arg = static_cast<uint16_t>(it->second.tmp);
+    return true;
+  }
+  return fail(QSGPU_ERR_INVALID, "not a leaf");
+}
+
+void Lowering::lower_cast_acc(uint8_t from, uint8_t to) {
+  if (from == V_DATE) from = V_I64;
+  if (from == to) return;
+  Instr in{};
+  in.op = OP_CVT; in.type = from; in.aux = to;
+  push(in);
+}
+
+uint8_t Lowering::lower_scalar(int i) {
+  const qs_node *n = node(i);
+  if (!n || !ok()) return V_I64;
+  switch (n->kind) {
+    case QS_N_LITERAL:
+    case QS_N_ATTRIBUTE: {
+      const uint8_t t = scalar_vtype(i);
+      Instr in{};
+      in.op = OP_LOAD; in.type = t;
+      leaf_ref(i, t, &in);
+      push(in);
+      return t;
+    }
+    case QS_N_SHARED: {
+      auto it = shared.find(n->b);
+      if (it != shared.end()) {
+        Instr in{};
+        in.op = OP_LOAD; in.type = it->second.type;
+        leaf_ref(i, it->second.type, &in);
+        push(in);
+        return it->second.type;
+      }
+      const uint8_t t = lower_scalar(n->a);
+      for (int k = 0; k < kMaxTmp; ++k) {
+        if (!tmp_busy[k]) {
+          tmp_busy[k] = true;            // held for the rest of the program
+          Instr st{};
+          st.op = OP_ST_TMP; st.type = t; st.arg = static_cast<uint16_t>(k);
+          push(st);
+          shared[n->b] = Shared{k, t};
+          break;
+        }
+      }
+      return t;                           // no free temp: recomputed at the next use
+    }
+    case QS_N_UNARY: {
+      const uint8_t t = lower_scalar(n->a);
+      if (n->op == QS_NEGATE) {
+        Instr in{};
+        in.op = OP_NEG; in.type = t;
+        push(in);
+        return t;
+      }
+      if (n->op == QS_CAST) {
+        uint8_t to = vtype_of(n->type);
+        if (to == 0xff) { fail(QSGPU_ERR_UNSUPPORTED, "CAST to a non-numeric type"); return t; }
+        if (to == V_DATE) to = V_I64;
+        lower_cast_acc(t, to);
+        return to;
+      }
+      fail(QSGPU_ERR_UNSUPPORTED, "unary operation not lowered (DateExtract/Substring)");
+      return t;
+    }
+    case QS_N_BINARY: {
+      const uint8_t ta = scalar_vtype(n->a), tb = scalar_vtype(n->b);
+      const uint8_t T = unify(ta, tb);
+      if (n->op > QS_MOD) { fail(QSGPU_ERR_INVALID, "bad binary operation id"); return T; }
+      Instr in{};
+      in.op = static_cast<uint8_t>(OP_ADD + n->op);
+      in.type = T;
+      if (is_leaf(n->b)) {
+        const uint8_t t = lower_scalar(n->a);
+        lower_cast_acc(t, T);
+        leaf_ref(n->b, T, &in);
+      } else if (is_leaf(n->a)) {
+        const uint8_t t = lower_scalar(n->b);
+        lower_cast_acc(t, T);
+        leaf_ref(n->a, T, &in);
+        in.flags = 1;
+      } else {
+        int k = -1;
+        for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
+        if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "expression too deep for the VM temporaries"); return T; }
+        const uint8_t t_b = lower_scalar(n->b);
+        tmp_busy[k] = true;
+        Instr st{};
+        st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);
+        push(st);
+        const uint8_t t_a = lower_scalar(n->a);
+        lower_cast_acc(t_a, T);
+        in.leaf = LEAF_TMP; in.ltype = t_b; in.arg = static_cast<uint16_t>(k);
+        tmp_busy[k] = false;
+      }
+      push(in);
+      return T;
+    }
+    default:
+      fail(QSGPU_ERR_INVALID, "predicate node used as scalar");
+      return V_I64;
+  }
+}
+
+static uint8_t flip_cmp(uint8_t c) {
+  switch (c) {
+    case QS_LT: return QS_GT;
+    case QS_LE: return QS_GE;
+    case QS_GT: return QS_LT;
+    case QS_GE: return QS_LE;
+    default: return c;
+  }
+}
+
+void Lowering::lower_pred(int i) {
+  const qs_node *n = node(i);
+  if (!n || !ok()) return;
+  Instr in{};
+  switch (n->kind) {
+    case QS_N_TRUE: in.op = OP_PUSH_TRUE; push(in); return;
+    case QS_N_FALSE: in.op = OP_PUSH_FALSE; push(in); return;
+    case QS_N_NEGATION: lower_pred(n->a); in.op = OP_NOT; push(in); return;
+    case QS_N_CONJUNCTION:
+    case QS_N_DISJUNCTION:
+      lower_pred(n->a);
+      lower_pred(n->b);
+      in.op = n->kind == QS_N_CONJUNCTION ? OP_AND : OP_OR;
+      push(in);
+      return;
+    case QS_N_COMPARISON: {
+      const qs_node *l = node(n->a), *r = node(n->b);
+      if (!l || !r) return;
+      if (n->op > QS_GE) { fail(QSGPU_ERR_UNSUPPORTED, "LIKE / regex comparisons are not lowered"); return; }
+      if (l->type == QS_CHAR || r->type == QS_CHAR) {
+        // attribute vs literal only; the literal is NUL-padded to the attribute width
+        const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
+        const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
+        if (attr->kind != QS_N_ATTRIBUTE || lit->kind != QS_N_LITERAL || attr->type != QS_CHAR ||
+            lit->type != QS_CHAR || attr->b == 2) {
+          fail(QSGPU_ERR_UNSUPPORTED, "CHAR comparison other than attribute-vs-literal");
+          return;
+        }
+        const uint32_t w = attr->width;
+        if (lit->lit.pool_offset + lit->width > ex->str_pool_bytes) { fail(QSGPU_ERR_INVALID, "CHAR literal outside pool"); return; }
+        if (lit->width > w && ex->str_pool[lit->lit.pool_offset + w] != 0) {
+          fail(QSGPU_ERR_UNSUPPORTED, "CHAR literal longer than the attribute");
+          return;
+        }
+        if (n_str + w > static_cast<uint32_t>(kStrPool)) { fail(QSGPU_ERR_UNSUPPORTED, "string pool full"); return; }
+        const uint32_t off = n_str;
+        for (uint32_t b = 0; b < w; ++b)
+          P.str_pool[off + b] = b < lit->width ? ex->str_pool[lit->lit.pool_offset + b] : 0;
+        n_str += w;
+        in.op = OP_CMP_CHAR;
+        in.arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(attr->a)));
+        in.ltype = static_cast<uint8_t>(off);
+        in.aux = (attr == l) ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op));
+        push(in);
+        return;
+      }
+      const uint8_t T = unify(scalar_vtype(n->a), scalar_vtype(n->b));
+      in.op = OP_CMP; in.type = T; in.aux = static_cast<uint8_t>(n->op);
+      if (is_leaf(n->b)) {
+        lower_cast_acc(lower_scalar(n->a), T);
+        leaf_ref(n->b, T, &in);
+      } else if (is_leaf(n->a)) {
+        lower_cast_acc(lower_scalar(n->b), T);
+        leaf_ref(n->a, T, &in);
+        in.flags = 1;
+      } else {
+        int k = -1;
+        for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
+        if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "comparison too deep for the VM temporaries"); return; }
+        const uint8_t t_b = lower_scalar(n->b);
+        tmp_busy[k] = true;
+        Instr st{};
+        st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);
+        push(st);
+        lower_cast_acc(lower_scalar(n->a), T);
+        in.leaf = LEAF_TMP; in.ltype = t_b; in.arg = static_cast<uint16_t>(k);
+        tmp_busy[k] = false;
+      }
+      push(in);
+      return;
+    }
+    default:
+      fail(QSGPU_ERR_INVALID, "scalar node used as predicate");
+  }
+}
+
+// LIPFilterAdaptiveProber: probe attribute `attr` against filter `lip_index`
+// and AND the answer into the running predicate.
+void Lowering::lower_lip_probe(uint32_t lip_index, uint32_t attr, bool have_pred) {
+  if (!rel || attr >= rel->attrs.size()) { fail(QSGPU_ERR_INVALID, "LIP probe attribute out of range"); return; }
+  const uint8_t lt = vtype_of(rel->attrs[attr].type);
+  if (lt != V_I32 && lt != V_I64) { fail(QSGPU_ERR_UNSUPPORTED, "LIP filters take INT/LONG attributes"); return; }
+  Instr ld{};
+  ld.op = OP_LOAD; ld.type = V_I64; ld.leaf = LEAF_COL; ld.ltype = lt;
+  ld.arg = static_cast<uint16_t>(stage_attr(attr));
+  push(ld);
+  Instr pr{};
+  pr.op = OP_LIP; pr.type = V_I64; pr.arg = static_cast<uint16_t>(lip_index);
+  pr.flags = have_pred ? 2 : 0;
+  push(pr);
+  if (have_pred) { Instr a{}; a.op = OP_AND; push(a); }
+}
+
+}  // namespace qs

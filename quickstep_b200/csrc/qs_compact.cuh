@@ -1,0 +1,62 @@
+// CTA-wide, order-preserving stream compaction: warp ballots -> one warp scan
+// over the kRows*8 per-warp counts -> one atomicAdd per CTA per tile.
+// The device analogue of building a TupleIdSequence and iterating its set bits
+// (storage/TupleIdSequence.hpp:121, utility/BitVector.hpp:625-640).
+#pragma once
+
+#include "qs_common.cuh"
+
+namespace qs {
+
+
+
+// Must be called by all threads of the CTA (contains __syncthreads).
+__device__ __forceinline__ void cta_compact(const bool (&flag)[kRows], uint32_t *s,
+                                            unsigned long long *counter, uint64_t capacity,
+                                            uint32_t *error_flag, uint64_t (&idx)[kRows]) {
+  static_assert(kRows * (kBlock / 32) == 32, "one warp scans the per-warp counts");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t ball[kRows];
+  __syncthreads();                               // previous users of `s` are done
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    ball[r] = __ballot_sync(0xffffffffu, flag[r]);
+    if (lane == 0) s[r * (kBlock / 32) + warp] = __popc(ball[r]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = s[lane];
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    s[lane] = inc - v;                           // exclusive prefix in (r, warp) order
+    if (lane == 31) {
+      unsigned long long base = 0;
+      uint32_t overflow = 0;
+      if (inc) {
+        base = atomicAdd(counter, static_cast<unsigned long long>(inc));
+        if (base + inc > capacity) {
+          overflow = 1;
+          atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+        }
+      }
+      s[32] = static_cast<uint32_t>(base);
+      s[33] = static_cast<uint32_t>(base >> 32);
+      s[34] = overflow;
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = static_cast<unsigned long long>(s[32]) | (static_cast<unsigned long long>(s[33]) << 32);
+  const bool overflow = s[34] != 0;
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    idx[r] = (flag[r] && !overflow)
+                 ? base + s[r * (kBlock / 32) + warp] + __popc(ball[r] & ((1u << lane) - 1u))
+                 : ~0ull;
+  }
+}
+
+}  // namespace qs

@@ -1,0 +1,95 @@
+// Host-side objects behind the opaque C-ABI handles.
+#pragma once
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "qs_ops.cuh"
+
+struct qsgpu_relation {
+  int dev = 0;
+  std::vector<qs_attr> attrs;
+  std::vector<char *> cols;
+  bool owns_memory = true;
+  uint64_t capacity = 0;
+  // Row count: authoritative copy lives on the device (kernels append with
+  // atomics); host_rows is valid only while !dirty.
+  unsigned long long *d_rows = nullptr;
+  uint64_t host_rows = 0;
+  bool dirty = false;
+};
+
+struct qsgpu_lip {
+  int dev = 0;
+  qs::LipDesc d{};
+  uint32_t attr_type = QS_INT;
+  uint64_t n_words = 0;
+};
+
+struct qsgpu_agg_state {
+  int dev = 0;
+  uint32_t strategy = 0;
+  // deep copy of the expression set
+  std::vector<qs_node> nodes;
+  std::string str_pool;
+  qs_expr_set exprs{};
+  int32_t predicate_root = -1;
+  std::vector<qs_aggregate> aggregates;
+  std::vector<int32_t> group_by_roots;
+  std::vector<int> value_word;        // per aggregate: state word (0 = row count only)
+  std::vector<uint8_t> arg_vtype;     // per aggregate: VType of the argument (V_I32.. ; 0 for COUNT(*))
+  std::vector<qs_attr> key_attrs;     // group-by attribute types
+  std::vector<uint32_t> key_attr_ids;
+  qs::AggDesc A{};
+  uint32_t max_ctas = 0;
+  unsigned int *d_done = nullptr;     // last-CTA-merges ticket
+  // dense export buffers (hash / collision-free partials, finalize index)
+  uint64_t *d_idx = nullptr;
+  uint64_t idx_cap = 0;
+  unsigned long long *d_idx_count = nullptr;
+  uint64_t *d_exp_states = nullptr, *d_exp_keys = nullptr;
+  uint64_t exp_cap = 0;
+  uint64_t estimated = 0;
+};
+
+struct qsgpu_join_table {
+  int dev = 0;
+  uint32_t key_type = QS_INT;
+  qs::JoinDesc J{};
+  const qsgpu_relation *build_rel = nullptr;
+};
+
+namespace qs {
+
+struct Device {
+  int id = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  size_t smem_per_sm = 0, smem_per_block_optin = 0;
+  uint32_t *d_error = nullptr;        // sticky device-side error word
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+Device *device(int dev);               // nullptr (+ last error) when unavailable
+void set_error(int status, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+bool timing_enabled();
+void record_ms(uint32_t family, float ms);
+
+// Launch geometry for a scan over `n_cols` staged columns.
+struct ScanPlan {
+  int grid = 0;
+  size_t smem = 0;
+};
+int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan);
+
+}  // namespace qs
+
+#define QS_CUDA(call)                                                     \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) return ::qs::cuda_fail(e__, #call);           \
+  } while (0)

@@ -1,0 +1,94 @@
+// Operator descriptors and kernel launchers shared between the .cu files and
+// the C-ABI implementation (capi.cu).
+#pragma once
+
+#include "qs_agg.cuh"
+#include "qs_common.cuh"
+
+namespace qs {
+
+// Output side of Select / HashJoin probe / BuildLIPFilter / BuildHash scans.
+struct SinkDesc {
+  uint32_t n_out;
+  uint8_t out_width[kMaxOut];
+  char *out[kMaxOut];               // output column base pointers
+  uint64_t capacity;                // rows the output relation can hold
+  unsigned long long *counter;      // device row counter of the output relation
+  uint32_t n_lip_build;             // LIPFilterBuilder::insertValueAccessor targets
+  LipDesc lip_build[kMaxLip];
+  uint16_t lip_build_col[kMaxLip];  // staged column slot of the build attribute
+  uint8_t lip_build_ltype[kMaxLip];
+  uint32_t *error_flag;
+};
+
+struct __align__(16) JoinSlot {                   // 16 bytes, one vector load per probe step
+  int64_t key;
+  unsigned long long row;           // build row id; ~0 = empty
+};
+
+struct JoinDesc {
+  JoinSlot *slots;
+  uint64_t cap;                     // power of two
+  unsigned long long *n_entries;
+  uint16_t key_col;                 // staged column slot of the key
+  uint8_t key_ltype;                // V_I32 / V_I64
+  uint8_t join_type;                // QS_JOIN_*
+  uint32_t n_build_cols;
+  ColDesc build_cols[kMaxCols];     // build relation columns for LEAF_BUILD / raw emits
+  uint32_t *error_flag;
+};
+
+struct FinalizeDesc {
+  uint32_t n_key_cols, key_words;
+  uint8_t key_width[kMaxKeyCols];
+  uint8_t key_off[kMaxKeyCols];
+  char *key_out[kMaxKeyCols];
+  uint32_t n_out;
+  uint8_t function[kMaxOut];   // QS_AGG_*
+  uint8_t word[kMaxOut];       // state word holding the value (0 = row count)
+  uint8_t out_vtype[kMaxOut];  // VType of the output column
+  uint8_t word_is_f64[kMaxOut];
+  char *out[kMaxOut];
+  int keys_are_slots;          // collision free: key value == slot index
+};
+
+// k_agg.cu
+size_t agg_smem_extra(int hot, int nagg_t, bool grouped, uint32_t words);
+void agg_template_shape(const AggDesc &A, int *hot, int *nagg_t);
+cudaError_t launch_scan_agg(const ScanDesc &S, const Program &P, const AggDesc &A, int grid, size_t smem,
+                            cudaStream_t st);
+cudaError_t launch_fill_identity(uint64_t *states, uint64_t n_rows, const AggDesc &A, cudaStream_t st);
+cudaError_t launch_merge_partials(const AggDesc &A, uint32_t n_ctas, cudaStream_t st);
+cudaError_t launch_merge_foreign_compact(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
+                                         uint32_t f_groups, cudaStream_t st);
+// k_groupby.cu
+cudaError_t launch_scan_groupby(const ScanDesc &S, const Program &P, const AggDesc &A, int grid, size_t smem,
+                                cudaStream_t st);
+cudaError_t launch_rehash(const AggDesc &from, const AggDesc &to, cudaStream_t st);
+cudaError_t launch_merge_foreign_table(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
+                                       uint64_t f_groups, cudaStream_t st);
+cudaError_t launch_collect_slots(const uint64_t *states, uint32_t words, uint64_t cap, uint64_t *out_idx,
+                                 unsigned long long *counter, cudaStream_t st);
+cudaError_t launch_gather_rows(const uint64_t *states, const uint64_t *keys, uint32_t words, uint32_t kw,
+                               const uint64_t *idx, uint64_t n, uint64_t *o_states, uint64_t *o_keys,
+                               int keys_are_slots, cudaStream_t st);
+cudaError_t launch_finalize(const uint64_t *states, const uint64_t *keys, uint32_t words, const uint64_t *idx,
+                            uint64_t n, const FinalizeDesc &F, cudaStream_t st);
+// k_select.cu
+cudaError_t launch_scan_select(const ScanDesc &S, const Program &P, const SinkDesc &K, int grid, size_t smem,
+                               cudaStream_t st);
+// k_join.cu
+cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st);
+cudaError_t launch_join_build(const ScanDesc &S, const Program &P, const SinkDesc &K, const JoinDesc &J,
+                              int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_join_probe(const ScanDesc &S, const Program &P, const SinkDesc &K, const JoinDesc &J,
+                              int grid, size_t smem, cudaStream_t st);
+// k_misc.cu
+cudaError_t launch_decode_dict(void *dst, const void *codes, const void *dict, uint64_t n, uint32_t code_width,
+                               uint32_t value_width, uint32_t dict_entries, cudaStream_t st);
+cudaError_t launch_decode_truncated(void *dst, const void *codes, uint64_t n, uint32_t code_width,
+                                    uint32_t value_width, cudaStream_t st);
+cudaError_t launch_decode_strided(void *dst, const void *slots, uint64_t n, uint32_t stride,
+                                  uint32_t value_width, cudaStream_t st);
+
+}  // namespace qs
