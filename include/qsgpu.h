@@ -204,7 +204,7 @@ typedef struct qs_stage_desc {
 
 /* Stage `n_desc` attributes of one block of `n_rows` tuples; all attributes
  * of the relation must be staged by the same call or by calls made before
- * qsgpu_relation_commit_block(). */
+ * the next work order reads it. */
 int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows,
                       const qs_stage_desc *descs, uint32_t n_desc);
 

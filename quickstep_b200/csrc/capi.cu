@@ -717,6 +717,10 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     s->max_ctas = static_cast<uint32_t>(d->sm_count) * 2;
     const size_t prow = static_cast<size_t>(A.partial_rows) * A.words * 8;
     QS_CUDA(cudaMalloc(&A.partials, prow * s->max_ctas));
+    // every partial row starts as (and is reset to, by k_merge_partials) the identity, so rows of
+    // groups a CTA never met contribute nothing to the fold
+    QS_CUDA(launch_fill_identity(A.partials, static_cast<uint64_t>(A.partial_rows) * s->max_ctas, A, d->stream));
+    count_launch();
     A.dir_cap = 1024;
     QS_CUDA(cudaMalloc(&A.dir_keys, A.dir_cap * 8));
     QS_CUDA(cudaMalloc(&A.dir_gid, A.dir_cap * 4));

@@ -294,8 +294,12 @@ __global__ void k_merge_partials(const __grid_constant__ AggDesc A, uint32_t n_c
   const uint32_t g = i / A.words, w = i % A.words;
   uint64_t x = A.states[i];
   const uint8_t kind = w == 0 ? AK_SUM_I64 : A.kind[w - 1];
-  for (uint32_t c = 0; c < n_ctas; ++c)
-    x = agg_combine(kind, x, A.partials[(static_cast<uint64_t>(c) * A.partial_rows + g) * A.words + w]);
+  const uint64_t ident = w == 0 ? 0 : agg_identity(kind);
+  for (uint32_t c = 0; c < n_ctas; ++c) {
+    uint64_t *p = &A.partials[(static_cast<uint64_t>(c) * A.partial_rows + g) * A.words + w];
+    x = agg_combine(kind, x, *p);
+    *p = ident;                     // consumed: ready for the next work order
+  }
   A.states[i] = x;
 }
 

@@ -1,0 +1,344 @@
+"""Thin Python handles over the C-ABI objects of libqsgpu.so.
+
+Harness plumbing only (tests/, bench.py, __graft_entry__): every method is one
+C-ABI call; results are read back as numpy arrays.  All compute happens in the
+CUDA kernels behind the ABI -- a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi as A
+from .table import Column, HostTable, np_dtype
+
+_inited = False
+
+
+def init(devices=None):
+    """qsgpu_init; devices=None -> device 0 only (one process per GPU)."""
+    global _inited
+    L = A.load()
+    if _inited:
+        return L
+    devs = [0] if devices is None else list(devices)
+    arr = (C.c_int * len(devs))(*devs)
+    A.check(L.qsgpu_init(len(devs), arr))
+    _inited = True
+    return L
+
+
+def shutdown():
+    global _inited
+    if _inited:
+        A.load().qsgpu_shutdown()
+        _inited = False
+
+
+def launch_count() -> int:
+    n = C.c_uint64(0)
+    A.check(A.load().qsgpu_launch_count(C.byref(n)))
+    return n.value
+
+
+def synchronize(dev=0):
+    A.check(A.load().qsgpu_synchronize(dev))
+
+
+def set_timing(on: bool):
+    A.check(A.load().qsgpu_set_timing(1 if on else 0))
+
+
+def last_kernel_ms(family: int) -> float:
+    ms = C.c_float(0)
+    A.check(A.load().qsgpu_last_kernel_ms(family, C.byref(ms)))
+    return ms.value
+
+
+def _attrs(schema):
+    arr = (A.qs_attr * len(schema))()
+    for i, (t, w) in enumerate(schema):
+        arr[i].type, arr[i].width = t, w
+    return arr
+
+
+class Relation:
+    """qsgpu_relation_t: device-resident columns of one relation."""
+
+    def __init__(self, handle, schema, names=None, dev=0, owner=True, keep=None):
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        self.schema = list(schema)         # [(type, width)]
+        self.names = list(names) if names else [f"c{i}" for i in range(len(schema))]
+        self.dev = dev
+        self.owner = owner
+        self._keep = keep
+
+    # -- construction ---------------------------------------------------
+    @classmethod
+    def create(cls, schema, capacity, names=None, dev=0):
+        L = init()
+        out = C.c_void_p()
+        A.check(L.qsgpu_relation_create(dev, len(schema), _attrs(schema), capacity, C.byref(out)))
+        return cls(out, schema, names, dev)
+
+    @classmethod
+    def from_host(cls, table: HostTable, dev=0, block_rows=None):
+        """Stage a host table block by block (QS_ENC_PLAIN stripes)."""
+        schema = [(c.type, c.width) for c in table.columns]
+        rel = cls.create(schema, max(table.n_rows, 1), [c.name for c in table.columns], dev)
+        step = block_rows or max(table.n_rows, 1)
+        for lo in range(0, table.n_rows, step):
+            hi = min(table.n_rows, lo + step)
+            rel.stage_plain([c.data[lo:hi] for c in table.columns])
+        return rel
+
+    @classmethod
+    def wrap(cls, schema, device_ptrs, n_rows, names=None, dev=0, keep=None):
+        L = init()
+        out = C.c_void_p()
+        ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
+        A.check(L.qsgpu_relation_wrap(dev, len(schema), _attrs(schema), ptrs, n_rows, C.byref(out)))
+        return cls(out, schema, names, dev, keep=keep)
+
+    def stage_plain(self, arrays):
+        descs = (A.qs_stage_desc * len(arrays))()
+        keep = []
+        n = len(arrays[0])
+        for i, a in enumerate(arrays):
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            descs[i].attr, descs[i].encoding, descs[i].host = i, A.QS_ENC_PLAIN, a.ctypes.data
+        A.check(A.load().qsgpu_stage_block(self.h, n, descs, len(arrays)))
+
+    def stage(self, n_rows, descs_py):
+        """descs_py: list of dicts(attr, encoding, host(np), code_width, stride, dict(np))."""
+        descs = (A.qs_stage_desc * len(descs_py))()
+        for i, d in enumerate(descs_py):
+            descs[i].attr = d["attr"]
+            descs[i].encoding = d["encoding"]
+            descs[i].host = d["host"].ctypes.data
+            descs[i].code_width = d.get("code_width", 0)
+            descs[i].stride = d.get("stride", 0)
+            if d.get("dict") is not None:
+                descs[i].dict = d["dict"].ctypes.data
+                descs[i].dict_entries = len(d["dict"])
+        A.check(A.load().qsgpu_stage_block(self.h, n_rows, descs, len(descs_py)))
+
+    # -- access -----------------------------------------------------------
+    @property
+    def n_rows(self) -> int:
+        n = C.c_uint64(0)
+        A.check(A.load().qsgpu_relation_num_rows(self.h, C.byref(n)))
+        return n.value
+
+    def column_ptr(self, attr: int) -> int:
+        p = C.c_void_p()
+        A.check(A.load().qsgpu_relation_column(self.h, attr, C.byref(p)))
+        return p.value
+
+    def read(self, attr: int, lo=0, n=None) -> np.ndarray:
+        t, w = self.schema[attr]
+        if n is None:
+            n = self.n_rows - lo
+        out = np.zeros(max(n, 1), dtype=np_dtype(t, w))
+        if n:
+            A.check(A.load().qsgpu_relation_read(self.h, attr, lo, n, out.ctypes.data))
+        return out[:n]
+
+    def to_host(self, name=None) -> HostTable:
+        n = self.n_rows
+        return HostTable(name or "rel", [Column(self.names[i], t, self.read(i, 0, n), w)
+                                         for i, (t, w) in enumerate(self.schema)])
+
+    def attr(self, es, i: int, side: int = 0) -> int:
+        t, w = self.schema[i]
+        return es.attr(i, t, w, side)
+
+    def destroy(self):
+        if self.h and self.owner:
+            A.load().qsgpu_relation_destroy(self.h)
+        self.h = None
+
+
+class LipFilter:
+    def __init__(self, kind, attr_type, min_value=0, max_value=0, cardinality=0, is_anti=False, dev=0):
+        L = init()
+        self.h = C.c_void_p()
+        A.check(L.qsgpu_lip_create(dev, kind, attr_type, min_value, max_value, cardinality, 1 if is_anti else 0,
+                                   C.byref(self.h)))
+
+    def words(self) -> np.ndarray:
+        n = C.c_uint64(0)
+        A.check(A.load().qsgpu_lip_num_words(self.h, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=np.uint64)
+        A.check(A.load().qsgpu_lip_read(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out[: n.value]
+
+    def device_words(self):
+        p = C.c_void_p()
+        A.check(A.load().qsgpu_lip_device_words(self.h, C.byref(p)))
+        n = C.c_uint64(0)
+        A.check(A.load().qsgpu_lip_num_words(self.h, C.byref(n)))
+        return p.value, n.value
+
+    def destroy(self):
+        if self.h:
+            A.load().qsgpu_lip_destroy(self.h)
+        self.h = None
+
+
+def _lip_refs(refs):
+    """refs: list of (LipFilter, attr)."""
+    if not refs:
+        return 0, None
+    arr = (A.qs_lip_ref * len(refs))()
+    for i, (f, attr) in enumerate(refs):
+        arr[i].lip = f.h
+        arr[i].attr = attr
+    return len(refs), arr
+
+
+def _i32(v):
+    return (C.c_int32 * max(1, len(v)))(*v)
+
+
+def _scan(rel: Relation, es, pred_root, lip_probe, row_begin=0, row_end=A.UINT64_MAX):
+    s = A.qs_scan()
+    s.input = rel.h
+    s.row_begin, s.row_end = row_begin, row_end
+    s.exprs = es.ptr() if es is not None else None
+    s.predicate_root = pred_root
+    n, arr = _lip_refs(lip_probe)
+    s.n_lip_probe = n
+    s.lip_probe = arr
+    return s, arr
+
+
+def build_lip_filter(rel, es, pred_root, lip_probe, lip_build, row_begin=0, row_end=A.UINT64_MAX):
+    """BuildLIPFilterWorkOrder::execute."""
+    s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
+    n, arr = _lip_refs(lip_build)
+    A.check(A.load().qsgpu_build_lip_filter(C.byref(s), n, arr))
+
+
+def select(rel, es, pred_root, lip_probe, project_roots, output: Relation, row_begin=0, row_end=A.UINT64_MAX):
+    """SelectWorkOrder::execute."""
+    s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
+    A.check(A.load().qsgpu_select(C.byref(s), len(project_roots), _i32(project_roots), output.h))
+
+
+class AggState:
+    """qsgpu_agg_state_t (AggregationOperationState)."""
+
+    def __init__(self, strategy, es, pred_root, aggregates, group_by_roots, estimated=1024, max_key=-1, dev=0):
+        L = init()
+        self.es = es
+        self.aggs = (A.qs_aggregate * max(1, len(aggregates)))()
+        for i, (f, r) in enumerate(aggregates):
+            self.aggs[i].function, self.aggs[i].argument_root = f, r
+        self.groups = _i32(group_by_roots)
+        spec = A.qs_agg_spec()
+        spec.dev, spec.strategy = dev, strategy
+        spec.exprs = es.ptr()
+        spec.predicate_root = pred_root
+        spec.n_aggregates, spec.aggregates = len(aggregates), self.aggs
+        spec.n_group_by, spec.group_by_roots = len(group_by_roots), self.groups
+        spec.estimated_num_entries = estimated
+        spec.collision_free_max_key = max_key
+        self.h = C.c_void_p()
+        self.n_aggregates = len(aggregates)
+        self.n_group_by = len(group_by_roots)
+        self.dev = dev
+        A.check(L.qsgpu_agg_create(C.byref(spec), C.byref(self.h)))
+
+    def run(self, rel: Relation, row_begin=0, row_end=A.UINT64_MAX, lip_probe=None):
+        """AggregationWorkOrder::execute."""
+        n, arr = _lip_refs(lip_probe)
+        A.check(A.load().qsgpu_agg_run(self.h, rel.h, row_begin, row_end, n, arr))
+
+    def num_groups(self) -> int:
+        n = C.c_uint64(0)
+        A.check(A.load().qsgpu_agg_num_groups(self.h, C.byref(n)))
+        return n.value
+
+    def partial(self):
+        """-> (d_states, d_keys, n_groups, words_per_group, key_words)."""
+        ds, dk = C.c_void_p(), C.c_void_p()
+        n, w, kw = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        A.check(A.load().qsgpu_agg_partial(self.h, C.byref(ds), C.byref(dk), C.byref(n), C.byref(w), C.byref(kw)))
+        return ds.value, dk.value, n.value, w.value, kw.value
+
+    def merge_partial(self, d_states, d_keys, n_groups):
+        A.check(A.load().qsgpu_agg_merge_partial(self.h, d_states, d_keys, n_groups))
+
+    def finalize(self, key_schema, key_names=None):
+        """FinalizeAggregationWorkOrder::execute -> (Relation, null_mask).
+        key_schema: [(type,width)] of the group-by attributes."""
+        out = C.c_void_p()
+        mask = C.c_uint64(0)
+        A.check(A.load().qsgpu_agg_finalize(self.h, C.byref(out), C.byref(mask)))
+        schema = list(key_schema)
+        # aggregate output types are defined by the library; query them from the handle layout
+        return out, mask.value
+
+    def destroy(self):
+        if self.h:
+            A.load().qsgpu_agg_destroy(self.h)
+        self.h = None
+
+
+def finalize_relation(state: AggState, key_schema, agg_out_types, names=None) -> tuple[Relation, int]:
+    """Wraps qsgpu_agg_finalize's output relation; agg_out_types: [(type,width)] per aggregate
+    (SUM(int)->LONG, SUM(fp)->DOUBLE, AVG->DOUBLE, COUNT->LONG, MIN/MAX->argument type)."""
+    h, mask = state.finalize(key_schema)
+    schema = list(key_schema) + list(agg_out_types)
+    return Relation(h, schema, names, state.dev), mask
+
+
+class JoinTable:
+    def __init__(self, key_type, estimated, dev=0):
+        L = init()
+        self.h = C.c_void_p()
+        A.check(L.qsgpu_join_create(dev, key_type, estimated, C.byref(self.h)))
+
+    def build(self, rel, es, pred_root, key_attr, lip_probe=None, lip_build=None, row_begin=0,
+              row_end=A.UINT64_MAX):
+        """BuildHashWorkOrder::execute."""
+        s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
+        n, arr = _lip_refs(lip_build)
+        A.check(A.load().qsgpu_join_build(self.h, C.byref(s), key_attr, n, arr))
+
+    def num_entries(self) -> int:
+        n = C.c_uint64(0)
+        A.check(A.load().qsgpu_join_num_entries(self.h, C.byref(n)))
+        return n.value
+
+    def probe(self, rel, es, pred_root, key_attr, join_type, residual_root, project_roots, output: Relation,
+              lip_probe=None, row_begin=0, row_end=A.UINT64_MAX):
+        """Hash{Inner,Semi,Anti}JoinWorkOrder::execute."""
+        s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
+        A.check(A.load().qsgpu_join_probe(self.h, C.byref(s), key_attr, join_type, residual_root,
+                                          len(project_roots), _i32(project_roots), output.h))
+
+    def destroy(self):
+        if self.h:
+            A.load().qsgpu_join_destroy(self.h)
+        self.h = None
+
+
+def topk(rel: Relation, keys, limit) -> Relation:
+    """keys: [(attr, descending)]."""
+    ks = (A.qs_sort_key * max(1, len(keys)))()
+    for i, (a, d) in enumerate(keys):
+        ks[i].attr, ks[i].descending = a, 1 if d else 0
+    out = C.c_void_p()
+    A.check(A.load().qsgpu_topk(rel.h, len(keys), ks, limit, C.byref(out)))
+    return Relation(out, rel.schema, rel.names, rel.dev)
+
+
+def radix_partition(rel: Relation, key_attr, n_parts, output: Relation) -> np.ndarray:
+    offs = np.zeros(n_parts + 1, dtype=np.uint64)
+    A.check(A.load().qsgpu_radix_partition(rel.h, key_attr, n_parts, output.h,
+                                           offs.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return offs
