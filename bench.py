@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H Q1 (headline, BASELINE.json configs[1]: Q1 at SF10) plus Q6 and Q3 on the same
+SF10-shaped synthetic relations, through the C-ABI of libqsgpu.so.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the CPU path (oracle port) on the host cores
+
+One "step" is one complete query: create the aggregation state, run the work orders over the
+device-resident relation(s), finalize, read the result rows back.  Weak scaling: every rank owns its
+own SF10-sized partition of lineitem (block partitioning per GPU); partial aggregation states are
+merged across ranks with an NCCL all-gather + the device merge kernel.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SF10_LINEITEM_ROWS = 59_986_052
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(int(f[0])); mx = max(mx, int(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_q1(O, OT, table, steps, warmup):
+    for _ in range(warmup):
+        OT.q1(table)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rows = OT.q1(table)
+    return (time.perf_counter() - t0) * 1e3 / steps, rows
+
+
+def numpy_lineitem(n, seed):
+    import tpch_data as D
+    from quickstep_b200 import tpch as T
+    from quickstep_b200.table import Column, HostTable
+    arrays, _ = D.synthetic_lineitem_arrays(n, seed)
+    return HostTable("lineitem", [Column(nm, t, arrays[nm], w) for (nm, t, w) in T.LINEITEM])
+
+
+def run_reference(args):
+    """The reference's CPU algorithm for the path (oracle port; the reference itself needs its CMake
+    build + un-vendored third-party libraries) on all host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import qs_oracle as O
+    import oracle_tpch as OT
+    cores = os.cpu_count() or 1
+    O.load()
+    O.set_workers(cores)
+    O.set_block_rows(63_000)               # ~ rows of one 4 MB lineitem block
+    n = args.cpu_sample_rows
+    table = numpy_lineitem(n, 11)
+    ms, _ = cpu_q1(O, OT, table, max(1, args.steps), max(1, min(args.warmup, 2)))
+    scaled = ms * (args.rows / n)
+    line = {
+        "impl": "reference", "metric": "tpch_q1_sf10_query_ms", "value": scaled, "unit": "ms", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)",
+                   "rows": args.rows},
+        "cpu_baseline": {"value": scaled, "unit": "ms", "cores": cores, "kind": "port",
+                         "sample": f"Q1 over {n} synthetic lineitem rows ({ms:.2f} ms/step, {cores} threads, 63k-row "
+                                   f"work orders), scaled x{args.rows / n:.2f} to {args.rows} rows"},
+        "e2e": {"value": scaled, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=SF10_LINEITEM_ROWS, help="lineitem rows per GPU")
+    ap.add_argument("--cpu-sample-rows", type=int, default=6_001_215)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--queries", default="q1,q6,q3")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from quickstep_b200 import capi as A
+    from quickstep_b200 import engine as E
+    from quickstep_b200 import synth as S
+    from quickstep_b200 import tpch as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    E.init([local])
+
+    def barrier():
+        E.synchronize(local)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ data (synthetic, in HBM)
+    n = args.rows
+    cols = S.generate(n, seed=1234 + rank, device=device, key_base=rank * (n // 4 + 8))
+    stats = cols.pop("_stats")
+    rels = S.wrap_relations(E, cols, local)
+    li = rels["lineitem"]
+    torch.cuda.synchronize()
+
+    q1p, q6p, q3p = T.Q1Plan(), T.Q6Plan(), T.Q3Plan()
+    gather_buf = {}
+
+    def merge_across_ranks(st):
+        """Partial aggregation states: all-gather over NCCL, merged by the device merge kernel."""
+        if world == 1:
+            return
+        ds, dk, ng, w, kw = st.partial()
+        cap = 256
+        row = w + kw
+        key = (w, kw)
+        if key not in gather_buf:
+            gather_buf[key] = (torch.zeros(1 + cap * row, dtype=torch.int64, device=device),
+                               torch.zeros(world * (1 + cap * row), dtype=torch.int64, device=device))
+        mine, allb = gather_buf[key]
+        mine.zero_()
+        mine[0] = ng
+        if ng:
+            E.memcpy_d2d(mine.data_ptr() + 8, ds, ng * w * 8, local)
+            E.memcpy_d2d(mine.data_ptr() + 8 + cap * w * 8, dk, ng * kw * 8, local)
+        torch.cuda.synchronize()
+        dist.all_gather_into_tensor(allb, mine)
+        torch.cuda.synchronize()
+        counts = allb.view(world, -1)[:, 0].tolist()
+        for r in range(world):
+            if r == rank or counts[r] == 0:
+                continue
+            base = allb.data_ptr() + r * (1 + cap * row) * 8
+            st.merge_partial(base + 8, base + 8 + cap * w * 8, int(counts[r]))
+
+    def step_q1(rel=li):
+        st = E.AggState(q1p.strategy, q1p.es, q1p.pred, q1p.aggregates, q1p.group_by, estimated=8, dev=local)
+        try:
+            st.run(rel)
+            merge_across_ranks(st)
+            fin, _ = E.finalize_relation(st, q1p.key_schema, [(A.QS_DOUBLE, 8)] * 5 + [(A.QS_LONG, 8)])
+            c = [fin.read(i) for i in range(8)]
+            fin.destroy()
+            return T.q1_rows_from_states(c[0], c[1], c[2:7], c[7])
+        finally:
+            st.destroy()
+
+    def step_q6(rel=li):
+        st = E.AggState(q6p.strategy, q6p.es, q6p.pred, q6p.aggregates, [], dev=local)
+        try:
+            st.run(rel)
+            merge_across_ranks(st)
+            fin, mask = E.finalize_relation(st, [], [(A.QS_DOUBLE, 8)])
+            v = float(fin.read(0)[0])
+            fin.destroy()
+            return v
+        finally:
+            st.destroy()
+
+    def step_q3():
+        top = T.run_q3(rels["customer"], rels["orders"], li, stats, q3p)
+        if world > 1:   # groups are disjoint per rank (lineitem is range-partitioned on l_orderkey): gather top-10s
+            t = torch.tensor([[r[0], r[1], r[2][0] * 10000 + r[2][1] * 100 + r[2][2], r[3]] for r in top] +
+                             [[0, -1.0, 0, 0]] * (10 - len(top)), dtype=torch.float64, device=device)
+            allt = torch.zeros(world * 10, 4, dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(allt, t)
+            rows = sorted(allt.tolist(), key=lambda r: (-r[1], r[2]))[:10]
+            return rows
+        return top
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        l0 = E.launch_count()
+        w0 = time.perf_counter()
+        E.timer_start(local)
+        for _ in range(steps):
+            out = step()
+        dev_ms = E.timer_stop(local)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        # device events bracket the library stream; host-side result reads are inside both clocks
+        return max_over_ranks(max(dev_ms, 0.0)) / steps, max_over_ranks(wall_ms) / steps, (E.launch_count() - l0), out
+
+    results, launches = {}, 0
+    want = args.queries.split(",")
+    with ClockSampler(local) as clk:
+        q1_ms, q1_wall, q1_launches, q1_rows = timed(step_q1, args.steps, args.warmup)
+        if "q6" in want:
+            results["q6"] = timed(step_q6, args.steps, args.warmup)
+        if "q3" in want:
+            results["q3"] = timed(step_q3, max(1, args.steps // 2), args.warmup)
+    clocks = clk.summary()
+
+    # ---- kernel-only time of the dominant kernel (scan+aggregate), CUDA events around the launch
+    def kernel_ms(plan, reps):
+        st = E.AggState(plan.strategy, plan.es, plan.pred, plan.aggregates, plan.group_by, estimated=8, dev=local)
+        E.set_timing(True)
+        xs = []
+        try:
+            for i in range(reps + 3):
+                st.run(li)
+                if i >= 3:
+                    xs.append(E.last_kernel_ms(A.QS_K_SCAN_AGG))
+        finally:
+            E.set_timing(False)
+            st.destroy()
+        return float(np.mean(xs))
+
+    peak, peak_src = measured_peak()
+    k_q1 = kernel_ms(q1p, args.steps)
+    k_q6 = kernel_ms(q6p, args.steps) if "q6" in want else None
+    q1_bytes = n * T.Q1_BYTES_PER_ROW
+    roofline = {"bound": "hbm", "kernel": "k_scan_agg<HOT=4,NAGG=6> (Q1 scan + group-by aggregation)",
+                "achieved": q1_bytes / (k_q1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": q1_bytes / (k_q1 * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "frac_of_nominal_8tbs": q1_bytes / (k_q1 * 1e-3) / 1e9 / 8000.0,
+                "kernel_ms": k_q1, "algorithmic_bytes": q1_bytes, "traffic": None}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            roofline["traffic"] = json.load(open(tpath)).get("q1_scan_agg_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers -> stage (H2D) -> query -> result rows (D2H), through the C-ABI
+    e2e = None
+    if not args.no_e2e:
+        q1_cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+        sub_schema = [(nm, t, w) for (nm, t, w) in T.LINEITEM if nm in q1_cols]
+        plan_e = T.Q1Plan(sub_schema)
+        host = []
+        for (nm, t, w) in sub_schema:
+            src = cols[nm].view(torch.uint8).reshape(-1) if cols[nm].dtype != torch.uint8 else cols[nm].reshape(-1)
+            pin = torch.empty(src.numel(), dtype=torch.uint8, pin_memory=True)
+            pin.copy_(src)
+            host.append(pin)
+        torch.cuda.synchronize()
+        h2d = sum(h.numel() for h in host)
+        stage_rel = E.Relation.create([(t, w) for (_n, t, w) in sub_schema], n, [nm for (nm, _t, _w) in sub_schema], local)
+        vdt = {1: "u1", 4: "<u4", 8: "<u8"}
+        np_host = [h.numpy().view(vdt[sub_schema[i][2]]) for i, h in enumerate(host)]
+        chunk = 1 << 22          # rows per staged batch of storage blocks
+
+        def step_e2e():
+            A.check(A.load().qsgpu_relation_set_num_rows(stage_rel.h, 0))
+            for lo in range(0, n, chunk):
+                hi = min(n, lo + chunk)
+                stage_rel.stage_plain([c[lo:hi] for c in np_host])
+            st = E.AggState(plan_e.strategy, plan_e.es, plan_e.pred, plan_e.aggregates, plan_e.group_by, estimated=8, dev=local)
+            try:
+                st.run(stage_rel)
+                merge_across_ranks(st)
+                fin, _ = E.finalize_relation(st, plan_e.key_schema, [(A.QS_DOUBLE, 8)] * 5 + [(A.QS_LONG, 8)])
+                c = [fin.read(i) for i in range(8)]
+                fin.destroy()
+                return T.q1_rows_from_states(c[0], c[1], c[2:7], c[7])
+            finally:
+                st.destroy()
+
+        e_steps = max(2, min(args.steps, 5))
+        e_ms, e_wall, _, e_rows = timed(step_e2e, e_steps, 1)
+        assert [r["count_order"] for r in e_rows] == [r["count_order"] for r in q1_rows]
+        d2h = 4 * 8 * 8
+        e2e = {"value": e_wall, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "device_ms": e_ms, "steps": e_steps,
+               "note": "qsgpu_stage_block from pinned host stripes (plain encoding) + Q1 + result read; wall clock"}
+        stage_rel.destroy()
+        del host, np_host
+
+    # ---- CPU baseline (oracle port) on the host cores, bounded sample, rank 0 at N=1
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import qs_oracle as O
+        import oracle_tpch as OT
+        cores = os.cpu_count() or 1
+        O.load(); O.set_workers(cores); O.set_block_rows(63_000)
+        ns = min(n, args.cpu_sample_rows)
+        sample = S.host_table(cols, T.LINEITEM, ns)
+        c_ms, c_rows = cpu_q1(O, OT, sample, 3, 1)
+        cpu = {"value": c_ms * (n / ns), "unit": "ms", "cores": cores, "kind": "port",
+               "sample": f"oracle Q1 over the first {ns} rows of the same relation: {c_ms:.2f} ms/step with {cores} "
+                         f"threads (63k-row work orders), scaled x{n / ns:.2f}"}
+        # parity spot check of the benchmarked path on that same prefix
+        chk = T.run_q1(li, row_ranges=[(0, ns)])
+        for a, b in zip(chk, c_rows):
+            assert a["count_order"] == b["count_order"], (a, b)
+            assert abs(a["sum_charge"] - b["sum_charge"]) <= 1e-9 * abs(b["sum_charge"]), (a, b)
+
+    if rank == 0:
+        line = {
+            "metric": "tpch_q1_sf10_query_ms", "value": q1_ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": q1_wall, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)",
+                       "rows_per_gpu": n, "total_rows": n * world, "partitioning": f"lineitem block-partitioned over {world} GPU(s)",
+                       "l2": "inputs (2.5 GB per GPU) larger than L2 (126 MB); no flush needed",
+                       "timing": "CUDA events on the library stream around K whole queries; max over ranks"},
+            "rows_per_s": n * world / (q1_ms * 1e-3),
+            "query_ms": {"q1": q1_ms, **{k: v[0] for k, v in results.items()}},
+            "query_wall_ms": {"q1": q1_wall, **{k: v[1] for k, v in results.items()}},
+            "kernel_ms": {"q1_scan_agg": k_q1, "q6_scan_agg": k_q6},
+            "hbm_frac": {"q1": roofline["frac"],
+                         "q6": (n * T.Q6_BYTES_PER_ROW / (k_q6 * 1e-3) / 1e9 / peak) if k_q6 else None},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": q1_launches,
+            "result_check": {"q1_groups": len(q1_rows), "q1_count": sum(r["count_order"] for r in q1_rows)},
+        }
+        print(json.dumps(line), flush=True)
+    for r in rels.values():
+        r.destroy()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,7 @@ int qsgpu_malloc(int dev, size_t bytes, void **dptr);
 int qsgpu_free(int dev, void *dptr);
 int qsgpu_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes);
 int qsgpu_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes);
+int qsgpu_memcpy_d2d(int dev, void *dst, const void *src, size_t bytes);
 /* Pinned host memory for staging buffers. */
 int qsgpu_host_alloc(size_t bytes, void **hptr);
 int qsgpu_host_free(void *hptr);
@@ -403,6 +404,10 @@ enum { QS_K_SCAN_AGG = 0, QS_K_SELECT = 1, QS_K_LIP = 2, QS_K_JOIN_BUILD = 3,
        QS_K_JOIN_PROBE = 4, QS_K_GROUPBY = 5, QS_K_PARTITION = 6, QS_K_TOPK = 7,
        QS_K_STAGE = 8, QS_K_FAMILIES = 9 };
 int qsgpu_set_timing(int enabled);
+/* CUDA events on the library's stream of `dev`: device time of everything
+ * queued between start and stop (bench.py's timed region). */
+int qsgpu_timer_start(int dev);
+int qsgpu_timer_stop(int dev, float *ms);
 int qsgpu_last_kernel_ms(uint32_t family, float *ms);
 
 #ifdef __cplusplus

@@ -103,6 +103,9 @@ SIGNATURES = {
     "qsgpu_free": (C.c_int, [C.c_int, _VP]),
     "qsgpu_memcpy_h2d": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
     "qsgpu_memcpy_d2h": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
+    "qsgpu_memcpy_d2d": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
+    "qsgpu_timer_start": (C.c_int, [C.c_int]),
+    "qsgpu_timer_stop": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "qsgpu_host_alloc": (C.c_int, [C.c_size_t, _VPP]),
     "qsgpu_host_free": (C.c_int, [_VP]),
     "qsgpu_relation_create": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), C.c_uint64, _VPP]),

@@ -69,7 +69,8 @@ struct Device {
   int sm_count = 148;
   size_t smem_per_sm = 0, smem_per_block_optin = 0;
   uint32_t *d_error = nullptr;        // sticky device-side error word
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // per-kernel-family timing
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // qsgpu_timer_start/stop
 };
 
 Device *device(int dev);               // nullptr (+ last error) when unavailable

@@ -46,6 +46,20 @@ def synchronize(dev=0):
     A.check(A.load().qsgpu_synchronize(dev))
 
 
+def timer_start(dev=0):
+    A.check(A.load().qsgpu_timer_start(dev))
+
+
+def timer_stop(dev=0) -> float:
+    ms = C.c_float(0)
+    A.check(A.load().qsgpu_timer_stop(dev, C.byref(ms)))
+    return ms.value
+
+
+def memcpy_d2d(dst_ptr: int, src_ptr: int, nbytes: int, dev=0):
+    A.check(A.load().qsgpu_memcpy_d2d(dev, dst_ptr, src_ptr, nbytes))
+
+
 def set_timing(on: bool):
     A.check(A.load().qsgpu_set_timing(1 if on else 0))
 

@@ -1,0 +1,121 @@
+"""Synthetic TPC-H-shaped relations generated directly in HBM with torch (bench harness only;
+there is no network for dbgen output at SF10+ and dbgen at SF10 takes minutes).
+
+Value domains and correlations follow dbgen (SURVEY.md section 8d "Data"):
+  orders:   o_orderkey sparse (8 used of every 32), o_orderdate uniform 1992-01-01..1998-08-02,
+            o_custkey in [1, n_cust] with custkey % 3 != 0, o_shippriority 0
+  lineitem: ~4 rows per order, sorted on l_orderkey; l_shipdate = o_orderdate + 1..121 days;
+            l_quantity 1..50; l_discount 0.00..0.10; l_tax 0.00..0.08;
+            l_extendedprice = quantity * retail price (900.00..2100.00), cents;
+            l_returnflag R/A if receipt date <= 1995-06-17 else N; l_linestatus O if shipped after
+            1995-06-17 else F
+  customer: c_custkey 1..n_cust, c_mktsegment uniform over the five segments
+DATE columns are Quickstep DateLit structs {int32 year; u8 month; u8 day; 2 pad} packed in int64.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi as A
+from . import tpch as T
+
+_EPOCH_1992 = 8035        # days from 1970-01-01 to 1992-01-01
+_CUTOFF = 9298            # 1995-06-17
+SEGMENTS = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"MACHINERY", b"HOUSEHOLD"]
+
+
+def datelit_from_days(days: torch.Tensor) -> torch.Tensor:
+    """days since 1970-01-01 (int64) -> packed DateLit (int64).  Civil-from-days, proleptic Gregorian."""
+    z = days + 719468
+    era = torch.div(z, 146097, rounding_mode="floor")
+    doe = z - era * 146097
+    yoe = torch.div(doe - torch.div(doe, 1460, rounding_mode="floor") + torch.div(doe, 36524, rounding_mode="floor")
+                    - torch.div(doe, 146096, rounding_mode="floor"), 365, rounding_mode="floor")
+    y = yoe + era * 400
+    doy = doe - (365 * yoe + torch.div(yoe, 4, rounding_mode="floor") - torch.div(yoe, 100, rounding_mode="floor"))
+    mp = torch.div(5 * doy + 2, 153, rounding_mode="floor")
+    d = doy - torch.div(153 * mp + 2, 5, rounding_mode="floor") + 1
+    m = torch.where(mp < 10, mp + 3, mp - 9)
+    y = y + (m <= 2).to(torch.int64)
+    return (y & 0xFFFFFFFF) | (m << 32) | (d << 40)
+
+
+def generate(n_lineitem: int, seed: int, device, key_base: int = 0):
+    """-> dict of torch tensors (device) for customer / orders / lineitem columns."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    ri = lambda lo, hi, n: torch.randint(lo, hi, (n,), generator=g, device=device, dtype=torch.int64)
+    n_orders = max(8, n_lineitem // 4)
+    n_cust = max(3, n_orders // 10)
+    out = {}
+    # ---- orders
+    dense = torch.arange(n_orders, device=device, dtype=torch.int64) + key_base
+    out["o_orderkey"] = ((((dense >> 3) << 5) | (dense & 7)) + 1).to(torch.int32)
+    ck = ri(0, (n_cust * 2) // 3, n_orders)
+    out["o_custkey"] = (ck + torch.div(ck, 2, rounding_mode="floor") + 1).clamp_(max=n_cust).to(torch.int32)  # skips multiples of 3
+    o_days = _EPOCH_1992 + ri(0, 2406, n_orders)
+    out["o_orderdate"] = datelit_from_days(o_days)
+    out["o_shippriority"] = torch.zeros(n_orders, device=device, dtype=torch.int32)
+    # ---- lineitem (sorted on l_orderkey)
+    oidx, _ = torch.sort(ri(0, n_orders, n_lineitem))
+    out["l_orderkey"] = out["o_orderkey"][oidx].contiguous()
+    ship = o_days[oidx] + ri(1, 122, n_lineitem)
+    del oidx
+    out["l_shipdate"] = datelit_from_days(ship)
+    receipt = ship + ri(1, 31, n_lineitem)
+    qty = ri(1, 51, n_lineitem)
+    out["l_quantity"] = qty.to(torch.float64)
+    cents = ri(90000, 210001, n_lineitem) * qty
+    out["l_extendedprice"] = cents.to(torch.float64) / 100.0
+    del cents, qty
+    out["l_discount"] = ri(0, 11, n_lineitem).to(torch.float64) / 100.0
+    out["l_tax"] = ri(0, 9, n_lineitem).to(torch.float64) / 100.0
+    ra = torch.where(ri(0, 2, n_lineitem) == 0, ord("R"), ord("A"))
+    out["l_returnflag"] = torch.where(receipt <= _CUTOFF, ra, torch.full_like(ra, ord("N"))).to(torch.uint8)
+    out["l_linestatus"] = torch.where(ship > _CUTOFF, ord("O"), ord("F")).to(torch.uint8)
+    del ra, receipt, ship
+    # ---- customer
+    out["c_custkey"] = torch.arange(1, n_cust + 1, device=device, dtype=torch.int32)
+    seg = torch.tensor([list(s.ljust(10, b"\0")) for s in SEGMENTS], dtype=torch.uint8, device=device)
+    out["c_mktsegment"] = seg[ri(0, 5, n_cust)].contiguous()       # [n_cust, 10] bytes
+    out["_stats"] = dict(c_custkey_min=1, c_custkey_max=n_cust,
+                         o_orderkey_min=int(out["o_orderkey"][0]), o_orderkey_max=int(out["o_orderkey"][-1]),
+                         orders_rows=n_orders, lineitem_rows=n_lineitem, customer_rows=n_cust,
+                         t2_estimate=n_orders // 2, groups_estimate=max(1024, n_orders // 8),
+                         t4_capacity=max(1024, n_lineitem // 4))
+    return out
+
+
+def _padded(t: torch.Tensor) -> torch.Tensor:
+    """Relations wrapped without a copy must be readable 16 bytes past the last row (qsgpu.h)."""
+    flat = t.reshape(-1).view(torch.uint8) if t.dtype != torch.uint8 else t.reshape(-1)
+    buf = torch.zeros(flat.numel() + 256, dtype=torch.uint8, device=t.device)
+    buf[: flat.numel()] = flat
+    return buf
+
+
+def wrap_relations(E, cols: dict, dev: int):
+    """Wrap the generated tensors as device relations (no copy besides tail padding)."""
+    rels, keep = {}, []
+    for name, schema in (("customer", T.CUSTOMER), ("orders", T.ORDERS), ("lineitem", T.LINEITEM)):
+        bufs = [_padded(cols[n]) for (n, _t, _w) in schema]
+        keep.append(bufs)
+        n_rows = cols[schema[0][0]].shape[0]
+        rels[name] = E.Relation.wrap([(t, w) for (_n, t, w) in schema], [b.data_ptr() for b in bufs], n_rows,
+                                     [n for (n, _t, _w) in schema], dev, keep=bufs)
+    return rels
+
+
+def host_table(cols: dict, schema, n: int | None = None):
+    """Host (numpy) copy of one relation's columns, for the CPU baseline and the e2e legs."""
+    from .table import Column, HostTable, DATE_DTYPE
+    out = []
+    for (name, t, w) in schema:
+        a = cols[name][:n] if n is not None else cols[name]
+        a = a.cpu().numpy()
+        if t == A.QS_DATE:
+            a = a.view(DATE_DTYPE)
+        elif t == A.QS_CHAR:
+            a = a.reshape(a.shape[0], -1).view(f"S{w}").reshape(-1)
+        out.append(Column(name, t, a, w))
+    return HostTable(schema[0][0].split("_")[0], out)

@@ -167,7 +167,7 @@ class GpuBackend:
             finally:
                 fin.destroy()
             if key_schema:
-                keys = np.concatenate([np.ascontiguousarray(k).view(np.uint8).reshape(n, -1) for k in kcols], axis=1)
+                keys = np.concatenate([np.ascontiguousarray(k).view(np.uint8).reshape(n, k.dtype.itemsize) for k in kcols], axis=1)
             else:
                 keys = np.zeros((n, 0), dtype=np.uint8)
             keys, vals = _sort_groups(keys, vals)
