@@ -96,6 +96,8 @@ class OracleBackend:
                 v = v.astype(np.int32)
             elif t == A.QS_FLOAT:
                 v = v.astype(np.float32)
+            if len(v) == 0:          # no groups: the oracle has no state to take the type from
+                v = v.astype(np_dtype(t, w))
             vals.append(v)
         mask = 0
         for j, nul in enumerate(r.is_null):
