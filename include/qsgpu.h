@@ -27,48 +27,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "qsgpu_types.h"   /* status codes and the reference's enum values */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
-
-/* ------------------------------------------------------------------ status */
-typedef enum qsgpu_status {
-  QSGPU_OK = 0,
-  QSGPU_ERR_NO_DEVICE = 1,      /* no CUDA device / init not called           */
-  QSGPU_ERR_CUDA = 2,           /* a CUDA runtime call failed                 */
-  QSGPU_ERR_INVALID = 3,        /* bad argument / malformed expression tree   */
-  QSGPU_ERR_UNSUPPORTED = 4,    /* valid in the reference, not lowered (yet)  */
-  QSGPU_ERR_CAPACITY = 5,       /* table / output relation capacity exceeded  */
-  QSGPU_ERR_OOM = 6
-} qsgpu_status;
-
 /* Thread-local text of the last error raised on the calling thread. */
 const char *qsgpu_last_error(void);
 
-/* ------------------------------------------------------------------- types */
-/* Values follow types/TypeID.hpp:33-45. */
-enum {
-  QS_INT = 0,      /* int32                                                    */
-  QS_LONG = 1,     /* int64                                                    */
-  QS_FLOAT = 2,    /* float                                                    */
-  QS_DOUBLE = 3,   /* double (SQL DECIMAL parses to this, SqlParser.ypp:791)   */
-  QS_CHAR = 4,     /* fixed width, NUL padded, strncmp order                   */
-  QS_VARCHAR = 5,  /* never staged on device (QSGPU_ERR_UNSUPPORTED)           */
-  QS_DATE = 6      /* DateLit {int32 year; u8 month; u8 day; 2 pad} = 8 bytes, */
-                   /* lexicographic order (types/DatetimeLit.hpp:38-93)        */
-};
-
-/* Comparison ids (types/operations/comparisons/ComparisonID.hpp). */
-enum { QS_EQ = 0, QS_NE = 1, QS_LT = 2, QS_LE = 3, QS_GT = 4, QS_GE = 5 };
-
-/* Binary operation ids (binary_operations/BinaryOperationID.hpp). */
-enum { QS_ADD = 0, QS_SUB = 1, QS_MUL = 2, QS_DIV = 3, QS_MOD = 4 };
-
-/* Unary operation ids used on the path. */
-enum { QS_NEGATE = 0, QS_CAST = 1 };
-
-/* Aggregate function ids (expressions/aggregation/AggregationID.hpp). */
-enum { QS_AGG_AVG = 0, QS_AGG_COUNT = 1, QS_AGG_MAX = 2, QS_AGG_MIN = 3, QS_AGG_SUM = 4 };
 
 /*
  * Flattened expression tree: serialization::Predicate and
@@ -219,7 +185,6 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows,
  * compared with (or handed to) the host structure bit for bit.
  */
 typedef struct qsgpu_lip *qsgpu_lip_t;
-enum { QS_LIP_BITVECTOR_EXACT = 0, QS_LIP_SINGLE_IDENTITY_HASH = 1 };
 
 int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type /*QS_INT|QS_LONG*/,
                      int64_t min_value, int64_t max_value, /* exact filter     */
@@ -287,12 +252,6 @@ int qsgpu_select(const qs_scan *scan, uint32_t n_project,
  *   QS_AGG_COLLISION_FREE   one INT/LONG key used as the array index
  *                                              (K7d; CollisionFreeVectorTable)
  */
-enum {
-  QS_AGG_SINGLE_STATE = 0,
-  QS_AGG_COMPACT_KEY = 1,
-  QS_AGG_SEPARATE_CHAINING = 2,
-  QS_AGG_COLLISION_FREE = 3
-};
 
 typedef struct qs_aggregate {
   uint32_t function;     /* QS_AGG_*                                           */
@@ -356,7 +315,6 @@ int qsgpu_agg_destroy(qsgpu_agg_state_t state);
  * attributes are gathered through it at probe time.
  */
 typedef struct qsgpu_join_table *qsgpu_join_table_t;
-enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };
 
 int qsgpu_join_create(int dev, uint32_t key_type /*QS_INT|QS_LONG*/,
                       uint64_t estimated_num_entries, qsgpu_join_table_t *out);
@@ -409,6 +367,25 @@ int qsgpu_set_timing(int enabled);
 int qsgpu_timer_start(int dev);
 int qsgpu_timer_stop(int dev, float *ms);
 int qsgpu_last_kernel_ms(uint32_t family, float *ms);
+
+
+/* ------------------------------------------------------------ query compiler */
+/*
+ * The scan kernels are compiled per query shape at first use (NVRTC, sm_100a)
+ * and cached in memory and under QSGPU_JIT_CACHE (default: jitcache/ next to
+ * the library).  qsgpu_jit_selfcheck compiles representative work order
+ * `which` (0..QSGPU_JIT_SELFCHECK_CASES-1: Q6-style single-state aggregate,
+ * Q1-style compact-key group-by, select with LIP probes, BuildLIPFilter, join
+ * build, inner probe with residual, anti probe, hash group-by, dense group-by)
+ * WITHOUT a device -- the "does every kernel family still compile" check of
+ * build() and the CPU test suite.  The generated CUDA source and the NVRTC log
+ * are copied into the optional buffers.
+ */
+#define QSGPU_JIT_SELFCHECK_CASES 9
+int qsgpu_jit_selfcheck(uint32_t which, char *source_out, size_t source_bytes,
+                        char *log_out, size_t log_bytes);
+/* NVRTC compilations / disk-cache hits / in-memory hits since load. */
+int qsgpu_jit_stats(uint64_t *compiled, uint64_t *disk_hits, uint64_t *mem_hits);
 
 #ifdef __cplusplus
 }

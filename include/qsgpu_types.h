@@ -1,0 +1,59 @@
+/*
+ * qsgpu_types.h -- constants shared by the C ABI (qsgpu.h), the host library
+ * and the device code of libqsgpu (this header is also what the query compiler
+ * hands to NVRTC, so it declares no functions).
+ */
+#ifndef QSGPU_TYPES_H_
+#define QSGPU_TYPES_H_
+
+/* ------------------------------------------------------------------ status */
+typedef enum qsgpu_status {
+  QSGPU_OK = 0,
+  QSGPU_ERR_NO_DEVICE = 1,      /* no CUDA device / init not called           */
+  QSGPU_ERR_CUDA = 2,           /* a CUDA runtime call failed                 */
+  QSGPU_ERR_INVALID = 3,        /* bad argument / malformed expression tree   */
+  QSGPU_ERR_UNSUPPORTED = 4,    /* valid in the reference, not lowered (yet)  */
+  QSGPU_ERR_CAPACITY = 5,       /* table / output relation capacity exceeded  */
+  QSGPU_ERR_OOM = 6
+} qsgpu_status;
+
+/* ------------------------------------------------------------------- types */
+/* Values follow types/TypeID.hpp:33-45. */
+enum {
+  QS_INT = 0,      /* int32                                                    */
+  QS_LONG = 1,     /* int64                                                    */
+  QS_FLOAT = 2,    /* float                                                    */
+  QS_DOUBLE = 3,   /* double (SQL DECIMAL parses to this, SqlParser.ypp:791)   */
+  QS_CHAR = 4,     /* fixed width, NUL padded, strncmp order                   */
+  QS_VARCHAR = 5,  /* never staged on device (QSGPU_ERR_UNSUPPORTED)           */
+  QS_DATE = 6      /* DateLit {int32 year; u8 month; u8 day; 2 pad} = 8 bytes, */
+                   /* lexicographic order (types/DatetimeLit.hpp:38-93)        */
+};
+
+/* Comparison ids (types/operations/comparisons/ComparisonID.hpp). */
+enum { QS_EQ = 0, QS_NE = 1, QS_LT = 2, QS_LE = 3, QS_GT = 4, QS_GE = 5 };
+
+/* Binary operation ids (binary_operations/BinaryOperationID.hpp). */
+enum { QS_ADD = 0, QS_SUB = 1, QS_MUL = 2, QS_DIV = 3, QS_MOD = 4 };
+
+/* Unary operation ids used on the path. */
+enum { QS_NEGATE = 0, QS_CAST = 1 };
+
+/* Aggregate function ids (expressions/aggregation/AggregationID.hpp). */
+enum { QS_AGG_AVG = 0, QS_AGG_COUNT = 1, QS_AGG_MAX = 2, QS_AGG_MIN = 3, QS_AGG_SUM = 4 };
+
+/* LIP filter kinds (utility/lip_filter/LIPFilter.proto:24-62). */
+enum { QS_LIP_BITVECTOR_EXACT = 0, QS_LIP_SINGLE_IDENTITY_HASH = 1 };
+
+/* Aggregation strategies (see qsgpu_agg_create in qsgpu.h). */
+enum {
+  QS_AGG_SINGLE_STATE = 0,
+  QS_AGG_COMPACT_KEY = 1,
+  QS_AGG_SEPARATE_CHAINING = 2,
+  QS_AGG_COLLISION_FREE = 3
+};
+
+/* Join types (relational_operators/HashJoinOperator.hpp:82-87). */
+enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };
+
+#endif  /* QSGPU_TYPES_H_ */

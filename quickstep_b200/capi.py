@@ -140,7 +140,10 @@ SIGNATURES = {
     "qsgpu_radix_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
+    "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }
+JIT_SELFCHECK_CASES = 9
 
 
 class QsGpuError(RuntimeError):

@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "qs_host.h"
+#include "qs_jit.h"
 #include "qs_lower.h"
 
 namespace qs {
@@ -16,6 +17,18 @@ static bool g_inited = false;
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<bool> g_timing{false};
 static thread_local std::string t_error;
+
+// qsgpu_jit_selfcheck: runs the real entry points on fake (host-only) handles
+// up to the point where the query kernel would be fetched, compiles the
+// generated source with NVRTC and stops.  No device is touched.
+struct SelfCheck {
+  Device dev;
+  std::string source, log;
+  bool reached = false, compiled = false;
+  uint32_t which = 0;
+};
+static thread_local SelfCheck *t_sc = nullptr;
+static constexpr int kSelfCheckStop = 1000;
 static thread_local float t_ms[QS_K_FAMILIES];
 
 void set_error(int status, const std::string &msg) {
@@ -35,6 +48,7 @@ bool timing_enabled() { return g_timing.load(); }
 void record_ms(uint32_t family, float ms) { if (family < QS_K_FAMILIES) t_ms[family] = ms; }
 
 Device *device(int dev) {
+  if (t_sc) return &t_sc->dev;
   if (!g_inited) {
     set_error(QSGPU_ERR_NO_DEVICE, "qsgpu_init has not been called (or found no CUDA device); there is no CPU fallback");
     return nullptr;
@@ -88,6 +102,7 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   if (n_stages > static_cast<uint32_t>(kMaxStages)) n_stages = kMaxStages;
   S->n_stages = n_stages;
   plan->smem = kBarBytes + static_cast<size_t>(n_stages) * stage + extra_smem + 64;
+  plan->ctas = ctas;
   int grid = d->sm_count * ctas;
   if (S->d_row_end == nullptr && S->n_tiles < static_cast<uint32_t>(grid)) grid = std::max<int>(1, S->n_tiles);
   plan->grid = grid;
@@ -105,6 +120,39 @@ static int check_device_error(Device *d) {
     return static_cast<int>(flag);
   }
   return QSGPU_OK;
+}
+
+// Fetches (compiling on first use) the kernel specialised for this work order.
+static int query_kernel(JitFamily fam, const ScanDesc &S, const Program &P, const ScanPlan &plan, const AggDesc *A,
+                        const SinkDesc *K, const JoinDesc *J, int hot, JitKernel **out) {
+  JitSpec sp;
+  sp.family = fam; sp.S = &S; sp.P = &P; sp.A = A; sp.K = K; sp.J = J; sp.hot = hot; sp.ctas_per_sm = plan.ctas;
+  if (t_sc) {
+    std::string cubin;
+    t_sc->reached = true;
+    t_sc->source = jit_source(sp);
+    t_sc->compiled = jit_compile_only(t_sc->source, &cubin, &t_sc->log) == QSGPU_OK;
+    if (const char *dir = std::getenv("QSGPU_JIT_DUMP")) {   // for cuobjdump / ptxas inspection
+      const std::string stem = std::string(dir) + "/selfcheck_" + std::to_string(t_sc->which);
+      if (FILE *f = std::fopen((stem + ".cu").c_str(), "wb")) { std::fwrite(t_sc->source.data(), 1, t_sc->source.size(), f); std::fclose(f); }
+      if (t_sc->compiled) if (FILE *f = std::fopen((stem + ".cubin").c_str(), "wb")) { std::fwrite(cubin.data(), 1, cubin.size(), f); std::fclose(f); }
+    }
+    return kSelfCheckStop;
+  }
+  return jit_get(sp, out);
+}
+
+static cudaError_t launch_query_kernel(Device *d, JitKernel *k, const ScanDesc &S, const Program &P,
+                                       const ScanPlan &plan, const AggDesc *A, const SinkDesc *K,
+                                       const JoinDesc *J) {
+  void *args[5];
+  int n = 0;
+  args[n++] = const_cast<ScanDesc *>(&S);
+  args[n++] = const_cast<Lits *>(&P.L);
+  if (A) args[n++] = const_cast<AggDesc *>(A);
+  if (K) args[n++] = const_cast<SinkDesc *>(K);
+  if (J) args[n++] = const_cast<JoinDesc *>(J);
+  return jit_launch(k, plan.grid, plan.smem, d->stream, args);
 }
 
 static int sync_rows(qsgpu_relation *rel) {
@@ -602,8 +650,11 @@ int qsgpu_build_lip_filter(const qs_scan *scan, uint32_t n_build, const qs_lip_r
   ScanPlan plan;
   st = plan_scan(d, &S, kCompactSmemBytes, &plan);
   if (st) return st;
+  JitKernel *kern = nullptr;
+  st = query_kernel(JF_SELECT, S, L.P, plan, nullptr, &K, nullptr, 1, &kern);
+  if (st) return st;
   KernelTimer timer(d, QS_K_LIP);
-  QS_CUDA(launch_scan_select(S, L.P, K, plan.grid, plan.smem, d->stream));
+  QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, nullptr, &K, nullptr));
   count_launch();
   return QSGPU_OK;
 }
@@ -629,8 +680,11 @@ int qsgpu_select(const qs_scan *scan, uint32_t n_project, const int32_t *project
   ScanPlan plan;
   st = plan_scan(d, &S, kCompactSmemBytes, &plan);
   if (st) return st;
+  JitKernel *kern = nullptr;
+  st = query_kernel(JF_SELECT, S, L.P, plan, nullptr, &K, nullptr, 1, &kern);
+  if (st) return st;
   KernelTimer timer(d, QS_K_SELECT);
-  QS_CUDA(launch_scan_select(S, L.P, K, plan.grid, plan.smem, d->stream));
+  QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, nullptr, &K, nullptr));
   count_launch();
   output->dirty = true;
   return QSGPU_OK;
@@ -733,6 +787,7 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     default: set_error(QSGPU_ERR_INVALID, "unknown aggregation strategy"); return QSGPU_ERR_INVALID;
   }
 
+  if (t_sc) { *out = s.release(); return QSGPU_OK; }   // selfcheck: description only, no device memory
   QS_CUDA(cudaMalloc(&A.n_groups, 256));
   QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 256, d->stream));
   QS_CUDA(cudaMalloc(&s->d_done, 256));
@@ -844,19 +899,21 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
   if (st) return st;
   ScanPlan plan;
   if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
-    int hot, nt;
-    agg_template_shape(A, &hot, &nt);
-    st = plan_scan(d, &S, agg_smem_extra(hot, nt, A.n_key_cols > 0, A.words), &plan);
+    const int hot = agg_hot_groups(A);
+    st = plan_scan(d, &S, agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words), &plan);
     if (st) return st;
     if (static_cast<uint32_t>(plan.grid) > state->max_ctas) plan.grid = static_cast<int>(state->max_ctas);
+    JitKernel *kern = nullptr;
+    st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern);
+    if (st) return st;
     {
       KernelTimer timer(d, QS_K_SCAN_AGG);      // the scan kernel alone (roofline numerator)
-      QS_CUDA(launch_scan_agg(S, L.P, A, plan.grid, plan.smem, d->stream));
+      QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, &A, nullptr, nullptr));
     }
     QS_CUDA(launch_merge_partials(A, static_cast<uint32_t>(plan.grid), d->stream));
     count_launch(2);
   } else {
-    if (state->strategy == QS_AGG_SEPARATE_CHAINING) {
+    if (state->strategy == QS_AGG_SEPARATE_CHAINING && !t_sc) {
       uint64_t rows = (row_end == UINT64_MAX ? input->capacity : row_end) - row_begin;
       if (!input->dirty) rows = std::min<uint64_t>(rows, input->host_rows);
       st = maybe_grow(state, d, rows);
@@ -865,8 +922,11 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     }
     st = plan_scan(d, &S, 0, &plan);
     if (st) return st;
+    JitKernel *kern = nullptr;
+    st = query_kernel(JF_GROUPBY, S, L.P, plan, &A, nullptr, nullptr, 1, &kern);
+    if (st) return st;
     KernelTimer timer(d, QS_K_GROUPBY);
-    QS_CUDA(launch_scan_groupby(S, L.P, A, plan.grid, plan.smem, d->stream));
+    QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, &A, nullptr, nullptr));
     count_launch();
   }
   return QSGPU_OK;
@@ -1078,8 +1138,11 @@ int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan, uint32_t key
   ScanPlan plan;
   st = plan_scan(d, &S, 0, &plan);
   if (st) return st;
+  JitKernel *kern = nullptr;
+  st = query_kernel(JF_JOIN_BUILD, S, L.P, plan, nullptr, &K, &J, 1, &kern);
+  if (st) return st;
   KernelTimer timer(d, QS_K_JOIN_BUILD);
-  QS_CUDA(launch_join_build(S, L.P, K, J, plan.grid, plan.smem, d->stream));
+  QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, nullptr, &K, &J));
   count_launch();
   return QSGPU_OK;
 }
@@ -1135,8 +1198,11 @@ int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t pr
   ScanPlan plan;
   st = plan_scan(d, &S, kCompactSmemBytes, &plan);
   if (st) return st;
+  JitKernel *kern = nullptr;
+  st = query_kernel(JF_JOIN_PROBE, S, L.P, plan, nullptr, &K, &J, 1, &kern);
+  if (st) return st;
   KernelTimer timer(d, QS_K_JOIN_PROBE);
-  QS_CUDA(launch_join_probe(S, L.P, K, J, plan.grid, plan.smem, d->stream));
+  QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, nullptr, &K, &J));
   count_launch();
   output->dirty = true;
   return QSGPU_OK;
@@ -1153,3 +1219,14 @@ int qsgpu_join_destroy(qsgpu_join_table_t t) {
 }
 
 }  // extern "C"
+
+#include "qs_selfcheck.inc"
+
+extern "C" int qsgpu_jit_stats(uint64_t *compiled, uint64_t *disk_hits, uint64_t *mem_hits) {
+  uint64_t a = 0, b = 0, c = 0;
+  qs::jit_stats(&a, &b, &c);
+  if (compiled) *compiled = a;
+  if (disk_hits) *disk_hits = b;
+  if (mem_hits) *mem_hits = c;
+  return QSGPU_OK;
+}

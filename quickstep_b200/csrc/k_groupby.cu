@@ -1,4 +1,5 @@
-// K7: hash and dense GROUP BY aggregation over a global table, plus finalize.
+// K7: fixed kernels of the hash / dense GROUP BY path (rehash, foreign merge, slot
+// collection, finalize); the scan kernel is qs_kernels.cuh scan_groupby_body.
 //
 //   generic keys (<= 32 B)  PackedPayloadHashTable::upsertValueAccessorCompositeKeyInternal
 //                           (storage/PackedPayloadHashTable.hpp:780-909)  -- the
@@ -12,122 +13,28 @@
 //   finalize                AggregationOperationState::finalizeAggregate
 //                           (storage/AggregationOperationState.cpp:641-948),
 //                           AggregationHandleAvg::finalize (AggregationHandleAvg.cpp:144-155)
-#include "qs_ops.cuh"
-#include "qs_vm.cuh"
+#include "qs_kernels.cuh"
 
 namespace qs {
 
 __device__ __forceinline__ void global_update(uint8_t kind, uint64_t *p, uint64_t v) {
   switch (kind) {
-    case AK_SUM_F64: atomicAdd(reinterpret_cast<double *>(p), u2d(v)); break;
-    case AK_SUM_I64: atomicAdd(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v)); break;
-    case AK_MIN_I64: atomicMin(reinterpret_cast<long long *>(p), static_cast<long long>(v)); break;
-    case AK_MAX_I64: atomicMax(reinterpret_cast<long long *>(p), static_cast<long long>(v)); break;
-    default: {
-      unsigned long long *q = reinterpret_cast<unsigned long long *>(p);
-      unsigned long long old = *q;
-      while (true) {
-        const uint64_t want = agg_combine(kind, old, v);
-        if (want == old) break;
-        const unsigned long long seen = atomicCAS(q, old, static_cast<unsigned long long>(want));
-        if (seen == old) break;
-        old = seen;
-      }
-    }
+    case AK_SUM_F64: atomic_update<AK_SUM_F64>(p, v); break;
+    case AK_SUM_I64: atomic_update<AK_SUM_I64>(p, v); break;
+    case AK_MIN_I64: atomic_update<AK_MIN_I64>(p, v); break;
+    case AK_MAX_I64: atomic_update<AK_MAX_I64>(p, v); break;
+    case AK_MIN_F64: atomic_update<AK_MIN_F64>(p, v); break;
+    default: atomic_update<AK_MAX_F64>(p, v); break;
   }
 }
 
-// Find-or-insert `key` (kw words); returns the slot or -1 when the table is full.
-__device__ __forceinline__ int64_t table_upsert(const uint64_t *key, uint32_t kw, const AggDesc &A) {
-  uint64_t h = 0x9e3779b97f4a7c15ull;
-  for (uint32_t i = 0; i < kw; ++i) h = mix64(h ^ key[i]);
-  const uint64_t mask = A.cap - 1;
-  uint64_t slot = h & mask;
-  volatile uint32_t *tags = A.tags;
-  volatile uint64_t *keys = A.keys;
-  for (uint64_t probes = 0; probes <= mask;) {
-    const uint32_t t = tags[slot];
-    if (t == 2u) {
-      bool eq = true;
-      for (uint32_t i = 0; i < kw; ++i) eq &= keys[slot * kw + i] == key[i];
-      if (eq) return static_cast<int64_t>(slot);
-      slot = (slot + 1) & mask;
-      ++probes;
-      continue;
-    }
-    if (t == 0u && atomicCAS(&A.tags[slot], 0u, 1u) == 0u) {
-      for (uint32_t i = 0; i < kw; ++i) keys[slot * kw + i] = key[i];
-      __threadfence();
-      tags[slot] = 2u;
-      atomicAdd(A.n_groups, 1u);
-      return static_cast<int64_t>(slot);
-    }
-    // busy (or lost the race): look at the same slot again
+__device__ __forceinline__ int64_t table_upsert_rt(const uint64_t *key, uint32_t kw, const AggDesc &A) {
+  switch (kw) {
+    case 1: return table_upsert<1>(key, A);
+    case 2: return table_upsert<2>(key, A);
+    case 3: return table_upsert<3>(key, A);
+    default: return table_upsert<4>(key, A);
   }
-  atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-  return -1;
-}
-
-struct GlobalAggSink : SinkBase {
-  int64_t slot[kRows];
-  const AggDesc *A;
-  __device__ __forceinline__ void emit(uint32_t j, uint8_t, const uint64_t (&acc)[kRows]) {
-    const uint8_t kind = A->kind[j];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r)
-      if (slot[r] >= 0) global_update(kind, &A->states[slot[r] * A->words + 1 + j], acc[r]);
-  }
-};
-
-__global__ void __launch_bounds__(kBlock, 2)
-k_scan_groupby(const __grid_constant__ ScanDesc S, const __grid_constant__ Program P,
-               const __grid_constant__ AggDesc A) {
-  extern __shared__ __align__(128) char smem[];
-  const int tid = threadIdx.x;
-  GlobalAggSink sink;
-  sink.A = &A;
-  VmRegs regs;
-  scan_tiles(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
-    bool valid[kRows];
-    tile_valid(S, rt, tile, tid, valid);
-    uint32_t bits[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
-    SinkBase ns;
-    vm_run(P, 0, P.n_pred, S, stage, tid, regs, bits, ns);
-    bool any = false;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const bool pass = valid[r] && (bits[r] & 1u);
-      sink.slot[r] = -1;
-      if (pass) {
-        if (A.strategy == QS_AGG_COLLISION_FREE) {
-          const uint32_t w = A.key_width[0];
-          const char *src = stage + S.cols[A.key_col[0]].smem_off + tile_row(r, tid) * w;
-          const int64_t k = w == 4 ? static_cast<int64_t>(*reinterpret_cast<const int32_t *>(src))
-                                   : *reinterpret_cast<const int64_t *>(src);
-          if (k >= 0 && static_cast<uint64_t>(k) < A.cap) sink.slot[r] = k;
-          else atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-        } else {
-          uint64_t key[kMaxKeyWords] = {0, 0, 0, 0};
-          for (uint32_t k = 0; k < A.n_key_cols; ++k) {
-            const uint32_t w = A.key_width[k];
-            const char *src = stage + S.cols[A.key_col[k]].smem_off + tile_row(r, tid) * w;
-            for (uint32_t b = 0; b < w; ++b) {
-              const uint32_t pos = A.key_off[k] + b;
-              key[pos >> 3] |= static_cast<uint64_t>(static_cast<unsigned char>(src[b])) << (8 * (pos & 7));
-            }
-          }
-          sink.slot[r] = table_upsert(key, A.key_words, A);
-        }
-        if (sink.slot[r] >= 0)
-          atomicAdd(reinterpret_cast<unsigned long long *>(&A.states[sink.slot[r] * A.words]), 1ull);
-      }
-      any |= sink.slot[r] >= 0;
-    }
-    if (!__any_sync(0xffffffffu, any)) return;
-    vm_run(P, P.n_mid, P.n_total, S, stage, tid, regs, bits, sink);
-  });
 }
 
 // Rehash every ready slot of `from` into `to` (table growth between work orders).
@@ -137,7 +44,7 @@ __global__ void k_rehash(const __grid_constant__ AggDesc from, const __grid_cons
     if (from.tags[s] != 2u) continue;
     uint64_t key[kMaxKeyWords];
     for (uint32_t i = 0; i < from.key_words; ++i) key[i] = from.keys[s * from.key_words + i];
-    const int64_t d = table_upsert(key, from.key_words, to);
+    const int64_t d = table_upsert_rt(key, from.key_words, to);
     if (d < 0) continue;
     for (uint32_t w = 0; w < from.words; ++w) to.states[d * to.words + w] = from.states[s * from.words + w];
   }
@@ -156,7 +63,7 @@ __global__ void k_merge_foreign_table(const __grid_constant__ AggDesc A, const u
     } else {
       uint64_t key[kMaxKeyWords];
       for (uint32_t i = 0; i < A.key_words; ++i) key[i] = f_keys[g * A.key_words + i];
-      slot = table_upsert(key, A.key_words, A);
+      slot = table_upsert_rt(key, A.key_words, A);
       if (slot < 0) continue;
     }
     for (uint32_t w = 0; w < A.words; ++w) {
@@ -237,15 +144,6 @@ __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t launch_scan_groupby(const ScanDesc &S, const Program &P, const AggDesc &A, int grid, size_t smem,
-                                cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_scan_groupby, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  k_scan_groupby<<<grid, kBlock, smem, st>>>(S, P, A);
-  return cudaGetLastError();
-}
-
 static int grid_for(uint64_t n, int block) {
   uint64_t g = (n + block - 1) / block;
   if (g > 148ull * 16) g = 148ull * 16;

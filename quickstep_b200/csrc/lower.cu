@@ -96,9 +96,10 @@ void Lowering::push(Instr in) {
 }
 
 int Lowering::add_lit(uint64_t v) {
-  for (uint32_t i = 0; i < n_lits; ++i) if (P.lits[i] == v) return static_cast<int>(i);
+  // no de-duplication by value: the instruction stream (= the compiled kernel's identity)
+  // must not depend on literal values
   if (n_lits >= static_cast<uint32_t>(kMaxLits)) { fail(QSGPU_ERR_UNSUPPORTED, "too many literals"); return 0; }
-  P.lits[n_lits] = v;
+  P.L.lits[n_lits] = v;
   return static_cast<int>(n_lits++);
 }
 
@@ -319,7 +320,7 @@ void Lowering::lower_pred(int i) {
         if (n_str + w > static_cast<uint32_t>(kStrPool)) { fail(QSGPU_ERR_UNSUPPORTED, "string pool full"); return; }
         const uint32_t off = n_str;
         for (uint32_t b = 0; b < w; ++b)
-          P.str_pool[off + b] = b < lit->width ? ex->str_pool[lit->lit.pool_offset + b] : 0;
+          P.L.str_pool[off + b] = b < lit->width ? ex->str_pool[lit->lit.pool_offset + b] : 0;
         n_str += w;
         in.op = OP_CMP_CHAR;
         in.arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(attr->a)));

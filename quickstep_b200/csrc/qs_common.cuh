@@ -4,10 +4,13 @@
 // mbarrier + bulk-copy (TMA, SASS UBLKCP) pipeline every scan kernel uses.
 #pragma once
 
+// Under NVRTC (the query compiler, qs_jit.cu) the three includes below resolve
+// to the minimal stand-ins the JIT embeds, so this header and everything that
+// builds on it compile without a CUDA toolkit tree at run time.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "qsgpu.h"
+#include "qsgpu_types.h"
 
 namespace qs {
 
@@ -64,14 +67,22 @@ struct Instr {          // 8 bytes
   uint8_t aux;          // comparison id / cvt target / char width low bits
 };
 
+// Host-side result of lowering.  The instruction stream is a COMPILE-TIME
+// constant of the kernel the query compiler instantiates for it (qs_jit.cu);
+// only the literal values travel as a kernel argument (Lits), so the same
+// kernel serves every query of the same shape.
+struct Lits {
+  uint64_t lits[kMaxLits];
+  char str_pool[kStrPool];
+};
+
 struct Program {
   uint32_t n_pred;      // code[0,n_pred): predicate section (bit-stack result)
   uint32_t n_mid;       // code[n_pred,n_mid): join residual predicate (else == n_pred)
   uint32_t n_total;     // code[n_mid,n_total): emit section
   uint32_t pad;
   Instr code[kMaxInstr];
-  uint64_t lits[kMaxLits];
-  char str_pool[kStrPool];
+  Lits L;
 };
 
 struct ColDesc {
@@ -161,16 +172,21 @@ __device__ __forceinline__ void bv_set(uint64_t *words, uint64_t bit) {
            0x8000000000000000ull >> (bit & 63));
 }
 
+// KIND / ANTI are compile-time properties of the kernel (Q::lip_kind); bounds,
+// cardinality and the bit words are run-time.
+template <uint32_t KIND, uint32_t ANTI>
 __device__ __forceinline__ bool lip_contains(const LipDesc &f, int64_t v) {
-  if (f.kind == QS_LIP_BITVECTOR_EXACT) {
-    if (v < f.min_value || v > f.max_value) return f.is_anti != 0;
+  if constexpr (KIND == QS_LIP_BITVECTOR_EXACT) {
+    if (v < f.min_value || v > f.max_value) return ANTI != 0;
     const bool set = bv_get(f.words, static_cast<uint64_t>(v - f.min_value));
-    return f.is_anti ? !set : set;
+    return ANTI ? !set : set;
+  } else {
+    return bv_get(f.words, static_cast<uint64_t>(v) % f.cardinality);
   }
-  return bv_get(f.words, static_cast<uint64_t>(v) % f.cardinality);
 }
+template <uint32_t KIND>
 __device__ __forceinline__ void lip_insert(const LipDesc &f, int64_t v) {
-  if (f.kind == QS_LIP_BITVECTOR_EXACT) {
+  if constexpr (KIND == QS_LIP_BITVECTOR_EXACT) {
     if (v < f.min_value || v > f.max_value) return;   // DCHECK in the reference
     bv_set(f.words, static_cast<uint64_t>(v - f.min_value));
   } else {

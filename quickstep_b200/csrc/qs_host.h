@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "qs_ops.cuh"
+#include "qsgpu.h"
 
 struct qsgpu_relation {
   int dev = 0;
@@ -83,6 +84,7 @@ void record_ms(uint32_t family, float ms);
 // Launch geometry for a scan over `n_cols` staged columns.
 struct ScanPlan {
   int grid = 0;
+  int ctas = 2;        // resident CTAs per SM the shared-memory budget allows
   size_t smem = 0;
 };
 int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan);

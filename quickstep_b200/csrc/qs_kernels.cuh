@@ -1,0 +1,710 @@
+// The five scan-kernel families of libqsgpu, as templates over a compile-time
+// query description Q (printed by the query compiler, qs_jit.cu):
+//
+//   scan_agg_body      K1 / K2  predicate scan + aggregation, no / compact GROUP BY
+//                      AggregationOperationState::aggregateBlockSingleState
+//                        (storage/AggregationOperationState.cpp:476-519)
+//                      ThreadPrivateCompactKeyHashTable::upsertValueAccessorCompositeKey
+//                        (storage/ThreadPrivateCompactKeyHashTable.cpp:203-363)
+//   scan_groupby_body  K7       hash / dense GROUP BY over a global table
+//                      PackedPayloadHashTable (storage/PackedPayloadHashTable.hpp:780-909)
+//                      CollisionFreeVectorTable (storage/CollisionFreeVectorTable.hpp:530-645)
+//   scan_select_body   K3 / K4  Select and BuildLIPFilter
+//                      SelectWorkOrder::execute (relational_operators/SelectOperator.cpp:161-195)
+//                      BuildLIPFilterWorkOrder::execute (…/BuildLIPFilterOperator.cpp:146-172)
+//   join_build_body    K5       BuildHashWorkOrder::execute (…/BuildHashOperator.cpp:162-207)
+//   join_probe_body    K6       HashInnerJoin / Semi / Anti (…/HashJoinOperator.cpp:450-987)
+//
+// Common skeleton: one persistent CTA pair per SM; column tiles arrive in
+// shared memory through the TMA bulk-copy ring (qs_vm.cuh scan_tiles); the
+// compile-time VM evaluates predicates and expressions in registers.
+//
+// Q provides (all static constexpr):
+//   n_cols n_stages stage_bytes col_w(c) col_off(c)        staged columns / ring
+//   n_pred n_mid n_total code(pc)                          the program
+//   lip_kind(i) lip_anti(i)                                LIP filters probed
+//   n_agg words hot grouped strategy n_key_cols key_words  aggregation
+//   agg_kind(j) key_col(k) key_w(k) key_off(k)
+//   n_out out_w(j) n_lip_build lb_col(i) lb_ltype(i) lb_kind(i)   output side
+//   j_key_col j_key_ltype j_type build_w(c)                join
+#pragma once
+
+#include "qs_compact.cuh"
+#include "qs_ops.cuh"
+#include "qs_vm.cuh"
+
+namespace qs {
+
+// ------------------------------------------------------------ small helpers
+template <uint32_t W>
+__device__ __forceinline__ uint64_t load_bytes(const char *p) {
+  if constexpr (W == 1) return static_cast<uint64_t>(*reinterpret_cast<const unsigned char *>(p));
+  else if constexpr (W == 2) return static_cast<uint64_t>(*reinterpret_cast<const uint16_t *>(p));
+  else if constexpr (W == 4) return static_cast<uint64_t>(*reinterpret_cast<const uint32_t *>(p));
+  else if constexpr (W == 8) return *reinterpret_cast<const uint64_t *>(p);
+  else {
+    static_assert(W < 8, "wide values are copied, not loaded");
+    uint64_t v = 0;
+#pragma unroll
+    for (uint32_t b = 0; b < W; ++b) v |= static_cast<uint64_t>(static_cast<unsigned char>(p[b])) << (8 * b);
+    return v;
+  }
+}
+
+template <uint32_t W>
+__device__ __forceinline__ void copy_value(char *dst, const char *src) {
+  if constexpr (W == 8) *reinterpret_cast<uint64_t *>(dst) = *reinterpret_cast<const uint64_t *>(src);
+  else if constexpr (W == 4) *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
+  else if constexpr (W == 2) *reinterpret_cast<uint16_t *>(dst) = *reinterpret_cast<const uint16_t *>(src);
+  else {
+#pragma unroll
+    for (uint32_t b = 0; b < W; ++b) dst[b] = src[b];
+  }
+}
+
+// Group key of one row, packed like ThreadPrivateCompactKeyHashTable::ConstructKeyCode
+// (storage/ThreadPrivateCompactKeyHashTable.hpp:125-142): key i is memcpy'd at
+// byte offset sum(widths of keys < i) of a zeroed word array.
+template <class Q>
+__device__ __forceinline__ void pack_key(const char *stage, uint32_t row, uint64_t (&key)[kMaxKeyWords]) {
+#pragma unroll
+  for (int i = 0; i < kMaxKeyWords; ++i) key[i] = 0;
+  static_for<0, Q::n_key_cols>([&](auto kk) {
+    constexpr int k = QS_IDX(kk);
+    constexpr uint32_t w = Q::key_w(k), off = Q::key_off(k);
+    const char *src = stage + Q::col_off(Q::key_col(k)) + row * w;
+    if constexpr (w <= 8 && (w == 1 || w == 2 || w == 4 || w == 8 || (off & 7) + w <= 8)) {
+      const uint64_t v = load_bytes<w>(src);
+      constexpr uint32_t sh = 8 * (off & 7);
+      key[off >> 3] |= v << sh;
+      if constexpr ((off & 7) + w > 8) key[(off >> 3) + 1] |= v >> (64 - sh);
+    } else {
+#pragma unroll
+      for (uint32_t b = 0; b < w; ++b) {
+        constexpr uint32_t base = off;
+        const uint32_t pos = base + b;
+        key[pos >> 3] |= static_cast<uint64_t>(static_cast<unsigned char>(src[b])) << (8 * (pos & 7));
+      }
+    }
+  });
+}
+
+template <uint8_t KIND>
+__device__ __forceinline__ void atomic_update(uint64_t *p, uint64_t v) {
+  if constexpr (KIND == AK_SUM_F64) atomicAdd(reinterpret_cast<double *>(p), u2d(v));
+  else if constexpr (KIND == AK_SUM_I64) atomicAdd(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
+  else if constexpr (KIND == AK_MIN_I64) atomicMin(reinterpret_cast<long long *>(p), static_cast<long long>(v));
+  else if constexpr (KIND == AK_MAX_I64) atomicMax(reinterpret_cast<long long *>(p), static_cast<long long>(v));
+  else {   // MIN/MAX over doubles: CAS loop
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(p);
+    unsigned long long old = *q;
+    while (true) {
+      const uint64_t want = agg_combine(KIND, old, v);
+      if (want == old) break;
+      const unsigned long long seen = atomicCAS(q, old, static_cast<unsigned long long>(want));
+      if (seen == old) break;
+      old = seen;
+    }
+  }
+}
+
+// =========================================================== K1 / K2  scan_agg
+struct AggSmem {
+  uint64_t *red;         // [8 warps][HOT*(NA+1)]
+  uint64_t *lstate;      // [LG][words]
+  uint64_t *lkey_by_id;  // [LG]
+  uint64_t *lkeys;       // [LS]
+  int *lslot;            // [LS]
+  uint32_t *lready;      // [LG]  1 once lkey_by_id[id] is published
+  uint32_t *nlocal;
+};
+
+template <class Q>
+struct AggSink : SinkBase {
+  static constexpr int HOT = Q::hot;
+  static constexpr int NA = Q::n_agg > 0 ? Q::n_agg : 1;
+  uint64_t hv[HOT][NA];
+  uint32_t hc[HOT];
+  int slot[kRows];
+  uint64_t *lstate;
+
+  template <int J, int TYPE>
+  __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
+    constexpr uint8_t kind = Q::agg_kind(J);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+      for (int g = 0; g < HOT; ++g)
+        if (slot[r] == g) hv[g][J] = agg_combine(kind, hv[g][J], acc[r]);
+    }
+    if constexpr (Q::grouped) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        if (slot[r] >= HOT) atomic_update<kind>(&lstate[slot[r] * Q::words + 1 + J], acc[r]);
+    }
+  }
+};
+
+// Per-CTA key -> local group id table (shared memory, open addressing).  Ids
+// are handed out in arrival order; ids < HOT live in registers.
+__device__ __forceinline__ int local_lookup(uint64_t key, const AggSmem &M, uint32_t LS, uint32_t LG,
+                                            uint32_t *error_flag) {
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & (LS - 1);
+  volatile int *lslot = M.lslot;
+  volatile uint64_t *lkeys = M.lkeys;
+  while (true) {
+    const int s = lslot[h];
+    if (s >= 0) {
+      if (lkeys[h] == key) return s;
+      h = (h + 1) & (LS - 1);
+      continue;
+    }
+    if (s == -1 && atomicCAS(&M.lslot[h], -1, -2) == -1) {
+      uint32_t id = atomicAdd(M.nlocal, 1u);
+      if (id >= LG) {
+        atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+        id = 0;
+      } else {
+        M.lkey_by_id[id] = key;
+      }
+      lkeys[h] = key;
+      __threadfence_block();
+      if (id < LG) *reinterpret_cast<volatile uint32_t *>(&M.lready[id]) = 1u;
+      lslot[h] = static_cast<int>(id);
+      return static_cast<int>(id);
+    }
+  }
+}
+
+// Global key -> dense group id directory (persists across work orders).
+__device__ __forceinline__ int dir_insert(uint64_t key, const AggDesc &A) {
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & (A.dir_cap - 1);
+  volatile int *gid = A.dir_gid;
+  volatile uint64_t *keys = A.dir_keys;
+  while (true) {
+    const int g = gid[h];
+    if (g >= 0) {
+      if (keys[h] == key) return g;
+      h = (h + 1) & (A.dir_cap - 1);
+      continue;
+    }
+    if (g == -1 && atomicCAS(&A.dir_gid[h], -1, -2) == -1) {
+      uint32_t id = atomicAdd(A.n_groups, 1u);
+      if (id >= A.partial_rows) {
+        atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+        id = A.partial_rows - 1;
+      }
+      keys[h] = key;
+      A.gid_keys[id] = key;
+      __threadfence();
+      gid[h] = static_cast<int>(id);
+      return static_cast<int>(id);
+    }
+  }
+}
+
+template <class Q>
+__device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, const Lits &L, const AggDesc &A) {
+  constexpr int HOT = Q::hot;
+  constexpr int NA = Q::n_agg > 0 ? Q::n_agg : 1;
+  constexpr uint32_t LG = Q::grouped ? kCompactMaxGroups : 1;
+  constexpr uint32_t LS = Q::grouped ? kCompactLocalSlots : 0;
+  constexpr uint32_t W = Q::words;
+  const int tid = threadIdx.x;
+
+  AggSmem M;
+  {
+    char *p = smem + kBarBytes + Q::n_stages * Q::stage_bytes;
+    M.red = reinterpret_cast<uint64_t *>(p); p += 8 * HOT * (NA + 1) * 8;
+    M.lstate = reinterpret_cast<uint64_t *>(p); p += LG * W * 8;
+    M.lkey_by_id = reinterpret_cast<uint64_t *>(p); p += LG * 8;
+    M.lkeys = reinterpret_cast<uint64_t *>(p); p += LS * 8;
+    M.lslot = reinterpret_cast<int *>(p); p += LS * 4;
+    M.lready = reinterpret_cast<uint32_t *>(p); p += LG * 4;
+    M.nlocal = reinterpret_cast<uint32_t *>(p);
+  }
+  if constexpr (Q::grouped) {
+    for (uint32_t i = tid; i < LG * W; i += kBlock) {
+      const uint32_t w = i % W;
+      M.lstate[i] = w == 0 ? 0 : agg_identity(A.kind[w - 1]);
+    }
+    for (uint32_t i = tid; i < LS; i += kBlock) M.lslot[i] = -1;
+    for (uint32_t i = tid; i < LG; i += kBlock) M.lready[i] = 0;
+  }
+  if (tid == 0) {
+    *M.nlocal = Q::grouped ? 0u : 1u;
+    if (!Q::grouped) M.lkey_by_id[0] = 0;
+  }
+  // (scan_tiles starts with a __syncthreads)
+
+  AggSink<Q> sink;
+  sink.lstate = M.lstate;
+#pragma unroll
+  for (int g = 0; g < HOT; ++g) {
+    sink.hc[g] = 0;
+    static_for<0, Q::n_agg>([&](auto j) { sink.hv[g][QS_IDX(j)] = agg_identity(Q::agg_kind(QS_IDX(j))); });
+  }
+  VmRegs regs;
+  uint64_t hk[HOT];          // keys of the register-resident groups (ids 0..nhot-1)
+  int nhot = 0;
+#pragma unroll
+  for (int g = 0; g < HOT; ++g) hk[g] = 0;
+
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+    bool valid[kRows];
+    tile_valid(S, rt, tile, tid, valid);
+    uint32_t bits[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    SinkBase ns;
+    vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const bool pass = valid[r] && (bits[r] & 1u);
+      sink.slot[r] = pass ? 0 : -1;
+      any |= pass;
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    if constexpr (Q::grouped) {
+      // Fast path: compare against the (<= HOT) keys already known to live in
+      // registers; only rows of other groups take the shared-memory table.
+      if (nhot < HOT) {
+        nhot = 0;
+#pragma unroll
+        for (int g = 0; g < HOT; ++g) {
+          if (nhot == g && *reinterpret_cast<volatile uint32_t *>(&M.lready[g]) != 0u) {
+            hk[g] = *reinterpret_cast<volatile uint64_t *>(&M.lkey_by_id[g]);
+            nhot = g + 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (sink.slot[r] < 0) continue;
+        uint64_t key[kMaxKeyWords];
+        pack_key<Q>(stage, tile_row(r, tid), key);
+        int s = -2;
+#pragma unroll
+        for (int g = 0; g < HOT; ++g)
+          if (g < nhot && key[0] == hk[g]) s = g;
+        if (s == -2) s = local_lookup(key[0], M, LS, LG, A.error_flag);
+        sink.slot[r] = s;
+      }
+    }
+    // row counts
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+      for (int g = 0; g < HOT; ++g) sink.hc[g] += (sink.slot[r] == g) ? 1u : 0u;
+      if constexpr (Q::grouped) {
+        if (sink.slot[r] >= HOT)
+          atomicAdd(reinterpret_cast<unsigned long long *>(&M.lstate[sink.slot[r] * W]), 1ull);
+      }
+    }
+    vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+  });
+
+  // ---- CTA reduction of the register-resident (hot) groups, fixed tree.
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int g = 0; g < HOT; ++g) {
+    uint64_t c = sink.hc[g];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) M.red[(warp * HOT + g) * (NA + 1)] = c;
+    static_for<0, Q::n_agg>([&](auto jj) {
+      constexpr int j = QS_IDX(jj);
+      constexpr uint8_t kind = Q::agg_kind(j);
+      uint64_t x = sink.hv[g][j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t y = __shfl_xor_sync(0xffffffffu, x, off);
+        // keep operand order lane-independent: lower lane first
+        x = (lane & off) ? agg_combine(kind, y, x) : agg_combine(kind, x, y);
+      }
+      if (lane == 0) M.red[(warp * HOT + g) * (NA + 1) + 1 + j] = x;
+    });
+  }
+  __syncthreads();
+  const uint32_t nlocal = min(*M.nlocal, LG);
+  if (tid < HOT * (NA + 1)) {
+    const int g = tid / (NA + 1), w = tid % (NA + 1);
+    if (static_cast<uint32_t>(g) < nlocal && static_cast<uint32_t>(w) < W) {
+      uint64_t x = M.red[(0 * HOT + g) * (NA + 1) + w];
+      for (int wp = 1; wp < kBlock / 32; ++wp) {
+        const uint64_t y = M.red[(wp * HOT + g) * (NA + 1) + w];
+        x = w == 0 ? x + y : agg_combine(A.kind[w - 1], x, y);
+      }
+      // lstate[g] holds identity (hot groups never touch it during the scan)
+      M.lstate[g * W + w] = x;
+    }
+  }
+  __syncthreads();
+  // ---- publish this CTA's partial state, one row per group it met.
+  for (uint32_t l = tid; l < nlocal; l += kBlock) {
+    const int gid = Q::grouped ? dir_insert(M.lkey_by_id[l], A) : 0;
+    uint64_t *dst = A.partials + (static_cast<uint64_t>(blockIdx.x) * A.partial_rows + gid) * W;
+    for (uint32_t w = 0; w < W; ++w) dst[w] = M.lstate[l * W + w];
+  }
+}
+
+// ============================================================ K7  scan_groupby
+// Find-or-insert `key` (kw words); returns the slot or -1 when the table is full.
+template <uint32_t KW>
+__device__ __forceinline__ int64_t table_upsert(const uint64_t *key, const AggDesc &A) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+  for (uint32_t i = 0; i < KW; ++i) h = mix64(h ^ key[i]);
+  const uint64_t mask = A.cap - 1;
+  uint64_t slot = h & mask;
+  volatile uint32_t *tags = A.tags;
+  volatile uint64_t *keys = A.keys;
+  for (uint64_t probes = 0; probes <= mask;) {
+    const uint32_t t = tags[slot];
+    if (t == 2u) {
+      bool eq = true;
+#pragma unroll
+      for (uint32_t i = 0; i < KW; ++i) eq &= keys[slot * KW + i] == key[i];
+      if (eq) return static_cast<int64_t>(slot);
+      slot = (slot + 1) & mask;
+      ++probes;
+      continue;
+    }
+    if (t == 0u && atomicCAS(&A.tags[slot], 0u, 1u) == 0u) {
+#pragma unroll
+      for (uint32_t i = 0; i < KW; ++i) keys[slot * KW + i] = key[i];
+      __threadfence();
+      tags[slot] = 2u;
+      atomicAdd(A.n_groups, 1u);
+      return static_cast<int64_t>(slot);
+    }
+    // busy (or lost the race): look at the same slot again
+  }
+  atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+  return -1;
+}
+
+template <class Q>
+struct GlobalAggSink : SinkBase {
+  int64_t slot[kRows];
+  const AggDesc *A;
+  template <int J, int TYPE>
+  __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      if (slot[r] >= 0) atomic_update<Q::agg_kind(J)>(&A->states[slot[r] * Q::words + 1 + J], acc[r]);
+  }
+};
+
+template <class Q>
+__device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S, const Lits &L, const AggDesc &A) {
+  const int tid = threadIdx.x;
+  GlobalAggSink<Q> sink;
+  sink.A = &A;
+  VmRegs regs;
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+    bool valid[kRows];
+    tile_valid(S, rt, tile, tid, valid);
+    uint32_t bits[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    SinkBase ns;
+    vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const bool pass = valid[r] && (bits[r] & 1u);
+      sink.slot[r] = -1;
+      if (pass) {
+        if constexpr (Q::strategy == QS_AGG_COLLISION_FREE) {
+          constexpr uint32_t w = Q::key_w(0);
+          const char *src = stage + Q::col_off(Q::key_col(0)) + tile_row(r, tid) * w;
+          const int64_t k = w == 4 ? static_cast<int64_t>(*reinterpret_cast<const int32_t *>(src))
+                                   : *reinterpret_cast<const int64_t *>(src);
+          if (k >= 0 && static_cast<uint64_t>(k) < A.cap) sink.slot[r] = k;
+          else atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+        } else {
+          uint64_t key[kMaxKeyWords];
+          pack_key<Q>(stage, tile_row(r, tid), key);
+          sink.slot[r] = table_upsert<Q::key_words>(key, A);
+        }
+        if (sink.slot[r] >= 0)
+          atomicAdd(reinterpret_cast<unsigned long long *>(&A.states[sink.slot[r] * Q::words]), 1ull);
+      }
+      any |= sink.slot[r] >= 0;
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+  });
+}
+
+// ======================================================= K3 / K4  scan_select
+// The reference builds a TupleIdSequence bitmap, then one ColumnVector per
+// projected expression, then copies tuples into the destination block.  Here
+// the bitmap is a warp ballot: each warp counts its survivors, one atomicAdd
+// per CTA tile reserves the output range, and survivors are written straight
+// from the staged tile to their final position (rows of a tile keep their
+// input order).
+template <class Q>
+struct SelectSink : SinkBase {
+  const SinkDesc *K;
+  uint64_t idx[kRows];     // output row, ~0 when the row does not survive
+  int tid;
+  template <int J, int TYPE>
+  __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
+    constexpr uint32_t w = Q::out_w(J);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (idx[r] == ~0ull) continue;
+      if constexpr (w == 4) *reinterpret_cast<uint32_t *>(K->out[J] + idx[r] * 4) = static_cast<uint32_t>(acc[r]);
+      else *reinterpret_cast<uint64_t *>(K->out[J] + idx[r] * 8) = acc[r];
+    }
+  }
+  template <int J, int COL, int W>
+  __device__ __forceinline__ void emit_raw(const char *col) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (idx[r] == ~0ull) continue;
+      copy_value<W>(K->out[J] + idx[r] * W, col + tile_row(r, tid) * W);
+    }
+  }
+};
+
+template <class Q, class SinkT>
+__device__ __forceinline__ void lip_build_rows(const SinkDesc &K, const char *stage, int tid,
+                                               const bool (&pass)[kRows]) {
+  static_for<0, Q::n_lip_build>([&](auto ff) {
+    constexpr int f = QS_IDX(ff);
+    constexpr uint8_t lt = Q::lb_ltype(f);
+    constexpr uint32_t w = (lt == V_I32 || lt == V_F32) ? 4u : 8u;
+    const char *base = stage + Q::col_off(Q::lb_col(f));
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      if (pass[r])
+        lip_insert<Q::lb_kind(f)>(K.lip_build[f], static_cast<int64_t>(load_native(base + tile_row(r, tid) * w, lt)));
+  });
+}
+
+template <class Q>
+__device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K) {
+  const int tid = threadIdx.x;
+  uint32_t *s_compact = reinterpret_cast<uint32_t *>(smem + kBarBytes + Q::n_stages * Q::stage_bytes);
+  SelectSink<Q> sink;
+  sink.K = &K;
+  sink.tid = tid;
+  VmRegs regs;
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+    bool valid[kRows];
+    tile_valid(S, rt, tile, tid, valid);
+    uint32_t bits[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    SinkBase ns;
+    vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+    bool pass[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) pass[r] = valid[r] && (bits[r] & 1u);
+
+    // LIPFilterBuilder::insertValueAccessor on the survivors.
+    lip_build_rows<Q, SelectSink<Q>>(K, stage, tid, pass);
+    if constexpr (Q::n_out > 0) {   // BuildLIPFilter has nothing to materialise
+      cta_compact(pass, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+      vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+    }
+  });
+}
+
+// ============================================================== K5 join build
+// The reference's JoinHashTable is a separate-chaining multi-map from key to
+// TupleReference{block, tuple}; probes collect (probe_tid, build_tid) pairs per
+// build block and re-open every build block.  On the device the table is one
+// open-addressing array of 16-byte {key, build row} slots (linear probing,
+// duplicates occupy their own slots), the probe keys arrive as TMA-staged
+// tiles, and matched pairs are projected in the same kernel: build-side
+// operands are gathered through the stored row id.  Rows that share a probe
+// tile advance in lock-step "rounds" (one match per row per round) so that the
+// warp-ballot compaction and the VM stay CTA-uniform even with duplicate keys.
+constexpr unsigned long long kEmptyRow = ~0ull;
+
+template <class Q>
+__device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K,
+                                                const JoinDesc &J) {
+  const int tid = threadIdx.x;
+  VmRegs regs;
+  const uint64_t mask = J.cap - 1;
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+    bool valid[kRows];
+    tile_valid(S, rt, tile, tid, valid);
+    uint32_t bits[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    SinkBase ns;
+    vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+    const uint64_t row0 = S.first_row + static_cast<uint64_t>(tile) * kTileRows;
+    bool pass[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) pass[r] = valid[r] && (bits[r] & 1u);
+    lip_build_rows<Q, SinkBase>(K, stage, tid, pass);
+    constexpr uint8_t klt = Q::j_key_ltype;
+    constexpr uint32_t kw = (klt == V_I32) ? 4u : 8u;
+    const char *kbase = stage + Q::col_off(Q::j_key_col);
+    uint32_t inserted = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (!pass[r]) continue;
+      const int64_t key = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
+      const unsigned long long row = row0 + tile_row(r, tid);
+      uint64_t h = mix64(static_cast<uint64_t>(key)) & mask;
+      bool done = false;
+      for (uint64_t probes = 0; probes <= mask; ++probes) {
+        if (atomicCAS(&J.slots[h].row, kEmptyRow, row) == kEmptyRow) {
+          J.slots[h].key = key;
+          done = true;
+          break;
+        }
+        h = (h + 1) & mask;
+      }
+      if (done) ++inserted;
+      else atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+    }
+    // one counter update per warp instead of one per row
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, off);
+    if ((tid & 31) == 0 && inserted) atomicAdd(J.n_entries, static_cast<unsigned long long>(inserted));
+  });
+}
+
+// ============================================================== K6 join probe
+template <class Q>
+struct JoinSink : SinkBase {
+  const SinkDesc *K;
+  const JoinDesc *J;
+  uint64_t idx[kRows];
+  unsigned long long brow[kRows];
+  int tid;
+  template <int JJ, int TYPE>
+  __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
+    constexpr uint32_t w = Q::out_w(JJ);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (idx[r] == ~0ull) continue;
+      if constexpr (w == 4) *reinterpret_cast<uint32_t *>(K->out[JJ] + idx[r] * 4) = static_cast<uint32_t>(acc[r]);
+      else *reinterpret_cast<uint64_t *>(K->out[JJ] + idx[r] * 8) = acc[r];
+    }
+  }
+  template <int JJ, int COL, int W>
+  __device__ __forceinline__ void emit_raw(const char *col) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (idx[r] == ~0ull) continue;
+      copy_value<W>(K->out[JJ] + idx[r] * W, col + tile_row(r, tid) * W);
+    }
+  }
+  template <int JJ, int COL, int W>
+  __device__ __forceinline__ void emit_raw_build() {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (idx[r] == ~0ull || brow[r] == kEmptyRow) continue;
+      copy_value<W>(K->out[JJ] + idx[r] * W, J->build_cols[COL].ptr + brow[r] * W);
+    }
+  }
+  template <int COL, int LTYPE, int W>
+  __device__ __forceinline__ uint64_t build_leaf(int r) {
+    if (brow[r] == kEmptyRow) return 0;
+    return load_native(J->build_cols[COL].ptr + brow[r] * W, LTYPE);
+  }
+};
+
+template <class Q>
+__device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K,
+                                                const JoinDesc &J) {
+  const int tid = threadIdx.x;
+  uint32_t *s_compact = reinterpret_cast<uint32_t *>(smem + kBarBytes + Q::n_stages * Q::stage_bytes);
+  JoinSink<Q> sink;
+  sink.K = &K;
+  sink.J = &J;
+  sink.tid = tid;
+  VmRegs regs;
+  const uint64_t mask = J.cap - 1;
+  constexpr bool has_residual = Q::n_mid > Q::n_pred;
+  constexpr bool inner = Q::j_type == QS_JOIN_INNER;
+
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+    bool valid[kRows];
+    tile_valid(S, rt, tile, tid, valid);
+    uint32_t bits[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    SinkBase ns;
+    vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+
+    bool pass[kRows], active[kRows], matched[kRows];
+    int64_t key[kRows];
+    uint64_t h[kRows];
+    constexpr uint8_t klt = Q::j_key_ltype;
+    constexpr uint32_t kw = (klt == V_I32) ? 4u : 8u;
+    const char *kbase = stage + Q::col_off(Q::j_key_col);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      pass[r] = valid[r] && (bits[r] & 1u);
+      active[r] = pass[r];
+      matched[r] = false;
+      key[r] = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
+      h[r] = mix64(static_cast<uint64_t>(key[r])) & mask;
+    }
+
+    while (true) {
+      bool found[kRows];
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        found[r] = false;
+        sink.brow[r] = kEmptyRow;
+        if (!active[r]) continue;
+        for (uint64_t probes = 0; probes <= mask; ++probes) {
+          const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(&J.slots[h[r]]);
+          if (s.y == kEmptyRow) { active[r] = false; break; }
+          h[r] = (h[r] + 1) & mask;
+          if (static_cast<int64_t>(s.x) == key[r]) { found[r] = true; sink.brow[r] = s.y; break; }
+        }
+        if (!found[r]) active[r] = false;
+        any |= found[r];
+      }
+      if (!__syncthreads_or(any)) break;
+      bool ok[kRows];
+      if constexpr (has_residual) {
+        uint32_t rb[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) rb[r] = 1u;
+        vm_run<Q, Q::n_pred, Q::n_mid>(L, S, stage, tid, regs, rb, sink);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) ok[r] = found[r] && (rb[r] & 1u);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) ok[r] = found[r];
+      }
+      if constexpr (inner) {
+        cta_compact(ok, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+        vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (ok[r]) { matched[r] = true; active[r] = false; }   // existence is enough
+        }
+      }
+    }
+    if constexpr (!inner) {
+      bool flag[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        flag[r] = pass[r] && (Q::j_type == QS_JOIN_LEFT_SEMI ? matched[r] : !matched[r]);
+        sink.brow[r] = kEmptyRow;
+      }
+      cta_compact(flag, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+      vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+    }
+  });
+}
+
+}  // namespace qs

@@ -52,18 +52,15 @@ struct FinalizeDesc {
   int keys_are_slots;          // collision free: key value == slot index
 };
 
+#ifndef __CUDACC_RTC__
 // k_agg.cu
-size_t agg_smem_extra(int hot, int nagg_t, bool grouped, uint32_t words);
-void agg_template_shape(const AggDesc &A, int *hot, int *nagg_t);
-cudaError_t launch_scan_agg(const ScanDesc &S, const Program &P, const AggDesc &A, int grid, size_t smem,
-                            cudaStream_t st);
+size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words);
+int agg_hot_groups(const AggDesc &A);
 cudaError_t launch_fill_identity(uint64_t *states, uint64_t n_rows, const AggDesc &A, cudaStream_t st);
 cudaError_t launch_merge_partials(const AggDesc &A, uint32_t n_ctas, cudaStream_t st);
 cudaError_t launch_merge_foreign_compact(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
                                          uint32_t f_groups, cudaStream_t st);
 // k_groupby.cu
-cudaError_t launch_scan_groupby(const ScanDesc &S, const Program &P, const AggDesc &A, int grid, size_t smem,
-                                cudaStream_t st);
 cudaError_t launch_rehash(const AggDesc &from, const AggDesc &to, cudaStream_t st);
 cudaError_t launch_merge_foreign_table(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
                                        uint64_t f_groups, cudaStream_t st);
@@ -74,15 +71,8 @@ cudaError_t launch_gather_rows(const uint64_t *states, const uint64_t *keys, uin
                                int keys_are_slots, cudaStream_t st);
 cudaError_t launch_finalize(const uint64_t *states, const uint64_t *keys, uint32_t words, const uint64_t *idx,
                             uint64_t n, const FinalizeDesc &F, cudaStream_t st);
-// k_select.cu
-cudaError_t launch_scan_select(const ScanDesc &S, const Program &P, const SinkDesc &K, int grid, size_t smem,
-                               cudaStream_t st);
 // k_join.cu
 cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st);
-cudaError_t launch_join_build(const ScanDesc &S, const Program &P, const SinkDesc &K, const JoinDesc &J,
-                              int grid, size_t smem, cudaStream_t st);
-cudaError_t launch_join_probe(const ScanDesc &S, const Program &P, const SinkDesc &K, const JoinDesc &J,
-                              int grid, size_t smem, cudaStream_t st);
 // k_misc.cu
 cudaError_t launch_decode_dict(void *dst, const void *codes, const void *dict, uint64_t n, uint32_t code_width,
                                uint32_t value_width, uint32_t dict_entries, cudaStream_t st);
@@ -90,5 +80,6 @@ cudaError_t launch_decode_truncated(void *dst, const void *codes, uint64_t n, ui
                                     uint32_t value_width, cudaStream_t st);
 cudaError_t launch_decode_strided(void *dst, const void *slots, uint64_t n, uint32_t stride,
                                   uint32_t value_width, cudaStream_t st);
+#endif  // !__CUDACC_RTC__
 
 }  // namespace qs

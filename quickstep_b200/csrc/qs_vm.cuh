@@ -8,13 +8,19 @@
 //   arithmetic functors             types/operations/binary_operations/ArithmeticBinaryOperators.hpp:51-159
 //   comparison functors             types/operations/comparisons/LiteralComparators.hpp:36-72
 //
-// Design: an accumulator machine.  Each thread owns kRows rows of the current
-// tile; one decoded instruction is applied to all of them (so decode cost is
-// amortised and the kRows independent chains give ILP).  Column operands come
-// from the shared-memory tile that the TMA unit filled, so operand fetch is an
-// LDS with a *dynamic* column index -- something registers cannot do.  The
-// reference materialises one ColumnVector per expression node; here no
-// intermediate ever leaves registers.
+// Design: an accumulator machine whose instruction stream is a compile-time
+// constant.  The host lowers the expression trees of a work order into a
+// linear program (lower.cu); the query compiler (qs_jit.cu) prints that
+// program as the constexpr tables of a struct Q and instantiates the kernel
+// template for it with NVRTC.  vm_run<Q, PC, END> below is the interpreter
+// loop unrolled by template recursion: every `if constexpr` on Q::code(PC)
+// folds away, so what reaches SASS is the straight-line typed arithmetic a
+// hand-written kernel for that query would contain (the reference gets the
+// same effect on the CPU from its template-instantiated functors).  Each
+// thread owns kRows rows of the current tile and applies each instruction to
+// all of them (kRows independent chains of ILP).  Column operands come from
+// the shared-memory tile the TMA unit filled.  The reference materialises one
+// ColumnVector per expression node; here no intermediate ever leaves registers.
 //
 // Arithmetic is IEEE, evaluated in the reference's operand order, compiled
 // with --fmad=false so a*b+c is never contracted: per-row values are
@@ -128,9 +134,11 @@ __device__ __forceinline__ bool vcmp(uint8_t c, uint8_t type, uint64_t a, uint64
 
 // strncmp(col, lit, n) <cmp> 0 for fixed-width NUL-padded CHAR(n)
 // (types/operations/comparisons/AsciiStringComparators.hpp:218-251).
-__device__ __forceinline__ bool char_cmp(uint8_t c, const char *v, const char *lit, uint32_t n) {
+template <uint32_t N>
+__device__ __forceinline__ bool char_cmp(uint8_t c, const char *v, const char *lit) {
   int res = 0;
-  for (uint32_t i = 0; i < n; ++i) {
+#pragma unroll
+  for (uint32_t i = 0; i < N; ++i) {
     const unsigned char a = static_cast<unsigned char>(v[i]);
     const unsigned char b = static_cast<unsigned char>(lit[i]);
     if (a != b) { res = a < b ? -1 : 1; break; }
@@ -139,183 +147,144 @@ __device__ __forceinline__ bool char_cmp(uint8_t c, const char *v, const char *l
   return cmp_t<int>(c, res, 0);
 }
 
+// ------------------------------------------------------ compile-time loops
+template <int I> struct IC { static constexpr int value = I; };
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (B < E) {
+    f(IC<B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+#define QS_IDX(x) (decltype(x)::value)
+
 // Default (no-op) sink hooks; concrete sinks override what they consume.
 struct SinkBase {
-  __device__ __forceinline__ void emit(uint32_t, uint8_t, const uint64_t (&)[kRows]) {}
-  __device__ __forceinline__ void emit_raw(uint32_t, const char *, uint32_t) {}
-  __device__ __forceinline__ void emit_raw_build(uint32_t, uint32_t) {}
-  __device__ __forceinline__ uint64_t build_leaf(uint32_t, uint8_t, int) { return 0; }
+  template <int J, int TYPE> __device__ __forceinline__ void emit(const uint64_t (&)[kRows]) {}
+  template <int J, int COL, int W> __device__ __forceinline__ void emit_raw(const char *) {}
+  template <int J, int COL, int W> __device__ __forceinline__ void emit_raw_build() {}
+  template <int COL, int LTYPE, int W> __device__ __forceinline__ uint64_t build_leaf(int) { return 0; }
 };
 
 // Per-thread VM state that survives between the predicate and emit sections.
 struct VmRegs {
   uint64_t tmp[kMaxTmp][kRows];
+  uint64_t acc[kRows];
 };
 
 // Row i of the tile that thread `tid` owns in its r-th lane: r*kBlock + tid.
 __device__ __forceinline__ uint32_t tile_row(int r, int tid) { return r * kBlock + tid; }
 
 /*
- * Run code[pc,end) for this thread's kRows rows.
+ * Run Q::code[PC,END) for this thread's kRows rows.
  *   bits[r]  predicate bit stack (bit 0 = top)
- *   Sink     provides emit(j, type, acc), emit_raw(j, src, width, r) and
- *            build_leaf(col, ltype, r) (join build-side operand).
+ *   Sink     provides emit<J,TYPE>(acc), emit_raw<J,COL,W>(col tile),
+ *            emit_raw_build<J,COL,W>() and build_leaf<COL,LTYPE,W>(r).
  */
-template <class Sink>
-__device__ __forceinline__ void vm_run(const Program &P, uint32_t pc, uint32_t end,
-                                       const ScanDesc &S, const char *stage, int tid,
+template <class Q, int PC, int END, class Sink>
+__device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const char *stage, int tid,
                                        VmRegs &regs, uint32_t (&bits)[kRows], Sink &sink) {
-  uint64_t acc[kRows];
-#pragma unroll
-  for (int r = 0; r < kRows; ++r) acc[r] = 0;
-
-  for (; pc < end; ++pc) {
-    const Instr in = P.code[pc];
+  if constexpr (PC < END) {
+    constexpr Instr in = Q::code(PC);
+    uint64_t (&acc)[kRows] = regs.acc;
     uint64_t leaf[kRows];
-    const bool wants_leaf = (in.op <= OP_MOD) || in.op == OP_CMP;
-    if (wants_leaf) {
-      switch (in.leaf) {
-        case LEAF_COL: {
-          const char *base = stage + S.cols[in.arg].smem_off;
-          const uint32_t w = native_width(in.ltype);
+    constexpr bool wants_leaf = (in.op <= OP_MOD) || in.op == OP_CMP;
+    if constexpr (wants_leaf) {
+      if constexpr (in.leaf == LEAF_COL) {
+        const char *base = stage + Q::col_off(in.arg);
+        constexpr uint32_t w = (in.ltype == V_I32 || in.ltype == V_F32) ? 4u : 8u;
 #pragma unroll
-          for (int r = 0; r < kRows; ++r)
-            leaf[r] = vcvt(load_native(base + tile_row(r, tid) * w, in.ltype), in.ltype, in.type);
-          break;
-        }
-        case LEAF_LIT: {
-          const uint64_t v = P.lits[in.arg];
+        for (int r = 0; r < kRows; ++r)
+          leaf[r] = vcvt(load_native(base + tile_row(r, tid) * w, in.ltype), in.ltype, in.type);
+      } else if constexpr (in.leaf == LEAF_LIT) {
+        const uint64_t v = L.lits[in.arg];
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) leaf[r] = v;
-          break;
-        }
-        case LEAF_TMP: {
-          if (in.arg == 0) {
+        for (int r = 0; r < kRows; ++r) leaf[r] = v;
+      } else if constexpr (in.leaf == LEAF_TMP) {
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) leaf[r] = vcvt(regs.tmp[0][r], in.ltype, in.type);
-          } else {
+        for (int r = 0; r < kRows; ++r) leaf[r] = vcvt(regs.tmp[in.arg == 0 ? 0 : kMaxTmp - 1][r], in.ltype, in.type);
+      } else {  // LEAF_BUILD
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) leaf[r] = vcvt(regs.tmp[kMaxTmp - 1][r], in.ltype, in.type);
-          }
-          break;
-        }
-        default: {  // LEAF_BUILD
-#pragma unroll
-          for (int r = 0; r < kRows; ++r)
-            leaf[r] = vcvt(sink.build_leaf(in.arg, in.ltype, r), in.ltype, in.type);
-          break;
-        }
+        for (int r = 0; r < kRows; ++r)
+          leaf[r] = vcvt(sink.template build_leaf<in.arg, in.ltype, Q::build_w(in.arg)>(r), in.ltype, in.type);
       }
     }
-    switch (in.op) {
-      case OP_LOAD:
+    if constexpr (in.op == OP_LOAD) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = leaf[r];
-        break;
-      case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: case OP_MOD:
-        if (in.flags & 1) {
+      for (int r = 0; r < kRows; ++r) acc[r] = leaf[r];
+    } else if constexpr (in.op >= OP_ADD && in.op <= OP_MOD) {
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) acc[r] = valu(in.op, in.type, leaf[r], acc[r]);
-        } else {
+      for (int r = 0; r < kRows; ++r)
+        acc[r] = (in.flags & 1) ? valu(in.op, in.type, leaf[r], acc[r]) : valu(in.op, in.type, acc[r], leaf[r]);
+    } else if constexpr (in.op == OP_NEG) {
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) acc[r] = valu(in.op, in.type, acc[r], leaf[r]);
-        }
-        break;
-      case OP_NEG:
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          switch (in.type) {
-            case V_F64: acc[r] = d2u(-u2d(acc[r])); break;
-            case V_F32: acc[r] = f2u(-u2f(acc[r])); break;
-            case V_I64: acc[r] = static_cast<uint64_t>(-static_cast<int64_t>(acc[r])); break;
-            default: acc[r] = static_cast<uint64_t>(static_cast<int64_t>(-static_cast<int32_t>(acc[r]))); break;
-          }
-        }
-        break;
-      case OP_CVT:
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = vcvt(acc[r], in.type, in.aux);
-        break;
-      case OP_ST_TMP:
-        if (in.arg == 0) {
-#pragma unroll
-          for (int r = 0; r < kRows; ++r) regs.tmp[0][r] = acc[r];
-        } else {
-#pragma unroll
-          for (int r = 0; r < kRows; ++r) regs.tmp[kMaxTmp - 1][r] = acc[r];
-        }
-        break;
-      case OP_CMP:
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const bool b = (in.flags & 1) ? vcmp(in.aux, in.type, leaf[r], acc[r])
-                                        : vcmp(in.aux, in.type, acc[r], leaf[r]);
-          bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
-        }
-        break;
-      case OP_CMP_CHAR: {
-        const char *base = stage + S.cols[in.arg].smem_off;
-        const uint32_t w = S.cols[in.arg].width;
-        const char *lit = P.str_pool + in.ltype;    // ltype doubles as pool offset
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const bool b = char_cmp(in.aux, base + tile_row(r, tid) * w, lit, w);
-          bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
-        }
-        break;
+      for (int r = 0; r < kRows; ++r) {
+        if constexpr (in.type == V_F64) acc[r] = d2u(-u2d(acc[r]));
+        else if constexpr (in.type == V_F32) acc[r] = f2u(-u2f(acc[r]));
+        else if constexpr (in.type == V_I64) acc[r] = static_cast<uint64_t>(-static_cast<int64_t>(acc[r]));
+        else acc[r] = static_cast<uint64_t>(static_cast<int64_t>(-static_cast<int32_t>(acc[r])));
       }
-      case OP_AND:
+    } else if constexpr (in.op == OP_CVT) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) & (bits[r] | ~1u);
-        break;
-      case OP_OR:
+      for (int r = 0; r < kRows; ++r) acc[r] = vcvt(acc[r], in.type, in.aux);
+    } else if constexpr (in.op == OP_ST_TMP) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) | (bits[r] & 1u);
-        break;
-      case OP_NOT:
+      for (int r = 0; r < kRows; ++r) regs.tmp[in.arg == 0 ? 0 : kMaxTmp - 1][r] = acc[r];
+    } else if constexpr (in.op == OP_CMP) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) bits[r] ^= 1u;
-        break;
-      case OP_PUSH_TRUE:
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] << 1) | 1u;
-        break;
-      case OP_PUSH_FALSE:
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) bits[r] = bits[r] << 1;
-        break;
-      case OP_LIP: {
-        // Probe only rows still alive below the new stack top would need the
-        // conjunction structure; LIP probes are always AND-ed right after, so
-        // rows whose current top bit is 0 skip the (random) memory access.
-        const LipDesc &f = S.lip[in.arg];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          bool b = false;
-          if ((in.flags & 2) == 0 || (bits[r] & 1u)) {
-            const int64_t v = static_cast<int64_t>(acc[r]);
-            b = lip_contains(f, v);
-          }
-          bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
-        }
-        break;
+      for (int r = 0; r < kRows; ++r) {
+        const bool b = (in.flags & 1) ? vcmp(in.aux, in.type, leaf[r], acc[r])
+                                      : vcmp(in.aux, in.type, acc[r], leaf[r]);
+        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
       }
-      case OP_EMIT:
-        sink.emit(in.arg, in.type, acc);
-        break;
-      case OP_EMIT_RAW:
-        sink.emit_raw(in.arg, stage + S.cols[in.flags].smem_off, S.cols[in.flags].width);
-        break;
-      case OP_EMIT_RAW_BUILD:
-        sink.emit_raw_build(in.arg, in.flags);
-        break;
+    } else if constexpr (in.op == OP_CMP_CHAR) {
+      const char *base = stage + Q::col_off(in.arg);
+      constexpr uint32_t w = Q::col_w(in.arg);
+      const char *lit = L.str_pool + in.ltype;    // ltype doubles as pool offset
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const bool b = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit);
+        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
+      }
+    } else if constexpr (in.op == OP_AND) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) & (bits[r] | ~1u);
+    } else if constexpr (in.op == OP_OR) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) | (bits[r] & 1u);
+    } else if constexpr (in.op == OP_NOT) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) bits[r] ^= 1u;
+    } else if constexpr (in.op == OP_PUSH_TRUE) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] << 1) | 1u;
+    } else if constexpr (in.op == OP_PUSH_FALSE) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) bits[r] = bits[r] << 1;
+    } else if constexpr (in.op == OP_LIP) {
+      // LIP probes are always AND-ed right after (flags&2), so rows whose
+      // current top bit is 0 skip the (random) memory access.
+      const LipDesc &f = S.lip[in.arg];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        bool b = false;
+        if ((in.flags & 2) == 0 || (bits[r] & 1u))
+          b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, static_cast<int64_t>(acc[r]));
+        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
+      }
+    } else if constexpr (in.op == OP_EMIT) {
+      sink.template emit<in.arg, in.type>(acc);
+    } else if constexpr (in.op == OP_EMIT_RAW) {
+      sink.template emit_raw<in.arg, in.flags, Q::col_w(in.flags)>(stage + Q::col_off(in.flags));
+    } else if constexpr (in.op == OP_EMIT_RAW_BUILD) {
+      sink.template emit_raw_build<in.arg, in.flags, Q::build_w(in.flags)>();
     }
+    vm_run<Q, PC + 1, END>(L, S, stage, tid, regs, bits, sink);
   }
 }
 
 // --------------------------------------------------------- tile pipeline
 // Shared memory layout: [kMaxStages mbarriers][pad to 128][stage 0][stage 1]...
-
 
 // Run-time extent of a scan: the row count of a temporary relation may only be
 // known on the device (it is the output counter of the previous operator), so
@@ -339,20 +308,19 @@ __device__ __forceinline__ ScanRt scan_extent(const ScanDesc &S) {
   return rt;
 }
 
+template <class Q>
 __device__ __forceinline__ void issue_tile(const ScanDesc &S, const ScanRt &rt, uint32_t tile, char *stage,
                                            uint64_t *bar) {
   const uint64_t row0 = S.first_row + static_cast<uint64_t>(tile) * kTileRows;
-  uint64_t rows = rt.row_end - row0;
-  if (rows > kTileRows) rows = kTileRows;
+  uint64_t rows64 = rt.row_end - row0;
+  const uint32_t rows = rows64 > kTileRows ? kTileRows : static_cast<uint32_t>(rows64);
   uint32_t total = 0;
-  for (uint32_t c = 0; c < S.n_cols; ++c)
-    total += (static_cast<uint32_t>(rows) * S.cols[c].width + 15u) & ~15u;
+  static_for<0, Q::n_cols>([&](auto c) { total += (rows * Q::col_w(QS_IDX(c)) + 15u) & ~15u; });
   mbar_expect_tx(bar, total);
-  for (uint32_t c = 0; c < S.n_cols; ++c) {
-    const uint32_t w = S.cols[c].width;
-    const uint32_t bytes = (static_cast<uint32_t>(rows) * w + 15u) & ~15u;
-    bulk_g2s(stage + S.cols[c].smem_off, S.cols[c].ptr + row0 * w, bytes, bar);
-  }
+  static_for<0, Q::n_cols>([&](auto c) {
+    constexpr uint32_t w = Q::col_w(QS_IDX(c));
+    bulk_g2s(stage + Q::col_off(QS_IDX(c)), S.cols[QS_IDX(c)].ptr + row0 * w, (rows * w + 15u) & ~15u, bar);
+  });
 }
 
 /*
@@ -361,34 +329,34 @@ __device__ __forceinline__ void issue_tile(const ScanDesc &S, const ScanRt &rt, 
  * Thread 0 is the TMA producer; all threads consume.  body(tile, stage, rt)
  * may use CTA-wide barriers only if every thread reaches them.
  */
-template <class Body>
+template <class Q, class Body>
 __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &&body) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   char *stages = smem + kBarBytes;
   const int tid = threadIdx.x;
   const ScanRt rt = scan_extent(S);
   if (tid == 0) {
-    for (uint32_t s = 0; s < S.n_stages; ++s) mbar_init(&bars[s], 1);
+    for (uint32_t s = 0; s < Q::n_stages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
   if (tid == 0) {
     uint32_t tile = blockIdx.x;
-    for (uint32_t s = 0; s < S.n_stages && tile < rt.n_tiles; ++s, tile += gridDim.x)
-      issue_tile(S, rt, tile, stages + s * S.stage_bytes, &bars[s]);
+    for (uint32_t s = 0; s < Q::n_stages && tile < rt.n_tiles; ++s, tile += gridDim.x)
+      issue_tile<Q>(S, rt, tile, stages + s * Q::stage_bytes, &bars[s]);
   }
   uint32_t s = 0, parity = 0;
-  const uint32_t ahead = S.n_stages * gridDim.x;
+  const uint32_t ahead = Q::n_stages * gridDim.x;
   for (uint32_t tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
-    char *stage = stages + s * S.stage_bytes;
+    char *stage = stages + s * Q::stage_bytes;
     mbar_wait(&bars[s], parity);
     body(tile, stage, rt);
     __syncthreads();
     if (tid == 0) {
       const uint32_t next = tile + ahead;
-      if (next < rt.n_tiles) issue_tile(S, rt, next, stage, &bars[s]);
+      if (next < rt.n_tiles) issue_tile<Q>(S, rt, next, stage, &bars[s]);
     }
-    if (++s == S.n_stages) { s = 0; parity ^= 1; }
+    if (++s == Q::n_stages) { s = 0; parity ^= 1; }
   }
 }
 
