@@ -35,7 +35,8 @@ __global__ void k_fill_identity(uint64_t *states, uint64_t n_rows, const __grid_
 __global__ void __launch_bounds__(128) k_merge_partials(const __grid_constant__ AggDesc A, uint32_t n_ctas) {
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t n_groups = min(*A.n_groups, A.partial_rows);
+  // without GROUP BY there is exactly one state and the key directory is never touched
+  const uint32_t n_groups = A.n_key_cols == 0 ? 1u : min(*A.n_groups, A.partial_rows);
   if (i >= n_groups * A.words) return;
   const uint32_t g = i / A.words, w = i % A.words;
   const uint8_t kind = w == 0 ? AK_SUM_I64 : A.kind[w - 1];
