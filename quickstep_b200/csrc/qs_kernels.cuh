@@ -119,6 +119,27 @@ struct AggSmem {
   uint32_t *nlocal;
 };
 
+// hv (+)= v when slot == G, as ONE predicated instruction (ptxas shares the
+// setp between the aggregates of a row).  Written in PTX because the compiler
+// turns the equivalent if-chain over the hot groups into a jump table
+// (BRX + BSSY/BSYNC per row; r01c profile: 30 % of all issued instructions).
+template <uint8_t KIND, int G>
+__device__ __forceinline__ void hot_update(uint64_t &h, uint64_t v, int slot) {
+  if constexpr (KIND == AK_SUM_F64) {
+    double x = u2d(h);
+    asm("{\n.reg .pred p;\nsetp.eq.s32 p, %1, %2;\n@p add.rn.f64 %0, %0, %3;\n}" : "+d"(x) : "r"(slot), "n"(G), "d"(u2d(v)));
+    h = d2u(x);
+  } else if constexpr (KIND == AK_SUM_I64) {
+    asm("{\n.reg .pred p;\nsetp.eq.s32 p, %1, %2;\n@p add.s64 %0, %0, %3;\n}" : "+l"(h) : "r"(slot), "n"(G), "l"(v));
+  } else {
+    h = agg_combine(KIND, h, slot == G ? v : agg_identity(KIND));
+  }
+}
+template <int G>
+__device__ __forceinline__ void hot_count(uint32_t &c, int slot) {
+  asm("{\n.reg .pred p;\nsetp.eq.s32 p, %1, %2;\n@p add.u32 %0, %0, 1;\n}" : "+r"(c) : "r"(slot), "n"(G));
+}
+
 template <class Q>
 struct AggSink : SinkBase {
   static constexpr int HOT = Q::hot;
@@ -126,21 +147,21 @@ struct AggSink : SinkBase {
   uint64_t hv[HOT][NA];
   uint32_t hc[HOT];
   int slot[kRows];
+  bool cold;            // warp-uniform: some row of this warp's tile slice is in a non-hot group
   uint64_t *lstate;
 
   template <int J, int TYPE>
   __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
     constexpr uint8_t kind = Q::agg_kind(J);
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-#pragma unroll
-      for (int g = 0; g < HOT; ++g)
-        if (slot[r] == g) hv[g][J] = agg_combine(kind, hv[g][J], acc[r]);
-    }
+    for (int r = 0; r < kRows; ++r)
+      static_for<0, HOT>([&](auto gg) { hot_update<kind, QS_IDX(gg)>(hv[QS_IDX(gg)][J], acc[r], slot[r]); });
     if constexpr (Q::grouped) {
+      if (cold) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r)
-        if (slot[r] >= HOT) atomic_update<kind>(&lstate[slot[r] * Q::words + 1 + J], acc[r]);
+        for (int r = 0; r < kRows; ++r)
+          if (slot[r] >= HOT) atomic_update<kind>(&lstate[slot[r] * Q::words + 1 + J], acc[r]);
+      }
     }
   }
 };
@@ -293,13 +314,22 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
       }
     }
     // row counts
+    sink.cold = false;
+    if constexpr (Q::grouped) {
+      bool c = false;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
+      for (int r = 0; r < kRows; ++r) c |= sink.slot[r] >= HOT;
+      sink.cold = __any_sync(0xffffffffu, c);
+    }
 #pragma unroll
-      for (int g = 0; g < HOT; ++g) sink.hc[g] += (sink.slot[r] == g) ? 1u : 0u;
-      if constexpr (Q::grouped) {
-        if (sink.slot[r] >= HOT)
-          atomicAdd(reinterpret_cast<unsigned long long *>(&M.lstate[sink.slot[r] * W]), 1ull);
+    for (int r = 0; r < kRows; ++r)
+      static_for<0, HOT>([&](auto gg) { hot_count<QS_IDX(gg)>(sink.hc[QS_IDX(gg)], sink.slot[r]); });
+    if constexpr (Q::grouped) {
+      if (sink.cold) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (sink.slot[r] >= HOT)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&M.lstate[sink.slot[r] * W]), 1ull);
       }
     }
     vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
