@@ -47,6 +47,22 @@ void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
 bool timing_enabled() { return g_timing.load(); }
 void record_ms(uint32_t family, float ms) { if (family < QS_K_FAMILIES) t_ms[family] = ms; }
 
+// Device the calling thread last resolved through device(): where dev_malloc / dev_free go.
+static thread_local Device *t_dev = nullptr;
+
+cudaError_t dev_malloc_bytes(void **p, size_t bytes) {
+  Device *d = t_dev;
+  if (!d || !d->pool) return cudaErrorInvalidDevice;
+  return cudaMallocFromPoolAsync(p, bytes ? bytes : 256, d->pool, d->stream);
+}
+
+cudaError_t dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  Device *d = t_dev;
+  if (!d || !d->pool) return cudaFree(p);     // after shutdown: synchronous free is still legal
+  return cudaFreeAsync(p, d->stream);
+}
+
 Device *device(int dev) {
   if (t_sc) return &t_sc->dev;
   if (!g_inited) {
@@ -55,6 +71,7 @@ Device *device(int dev) {
   }
   for (auto &d : g_devices) if (d.id == dev) {
     if (cudaSetDevice(dev) != cudaSuccess) { set_error(QSGPU_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    t_dev = &d;
     return &d;
   }
   set_error(QSGPU_ERR_INVALID, "device was not passed to qsgpu_init");
@@ -250,6 +267,20 @@ int qsgpu_init(int n_dev, const int *dev_ids) {
     d.smem_per_sm = prop.sharedMemPerMultiprocessor;
     d.smem_per_block_optin = prop.sharedMemPerBlockOptin;
     QS_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    {
+      // Per-device stream-ordered arena: states, join tables and temporary relations are
+      // allocated and freed once per query, so cudaMalloc/cudaFree (a device-wide
+      // synchronisation each, ~0.7 ms apiece next to a large context; r01b call profile) must
+      // stay off the query path.  Freed blocks are kept (release threshold = max) and reused.
+      cudaMemPoolProps props{};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = id;
+      QS_CUDA(cudaMemPoolCreate(&d.pool, &props));
+      uint64_t keep = UINT64_MAX;
+      QS_CUDA(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     QS_CUDA(cudaMalloc(&d.d_error, 256));
     QS_CUDA(cudaMemset(d.d_error, 0, 256));
     QS_CUDA(cudaEventCreate(&d.ev0));
@@ -272,8 +303,10 @@ int qsgpu_shutdown(void) {
     cudaEventDestroy(d.ev1);
     cudaEventDestroy(d.ev_t0);
     cudaEventDestroy(d.ev_t1);
+    if (d.pool) cudaMemPoolDestroy(d.pool);
     cudaStreamDestroy(d.stream);
   }
+  t_dev = nullptr;
   g_devices.clear();
   g_inited = false;
   return QSGPU_OK;
@@ -305,14 +338,15 @@ int qsgpu_last_kernel_ms(uint32_t family, float *ms) {
 int qsgpu_malloc(int dev, size_t bytes, void **dptr) {
   Device *d = device(dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
-  QS_CUDA(cudaMalloc(dptr, bytes ? bytes : 256));
+  QS_CUDA(dev_malloc(dptr, bytes ? bytes : 256));
+  QS_CUDA(cudaStreamSynchronize(d->stream));   // the caller may use the block on any stream
   return QSGPU_OK;
 }
 int qsgpu_free(int dev, void *dptr) {
   Device *d = device(dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   QS_CUDA(cudaStreamSynchronize(d->stream));
-  QS_CUDA(cudaFree(dptr));
+  QS_CUDA(dev_free(dptr));
   return QSGPU_OK;
 }
 int qsgpu_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes) {
@@ -374,7 +408,7 @@ static int relation_new(int dev, uint32_t n_attrs, const qs_attr *attrs, qsgpu_r
     if (a.width == 0) { set_error(QSGPU_ERR_INVALID, "zero-width attribute"); return QSGPU_ERR_INVALID; }
     r->attrs.push_back(a);
   }
-  QS_CUDA(cudaMalloc(&r->d_rows, 256));
+  QS_CUDA(dev_malloc(&r->d_rows, 256));
   QS_CUDA(cudaMemsetAsync(r->d_rows, 0, 256, d->stream));
   *out = r.release();
   return QSGPU_OK;
@@ -389,8 +423,8 @@ int qsgpu_relation_create(int dev, uint32_t n_attrs, const qs_attr *attrs, uint6
   r->owns_memory = true;
   for (auto &a : r->attrs) {
     char *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, padded_bytes(capacity_rows, a.width));
-    if (e != cudaSuccess) { qsgpu_relation_destroy(r); return cuda_fail(e, "cudaMalloc(relation column)"); }
+    cudaError_t e = dev_malloc(&p, padded_bytes(capacity_rows, a.width));
+    if (e != cudaSuccess) { qsgpu_relation_destroy(r); return cuda_fail(e, "dev_malloc(relation column)"); }
     r->cols.push_back(p);
   }
   *out = r;
@@ -424,9 +458,11 @@ int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs, void *c
 int qsgpu_relation_destroy(qsgpu_relation_t rel) {
   if (!rel) return QSGPU_OK;
   Device *d = device(rel->dev);
-  if (d) cudaStreamSynchronize(d->stream);
-  if (rel->owns_memory) for (char *p : rel->cols) cudaFree(p);
-  cudaFree(rel->d_rows);
+  // owned columns are freed in stream order; wrapped ones belong to the caller, who may release
+  // them as soon as this returns
+  if (d && !rel->owns_memory) cudaStreamSynchronize(d->stream);
+  if (rel->owns_memory) for (char *p : rel->cols) dev_free(p);
+  dev_free(rel->d_rows);
   delete rel;
   return QSGPU_OK;
 }
@@ -492,7 +528,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
       case QS_ENC_STRIDED: {
         void *tmp = nullptr;
         const size_t bytes = n_rows ? (n_rows - 1) * s.stride + w : 0;
-        e = cudaMalloc(&tmp, bytes + 16);
+        e = dev_malloc(&tmp, bytes + 16);
         if (e == cudaSuccess) { scratch.push_back(tmp); e = cudaMemcpyAsync(tmp, s.host, bytes, cudaMemcpyHostToDevice, d->stream); }
         if (e == cudaSuccess) { e = launch_decode_strided(dst, tmp, n_rows, s.stride, w, d->stream); count_launch(); }
         break;
@@ -500,8 +536,8 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
       case QS_ENC_DICT: {
         if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; break; }
         void *codes = nullptr, *dict = nullptr;
-        e = cudaMalloc(&codes, n_rows * s.code_width + 16);
-        if (e == cudaSuccess) { scratch.push_back(codes); e = cudaMalloc(&dict, static_cast<size_t>(s.dict_entries) * w + 16); }
+        e = dev_malloc(&codes, n_rows * s.code_width + 16);
+        if (e == cudaSuccess) { scratch.push_back(codes); e = dev_malloc(&dict, static_cast<size_t>(s.dict_entries) * w + 16); }
         if (e == cudaSuccess) { scratch.push_back(dict); e = cudaMemcpyAsync(codes, s.host, n_rows * s.code_width, cudaMemcpyHostToDevice, d->stream); }
         if (e == cudaSuccess) e = cudaMemcpyAsync(dict, s.dict, static_cast<size_t>(s.dict_entries) * w, cudaMemcpyHostToDevice, d->stream);
         if (e == cudaSuccess) { e = launch_decode_dict(dst, codes, dict, n_rows, s.code_width, w, s.dict_entries, d->stream); count_launch(); }
@@ -510,7 +546,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
       case QS_ENC_TRUNCATED: {
         if ((w != 4 && w != 8) || (s.code_width != 1 && s.code_width != 2 && s.code_width != 4)) { set_error(QSGPU_ERR_INVALID, "truncation applies to INT/LONG with 1/2/4-byte codes"); rc = QSGPU_ERR_INVALID; break; }
         void *codes = nullptr;
-        e = cudaMalloc(&codes, n_rows * s.code_width + 16);
+        e = dev_malloc(&codes, n_rows * s.code_width + 16);
         if (e == cudaSuccess) { scratch.push_back(codes); e = cudaMemcpyAsync(codes, s.host, n_rows * s.code_width, cudaMemcpyHostToDevice, d->stream); }
         if (e == cudaSuccess) { e = launch_decode_truncated(dst, codes, n_rows, s.code_width, w, d->stream); count_launch(); }
         break;
@@ -522,7 +558,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
     if (rc == QSGPU_OK && e != cudaSuccess) rc = cuda_fail(e, "qsgpu_stage_block");
   }
   cudaStreamSynchronize(d->stream);     // host stripes may be unpinned / reused by the caller
-  for (void *p : scratch) cudaFree(p);
+  for (void *p : scratch) dev_free(p);
   if (rc != QSGPU_OK) return rc;
   return qsgpu_relation_set_num_rows(rel, rel->host_rows + n_rows);
 }
@@ -550,16 +586,15 @@ int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type, int64_t min_val
   f->d.max_value = max_value;
   f->d.cardinality = cardinality;
   f->d.is_anti = is_anti ? 1 : 0;
-  QS_CUDA(cudaMalloc(&f->d.words, f->n_words * 8 + 64));
+  QS_CUDA(dev_malloc(&f->d.words, f->n_words * 8 + 64));
   QS_CUDA(cudaMemsetAsync(f->d.words, 0, f->n_words * 8 + 64, d->stream));
   *out = f.release();
   return QSGPU_OK;
 }
 int qsgpu_lip_destroy(qsgpu_lip_t lip) {
   if (!lip) return QSGPU_OK;
-  Device *d = device(lip->dev);
-  if (d) cudaStreamSynchronize(d->stream);
-  cudaFree(lip->d.words);
+  device(lip->dev);
+  dev_free(lip->d.words);
   delete lip;
   return QSGPU_OK;
 }
@@ -788,26 +823,26 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   }
 
   if (t_sc) { *out = s.release(); return QSGPU_OK; }   // selfcheck: description only, no device memory
-  QS_CUDA(cudaMalloc(&A.n_groups, 256));
+  QS_CUDA(dev_malloc(&A.n_groups, 256));
   QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 256, d->stream));
-  QS_CUDA(cudaMalloc(&s->d_done, 256));
+  QS_CUDA(dev_malloc(&s->d_done, 256));
   QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
-  QS_CUDA(cudaMalloc(&s->d_idx_count, 256));
+  QS_CUDA(dev_malloc(&s->d_idx_count, 256));
   if (spec->strategy == QS_AGG_SINGLE_STATE || spec->strategy == QS_AGG_COMPACT_KEY) {
     s->max_ctas = static_cast<uint32_t>(d->sm_count) * 2;
     const size_t prow = static_cast<size_t>(A.partial_rows) * A.words * 8;
-    QS_CUDA(cudaMalloc(&A.partials, prow * s->max_ctas));
+    QS_CUDA(dev_malloc(&A.partials, prow * s->max_ctas));
     // every partial row starts as (and is reset to, by k_merge_partials) the identity, so rows of
     // groups a CTA never met contribute nothing to the fold
     QS_CUDA(launch_fill_identity(A.partials, static_cast<uint64_t>(A.partial_rows) * s->max_ctas, A, d->stream));
     count_launch();
     A.dir_cap = 1024;
-    QS_CUDA(cudaMalloc(&A.dir_keys, A.dir_cap * 8));
-    QS_CUDA(cudaMalloc(&A.dir_gid, A.dir_cap * 4));
+    QS_CUDA(dev_malloc(&A.dir_keys, A.dir_cap * 8));
+    QS_CUDA(dev_malloc(&A.dir_gid, A.dir_cap * 4));
     QS_CUDA(cudaMemsetAsync(A.dir_gid, 0xff, A.dir_cap * 4, d->stream));
-    QS_CUDA(cudaMalloc(&A.gid_keys, kCompactMaxGroups * 8));
+    QS_CUDA(dev_malloc(&A.gid_keys, kCompactMaxGroups * 8));
     QS_CUDA(cudaMemsetAsync(A.gid_keys, 0, kCompactMaxGroups * 8, d->stream));
-    QS_CUDA(cudaMalloc(&A.states, prow));
+    QS_CUDA(dev_malloc(&A.states, prow));
     A.cap = A.partial_rows;
     QS_CUDA(launch_fill_identity(A.states, A.partial_rows, A, d->stream));
     count_launch();
@@ -818,11 +853,11 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
       uint64_t cap = 1024;
       while (cap < want) cap <<= 1;
       A.cap = cap;
-      QS_CUDA(cudaMalloc(&A.tags, cap * 4));
+      QS_CUDA(dev_malloc(&A.tags, cap * 4));
       QS_CUDA(cudaMemsetAsync(A.tags, 0, cap * 4, d->stream));
-      QS_CUDA(cudaMalloc(&A.keys, cap * A.key_words * 8));
+      QS_CUDA(dev_malloc(&A.keys, cap * A.key_words * 8));
     }
-    QS_CUDA(cudaMalloc(&A.states, A.cap * A.words * 8));
+    QS_CUDA(dev_malloc(&A.states, A.cap * A.words * 8));
     QS_CUDA(launch_fill_identity(A.states, A.cap, A, d->stream));
     count_launch();
   }
@@ -846,16 +881,16 @@ static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
   while (cap < worst * 2) cap <<= 1;
   AggDesc B = A;
   B.cap = cap;
-  QS_CUDA(cudaMalloc(&B.tags, cap * 4));
+  QS_CUDA(dev_malloc(&B.tags, cap * 4));
   QS_CUDA(cudaMemsetAsync(B.tags, 0, cap * 4, d->stream));
-  QS_CUDA(cudaMalloc(&B.keys, cap * A.key_words * 8));
-  QS_CUDA(cudaMalloc(&B.states, cap * A.words * 8));
+  QS_CUDA(dev_malloc(&B.keys, cap * A.key_words * 8));
+  QS_CUDA(dev_malloc(&B.states, cap * A.words * 8));
   QS_CUDA(launch_fill_identity(B.states, cap, B, d->stream));
   QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 4, d->stream));
   QS_CUDA(launch_rehash(A, B, d->stream));
   count_launch(2);
   QS_CUDA(cudaStreamSynchronize(d->stream));
-  cudaFree(A.tags); cudaFree(A.keys); cudaFree(A.states);
+  dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
   A = B;
   return QSGPU_OK;
 }
@@ -935,8 +970,8 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
 static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
   AggDesc &A = s->A;
   if (s->idx_cap < A.cap) {
-    if (s->d_idx) cudaFree(s->d_idx);
-    QS_CUDA(cudaMalloc(&s->d_idx, A.cap * 8 + 64));
+    if (s->d_idx) dev_free(s->d_idx);
+    QS_CUDA(dev_malloc(&s->d_idx, A.cap * 8 + 64));
     s->idx_cap = A.cap;
   }
   QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
@@ -980,10 +1015,10 @@ int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys, u
   int st = collect_groups(state, d, &n);
   if (st) return st;
   if (state->exp_cap < n || !state->d_exp_states) {
-    if (state->d_exp_states) { cudaFree(state->d_exp_states); cudaFree(state->d_exp_keys); }
+    if (state->d_exp_states) { dev_free(state->d_exp_states); dev_free(state->d_exp_keys); }
     const uint64_t cap = std::max<uint64_t>(n, 1024);
-    QS_CUDA(cudaMalloc(&state->d_exp_states, cap * A.words * 8));
-    QS_CUDA(cudaMalloc(&state->d_exp_keys, cap * (*key_words) * 8));
+    QS_CUDA(dev_malloc(&state->d_exp_states, cap * A.words * 8));
+    QS_CUDA(dev_malloc(&state->d_exp_keys, cap * (*key_words) * 8));
     state->exp_cap = cap;
   }
   QS_CUDA(launch_gather_rows(A.states, A.keys, A.words, A.key_words, state->d_idx, n, state->d_exp_states,
@@ -1081,12 +1116,11 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
 
 int qsgpu_agg_destroy(qsgpu_agg_state_t s) {
   if (!s) return QSGPU_OK;
-  Device *d = device(s->dev);
-  if (d) cudaStreamSynchronize(d->stream);
+  device(s->dev);
   AggDesc &A = s->A;
-  cudaFree(A.partials); cudaFree(A.dir_keys); cudaFree(A.dir_gid); cudaFree(A.n_groups); cudaFree(A.gid_keys);
-  cudaFree(A.tags); cudaFree(A.keys); cudaFree(A.states);
-  cudaFree(s->d_done); cudaFree(s->d_idx); cudaFree(s->d_idx_count); cudaFree(s->d_exp_states); cudaFree(s->d_exp_keys);
+  dev_free(A.partials); dev_free(A.dir_keys); dev_free(A.dir_gid); dev_free(A.n_groups); dev_free(A.gid_keys);
+  dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
+  dev_free(s->d_done); dev_free(s->d_idx); dev_free(s->d_idx_count); dev_free(s->d_exp_states); dev_free(s->d_exp_keys);
   delete s;
   return QSGPU_OK;
 }
@@ -1104,8 +1138,8 @@ int qsgpu_join_create(int dev, uint32_t key_type, uint64_t estimated_num_entries
   t->J.cap = cap;
   t->J.error_flag = d->d_error;
   t->J.key_ltype = key_type == QS_INT ? V_I32 : V_I64;
-  QS_CUDA(cudaMalloc(&t->J.slots, cap * sizeof(JoinSlot)));
-  QS_CUDA(cudaMalloc(&t->J.n_entries, 256));
+  QS_CUDA(dev_malloc(&t->J.slots, cap * sizeof(JoinSlot)));
+  QS_CUDA(dev_malloc(&t->J.n_entries, 256));
   QS_CUDA(cudaMemsetAsync(t->J.n_entries, 0, 256, d->stream));
   QS_CUDA(launch_join_clear(t->J, d->stream));
   count_launch();
@@ -1210,10 +1244,9 @@ int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t pr
 
 int qsgpu_join_destroy(qsgpu_join_table_t t) {
   if (!t) return QSGPU_OK;
-  Device *d = device(t->dev);
-  if (d) cudaStreamSynchronize(d->stream);
-  cudaFree(t->J.slots);
-  cudaFree(t->J.n_entries);
+  device(t->dev);
+  dev_free(t->J.slots);
+  dev_free(t->J.n_entries);
   delete t;
   return QSGPU_OK;
 }

@@ -255,7 +255,7 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   D.n_parts = n_parts;
   D.n_rows = n;
   unsigned long long *d_buf = nullptr;
-  QS_CUDA(cudaMalloc(&d_buf, 2ull * n_parts * 8 + 64));
+  QS_CUDA(dev_malloc(&d_buf, 2ull * n_parts * 8 + 64));
   QS_CUDA(cudaMemsetAsync(d_buf, 0, 2ull * n_parts * 8, d->stream));
   D.hist = d_buf;
   D.cursor = d_buf + n_parts;
@@ -268,12 +268,12 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
     std::vector<unsigned long long> hist(n_parts), cur(n_parts);
     cudaError_t e = cudaMemcpyAsync(hist.data(), D.hist, n_parts * 8, cudaMemcpyDeviceToHost, d->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) { cudaFree(d_buf); return cuda_fail(e, "partition histogram"); }
+    if (e != cudaSuccess) { dev_free(d_buf); return cuda_fail(e, "partition histogram"); }
     uint64_t acc = 0;
     for (uint32_t p = 0; p < n_parts; ++p) { host_offsets[p] = acc; cur[p] = acc; acc += hist[p]; }
     host_offsets[n_parts] = acc;
     e = cudaMemcpyAsync(D.cursor, cur.data(), n_parts * 8, cudaMemcpyHostToDevice, d->stream);
-    if (e != cudaSuccess) { cudaFree(d_buf); return cuda_fail(e, "partition cursors"); }
+    if (e != cudaSuccess) { dev_free(d_buf); return cuda_fail(e, "partition cursors"); }
     const size_t smem = ((n_parts + 1) & ~1u) * 4 + n_parts * 8;
     k_part_scatter<<<grid, kBlock, smem, d->stream>>>(D);
     count_launch(2);
@@ -285,7 +285,7 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
       record_ms(QS_K_PARTITION, ms);
     }
     e = cudaStreamSynchronize(d->stream);
-    cudaFree(d_buf);
+    dev_free(d_buf);
     if (e != cudaSuccess) return cuda_fail(e, "partition scatter");
   }
   return qsgpu_relation_set_num_rows(output, n);
@@ -328,10 +328,10 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
 
   uint64_t *pk = nullptr, *cand = nullptr;
   unsigned long long *hist = nullptr;
-  auto cleanup = [&]() { cudaFree(pk); cudaFree(cand); cudaFree(hist); };
-  cudaError_t e = cudaMalloc(&pk, n * 8 + 64);
-  if (e == cudaSuccess) e = cudaMalloc(&cand, kTopkMaxCand * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&hist, 257 * 8);
+  auto cleanup = [&]() { dev_free(pk); dev_free(cand); dev_free(hist); };
+  cudaError_t e = dev_malloc(&pk, n * 8 + 64);
+  if (e == cudaSuccess) e = dev_malloc(&cand, kTopkMaxCand * 8);
+  if (e == cudaSuccess) e = dev_malloc(&hist, 257 * 8);
   if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k scratch"); }
   const bool on = timing_enabled();
   if (on) cudaEventRecord(d->ev0, d->stream);

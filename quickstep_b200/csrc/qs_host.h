@@ -72,9 +72,17 @@ struct Device {
   uint32_t *d_error = nullptr;        // sticky device-side error word
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // per-kernel-family timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // qsgpu_timer_start/stop
+  cudaMemPool_t pool = nullptr;       // stream-ordered arena for everything allocated per query
 };
 
 Device *device(int dev);               // nullptr (+ last error) when unavailable
+// Stream-ordered allocation on the device the calling thread last resolved with device():
+// ordered on that device's library stream, served from its retained pool (no device sync).
+cudaError_t dev_malloc_bytes(void **p, size_t bytes);
+template <class T> inline cudaError_t dev_malloc(T **p, size_t bytes) {
+  return dev_malloc_bytes(reinterpret_cast<void **>(p), bytes);
+}
+cudaError_t dev_free(void *p);
 void set_error(int status, const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch(int n = 1);
