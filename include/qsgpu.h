@@ -156,7 +156,7 @@ int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
  *                     (storage/CompressedBlockBuilder.cpp:434-506)
  * The block is decoded to native width on the device by the K0 kernels.
  */
-enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3 };
+/* enum { QS_ENC_PLAIN, QS_ENC_STRIDED, QS_ENC_DICT, QS_ENC_TRUNCATED }: qsgpu_types.h */
 
 typedef struct qs_stage_desc {
   uint32_t attr;         /* target attribute                                   */
@@ -174,6 +174,25 @@ typedef struct qs_stage_desc {
  * the next work order reads it. */
 int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows,
                       const qs_stage_desc *descs, uint32_t n_desc);
+
+/*
+ * Batched form for a run of storage blocks (what a GPU work order that covers
+ * many 4 MB blocks stages at once).  Each block is described by the extent of
+ * its memory (StorageBlock::getMemory / getSize, storage/StorageBlockBase.hpp)
+ * and the per-attribute stripes inside it; the whole image travels in ONE
+ * host-to-device copy (runs of blocks that are contiguous in host memory are
+ * merged into one copy), and ONE kernel decodes every stripe of the batch to
+ * native width.  descs[i].host / .dict must point inside [host, host+bytes).
+ */
+typedef struct qs_block_image {
+  const void *host;            /* first byte of the block image                 */
+  uint64_t bytes;              /* bytes of the image to copy                    */
+  uint64_t n_rows;             /* tuples in the block                           */
+  const qs_stage_desc *descs;  /* n_desc entries, one per attribute             */
+} qs_block_image;
+
+int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks,
+                       const qs_block_image *blocks, uint32_t n_desc);
 
 /* ----------------------------------------------------------- LIP filters  */
 /*

@@ -53,6 +53,9 @@ enum {
   QS_AGG_COLLISION_FREE = 3
 };
 
+/* Physical encodings of a staged block stripe (see qsgpu_stage_block in qsgpu.h). */
+enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3 };
+
 /* Join types (relational_operators/HashJoinOperator.hpp:82-87). */
 enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };
 

@@ -63,6 +63,11 @@ class qs_stage_desc(C.Structure):
                 ("dict_entries", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class qs_block_image(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("bytes", C.c_uint64), ("n_rows", C.c_uint64),
+                ("descs", C.POINTER(qs_stage_desc))]
+
+
 class qs_lip_ref(C.Structure):
     _fields_ = [("lip", C.c_void_p), ("attr", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -116,6 +121,7 @@ SIGNATURES = {
     "qsgpu_relation_wrap": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), _VPP, C.c_uint64, _VPP]),
     "qsgpu_relation_read": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, _VP]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
+    "qsgpu_stage_blocks": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
     "qsgpu_lip_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_uint64, C.c_int, _VPP]),
     "qsgpu_lip_destroy": (C.c_int, [_VP]),
     "qsgpu_lip_num_words": (C.c_int, [_VP, _U64P]),

@@ -563,6 +563,101 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
   return qsgpu_relation_set_num_rows(rel, rel->host_rows + n_rows);
 }
 
+int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks, const qs_block_image *blocks, uint32_t n_desc) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (!rel->owns_memory) { set_error(QSGPU_ERR_INVALID, "cannot stage into a wrapped relation"); return QSGPU_ERR_INVALID; }
+  if (n_desc != rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "qsgpu_stage_blocks must stage every attribute of the relation"); return QSGPU_ERR_INVALID; }
+  if (n_blocks == 0) return QSGPU_OK;
+  uint64_t total_rows = 0, image_bytes = 0;
+  std::vector<uint64_t> img_off(n_blocks);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    if (!blocks[b].host || !blocks[b].descs) { set_error(QSGPU_ERR_INVALID, "block image without memory / descriptors"); return QSGPU_ERR_INVALID; }
+    img_off[b] = image_bytes;
+    image_bytes += (blocks[b].bytes + 15) & ~15ull;
+    total_rows += blocks[b].n_rows;
+  }
+  if (rel->host_rows + total_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "relation capacity exceeded while staging"); return QSGPU_ERR_CAPACITY; }
+  KernelTimer timer(d, QS_K_STAGE);
+  char *d_img = nullptr;
+  StageSeg *d_segs = nullptr;
+  QS_CUDA(dev_malloc(&d_img, image_bytes + 64));
+  // ---- H2D: one copy per run of blocks that are contiguous in host memory (a buffer-pool slab)
+  for (uint32_t b = 0; b < n_blocks;) {
+    uint32_t e = b + 1;
+    uint64_t bytes = blocks[b].bytes;
+    while (e < n_blocks && (blocks[e - 1].bytes & 15) == 0 &&
+           static_cast<const char *>(blocks[e].host) == static_cast<const char *>(blocks[e - 1].host) + blocks[e - 1].bytes) {
+      bytes += blocks[e].bytes;
+      ++e;
+    }
+    cudaError_t ce = cudaMemcpyAsync(d_img + img_off[b], blocks[b].host, bytes, cudaMemcpyHostToDevice, d->stream);
+    if (ce != cudaSuccess) { dev_free(d_img); return cuda_fail(ce, "qsgpu_stage_blocks H2D"); }
+    b = e;
+  }
+  // ---- one segment per (block, attribute)
+  std::vector<StageSeg> segs;
+  segs.reserve(static_cast<size_t>(n_blocks) * n_desc);
+  uint64_t row_base = rel->host_rows, tiles = 0;
+  int rc = QSGPU_OK;
+  for (uint32_t b = 0; b < n_blocks && rc == QSGPU_OK; ++b) {
+    const qs_block_image &B = blocks[b];
+    const char *h0 = static_cast<const char *>(B.host);
+    for (uint32_t i = 0; i < n_desc; ++i) {
+      const qs_stage_desc &s = B.descs[i];
+      if (s.attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "stage: attribute out of range"); rc = QSGPU_ERR_INVALID; break; }
+      const uint32_t w = rel->attrs[s.attr].width;
+      const char *hs = static_cast<const char *>(s.host);
+      uint64_t need = 0;
+      switch (s.encoding) {
+        case QS_ENC_PLAIN: need = B.n_rows * w; break;
+        case QS_ENC_STRIDED: need = B.n_rows ? (B.n_rows - 1) * s.stride + w : 0; break;
+        case QS_ENC_DICT: case QS_ENC_TRUNCATED:
+          if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; }
+          if (s.encoding == QS_ENC_TRUNCATED && w != 4 && w != 8) { set_error(QSGPU_ERR_INVALID, "truncation applies to INT/LONG"); rc = QSGPU_ERR_INVALID; }
+          need = B.n_rows * s.code_width;
+          break;
+        default: set_error(QSGPU_ERR_INVALID, "unknown staging encoding"); rc = QSGPU_ERR_INVALID;
+      }
+      if (rc != QSGPU_OK) break;
+      if (hs < h0 || hs + need > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: stripe lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+      StageSeg g{};
+      g.dst = rel->cols[s.attr] + row_base * w;
+      g.src = d_img + img_off[b] + (hs - h0);
+      g.n_rows = B.n_rows;
+      g.tile_begin = tiles;
+      g.encoding = s.encoding;
+      g.cw = s.code_width; g.vw = w; g.stride = s.stride; g.dict_entries = s.dict_entries;
+      const bool pow2 = w == 4 || w == 8;
+      bool val_al = pow2 && (reinterpret_cast<uintptr_t>(g.dst) % w) == 0;
+      if (s.encoding == QS_ENC_PLAIN) val_al = val_al && (reinterpret_cast<uintptr_t>(g.src) % w) == 0;
+      if (s.encoding == QS_ENC_DICT) {
+        const char *hd = static_cast<const char *>(s.dict);
+        if (!hd || s.dict_entries == 0 || hd < h0 || hd + static_cast<uint64_t>(s.dict_entries) * w > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: dictionary lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+        g.dict = d_img + img_off[b] + (hd - h0);
+        val_al = val_al && (reinterpret_cast<uintptr_t>(g.dict) % w) == 0;
+      }
+      const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
+      g.aligned = (val_al ? 1u : 0u) | (code_al ? 2u : 0u);
+      if (B.n_rows) { segs.push_back(g); tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows; }
+    }
+    row_base += B.n_rows;
+  }
+  if (rc == QSGPU_OK && !segs.empty()) {
+    cudaError_t ce = dev_malloc(&d_segs, segs.size() * sizeof(StageSeg));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(StageSeg), cudaMemcpyHostToDevice, d->stream);
+    if (ce == cudaSuccess) { ce = launch_decode_segments(d_segs, static_cast<uint32_t>(segs.size()), tiles, d->sm_count, d->stream); count_launch(); }
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "qsgpu_stage_blocks decode");
+  }
+  cudaStreamSynchronize(d->stream);     // host block memory and `segs` may be reused by the caller
+  dev_free(d_img);
+  dev_free(d_segs);
+  if (rc != QSGPU_OK) return rc;
+  return qsgpu_relation_set_num_rows(rel, rel->host_rows + total_rows);
+}
+
 /* ------------------------------------------------------------ LIP filters */
 int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type, int64_t min_value, int64_t max_value,
                      uint64_t cardinality, int is_anti, qsgpu_lip_t *out) {

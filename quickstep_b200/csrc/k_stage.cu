@@ -56,6 +56,82 @@ __global__ void k_decode_strided(char *dst, const char *slots, uint64_t n, uint3
   }
 }
 
+// Batched form: every (block, attribute) stripe of a staging batch is one
+// StageSeg; the batch is cut into 4096-row tiles and a persistent grid walks
+// the tiles (binary search tile -> segment), so a whole relation's blocks are
+// decoded by ONE launch instead of one per stripe.
+// Code stripes inside a block image start wherever the previous stripe ended
+// (stripe i is max_tuples x attribute_size(i) bytes), so 2/4-byte codes may be misaligned.
+__device__ __forceinline__ uint32_t load_code_any(const unsigned char *codes, uint64_t i, uint32_t cw, bool aligned) {
+  if (aligned || cw == 1) return load_code(codes, i, cw);
+  uint32_t v = 0;
+  for (uint32_t b = 0; b < cw; ++b) v |= static_cast<uint32_t>(codes[i * cw + b]) << (8 * b);
+  return v;
+}
+
+__device__ __forceinline__ void copy_vw(char *d, const char *src, uint32_t vw, bool aligned) {
+  if (aligned && vw == 8) *reinterpret_cast<uint64_t *>(d) = *reinterpret_cast<const uint64_t *>(src);
+  else if (aligned && vw == 4) *reinterpret_cast<uint32_t *>(d) = *reinterpret_cast<const uint32_t *>(src);
+  else for (uint32_t b = 0; b < vw; ++b) d[b] = src[b];
+}
+
+__global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, uint32_t n_segs, uint64_t n_tiles) {
+  __shared__ StageSeg sg;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t lo = 0, hi = n_segs - 1;            // last segment with tile_begin <= tile
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (segs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+      }
+      sg = segs[lo];
+    }
+    __syncthreads();
+    const uint64_t r0 = (tile - sg.tile_begin) * kStageTileRows;
+    const uint64_t r1 = min(sg.n_rows, r0 + kStageTileRows);
+    const bool al = (sg.aligned & 1) != 0;
+    const uint32_t vw = sg.vw;
+    if (sg.encoding == QS_ENC_PLAIN && al && ((vw * r0) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(sg.src) | reinterpret_cast<uintptr_t>(sg.dst)) & 15) == 0) {
+      // 16-byte vector copy of the tile, byte tail
+      const uint64_t b0 = r0 * vw, b1 = r1 * vw;
+      const uint64_t n16 = (b1 - b0) >> 4;
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(sg.src + b0);
+      uint4 *d4 = reinterpret_cast<uint4 *>(sg.dst + b0);
+      for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+      for (uint64_t b = b0 + (n16 << 4) + threadIdx.x; b < b1; b += blockDim.x) sg.dst[b] = sg.src[b];
+      continue;
+    }
+    for (uint64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+      char *d = sg.dst + i * vw;
+      switch (sg.encoding) {
+        case QS_ENC_PLAIN: copy_vw(d, sg.src + i * vw, vw, al); break;
+        case QS_ENC_STRIDED: copy_vw(d, sg.src + i * sg.stride, vw, false); break;
+        case QS_ENC_DICT: {
+          uint32_t c = load_code_any(reinterpret_cast<const unsigned char *>(sg.src), i, sg.cw, (sg.aligned & 2) != 0);
+          if (c >= sg.dict_entries) c = sg.dict_entries - 1;
+          copy_vw(d, sg.dict + static_cast<uint64_t>(c) * vw, vw, al);
+          break;
+        }
+        default: {   // QS_ENC_TRUNCATED
+          const uint32_t c = load_code_any(reinterpret_cast<const unsigned char *>(sg.src), i, sg.cw, (sg.aligned & 2) != 0);
+          if (vw == 8) *reinterpret_cast<int64_t *>(d) = static_cast<int64_t>(c);
+          else *reinterpret_cast<int32_t *>(d) = static_cast<int32_t>(c);
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_decode_segments(const StageSeg *d_segs, uint32_t n_segs, uint64_t n_tiles, int sm_count,
+                                   cudaStream_t st) {
+  if (n_segs == 0 || n_tiles == 0) return cudaSuccess;
+  const uint64_t grid = n_tiles < static_cast<uint64_t>(sm_count) * 8 ? n_tiles : static_cast<uint64_t>(sm_count) * 8;
+  k_decode_segments<<<static_cast<unsigned>(grid), 256, 0, st>>>(d_segs, n_segs, n_tiles);
+  return cudaGetLastError();
+}
+
 static int grid_for(uint64_t n) {
   uint64_t g = (n + 255) / 256;
   if (g > 148ull * 8) g = 148ull * 8;

@@ -52,6 +52,19 @@ struct FinalizeDesc {
   int keys_are_slots;          // collision free: key value == slot index
 };
 
+// One (block, attribute) stripe of a batched staging call (qsgpu_stage_blocks).
+struct __align__(16) StageSeg {
+  char *dst;                   // native-width destination (column base + first row * vw)
+  const char *src;             // stripe / first slot inside the device copy of the block image
+  const char *dict;            // QS_ENC_DICT: sorted values
+  uint64_t n_rows;
+  uint64_t tile_begin;         // first tile (kStageTileRows rows each) of this segment in the batch
+  uint32_t encoding;           // QS_ENC_*
+  uint32_t cw, vw, stride, dict_entries;
+  uint32_t aligned;            // src (and dict) are vw-aligned: whole-value loads are legal
+};
+constexpr uint32_t kStageTileRows = 4096;
+
 #ifndef __CUDACC_RTC__
 // k_agg.cu
 size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words);
@@ -80,6 +93,8 @@ cudaError_t launch_decode_truncated(void *dst, const void *codes, uint64_t n, ui
                                     uint32_t value_width, cudaStream_t st);
 cudaError_t launch_decode_strided(void *dst, const void *slots, uint64_t n, uint32_t stride,
                                   uint32_t value_width, cudaStream_t st);
+cudaError_t launch_decode_segments(const StageSeg *d_segs, uint32_t n_segs, uint64_t n_tiles, int sm_count,
+                                   cudaStream_t st);
 #endif  // !__CUDACC_RTC__
 
 }  // namespace qs

@@ -139,6 +139,29 @@ class Relation:
                 descs[i].dict_entries = len(d["dict"])
         A.check(A.load().qsgpu_stage_block(self.h, n_rows, descs, len(descs_py)))
 
+    def stage_blocks(self, images):
+        """qsgpu_stage_blocks.  images: list of (memory: np.uint8 array, n_rows, descs) where descs is a
+        list of dicts(attr, encoding, offset, code_width, stride, dict_offset, dict_entries): byte
+        offsets of the stripe / dictionary inside `memory`."""
+        n_desc = len(self.schema)
+        imgs = (A.qs_block_image * len(images))()
+        keep = []
+        for b, (mem, n_rows, descs_py) in enumerate(images):
+            assert len(descs_py) == n_desc
+            descs = (A.qs_stage_desc * n_desc)()
+            base = mem.ctypes.data
+            for i, d in enumerate(descs_py):
+                descs[i].attr, descs[i].encoding = d["attr"], d["encoding"]
+                descs[i].host = base + d["offset"]
+                descs[i].code_width = d.get("code_width", 0)
+                descs[i].stride = d.get("stride", 0)
+                if d.get("dict_offset") is not None:
+                    descs[i].dict = base + d["dict_offset"]
+                    descs[i].dict_entries = d["dict_entries"]
+            keep.append(descs)
+            imgs[b].host, imgs[b].bytes, imgs[b].n_rows, imgs[b].descs = base, mem.nbytes, n_rows, descs
+        A.check(A.load().qsgpu_stage_blocks(self.h, len(images), imgs, n_desc))
+
     # -- access -----------------------------------------------------------
     @property
     def n_rows(self) -> int:

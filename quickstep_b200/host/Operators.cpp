@@ -1,0 +1,252 @@
+#include "Operators.hpp"
+
+namespace quickstep {
+
+std::uint64_t FLAGS_gpu_rows_per_workorder = 0;
+
+std::vector<DeviceExtent> InputFeed::take(StorageManager *sm) {
+  std::vector<DeviceExtent> out;
+  if (stored_) {
+    if (started_) return out;
+    started_ = true;
+    sm->deviceRelation(relation_);                 // K0: stage whatever is not resident yet (one batch)
+    DeviceExtent cur;
+    for (block_id b : relation_.getBlocksSnapshot()) {
+      const DeviceExtent e = sm->blockExtent(b);
+      if (cur.relation && cur.row_end == e.row_begin &&
+          (FLAGS_gpu_rows_per_workorder == 0 || e.row_end - cur.row_begin <= FLAGS_gpu_rows_per_workorder)) {
+        cur.row_end = e.row_end;                   // grow the run of adjacent blocks
+      } else {
+        if (cur.relation) out.push_back(cur);
+        cur = e;
+      }
+    }
+    if (cur.relation) out.push_back(cur);
+    return out;
+  }
+  for (block_id b : pending_) out.push_back(sm->blockExtent(b));
+  pending_.clear();
+  return out;
+}
+
+namespace {
+
+struct Lowered {
+  ExprSet es;
+  int predicate_root = -1;
+  std::vector<std::int32_t> roots;
+};
+
+void addPredicate(Lowered *L, const QueryContext::Predicate *p) {
+  if (!p) return;
+  const int off = L->es.append(p->exprs);
+  L->predicate_root = p->root + off;
+}
+
+void addScalars(Lowered *L, const QueryContext::ScalarGroup *g) {
+  if (!g) return;
+  const int off = L->es.append(g->exprs);
+  for (int r : g->roots) L->roots.push_back(r + off);
+}
+
+qs_scan makeScan(const DeviceExtent &in, const qs_expr_set *es, int predicate_root, const std::vector<qs_lip_ref> &lip_probe) {
+  qs_scan s{};
+  s.input = in.relation;
+  s.row_begin = in.row_begin;
+  s.row_end = in.row_end;
+  s.exprs = es;
+  s.predicate_root = predicate_root;
+  s.n_lip_probe = static_cast<std::uint32_t>(lip_probe.size());
+  s.lip_probe = lip_probe.empty() ? nullptr : lip_probe.data();
+  return s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ Select
+bool SelectOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                      StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  InsertDestination *dest = query_context->getInsertDestination(output_destination_index_);
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(
+        new SelectWorkOrder(query_id_, feed_.relation(), e, query_context->getPredicate(predicate_index_),
+                            simple_projection_ ? nullptr : &query_context->getScalarGroup(selection_index_),
+                            simple_projection_ ? &simple_selection_ : nullptr, dest,
+                            query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void SelectWorkOrder::execute() {
+  Lowered L;
+  addPredicate(&L, predicate_);
+  if (simple_selection_) {
+    for (attribute_id a : *simple_selection_) L.roots.push_back(L.es.attr(a, input_relation_.getAttributeById(a).type));
+  } else {
+    addScalars(&L, selection_);
+  }
+  const qs_expr_set es = L.es.view();
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  QS_CHECK_GPU(qsgpu_select(&scan, static_cast<std::uint32_t>(L.roots.size()), L.roots.data(),
+                            output_destination_->deviceRelation()));
+}
+
+// ---------------------------------------------------------- BuildLIPFilter
+bool BuildLIPFilterOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                              StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(
+        new BuildLIPFilterWorkOrder(query_id_, e, query_context->getPredicate(build_side_predicate_index_),
+                                    query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe),
+                                    query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kBuild)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void BuildLIPFilterWorkOrder::execute() {
+  Lowered L;
+  addPredicate(&L, build_side_predicate_);
+  const qs_expr_set es = L.es.view();
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  QS_CHECK_GPU(qsgpu_build_lip_filter(&scan, static_cast<std::uint32_t>(lip_build_.size()), lip_build_.data()));
+}
+
+// --------------------------------------------------------------- BuildHash
+bool BuildHashOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                         StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(
+        new BuildHashWorkOrder(query_id_, e, join_key_attributes_[0], query_context->getPredicate(build_predicate_index_),
+                               query_context->getJoinHashTable(hash_table_index_),
+                               query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe),
+                               query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kBuild)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void BuildHashWorkOrder::execute() {
+  Lowered L;
+  addPredicate(&L, predicate_);
+  const qs_expr_set es = L.es.view();
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  QS_CHECK_GPU(qsgpu_join_build(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attribute_),
+                                static_cast<std::uint32_t>(lip_build_.size()), lip_build_.empty() ? nullptr : lip_build_.data()));
+}
+
+// ---------------------------------------------------------------- HashJoin
+bool HashJoinOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                        StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  InsertDestination *dest = query_context->getInsertDestination(output_destination_index_);
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(
+        new HashJoinWorkOrder(query_id_, e, join_key_attributes_[0], query_context->getPredicate(residual_predicate_index_),
+                              &query_context->getScalarGroup(selection_index_),
+                              query_context->getJoinHashTable(hash_table_index_), dest, join_type_,
+                              query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void HashJoinWorkOrder::execute() {
+  Lowered L;
+  int residual_root = -1;
+  if (residual_predicate_) {
+    const int off = L.es.append(residual_predicate_->exprs);
+    residual_root = residual_predicate_->root + off;
+  }
+  addScalars(&L, selection_);
+  const qs_expr_set es = L.es.view();
+  const qs_scan scan = makeScan(probe_, &es, -1, lip_probe_);
+  std::uint32_t jt = QS_JOIN_INNER;
+  switch (join_type_) {
+    case JoinType::kInnerJoin: jt = QS_JOIN_INNER; break;
+    case JoinType::kLeftSemiJoin: jt = QS_JOIN_LEFT_SEMI; break;
+    case JoinType::kLeftAntiJoin: jt = QS_JOIN_LEFT_ANTI; break;
+    case JoinType::kLeftOuterJoin: jt = QS_JOIN_LEFT_OUTER; break;
+  }
+  QS_CHECK_GPU(qsgpu_join_probe(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attribute_), jt, residual_root,
+                                static_cast<std::uint32_t>(L.roots.size()), L.roots.data(),
+                                output_destination_->deviceRelation()));
+}
+
+// ------------------------------------------------------------- Aggregation
+bool AggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                           StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(
+        new AggregationWorkOrder(query_id_, e, query_context->getAggregationState(aggr_state_index_),
+                                 query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void AggregationWorkOrder::execute() {
+  QS_CHECK_GPU(qsgpu_agg_run(state_, input_.relation, input_.row_begin, input_.row_end,
+                             static_cast<std::uint32_t>(lip_probe_.size()), lip_probe_.empty() ? nullptr : lip_probe_.data()));
+}
+
+bool FinalizeAggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                                   StorageManager *, const tmb::client_id, tmb::MessageBus *) {
+  if (!started_) {
+    started_ = true;
+    container->addNormalWorkOrder(
+        new FinalizeAggregationWorkOrder(query_id_, query_context->getAggregationState(aggr_state_index_),
+                                         query_context->getInsertDestination(output_destination_index_)),
+        op_index_);
+  }
+  return true;
+}
+
+void FinalizeAggregationWorkOrder::execute() {
+  qsgpu_relation_t out = nullptr;
+  std::uint64_t mask = 0;
+  QS_CHECK_GPU(qsgpu_agg_finalize(state_, &out, &mask));
+  output_destination_->adopt(out);
+  output_destination_->null_mask = mask;
+}
+
+bool DestroyAggregationStateOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                                       StorageManager *, const tmb::client_id, tmb::MessageBus *) {
+  if (!started_) {
+    started_ = true;
+    const QueryContext::aggregation_state_id id = aggr_state_index_;
+    container->addNormalWorkOrder(new ContextCallWorkOrder(query_id_, [query_context, id] { query_context->destroyAggregationState(id); }),
+                                  op_index_);
+  }
+  return true;
+}
+
+bool DestroyHashOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context, StorageManager *,
+                                           const tmb::client_id, tmb::MessageBus *) {
+  if (!started_) {
+    started_ = true;
+    const QueryContext::join_hash_table_id id = hash_table_index_;
+    container->addNormalWorkOrder(new ContextCallWorkOrder(query_id_, [query_context, id] { query_context->destroyJoinHashTable(id); }),
+                                  op_index_);
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------- top-k
+bool SortMergeRunOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                            StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+    container->addNormalWorkOrder(new TopKWorkOrder(query_id_, e, &query_context->getSortConfig(sort_config_index_), top_k_,
+                                                    query_context->getInsertDestination(output_destination_index_)),
+                                  op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void TopKWorkOrder::execute() {
+  qsgpu_relation_t out = nullptr;
+  QS_CHECK_GPU(qsgpu_topk(input_.relation, static_cast<std::uint32_t>(config_->keys.size()), config_->keys.data(), top_k_, &out));
+  output_destination_->adopt(out);
+}
+
+}  // namespace quickstep

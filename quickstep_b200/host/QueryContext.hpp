@@ -1,0 +1,167 @@
+// Per-query execution state shared by the work orders of a query: the GPU twin
+// of query_execution/QueryContext.hpp:57-620 (built from serialization::QueryContext,
+// query_execution/QueryContext.cpp:57-171).  Same id spaces, same getters; what
+// differs is what an id resolves to:
+//   aggregation_state_id -> qsgpu_agg_state_t       (AggregationOperationState)
+//   join_hash_table_id   -> qsgpu_join_table_t      (JoinHashTable)
+//   lip_filter_id        -> qsgpu_lip_t             (LIPFilter)
+//   predicate_id / scalar_group_id -> expression sets (Predicate, vector<Scalar>)
+//   insert_destination_id -> InsertDestination over a device-resident temporary relation
+// Objects are owned here and released by the Destroy* work orders or with the
+// context, as in the reference.
+#pragma once
+
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "ExprSet.hpp"
+#include "QsTypes.hpp"
+#include "StorageManager.hpp"
+
+namespace quickstep {
+
+// storage/InsertDestination.hpp: the sink of Select / HashJoin / FinalizeAggregation.
+// The device relation is created on first use with the capacity the plan estimated.
+class InsertDestination {
+ public:
+  InsertDestination(const CatalogRelation *relation, std::uint64_t capacity_rows, StorageManager *sm)
+      : relation_(relation), capacity_(capacity_rows), sm_(sm) {}
+  const CatalogRelation &getRelation() const { return *relation_; }
+  // bit j set: aggregate j of a single-state aggregation saw no rows, its value is SQL NULL
+  // (AggregationHandleSum.cpp:134-143); written by FinalizeAggregationWorkOrder
+  std::uint64_t null_mask = 0;
+  qsgpu_relation_t deviceRelation() { sm_->createTemporary(*relation_, capacity_); return sm_->temporary(*relation_); }
+  // FinalizeAggregation / top-k create their output relation themselves
+  void adopt(qsgpu_relation_t handle) { sm_->adoptTemporary(*relation_, handle); }
+  // QueryManagerBase::markOperatorFinished -> getPartiallyFilledBlocks: the blocks to feed downstream
+  std::vector<block_id> getTouchedBlocks() { return {sm_->createTemporary(*relation_, capacity_)}; }
+
+ private:
+  const CatalogRelation *relation_;
+  std::uint64_t capacity_;
+  StorageManager *sm_;
+};
+
+class QueryContext {
+ public:
+  typedef std::uint32_t aggregation_state_id;
+  typedef std::int32_t insert_destination_id;
+  typedef std::uint32_t join_hash_table_id;
+  typedef std::int32_t lip_deployment_id;
+  typedef std::uint32_t lip_filter_id;
+  typedef std::int32_t predicate_id;
+  typedef std::int32_t scalar_group_id;
+  typedef std::uint32_t sort_config_id;
+  static constexpr insert_destination_id kInvalidInsertDestinationId = -1;
+  static constexpr lip_deployment_id kInvalidLIPDeploymentId = -1;
+  static constexpr predicate_id kInvalidPredicateId = -1;
+  static constexpr scalar_group_id kInvalidScalarGroupId = -1;
+
+  struct Predicate { ExprSet exprs; int root = -1; };
+  struct ScalarGroup { ExprSet exprs; std::vector<int> roots; };
+  // serialization::AggregationOperationState: aggregates, group-by, predicate, estimate, strategy
+  struct AggregationSpec {
+    ExprSet exprs;
+    int predicate_root = -1;
+    std::vector<qs_aggregate> aggregates;
+    std::vector<int> group_by_roots;
+    std::uint32_t strategy = QS_AGG_SINGLE_STATE;
+    std::uint64_t estimated_num_entries = 1024;
+    std::int64_t collision_free_max_key = -1;
+  };
+  // utility/lip_filter/LIPFilterDeployment.hpp: which filters an operator builds or probes, on which attribute
+  // (LIPFilter.proto:50-62: a deployment carries build entries and probe entries)
+  enum class LIPAction { kBuild, kProbe };
+  struct LIPEntry { lip_filter_id filter; attribute_id attr; };
+  struct LIPDeployment { std::vector<LIPEntry> build_entries, probe_entries; };
+  // SortConfiguration (+ LIMIT) of SortMergeRunOperator's top-k path
+  struct SortConfig { std::vector<qs_sort_key> keys; };
+
+  QueryContext(StorageManager *sm, int device) : sm_(sm), device_(device) {}
+  ~QueryContext() {
+    for (auto h : agg_states_) if (h) qsgpu_agg_destroy(h);
+    for (auto h : join_tables_) if (h) qsgpu_join_destroy(h);
+    for (auto h : lip_filters_) if (h) qsgpu_lip_destroy(h);
+  }
+  int device() const { return device_; }
+
+  // ---- construction (what QueryContext::QueryContext does from the proto)
+  predicate_id addPredicate(Predicate p) { predicates_.push_back(std::move(p)); return static_cast<predicate_id>(predicates_.size()) - 1; }
+  scalar_group_id addScalarGroup(ScalarGroup g) { scalar_groups_.push_back(std::move(g)); return static_cast<scalar_group_id>(scalar_groups_.size()) - 1; }
+  aggregation_state_id addAggregationState(AggregationSpec spec) {
+    agg_specs_.push_back(std::move(spec));
+    agg_states_.push_back(nullptr);
+    const AggregationSpec &s = agg_specs_.back();
+    const qs_expr_set es = s.exprs.view();
+    qs_agg_spec c{};
+    c.dev = device_; c.strategy = s.strategy; c.exprs = &es; c.predicate_root = s.predicate_root;
+    c.n_aggregates = static_cast<std::uint32_t>(s.aggregates.size()); c.aggregates = s.aggregates.data();
+    c.n_group_by = static_cast<std::uint32_t>(s.group_by_roots.size()); c.group_by_roots = s.group_by_roots.data();
+    c.estimated_num_entries = s.estimated_num_entries; c.collision_free_max_key = s.collision_free_max_key;
+    QS_CHECK_GPU(qsgpu_agg_create(&c, &agg_states_.back()));
+    return static_cast<aggregation_state_id>(agg_states_.size()) - 1;
+  }
+  join_hash_table_id addJoinHashTable(std::uint32_t key_type, std::uint64_t estimated_num_entries) {
+    qsgpu_join_table_t t = nullptr;
+    QS_CHECK_GPU(qsgpu_join_create(device_, key_type, estimated_num_entries, &t));
+    join_tables_.push_back(t);
+    return static_cast<join_hash_table_id>(join_tables_.size()) - 1;
+  }
+  lip_filter_id addLIPFilter(std::uint32_t kind, std::uint32_t attr_type, std::int64_t min_value, std::int64_t max_value,
+                             std::uint64_t cardinality, bool is_anti) {
+    qsgpu_lip_t f = nullptr;
+    QS_CHECK_GPU(qsgpu_lip_create(device_, kind, attr_type, min_value, max_value, cardinality, is_anti ? 1 : 0, &f));
+    lip_filters_.push_back(f);
+    return static_cast<lip_filter_id>(lip_filters_.size()) - 1;
+  }
+  lip_deployment_id addLIPDeployment(LIPDeployment d) { lip_deployments_.push_back(std::move(d)); return static_cast<lip_deployment_id>(lip_deployments_.size()) - 1; }
+  insert_destination_id addInsertDestination(const CatalogRelation *rel, std::uint64_t capacity_rows) {
+    destinations_.emplace_back(new InsertDestination(rel, capacity_rows, sm_));
+    return static_cast<insert_destination_id>(destinations_.size()) - 1;
+  }
+  sort_config_id addSortConfig(SortConfig c) { sort_configs_.push_back(std::move(c)); return static_cast<sort_config_id>(sort_configs_.size()) - 1; }
+
+  // ---- getters (same names as the reference)
+  const Predicate *getPredicate(predicate_id id) const { return id < 0 ? nullptr : &predicates_[static_cast<std::size_t>(id)]; }
+  const ScalarGroup &getScalarGroup(scalar_group_id id) const { return scalar_groups_[static_cast<std::size_t>(id)]; }
+  qsgpu_agg_state_t getAggregationState(aggregation_state_id id, partition_id = 0) const { return agg_states_[id]; }
+  const AggregationSpec &getAggregationSpec(aggregation_state_id id) const { return agg_specs_[id]; }
+  void destroyAggregationState(aggregation_state_id id, partition_id = 0) {
+    if (agg_states_[id]) QS_CHECK_GPU(qsgpu_agg_destroy(agg_states_[id]));
+    agg_states_[id] = nullptr;
+  }
+  qsgpu_join_table_t getJoinHashTable(join_hash_table_id id, partition_id = 0) const { return join_tables_[id]; }
+  void destroyJoinHashTable(join_hash_table_id id, partition_id = 0) {
+    if (join_tables_[id]) QS_CHECK_GPU(qsgpu_join_destroy(join_tables_[id]));
+    join_tables_[id] = nullptr;
+  }
+  qsgpu_lip_t getLIPFilter(lip_filter_id id) const { return lip_filters_[id]; }
+  const LIPDeployment *getLIPDeployment(lip_deployment_id id) const { return id < 0 ? nullptr : &lip_deployments_[static_cast<std::size_t>(id)]; }
+  InsertDestination *getInsertDestination(insert_destination_id id) { return id < 0 ? nullptr : destinations_[static_cast<std::size_t>(id)].get(); }
+  const SortConfig &getSortConfig(sort_config_id id) const { return sort_configs_[id]; }
+
+  // LIPFilterUtil: the C-ABI references of a deployment (filter handle + attribute)
+  std::vector<qs_lip_ref> lipRefs(lip_deployment_id id, LIPAction action) const {
+    std::vector<qs_lip_ref> refs;
+    const LIPDeployment *d = getLIPDeployment(id);
+    if (d)
+      for (const LIPEntry &e : (action == LIPAction::kBuild ? d->build_entries : d->probe_entries)) { qs_lip_ref r{}; r.lip = lip_filters_[e.filter]; r.attr = static_cast<std::uint32_t>(e.attr); refs.push_back(r); }
+    return refs;
+  }
+
+ private:
+  StorageManager *sm_;
+  int device_;
+  std::vector<Predicate> predicates_;
+  std::vector<ScalarGroup> scalar_groups_;
+  std::vector<AggregationSpec> agg_specs_;
+  std::vector<qsgpu_agg_state_t> agg_states_;
+  std::vector<qsgpu_join_table_t> join_tables_;
+  std::vector<qsgpu_lip_t> lip_filters_;
+  std::vector<LIPDeployment> lip_deployments_;
+  std::vector<std::unique_ptr<InsertDestination>> destinations_;
+  std::vector<SortConfig> sort_configs_;
+};
+
+}  // namespace quickstep

@@ -1,0 +1,118 @@
+#include "QueryManager.hpp"
+
+namespace quickstep {
+
+void QueryManager::fetchNormalWorkOrders(std::size_t op) {
+  if (done_gen_[op] || blocking_deps_[op] != 0) return;
+  done_gen_[op] = plan_->op(op)->getAllWorkOrders(&container_, context_, sm_, /*scheduler_client_id=*/0, /*bus=*/nullptr);
+}
+
+void QueryManager::markOperatorFinished(std::size_t op) {
+  finished_[op] = true;
+  RelationalOperator *producer = plan_->op(op);
+  const relation_id out_rel = producer->getOutputRelationID();
+  InsertDestination *dest = context_->getInsertDestination(producer->getInsertDestinationID());
+  for (const QueryPlan::Edge &e : plan_->consumers(op)) {
+    RelationalOperator *consumer = plan_->op(e.consumer);
+    if (dest != nullptr && out_rel >= 0) {
+      for (block_id b : dest->getTouchedBlocks()) consumer->feedInputBlock(b, out_rel, 0);
+      consumer->doneFeedingInputBlocks(out_rel);
+    }
+    if (e.is_pipeline_breaker) --blocking_deps_[e.consumer];
+    fetchNormalWorkOrders(e.consumer);
+  }
+}
+
+WorkerPool::WorkerPool(int num_workers) {
+  for (int i = 0; i < (num_workers < 1 ? 1 : num_workers); ++i) threads_.emplace_back([this] { workerLoop(); });
+}
+
+WorkerPool::~WorkerPool() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    shutdown_ = true;
+  }
+  work_cv_.notify_all();
+  for (auto &t : threads_) t.join();
+}
+
+void WorkerPool::submit(WorkOrder *w, std::size_t op_index) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    work_queue_.push({w, op_index});
+  }
+  work_cv_.notify_one();
+}
+
+std::size_t WorkerPool::waitForCompletion() {
+  std::unique_lock<std::mutex> lk(mu_);
+  done_cv_.wait(lk, [&] { return !done_queue_.empty(); });
+  const std::size_t op = done_queue_.front();
+  done_queue_.pop();
+  return op;
+}
+
+void WorkerPool::workerLoop() {
+  for (;;) {
+    Message m;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      work_cv_.wait(lk, [&] { return shutdown_ || !work_queue_.empty(); });
+      if (work_queue_.empty()) return;
+      m = work_queue_.front();
+      work_queue_.pop();
+    }
+    std::unique_ptr<WorkOrder> wo(m.work_order);     // Worker.cpp:127-139: executed, then destroyed
+    wo->execute();
+    wo.reset();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      done_queue_.push(m.op_index);
+    }
+    done_cv_.notify_one();
+  }
+}
+
+void QueryManager::run() {
+  const std::size_t n = plan_->size();
+  done_gen_.assign(n, false);
+  finished_.assign(n, false);
+  pending_.assign(n, 0);
+  blocking_deps_.assign(n, 0);
+  executed_.assign(n, 0);
+  for (std::size_t p = 0; p < n; ++p)
+    for (const QueryPlan::Edge &e : plan_->consumers(p))
+      if (e.is_pipeline_breaker) ++blocking_deps_[e.consumer];
+
+  for (std::size_t op = 0; op < n; ++op) fetchNormalWorkOrders(op);
+  std::size_t n_finished = 0;
+  while (n_finished < n) {
+    // dispatch everything that is ready
+    bool dispatched = false;
+    for (std::size_t op = 0; op < n; ++op) {
+      while (WorkOrder *w = container_.getNormalWorkOrder(op)) {
+        ++pending_[op];
+        ++executed_[op];
+        workers_->submit(w, op);
+        dispatched = true;
+      }
+    }
+    // operators with nothing left
+    bool progressed = false;
+    for (std::size_t op = 0; op < n; ++op) {
+      if (!finished_[op] && done_gen_[op] && pending_[op] == 0 && !container_.hasNormalWorkOrder(op)) {
+        markOperatorFinished(op);
+        ++n_finished;
+        progressed = true;
+      }
+    }
+    if (progressed || n_finished == n) continue;
+    (void)dispatched;
+    // wait for a completion
+    const std::size_t op = workers_->waitForCompletion();
+    --pending_[op];
+    fetchNormalWorkOrders(op);
+  }
+}
+
+}  // namespace quickstep

@@ -1,0 +1,348 @@
+#include "StorageManager.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <type_traits>
+
+namespace quickstep {
+
+namespace {
+
+std::size_t pad16(std::size_t n) { return (n + 15) & ~static_cast<std::size_t>(15); }
+
+// What the block builder decided for one attribute of one block.
+struct StripePlan {
+  std::uint32_t encoding = QS_ENC_PLAIN;
+  std::uint32_t code_width = 0;
+  std::vector<char> dict;            // sorted distinct values, native width
+  std::size_t stripe_bytes = 0;
+};
+
+// CompressedBlockBuilder's rule (storage/CompressedBlockBuilder.cpp:470-498): keep the
+// smaller of {truncated (or native) stripe} and {dictionary + code stripe}.
+// Value order first, bit pattern as the tie-break (-0.0 and 0.0 are distinct dictionary entries,
+// exactly one code per stored bit pattern, so decode(encode(x)) is bit-identical to x).
+template <class T>
+bool valueLess(const T &a, const T &b) {
+  if (a < b) return true;
+  if (b < a) return false;
+  return std::memcmp(&a, &b, sizeof(T)) < 0;
+}
+
+template <class T>
+StripePlan planCompressed(const T *v, std::uint64_t n, bool is_integer) {
+  StripePlan p;
+  const std::size_t w = sizeof(T);
+  std::size_t truncated = w;
+  if constexpr (std::is_integral<T>::value) {
+    if (is_integer && n > 0) {
+      bool nonneg = true;
+      std::uint64_t mx = 0;
+      for (std::uint64_t i = 0; i < n; ++i) {
+        if (v[i] < 0) { nonneg = false; break; }
+        mx = std::max<std::uint64_t>(mx, static_cast<std::uint64_t>(v[i]));
+      }
+      if (nonneg) {
+        if (mx < (1ull << 8)) truncated = 1;
+        else if (mx < (1ull << 16)) truncated = 2;
+        else if (mx < (1ull << 32) && w > 4) truncated = 4;
+      }
+    }
+  }
+  std::vector<T> d(v, v + n);
+  std::sort(d.begin(), d.end(), valueLess<T>);
+  d.erase(std::unique(d.begin(), d.end(), [](const T &a, const T &b) { return std::memcmp(&a, &b, sizeof(T)) == 0; }), d.end());
+  const std::size_t codes = d.size() + 1;                    // one code is reserved for NULL
+  const std::size_t cw = codes <= (1u << 8) ? 1 : codes <= (1u << 16) ? 2 : 4;
+  const std::size_t dict_bytes = 8 + d.size() * w + n * cw;   // [u32 num_codes][u32 null_code][values] + codes
+  if (truncated * n < dict_bytes) {
+    if (truncated < w) { p.encoding = QS_ENC_TRUNCATED; p.code_width = static_cast<std::uint32_t>(truncated); p.stripe_bytes = n * truncated; }
+    else { p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * w; }
+  } else {
+    p.encoding = QS_ENC_DICT;
+    p.code_width = static_cast<std::uint32_t>(cw);
+    p.stripe_bytes = n * cw;
+    p.dict.resize(d.size() * w);
+    std::memcpy(p.dict.data(), d.data(), d.size() * w);
+  }
+  return p;
+}
+
+template <class T>
+void writeCodes(char *dst, const T *v, std::uint64_t n, const StripePlan &p) {
+  if (p.encoding == QS_ENC_TRUNCATED) {
+    if constexpr (std::is_integral<T>::value) {
+      for (std::uint64_t i = 0; i < n; ++i) {
+        const std::uint64_t x = static_cast<std::uint64_t>(v[i]);
+        std::memcpy(dst + i * p.code_width, &x, p.code_width);          // little endian
+      }
+    }
+    return;
+  }
+  const T *d = reinterpret_cast<const T *>(p.dict.data());
+  const std::size_t nd = p.dict.size() / sizeof(T);
+  for (std::uint64_t i = 0; i < n; ++i) {
+    // ordered dictionary: code = rank of the value (CompressionDictionaryLite: code order = value order)
+    const std::uint32_t c = static_cast<std::uint32_t>(std::lower_bound(d, d + nd, v[i], valueLess<T>) - d);
+    std::memcpy(dst + i * p.code_width, &c, p.code_width);
+  }
+}
+
+struct DateKey {           // DateLit ordered as (year, month, day): types/DatetimeLit.hpp:65-93
+  std::uint64_t raw;
+  std::int64_t key() const {
+    return static_cast<std::int64_t>(static_cast<std::int32_t>(raw & 0xffffffffu)) * 65536 +
+           static_cast<std::int64_t>(((raw >> 32) & 0xff) << 8 | ((raw >> 40) & 0xff));
+  }
+  bool operator<(const DateKey &o) const { return key() < o.key(); }
+};
+
+StripePlan planAttr(const qs_attr &a, const char *col, std::uint64_t n) {
+  switch (a.type) {
+    case QS_INT: return planCompressed(reinterpret_cast<const std::int32_t *>(col), n, true);
+    case QS_LONG: return planCompressed(reinterpret_cast<const std::int64_t *>(col), n, true);
+    case QS_FLOAT: return planCompressed(reinterpret_cast<const float *>(col), n, false);
+    case QS_DOUBLE: return planCompressed(reinterpret_cast<const double *>(col), n, false);
+    case QS_DATE: return planCompressed(reinterpret_cast<const DateKey *>(col), n, false);
+    default: {            // CHAR(n): kept native here (the reference would dictionary-encode long strings)
+      StripePlan p; p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * a.width; return p;
+    }
+  }
+}
+
+void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, const StripePlan &p) {
+  if (p.encoding == QS_ENC_PLAIN) { std::memcpy(dst, col, n * a.width); return; }
+  switch (a.type) {
+    case QS_INT: writeCodes(dst, reinterpret_cast<const std::int32_t *>(col), n, p); break;
+    case QS_LONG: writeCodes(dst, reinterpret_cast<const std::int64_t *>(col), n, p); break;
+    case QS_FLOAT: writeCodes(dst, reinterpret_cast<const float *>(col), n, p); break;
+    case QS_DOUBLE: writeCodes(dst, reinterpret_cast<const double *>(col), n, p); break;
+    case QS_DATE: writeCodes(dst, reinterpret_cast<const DateKey *>(col), n, p); break;
+    default: QS_CHECK(false);
+  }
+}
+
+}  // namespace
+
+StorageManager::~StorageManager() {
+  for (auto &kv : resident_) if (kv.second.handle) qsgpu_relation_destroy(kv.second.handle);
+  for (auto &kv : temporaries_) if (kv.second) qsgpu_relation_destroy(kv.second);
+  for (auto &kv : slabs_) for (Slab &s : kv.second) if (s.base) qsgpu_host_free(s.base);
+}
+
+void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const void *> &columns, std::uint64_t n_rows,
+                                  std::uint64_t rows_per_block, TupleStoreLayout layout) {
+  const std::vector<qs_attr> schema = rel->schema();
+  QS_CHECK(columns.size() == schema.size());
+  if (rows_per_block == 0) rows_per_block = std::max<std::uint64_t>(n_rows, 1);
+  const std::uint64_t n_blocks = (n_rows + rows_per_block - 1) / rows_per_block;
+  std::size_t slot_bytes = 0;
+  for (const qs_attr &a : schema) slot_bytes += a.width;
+
+  // ---- pass 1 (parallel): decide the physical form of every stripe, size the images
+  std::vector<std::vector<StripePlan>> plans(n_blocks, std::vector<StripePlan>(schema.size()));
+  std::vector<std::size_t> image_bytes(n_blocks, 0);
+  const unsigned n_threads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
+  auto for_blocks = [&](auto &&fn) {
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < n_threads; ++t)
+      ts.emplace_back([&, t] { for (std::uint64_t b = t; b < n_blocks; b += n_threads) fn(b); });
+    for (auto &t : ts) t.join();
+  };
+  for_blocks([&](std::uint64_t b) {
+    const std::uint64_t r0 = b * rows_per_block, n = std::min(rows_per_block, n_rows - r0);
+    std::size_t bytes = 0;
+    if (layout == TupleStoreLayout::kSplitRowStore) {
+      bytes = n * slot_bytes;
+    } else {
+      for (std::size_t a = 0; a < schema.size(); ++a) {
+        const char *col = static_cast<const char *>(columns[a]) + r0 * schema[a].width;
+        StripePlan &p = plans[b][a];
+        if (layout == TupleStoreLayout::kCompressedColumnStore) p = planAttr(schema[a], col, n);
+        else { p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * schema[a].width; }
+        bytes += p.dict.size() + p.stripe_bytes;
+      }
+    }
+    image_bytes[b] = pad16(bytes);
+  });
+
+  // ---- one pinned slab for the relation's blocks (contiguous images => one H2D copy per batch)
+  std::size_t total = 0;
+  std::vector<std::size_t> off(n_blocks);
+  for (std::uint64_t b = 0; b < n_blocks; ++b) { off[b] = total; total += image_bytes[b]; }
+  Slab slab;
+  slab.bytes = total;
+  void *hp = nullptr;
+  QS_CHECK_GPU(qsgpu_host_alloc(std::max<std::size_t>(total, 16), &hp));
+  slab.base = static_cast<char *>(hp);
+
+  // ---- pass 2 (parallel): write the images
+  std::vector<StorageBlock> built(n_blocks);
+  for_blocks([&](std::uint64_t b) {
+    const std::uint64_t r0 = b * rows_per_block, n = std::min(rows_per_block, n_rows - r0);
+    StorageBlock &B = built[b];
+    B.relation = rel->getID();
+    B.num_tuples = static_cast<tuple_id>(n);
+    B.memory = slab.base + off[b];
+    B.size = image_bytes[b];
+    B.stripes.resize(schema.size());
+    char *w = slab.base + off[b];
+    std::memset(w, 0, image_bytes[b]);
+    if (layout == TupleStoreLayout::kSplitRowStore) {
+      std::size_t attr_off = 0;
+      for (std::size_t a = 0; a < schema.size(); ++a) {
+        const std::uint32_t vw = schema[a].width;
+        const char *col = static_cast<const char *>(columns[a]) + r0 * vw;
+        for (std::uint64_t i = 0; i < n; ++i) std::memcpy(w + i * slot_bytes + attr_off, col + i * vw, vw);
+        qs_stage_desc &s = B.stripes[a];
+        s = qs_stage_desc{};
+        s.attr = static_cast<std::uint32_t>(a); s.encoding = QS_ENC_STRIDED; s.host = w + attr_off;
+        s.stride = static_cast<std::uint32_t>(slot_bytes);
+        attr_off += vw;
+      }
+      return;
+    }
+    // dictionaries first, then the stripes (CompressedTupleStorageSubBlock.cpp:281-342 layout order)
+    std::vector<const char *> dict_at(schema.size(), nullptr);
+    for (std::size_t a = 0; a < schema.size(); ++a) {
+      const StripePlan &p = plans[b][a];
+      if (!p.dict.empty()) { std::memcpy(w, p.dict.data(), p.dict.size()); dict_at[a] = w; w += p.dict.size(); }
+    }
+    for (std::size_t a = 0; a < schema.size(); ++a) {
+      const StripePlan &p = plans[b][a];
+      const char *col = static_cast<const char *>(columns[a]) + r0 * schema[a].width;
+      writeAttr(schema[a], w, col, n, p);
+      qs_stage_desc &s = B.stripes[a];
+      s = qs_stage_desc{};
+      s.attr = static_cast<std::uint32_t>(a); s.encoding = p.encoding; s.host = w; s.code_width = p.code_width;
+      if (p.encoding == QS_ENC_DICT) { s.dict = dict_at[a]; s.dict_entries = static_cast<std::uint32_t>(p.dict.size() / schema[a].width); }
+      w += p.stripe_bytes;
+    }
+  });
+
+  std::lock_guard<std::mutex> lk(mu_);
+  slabs_[rel->getID()].push_back(slab);
+  for (StorageBlock &B : built) {
+    B.id = next_block_++;
+    rel->addBlock(B.id);
+    blocks_.emplace(B.id, std::move(B));
+  }
+}
+
+const StorageBlock &StorageManager::getBlock(block_id id) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = blocks_.find(id);
+  QS_CHECK(it != blocks_.end());
+  return it->second;
+}
+
+std::uint64_t StorageManager::hostBytes(const CatalogRelation &rel) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  std::uint64_t n = 0;
+  auto it = slabs_.find(rel.getID());
+  if (it != slabs_.end()) for (const Slab &s : it->second) n += s.bytes;
+  return n;
+}
+
+qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel) {
+  std::lock_guard<std::mutex> lk(mu_);
+  const std::vector<block_id> ids = rel.getBlocksSnapshot();
+  Resident &R = resident_[rel.getID()];
+  if (R.handle && R.n_blocks_staged == ids.size()) return R.handle;
+  std::uint64_t rows = 0;
+  for (block_id id : ids) rows += static_cast<std::uint64_t>(blocks_.at(id).num_tuples);
+  const std::vector<qs_attr> schema = rel.schema();
+  if (!R.handle) {
+    QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
+                                       std::max<std::uint64_t>(rows, 1), &R.handle));
+    R.n_blocks_staged = 0;
+    R.rows = 0;
+  } else {
+    // the relation grew since the image was built (blocks are append-only): rebuild it
+    QS_CHECK_GPU(qsgpu_relation_destroy(R.handle));
+    QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
+                                       std::max<std::uint64_t>(rows, 1), &R.handle));
+    R.n_blocks_staged = 0;
+    R.rows = 0;
+  }
+  std::vector<qs_block_image> images;
+  for (std::size_t i = R.n_blocks_staged; i < ids.size(); ++i) {
+    const StorageBlock &B = blocks_.at(ids[i]);
+    block_first_row_[B.id] = {rel.getID(), R.rows};
+    R.rows += static_cast<std::uint64_t>(B.num_tuples);
+    qs_block_image im{};
+    im.host = B.memory; im.bytes = B.size; im.n_rows = static_cast<std::uint64_t>(B.num_tuples); im.descs = B.stripes.data();
+    images.push_back(im);
+  }
+  if (!images.empty())
+    QS_CHECK_GPU(qsgpu_stage_blocks(R.handle, static_cast<std::uint32_t>(images.size()), images.data(),
+                                    static_cast<std::uint32_t>(schema.size())));
+  R.n_blocks_staged = ids.size();
+  return R.handle;
+}
+
+DeviceExtent StorageManager::blockExtent(block_id id) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto t = blocks_.find(id);
+  if (t == blocks_.end()) {          // pseudo block of a temporary relation: every row produced so far
+    for (auto &kv : temporary_block_)
+      if (kv.second == id) { DeviceExtent e; e.relation = temporaries_.at(kv.first); return e; }
+    QS_CHECK(false);
+  }
+  auto f = block_first_row_.find(id);
+  QS_CHECK(f != block_first_row_.end());     // deviceRelation() first
+  DeviceExtent e;
+  e.relation = resident_.at(f->second.first).handle;
+  e.row_begin = f->second.second;
+  e.row_end = e.row_begin + static_cast<std::uint64_t>(t->second.num_tuples);
+  return e;
+}
+
+void StorageManager::evict(const CatalogRelation &rel) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = resident_.find(rel.getID());
+  if (it == resident_.end()) return;
+  if (it->second.handle) QS_CHECK_GPU(qsgpu_relation_destroy(it->second.handle));
+  resident_.erase(it);
+}
+
+block_id StorageManager::createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = temporaries_.find(rel.getID());
+  if (it == temporaries_.end()) {
+    const std::vector<qs_attr> schema = rel.schema();
+    qsgpu_relation_t h = nullptr;
+    QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
+                                       std::max<std::uint64_t>(capacity_rows, 1), &h));
+    temporaries_[rel.getID()] = h;
+    temporary_block_[rel.getID()] = next_block_++;
+  }
+  return temporary_block_.at(rel.getID());
+}
+
+void StorageManager::adoptTemporary(const CatalogRelation &rel, qsgpu_relation_t handle) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = temporaries_.find(rel.getID());
+  if (it != temporaries_.end() && it->second) QS_CHECK_GPU(qsgpu_relation_destroy(it->second));
+  temporaries_[rel.getID()] = handle;
+  if (!temporary_block_.count(rel.getID())) temporary_block_[rel.getID()] = next_block_++;
+}
+
+qsgpu_relation_t StorageManager::temporary(const CatalogRelation &rel) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = temporaries_.find(rel.getID());
+  QS_CHECK(it != temporaries_.end());
+  return it->second;
+}
+
+void StorageManager::dropTemporary(const CatalogRelation &rel) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = temporaries_.find(rel.getID());
+  if (it == temporaries_.end()) return;
+  if (it->second) QS_CHECK_GPU(qsgpu_relation_destroy(it->second));
+  temporaries_.erase(it);
+  temporary_block_.erase(rel.getID());
+}
+
+}  // namespace quickstep

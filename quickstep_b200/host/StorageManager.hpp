@@ -1,0 +1,93 @@
+// Host storage blocks in the reference's three physical layouts, and their
+// device residency (kernel family K0).
+//
+// Stands in for storage/StorageManager.hpp + the TupleStorageSubBlock formats
+// so the GPU operators can be driven and tested without the reference's buffer
+// pool.  What it keeps of the reference:
+//   * a relation is a list of blocks (CatalogRelation::getBlocksSnapshot);
+//   * a block is one contiguous piece of memory whose stripes are found from
+//     the sub-block header:
+//       BasicColumnStore       stripes back to back, stripe i = n x width_i
+//                              (storage/BasicColumnStoreTupleStorageSubBlock.cpp:100-183)
+//       CompressedColumnStore  [dictionaries][stripes]; per attribute and per
+//                              block the builder keeps the smaller of truncation
+//                              (non-negative INT/LONG to 1/2/4 bytes), an ordered
+//                              dictionary with 1/2/4-byte codes, or the native
+//                              stripe (storage/CompressedBlockBuilder.cpp:434-506,
+//                              compression/CompressionDictionaryLite.hpp:40-51)
+//       SplitRowStore          fixed-width attributes back to back inside
+//                              tuple slots (storage/SplitRowStoreTupleStorageSubBlock.cpp:103-179)
+//   * getBlock()-style access by block id.
+// What it adds: deviceRelation(), the HBM image of a relation's blocks, staged
+// by ONE qsgpu_stage_blocks call per batch of blocks and cached (the analogue
+// of the warm buffer pool); and device-only temporary relations.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "QsTypes.hpp"
+
+namespace quickstep {
+
+enum class TupleStoreLayout { kBasicColumnStore = 0, kCompressedColumnStore = 1, kSplitRowStore = 2 };
+
+struct StorageBlock {
+  block_id id = 0;
+  relation_id relation = -1;
+  tuple_id num_tuples = 0;
+  const char *memory = nullptr;          // block image (inside the relation's slab)
+  std::size_t size = 0;                  // bytes of the image
+  std::vector<qs_stage_desc> stripes;    // one per attribute, pointers into `memory`
+};
+
+// Row range of a device relation: what a GPU work order scans.
+struct DeviceExtent {
+  qsgpu_relation_t relation = nullptr;
+  std::uint64_t row_begin = 0, row_end = UINT64_MAX;
+};
+
+class StorageManager {
+ public:
+  explicit StorageManager(int device = 0) : device_(device) {}
+  ~StorageManager();
+  int device() const { return device_; }
+
+  // The loader's job in the reference (TextScan -> InsertDestination -> blocks):
+  // cut `n_rows` tuples given as native-width columns into blocks of
+  // `rows_per_block` tuples in the requested layout and register them with `rel`.
+  void loadRelation(CatalogRelation *rel, const std::vector<const void *> &columns, std::uint64_t n_rows,
+                    std::uint64_t rows_per_block, TupleStoreLayout layout);
+  const StorageBlock &getBlock(block_id id) const;
+  std::uint64_t hostBytes(const CatalogRelation &rel) const;      // bytes of all block images
+
+  // HBM image of every block of a stored relation, in block-list order.
+  qsgpu_relation_t deviceRelation(const CatalogRelation &rel);
+  DeviceExtent blockExtent(block_id id);                           // rows of one block inside it
+  void evict(const CatalogRelation &rel);                          // drop the HBM image
+
+  // Device-only temporary relation (output of Select / HashJoin / Finalize);
+  // its single pseudo block id stands for "every row produced so far".
+  block_id createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows);
+  void adoptTemporary(const CatalogRelation &rel, qsgpu_relation_t handle);   // takes ownership
+  qsgpu_relation_t temporary(const CatalogRelation &rel);
+  void dropTemporary(const CatalogRelation &rel);
+
+ private:
+  struct Slab { char *base = nullptr; std::size_t bytes = 0; };
+  struct Resident { qsgpu_relation_t handle = nullptr; std::size_t n_blocks_staged = 0; std::uint64_t rows = 0; };
+  int device_;
+  mutable std::mutex mu_;
+  block_id next_block_ = 1;
+  std::unordered_map<block_id, StorageBlock> blocks_;
+  std::unordered_map<block_id, std::pair<relation_id, std::uint64_t>> block_first_row_;
+  std::map<relation_id, std::vector<Slab>> slabs_;
+  std::map<relation_id, Resident> resident_;
+  std::map<relation_id, qsgpu_relation_t> temporaries_;
+  std::map<relation_id, block_id> temporary_block_;
+};
+
+}  // namespace quickstep

@@ -480,6 +480,60 @@ def test_stage_block_decoders(engine, oracle):
         rel.destroy()
 
 
+def test_stage_blocks_batched_images(engine, oracle):
+    """qsgpu_stage_blocks: several block images (stripes back to back, so 2/4/8-byte stripes start at odd
+    offsets; two of the images adjacent in host memory, merged into one H2D copy) decode to the same
+    columns as staging stripe by stripe."""
+    rng = np.random.default_rng(5)
+    schema = [(A.QS_DOUBLE, 8), (A.QS_INT, 4), (A.QS_CHAR, 3), (A.QS_LONG, 8), (A.QS_DOUBLE, 8)]
+    sizes = [7001, 4096, 1, 5000]
+
+    def make(n, pad):
+        dvals = np.sort(rng.normal(0, 50, size=300))
+        parts, descs, off = [], [], 0
+
+        def put(arr, align=1):
+            nonlocal off
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            skip = (-off) % align
+            parts.append(np.zeros(skip, np.uint8)); off += skip
+            parts.append(raw); at = off; off += raw.size
+            return at
+        codes = rng.integers(0, 300, size=n).astype(np.uint16)
+        trunc = rng.integers(0, 70000, size=n).astype(np.uint32)
+        chars = rng.integers(65, 91, size=(n, 3)).astype(np.uint8)
+        stride = 21
+        slots = rng.integers(0, 256, size=n * stride + 8).astype(np.uint8)
+        plain = rng.normal(size=n)
+        put(np.zeros(pad, np.uint8))
+        d_off = put(dvals)
+        descs.append(dict(attr=2, encoding=A.QS_ENC_PLAIN, offset=put(chars)))
+        descs.append(dict(attr=0, encoding=A.QS_ENC_DICT, offset=put(codes), code_width=2, dict_offset=d_off, dict_entries=300))
+        descs.append(dict(attr=1, encoding=A.QS_ENC_TRUNCATED, offset=put(trunc), code_width=4))
+        descs.append(dict(attr=3, encoding=A.QS_ENC_STRIDED, offset=put(slots) + 5, stride=stride))
+        descs.append(dict(attr=4, encoding=A.QS_ENC_PLAIN, offset=put(plain)))
+        put(np.zeros((-off) % 16, np.uint8))
+        exp = {0: oracle.decode_dict(codes, dvals), 1: oracle.decode_truncated(trunc, np.int32), 2: chars.reshape(-1),
+               3: oracle.decode_strided(slots[5:], n, stride, np.int64), 4: plain}
+        return np.concatenate(parts), descs, exp
+    built = [make(n, pad) for n, pad in zip(sizes, [1, 16, 3, 0])]
+    slab = np.concatenate([built[1][0], built[2][0]])          # images 1 and 2 contiguous in host memory
+    mems = [built[0][0], slab[:built[1][0].size], slab[built[1][0].size:], built[3][0]]
+    rel = engine.Relation.create(schema, sum(sizes) + 10)
+    try:
+        rel.stage_blocks([(mems[i], sizes[i], built[i][1]) for i in range(4)])
+        assert rel.n_rows == sum(sizes)
+        base = 0
+        for i, n in enumerate(sizes):
+            for a in range(5):
+                got = np.ascontiguousarray(rel.read(a, base, n)).view(np.uint8).reshape(-1)
+                want = np.ascontiguousarray(built[i][2][a]).view(np.uint8).reshape(-1)
+                assert (got == want).all(), (i, a)
+            base += n
+    finally:
+        rel.destroy()
+
+
 # ------------------------------------------------ full-size properties (HBM-resident)
 def test_q6_q1_full_size_properties(engine, oracle):
     """At BASELINE.json's sizes the oracle is too slow for an exhaustive check inside the test budget, so:
