@@ -49,6 +49,8 @@ typedef struct qshost_q1_row {
   char pad[6];
   double sum_qty, sum_base_price, sum_disc_price, sum_charge, avg_qty, avg_price, avg_disc;
   int64_t count_order;
+  double sum_disc;   /* SUM(l_discount): not in the query's select list; kept so that partial results of
+                        lineitem partitions (one per GPU) can be merged exactly (AVG = SUM / COUNT) */
 } qshost_q1_row;
 
 typedef struct qshost_q3_row {

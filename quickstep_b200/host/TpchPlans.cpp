@@ -206,15 +206,16 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
   // finalize output: flag, status, 5 sums, count
   CatalogRelation *t_fin = db->temp(anon({kChar1, kChar1, kDouble, kDouble, kDouble, kDouble, kDouble, kLong}));
   const auto d_fin = ctx.addInsertDestination(t_fin, 256);
-  // wrapping Selection: flag, status, sum_qty, sum_base_price, sum_disc_price, sum_charge, avg_qty, avg_price, avg_disc, count
-  CatalogRelation *t_out = db->temp(anon({kChar1, kChar1, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kLong}));
+  // wrapping Selection: flag, status, sum_qty, sum_base_price, sum_disc_price, sum_charge, avg_qty, avg_price, avg_disc,
+  // count (+ the raw SUM(l_discount), see qshost_q1_row)
+  CatalogRelation *t_out = db->temp(anon({kChar1, kChar1, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kLong, kDouble}));
   const auto d_out = ctx.addInsertDestination(t_out, 256);
   QueryContext::ScalarGroup sel;
   {
     ExprSet &e = sel.exprs;
     auto a = [&](int id) { return e.attr(id, t_fin->getAttributeById(id).type); };
     sel.roots = {a(0), a(1), a(2), a(3), a(4), a(5), e.binary(QS_DIV, a(2), a(7)), e.binary(QS_DIV, a(3), a(7)),
-                 e.binary(QS_DIV, a(6), a(7)), a(7)};
+                 e.binary(QS_DIV, a(6), a(7)), a(7), a(6)};
   }
   const auto sel_id = ctx.addScalarGroup(std::move(sel));
 
@@ -235,6 +236,7 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
   std::array<std::vector<double>, 7> d;
   for (int j = 0; j < 7; ++j) d[j] = readColumn<double>(out, 2 + j, n);
   const auto count = readColumn<std::int64_t>(out, 9, n);
+  const auto sum_disc = readColumn<double>(out, 10, n);
   std::vector<qshost_q1_row> res(n);
   for (std::uint64_t i = 0; i < n; ++i) {
     qshost_q1_row &r = res[i];
@@ -243,6 +245,7 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
     r.sum_qty = d[0][i]; r.sum_base_price = d[1][i]; r.sum_disc_price = d[2][i]; r.sum_charge = d[3][i];
     r.avg_qty = d[4][i]; r.avg_price = d[5][i]; r.avg_disc = d[6][i];
     r.count_order = count[i];
+    r.sum_disc = sum_disc[i];
   }
   // ORDER BY l_returnflag, l_linestatus (<= 6 rows; the sort operators are outside the path)
   std::sort(res.begin(), res.end(), [](const qshost_q1_row &x, const qshost_q1_row &y) {

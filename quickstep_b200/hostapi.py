@@ -18,7 +18,7 @@ class q1_row(C.Structure):
     _fields_ = [("l_returnflag", C.c_char), ("l_linestatus", C.c_char), ("pad", C.c_char * 6),
                 ("sum_qty", C.c_double), ("sum_base_price", C.c_double), ("sum_disc_price", C.c_double),
                 ("sum_charge", C.c_double), ("avg_qty", C.c_double), ("avg_price", C.c_double),
-                ("avg_disc", C.c_double), ("count_order", C.c_int64)]
+                ("avg_disc", C.c_double), ("count_order", C.c_int64), ("sum_disc", C.c_double)]
 
 
 class q3_row(C.Structure):
@@ -90,7 +90,7 @@ class Database:
             out.append(dict(l_returnflag=r.l_returnflag, l_linestatus=r.l_linestatus, sum_qty=r.sum_qty,
                             sum_base_price=r.sum_base_price, sum_disc_price=r.sum_disc_price,
                             sum_charge=r.sum_charge, avg_qty=r.avg_qty, avg_price=r.avg_price,
-                            avg_disc=r.avg_disc, count_order=r.count_order))
+                            avg_disc=r.avg_disc, count_order=r.count_order, sum_disc=r.sum_disc))
         return out, wo.value
 
     def q6(self):

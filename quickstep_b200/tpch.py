@@ -104,6 +104,28 @@ def q1_rows_from_states(keys_flag, keys_status, sums, counts):
     return rows
 
 
+def merge_q1_partitions(parts):
+    """Merge the Q1 result rows of lineitem partitions (one list per GPU; rows carry sum_disc): SUMs and
+    COUNT add, the AVGs are recomputed from the merged SUM / COUNT.  Keyed by (flag, status): the same
+    group may sit at a different position in each partition's result."""
+    acc = {}
+    for rows in parts:
+        for r in rows:
+            k = (r["l_returnflag"], r["l_linestatus"])
+            a = acc.setdefault(k, dict(l_returnflag=k[0], l_linestatus=k[1], sum_qty=0.0, sum_base_price=0.0,
+                                       sum_disc_price=0.0, sum_charge=0.0, sum_disc=0.0, count_order=0))
+            for f in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "sum_disc"):
+                a[f] += r[f]
+            a["count_order"] += int(r["count_order"])
+    out = []
+    for k in sorted(acc):
+        a = acc[k]
+        c = float(a["count_order"])
+        a.update(avg_qty=a["sum_qty"] / c, avg_price=a["sum_base_price"] / c, avg_disc=a["sum_disc"] / c)
+        out.append(a)
+    return out
+
+
 # ----------------------------------------------------------------------- Q3
 class Q3Plan:
     """[1] BuildLIPFilter(customer, c_mktsegment='BUILDING' -> exact filter on c_custkey)

@@ -28,7 +28,7 @@ def test_qshost_symbols_exported():
     assert set(names) == set(H.SIGNATURES)
     for n in names:
         assert hasattr(lib, n)
-    assert ctypes.sizeof(H.q1_row) == 72 and ctypes.sizeof(H.q3_row) == 24
+    assert ctypes.sizeof(H.q1_row) == 80 and ctypes.sizeof(H.q3_row) == 24
 
 
 def test_qshost_fails_without_device():
