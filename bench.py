@@ -158,6 +158,12 @@ def main():
         run_reference(args)
         return
 
+    # Libraries (NCCL with NCCL_DEBUG set, the CUDA runtime) may print to fd 1; the contract is ONE JSON line
+    # on stdout, so everything else is sent to stderr and the line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -202,31 +208,28 @@ def main():
     gather_buf = {}
 
     def merge_across_ranks(st):
-        """Partial aggregation states: all-gather over NCCL, merged by the device merge kernel."""
+        """Partial aggregation states (AggregationHandle::mergeStates across GPUs): every rank contributes a
+        fixed-size block [states: cap x words | packed keys: cap x key_words], one NCCL all-gather, then the
+        device merge kernel folds each foreign block into the local state keyed by the packed group key
+        (rows with a zero row count are skipped, so no group counts have to visit the host)."""
         if world == 1:
             return
-        ds, dk, ng, w, kw = st.partial()
-        cap = 256
-        row = w + kw
-        key = (w, kw)
+        ds, dk, _ng, w, kw = st.partial()          # waits for the scan; pointers + layout
+        cap = 256 if kw and st.n_group_by else 1
+        key = (w, kw, cap)
         if key not in gather_buf:
-            gather_buf[key] = (torch.zeros(1 + cap * row, dtype=torch.int64, device=device),
-                               torch.zeros(world * (1 + cap * row), dtype=torch.int64, device=device))
+            gather_buf[key] = (torch.zeros(cap * (w + kw), dtype=torch.int64, device=device),
+                               torch.zeros(world * cap * (w + kw), dtype=torch.int64, device=device))
         mine, allb = gather_buf[key]
-        mine.zero_()
-        mine[0] = ng
-        if ng:
-            E.memcpy_d2d(mine.data_ptr() + 8, ds, ng * w * 8, local)
-            E.memcpy_d2d(mine.data_ptr() + 8 + cap * w * 8, dk, ng * kw * 8, local)
-        torch.cuda.synchronize()
+        E.memcpy_d2d_async(mine.data_ptr(), ds, cap * w * 8, local)
+        E.memcpy_d2d_async(mine.data_ptr() + cap * w * 8, dk, cap * kw * 8, local)
+        E.synchronize(local)                       # library stream -> visible to NCCL's stream
         dist.all_gather_into_tensor(allb, mine)
         torch.cuda.synchronize()
-        counts = allb.view(world, -1)[:, 0].tolist()
         for r in range(world):
-            if r == rank or counts[r] == 0:
-                continue
-            base = allb.data_ptr() + r * (1 + cap * row) * 8
-            st.merge_partial(base + 8, base + 8 + cap * w * 8, int(counts[r]))
+            if r != rank:
+                base = allb.data_ptr() + r * cap * (w + kw) * 8
+                st.merge_partial(base, base + cap * w * 8, cap)
 
     def step_q1(rel=li):
         st = E.AggState(q1p.strategy, q1p.es, q1p.pred, q1p.aggregates, q1p.group_by, estimated=8, dev=local)
@@ -397,7 +400,8 @@ def main():
             "gpu_launches": q1_launches,
             "result_check": {"q1_groups": len(q1_rows), "q1_count": sum(r["count_order"] for r in q1_rows)},
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     for r in rels.values():
         r.destroy()
     if world > 1:

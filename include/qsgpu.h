@@ -101,6 +101,9 @@ int qsgpu_free(int dev, void *dptr);
 int qsgpu_memcpy_h2d(int dev, void *dst, const void *src, size_t bytes);
 int qsgpu_memcpy_d2h(int dev, void *dst, const void *src, size_t bytes);
 int qsgpu_memcpy_d2d(int dev, void *dst, const void *src, size_t bytes);
+/* Same copy, only enqueued on the library stream of `dev`: call qsgpu_synchronize
+ * before another stream (e.g. NCCL's) touches dst. */
+int qsgpu_memcpy_d2d_async(int dev, void *dst, const void *src, size_t bytes);
 /* Pinned host memory for staging buffers. */
 int qsgpu_host_alloc(size_t bytes, void **hptr);
 int qsgpu_host_free(void *hptr);

@@ -68,6 +68,10 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
 int qshost_q6(qshost_db_t db, double *revenue, int *is_null, uint64_t *work_orders);
 int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *work_orders);
 
+/* Per-operator profile of the last query: one text line per operator (index, name, work orders, ms inside
+ * execute(), ms inside getAllWorkOrders()); the analogue of -profile_and_report_workorder_perf. */
+int qshost_last_profile(qshost_db_t db, char *buf, uint64_t buf_bytes);
+
 #ifdef __cplusplus
 }
 #endif

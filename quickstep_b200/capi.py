@@ -109,6 +109,7 @@ SIGNATURES = {
     "qsgpu_memcpy_h2d": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
     "qsgpu_memcpy_d2h": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
     "qsgpu_memcpy_d2d": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
+    "qsgpu_memcpy_d2d_async": (C.c_int, [C.c_int, _VP, _VP, C.c_size_t]),
     "qsgpu_timer_start": (C.c_int, [C.c_int]),
     "qsgpu_timer_stop": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "qsgpu_host_alloc": (C.c_int, [C.c_size_t, _VPP]),

@@ -370,6 +370,12 @@ int qsgpu_memcpy_d2d(int dev, void *dst, const void *src, size_t bytes) {
   QS_CUDA(cudaStreamSynchronize(d->stream));
   return QSGPU_OK;
 }
+int qsgpu_memcpy_d2d_async(int dev, void *dst, const void *src, size_t bytes) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
+  return QSGPU_OK;
+}
 int qsgpu_timer_start(int dev) {
   Device *d = device(dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;

@@ -60,6 +60,10 @@ def memcpy_d2d(dst_ptr: int, src_ptr: int, nbytes: int, dev=0):
     A.check(A.load().qsgpu_memcpy_d2d(dev, dst_ptr, src_ptr, nbytes))
 
 
+def memcpy_d2d_async(dst_ptr: int, src_ptr: int, nbytes: int, dev=0):
+    A.check(A.load().qsgpu_memcpy_d2d_async(dev, dst_ptr, src_ptr, nbytes))
+
+
 def set_timing(on: bool):
     A.check(A.load().qsgpu_set_timing(1 if on else 0))
 

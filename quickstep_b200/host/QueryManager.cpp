@@ -1,10 +1,15 @@
 #include "QueryManager.hpp"
 
+#include <chrono>
+#include <sstream>
+
 namespace quickstep {
 
 void QueryManager::fetchNormalWorkOrders(std::size_t op) {
   if (done_gen_[op] || blocking_deps_[op] != 0) return;
+  const auto t0 = std::chrono::steady_clock::now();
   done_gen_[op] = plan_->op(op)->getAllWorkOrders(&container_, context_, sm_, /*scheduler_client_id=*/0, /*bus=*/nullptr);
+  generate_ms_[op] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void QueryManager::markOperatorFinished(std::size_t op) {
@@ -44,12 +49,13 @@ void WorkerPool::submit(WorkOrder *w, std::size_t op_index) {
   work_cv_.notify_one();
 }
 
-std::size_t WorkerPool::waitForCompletion() {
+std::size_t WorkerPool::waitForCompletion(double *execute_ms) {
   std::unique_lock<std::mutex> lk(mu_);
   done_cv_.wait(lk, [&] { return !done_queue_.empty(); });
-  const std::size_t op = done_queue_.front();
+  const std::pair<std::size_t, double> m = done_queue_.front();
   done_queue_.pop();
-  return op;
+  if (execute_ms) *execute_ms = m.second;
+  return m.first;
 }
 
 void WorkerPool::workerLoop() {
@@ -63,11 +69,13 @@ void WorkerPool::workerLoop() {
       work_queue_.pop();
     }
     std::unique_ptr<WorkOrder> wo(m.work_order);     // Worker.cpp:127-139: executed, then destroyed
+    const auto t0 = std::chrono::steady_clock::now();
     wo->execute();
     wo.reset();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     {
       std::lock_guard<std::mutex> lk(mu_);
-      done_queue_.push(m.op_index);
+      done_queue_.push({m.op_index, ms});
     }
     done_cv_.notify_one();
   }
@@ -80,6 +88,8 @@ void QueryManager::run() {
   pending_.assign(n, 0);
   blocking_deps_.assign(n, 0);
   executed_.assign(n, 0);
+  execute_ms_.assign(n, 0.0);
+  generate_ms_.assign(n, 0.0);
   for (std::size_t p = 0; p < n; ++p)
     for (const QueryPlan::Edge &e : plan_->consumers(p))
       if (e.is_pipeline_breaker) ++blocking_deps_[e.consumer];
@@ -109,10 +119,20 @@ void QueryManager::run() {
     if (progressed || n_finished == n) continue;
     (void)dispatched;
     // wait for a completion
-    const std::size_t op = workers_->waitForCompletion();
+    double ms = 0;
+    const std::size_t op = workers_->waitForCompletion(&ms);
+    execute_ms_[op] += ms;
     --pending_[op];
     fetchNormalWorkOrders(op);
   }
+}
+
+std::string QueryManager::profile() const {
+  std::ostringstream o;
+  for (std::size_t op = 0; op < plan_->size(); ++op)
+    o << op << " " << plan_->op(op)->getName() << " work_orders=" << executed_[op] << " execute_ms=" << execute_ms_[op]
+      << " get_all_work_orders_ms=" << generate_ms_[op] << "\n";
+  return o.str();
 }
 
 }  // namespace quickstep

@@ -15,6 +15,8 @@
 #include <memory>
 #include <mutex>
 #include <queue>
+#include <string>
+#include <utility>
 #include <thread>
 #include <vector>
 
@@ -52,7 +54,9 @@ class WorkerPool {
   ~WorkerPool();
   int size() const { return static_cast<int>(threads_.size()); }
   void submit(WorkOrder *w, std::size_t op_index);      // kWorkOrderMessage
-  std::size_t waitForCompletion();                      // kWorkOrderCompleteMessage -> operator index
+  // kWorkOrderCompleteMessage -> operator index (+ the wall time execute() took, for the query profile
+  // the reference prints with --visualize_execution_dag / -profile_and_report_workorder_perf)
+  std::size_t waitForCompletion(double *execute_ms = nullptr);
 
  private:
   struct Message { WorkOrder *work_order; std::size_t op_index; };
@@ -60,7 +64,7 @@ class WorkerPool {
   std::mutex mu_;
   std::condition_variable work_cv_, done_cv_;
   std::queue<Message> work_queue_;
-  std::queue<std::size_t> done_queue_;
+  std::queue<std::pair<std::size_t, double>> done_queue_;
   bool shutdown_ = false;
   std::vector<std::thread> threads_;
 };
@@ -73,6 +77,8 @@ class QueryManager {
   void run();
   std::size_t numWorkOrdersExecuted(std::size_t op_index) const { return executed_[op_index]; }
   std::size_t totalWorkOrdersExecuted() const { std::size_t n = 0; for (auto x : executed_) n += x; return n; }
+  // one line per operator: index, name, work orders, ms inside execute(), ms inside getAllWorkOrders()
+  std::string profile() const;
 
  private:
   void fetchNormalWorkOrders(std::size_t op);
@@ -85,6 +91,7 @@ class QueryManager {
   WorkOrdersContainer container_;
   std::vector<bool> done_gen_, finished_;
   std::vector<std::size_t> pending_, blocking_deps_, executed_;
+  std::vector<double> execute_ms_, generate_ms_;
 };
 
 }  // namespace quickstep

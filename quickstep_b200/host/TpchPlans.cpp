@@ -48,6 +48,7 @@ struct qshost_db {
   std::uint64_t rows[3] = {0, 0, 0};
   // what \analyze records and AttachLIPFilters / InjectJoinFilters read (exact min/max statistics)
   std::int64_t c_custkey_min = 0, c_custkey_max = 0, o_orderkey_min = 0, o_orderkey_max = 0;
+  std::string last_profile;
   relation_id next_relation_id = 100;
   std::size_t next_query_id = 1;
 
@@ -123,6 +124,12 @@ int qshost_db_load(qshost_db_t db, int which, const void *const *columns, uint64
   return 0;
 }
 
+int qshost_last_profile(qshost_db_t db, char *buf, uint64_t buf_bytes) {
+  if (!buf || buf_bytes == 0) return QSGPU_ERR_INVALID;
+  std::snprintf(buf, buf_bytes, "%s", db->last_profile.c_str());
+  return 0;
+}
+
 int qshost_db_evict(qshost_db_t db, int which) {
   if (which < 0 || which > 2 || !db->rel[which]) return QSGPU_ERR_INVALID;
   db->sm->evict(*db->rel[which]);
@@ -176,6 +183,7 @@ int qshost_q6(qshost_db_t db, double *revenue, int *is_null, uint64_t *work_orde
   *revenue = v.empty() ? 0.0 : v[0];
   if (is_null) *is_null = (ctx.getInsertDestination(dest)->null_mask & 1) ? 1 : 0;
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
+  db->last_profile = qm.profile();
   db->dropTemps();
   return 0;
 }
@@ -256,6 +264,7 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
   *n_rows = static_cast<std::uint32_t>(n);
   for (std::uint32_t i = 0; i < std::min<std::uint64_t>(cap, n); ++i) rows[i] = res[i];
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
+  db->last_profile = qm.profile();
   db->dropTemps();
   return n > cap ? QSGPU_ERR_CAPACITY : 0;
 }
@@ -298,7 +307,7 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   const auto dst2 = ctx.addInsertDestination(t2, n_orders), dst0 = ctx.addInsertDestination(t0, n_lineitem),
              dst4 = ctx.addInsertDestination(t4, n_lineitem), dst7 = ctx.addInsertDestination(t7, 1),
              dst9 = ctx.addInsertDestination(t9, 10);
-  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, n_orders / 4));
+  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, n_orders / 2));
 
   QueryContext::ScalarGroup s4;     // l_orderkey, o_orderdate, o_shippriority, l_extendedprice, l_discount
   s4.roots = {s4.exprs.attr(0, kInt), s4.exprs.attr(1, kDate, 2), s4.exprs.attr(2, kInt, 2), s4.exprs.attr(1, kDouble),
@@ -311,7 +320,8 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
     spec.aggregates.push_back({QS_AGG_SUM, e.binary(QS_MUL, e.attr(3, kDouble), e.binary(QS_SUB, e.lit_int(1), e.attr(4, kDouble)))});
     spec.group_by_roots = {e.attr(0, kInt), e.attr(1, kDate), e.attr(2, kInt)};
     spec.strategy = QS_AGG_SEPARATE_CHAINING;
-    spec.estimated_num_entries = 1u << 16;
+    // the optimizer's group estimate (StarSchemaSimpleCostModel::estimateNumGroupsForAggregate): ~ #orders / 8
+    spec.estimated_num_entries = std::max<std::uint64_t>(1u << 16, n_orders / 8);
   }
   const auto state = ctx.addAggregationState(std::move(spec));
   QueryContext::SortConfig sc; sc.keys = {{3, 1}, {1, 0}};
@@ -364,6 +374,7 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
     r.day = static_cast<std::uint8_t>((od[i] >> 40) & 0xff);
   }
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
+  db->last_profile = qm.profile();
   db->dropTemps();
   return n > cap ? QSGPU_ERR_CAPACITY : 0;
 }

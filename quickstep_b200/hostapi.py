@@ -37,6 +37,7 @@ SIGNATURES = {
     "qshost_q1": [_VP, C.POINTER(q1_row), C.POINTER(C.c_uint32), _U64P],
     "qshost_q6": [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int), _U64P],
     "qshost_q3": [_VP, C.POINTER(q3_row), C.POINTER(C.c_uint32), _U64P],
+    "qshost_last_profile": [_VP, C.c_char_p, C.c_uint64],
 }
 _lib = None
 
@@ -103,6 +104,11 @@ class Database:
         n, wo = C.c_uint32(16), C.c_uint64(0)
         A.check(load().qshost_q3(self.h, rows, C.byref(n), C.byref(wo)))
         return [(r.l_orderkey, r.revenue, (r.year, r.month, r.day), r.o_shippriority) for r in rows[: n.value]], wo.value
+
+    def last_profile(self) -> str:
+        buf = C.create_string_buffer(8192)
+        A.check(load().qshost_last_profile(self.h, buf, 8192))
+        return buf.value.decode()
 
     def destroy(self):
         if self.h:
