@@ -8,6 +8,10 @@
 #include <cstring>
 #include <memory>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "Operators.hpp"
 #include "QueryManager.hpp"
 #include "qshost.h"
@@ -84,7 +88,16 @@ std::uint64_t numRows(qsgpu_relation_t rel) {
 
 extern "C" {
 
+static void backtraceOnSegv(int sig) {
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
 int qshost_db_create(int dev, int num_workers, qshost_db_t *out) {
+  if (std::getenv("QSHOST_BACKTRACE")) signal(SIGSEGV, backtraceOnSegv);
   const int st = qsgpu_init(1, &dev);
   if (st != 0) return st;
   std::unique_ptr<qshost_db> db(new qshost_db);
