@@ -976,6 +976,7 @@ static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
   QS_CUDA(cudaMemcpyAsync(&n, A.n_groups, 4, cudaMemcpyDeviceToHost, d->stream));
   QS_CUDA(cudaStreamSynchronize(d->stream));
   // worst case every row opens a group, but never plan for more than 8x the optimizer's estimate at once
+  // (a kernel that still overflows raises QSGPU_ERR_CAPACITY; nothing is silently dropped)
   uint64_t worst = n + std::min<uint64_t>(extra_rows, std::max<uint64_t>(8 * s->estimated, 1u << 20));
   if (worst * 3 / 2 <= A.cap) return QSGPU_OK;
   uint64_t cap = A.cap;
@@ -998,6 +999,7 @@ static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
 
 int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_begin, uint64_t row_end,
                   uint32_t n_lip_probe, const qs_lip_ref *lip_probe) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
   Device *d = device(state->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   if (input->dev != state->dev) { set_error(QSGPU_ERR_INVALID, "input relation on another device"); return QSGPU_ERR_INVALID; }
@@ -1050,8 +1052,13 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     count_launch(2);
   } else {
     if (state->strategy == QS_AGG_SEPARATE_CHAINING && !t_sc) {
-      uint64_t rows = (row_end == UINT64_MAX ? input->capacity : row_end) - row_begin;
-      if (!input->dirty) rows = std::min<uint64_t>(rows, input->host_rows);
+      // Size the table for the rows this work order can really add.  The input's row count may still be
+      // device-only (a temporary relation just produced); maybe_grow synchronises anyway, so read it
+      // first instead of planning for the relation's capacity.
+      st = sync_rows(input);
+      if (st) return st;
+      uint64_t rows = std::min<uint64_t>(row_end == UINT64_MAX ? input->host_rows : row_end, input->host_rows);
+      rows = rows > row_begin ? rows - row_begin : 0;
       st = maybe_grow(state, d, rows);
       if (st) return st;
       A.tags = state->A.tags; A.keys = state->A.keys; A.states = state->A.states; A.cap = state->A.cap;
@@ -1085,7 +1092,7 @@ static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
   return check_device_error(d);
 }
 
-int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups) {
+static int agg_num_groups_locked(qsgpu_agg_state_t state, uint64_t *n_groups) {
   Device *d = device(state->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   if (state->strategy == QS_AGG_COLLISION_FREE) return collect_groups(state, d, n_groups);
@@ -1098,15 +1105,21 @@ int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups) {
   return QSGPU_OK;
 }
 
+int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
+  return agg_num_groups_locked(state, n_groups);
+}
+
 int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys, uint64_t *n_groups,
                       uint32_t *words_per_group, uint32_t *key_words) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
   Device *d = device(state->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   AggDesc &A = state->A;
   *words_per_group = A.words;
   *key_words = state->strategy == QS_AGG_COLLISION_FREE ? 1 : A.key_words;
   if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
-    int st = qsgpu_agg_num_groups(state, n_groups);
+    int st = agg_num_groups_locked(state, n_groups);
     if (st) return st;
     *d_states = A.states;
     *d_keys = A.gid_keys;
@@ -1133,6 +1146,7 @@ int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys, u
 }
 
 int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states, const void *d_keys, uint64_t n_groups) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
   Device *d = device(state->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   const AggDesc &A = state->A;
@@ -1152,12 +1166,13 @@ int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states, const
 }
 
 int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t *null_mask) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
   Device *d = device(state->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   AggDesc &A = state->A;
   const bool dense = state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY;
   uint64_t n = 0;
-  int st = dense ? qsgpu_agg_num_groups(state, &n) : collect_groups(state, d, &n);
+  int st = dense ? agg_num_groups_locked(state, &n) : collect_groups(state, d, &n);
   if (st) return st;
   // output schema: group-by attributes, then one column per aggregate
   std::vector<qs_attr> attrs = state->key_attrs;

@@ -30,6 +30,11 @@ struct qsgpu_lip {
 };
 
 struct qsgpu_agg_state {
+  // Work orders of one operator run concurrently on Worker threads and share the state (the reference
+  // guards its states with SpinMutex / atomics, AggregationHandleSum.cpp:113).  Here the lock makes each
+  // call's launches one unit in stream order: a scan's per-CTA partial rows must be folded by ITS merge
+  // launch before the next scan overwrites them, and table growth must not race a scan.
+  std::mutex mu;
   int dev = 0;
   uint32_t strategy = 0;
   // deep copy of the expression set
