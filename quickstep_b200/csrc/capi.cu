@@ -53,13 +53,55 @@ static thread_local Device *t_dev = nullptr;
 cudaError_t dev_malloc_bytes(void **p, size_t bytes) {
   Device *d = t_dev;
   if (!d || !d->pool) return cudaErrorInvalidDevice;
-  return cudaMallocFromPoolAsync(p, bytes ? bytes : 256, d->pool, d->stream);
+  if (bytes < BlockCache::kMinBytes || !d->cache)
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 256, d->pool, d->stream);
+  const size_t rounded = (bytes + BlockCache::kRound - 1) / BlockCache::kRound * BlockCache::kRound;
+  BlockCache &C = *d->cache;
+  {
+    std::lock_guard<std::mutex> lk(C.mu);
+    auto it = C.parked.find(rounded);
+    if (it != C.parked.end()) {
+      *p = it->second;
+      C.parked.erase(it);
+      C.parked_bytes -= rounded;
+      C.live[*p] = rounded;
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMallocFromPoolAsync(p, rounded, d->pool, d->stream);
+  if (e == cudaErrorMemoryAllocation) {          // give the parked blocks back and retry once
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lk(C.mu);
+    for (auto &kv : C.parked) cudaFreeAsync(kv.second, d->stream);
+    C.parked.clear();
+    C.parked_bytes = 0;
+    e = cudaMallocFromPoolAsync(p, rounded, d->pool, d->stream);
+  }
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(C.mu);
+    C.live[*p] = rounded;
+  }
+  return e;
 }
 
 cudaError_t dev_free(void *p) {
   if (!p) return cudaSuccess;
   Device *d = t_dev;
   if (!d || !d->pool) return cudaFree(p);     // after shutdown: synchronous free is still legal
+  if (d->cache) {
+    BlockCache &C = *d->cache;
+    std::lock_guard<std::mutex> lk(C.mu);
+    auto it = C.live.find(p);
+    if (it != C.live.end()) {
+      const size_t sz = it->second;
+      C.live.erase(it);
+      if (C.parked_bytes + sz <= BlockCache::kMaxParkedBytes) {
+        C.parked.emplace(sz, p);
+        C.parked_bytes += sz;
+        return cudaSuccess;
+      }
+    }
+  }
   return cudaFreeAsync(p, d->stream);
 }
 
@@ -280,6 +322,7 @@ int qsgpu_init(int n_dev, const int *dev_ids) {
       QS_CUDA(cudaMemPoolCreate(&d.pool, &props));
       uint64_t keep = UINT64_MAX;
       QS_CUDA(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      d.cache = std::make_shared<BlockCache>();
     }
     QS_CUDA(cudaMalloc(&d.d_error, 256));
     QS_CUDA(cudaMemset(d.d_error, 0, 256));
@@ -303,6 +346,8 @@ int qsgpu_shutdown(void) {
     cudaEventDestroy(d.ev1);
     cudaEventDestroy(d.ev_t0);
     cudaEventDestroy(d.ev_t1);
+    if (d.cache) for (auto &kv : d.cache->parked) cudaFreeAsync(kv.second, d.stream);
+    cudaStreamSynchronize(d.stream);
     if (d.pool) cudaMemPoolDestroy(d.pool);
     cudaStreamDestroy(d.stream);
   }

@@ -2,8 +2,11 @@
 #pragma once
 
 #include <atomic>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "qs_ops.cuh"
@@ -69,8 +72,24 @@ struct qsgpu_join_table {
 
 namespace qs {
 
+// Exact-size cache of large device blocks in front of the stream-ordered pool.  A query allocates the
+// same temporaries (Select / join outputs, hash tables, block images) in the same sizes every time; the
+// driver pool may split a bigger free block for a smaller request and then has to map fresh memory for the
+// big one (15 ms for 1.9 GB, r01g profile).  Blocks >= 1 MB are therefore rounded to 2 MB multiples and,
+// when freed, parked here for the next request of the same size.  Safe without events because every user
+// of such a block runs on the device's single library stream.
+struct BlockCache {
+  std::mutex mu;
+  std::unordered_map<void *, size_t> live;          // large blocks handed out -> rounded size
+  std::multimap<size_t, void *> parked;             // freed, ready for reuse
+  size_t parked_bytes = 0;
+  static constexpr size_t kMinBytes = 1u << 20, kRound = 2u << 20;
+  static constexpr size_t kMaxParkedBytes = 64ull << 30;
+};
+
 struct Device {
   int id = 0;
+  std::shared_ptr<BlockCache> cache;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   size_t smem_per_sm = 0, smem_per_block_optin = 0;
