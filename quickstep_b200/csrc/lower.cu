@@ -137,8 +137,9 @@ static uint64_t literal_raw(const qs_node *n) {
     case QS_FLOAT: { uint32_t u; std::memcpy(&u, &n->lit.f32, 4); return u; }
     case QS_DOUBLE: { uint64_t u; std::memcpy(&u, &n->lit.f64, 8); return u; }
     case QS_DATE:
-      return static_cast<uint64_t>(static_cast<int64_t>(n->lit.date.year) * 65536 +
-                                   (static_cast<int64_t>(n->lit.date.month) << 8) + n->lit.date.day);
+      // same key as date_key() on the device: year in the high word, month<<8 | day in the low word
+      return (static_cast<uint64_t>(static_cast<uint32_t>(n->lit.date.year)) << 32) |
+             (static_cast<uint64_t>(n->lit.date.month) << 8) | n->lit.date.day;
     default: return 0;
   }
 }

@@ -36,11 +36,14 @@ __device__ __forceinline__ double u2d(uint64_t u) { return __longlong_as_double(
 __device__ __forceinline__ uint64_t f2u(float f) { return static_cast<uint64_t>(__float_as_uint(f)); }
 __device__ __forceinline__ float u2f(uint64_t u) { return __uint_as_float(static_cast<uint32_t>(u)); }
 
-// DateLit {int32 year; u8 month; u8 day; pad} -> order-preserving int64 key.
+// DateLit {int32 year; u8 month; u8 day; pad} -> order-preserving int64 key: year in the high word (signed),
+// month<<8 | day in the low word.  One PRMT: the year is already its own 32-bit register, and a 64-bit signed
+// compare against a literal key is an ISETP pair (the previous year*65536+month*256+day form cost 9
+// instructions per row in the Q1/Q6 predicates, r01c SASS).  lower.cu builds literal keys the same way.
 __device__ __forceinline__ uint64_t date_key(uint64_t raw) {
-  const int64_t year = static_cast<int32_t>(raw & 0xffffffffu);
-  const uint64_t md = ((raw >> 32) & 0xff) << 8 | ((raw >> 40) & 0xff);
-  return static_cast<uint64_t>(year * 65536 + static_cast<int64_t>(md));
+  const uint32_t year = static_cast<uint32_t>(raw);
+  const uint32_t md = __byte_perm(static_cast<uint32_t>(raw >> 32), 0u, 0x4401);   // byte0 = day, byte1 = month
+  return (static_cast<uint64_t>(year) << 32) | md;
 }
 
 // Load one native value (sign-extending ints) from a staged / global column.
@@ -360,15 +363,23 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
   }
 }
 
-// Validity of this thread's rows in `tile` (row range may start/end mid-tile).
+// Validity of this thread's rows in `tile` (row range may start/end mid-tile).  Only the first and the
+// last tile of a scan can hold rows outside [row_begin, row_end): every other tile takes the CTA-uniform
+// fast path and pays nothing per row.
 __device__ __forceinline__ void tile_valid(const ScanDesc &S, const ScanRt &rt, uint32_t tile, int tid,
                                            bool (&valid)[kRows]) {
   const uint64_t row0 = S.first_row + static_cast<uint64_t>(tile) * kTileRows;
+  uint32_t mask = (1u << kRows) - 1u;
+  if (row0 < S.row_begin || row0 + kTileRows > rt.row_end) {
+    mask = 0;
 #pragma unroll
-  for (int r = 0; r < kRows; ++r) {
-    const uint64_t row = row0 + tile_row(r, tid);
-    valid[r] = row >= S.row_begin && row < rt.row_end;
+    for (int r = 0; r < kRows; ++r) {
+      const uint64_t row = row0 + tile_row(r, tid);
+      mask |= (row >= S.row_begin && row < rt.row_end) ? (1u << r) : 0u;
+    }
   }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) valid[r] = (mask >> r) & 1u;
 }
 
 }  // namespace qs
