@@ -237,7 +237,7 @@ def main():
             st.run(rel)
             merge_across_ranks(st)
             fin, _ = E.finalize_relation(st, q1p.key_schema, [(A.QS_DOUBLE, 8)] * 5 + [(A.QS_LONG, 8)])
-            c = [fin.read(i) for i in range(8)]
+            c = fin.read_all()
             fin.destroy()
             return T.q1_rows_from_states(c[0], c[1], c[2:7], c[7])
         finally:

@@ -142,6 +142,12 @@ int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs,
 int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
                         uint64_t n_rows, void *host_out);
 
+/* All attributes at once: host_out[a] receives rows [row_begin, row_begin+n_rows) of attribute a; the
+ * copies are queued back to back and waited for once (result relations are a handful of rows wide and
+ * tall: one synchronisation instead of one per column). */
+int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows,
+                            void *const *host_out);
+
 /*
  * K0 -- staging of one storage block's attribute into a device relation,
  * appended at the relation's current end.  Physical encodings of the

@@ -121,6 +121,7 @@ SIGNATURES = {
     "qsgpu_relation_column": (C.c_int, [_VP, C.c_uint32, _VPP]),
     "qsgpu_relation_wrap": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), _VPP, C.c_uint64, _VPP]),
     "qsgpu_relation_read": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, _VP]),
+    "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
     "qsgpu_stage_blocks": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
     "qsgpu_lip_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_uint64, C.c_int, _VPP]),

@@ -555,6 +555,20 @@ int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
   return QSGPU_OK;
 }
 
+int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, void *const *host_out) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  if (row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  for (size_t a = 0; a < rel->cols.size(); ++a) {
+    const uint32_t w = rel->attrs[a].width;
+    if (n_rows) QS_CUDA(cudaMemcpyAsync(host_out[a], rel->cols[a] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
+  }
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return QSGPU_OK;
+}
+
 int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc *descs, uint32_t n_desc) {
   int st = sync_rows(rel);
   if (st) return st;

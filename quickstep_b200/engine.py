@@ -187,6 +187,16 @@ class Relation:
             A.check(A.load().qsgpu_relation_read(self.h, attr, lo, n, out.ctypes.data))
         return out[:n]
 
+    def read_all(self, lo=0, n=None):
+        """Every column of rows [lo, lo+n) with one synchronisation (qsgpu_relation_read_all)."""
+        if n is None:
+            n = self.n_rows - lo
+        outs = [np.zeros(max(n, 1), dtype=np_dtype(t, w)) for (t, w) in self.schema]
+        if n:
+            ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+            A.check(A.load().qsgpu_relation_read_all(self.h, lo, n, ptrs))
+        return [o[:n] for o in outs]
+
     def to_host(self, name=None) -> HostTable:
         n = self.n_rows
         return HostTable(name or "rel", [Column(self.names[i], t, self.read(i, 0, n), w)

@@ -253,11 +253,16 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
 
   qsgpu_relation_t out = db->sm->temporary(*t_out);
   const std::uint64_t n = numRows(out);
-  const auto flag = readColumn<char>(out, 0, n), status = readColumn<char>(out, 1, n);
+  std::vector<char> flag(n + 1), status(n + 1);
   std::array<std::vector<double>, 7> d;
-  for (int j = 0; j < 7; ++j) d[j] = readColumn<double>(out, 2 + j, n);
-  const auto count = readColumn<std::int64_t>(out, 9, n);
-  const auto sum_disc = readColumn<double>(out, 10, n);
+  for (auto &v : d) v.resize(n + 1);
+  std::vector<std::int64_t> count(n + 1);
+  std::vector<double> sum_disc(n + 1);
+  {
+    void *cols[11] = {flag.data(), status.data(), d[0].data(), d[1].data(), d[2].data(), d[3].data(), d[4].data(),
+                      d[5].data(), d[6].data(), count.data(), sum_disc.data()};
+    QS_CHECK_GPU(qsgpu_relation_read_all(out, 0, n, cols));
+  }
   std::vector<qshost_q1_row> res(n);
   for (std::uint64_t i = 0; i < n; ++i) {
     qshost_q1_row &r = res[i];
@@ -320,7 +325,7 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   const auto dst2 = ctx.addInsertDestination(t2, n_orders), dst0 = ctx.addInsertDestination(t0, n_lineitem),
              dst4 = ctx.addInsertDestination(t4, n_lineitem), dst7 = ctx.addInsertDestination(t7, 1),
              dst9 = ctx.addInsertDestination(t9, 10);
-  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, n_orders / 2));
+  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, n_orders / 4));
 
   QueryContext::ScalarGroup s4;     // l_orderkey, o_orderdate, o_shippriority, l_extendedprice, l_discount
   s4.roots = {s4.exprs.attr(0, kInt), s4.exprs.attr(1, kDate, 2), s4.exprs.attr(2, kInt, 2), s4.exprs.attr(1, kDouble),
@@ -372,10 +377,13 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
 
   qsgpu_relation_t out = db->sm->temporary(*t9);
   const std::uint64_t n = numRows(out);
-  const auto ok = readColumn<std::int32_t>(out, 0, n);
-  const auto od = readColumn<std::uint64_t>(out, 1, n);
-  const auto sp = readColumn<std::int32_t>(out, 2, n);
-  const auto rev = readColumn<double>(out, 3, n);
+  std::vector<std::int32_t> ok(n + 1), sp(n + 1);
+  std::vector<std::uint64_t> od(n + 1);
+  std::vector<double> rev(n + 1);
+  {
+    void *cols[4] = {ok.data(), od.data(), sp.data(), rev.data()};
+    QS_CHECK_GPU(qsgpu_relation_read_all(out, 0, n, cols));
+  }
   const std::uint32_t cap = *n_rows;
   *n_rows = static_cast<std::uint32_t>(n);
   for (std::uint32_t i = 0; i < std::min<std::uint64_t>(cap, n); ++i) {

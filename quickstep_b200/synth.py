@@ -81,7 +81,7 @@ def generate(n_lineitem: int, seed: int, device, key_base: int = 0):
     out["_stats"] = dict(c_custkey_min=1, c_custkey_max=n_cust,
                          o_orderkey_min=int(out["o_orderkey"][0]), o_orderkey_max=int(out["o_orderkey"][-1]),
                          orders_rows=n_orders, lineitem_rows=n_lineitem, customer_rows=n_cust,
-                         t2_estimate=n_orders // 2, groups_estimate=max(1024, n_orders // 8),
+                         t2_estimate=n_orders // 4, groups_estimate=max(1024, n_orders // 8),
                          t4_capacity=max(1024, n_lineitem // 4))
     return out
 

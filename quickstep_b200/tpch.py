@@ -200,7 +200,7 @@ def run_q1(lineitem: E.Relation, plan: Q1Plan | None = None, row_ranges=None):
             st.run(lineitem, lo, hi)
         out_types = [(A.QS_DOUBLE, 8)] * 5 + [(A.QS_LONG, 8)]
         rel, _ = E.finalize_relation(st, plan.key_schema, out_types)
-        cols = [rel.read(i) for i in range(8)]
+        cols = rel.read_all()
         rel.destroy()
         return q1_rows_from_states(cols[0], cols[1], cols[2:7], cols[7])
     finally:

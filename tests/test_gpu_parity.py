@@ -299,6 +299,36 @@ def test_group_by_strategies(G, OB, strategy, n):
     assert_agg_equal(g, o, es, aggs)
 
 
+def test_compact_key_non_finite_values_stay_in_their_group(G, OB):
+    """inf / NaN arguments of a double SUM poison only their own group (the register-resident hot groups are
+    updated with v * {1.0|0.0} + sum, which must not see non-finite v), and the other aggregates of the same
+    rows are unaffected.  Group 0: finite only; 1: +inf; 2: NaN; 3: +inf and -inf (NaN); 4..5: cold groups."""
+    n = 40000
+    rng = np.random.default_rng(77)
+    g = rng.integers(0, 6, size=n).astype(np.int32)
+    v = rng.normal(0, 100, size=n)
+    w = rng.normal(0, 1, size=n)
+    idx = lambda k: np.flatnonzero(g == k)
+    v[idx(1)[5]] = np.inf
+    v[idx(2)[7]] = np.nan
+    v[idx(3)[3]] = np.inf
+    v[idx(3)[900]] = -np.inf
+    v[idx(5)[11]] = np.inf
+    th = HostTable("t", [Column("g", A.QS_INT, g), Column("v", A.QS_DOUBLE, v), Column("w", A.QS_DOUBLE, w)])
+    es = ExprSet()
+    aggs = [(A.QS_AGG_SUM, th.attr(es, "v")), (A.QS_AGG_SUM, th.attr(es, "w")), (A.QS_AGG_COUNT, -1)]
+    gr = G.aggregate(G.relation(th), es, -1, aggs, [th.attr(es, "g")], A.QS_AGG_COMPACT_KEY, [(A.QS_INT, 4)])
+    o = OB.aggregate(th, es, -1, aggs, [th.attr(es, "g")], A.QS_AGG_COMPACT_KEY, [(A.QS_INT, 4)])
+    assert gr.n_groups == o.n_groups == 6 and (gr.keys == o.keys).all()
+    gs, os_ = np.asarray(gr.values[0], dtype=np.float64), np.asarray(o.values[0], dtype=np.float64)
+    assert (np.isnan(gs) == np.isnan(os_)).all() and (np.isinf(gs) == np.isinf(os_)).all()
+    fin = np.isfinite(os_)
+    assert fin.sum() == 2 and np.allclose(gs[fin], os_[fin], rtol=1e-9, atol=0)
+    assert (gs[np.isinf(os_)] == os_[np.isinf(os_)]).all()
+    assert np.allclose(np.asarray(gr.values[1], dtype=np.float64), np.asarray(o.values[1], dtype=np.float64), rtol=1e-9, atol=1e-12)
+    assert (gr.values[2] == o.values[2]).all()
+
+
 def test_single_state_empty_input_is_null(G, OB):
     """SUM over zero rows is NULL (AggregationHandleSum.cpp:134-143); COUNT is 0."""
     th = K.random_table(500, seed=3)
