@@ -323,6 +323,9 @@ int qsgpu_init(int n_dev, const int *dev_ids) {
       uint64_t keep = UINT64_MAX;
       QS_CUDA(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
       d.cache = std::make_shared<BlockCache>();
+      d.read_mu = std::make_shared<std::mutex>();
+      QS_CUDA(cudaMalloc(&d.read_scratch, kReadScratchBytes));
+      QS_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d.read_pinned), kReadScratchBytes, cudaHostAllocPortable));
     }
     QS_CUDA(cudaMalloc(&d.d_error, 256));
     QS_CUDA(cudaMemset(d.d_error, 0, 256));
@@ -342,6 +345,8 @@ int qsgpu_shutdown(void) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
     cudaFree(d.d_error);
+    cudaFree(d.read_scratch);
+    cudaFreeHost(d.read_pinned);
     cudaEventDestroy(d.ev0);
     cudaEventDestroy(d.ev1);
     cudaEventDestroy(d.ev_t0);
@@ -561,9 +566,32 @@ int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n
   if (row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
   Device *d = device(rel->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (n_rows == 0) return QSGPU_OK;
+  size_t total = 0;
+  for (size_t a = 0; a < rel->cols.size(); ++a) total += (n_rows * rel->attrs[a].width + 15) & ~static_cast<size_t>(15);
+  if (total <= kReadScratchBytes && d->read_scratch) {
+    // Small result: pack the columns with device-to-device copies (truly asynchronous), ONE transfer into
+    // pinned memory, one wait.  A pageable destination would make every column copy a blocking call.
+    std::lock_guard<std::mutex> lk(*d->read_mu);
+    size_t off = 0;
+    for (size_t a = 0; a < rel->cols.size(); ++a) {
+      const size_t bytes = n_rows * rel->attrs[a].width;
+      QS_CUDA(cudaMemcpyAsync(d->read_scratch + off, rel->cols[a] + row_begin * rel->attrs[a].width, bytes, cudaMemcpyDeviceToDevice, d->stream));
+      off += (bytes + 15) & ~static_cast<size_t>(15);
+    }
+    QS_CUDA(cudaMemcpyAsync(d->read_pinned, d->read_scratch, total, cudaMemcpyDeviceToHost, d->stream));
+    QS_CUDA(cudaStreamSynchronize(d->stream));
+    off = 0;
+    for (size_t a = 0; a < rel->cols.size(); ++a) {
+      const size_t bytes = n_rows * rel->attrs[a].width;
+      std::memcpy(host_out[a], d->read_pinned + off, bytes);
+      off += (bytes + 15) & ~static_cast<size_t>(15);
+    }
+    return QSGPU_OK;
+  }
   for (size_t a = 0; a < rel->cols.size(); ++a) {
     const uint32_t w = rel->attrs[a].width;
-    if (n_rows) QS_CUDA(cudaMemcpyAsync(host_out[a], rel->cols[a] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
+    QS_CUDA(cudaMemcpyAsync(host_out[a], rel->cols[a] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
   }
   QS_CUDA(cudaStreamSynchronize(d->stream));
   return QSGPU_OK;
@@ -1230,8 +1258,9 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   if (!d) return QSGPU_ERR_NO_DEVICE;
   AggDesc &A = state->A;
   const bool dense = state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY;
-  uint64_t n = 0;
-  int st = dense ? agg_num_groups_locked(state, &n) : collect_groups(state, d, &n);
+  uint64_t n = 1;                     // a single state is one row; no need to ask the device
+  int st = state->strategy == QS_AGG_SINGLE_STATE ? QSGPU_OK
+           : dense ? agg_num_groups_locked(state, &n) : collect_groups(state, d, &n);
   if (st) return st;
   // output schema: group-by attributes, then one column per aggregate
   std::vector<qs_attr> attrs = state->key_attrs;
@@ -1268,6 +1297,7 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   for (uint32_t k = 0; k < A.n_key_cols; ++k) F.key_out[k] = rel->cols[k];
   for (uint32_t j = 0; j < F.n_out; ++j) F.out[j] = rel->cols[A.n_key_cols + j];
   const uint64_t *keys = dense ? A.gid_keys : A.keys;
+  F.rows_out = rel->d_rows;
   KernelTimer timer(d, QS_K_GROUPBY);
   cudaError_t e = launch_finalize(A.states, keys, A.words, dense ? nullptr : state->d_idx, n, F, d->stream);
   count_launch();
@@ -1283,8 +1313,8 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
           if (state->aggregates[j].function != QS_AGG_COUNT) *null_mask |= 1ull << j;
     }
   }
-  st = qsgpu_relation_set_num_rows(rel, n);
-  if (st) { qsgpu_relation_destroy(rel); return st; }
+  rel->host_rows = n;                 // the kernel stored n in the relation's device counter
+  rel->dirty = false;
   *out = rel;
   return QSGPU_OK;
 }

@@ -126,6 +126,7 @@ __global__ void k_gather_rows(const uint64_t *states, const uint64_t *keys, uint
 
 __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_t words, const uint64_t *idx,
                            uint64_t n, const __grid_constant__ FinalizeDesc F) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && F.rows_out) *F.rows_out = n;
   for (uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; g < n;
        g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t s = idx ? idx[g] : g;
@@ -205,8 +206,7 @@ cudaError_t launch_gather_rows(const uint64_t *states, const uint64_t *keys, uin
 
 cudaError_t launch_finalize(const uint64_t *states, const uint64_t *keys, uint32_t words, const uint64_t *idx,
                             uint64_t n, const FinalizeDesc &F, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  k_finalize<<<grid_for(n, 256), 256, 0, st>>>(states, keys, words, idx, n, F);
+  k_finalize<<<grid_for(n ? n : 1, 256), 256, 0, st>>>(states, keys, words, idx, n, F);
   return cudaGetLastError();
 }
 

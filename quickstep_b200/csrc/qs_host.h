@@ -72,6 +72,8 @@ struct qsgpu_join_table {
 
 namespace qs {
 
+constexpr size_t kReadScratchBytes = 256u << 10;
+
 // Exact-size cache of large device blocks in front of the stream-ordered pool.  A query allocates the
 // same temporaries (Select / join outputs, hash tables, block images) in the same sizes every time; the
 // driver pool may split a bigger free block for a smaller request and then has to map fresh memory for the
@@ -90,6 +92,9 @@ struct BlockCache {
 struct Device {
   int id = 0;
   std::shared_ptr<BlockCache> cache;
+  // staging for qsgpu_relation_read_all of small results: device pack buffer + pinned landing buffer
+  char *read_scratch = nullptr, *read_pinned = nullptr;
+  std::shared_ptr<std::mutex> read_mu;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   size_t smem_per_sm = 0, smem_per_block_optin = 0;

@@ -50,6 +50,7 @@ struct FinalizeDesc {
   uint8_t word_is_f64[kMaxOut];
   char *out[kMaxOut];
   int keys_are_slots;          // collision free: key value == slot index
+  unsigned long long *rows_out;   // device row counter of the output relation (set to n by the kernel)
 };
 
 // One (block, attribute) stripe of a batched staging call (qsgpu_stage_blocks).
