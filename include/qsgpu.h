@@ -346,6 +346,12 @@ typedef struct qsgpu_join_table *qsgpu_join_table_t;
 
 int qsgpu_join_create(int dev, uint32_t key_type /*QS_INT|QS_LONG*/,
                       uint64_t estimated_num_entries, qsgpu_join_table_t *out);
+/* Dense ("CollisionFreeVector-style") table for build keys bounded by exact statistics [min_key, max_key]
+ * (what \analyze records, catalog/CatalogRelationStatistics.hpp): heads[key - min_key] -> chain of build
+ * rows.  No hashing and no key comparison; duplicates are chained.  Same build / probe entry points; a
+ * build key outside the declared range raises QSGPU_ERR_INVALID. */
+int qsgpu_join_create_dense(int dev, uint32_t key_type, int64_t min_key, int64_t max_key,
+                            qsgpu_join_table_t *out);
 /* BuildHashWorkOrder::execute (BuildHashOperator.cpp:162-207): predicate ->
  * LIP build -> put(key -> row id).  The build relation must outlive the table. */
 int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan,
@@ -404,12 +410,13 @@ int qsgpu_last_kernel_ms(uint32_t family, float *ms);
  * the library).  qsgpu_jit_selfcheck compiles representative work order
  * `which` (0..QSGPU_JIT_SELFCHECK_CASES-1: Q6-style single-state aggregate,
  * Q1-style compact-key group-by, select with LIP probes, BuildLIPFilter, join
- * build, inner probe with residual, anti probe, hash group-by, dense group-by)
+ * build, inner probe with residual, anti probe, hash group-by, dense group-by,
+ * dense join build, dense inner probe)
  * WITHOUT a device -- the "does every kernel family still compile" check of
  * build() and the CPU test suite.  The generated CUDA source and the NVRTC log
  * are copied into the optional buffers.
  */
-#define QSGPU_JIT_SELFCHECK_CASES 9
+#define QSGPU_JIT_SELFCHECK_CASES 11
 int qsgpu_jit_selfcheck(uint32_t which, char *source_out, size_t source_bytes,
                         char *log_out, size_t log_bytes);
 /* NVRTC compilations / disk-cache hits / in-memory hits since load. */

@@ -139,6 +139,7 @@ SIGNATURES = {
     "qsgpu_agg_finalize": (C.c_int, [_VP, _VPP, _U64P]),
     "qsgpu_agg_destroy": (C.c_int, [_VP]),
     "qsgpu_join_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, _VPP]),
+    "qsgpu_join_create_dense": (C.c_int, [C.c_int, C.c_uint32, C.c_int64, C.c_int64, _VPP]),
     "qsgpu_join_build": (C.c_int, [_VP, C.POINTER(qs_scan), C.c_uint32, C.c_uint32, C.POINTER(qs_lip_ref)]),
     "qsgpu_join_num_entries": (C.c_int, [_VP, _U64P]),
     "qsgpu_join_probe": (C.c_int, [_VP, C.POINTER(qs_scan), C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
@@ -151,7 +152,7 @@ SIGNATURES = {
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }
-JIT_SELFCHECK_CASES = 9
+JIT_SELFCHECK_CASES = 11
 
 
 class QsGpuError(RuntimeError):

@@ -1352,14 +1352,40 @@ int qsgpu_join_create(int dev, uint32_t key_type, uint64_t estimated_num_entries
   return QSGPU_OK;
 }
 
+int qsgpu_join_create_dense(int dev, uint32_t key_type, int64_t min_key, int64_t max_key, qsgpu_join_table_t *out) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (key_type != QS_INT && key_type != QS_LONG) { set_error(QSGPU_ERR_UNSUPPORTED, "join keys are single INT/LONG attributes"); return QSGPU_ERR_UNSUPPORTED; }
+  if (max_key < min_key || static_cast<uint64_t>(max_key - min_key) >= (1ull << 34)) { set_error(QSGPU_ERR_INVALID, "dense join table needs min <= max and a key range below 2^34"); return QSGPU_ERR_INVALID; }
+  std::unique_ptr<qsgpu_join_table> t(new qsgpu_join_table);
+  t->dev = dev;
+  t->key_type = key_type;
+  t->J.dense = 1;
+  t->J.min_key = min_key;
+  t->J.cap = static_cast<uint64_t>(max_key - min_key) + 1;
+  t->J.error_flag = d->d_error;
+  t->J.key_ltype = key_type == QS_INT ? V_I32 : V_I64;
+  QS_CUDA(dev_malloc(&t->J.heads, t->J.cap * 8));
+  QS_CUDA(dev_malloc(&t->J.n_entries, 256));
+  QS_CUDA(cudaMemsetAsync(t->J.n_entries, 0, 256, d->stream));
+  QS_CUDA(launch_join_clear(t->J, d->stream));
+  count_launch();
+  *out = t.release();
+  return QSGPU_OK;
+}
+
 int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan, uint32_t key_attr, uint32_t n_lip_build,
                      const qs_lip_ref *lip_build) {
   qsgpu_relation *rel = scan->input;
   Device *d = device(table->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   if (rel->dev != table->dev || key_attr >= rel->attrs.size() || rel->attrs[key_attr].type != table->key_type) { set_error(QSGPU_ERR_INVALID, "build key attribute does not match the table"); return QSGPU_ERR_INVALID; }
-  if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
-  table->build_rel = rel;
+  {
+    std::lock_guard<std::mutex> lk(table->mu);      // build work orders of one operator run concurrently
+    if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
+    table->build_rel = rel;
+    if (table->J.dense && !table->J.next && !t_sc) QS_CUDA(dev_malloc(&table->J.next, std::max<uint64_t>(rel->capacity, 1) * 8));
+  }
   Lowering L(scan->exprs, rel);
   int st = lower_scan_predicate(L, scan);
   if (st) return st;
@@ -1451,6 +1477,8 @@ int qsgpu_join_destroy(qsgpu_join_table_t t) {
   if (!t) return QSGPU_OK;
   device(t->dev);
   dev_free(t->J.slots);
+  dev_free(t->J.heads);
+  dev_free(t->J.next);
   dev_free(t->J.n_entries);
   delete t;
   return QSGPU_OK;

@@ -12,7 +12,22 @@ __global__ void k_join_clear(JoinSlot *slots, uint64_t cap) {
   }
 }
 
+__global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
+cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  uint64_t g = (n + 255) / 256;
+  if (g > 148ull * 16) g = 148ull * 16;
+  k_fill_u64<<<static_cast<unsigned>(g), 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st) {
+  if (J.dense) return launch_fill_u64(J.heads, J.cap, kEmptyRow, st);
   uint64_t g = (J.cap + 255) / 256;
   if (g > 148ull * 16) g = 148ull * 16;
   k_join_clear<<<static_cast<unsigned>(g), 256, 0, st>>>(J.slots, J.cap);

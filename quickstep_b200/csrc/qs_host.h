@@ -64,6 +64,7 @@ struct qsgpu_agg_state {
 };
 
 struct qsgpu_join_table {
+  std::mutex mu;
   int dev = 0;
   uint32_t key_type = QS_INT;
   qs::JoinDesc J{};

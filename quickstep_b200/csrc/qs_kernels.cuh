@@ -622,6 +622,14 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
       if (!pass[r]) continue;
       const int64_t key = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
       const unsigned long long row = row0 + tile_row(r, tid);
+      if constexpr (Q::j_dense) {
+        // push the row on the front of its key's chain: one exchange, one store
+        const uint64_t k = static_cast<uint64_t>(key - J.min_key);
+        if (key < J.min_key || k >= J.cap) { atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_INVALID)); continue; }
+        J.next[row] = atomicExch(&J.heads[k], row);
+        ++inserted;
+        continue;
+      }
       uint64_t h = mix64(static_cast<uint64_t>(key)) & mask;
       bool done = false;
       for (uint64_t probes = 0; probes <= mask; ++probes) {
@@ -718,7 +726,13 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       active[r] = pass[r];
       matched[r] = false;
       key[r] = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
-      h[r] = mix64(static_cast<uint64_t>(key[r])) & mask;
+      if constexpr (Q::j_dense) {
+        // h[r] walks the chain of build rows: head of the key's chain, then next[]
+        const uint64_t k = static_cast<uint64_t>(key[r] - J.min_key);
+        h[r] = (active[r] && key[r] >= J.min_key && k < J.cap) ? J.heads[k] : kEmptyRow;
+      } else {
+        h[r] = mix64(static_cast<uint64_t>(key[r])) & mask;
+      }
     }
 
     while (true) {
@@ -729,6 +743,13 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         found[r] = false;
         sink.brow[r] = kEmptyRow;
         if (!active[r]) continue;
+        if constexpr (Q::j_dense) {
+          if (h[r] != kEmptyRow) {
+            found[r] = true;
+            sink.brow[r] = h[r];
+            h[r] = J.next[h[r]];
+          }
+        } else
         for (uint64_t probes = 0; probes <= mask; ++probes) {
           const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(&J.slots[h[r]]);
           if (s.y == kEmptyRow) { active[r] = false; break; }

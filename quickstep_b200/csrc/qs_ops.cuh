@@ -27,8 +27,16 @@ struct __align__(16) JoinSlot {                   // 16 bytes, one vector load p
 };
 
 struct JoinDesc {
-  JoinSlot *slots;
-  uint64_t cap;                     // power of two
+  JoinSlot *slots;                  // open addressing: {key, build row} slots
+  // Dense ("collision-free vector") table: heads[key - min_key] is the most recently inserted build row
+  // with that key (~0 = none), next[row] chains the earlier ones.  No hashing, no key compare, 8 bytes
+  // per key of the declared range -- the join-side analogue of CollisionFreeVectorTable
+  // (storage/CollisionFreeVectorTable.hpp:56), usable when exact min/max statistics bound the build key.
+  unsigned long long *heads;
+  unsigned long long *next;         // indexed by build row id; sized to the build relation's capacity
+  int64_t min_key;
+  uint32_t dense;                   // 0 = open addressing, 1 = dense
+  uint64_t cap;                     // open addressing: power of two;  dense: max_key - min_key + 1
   unsigned long long *n_entries;
   uint16_t key_col;                 // staged column slot of the key
   uint8_t key_ltype;                // V_I32 / V_I64
@@ -87,6 +95,7 @@ cudaError_t launch_finalize(const uint64_t *states, const uint64_t *keys, uint32
                             uint64_t n, const FinalizeDesc &F, cudaStream_t st);
 // k_join.cu
 cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st);
+cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st);
 // k_misc.cu
 cudaError_t launch_decode_dict(void *dst, const void *codes, const void *dict, uint64_t n, uint32_t code_width,
                                uint32_t value_width, uint32_t dict_entries, cudaStream_t st);

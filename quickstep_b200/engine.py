@@ -348,10 +348,14 @@ def finalize_relation(state: AggState, key_schema, agg_out_types, names=None) ->
 
 
 class JoinTable:
-    def __init__(self, key_type, estimated, dev=0):
+    def __init__(self, key_type, estimated, dev=0, dense_range=None):
+        """dense_range=(min_key, max_key): a dense (collision-free vector style) table over that key range."""
         L = init()
         self.h = C.c_void_p()
-        A.check(L.qsgpu_join_create(dev, key_type, estimated, C.byref(self.h)))
+        if dense_range is not None:
+            A.check(L.qsgpu_join_create_dense(dev, key_type, dense_range[0], dense_range[1], C.byref(self.h)))
+        else:
+            A.check(L.qsgpu_join_create(dev, key_type, estimated, C.byref(self.h)))
 
     def build(self, rel, es, pred_root, key_attr, lip_probe=None, lip_build=None, row_begin=0,
               row_end=A.UINT64_MAX):

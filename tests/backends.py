@@ -180,7 +180,11 @@ class GpuBackend:
     def hash_join(self, build, bes_pred, build_key, probe, es, probe_pred, probe_key, join_type, residual, roots,
                   out_schema, capacity, build_es=None, probe_lips=None) -> HostTable:
         key_type = build.schema[build_key][0]
-        jt = self.E.JoinTable(key_type, max(16, build.n_rows))
+        dense = None
+        if getattr(self, "dense_join", False):       # dense (collision-free vector style) table over [min, max]
+            kv = build.read(build_key)
+            dense = (int(kv.min()), int(kv.max())) if len(kv) else (0, 0)
+        jt = self.E.JoinTable(key_type, max(16, build.n_rows), dense_range=dense)
         out = self.E.Relation.create(out_schema, max(1, capacity))
         try:
             jt.build(build, build_es if bes_pred >= 0 else None, bes_pred, build_key)

@@ -108,7 +108,9 @@ def test_aggregation_unittest_block_work_orders(G, OB):
 @pytest.mark.parametrize("key", ["long", "int"])
 @pytest.mark.parametrize("join_type", [A.QS_JOIN_INNER, A.QS_JOIN_LEFT_SEMI, A.QS_JOIN_LEFT_ANTI])
 @pytest.mark.parametrize("residual", [False, True])
-def test_hash_join_unittest(G, OB, key, join_type, residual):
+@pytest.mark.parametrize("table", ["open_addressing", "dense"])
+def test_hash_join_unittest(G, OB, key, join_type, residual, table):
+    G.dense_join = table == "dense"
     g = K.case_hash_join_unittest(G, key, join_type, residual)
     o = K.case_hash_join_unittest(OB, key, join_type, residual)
     assert g.n_rows == o.n_rows
@@ -116,6 +118,20 @@ def test_hash_join_unittest(G, OB, key, join_type, residual):
     if join_type == A.QS_JOIN_INNER and not residual:
         counts = np.bincount(g.columns[0].data.astype(np.int64), minlength=200)
         assert (counts[:100] == 3).all() and (counts[100:] == 0).all()
+
+
+def test_dense_join_rejects_keys_outside_declared_range(engine):
+    """A build key outside [min_key, max_key] of a dense table is an error, never a silent drop."""
+    from quickstep_b200.capi import QsGpuError
+    build = HostTable("b", [Column("k", A.QS_LONG, np.array([5, 6, 7, 42], dtype=np.int64))])
+    rel = engine.Relation.from_host(build)
+    jt = engine.JoinTable(A.QS_LONG, 16, dense_range=(0, 10))
+    try:
+        jt.build(rel, None, -1, 0)
+        with pytest.raises(QsGpuError):
+            jt.num_entries()
+    finally:
+        jt.destroy(); rel.destroy()
 
 
 # ------------------------------------------------------------ TPC-H, dbgen data
@@ -389,8 +405,10 @@ def test_partial_merge_between_states(engine, OB):
 
 
 # ----------------------------------------------------- joins, LIP, top-k, K8
-def test_join_duplicate_build_keys(G, OB):
+@pytest.mark.parametrize("table", ["open_addressing", "dense"])
+def test_join_duplicate_build_keys(G, OB, table):
     """allow_duplicate_keys (storage/HashTable.hpp:1284): every (probe, build) pair appears once."""
+    G.dense_join = table == "dense"
     rng = np.random.default_rng(4)
     build = HostTable("b", [Column("k", A.QS_INT, rng.integers(0, 300, size=2000).astype(np.int32)),
                             Column("p", A.QS_LONG, np.arange(2000, dtype=np.int64))])

@@ -33,6 +33,7 @@ ap.add_argument("--build-rows", type=int, default=1 << 26)
 ap.add_argument("--probe-rows", type=int, default=1 << 30)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--dense", action="store_true", help="dense (collision-free vector style) join table over the key range")
 args = ap.parse_args()
 
 sys.stdout.flush()
@@ -129,7 +130,7 @@ def step():
     else:
         lb, lp, n_b, n_p = build_rel, probe_rel, nb, npr
     E.set_timing(True)
-    jt = E.JoinTable(A.QS_LONG, max(n_b, 1024), dev=local)
+    jt = E.JoinTable(A.QS_LONG, max(n_b, 1024), dev=local, dense_range=(0, B - 1) if args.dense else None)
     jt.build(lb, None, -1, 0)
     t["build_ms"] = E.last_kernel_ms(A.QS_K_JOIN_BUILD)
     A.check(A.load().qsgpu_relation_set_num_rows(out_rel.h, 0))
@@ -168,6 +169,7 @@ if rank == 0:
     nbr, npp = res["n_build"], res["n_probe"]
     line = {"metric": "hash_join_microbench_ms", "value": tot, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "config": {"workload": f"{B} build rows x {P} probe rows, int64 keys, payload int64, 100% hit",
+                       "join_table": "dense heads[key-min] + next[row] chains" if args.dense else "open addressing, 16 B slots, load factor <= 0.5",
                        "build_rows_per_gpu": nb, "probe_rows_per_gpu": npr},
             "rows_per_s": (B + P) / (tot * 1e-3),
             "phases_ms": {"partition": part, "exchange": exch, "build": build, "probe": probe},
