@@ -593,6 +593,7 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
 // tile advance in lock-step "rounds" (one match per row per round) so that the
 // warp-ballot compaction and the VM stay CTA-uniform even with duplicate keys.
 constexpr unsigned long long kEmptyRow = ~0ull;
+constexpr unsigned long long kChainBit = 1ull << 63;     // dense join heads: "more rows follow in next[]"
 
 template <class Q>
 __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K,
@@ -626,7 +627,13 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
         // push the row on the front of its key's chain: one exchange, one store
         const uint64_t k = static_cast<uint64_t>(key - J.min_key);
         if (key < J.min_key || k >= J.cap) { atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_INVALID)); continue; }
-        J.next[row] = atomicExch(&J.heads[k], row);
+        // A head whose chain has more than one row carries kChainBit, so a probe of a unique key (the
+        // common case: the build side is a primary key) never has to read next[] to learn the chain ended.
+        // Every insert that displaces a non-empty head ORs the bit in afterwards; whichever order the
+        // exchanges and ORs land in, the final head of a multi-row chain has it set.
+        const unsigned long long old = atomicExch(&J.heads[k], row);
+        J.next[row] = old == kEmptyRow ? kEmptyRow : (old & ~kChainBit);
+        if (old != kEmptyRow) atomicOr(&J.heads[k], kChainBit);
         ++inserted;
         continue;
       }
@@ -735,6 +742,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       }
     }
 
+    bool first_step = true;
     while (true) {
       bool found[kRows];
       bool any = false;
@@ -746,8 +754,10 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         if constexpr (Q::j_dense) {
           if (h[r] != kEmptyRow) {
             found[r] = true;
-            sink.brow[r] = h[r];
-            h[r] = J.next[h[r]];
+            sink.brow[r] = h[r] & ~kChainBit;
+            // first step: the head says whether a chain follows; later steps walk next[] (rows there
+            // never carry the bit, so the walk ends at the kEmptyRow stored by the first insert)
+            h[r] = (first_step && !(h[r] & kChainBit)) ? kEmptyRow : J.next[h[r] & ~kChainBit];
           }
         } else
         for (uint64_t probes = 0; probes <= mask; ++probes) {
@@ -759,6 +769,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         if (!found[r]) active[r] = false;
         any |= found[r];
       }
+      first_step = false;
       if (!__syncthreads_or(any)) break;
       bool ok[kRows];
       if constexpr (has_residual) {
