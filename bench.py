@@ -380,12 +380,17 @@ def main():
             assert a["count_order"] == b["count_order"], (a, b)
             assert abs(a["sum_charge"] - b["sum_charge"]) <= 1e-9 * abs(b["sum_charge"]), (a, b)
 
+    if n == SF10_LINEITEM_ROWS:
+        workload = "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)"
+    else:
+        workload = (f"TPC-H Q1, lineitem {n:,} rows per GPU x {world} GPU(s) = {n * world:,} rows "
+                    f"(SF{n * world / 6_000_000:.0f}-sized), 42 B/row, 4 groups x 6 states")
     if rank == 0:
         line = {
             "metric": "tpch_q1_sf10_query_ms", "value": q1_ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": q1_wall, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)",
+            "config": {"workload": workload,
                        "rows_per_gpu": n, "total_rows": n * world, "partitioning": f"lineitem block-partitioned over {world} GPU(s)",
                        "l2": "inputs (2.5 GB per GPU) larger than L2 (126 MB); no flush needed",
                        "timing": "CUDA events on the library stream around K whole queries; max over ranks"},
