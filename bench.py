@@ -207,25 +207,28 @@ def main():
     q1p, q6p, q3p = T.Q1Plan(), T.Q6Plan(), T.Q3Plan()
     gather_buf = {}
 
+    lib_stream = torch.cuda.ExternalStream(E.stream_ptr(local), device=device) if world > 1 else None
+
     def merge_across_ranks(st):
         """Partial aggregation states (AggregationHandle::mergeStates across GPUs): every rank contributes a
-        fixed-size block [states: cap x words | packed keys: cap x key_words], one NCCL all-gather, then the
-        device merge kernel folds each foreign block into the local state keyed by the packed group key
-        (rows with a zero row count are skipped, so no group counts have to visit the host)."""
+        fixed-size block [states: rows x words | packed keys: rows x key_words], one NCCL all-gather, then the
+        device merge kernel folds each foreign block into the local state keyed by the packed group key (rows
+        with a zero row count are skipped).  Everything is queued on the library's stream behind the scan
+        kernel -- copies, the collective (NCCL orders itself after the current torch stream) and the merge
+        launches -- so the host never waits between the scan and the finalize."""
         if world == 1:
             return
-        ds, dk, _ng, w, kw = st.partial()          # waits for the scan; pointers + layout
-        cap = 256 if kw and st.n_group_by else 1
+        ds, dk, cap, w, kw = st.partial_layout()
         key = (w, kw, cap)
         if key not in gather_buf:
             gather_buf[key] = (torch.zeros(cap * (w + kw), dtype=torch.int64, device=device),
                                torch.zeros(world * cap * (w + kw), dtype=torch.int64, device=device))
+            torch.cuda.synchronize()
         mine, allb = gather_buf[key]
         E.memcpy_d2d_async(mine.data_ptr(), ds, cap * w * 8, local)
         E.memcpy_d2d_async(mine.data_ptr() + cap * w * 8, dk, cap * kw * 8, local)
-        E.synchronize(local)                       # library stream -> visible to NCCL's stream
-        dist.all_gather_into_tensor(allb, mine)
-        torch.cuda.synchronize()
+        with torch.cuda.stream(lib_stream):
+            dist.all_gather_into_tensor(allb, mine)
         for r in range(world):
             if r != rank:
                 base = allb.data_ptr() + r * cap * (w + kw) * 8

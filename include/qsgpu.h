@@ -91,6 +91,10 @@ int qsgpu_shutdown(void);
 int qsgpu_device_count(int *n_dev);
 /* Block until all work queued on `dev` by this library has completed. */
 int qsgpu_synchronize(int dev);
+/* The CUDA stream (cudaStream_t) all work of this library on `dev` is queued on.  A caller that runs its
+ * own device work between two calls (e.g. an NCCL collective on partial aggregation states) can queue it
+ * on this stream instead of synchronising the device around it. */
+int qsgpu_stream(int dev, void **stream);
 /* Number of kernels this library has launched since init (bench.py's
  * gpu_launches); never reset by the library. */
 int qsgpu_launch_count(uint64_t *n);
@@ -202,6 +206,15 @@ typedef struct qs_block_image {
 
 int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks,
                        const qs_block_image *blocks, uint32_t n_desc);
+/*
+ * Column pruning: a descriptor with encoding QS_ENC_SKIP leaves its attribute on the host (neither copied
+ * nor decoded; the device column keeps whatever it held).  qsgpu_stage_columns stages further attributes of
+ * blocks whose rows already exist on the device: the same blocks, in the same order, starting at row
+ * `first_row` -- the device cache is keyed by (block, attribute), so a query pays only for the attributes its
+ * operators reference, and a later query that needs more stages just those.
+ */
+int qsgpu_stage_columns(qsgpu_relation_t rel, uint64_t first_row, uint32_t n_blocks,
+                        const qs_block_image *blocks, uint32_t n_desc);
 
 /* ----------------------------------------------------------- LIP filters  */
 /*
@@ -319,6 +332,11 @@ int qsgpu_agg_num_groups(qsgpu_agg_state_t state, uint64_t *n_groups);
 int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys,
                       uint64_t *n_groups, uint32_t *words_per_group,
                       uint32_t *key_words);
+/* The same pointers and layout WITHOUT waiting for queued work orders, for the strategies whose state is a
+ * fixed-size array (SINGLE_STATE: 1 row, COMPACT_KEY: 256 rows; unused rows have a zero row count and are
+ * skipped by qsgpu_agg_merge_partial).  Contents are valid in stream order after the queued work orders. */
+int qsgpu_agg_partial_layout(qsgpu_agg_state_t state, void **d_states, void **d_keys,
+                             uint64_t *rows, uint32_t *words_per_group, uint32_t *key_words);
 /* Merge a partial state (device pointers on the state's device, same layout
  * as qsgpu_agg_partial returns) into `state`. */
 int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states,

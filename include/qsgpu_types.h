@@ -54,7 +54,8 @@ enum {
 };
 
 /* Physical encodings of a staged block stripe (see qsgpu_stage_block in qsgpu.h). */
-enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3 };
+enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3,
+       QS_ENC_SKIP = 4 /* batched staging only: leave this attribute on the host (column pruning) */ };
 
 /* Join types (relational_operators/HashJoinOperator.hpp:82-87). */
 enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };

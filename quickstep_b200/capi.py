@@ -21,7 +21,7 @@ QS_AGG_AVG, QS_AGG_COUNT, QS_AGG_MAX, QS_AGG_MIN, QS_AGG_SUM = range(5)
 QS_N_LITERAL, QS_N_ATTRIBUTE, QS_N_UNARY, QS_N_BINARY = 0, 1, 2, 3
 QS_N_SHARED = 5
 QS_N_TRUE, QS_N_FALSE, QS_N_COMPARISON, QS_N_NEGATION, QS_N_CONJUNCTION, QS_N_DISJUNCTION = 16, 17, 18, 19, 20, 21
-QS_ENC_PLAIN, QS_ENC_STRIDED, QS_ENC_DICT, QS_ENC_TRUNCATED = range(4)
+QS_ENC_PLAIN, QS_ENC_STRIDED, QS_ENC_DICT, QS_ENC_TRUNCATED, QS_ENC_SKIP = range(5)
 QS_LIP_BITVECTOR_EXACT, QS_LIP_SINGLE_IDENTITY_HASH = 0, 1
 QS_AGG_SINGLE_STATE, QS_AGG_COMPACT_KEY, QS_AGG_SEPARATE_CHAINING, QS_AGG_COLLISION_FREE = range(4)
 QS_JOIN_INNER, QS_JOIN_LEFT_SEMI, QS_JOIN_LEFT_ANTI, QS_JOIN_LEFT_OUTER = range(4)
@@ -103,6 +103,7 @@ SIGNATURES = {
     "qsgpu_shutdown": (C.c_int, []),
     "qsgpu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "qsgpu_synchronize": (C.c_int, [C.c_int]),
+    "qsgpu_stream": (C.c_int, [C.c_int, _VPP]),
     "qsgpu_launch_count": (C.c_int, [_U64P]),
     "qsgpu_malloc": (C.c_int, [C.c_int, C.c_size_t, _VPP]),
     "qsgpu_free": (C.c_int, [C.c_int, _VP]),
@@ -124,6 +125,7 @@ SIGNATURES = {
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
     "qsgpu_stage_blocks": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
+    "qsgpu_stage_columns": (C.c_int, [_VP, C.c_uint64, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
     "qsgpu_lip_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_uint64, C.c_int, _VPP]),
     "qsgpu_lip_destroy": (C.c_int, [_VP]),
     "qsgpu_lip_num_words": (C.c_int, [_VP, _U64P]),
@@ -135,6 +137,7 @@ SIGNATURES = {
     "qsgpu_agg_run": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(qs_lip_ref)]),
     "qsgpu_agg_num_groups": (C.c_int, [_VP, _U64P]),
     "qsgpu_agg_partial": (C.c_int, [_VP, _VPP, _VPP, _U64P, _U32P, _U32P]),
+    "qsgpu_agg_partial_layout": (C.c_int, [_VP, _VPP, _VPP, _U64P, _U32P, _U32P]),
     "qsgpu_agg_merge_partial": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
     "qsgpu_agg_finalize": (C.c_int, [_VP, _VPP, _U64P]),
     "qsgpu_agg_destroy": (C.c_int, [_VP]),

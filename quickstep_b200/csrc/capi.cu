@@ -309,6 +309,7 @@ int qsgpu_init(int n_dev, const int *dev_ids) {
     d.smem_per_sm = prop.sharedMemPerMultiprocessor;
     d.smem_per_block_optin = prop.sharedMemPerBlockOptin;
     QS_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    QS_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     {
       // Per-device stream-ordered arena: states, join tables and temporary relations are
       // allocated and freed once per query, so cudaMalloc/cudaFree (a device-wide
@@ -354,6 +355,7 @@ int qsgpu_shutdown(void) {
     if (d.cache) for (auto &kv : d.cache->parked) cudaFreeAsync(kv.second, d.stream);
     cudaStreamSynchronize(d.stream);
     if (d.pool) cudaMemPoolDestroy(d.pool);
+    cudaStreamDestroy(d.copy_stream);
     cudaStreamDestroy(d.stream);
   }
   t_dev = nullptr;
@@ -374,6 +376,13 @@ int qsgpu_synchronize(int dev) {
   if (!d) return QSGPU_ERR_NO_DEVICE;
   QS_CUDA(cudaStreamSynchronize(d->stream));
   return check_device_error(d);
+}
+
+int qsgpu_stream(int dev, void **stream) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  *stream = d->stream;
+  return QSGPU_OK;
 }
 
 int qsgpu_launch_count(uint64_t *n) { *n = g_launches.load(); return QSGPU_OK; }
@@ -656,13 +665,21 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
   return qsgpu_relation_set_num_rows(rel, rel->host_rows + n_rows);
 }
 
-int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks, const qs_block_image *blocks, uint32_t n_desc) {
-  int st = sync_rows(rel);
-  if (st) return st;
+// Shared body of qsgpu_stage_blocks (append) and qsgpu_stage_columns (fill attributes of rows that exist).
+//
+// Pipeline: the batch is cut into chunks of <= 64 MB of block images.  The images of chunk i travel on the
+// device's COPY stream while chunk i-1 is decoded on the library stream (one decode launch per chunk, every
+// stripe of the chunk in it).  Only the byte ranges of the stripes / dictionaries that are actually staged
+// are copied (attributes marked QS_ENC_SKIP stay on the host: column pruning), adjacent ranges -- also
+// across blocks that are contiguous in host memory, e.g. a buffer-pool slab -- merged into one copy.
+static constexpr uint64_t kStageChunkBytes = 64ull << 20;
+
+static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint32_t n_blocks,
+                      const qs_block_image *blocks, uint32_t n_desc) {
   Device *d = device(rel->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   if (!rel->owns_memory) { set_error(QSGPU_ERR_INVALID, "cannot stage into a wrapped relation"); return QSGPU_ERR_INVALID; }
-  if (n_desc != rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "qsgpu_stage_blocks must stage every attribute of the relation"); return QSGPU_ERR_INVALID; }
+  if (n_desc != rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "one stage descriptor per attribute of the relation is required (QS_ENC_SKIP leaves an attribute out)"); return QSGPU_ERR_INVALID; }
   if (n_blocks == 0) return QSGPU_OK;
   uint64_t total_rows = 0, image_bytes = 0;
   std::vector<uint64_t> img_off(n_blocks);
@@ -672,55 +689,50 @@ int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks, const qs_block_i
     image_bytes += (blocks[b].bytes + 15) & ~15ull;
     total_rows += blocks[b].n_rows;
   }
-  if (rel->host_rows + total_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "relation capacity exceeded while staging"); return QSGPU_ERR_CAPACITY; }
+  if (first_row + total_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "relation capacity exceeded while staging"); return QSGPU_ERR_CAPACITY; }
   KernelTimer timer(d, QS_K_STAGE);
   char *d_img = nullptr;
   StageSeg *d_segs = nullptr;
   QS_CUDA(dev_malloc(&d_img, image_bytes + 64));
-  // ---- H2D: one copy per run of blocks that are contiguous in host memory (a buffer-pool slab)
-  for (uint32_t b = 0; b < n_blocks;) {
-    uint32_t e = b + 1;
-    uint64_t bytes = blocks[b].bytes;
-    while (e < n_blocks && (blocks[e - 1].bytes & 15) == 0 &&
-           static_cast<const char *>(blocks[e].host) == static_cast<const char *>(blocks[e - 1].host) + blocks[e - 1].bytes) {
-      bytes += blocks[e].bytes;
-      ++e;
-    }
-    cudaError_t ce = cudaMemcpyAsync(d_img + img_off[b], blocks[b].host, bytes, cudaMemcpyHostToDevice, d->stream);
-    if (ce != cudaSuccess) { dev_free(d_img); return cuda_fail(ce, "qsgpu_stage_blocks H2D"); }
-    b = e;
-  }
-  // ---- one segment per (block, attribute)
+
+  struct Range { const char *host; uint64_t dev_off, bytes; };
+  struct Chunk { uint32_t seg_begin, seg_end; size_t range_begin, range_end; uint64_t tiles; };
   std::vector<StageSeg> segs;
+  std::vector<Range> ranges;
+  std::vector<Chunk> chunks;
   segs.reserve(static_cast<size_t>(n_blocks) * n_desc);
-  uint64_t row_base = rel->host_rows, tiles = 0;
+  uint64_t row_base = first_row, chunk_bytes = 0;
+  Chunk cur{0, 0, 0, 0, 0};
   int rc = QSGPU_OK;
+  std::vector<std::pair<uint64_t, uint64_t>> need;          // (offset, bytes) inside one block image
   for (uint32_t b = 0; b < n_blocks && rc == QSGPU_OK; ++b) {
     const qs_block_image &B = blocks[b];
     const char *h0 = static_cast<const char *>(B.host);
+    need.clear();
     for (uint32_t i = 0; i < n_desc; ++i) {
       const qs_stage_desc &s = B.descs[i];
+      if (s.encoding == QS_ENC_SKIP) continue;
       if (s.attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "stage: attribute out of range"); rc = QSGPU_ERR_INVALID; break; }
       const uint32_t w = rel->attrs[s.attr].width;
       const char *hs = static_cast<const char *>(s.host);
-      uint64_t need = 0;
+      uint64_t bytes = 0;
       switch (s.encoding) {
-        case QS_ENC_PLAIN: need = B.n_rows * w; break;
-        case QS_ENC_STRIDED: need = B.n_rows ? (B.n_rows - 1) * s.stride + w : 0; break;
+        case QS_ENC_PLAIN: bytes = B.n_rows * w; break;
+        case QS_ENC_STRIDED: bytes = B.n_rows ? (B.n_rows - 1) * s.stride + w : 0; break;
         case QS_ENC_DICT: case QS_ENC_TRUNCATED:
           if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; }
           if (s.encoding == QS_ENC_TRUNCATED && w != 4 && w != 8) { set_error(QSGPU_ERR_INVALID, "truncation applies to INT/LONG"); rc = QSGPU_ERR_INVALID; }
-          need = B.n_rows * s.code_width;
+          bytes = B.n_rows * s.code_width;
           break;
         default: set_error(QSGPU_ERR_INVALID, "unknown staging encoding"); rc = QSGPU_ERR_INVALID;
       }
       if (rc != QSGPU_OK) break;
-      if (hs < h0 || hs + need > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: stripe lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+      if (!hs || hs < h0 || hs + bytes > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: stripe lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
       StageSeg g{};
       g.dst = rel->cols[s.attr] + row_base * w;
       g.src = d_img + img_off[b] + (hs - h0);
       g.n_rows = B.n_rows;
-      g.tile_begin = tiles;
+      g.tile_begin = cur.tiles;
       g.encoding = s.encoding;
       g.cw = s.code_width; g.vw = w; g.stride = s.stride; g.dict_entries = s.dict_entries;
       const bool pow2 = w == 4 || w == 8;
@@ -728,27 +740,95 @@ int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks, const qs_block_i
       if (s.encoding == QS_ENC_PLAIN) val_al = val_al && (reinterpret_cast<uintptr_t>(g.src) % w) == 0;
       if (s.encoding == QS_ENC_DICT) {
         const char *hd = static_cast<const char *>(s.dict);
-        if (!hd || s.dict_entries == 0 || hd < h0 || hd + static_cast<uint64_t>(s.dict_entries) * w > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: dictionary lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+        const uint64_t dbytes = static_cast<uint64_t>(s.dict_entries) * w;
+        if (!hd || s.dict_entries == 0 || hd < h0 || hd + dbytes > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: dictionary lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
         g.dict = d_img + img_off[b] + (hd - h0);
         val_al = val_al && (reinterpret_cast<uintptr_t>(g.dict) % w) == 0;
+        need.emplace_back(static_cast<uint64_t>(hd - h0), dbytes);
       }
       const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
       g.aligned = (val_al ? 1u : 0u) | (code_al ? 2u : 0u);
-      if (B.n_rows) { segs.push_back(g); tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows; }
+      if (B.n_rows) {
+        segs.push_back(g);
+        cur.tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows;
+        need.emplace_back(static_cast<uint64_t>(hs - h0), bytes);
+      }
+    }
+    if (rc != QSGPU_OK) break;
+    // byte ranges of this block that have to travel: sorted, neighbours closer than 4 KB merged
+    std::sort(need.begin(), need.end());
+    uint64_t block_copied = 0;
+    for (size_t i = 0; i < need.size();) {
+      uint64_t lo = need[i].first, hi = need[i].first + need[i].second;
+      size_t j = i + 1;
+      while (j < need.size() && need[j].first <= hi + 4096) { hi = std::max(hi, need[j].first + need[j].second); ++j; }
+      hi = std::min<uint64_t>(hi, B.bytes);
+      const Range r{h0 + lo, img_off[b] + lo, hi - lo};
+      if (ranges.size() > cur.range_begin && ranges.back().host + ranges.back().bytes == r.host &&
+          ranges.back().dev_off + ranges.back().bytes == r.dev_off)
+        ranges.back().bytes += r.bytes;          // contiguous with the previous block's tail (same slab)
+      else
+        ranges.push_back(r);
+      block_copied += hi - lo;
+      i = j;
     }
     row_base += B.n_rows;
+    chunk_bytes += block_copied;
+    if (chunk_bytes >= kStageChunkBytes || b + 1 == n_blocks) {
+      cur.seg_end = static_cast<uint32_t>(segs.size());
+      cur.range_end = ranges.size();
+      chunks.push_back(cur);
+      cur = Chunk{cur.seg_end, cur.seg_end, ranges.size(), ranges.size(), 0};
+      chunk_bytes = 0;
+    }
   }
+  cudaEvent_t ev = nullptr;
   if (rc == QSGPU_OK && !segs.empty()) {
     cudaError_t ce = dev_malloc(&d_segs, segs.size() * sizeof(StageSeg));
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(StageSeg), cudaMemcpyHostToDevice, d->stream);
-    if (ce == cudaSuccess) { ce = launch_decode_segments(d_segs, static_cast<uint32_t>(segs.size()), tiles, d->sm_count, d->stream); count_launch(); }
-    if (ce != cudaSuccess) rc = cuda_fail(ce, "qsgpu_stage_blocks decode");
+    // the image buffer may be a recycled block that earlier work on the library stream still reads
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev, d->stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(d->copy_stream, ev, 0);
+    std::vector<cudaEvent_t> done(chunks.size(), nullptr);
+    for (size_t c = 0; c < chunks.size() && ce == cudaSuccess; ++c) {
+      const Chunk &C = chunks[c];
+      for (size_t r = C.range_begin; r < C.range_end && ce == cudaSuccess; ++r)
+        ce = cudaMemcpyAsync(d_img + ranges[r].dev_off, ranges[r].host, ranges[r].bytes, cudaMemcpyHostToDevice, d->copy_stream);
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventRecord(done[c], d->copy_stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(d->stream, done[c], 0);
+      if (ce == cudaSuccess && C.seg_end > C.seg_begin) {
+        ce = launch_decode_segments(d_segs + C.seg_begin, C.seg_end - C.seg_begin, C.tiles, d->sm_count, d->stream);
+        count_launch();
+      }
+    }
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "qsgpu_stage_blocks");
+    cudaStreamSynchronize(d->copy_stream);
+    cudaStreamSynchronize(d->stream);     // host block memory and `segs` may be reused by the caller
+    for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
+    if (ev) cudaEventDestroy(ev);
   }
-  cudaStreamSynchronize(d->stream);     // host block memory and `segs` may be reused by the caller
   dev_free(d_img);
   dev_free(d_segs);
   if (rc != QSGPU_OK) return rc;
-  return qsgpu_relation_set_num_rows(rel, rel->host_rows + total_rows);
+  const uint64_t rows_after = std::max<uint64_t>(rel->host_rows, first_row + total_rows);
+  if (!append && rows_after == rel->host_rows) return QSGPU_OK;
+  return qsgpu_relation_set_num_rows(rel, rows_after);
+}
+
+int qsgpu_stage_blocks(qsgpu_relation_t rel, uint32_t n_blocks, const qs_block_image *blocks, uint32_t n_desc) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  return stage_impl(rel, rel->host_rows, true, n_blocks, blocks, n_desc);
+}
+
+int qsgpu_stage_columns(qsgpu_relation_t rel, uint64_t first_row, uint32_t n_blocks, const qs_block_image *blocks,
+                        uint32_t n_desc) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  if (first_row > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "qsgpu_stage_columns: first_row beyond the relation's rows"); return QSGPU_ERR_INVALID; }
+  return stage_impl(rel, first_row, false, n_blocks, blocks, n_desc);
 }
 
 /* ------------------------------------------------------------ LIP filters */
@@ -1229,6 +1309,21 @@ int qsgpu_agg_partial(qsgpu_agg_state_t state, void **d_states, void **d_keys, u
   *d_states = state->d_exp_states;
   *d_keys = state->d_exp_keys;
   *n_groups = n;
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_partial_layout(qsgpu_agg_state_t state, void **d_states, void **d_keys, uint64_t *rows,
+                             uint32_t *words_per_group, uint32_t *key_words) {
+  if (state->strategy != QS_AGG_SINGLE_STATE && state->strategy != QS_AGG_COMPACT_KEY) {
+    set_error(QSGPU_ERR_UNSUPPORTED, "only fixed-size states (single state, compact key) have a static partial layout");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  const AggDesc &A = state->A;
+  *d_states = A.states;
+  *d_keys = A.gid_keys;
+  *rows = A.partial_rows;
+  *words_per_group = A.words;
+  *key_words = A.key_words;
   return QSGPU_OK;
 }
 

@@ -97,6 +97,7 @@ struct Device {
   char *read_scratch = nullptr, *read_pinned = nullptr;
   std::shared_ptr<std::mutex> read_mu;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-to-device block images, overlapped with decoding (qsgpu_stage_blocks)
   int sm_count = 148;
   size_t smem_per_sm = 0, smem_per_block_optin = 0;
   uint32_t *d_error = nullptr;        // sticky device-side error word

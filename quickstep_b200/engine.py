@@ -36,6 +36,13 @@ def shutdown():
         _inited = False
 
 
+def stream_ptr(dev=0) -> int:
+    """cudaStream_t of the library's stream on `dev` (for torch.cuda.ExternalStream)."""
+    p = C.c_void_p()
+    A.check(A.load().qsgpu_stream(dev, C.byref(p)))
+    return p.value
+
+
 def launch_count() -> int:
     n = C.c_uint64(0)
     A.check(A.load().qsgpu_launch_count(C.byref(n)))
@@ -318,6 +325,13 @@ class AggState:
         ds, dk = C.c_void_p(), C.c_void_p()
         n, w, kw = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
         A.check(A.load().qsgpu_agg_partial(self.h, C.byref(ds), C.byref(dk), C.byref(n), C.byref(w), C.byref(kw)))
+        return ds.value, dk.value, n.value, w.value, kw.value
+
+    def partial_layout(self):
+        """-> (d_states, d_keys, rows, words_per_group, key_words) without synchronising."""
+        ds, dk = C.c_void_p(), C.c_void_p()
+        n, w, kw = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        A.check(A.load().qsgpu_agg_partial_layout(self.h, C.byref(ds), C.byref(dk), C.byref(n), C.byref(w), C.byref(kw)))
         return ds.value, dk.value, n.value, w.value, kw.value
 
     def merge_partial(self, d_states, d_keys, n_groups):

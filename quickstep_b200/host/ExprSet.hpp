@@ -68,6 +68,14 @@ class ExprSet {
     return e;
   }
   std::size_t size() const { return nodes_.size(); }
+  // Bit a set: some ATTRIBUTE node of join side `side` (0 = scanned / probe relation, 2 = build relation)
+  // names attribute a.  What an operator asks the device cache to hold before its work orders run.
+  std::uint64_t referencedAttributes(int side = 0) const {
+    std::uint64_t m = 0;
+    for (const qs_node &x : nodes_)
+      if (x.kind == QS_N_ATTRIBUTE && x.b == side && x.a >= 0 && x.a < 64) m |= 1ull << x.a;
+    return m;
+  }
 
  private:
   int add(const qs_node &x) { nodes_.push_back(x); return static_cast<int>(nodes_.size()) - 1; }

@@ -4,12 +4,12 @@ namespace quickstep {
 
 std::uint64_t FLAGS_gpu_rows_per_workorder = 0;
 
-std::vector<DeviceExtent> InputFeed::take(StorageManager *sm) {
+std::vector<DeviceExtent> InputFeed::take(StorageManager *sm, std::uint64_t needed_attrs) {
   std::vector<DeviceExtent> out;
   if (stored_) {
     if (started_) return out;
     started_ = true;
-    sm->deviceRelation(relation_);                 // K0: stage whatever is not resident yet (one batch)
+    sm->deviceRelation(relation_, needed_attrs);   // K0: stage whatever is not resident yet (one batch)
     DeviceExtent cur;
     for (block_id b : relation_.getBlocksSnapshot()) {
       const DeviceExtent e = sm->blockExtent(b);
@@ -49,6 +49,13 @@ void addScalars(Lowered *L, const QueryContext::ScalarGroup *g) {
   for (int r : g->roots) L->roots.push_back(r + off);
 }
 
+std::uint64_t attrsOf(const QueryContext::Predicate *p) { return p ? p->exprs.referencedAttributes(0) : 0; }
+std::uint64_t attrsOf(const std::vector<qs_lip_ref> &refs) {
+  std::uint64_t m = 0;
+  for (const qs_lip_ref &r : refs) if (r.attr < 64) m |= 1ull << r.attr;
+  return m;
+}
+
 qs_scan makeScan(const DeviceExtent &in, const qs_expr_set *es, int predicate_root, const std::vector<qs_lip_ref> &lip_probe) {
   qs_scan s{};
   s.input = in.relation;
@@ -67,7 +74,11 @@ qs_scan makeScan(const DeviceExtent &in, const qs_expr_set *es, int predicate_ro
 bool SelectOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                       StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   InsertDestination *dest = query_context->getInsertDestination(output_destination_index_);
-  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+  std::uint64_t needed = attrsOf(query_context->getPredicate(predicate_index_)) |
+                         attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe));
+  if (simple_projection_) { for (attribute_id a : simple_selection_) needed |= 1ull << a; }
+  else needed |= query_context->getScalarGroup(selection_index_).exprs.referencedAttributes(0);
+  for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new SelectWorkOrder(query_id_, feed_.relation(), e, query_context->getPredicate(predicate_index_),
                             simple_projection_ ? nullptr : &query_context->getScalarGroup(selection_index_),
@@ -95,7 +106,10 @@ void SelectWorkOrder::execute() {
 // ---------------------------------------------------------- BuildLIPFilter
 bool BuildLIPFilterOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                               StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
-  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+  const std::uint64_t needed = attrsOf(query_context->getPredicate(build_side_predicate_index_)) |
+                               attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)) |
+                               attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kBuild));
+  for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new BuildLIPFilterWorkOrder(query_id_, e, query_context->getPredicate(build_side_predicate_index_),
                                     query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe),
@@ -176,7 +190,9 @@ void HashJoinWorkOrder::execute() {
 // ------------------------------------------------------------- Aggregation
 bool AggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                            StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
-  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+  const std::uint64_t needed = query_context->getAggregationSpec(aggr_state_index_).exprs.referencedAttributes(0) |
+                               attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe));
+  for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new AggregationWorkOrder(query_id_, e, query_context->getAggregationState(aggr_state_index_),
                                  query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)),

@@ -37,7 +37,8 @@ class InputFeed {
  public:
   InputFeed(const CatalogRelation &rel, bool stored) : relation_(rel), stored_(stored) {}
   void feed(block_id b) { pending_.push_back(b); }
-  std::vector<DeviceExtent> take(StorageManager *sm);
+  // needed_attrs: the attributes of the input relation the operator's work orders will read
+  std::vector<DeviceExtent> take(StorageManager *sm, std::uint64_t needed_attrs = ~0ull);
   // true once no further extent can appear
   bool exhausted(bool done_feeding) const { return stored_ ? started_ : (done_feeding && pending_.empty()); }
   const CatalogRelation &relation() const { return relation_; }

@@ -245,40 +245,53 @@ std::uint64_t StorageManager::hostBytes(const CatalogRelation &rel) const {
   return n;
 }
 
-qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel) {
+qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std::uint64_t needed_attrs) {
   std::lock_guard<std::mutex> lk(mu_);
   const std::vector<block_id> ids = rel.getBlocksSnapshot();
-  Resident &R = resident_[rel.getID()];
-  if (R.handle && R.n_blocks_staged == ids.size()) return R.handle;
-  std::uint64_t rows = 0;
-  for (block_id id : ids) rows += static_cast<std::uint64_t>(blocks_.at(id).num_tuples);
   const std::vector<qs_attr> schema = rel.schema();
-  if (!R.handle) {
+  QS_CHECK(schema.size() <= 64);
+  const std::uint64_t all = schema.size() == 64 ? ~0ull : ((1ull << schema.size()) - 1);
+  needed_attrs &= all;
+  Resident &R = resident_[rel.getID()];
+  const bool rebuild = !R.handle || R.n_blocks_staged != ids.size();
+  if (!rebuild && (needed_attrs & ~R.staged_attrs) == 0) return R.handle;
+  if (rebuild) {
+    // first use, or the relation grew since the image was built (blocks are append-only): (re)build it
+    if (R.handle) QS_CHECK_GPU(qsgpu_relation_destroy(R.handle));
+    std::uint64_t rows = 0;
+    for (block_id id : ids) rows += static_cast<std::uint64_t>(blocks_.at(id).num_tuples);
     QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
                                        std::max<std::uint64_t>(rows, 1), &R.handle));
     R.n_blocks_staged = 0;
     R.rows = 0;
-  } else {
-    // the relation grew since the image was built (blocks are append-only): rebuild it
-    QS_CHECK_GPU(qsgpu_relation_destroy(R.handle));
-    QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
-                                       std::max<std::uint64_t>(rows, 1), &R.handle));
-    R.n_blocks_staged = 0;
-    R.rows = 0;
+    R.staged_attrs = 0;
+    for (block_id id : ids) {
+      const StorageBlock &B = blocks_.at(id);
+      block_first_row_[B.id] = {rel.getID(), R.rows};
+      R.rows += static_cast<std::uint64_t>(B.num_tuples);
+    }
   }
-  std::vector<qs_block_image> images;
-  for (std::size_t i = R.n_blocks_staged; i < ids.size(); ++i) {
+  const std::uint64_t to_stage = needed_attrs & ~R.staged_attrs;
+  std::vector<std::vector<qs_stage_desc>> descs(ids.size());
+  std::vector<qs_block_image> images(ids.size());
+  for (std::size_t i = 0; i < ids.size(); ++i) {
     const StorageBlock &B = blocks_.at(ids[i]);
-    block_first_row_[B.id] = {rel.getID(), R.rows};
-    R.rows += static_cast<std::uint64_t>(B.num_tuples);
-    qs_block_image im{};
-    im.host = B.memory; im.bytes = B.size; im.n_rows = static_cast<std::uint64_t>(B.num_tuples); im.descs = B.stripes.data();
-    images.push_back(im);
+    descs[i] = B.stripes;
+    for (std::size_t a = 0; a < descs[i].size(); ++a)
+      if (!((to_stage >> a) & 1)) descs[i][a].encoding = QS_ENC_SKIP;
+    images[i].host = B.memory; images[i].bytes = B.size; images[i].n_rows = static_cast<std::uint64_t>(B.num_tuples);
+    images[i].descs = descs[i].data();
   }
-  if (!images.empty())
-    QS_CHECK_GPU(qsgpu_stage_blocks(R.handle, static_cast<std::uint32_t>(images.size()), images.data(),
-                                    static_cast<std::uint32_t>(schema.size())));
+  if (!images.empty()) {
+    if (rebuild)
+      QS_CHECK_GPU(qsgpu_stage_blocks(R.handle, static_cast<std::uint32_t>(images.size()), images.data(),
+                                      static_cast<std::uint32_t>(schema.size())));
+    else
+      QS_CHECK_GPU(qsgpu_stage_columns(R.handle, 0, static_cast<std::uint32_t>(images.size()), images.data(),
+                                       static_cast<std::uint32_t>(schema.size())));
+  }
   R.n_blocks_staged = ids.size();
+  R.staged_attrs |= to_stage;
   return R.handle;
 }
 

@@ -64,8 +64,11 @@ class StorageManager {
   const StorageBlock &getBlock(block_id id) const;
   std::uint64_t hostBytes(const CatalogRelation &rel) const;      // bytes of all block images
 
-  // HBM image of every block of a stored relation, in block-list order.
-  qsgpu_relation_t deviceRelation(const CatalogRelation &rel);
+  // HBM image of the blocks of a stored relation, in block-list order.  The device cache is keyed by
+  // (block, attribute): only the attributes in `needed_attrs` (bit a = attribute a; default all) are
+  // guaranteed resident on return; attributes staged by earlier calls stay, missing ones are staged now
+  // (qsgpu_stage_blocks / qsgpu_stage_columns with QS_ENC_SKIP for the rest).
+  qsgpu_relation_t deviceRelation(const CatalogRelation &rel, std::uint64_t needed_attrs = ~0ull);
   DeviceExtent blockExtent(block_id id);                           // rows of one block inside it
   void evict(const CatalogRelation &rel);                          // drop the HBM image
 
@@ -78,7 +81,12 @@ class StorageManager {
 
  private:
   struct Slab { char *base = nullptr; std::size_t bytes = 0; };
-  struct Resident { qsgpu_relation_t handle = nullptr; std::size_t n_blocks_staged = 0; std::uint64_t rows = 0; };
+  struct Resident {
+    qsgpu_relation_t handle = nullptr;
+    std::size_t n_blocks_staged = 0;
+    std::uint64_t rows = 0;
+    std::uint64_t staged_attrs = 0;      // bit a: attribute a of every staged block is in HBM
+  };
   int device_;
   mutable std::mutex mu_;
   block_id next_block_ = 1;
