@@ -673,6 +673,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
 // are copied (attributes marked QS_ENC_SKIP stay on the host: column pruning), adjacent ranges -- also
 // across blocks that are contiguous in host memory, e.g. a buffer-pool slab -- merged into one copy.
 static constexpr uint64_t kStageChunkBytes = 64ull << 20;
+static constexpr uint64_t kStageMergeGap = 192ull << 10;
 
 static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint32_t n_blocks,
                       const qs_block_image *blocks, uint32_t n_desc) {
@@ -761,14 +762,23 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
     for (size_t i = 0; i < need.size();) {
       uint64_t lo = need[i].first, hi = need[i].first + need[i].second;
       size_t j = i + 1;
-      while (j < need.size() && need[j].first <= hi + 4096) { hi = std::max(hi, need[j].first + need[j].second); ++j; }
+      while (j < need.size() && need[j].first <= hi + kStageMergeGap) { hi = std::max(hi, need[j].first + need[j].second); ++j; }
       hi = std::min<uint64_t>(hi, B.bytes);
       const Range r{h0 + lo, img_off[b] + lo, hi - lo};
-      if (ranges.size() > cur.range_begin && ranges.back().host + ranges.back().bytes == r.host &&
-          ranges.back().dev_off + ranges.back().bytes == r.dev_off)
-        ranges.back().bytes += r.bytes;          // contiguous with the previous block's tail (same slab)
-      else
-        ranges.push_back(r);
+      // Same slab, same host-to-device displacement, and a hole smaller than kStageMergeGap: extend the
+      // previous copy over the hole.  A DMA descriptor costs ~3 us, i.e. ~150 KB of PCIe time, so skipping
+      // anything smaller than that (a narrow stripe, a dictionary) is slower than copying it.
+      bool merged = false;
+      if (ranges.size() > cur.range_begin) {
+        Range &p = ranges.back();
+        const char *p_end = p.host + p.bytes;
+        if (r.host >= p_end && static_cast<uint64_t>(r.host - p_end) <= kStageMergeGap &&
+            static_cast<uint64_t>(r.host - p.host) == r.dev_off - p.dev_off) {
+          p.bytes = static_cast<uint64_t>(r.host - p.host) + r.bytes;
+          merged = true;
+        }
+      }
+      if (!merged) ranges.push_back(r);
       block_copied += hi - lo;
       i = j;
     }
