@@ -146,6 +146,10 @@ int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs,
 int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
                         uint64_t n_rows, void *host_out);
 
+/* NULL mask of rows [row_begin, row_begin+n_rows): bit j of word i = attribute j of row row_begin+i is NULL
+ * (its stored bytes are zero).  Only the output of a LEFT OUTER join can hold NULLs; all zeros otherwise. */
+int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows,
+                              uint64_t *host_out);
 /* All attributes at once: host_out[a] receives rows [row_begin, row_begin+n_rows) of attribute a; the
  * copies are queued back to back and waited for once (result relations are a handful of rows wide and
  * tall: one synchronisation instead of one per column). */
@@ -377,10 +381,12 @@ int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan,
                      const qs_lip_ref *lip_build);
 int qsgpu_join_num_entries(qsgpu_join_table_t table, uint64_t *n);
 /*
- * HashInnerJoinWorkOrder / Semi / Anti (HashJoinOperator.cpp:450-987): LIP
+ * HashInnerJoinWorkOrder / Semi / Anti / Outer (HashJoinOperator.cpp:450-1099): LIP
  * probe -> hash probe -> residual predicate over both sides -> projection.
  * In `exprs`, attribute nodes with b == 2 refer to the build relation.
  * residual_root == -1: none.  Output rows are appended to `output`.
+ * QS_JOIN_LEFT_OUTER (no residual predicate, as in the reference): probe rows without a match are emitted
+ * too, their build-side projections NULL (zero bytes + the row's bit in qsgpu_relation_read_nulls).
  */
 int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe,
                      uint32_t probe_key_attr, uint32_t join_type,
@@ -429,12 +435,12 @@ int qsgpu_last_kernel_ms(uint32_t family, float *ms);
  * `which` (0..QSGPU_JIT_SELFCHECK_CASES-1: Q6-style single-state aggregate,
  * Q1-style compact-key group-by, select with LIP probes, BuildLIPFilter, join
  * build, inner probe with residual, anti probe, hash group-by, dense group-by,
- * dense join build, dense inner probe)
+ * dense join build, dense inner probe, LEFT OUTER probe)
  * WITHOUT a device -- the "does every kernel family still compile" check of
  * build() and the CPU test suite.  The generated CUDA source and the NVRTC log
  * are copied into the optional buffers.
  */
-#define QSGPU_JIT_SELFCHECK_CASES 11
+#define QSGPU_JIT_SELFCHECK_CASES 12
 int qsgpu_jit_selfcheck(uint32_t which, char *source_out, size_t source_bytes,
                         char *log_out, size_t log_bytes);
 /* NVRTC compilations / disk-cache hits / in-memory hits since load. */

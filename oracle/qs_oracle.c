@@ -735,11 +735,27 @@ void qso_agg_result_free(qso_agg_result *r) {
 }
 
 /* --------------------------------------------------------------- hash join */
-int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t build_predicate_root,
+/* Does the scalar rooted at `i` read a build-side attribute?  (is_selection_on_build of
+ * HashOuterJoinWorkOrder, relational_operators/HashJoinOperator.hpp:724: such output columns are NULL for
+ * probe tuples without a match.) */
+static int refs_build_side(const qs_expr_set *ex, int32_t i) {
+  if (i < 0 || (uint32_t)i >= ex->n_nodes) return 0;
+  const qs_node *n = &ex->nodes[i];
+  switch (n->kind) {
+    case QS_N_ATTRIBUTE: return n->b == 2;
+    case QS_N_UNARY: case QS_N_SHARED: return refs_build_side(ex, n->a);
+    case QS_N_BINARY: return refs_build_side(ex, n->a) || refs_build_side(ex, n->b);
+    default: return 0;
+  }
+}
+
+static int64_t hash_join_impl(const qs_expr_set *ex, const qso_table *build, int32_t build_predicate_root,
                       uint32_t build_key_attr, const qso_table *probe, int32_t probe_predicate_root,
                       uint32_t probe_key_attr, uint32_t n_probe_lip, const qso_lip_ref *probe_lip,
                       uint32_t join_type, int32_t residual_root, uint32_t n_project,
-                      const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity) {
+                      const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity,
+                      uint64_t *out_nulls) {
+  if (join_type == QS_JOIN_LEFT_OUTER && residual_root >= 0) return -1;   /* DCHECK in the reference (HashJoinOperator.hpp:139-141) */
   /* BuildHashWorkOrder: predicate, then putValueAccessor(key -> tuple reference). */
   uint64_t *bbm = calloc(bm_words(build->n_rows) + 1, 8);
   {
@@ -805,7 +821,7 @@ int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t bui
   else for (uint64_t i = 0; i < n_pairs; ++i) bm_set(ok, i);
   int64_t n_out = 0;
   int error = pc.error;
-  if (!error && join_type == QS_JOIN_INNER) {
+  if (!error && (join_type == QS_JOIN_INNER || join_type == QS_JOIN_LEFT_OUTER)) {
     for (uint32_t p = 0; p < n_project && !error; ++p) {
       vec v = eval_scalar(&pc, project_roots[p]);
       if (pc.error) { error = 1; vec_free(&v); break; }
@@ -819,6 +835,46 @@ int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t bui
       vec_free(&v);
     }
     if (n_project == 0) for (uint64_t i = 0; i < n_pairs; ++i) n_out += bm_get(ok, i);
+    if (out_nulls) for (int64_t o = 0; o < n_out && (uint64_t)o < out_capacity; ++o) out_nulls[o] = 0;
+    if (!error && join_type == QS_JOIN_LEFT_OUTER) {
+      /* HashOuterJoinWorkOrder::execute second half (HashJoinOperator.cpp:1060-1099): probe tuples that passed
+       * the filters and found no match are emitted with the probe-side selection evaluated and every
+       * build-side selection NULL. */
+      uint64_t *matched = calloc(bm_words(probe->n_rows) + 1, 8);
+      for (uint64_t i = 0; i < n_pairs; ++i) bm_set(matched, pp[i]);
+      uint64_t n_un = 0;
+      for (uint64_t r = 0; r < probe->n_rows; ++r) n_un += bm_get(pbm, r) && !bm_get(matched, r);
+      qso_column *up = malloc(sizeof(qso_column) * (probe->n_cols + 1)), *ub = malloc(sizeof(qso_column) * (build->n_cols + 1));
+      for (uint32_t c = 0; c < probe->n_cols; ++c) {
+        up[c] = probe->cols[c];
+        char *d = malloc((n_un ? n_un : 1) * up[c].width);
+        uint64_t o = 0;
+        for (uint64_t r = 0; r < probe->n_rows; ++r)
+          if (bm_get(pbm, r) && !bm_get(matched, r)) { memcpy(d + o * up[c].width, (const char *)probe->cols[c].data + r * up[c].width, up[c].width); ++o; }
+        up[c].data = d;
+      }
+      for (uint32_t c = 0; c < build->n_cols; ++c) { ub[c] = build->cols[c]; ub[c].data = calloc(n_un ? n_un : 1, ub[c].width); }
+      qso_table tup = {up, probe->n_cols, n_un}, tub = {ub, build->n_cols, n_un};
+      blockctx uc = {ex, &tup, &tub, 0, n_un, 0};
+      uint64_t null_bits = 0;
+      for (uint32_t p = 0; p < n_project; ++p) if (refs_build_side(ex, project_roots[p])) null_bits |= 1ull << p;
+      for (uint32_t p = 0; p < n_project && !error; ++p) {
+        vec v = eval_scalar(&uc, project_roots[p]);
+        if (uc.error) { error = 1; vec_free(&v); break; }
+        for (uint64_t i = 0; i < n_un; ++i) {
+          const uint64_t o = (uint64_t)n_out + i;
+          if (o >= out_capacity) continue;
+          if (null_bits >> p & 1) memset((char *)out_cols[p] + o * v.width, 0, v.width);
+          else memcpy((char *)out_cols[p] + o * v.width, (const char *)v.data + (v.is_const ? 0 : i * v.width), v.width);
+        }
+        vec_free(&v);
+      }
+      if (out_nulls) for (uint64_t i = 0; i < n_un; ++i) if ((uint64_t)n_out + i < out_capacity) out_nulls[(uint64_t)n_out + i] = null_bits;
+      n_out += (int64_t)n_un;
+      for (uint32_t c = 0; c < probe->n_cols; ++c) free((void *)up[c].data);
+      for (uint32_t c = 0; c < build->n_cols; ++c) free((void *)ub[c].data);
+      free(up); free(ub); free(matched);
+    }
   } else if (!error) {
     /* semi / anti: existence bitmap over probe rows (HashJoinOperator.cpp:673-987) */
     uint64_t *matched = calloc(bm_words(probe->n_rows) + 1, 8);
@@ -849,6 +905,27 @@ int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t bui
   for (uint32_t c = 0; c < build->n_cols; ++c) free((void *)gb[c].data);
   free(gp); free(gb); free(ok); free(pp); free(pb); free(pbm);
   return error ? -1 : n_out;
+}
+
+int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t build_predicate_root,
+                      uint32_t build_key_attr, const qso_table *probe, int32_t probe_predicate_root,
+                      uint32_t probe_key_attr, uint32_t n_probe_lip, const qso_lip_ref *probe_lip,
+                      uint32_t join_type, int32_t residual_root, uint32_t n_project,
+                      const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity) {
+  return hash_join_impl(ex, build, build_predicate_root, build_key_attr, probe, probe_predicate_root, probe_key_attr,
+                        n_probe_lip, probe_lip, join_type, residual_root, n_project, project_roots, out_cols,
+                        out_capacity, NULL);
+}
+
+int64_t qso_hash_join_nulls(const qs_expr_set *ex, const qso_table *build, int32_t build_predicate_root,
+                            uint32_t build_key_attr, const qso_table *probe, int32_t probe_predicate_root,
+                            uint32_t probe_key_attr, uint32_t n_probe_lip, const qso_lip_ref *probe_lip,
+                            uint32_t join_type, int32_t residual_root, uint32_t n_project,
+                            const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity,
+                            uint64_t *out_nulls) {
+  return hash_join_impl(ex, build, build_predicate_root, build_key_attr, probe, probe_predicate_root, probe_key_attr,
+                        n_probe_lip, probe_lip, join_type, residual_root, n_project, project_roots, out_cols,
+                        out_capacity, out_nulls);
 }
 
 /* ------------------------------------------------------------------- top-k */

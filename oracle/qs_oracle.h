@@ -113,6 +113,16 @@ int64_t qso_hash_join(const qs_expr_set *ex, const qso_table *build, int32_t bui
                       uint32_t join_type, int32_t residual_root, uint32_t n_project,
                       const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity);
 
+/* Same, plus the NULL mask of every output row (bit p = projected column p is NULL): what a LEFT OUTER
+ * join (HashOuterJoinWorkOrder, relational_operators/HashJoinOperator.cpp:989-1099) produces for probe
+ * tuples without a match -- build-side selections are NULL, stored as zero bytes. */
+int64_t qso_hash_join_nulls(const qs_expr_set *ex, const qso_table *build, int32_t build_predicate_root,
+                            uint32_t build_key_attr, const qso_table *probe, int32_t probe_predicate_root,
+                            uint32_t probe_key_attr, uint32_t n_probe_lip, const qso_lip_ref *probe_lip,
+                            uint32_t join_type, int32_t residual_root, uint32_t n_project,
+                            const int32_t *project_roots, void *const *out_cols, uint64_t out_capacity,
+                            uint64_t *out_nulls);
+
 /* Sort + LIMIT (SortRunGeneration/SortMergeRun): returns the row ids of the
  * first `limit` rows in order. */
 int64_t qso_topk(const qso_table *t, uint32_t n_keys, const qs_sort_key *keys, uint64_t limit, uint64_t *row_ids);

@@ -85,6 +85,8 @@ def load():
                                 C.POINTER(qso_table), C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(qso_lip_ref),
                                 C.c_uint32, C.c_int32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
                                 C.c_uint64]
+    L.qso_hash_join_nulls.restype = C.c_int64
+    L.qso_hash_join_nulls.argtypes = L.qso_hash_join.argtypes + [C.POINTER(C.c_uint64)]
     L.qso_topk.restype = C.c_int64
     L.qso_topk.argtypes = [C.POINTER(qso_table), C.c_uint32, C.POINTER(A.qs_sort_key), C.c_uint64,
                            C.POINTER(C.c_uint64)]
@@ -242,12 +244,15 @@ def hash_join(es, build, build_pred, build_key_attr, probe, probe_pred, probe_ke
     outs = [np.zeros(max(1, capacity), dtype=np_dtype(t, w)) for (t, w) in out_types]
     ptrs = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
     np_, pa, _k = _lip_refs(probe_refs)
-    n = L.qso_hash_join(es.ptr(), cb.ptr(), build_pred, build_key_attr, cp.ptr(), probe_pred, probe_key_attr,
-                        np_, pa, join_type, residual_root, len(project_roots), _i32arr(project_roots), ptrs, capacity)
+    nulls = np.zeros(max(1, capacity), dtype=np.uint64)
+    n = L.qso_hash_join_nulls(es.ptr(), cb.ptr(), build_pred, build_key_attr, cp.ptr(), probe_pred, probe_key_attr,
+                              np_, pa, join_type, residual_root, len(project_roots), _i32arr(project_roots), ptrs,
+                              capacity, nulls.ctypes.data_as(C.POINTER(C.c_uint64)))
     if n < 0:
         raise RuntimeError("oracle: hash_join failed")
     if n > capacity:
         raise RuntimeError(f"oracle: join output {n} exceeds capacity {capacity}")
+    hash_join.last_nulls = nulls[:n]          # NULL mask of the rows just returned (LEFT OUTER joins)
     return [o[:n] for o in outs]
 
 

@@ -122,6 +122,7 @@ SIGNATURES = {
     "qsgpu_relation_column": (C.c_int, [_VP, C.c_uint32, _VPP]),
     "qsgpu_relation_wrap": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), _VPP, C.c_uint64, _VPP]),
     "qsgpu_relation_read": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, _VP]),
+    "qsgpu_relation_read_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
     "qsgpu_stage_blocks": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
@@ -155,7 +156,7 @@ SIGNATURES = {
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }
-JIT_SELFCHECK_CASES = 11
+JIT_SELFCHECK_CASES = 12
 
 
 class QsGpuError(RuntimeError):

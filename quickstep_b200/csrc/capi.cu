@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 
 #include "qs_host.h"
@@ -527,6 +528,7 @@ int qsgpu_relation_destroy(qsgpu_relation_t rel) {
   // them as soon as this returns
   if (d && !rel->owns_memory) cudaStreamSynchronize(d->stream);
   if (rel->owns_memory) for (char *p : rel->cols) dev_free(p);
+  dev_free(rel->d_nulls);
   dev_free(rel->d_rows);
   delete rel;
   return QSGPU_OK;
@@ -567,6 +569,14 @@ int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
   QS_CUDA(cudaMemcpyAsync(host_out, rel->cols[attr] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
   QS_CUDA(cudaStreamSynchronize(d->stream));
   return QSGPU_OK;
+}
+
+int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, uint64_t *host_out) {
+  int st = sync_rows(rel);
+  if (st) return st;
+  if (row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
+  if (!rel->d_nulls) { std::memset(host_out, 0, n_rows * 8); return QSGPU_OK; }
+  return qsgpu_memcpy_d2h(rel->dev, host_out, rel->d_nulls + row_begin, n_rows * 8);
 }
 
 int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, void *const *host_out) {
@@ -1533,8 +1543,12 @@ int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t pr
   qsgpu_relation *rel = probe->input;
   Device *d = device(table->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
-  if (join_type == QS_JOIN_LEFT_OUTER) { set_error(QSGPU_ERR_UNSUPPORTED, "outer joins need NULL-able output columns (not staged on the device yet)"); return QSGPU_ERR_UNSUPPORTED; }
-  if (join_type > QS_JOIN_LEFT_ANTI) { set_error(QSGPU_ERR_INVALID, "unknown join type"); return QSGPU_ERR_INVALID; }
+  if (join_type > QS_JOIN_LEFT_OUTER) { set_error(QSGPU_ERR_INVALID, "unknown join type"); return QSGPU_ERR_INVALID; }
+  if (join_type == QS_JOIN_LEFT_OUTER && residual_root >= 0) {
+    // DCHECK in the reference too (relational_operators/HashJoinOperator.hpp:139-141)
+    set_error(QSGPU_ERR_INVALID, "a LEFT OUTER join takes no residual predicate");
+    return QSGPU_ERR_INVALID;
+  }
   if (rel->dev != table->dev || output->dev != table->dev || probe_key_attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "bad probe arguments"); return QSGPU_ERR_INVALID; }
   const uint8_t klt = vtype_of(rel->attrs[probe_key_attr].type);
   if (klt != V_I32 && klt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "probe key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
@@ -1549,7 +1563,26 @@ int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t pr
   const size_t builds_before = L.build_attrs.size();
   st = lower_projection(L, n_project, project_roots, output, &K);
   if (st) return st;
-  if (join_type != QS_JOIN_INNER && L.build_attrs.size() != builds_before) { set_error(QSGPU_ERR_INVALID, "semi/anti joins cannot project build-side attributes"); return QSGPU_ERR_INVALID; }
+  if (join_type != QS_JOIN_INNER && join_type != QS_JOIN_LEFT_OUTER && L.build_attrs.size() != builds_before) { set_error(QSGPU_ERR_INVALID, "semi/anti joins cannot project build-side attributes"); return QSGPU_ERR_INVALID; }
+  if (join_type == QS_JOIN_LEFT_OUTER) {
+    // is_selection_on_build: the projected scalars that read the build side are NULL for unmatched probe rows
+    std::function<bool(int32_t)> on_build = [&](int32_t i) -> bool {
+      const qs_node *n = L.node(i);
+      if (!n) return false;
+      switch (n->kind) {
+        case QS_N_ATTRIBUTE: return n->b == 2;
+        case QS_N_UNARY: case QS_N_SHARED: return on_build(n->a);
+        case QS_N_BINARY: return on_build(n->a) || on_build(n->b);
+        default: return false;
+      }
+    };
+    for (uint32_t j = 0; j < n_project; ++j) if (on_build(project_roots[j])) K.null_bits |= 1ull << j;
+    if (!output->d_nulls && !t_sc) {
+      QS_CUDA(dev_malloc(&output->d_nulls, std::max<uint64_t>(output->capacity, 1) * 8));
+      QS_CUDA(cudaMemsetAsync(output->d_nulls, 0, std::max<uint64_t>(output->capacity, 1) * 8, d->stream));
+    }
+    K.null_out = output->d_nulls;
+  }
   JoinDesc J = table->J;
   J.join_type = static_cast<uint8_t>(join_type);
   J.key_col = static_cast<uint16_t>(L.stage_attr(probe_key_attr));

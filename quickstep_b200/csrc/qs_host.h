@@ -21,6 +21,9 @@ struct qsgpu_relation {
   // Row count: authoritative copy lives on the device (kernels append with
   // atomics); host_rows is valid only while !dirty.
   unsigned long long *d_rows = nullptr;
+  // Per-row NULL mask (bit j = attribute j is NULL), allocated only for relations that can hold NULLs
+  // (the output of a LEFT OUTER join); absent = no NULLs.
+  unsigned long long *d_nulls = nullptr;
   uint64_t host_rows = 0;
   bool dirty = false;
 };

@@ -671,8 +671,13 @@ struct JoinSink : SinkBase {
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       if (idx[r] == ~0ull) continue;
-      if constexpr (w == 4) *reinterpret_cast<uint32_t *>(K->out[JJ] + idx[r] * 4) = static_cast<uint32_t>(acc[r]);
-      else *reinterpret_cast<uint64_t *>(K->out[JJ] + idx[r] * 8) = acc[r];
+      uint64_t v = acc[r];
+      if constexpr (Q::j_type == QS_JOIN_LEFT_OUTER) {
+        // an expression over the build side of a probe row without a match is NULL: zero bytes
+        if (brow[r] == kEmptyRow && ((K->null_bits >> JJ) & 1ull)) v = 0;
+      }
+      if constexpr (w == 4) *reinterpret_cast<uint32_t *>(K->out[JJ] + idx[r] * 4) = static_cast<uint32_t>(v);
+      else *reinterpret_cast<uint64_t *>(K->out[JJ] + idx[r] * 8) = v;
     }
   }
   template <int JJ, int COL, int W>
@@ -687,7 +692,15 @@ struct JoinSink : SinkBase {
   __device__ __forceinline__ void emit_raw_build() {
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      if (idx[r] == ~0ull || brow[r] == kEmptyRow) continue;
+      if (idx[r] == ~0ull) continue;
+      if (brow[r] == kEmptyRow) {
+        // probe row without a match (only a LEFT OUTER join emits such rows): the value is NULL, stored as zeros
+        if constexpr (Q::j_type == QS_JOIN_LEFT_OUTER) {
+#pragma unroll
+          for (uint32_t b = 0; b < W; ++b) K->out[JJ][idx[r] * W + b] = 0;
+        }
+        continue;
+      }
       copy_value<W>(K->out[JJ] + idx[r] * W, J->build_cols[COL].ptr + brow[r] * W);
     }
   }
@@ -710,7 +723,9 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
   VmRegs regs;
   const uint64_t mask = J.cap - 1;
   constexpr bool has_residual = Q::n_mid > Q::n_pred;
-  constexpr bool inner = Q::j_type == QS_JOIN_INNER;
+  constexpr bool outer = Q::j_type == QS_JOIN_LEFT_OUTER;
+  // a LEFT OUTER join emits its matches exactly like an inner join, then the probe rows that never matched
+  constexpr bool inner = Q::j_type == QS_JOIN_INNER || outer;
 
   scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
     bool valid[kRows];
@@ -786,6 +801,13 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       if constexpr (inner) {
         cta_compact(ok, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
         vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+        if constexpr (outer) {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            matched[r] |= ok[r];
+            if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = 0ull;
+          }
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
@@ -793,7 +815,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         }
       }
     }
-    if constexpr (!inner) {
+    if constexpr (!inner || outer) {
       bool flag[kRows];
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
@@ -802,6 +824,11 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       }
       cta_compact(flag, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
       vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+      if constexpr (outer) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = K.null_bits;
+      }
     }
   });
 }

@@ -19,6 +19,10 @@ struct SinkDesc {
   uint16_t lip_build_col[kMaxLip];  // staged column slot of the build attribute
   uint8_t lip_build_ltype[kMaxLip];
   uint32_t *error_flag;
+  // LEFT OUTER join: per-output-row NULL mask (bit j = projected column j is NULL) and the mask of the
+  // columns whose scalar reads the build side (NULL for probe rows without a match)
+  unsigned long long *null_out;
+  uint64_t null_bits;
 };
 
 struct __align__(16) JoinSlot {                   // 16 bytes, one vector load per probe step

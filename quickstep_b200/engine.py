@@ -194,6 +194,15 @@ class Relation:
             A.check(A.load().qsgpu_relation_read(self.h, attr, lo, n, out.ctypes.data))
         return out[:n]
 
+    def read_nulls(self, lo=0, n=None) -> np.ndarray:
+        """NULL mask per row (bit j = column j is NULL); all zeros unless a LEFT OUTER join wrote the relation."""
+        if n is None:
+            n = self.n_rows - lo
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        if n:
+            A.check(A.load().qsgpu_relation_read_nulls(self.h, lo, n, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out[:n]
+
     def read_all(self, lo=0, n=None):
         """Every column of rows [lo, lo+n) with one synchronisation (qsgpu_relation_read_all)."""
         if n is None:

@@ -112,7 +112,9 @@ class OracleBackend:
         assert bes_pred == -1 or build_es is es
         cols = O.hash_join(es, build, bes_pred, build_key, probe, probe_pred, probe_key, probe_lips, join_type,
                            residual, roots, out_schema, capacity)
-        return HostTable("join", [Column(f"c{i}", t, cols[i], w) for i, (t, w) in enumerate(out_schema)])
+        out = HostTable("join", [Column(f"c{i}", t, cols[i], w) for i, (t, w) in enumerate(out_schema)])
+        out.nulls = np.array(O.hash_join.last_nulls, dtype=np.uint64)     # bit j of row i: column j is NULL
+        return out
 
     def topk(self, rel, keys, limit) -> HostTable:
         ids = O.topk(rel, keys, limit).astype(np.int64)
@@ -189,7 +191,9 @@ class GpuBackend:
         try:
             jt.build(build, build_es if bes_pred >= 0 else None, bes_pred, build_key)
             jt.probe(probe, es, probe_pred, probe_key, join_type, residual, roots, out, probe_lips)
-            return out.to_host("join")
+            host = out.to_host("join")
+            host.nulls = out.read_nulls()
+            return host
         finally:
             out.destroy()
             jt.destroy()

@@ -107,6 +107,43 @@ def case_partition_test_join(B):
     return sorted((int(out.columns[0].data[i]), bytes(out.columns[1].data[i])) for i in range(out.n_rows))
 
 
+def join_test_tables():
+    """Join.test:19-57: a(w INT, x LONG, y DOUBLE), b from a WHERE w % 2 = 0, c from a WHERE x % 3 = 0."""
+    w = np.arange(20, dtype=np.int32)
+    x = (w * 10).astype(np.int64)
+    y = (w * 100).astype(np.float64)
+    a = HostTable("a", [Column("w", A.QS_INT, w), Column("x", A.QS_LONG, x), Column("y", A.QS_DOUBLE, y)])
+    mb = w % 2 == 0
+    b = HostTable("b", [Column("w", A.QS_INT, w[mb]), Column("x", A.QS_LONG, x[mb] + (w[mb] // 2) % 2)])
+    mc = x % 3 == 0
+    c = HostTable("c", [Column("x", A.QS_LONG, x[mc]), Column("y", A.QS_DOUBLE, y[mc] + (x[mc] // 3) % 3 - 1)])
+    return a, b, c
+
+
+# Join.test:137-165, columns a.w, b.x, c.y of `a LEFT JOIN b ON a.w = b.w LEFT JOIN c ON a.x = c.x`
+JOIN_TEST_LEFT_OUTER_EXPECTED = [
+    (0, 0, -1.0), (1, None, None), (2, 21, None), (3, None, 300.0), (4, 40, None), (5, None, None), (6, 61, 601.0),
+    (7, None, None), (8, 80, None), (9, None, 899.0), (10, 101, None), (11, None, None), (12, 120, 1200.0),
+    (13, None, None), (14, 141, None), (15, None, 1501.0), (16, 160, None), (17, None, None), (18, 181, 1799.0),
+    (19, None, None)]
+
+
+def case_join_test_left_outer(B):
+    """The two INT/LONG-keyed LEFT JOINs of Join.test:137-165, each as one HashOuterJoin work order; returns
+    [(a.w, b.x | None, c.y | None)] ordered by a.w."""
+    a, b, c = join_test_tables()
+    es = ExprSet()
+    out1 = B.hash_join(B.relation(b), -1, 0, B.relation(a), es, -1, 0, A.QS_JOIN_LEFT_OUTER, -1,
+                       [es.attr(0, A.QS_INT), es.attr(1, A.QS_LONG, 8, 2)], [(A.QS_INT, 4), (A.QS_LONG, 8)], 64)
+    es2 = ExprSet()
+    out2 = B.hash_join(B.relation(c), -1, 0, B.relation(a), es2, -1, 1, A.QS_JOIN_LEFT_OUTER, -1,
+                       [es2.attr(0, A.QS_INT), es2.attr(1, A.QS_DOUBLE, 8, 2)], [(A.QS_INT, 4), (A.QS_DOUBLE, 8)], 64)
+    bx = {int(out1.columns[0].data[i]): (None if int(out1.nulls[i]) & 2 else int(out1.columns[1].data[i])) for i in range(out1.n_rows)}
+    cy = {int(out2.columns[0].data[i]): (None if int(out2.nulls[i]) & 2 else float(out2.columns[1].data[i])) for i in range(out2.n_rows)}
+    assert out1.n_rows == out2.n_rows == 20 and not any(int(n) & 1 for n in out1.nulls)
+    return [(w, bx[w], cy[w]) for w in sorted(bx)]
+
+
 # ------------------------------------------- AggregationOperator_unittest.cpp
 K_NUM_TUPLES, K_GROUP_WIDTH, K_GROUP1 = 300, 20, 4
 

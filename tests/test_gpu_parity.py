@@ -120,6 +120,52 @@ def test_hash_join_unittest(G, OB, key, join_type, residual, table):
         assert (counts[:100] == 3).all() and (counts[100:] == 0).all()
 
 
+@pytest.mark.parametrize("table", ["open_addressing", "dense"])
+def test_join_test_left_outer_golden(G, table):
+    """Join.test:137-165: LEFT OUTER joins on INT and LONG keys, NULLs for probe rows without a match."""
+    G.dense_join = table == "dense"
+    assert K.case_join_test_left_outer(G) == K.JOIN_TEST_LEFT_OUTER_EXPECTED
+
+
+@pytest.mark.parametrize("table", ["open_addressing", "dense"])
+def test_left_outer_join_random(G, OB, table):
+    """Duplicate build keys, a probe predicate, attribute and expression projections of both sides: row sets and
+    NULL masks equal the oracle's (rows compared order-insensitively, the NULL word appended as a column)."""
+    G.dense_join = table == "dense"
+    rng = np.random.default_rng(12)
+    build = HostTable("b", [Column("k", A.QS_INT, rng.integers(0, 500, size=1500).astype(np.int32)),
+                            Column("p", A.QS_LONG, rng.integers(-1000, 1000, size=1500)),
+                            Column("q", A.QS_DOUBLE, rng.normal(size=1500))])
+    probe = HostTable("p", [Column("k", A.QS_INT, rng.integers(0, 900, size=7000).astype(np.int32)),
+                            Column("v", A.QS_DOUBLE, rng.normal(size=7000))])
+    es = ExprSet()
+    pp = es.cmp(A.QS_GT, es.attr(1, A.QS_DOUBLE), es.lit_double(-1.0))
+    roots = [es.attr(0, A.QS_INT), es.attr(1, A.QS_LONG, 8, 2), es.attr(1, A.QS_DOUBLE),
+             es.add(es.attr(1, A.QS_DOUBLE), es.attr(2, A.QS_DOUBLE, 8, 2)), es.mul(es.attr(1, A.QS_DOUBLE), es.lit_double(2.0))]
+    schema = [(A.QS_INT, 4), (A.QS_LONG, 8), (A.QS_DOUBLE, 8), (A.QS_DOUBLE, 8), (A.QS_DOUBLE, 8)]
+    g = G.hash_join(G.relation(build), -1, 0, G.relation(probe), es, pp, 0, A.QS_JOIN_LEFT_OUTER, -1, roots, schema, 100000)
+    o = OB.hash_join(build, -1, 0, probe, es, pp, 0, A.QS_JOIN_LEFT_OUTER, -1, roots, schema, 100000)
+    assert g.n_rows == o.n_rows and (o.nulls != 0).sum() > 1000 and set(np.unique(o.nulls)) == {0, 0b01010}
+    for t in (g, o):
+        t.columns.append(Column("nulls", A.QS_LONG, t.nulls.astype(np.int64)))
+    assert table_rows(g) == table_rows(o)
+
+
+def test_left_outer_join_rejects_residual(engine):
+    from quickstep_b200.capi import QsGpuError
+    t = HostTable("t", [Column("k", A.QS_INT, np.arange(10, dtype=np.int32))])
+    rel = engine.Relation.from_host(t)
+    out = engine.Relation.create([(A.QS_INT, 4)], 100)
+    jt = engine.JoinTable(A.QS_INT, 16)
+    es = ExprSet()
+    try:
+        jt.build(rel, None, -1, 0)
+        with pytest.raises(QsGpuError):
+            jt.probe(rel, es, -1, 0, A.QS_JOIN_LEFT_OUTER, es.cmp(A.QS_GT, es.attr(0, A.QS_INT), es.lit_int(3)), [es.attr(0, A.QS_INT)], out)
+    finally:
+        jt.destroy(); out.destroy(); rel.destroy()
+
+
 def test_dense_join_rejects_keys_outside_declared_range(engine):
     """A build key outside [min_key, max_key] of a dense table is an error, never a silent drop."""
     from quickstep_b200.capi import QsGpuError

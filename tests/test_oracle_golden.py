@@ -122,6 +122,11 @@ def test_hash_join_unittest_match_counts(B, key):
         assert out.columns[1].data[i] == str(int(k[i])).encode()
 
 
+def test_join_test_left_outer_golden(B):
+    """Join.test:137-165 (LEFT JOIN on INT and LONG keys): the oracle's outer join against the reference's table."""
+    assert K.case_join_test_left_outer(B) == K.JOIN_TEST_LEFT_OUTER_EXPECTED
+
+
 def test_hash_join_semi_anti(B):
     semi = K.case_hash_join_unittest(B, "int", A.QS_JOIN_LEFT_SEMI)
     anti = K.case_hash_join_unittest(B, "int", A.QS_JOIN_LEFT_ANTI)
