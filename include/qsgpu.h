@@ -380,6 +380,17 @@ int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan,
                      uint32_t key_attr, uint32_t n_lip_build,
                      const qs_lip_ref *lip_build);
 int qsgpu_join_num_entries(qsgpu_join_table_t table, uint64_t *n);
+/* Composite join key (HashTable::putValueAccessorCompositeKey / getAllFromValueAccessorCompositeKey,
+ * storage/HashTable.hpp:1469,2183): n_keys = 2 INT attributes, compared component-wise; the table must be an
+ * open-addressing table created with QS_LONG keys (the pair is packed into one 64-bit key).  n_keys = 1 is
+ * qsgpu_join_build / qsgpu_join_probe. */
+int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, uint32_t n_keys,
+                               const uint32_t *key_attrs, uint32_t n_lip_build,
+                               const qs_lip_ref *lip_build);
+int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, uint32_t n_keys,
+                               const uint32_t *probe_key_attrs, uint32_t join_type,
+                               int32_t residual_root, uint32_t n_project,
+                               const int32_t *project_roots, qsgpu_relation_t output);
 /*
  * HashInnerJoinWorkOrder / Semi / Anti / Outer (HashJoinOperator.cpp:450-1099): LIP
  * probe -> hash probe -> residual predicate over both sides -> projection.

@@ -148,6 +148,9 @@ SIGNATURES = {
     "qsgpu_join_num_entries": (C.c_int, [_VP, _U64P]),
     "qsgpu_join_probe": (C.c_int, [_VP, C.POINTER(qs_scan), C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
                                    C.POINTER(C.c_int32), _VP]),
+    "qsgpu_join_build_composite": (C.c_int, [_VP, C.POINTER(qs_scan), C.c_uint32, _U32P, C.c_uint32, C.POINTER(qs_lip_ref)]),
+    "qsgpu_join_probe_composite": (C.c_int, [_VP, C.POINTER(qs_scan), C.c_uint32, _U32P, C.c_uint32, C.c_int32, C.c_uint32,
+                                             C.POINTER(C.c_int32), _VP]),
     "qsgpu_join_destroy": (C.c_int, [_VP]),
     "qsgpu_topk": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_sort_key), C.c_uint64, _VPP]),
     "qsgpu_radix_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),

@@ -1489,12 +1489,40 @@ int qsgpu_join_create_dense(int dev, uint32_t key_type, int64_t min_key, int64_t
   return QSGPU_OK;
 }
 
+// One key attribute of the table's key type, or two INT attributes packed into the LONG key of the table.
+static int check_join_keys(const qsgpu_join_table *table, const qsgpu_relation *rel, uint32_t n_keys, const uint32_t *key_attrs) {
+  if (n_keys == 0 || n_keys > 2 || !key_attrs) { set_error(QSGPU_ERR_UNSUPPORTED, "join keys: one INT/LONG attribute or two INT attributes"); return QSGPU_ERR_UNSUPPORTED; }
+  for (uint32_t i = 0; i < n_keys; ++i)
+    if (key_attrs[i] >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "join key attribute out of range"); return QSGPU_ERR_INVALID; }
+  if (n_keys == 1) {
+    const uint16_t t = rel->attrs[key_attrs[0]].type;
+    if (t != QS_INT && t != QS_LONG) { set_error(QSGPU_ERR_UNSUPPORTED, "join key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+    return QSGPU_OK;
+  }
+  if (rel->attrs[key_attrs[0]].type != QS_INT || rel->attrs[key_attrs[1]].type != QS_INT || table->key_type != QS_LONG || table->J.dense) {
+    set_error(QSGPU_ERR_UNSUPPORTED, "a composite join key is two INT attributes on an open-addressing table created with QS_LONG keys");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  return QSGPU_OK;
+}
+
 int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan, uint32_t key_attr, uint32_t n_lip_build,
                      const qs_lip_ref *lip_build) {
+  return qsgpu_join_build_composite(table, scan, 1, &key_attr, n_lip_build, lip_build);
+}
+
+int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, uint32_t n_keys, const uint32_t *key_attrs,
+                               uint32_t n_lip_build, const qs_lip_ref *lip_build) {
   qsgpu_relation *rel = scan->input;
   Device *d = device(table->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
-  if (rel->dev != table->dev || key_attr >= rel->attrs.size() || rel->attrs[key_attr].type != table->key_type) { set_error(QSGPU_ERR_INVALID, "build key attribute does not match the table"); return QSGPU_ERR_INVALID; }
+  if (rel->dev != table->dev) { set_error(QSGPU_ERR_INVALID, "build relation on another device"); return QSGPU_ERR_INVALID; }
+  {
+    const int ks = check_join_keys(table, rel, n_keys, key_attrs);
+    if (ks) return ks;
+  }
+  const uint32_t key_attr = key_attrs[0];
+  if (n_keys == 1 && rel->attrs[key_attr].type != table->key_type) { set_error(QSGPU_ERR_INVALID, "build key attribute does not match the table"); return QSGPU_ERR_INVALID; }
   {
     std::lock_guard<std::mutex> lk(table->mu);      // build work orders of one operator run concurrently
     if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
@@ -1510,6 +1538,8 @@ int qsgpu_join_build(qsgpu_join_table_t table, const qs_scan *scan, uint32_t key
   if (st) return st;
   JoinDesc J = table->J;
   J.key_col = static_cast<uint16_t>(L.stage_attr(key_attr));
+  J.key_ltype = vtype_of(rel->attrs[key_attr].type);
+  if (n_keys == 2) { J.key2_present = 1; J.key2_col = static_cast<uint16_t>(L.stage_attr(key_attrs[1])); }
   L.finish();
   ScanDesc S;
   fill_scan(rel, scan->row_begin, scan->row_end, L, &S);
@@ -1540,9 +1570,20 @@ int qsgpu_join_num_entries(qsgpu_join_table_t table, uint64_t *n) {
 int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t probe_key_attr, uint32_t join_type,
                      int32_t residual_root, uint32_t n_project, const int32_t *project_roots,
                      qsgpu_relation_t output) {
+  return qsgpu_join_probe_composite(table, probe, 1, &probe_key_attr, join_type, residual_root, n_project, project_roots, output);
+}
+
+int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, uint32_t n_keys, const uint32_t *probe_key_attrs,
+                               uint32_t join_type, int32_t residual_root, uint32_t n_project,
+                               const int32_t *project_roots, qsgpu_relation_t output) {
   qsgpu_relation *rel = probe->input;
   Device *d = device(table->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
+  {
+    const int ks = check_join_keys(table, rel, n_keys, probe_key_attrs);
+    if (ks) return ks;
+  }
+  const uint32_t probe_key_attr = probe_key_attrs[0];
   if (join_type > QS_JOIN_LEFT_OUTER) { set_error(QSGPU_ERR_INVALID, "unknown join type"); return QSGPU_ERR_INVALID; }
   if (join_type == QS_JOIN_LEFT_OUTER && residual_root >= 0) {
     // DCHECK in the reference too (relational_operators/HashJoinOperator.hpp:139-141)
@@ -1587,6 +1628,7 @@ int qsgpu_join_probe(qsgpu_join_table_t table, const qs_scan *probe, uint32_t pr
   J.join_type = static_cast<uint8_t>(join_type);
   J.key_col = static_cast<uint16_t>(L.stage_attr(probe_key_attr));
   J.key_ltype = klt;
+  if (n_keys == 2) { J.key2_present = 1; J.key2_col = static_cast<uint16_t>(L.stage_attr(probe_key_attrs[1])); }
   J.n_build_cols = static_cast<uint32_t>(L.build_attrs.size());
   for (uint32_t c = 0; c < J.n_build_cols; ++c) {
     const uint32_t a = L.build_attrs[c];

@@ -110,6 +110,8 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
     o << "  static constexpr uint32_t j_key_col = " << J.key_col << ", j_type = " << int(J.join_type) << ";\n";
     o << "  static constexpr uint8_t j_key_ltype = " << int(J.key_ltype) << ";\n";
     o << "  static constexpr bool j_dense = " << (J.dense ? "true" : "false") << ";\n";
+    o << "  static constexpr bool j_key2 = " << (J.key2_present ? "true" : "false") << ";\n";
+    o << "  static constexpr uint32_t j_key2_col = " << J.key2_col << ";\n";
     table(o, "uint32_t", "build_w", J.n_build_cols, J.build_cols, [](const ColDesc &c) { return c.width; });
   }
   o << "};\n}  // namespace qs\n";

@@ -582,6 +582,20 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
   });
 }
 
+// Join key of row `row` of the staged tile: one INT/LONG attribute, or two INT attributes packed into 64 bits.
+template <class Q>
+__device__ __forceinline__ int64_t join_key(const char *stage, uint32_t row) {
+  constexpr uint8_t klt = Q::j_key_ltype;
+  constexpr uint32_t kw = (klt == V_I32) ? 4u : 8u;
+  const int64_t k0 = static_cast<int64_t>(load_native(stage + Q::col_off(Q::j_key_col) + row * kw, klt));
+  if constexpr (Q::j_key2) {
+    const uint32_t k1 = *reinterpret_cast<const uint32_t *>(stage + Q::col_off(Q::j_key2_col) + row * 4u);
+    return static_cast<int64_t>((static_cast<uint64_t>(k1) << 32) | static_cast<uint32_t>(k0));
+  } else {
+    return k0;
+  }
+}
+
 // ============================================================== K5 join build
 // The reference's JoinHashTable is a separate-chaining multi-map from key to
 // TupleReference{block, tuple}; probes collect (probe_tid, build_tid) pairs per
@@ -614,14 +628,11 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
 #pragma unroll
     for (int r = 0; r < kRows; ++r) pass[r] = valid[r] && (bits[r] & 1u);
     lip_build_rows<Q, SinkBase>(K, stage, tid, pass);
-    constexpr uint8_t klt = Q::j_key_ltype;
-    constexpr uint32_t kw = (klt == V_I32) ? 4u : 8u;
-    const char *kbase = stage + Q::col_off(Q::j_key_col);
     uint32_t inserted = 0;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       if (!pass[r]) continue;
-      const int64_t key = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
+      const int64_t key = join_key<Q>(stage, tile_row(r, tid));
       const unsigned long long row = row0 + tile_row(r, tid);
       if constexpr (Q::j_dense) {
         // push the row on the front of its key's chain: one exchange, one store
@@ -739,15 +750,12 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
     bool pass[kRows], active[kRows], matched[kRows];
     int64_t key[kRows];
     uint64_t h[kRows];
-    constexpr uint8_t klt = Q::j_key_ltype;
-    constexpr uint32_t kw = (klt == V_I32) ? 4u : 8u;
-    const char *kbase = stage + Q::col_off(Q::j_key_col);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       pass[r] = valid[r] && (bits[r] & 1u);
       active[r] = pass[r];
       matched[r] = false;
-      key[r] = static_cast<int64_t>(load_native(kbase + tile_row(r, tid) * kw, klt));
+      key[r] = join_key<Q>(stage, tile_row(r, tid));
       if constexpr (Q::j_dense) {
         // h[r] walks the chain of build rows: head of the key's chain, then next[]
         const uint64_t k = static_cast<uint64_t>(key[r] - J.min_key);

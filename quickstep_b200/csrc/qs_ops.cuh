@@ -44,6 +44,11 @@ struct JoinDesc {
   unsigned long long *n_entries;
   uint16_t key_col;                 // staged column slot of the key
   uint8_t key_ltype;                // V_I32 / V_I64
+  // Composite key of two INT attributes (HashTable::putValueAccessorCompositeKey, storage/HashTable.hpp:1469):
+  // the pair is packed into one 64-bit key (first attribute in the low word), so equality of the packed key
+  // is equality of both components.  key2_present = 0: single-attribute key.
+  uint8_t key2_present;
+  uint16_t key2_col;
   uint8_t join_type;                // QS_JOIN_*
   uint32_t n_build_cols;
   ColDesc build_cols[kMaxCols];     // build relation columns for LEAF_BUILD / raw emits

@@ -385,7 +385,8 @@ class JoinTable:
         """BuildHashWorkOrder::execute."""
         s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
         n, arr = _lip_refs(lip_build)
-        A.check(A.load().qsgpu_join_build(self.h, C.byref(s), key_attr, n, arr))
+        keys = list(key_attr) if isinstance(key_attr, (list, tuple)) else [key_attr]      # 2 INT attrs: composite key
+        A.check(A.load().qsgpu_join_build_composite(self.h, C.byref(s), len(keys), (C.c_uint32 * len(keys))(*keys), n, arr))
 
     def num_entries(self) -> int:
         n = C.c_uint64(0)
@@ -396,8 +397,10 @@ class JoinTable:
               lip_probe=None, row_begin=0, row_end=A.UINT64_MAX):
         """Hash{Inner,Semi,Anti}JoinWorkOrder::execute."""
         s, _k = _scan(rel, es, pred_root, lip_probe, row_begin, row_end)
-        A.check(A.load().qsgpu_join_probe(self.h, C.byref(s), key_attr, join_type, residual_root,
-                                          len(project_roots), _i32(project_roots), output.h))
+        keys = list(key_attr) if isinstance(key_attr, (list, tuple)) else [key_attr]
+        A.check(A.load().qsgpu_join_probe_composite(self.h, C.byref(s), len(keys), (C.c_uint32 * len(keys))(*keys),
+                                                    join_type, residual_root, len(project_roots), _i32(project_roots),
+                                                    output.h))
 
     def destroy(self):
         if self.h:

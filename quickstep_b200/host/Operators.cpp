@@ -132,7 +132,7 @@ bool BuildHashOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryCo
                                          StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   for (const DeviceExtent &e : feed_.take(storage_manager)) {
     container->addNormalWorkOrder(
-        new BuildHashWorkOrder(query_id_, e, join_key_attributes_[0], query_context->getPredicate(build_predicate_index_),
+        new BuildHashWorkOrder(query_id_, e, join_key_attributes_, query_context->getPredicate(build_predicate_index_),
                                query_context->getJoinHashTable(hash_table_index_),
                                query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe),
                                query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kBuild)),
@@ -146,8 +146,9 @@ void BuildHashWorkOrder::execute() {
   addPredicate(&L, predicate_);
   const qs_expr_set es = L.es.view();
   const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
-  QS_CHECK_GPU(qsgpu_join_build(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attribute_),
-                                static_cast<std::uint32_t>(lip_build_.size()), lip_build_.empty() ? nullptr : lip_build_.data()));
+  QS_CHECK_GPU(qsgpu_join_build_composite(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attributes_.size()),
+                                          join_key_attributes_.data(), static_cast<std::uint32_t>(lip_build_.size()),
+                                          lip_build_.empty() ? nullptr : lip_build_.data()));
 }
 
 // ---------------------------------------------------------------- HashJoin
@@ -156,7 +157,7 @@ bool HashJoinOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryCon
   InsertDestination *dest = query_context->getInsertDestination(output_destination_index_);
   for (const DeviceExtent &e : feed_.take(storage_manager)) {
     container->addNormalWorkOrder(
-        new HashJoinWorkOrder(query_id_, e, join_key_attributes_[0], query_context->getPredicate(residual_predicate_index_),
+        new HashJoinWorkOrder(query_id_, e, join_key_attributes_, query_context->getPredicate(residual_predicate_index_),
                               &query_context->getScalarGroup(selection_index_),
                               query_context->getJoinHashTable(hash_table_index_), dest, join_type_,
                               query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)),
@@ -182,9 +183,10 @@ void HashJoinWorkOrder::execute() {
     case JoinType::kLeftAntiJoin: jt = QS_JOIN_LEFT_ANTI; break;
     case JoinType::kLeftOuterJoin: jt = QS_JOIN_LEFT_OUTER; break;
   }
-  QS_CHECK_GPU(qsgpu_join_probe(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attribute_), jt, residual_root,
-                                static_cast<std::uint32_t>(L.roots.size()), L.roots.data(),
-                                output_destination_->deviceRelation()));
+  QS_CHECK_GPU(qsgpu_join_probe_composite(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attributes_.size()),
+                                          join_key_attributes_.data(), jt, residual_root,
+                                          static_cast<std::uint32_t>(L.roots.size()), L.roots.data(),
+                                          output_destination_->deviceRelation()));
 }
 
 // ------------------------------------------------------------- Aggregation

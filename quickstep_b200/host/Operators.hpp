@@ -152,7 +152,7 @@ class BuildHashOperator : public RelationalOperator {
       : RelationalOperator(query_id, num_partitions), feed_(input_relation, input_relation_is_stored),
         join_key_attributes_(join_key_attributes), hash_table_index_(hash_table_index),
         build_predicate_index_(build_predicate_index) {
-    QS_CHECK(join_key_attributes.size() == 1u);     // composite join keys: SURVEY.md 8f row 3
+    QS_CHECK(join_key_attributes.size() == 1u || join_key_attributes.size() == 2u);   // composite: two INT attributes
     QS_CHECK(!any_join_key_attributes_nullable);
   }
   OperatorType getOperatorType() const override { return kBuildHash; }
@@ -170,16 +170,16 @@ class BuildHashOperator : public RelationalOperator {
 
 class BuildHashWorkOrder : public WorkOrder {
  public:
-  BuildHashWorkOrder(const std::size_t query_id, const DeviceExtent &input, attribute_id join_key_attribute,
+  BuildHashWorkOrder(const std::size_t query_id, const DeviceExtent &input, const std::vector<attribute_id> &join_key_attributes,
                      const QueryContext::Predicate *predicate, qsgpu_join_table_t hash_table,
                      std::vector<qs_lip_ref> lip_probe, std::vector<qs_lip_ref> lip_build)
-      : WorkOrder(query_id), input_(input), join_key_attribute_(join_key_attribute), predicate_(predicate),
+      : WorkOrder(query_id), input_(input), join_key_attributes_(join_key_attributes.begin(), join_key_attributes.end()), predicate_(predicate),
         hash_table_(hash_table), lip_probe_(std::move(lip_probe)), lip_build_(std::move(lip_build)) {}
   void execute() override;      // BuildHashOperator.cpp:162-207
 
  private:
   const DeviceExtent input_;
-  const attribute_id join_key_attribute_;
+  const std::vector<std::uint32_t> join_key_attributes_;
   const QueryContext::Predicate *predicate_;
   qsgpu_join_table_t hash_table_;
   const std::vector<qs_lip_ref> lip_probe_, lip_build_;
@@ -200,7 +200,7 @@ class HashJoinOperator : public RelationalOperator {
         join_key_attributes_(join_key_attributes), output_relation_(output_relation),
         output_destination_index_(output_destination_index), hash_table_index_(hash_table_index),
         residual_predicate_index_(residual_predicate_index), selection_index_(selection_index), join_type_(join_type) {
-    QS_CHECK(join_key_attributes.size() == 1u);
+    QS_CHECK(join_key_attributes.size() == 1u || join_key_attributes.size() == 2u);
     QS_CHECK(!any_join_key_attributes_nullable);
   }
   OperatorType getOperatorType() const override {
@@ -239,18 +239,18 @@ class HashJoinOperator : public RelationalOperator {
 // compile-time property of the kernel the C ABI instantiates, not of the host object.
 class HashJoinWorkOrder : public WorkOrder {
  public:
-  HashJoinWorkOrder(const std::size_t query_id, const DeviceExtent &probe, attribute_id join_key_attribute,
+  HashJoinWorkOrder(const std::size_t query_id, const DeviceExtent &probe, const std::vector<attribute_id> &join_key_attributes,
                     const QueryContext::Predicate *residual_predicate, const QueryContext::ScalarGroup *selection,
                     qsgpu_join_table_t hash_table, InsertDestination *output_destination, JoinType join_type,
                     std::vector<qs_lip_ref> lip_probe)
-      : WorkOrder(query_id), probe_(probe), join_key_attribute_(join_key_attribute), residual_predicate_(residual_predicate),
+      : WorkOrder(query_id), probe_(probe), join_key_attributes_(join_key_attributes.begin(), join_key_attributes.end()), residual_predicate_(residual_predicate),
         selection_(selection), hash_table_(hash_table), output_destination_(output_destination), join_type_(join_type),
         lip_probe_(std::move(lip_probe)) {}
   void execute() override;
 
  private:
   const DeviceExtent probe_;
-  const attribute_id join_key_attribute_;
+  const std::vector<std::uint32_t> join_key_attributes_;
   const QueryContext::Predicate *residual_predicate_;
   const QueryContext::ScalarGroup *selection_;
   qsgpu_join_table_t hash_table_;

@@ -151,6 +151,44 @@ def test_left_outer_join_random(G, OB, table):
     assert table_rows(g) == table_rows(o)
 
 
+@pytest.mark.parametrize("join_type", [A.QS_JOIN_INNER, A.QS_JOIN_LEFT_ANTI, A.QS_JOIN_LEFT_OUTER])
+def test_composite_join_key(engine, OB, join_type):
+    """Two INT attributes as the join key (HashTable.hpp:1469 compares every component).  The oracle joins on one
+    LONG column holding the same pair, which is the same equality; negative components included."""
+    rng = np.random.default_rng(23)
+    nb, npr = 3000, 9000
+    b0, b1 = rng.integers(-20, 20, size=nb).astype(np.int32), rng.integers(-20, 20, size=nb).astype(np.int32)
+    p0, p1 = rng.integers(-25, 25, size=npr).astype(np.int32), rng.integers(-25, 25, size=npr).astype(np.int32)
+    pack = lambda x, y: (x.astype(np.int64) & 0xFFFFFFFF) | (y.astype(np.int64) << 32)
+    build = HostTable("b", [Column("k0", A.QS_INT, b0), Column("k1", A.QS_INT, b1), Column("p", A.QS_LONG, np.arange(nb, dtype=np.int64)),
+                            Column("kk", A.QS_LONG, pack(b0, b1))])
+    probe = HostTable("p", [Column("k0", A.QS_INT, p0), Column("k1", A.QS_INT, p1), Column("v", A.QS_DOUBLE, rng.normal(size=npr)),
+                            Column("kk", A.QS_LONG, pack(p0, p1))])
+    es = ExprSet()
+    if join_type == A.QS_JOIN_LEFT_ANTI:
+        roots, schema = [es.attr(0, A.QS_INT), es.attr(1, A.QS_INT), es.attr(2, A.QS_DOUBLE)], [(A.QS_INT, 4), (A.QS_INT, 4), (A.QS_DOUBLE, 8)]
+    else:
+        roots = [es.attr(0, A.QS_INT), es.attr(1, A.QS_INT), es.attr(2, A.QS_LONG, 8, 2), es.attr(2, A.QS_DOUBLE)]
+        schema = [(A.QS_INT, 4), (A.QS_INT, 4), (A.QS_LONG, 8), (A.QS_DOUBLE, 8)]
+    cap = 400000
+    o = OB.hash_join(build, -1, 3, probe, es, -1, 3, join_type, -1, roots, schema, cap)
+    brel, prel = engine.Relation.from_host(build), engine.Relation.from_host(probe)
+    out = engine.Relation.create(schema, cap)
+    jt = engine.JoinTable(A.QS_LONG, nb)
+    try:
+        jt.build(brel, None, -1, [0, 1])
+        assert jt.num_entries() == nb
+        jt.probe(prel, es, -1, [0, 1], join_type, -1, roots, out)
+        g = out.to_host("join")
+        g.nulls = out.read_nulls()
+    finally:
+        jt.destroy(); out.destroy(); brel.destroy(); prel.destroy()
+    assert g.n_rows == o.n_rows > 0
+    for t in (g, o):
+        t.columns.append(Column("nulls", A.QS_LONG, t.nulls.astype(np.int64)))
+    assert table_rows(g) == table_rows(o)
+
+
 def test_left_outer_join_rejects_residual(engine):
     from quickstep_b200.capi import QsGpuError
     t = HostTable("t", [Column("k", A.QS_INT, np.arange(10, dtype=np.int32))])
