@@ -346,6 +346,15 @@ int qsgpu_agg_partial_layout(qsgpu_agg_state_t state, void **d_states, void **d_
 int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states,
                             const void *d_keys, uint64_t n_groups);
 /*
+ * CollisionFreeVectorTable::getExistenceMap (storage/CollisionFreeVectorTable.hpp:123-128), COLLISION_FREE
+ * states only: an exact bit-vector filter over the table's key range, owned by the state.
+ * BuildAggregationExistenceMapWorkOrder::execute (relational_operators/BuildAggregationExistenceMapOperator.cpp:176-212)
+ * is qsgpu_build_lip_filter with this filter as the build target and the build attribute as its key; a group
+ * whose bit is set is finalized even when no input row reached it (COUNT 0, SUM 0) -- the fused
+ * "LEFT OUTER JOIN ... GROUP BY left key" plans of ExecutionGenerator.cpp:2142-2180.
+ */
+int qsgpu_agg_existence_map(qsgpu_agg_state_t state, qsgpu_lip_t *out);
+/*
  * finalizeAggregate: output relation gets one row per group: the group-by
  * attributes in order, then one column per aggregate (SUM(int)->LONG,
  * SUM(float/double)->DOUBLE, AVG->DOUBLE, COUNT->LONG, MIN/MAX->argument

@@ -140,6 +140,7 @@ SIGNATURES = {
     "qsgpu_agg_partial": (C.c_int, [_VP, _VPP, _VPP, _U64P, _U32P, _U32P]),
     "qsgpu_agg_partial_layout": (C.c_int, [_VP, _VPP, _VPP, _U64P, _U32P, _U32P]),
     "qsgpu_agg_merge_partial": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
+    "qsgpu_agg_existence_map": (C.c_int, [_VP, _VPP]),
     "qsgpu_agg_finalize": (C.c_int, [_VP, _VPP, _U64P]),
     "qsgpu_agg_destroy": (C.c_int, [_VP]),
     "qsgpu_join_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, _VPP]),

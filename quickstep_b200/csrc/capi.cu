@@ -1270,7 +1270,8 @@ static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
     s->idx_cap = A.cap;
   }
   QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
-  QS_CUDA(launch_collect_slots(A.states, A.words, A.cap, s->d_idx, s->d_idx_count, d->stream));
+  QS_CUDA(launch_collect_slots(A.states, A.words, A.cap, s->d_idx, s->d_idx_count,
+                               s->existence ? s->existence->d.words : nullptr, d->stream));
   count_launch();
   unsigned long long n = 0;
   QS_CUDA(cudaMemcpyAsync(&n, s->d_idx_count, 8, cudaMemcpyDeviceToHost, d->stream));
@@ -1434,8 +1435,21 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   return QSGPU_OK;
 }
 
+int qsgpu_agg_existence_map(qsgpu_agg_state_t state, qsgpu_lip_t *out) {
+  std::lock_guard<std::mutex> state_lock(state->mu);
+  if (state->strategy != QS_AGG_COLLISION_FREE) { set_error(QSGPU_ERR_INVALID, "only a COLLISION_FREE state has an existence map"); return QSGPU_ERR_INVALID; }
+  if (!state->existence) {
+    const uint32_t key_type = state->key_attrs[0].type;
+    int st = qsgpu_lip_create(state->dev, QS_LIP_BITVECTOR_EXACT, key_type, 0, static_cast<int64_t>(state->A.cap) - 1, 0, 0, &state->existence);
+    if (st) return st;
+  }
+  *out = state->existence;
+  return QSGPU_OK;
+}
+
 int qsgpu_agg_destroy(qsgpu_agg_state_t s) {
   if (!s) return QSGPU_OK;
+  if (s->existence) qsgpu_lip_destroy(s->existence);
   device(s->dev);
   AggDesc &A = s->A;
   dev_free(A.partials); dev_free(A.dir_keys); dev_free(A.dir_gid); dev_free(A.n_groups); dev_free(A.gid_keys);

@@ -78,7 +78,8 @@ __global__ void k_merge_foreign_table(const __grid_constant__ AggDesc A, const u
 // same-address atomics for a 4M-slot table: 228 us in the r01b launch list).
 constexpr int kCollectPerThread = 16;
 __global__ void __launch_bounds__(256) k_collect_slots(const uint64_t *states, uint32_t words, uint64_t cap,
-                                                       uint64_t *out_idx, unsigned long long *counter) {
+                                                       uint64_t *out_idx, unsigned long long *counter,
+                                                       const uint64_t *exist_words) {
   __shared__ uint32_t s_warp[8];
   __shared__ unsigned long long s_base;
   const uint64_t base_slot = static_cast<uint64_t>(blockIdx.x) * (256 * kCollectPerThread);
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(256) k_collect_slots(const uint64_t *states, u
 #pragma unroll
   for (int i = 0; i < kCollectPerThread; ++i) {
     const uint64_t s = base_slot + static_cast<uint64_t>(i) * 256 + threadIdx.x;
-    if (s < cap && states[s * words] != 0) occ |= 1u << i;
+    // a dense table's group also exists when the existence map says so, even with no rows (COUNT = 0)
+    if (s < cap && (states[s * words] != 0 || (exist_words && bv_get(exist_words, s)))) occ |= 1u << i;
   }
   const uint32_t mine = __popc(occ);
   uint32_t incl = mine;                   // inclusive scan inside the warp
@@ -188,10 +190,10 @@ cudaError_t launch_merge_foreign_table(const AggDesc &A, const uint64_t *f_state
 }
 
 cudaError_t launch_collect_slots(const uint64_t *states, uint32_t words, uint64_t cap, uint64_t *out_idx,
-                                 unsigned long long *counter, cudaStream_t st) {
+                                 unsigned long long *counter, const uint64_t *exist_words, cudaStream_t st) {
   const uint64_t per_block = 256ull * kCollectPerThread;
   const uint64_t blocks = (cap + per_block - 1) / per_block;
-  k_collect_slots<<<static_cast<unsigned>(blocks), 256, 0, st>>>(states, words, cap, out_idx, counter);
+  k_collect_slots<<<static_cast<unsigned>(blocks), 256, 0, st>>>(states, words, cap, out_idx, counter, exist_words);
   return cudaGetLastError();
 }
 

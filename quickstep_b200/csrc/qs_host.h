@@ -62,6 +62,9 @@ struct qsgpu_agg_state {
   uint64_t idx_cap = 0;
   unsigned long long *d_idx_count = nullptr;
   uint64_t *d_exp_states = nullptr, *d_exp_keys = nullptr;
+  // COLLISION_FREE only: the table's existence map (CollisionFreeVectorTable::getExistenceMap), an exact
+  // bit-vector filter over [0, cap) that BuildAggregationExistenceMap work orders fill; owned by the state
+  qsgpu_lip *existence = nullptr;
   uint64_t exp_cap = 0;
   uint64_t estimated = 0;
 };

@@ -96,7 +96,7 @@ cudaError_t launch_rehash(const AggDesc &from, const AggDesc &to, cudaStream_t s
 cudaError_t launch_merge_foreign_table(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
                                        uint64_t f_groups, cudaStream_t st);
 cudaError_t launch_collect_slots(const uint64_t *states, uint32_t words, uint64_t cap, uint64_t *out_idx,
-                                 unsigned long long *counter, cudaStream_t st);
+                                 unsigned long long *counter, const uint64_t *exist_words, cudaStream_t st);
 cudaError_t launch_gather_rows(const uint64_t *states, const uint64_t *keys, uint32_t words, uint32_t kw,
                                const uint64_t *idx, uint64_t n, uint64_t *o_states, uint64_t *o_keys,
                                int keys_are_slots, cudaStream_t st);

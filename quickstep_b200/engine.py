@@ -336,6 +336,16 @@ class AggState:
         A.check(A.load().qsgpu_agg_partial(self.h, C.byref(ds), C.byref(dk), C.byref(n), C.byref(w), C.byref(kw)))
         return ds.value, dk.value, n.value, w.value, kw.value
 
+    def existence_map(self) -> "LipFilter":
+        """The COLLISION_FREE table's existence map as a (borrowed) exact LIP filter: build it with
+        build_lip_filter(..., [(state.existence_map(), build_attr)]) = BuildAggregationExistenceMapWorkOrder."""
+        h = C.c_void_p()
+        A.check(A.load().qsgpu_agg_existence_map(self.h, C.byref(h)))
+        f = LipFilter.__new__(LipFilter)
+        f.h = h
+        f.destroy = lambda: None          # owned by the state
+        return f
+
     def partial_layout(self):
         """-> (d_states, d_keys, rows, words_per_group, key_words) without synchronising."""
         ds, dk = C.c_void_p(), C.c_void_p()

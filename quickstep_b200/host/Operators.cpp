@@ -208,6 +208,27 @@ void AggregationWorkOrder::execute() {
                              static_cast<std::uint32_t>(lip_probe_.size()), lip_probe_.empty() ? nullptr : lip_probe_.data()));
 }
 
+bool BuildAggregationExistenceMapOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
+                                                            StorageManager *storage_manager, const tmb::client_id,
+                                                            tmb::MessageBus *) {
+  for (const DeviceExtent &e : feed_.take(storage_manager, 1ull << build_attribute_)) {
+    container->addNormalWorkOrder(
+        new BuildAggregationExistenceMapWorkOrder(query_id_, e, build_attribute_,
+                                                  query_context->getAggregationState(aggr_state_index_)),
+        op_index_);
+  }
+  return feed_.exhausted(done_feeding_input_relation_);
+}
+
+void BuildAggregationExistenceMapWorkOrder::execute() {
+  qs_lip_ref target{};
+  QS_CHECK_GPU(qsgpu_agg_existence_map(state_, &target.lip));
+  target.attr = static_cast<std::uint32_t>(build_attribute_);
+  const std::vector<qs_lip_ref> no_probe;
+  const qs_scan scan = makeScan(input_, nullptr, -1, no_probe);
+  QS_CHECK_GPU(qsgpu_build_lip_filter(&scan, 1, &target));
+}
+
 bool FinalizeAggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                                    StorageManager *, const tmb::client_id, tmb::MessageBus *) {
   if (!started_) {

@@ -290,6 +290,42 @@ class AggregationWorkOrder : public WorkOrder {
   const std::vector<qs_lip_ref> lip_probe_;
 };
 
+// BuildAggregationExistenceMapOperator (relational_operators/BuildAggregationExistenceMapOperator.hpp:61-150):
+// marks, in the CollisionFreeVectorTable of an aggregation state, the keys that exist on the build side of a
+// fused aggregate-join, so that they are finalized even when no probe-side row reaches them.
+class BuildAggregationExistenceMapOperator : public RelationalOperator {
+ public:
+  BuildAggregationExistenceMapOperator(const std::size_t query_id, const CatalogRelation &input_relation,
+                                       const attribute_id build_attribute, const bool input_relation_is_stored,
+                                       const QueryContext::aggregation_state_id aggr_state_index,
+                                       const std::size_t num_partitions)
+      : RelationalOperator(query_id, num_partitions), feed_(input_relation, input_relation_is_stored),
+        build_attribute_(build_attribute), aggr_state_index_(aggr_state_index) {}
+  OperatorType getOperatorType() const override { return kBuildAggregationExistenceMap; }
+  std::string getName() const override { return "BuildAggregationExistenceMapOperator"; }
+  bool getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context, StorageManager *storage_manager,
+                        const tmb::client_id scheduler_client_id, tmb::MessageBus *bus) override;
+  void feedInputBlock(const block_id input_block_id, const relation_id, const partition_id) override { feed_.feed(input_block_id); }
+
+ private:
+  InputFeed feed_;
+  const attribute_id build_attribute_;
+  const QueryContext::aggregation_state_id aggr_state_index_;
+};
+
+class BuildAggregationExistenceMapWorkOrder : public WorkOrder {
+ public:
+  BuildAggregationExistenceMapWorkOrder(const std::size_t query_id, const DeviceExtent &input, attribute_id build_attribute,
+                                        qsgpu_agg_state_t state)
+      : WorkOrder(query_id), input_(input), build_attribute_(build_attribute), state_(state) {}
+  void execute() override;      // BuildAggregationExistenceMapOperator.cpp:176-212
+
+ private:
+  const DeviceExtent input_;
+  const attribute_id build_attribute_;
+  qsgpu_agg_state_t state_;
+};
+
 // InitializeAggregationOperator.cpp:36-93 memsets CollisionFreeVectorTable segments in parallel; the
 // device state is zeroed by one fill kernel inside qsgpu_agg_create, so the work order has nothing left to do.
 class InitializeAggregationOperator : public RelationalOperator {

@@ -54,7 +54,7 @@ class RelationalOperator {
  public:
   virtual ~RelationalOperator() {}
   enum OperatorType : std::uint8_t {      // values of the operators on this path (RelationalOperator.hpp:65-96)
-    kAggregation = 0, kBuildHash = 2, kBuildLIPFilter = 3, kDestroyAggregationState = 7, kDestroyHash = 8,
+    kAggregation = 0, kBuildAggregationExistenceMap = 1, kBuildHash = 2, kBuildLIPFilter = 3, kDestroyAggregationState = 7, kDestroyHash = 8,
     kFinalizeAggregation = 10, kInitializeAggregation = 11, kInnerJoin = 12, kLeftAntiJoin = 14,
     kLeftOuterJoin = 15, kLeftSemiJoin = 16, kSelect = 20, kSortMergeRun = 21
   };

@@ -429,6 +429,35 @@ def test_compact_key_non_finite_values_stay_in_their_group(G, OB):
     assert (gr.values[2] == o.values[2]).all()
 
 
+def test_collision_free_existence_map(engine):
+    """BuildAggregationExistenceMap + collision-free aggregation (the fused LEFT OUTER JOIN ... GROUP BY left key
+    plans, ExecutionGenerator.cpp:2142-2180): every left key is finalized, with COUNT 0 / SUM 0 when no right row
+    carries it.  Expected values are the closed form over the generated data."""
+    rng = np.random.default_rng(8)
+    left_keys = np.arange(0, 3000, 3, dtype=np.int32)                     # existing groups: 0, 3, 6, ...
+    right_k = rng.choice(left_keys[::2], size=20000).astype(np.int32)     # only every other left key has rows
+    right_v = rng.integers(1, 100, size=20000).astype(np.int64)
+    left = HostTable("l", [Column("k", A.QS_INT, left_keys)])
+    right = HostTable("r", [Column("k", A.QS_INT, right_k), Column("v", A.QS_LONG, right_v)])
+    es = ExprSet()
+    aggs = [(A.QS_AGG_COUNT, -1), (A.QS_AGG_SUM, right.attr(es, "v"))]
+    lrel, rrel = engine.Relation.from_host(left), engine.Relation.from_host(right)
+    st = engine.AggState(A.QS_AGG_COLLISION_FREE, es, -1, aggs, [right.attr(es, "k")], max_key=2999)
+    try:
+        engine.build_lip_filter(lrel, None, -1, None, [(st.existence_map(), 0)])
+        st.run(rrel)
+        fin, _ = engine.finalize_relation(st, [(A.QS_INT, 4)], [(A.QS_LONG, 8), (A.QS_LONG, 8)])
+        k, c, sm = fin.read(0), fin.read(1), fin.read(2)
+        fin.destroy()
+    finally:
+        st.destroy(); lrel.destroy(); rrel.destroy()
+    order = np.argsort(k)
+    assert (k[order] == left_keys).all()
+    assert (c[order] == np.bincount(right_k, minlength=3000)[left_keys]).all()
+    assert (sm[order] == np.bincount(right_k, weights=right_v, minlength=3000)[left_keys].astype(np.int64)).all()
+    assert (c == 0).sum() == 500
+
+
 def test_single_state_empty_input_is_null(G, OB):
     """SUM over zero rows is NULL (AggregationHandleSum.cpp:134-143); COUNT is 0."""
     th = K.random_table(500, seed=3)
