@@ -433,6 +433,13 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr,
                           uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets);
 
+/* Same regrouping by KEY RANGE: partition p = clamp((key - min_key) / part_width, 0, n_parts-1).  Used to make
+ * a large join cache-resident (radix join): build and probe sides are range-partitioned, so the slice of the
+ * dense join table and of the build relation that one probe partition touches is contiguous and fits in L2. */
+int qsgpu_range_partition(qsgpu_relation_t input, uint32_t key_attr, int64_t min_key,
+                          uint64_t part_width, uint32_t n_parts, qsgpu_relation_t output,
+                          uint64_t *host_offsets);
+
 /* ---------------------------------------------------------- instrumentation */
 /* CUDA-event time (ms) of the most recent kernel of the given family launched
  * by the calling thread's last call, for bench.py's roofline block. */

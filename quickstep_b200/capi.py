@@ -155,6 +155,7 @@ SIGNATURES = {
     "qsgpu_join_destroy": (C.c_int, [_VP]),
     "qsgpu_topk": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_sort_key), C.c_uint64, _VPP]),
     "qsgpu_radix_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
+    "qsgpu_range_partition": (C.c_int, [_VP, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, _VP, _U64P]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),

@@ -150,10 +150,16 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   const size_t fixed = kBarBytes + extra_smem + 256;
   const size_t per_sm = d->smem_per_sm;                     // 228 KB on B200
   const size_t per_block_max = d->smem_per_block_optin;     // 227 KB
-  // two CTAs per SM when two stages of each fit, else one
-  int ctas = 2;
-  size_t budget = per_sm / 2 - 1024;                        // 1 KB per CTA is reserved by the driver
-  if (fixed + 2ull * stage > budget) { ctas = 1; budget = per_block_max; }
+  // Resident CTAs per SM the shared-memory ring allows: narrow scans (join keys, LIP builds: a few KB per
+  // tile) run 3-4 CTAs per SM so that more random table accesses are in flight; wide ones 2, very wide 1.
+  // Registers may allow fewer: the grid is finally sized from the occupancy the driver reports for the
+  // compiled kernel (launch_query_kernel).
+  int ctas = 1;
+  size_t budget = per_block_max;
+  for (int c = 4; c >= 2; --c) {
+    const size_t b = per_sm / c - 1024;                     // 1 KB per CTA is reserved by the driver
+    if (fixed + (c >= 3 ? 3ull : 2ull) * stage <= b) { ctas = c; budget = b; break; }
+  }
   if (fixed + 2ull * stage > budget) {
     set_error(QSGPU_ERR_UNSUPPORTED, "scan references too many bytes per row for the shared-memory tile ring");
     return QSGPU_ERR_UNSUPPORTED;
@@ -212,7 +218,11 @@ static cudaError_t launch_query_kernel(Device *d, JitKernel *k, const ScanDesc &
   if (A) args[n++] = const_cast<AggDesc *>(A);
   if (K) args[n++] = const_cast<SinkDesc *>(K);
   if (J) args[n++] = const_cast<JoinDesc *>(J);
-  return jit_launch(k, plan.grid, plan.smem, d->stream, args);
+  // persistent grid: no more CTAs than can be resident at once (registers may allow fewer than the ring does)
+  int grid = plan.grid;
+  const int occ = jit_occupancy(k, plan.smem);
+  if (occ > 0) grid = std::min(grid, d->sm_count * std::min(occ, plan.ctas));
+  return jit_launch(k, grid, plan.smem, d->stream, args);
 }
 
 static int sync_rows(qsgpu_relation *rel) {

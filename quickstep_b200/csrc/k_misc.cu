@@ -28,6 +28,9 @@ struct PartDesc {
   const char *key;
   uint8_t key_ltype;
   uint32_t n_parts;
+  uint32_t range_mode;           // 0: mix64(key) % n_parts;  1: (key - min_key) / part_width (clamped)
+  int64_t min_key;
+  uint64_t part_width;
   uint64_t n_rows;
   unsigned long long *hist;      // [n_parts]
   unsigned long long *cursor;    // [n_parts] absolute write positions
@@ -35,6 +38,13 @@ struct PartDesc {
 
 __device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
   const int64_t k = static_cast<int64_t>(load_native(D.key + row * native_width(D.key_ltype), D.key_ltype));
+  if (D.range_mode) {
+    // key-range partitions: partition p holds keys [min + p*width, min + (p+1)*width), so the slice of a
+    // dense join table (and of the range-partitioned build relation) one partition touches is contiguous
+    if (k < D.min_key) return 0u;
+    const uint64_t p = static_cast<uint64_t>(k - D.min_key) / D.part_width;
+    return p >= D.n_parts ? D.n_parts - 1 : static_cast<uint32_t>(p);
+  }
   return static_cast<uint32_t>(mix64(static_cast<uint64_t>(k)) % D.n_parts);
 }
 
@@ -228,8 +238,22 @@ int qsgpu_relation_destroy(qsgpu_relation_t);
 int qsgpu_relation_num_rows(qsgpu_relation_t, uint64_t *);
 int qsgpu_relation_set_num_rows(qsgpu_relation_t, uint64_t);
 
+static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, uint32_t range_mode, int64_t min_key,
+                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets);
+
 int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets) {
+  return partition_impl(input, key_attr, n_parts, 0, 0, 1, output, host_offsets);
+}
+
+int qsgpu_range_partition(qsgpu_relation_t input, uint32_t key_attr, int64_t min_key, uint64_t part_width, uint32_t n_parts,
+                          qsgpu_relation_t output, uint64_t *host_offsets) {
+  if (part_width == 0) { set_error(QSGPU_ERR_INVALID, "range partition needs a positive partition width"); return QSGPU_ERR_INVALID; }
+  return partition_impl(input, key_attr, n_parts, 1, min_key, part_width, output, host_offsets);
+}
+
+static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, uint32_t range_mode, int64_t min_key,
+                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets) {
   Device *d = device(input->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   uint64_t n = 0;
@@ -253,6 +277,9 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   D.key = input->cols[key_attr];
   D.key_ltype = lt;
   D.n_parts = n_parts;
+  D.range_mode = range_mode;
+  D.min_key = min_key;
+  D.part_width = part_width;
   D.n_rows = n;
   unsigned long long *d_buf = nullptr;
   QS_CUDA(dev_malloc(&d_buf, 2ull * n_parts * 8 + 64));

@@ -124,7 +124,9 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
                   static_cast<unsigned>(fnv1a(q.data(), q.size(), 0xcbf29ce484222325ull) >> 32));
   }
   if (kernel_name) *kernel_name = name;
-  o << "extern \"C\" __global__ void __launch_bounds__(qs::kBlock, " << sp.ctas_per_sm << ")\n" << name << "(";
+  // min-blocks 2 at most: 3-4 resident CTAs are taken when the kernel's registers happen to allow it, never
+  // forced by capping registers at 64 (that would spill the heavier probe / select kernels)
+  o << "extern \"C\" __global__ void __launch_bounds__(qs::kBlock, " << (sp.ctas_per_sm > 2 ? 2 : sp.ctas_per_sm) << ")\n" << name << "(";
   o << "const __grid_constant__ qs::ScanDesc S, const __grid_constant__ qs::Lits L";
   const char *body = "";
   switch (sp.family) {
@@ -265,6 +267,23 @@ cudaError_t jit_launch(JitKernel *k, int grid, size_t smem, cudaStream_t st, voi
     }
   }
   return cudaLaunchKernel(reinterpret_cast<const void *>(k->fn), dim3(grid), dim3(kBlock), args, smem, st);
+}
+
+int jit_occupancy(JitKernel *k, size_t smem) {
+  std::lock_guard<std::mutex> lk(g_jit_mutex);
+  if (k->occ_smem == smem) return k->occ;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t &set = k->smem_set[dev & 15];
+  if (smem > set) {
+    if (cudaFuncSetAttribute(reinterpret_cast<const void *>(k->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    set = smem;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(k->fn), kBlock, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  k->occ_smem = smem;
+  k->occ = occ;
+  return occ;
 }
 
 void jit_stats(uint64_t *compiled, uint64_t *disk_hits, uint64_t *mem_hits) {

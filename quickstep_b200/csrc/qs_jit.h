@@ -24,6 +24,8 @@ struct JitKernel {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t fn = nullptr;
   size_t smem_set[16] = {0};    // per device: largest dynamic smem size already opted in
+  size_t occ_smem = ~static_cast<size_t>(0);   // dynamic smem size `occ` was computed for
+  int occ = 0;                  // resident CTAs per SM at that size (cudaOccupancyMaxActiveBlocksPerMultiprocessor)
   std::string name;             // kernel symbol: family + hash of the description
 };
 
@@ -50,6 +52,8 @@ int jit_get(const JitSpec &spec, JitKernel **out);
 int jit_compile_only(const std::string &source, std::string *cubin, std::string *log);
 
 cudaError_t jit_launch(JitKernel *k, int grid, size_t smem, cudaStream_t st, void **args);
+// Resident CTAs per SM of the compiled kernel with `smem` bytes of dynamic shared memory (0 if unknown).
+int jit_occupancy(JitKernel *k, size_t smem);
 
 // Number of NVRTC compilations / disk-cache hits since load (diagnostics).
 void jit_stats(uint64_t *compiled, uint64_t *disk_hits, uint64_t *mem_hits);

@@ -428,6 +428,13 @@ def topk(rel: Relation, keys, limit) -> Relation:
     return Relation(out, rel.schema, rel.names, rel.dev)
 
 
+def range_partition(rel: Relation, key_attr, min_key, part_width, n_parts, output: Relation) -> np.ndarray:
+    offs = np.zeros(n_parts + 1, dtype=np.uint64)
+    A.check(A.load().qsgpu_range_partition(rel.h, key_attr, min_key, part_width, n_parts, output.h,
+                                           offs.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return offs
+
+
 def radix_partition(rel: Relation, key_attr, n_parts, output: Relation) -> np.ndarray:
     offs = np.zeros(n_parts + 1, dtype=np.uint64)
     A.check(A.load().qsgpu_radix_partition(rel.h, key_attr, n_parts, output.h,

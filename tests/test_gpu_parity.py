@@ -605,6 +605,31 @@ def test_radix_partition(engine, oracle, n_parts):
         out.destroy(); rel.destroy()
 
 
+def test_range_partition(engine):
+    """qsgpu_range_partition: partition p holds exactly the keys of [min + p*width, min + (p+1)*width) (clamped at
+    both ends), partitions are contiguous and ordered, and the multiset of rows is unchanged."""
+    rng = np.random.default_rng(17)
+    n, n_parts, mn, width = 50000, 7, 100, 1000
+    keys = rng.integers(-500, 9000, size=n).astype(np.int64)
+    th = HostTable("t", [Column("k", A.QS_LONG, keys), Column("v", A.QS_DOUBLE, rng.normal(size=n)),
+                         Column("c", A.QS_CHAR, rng.integers(65, 91, size=(n, 3)).astype(np.uint8).view("S3").reshape(-1), 3)])
+    rel = engine.Relation.from_host(th)
+    out = engine.Relation.create(rel.schema, n)
+    try:
+        offs = engine.range_partition(rel, 0, mn, width, n_parts, out)
+        got = out.to_host("p")
+        assert offs[0] == 0 and offs[-1] == n and (np.diff(offs.astype(np.int64)) >= 0).all()
+        expect_part = np.clip((keys - mn) // width, 0, n_parts - 1)
+        assert (np.bincount(expect_part, minlength=n_parts) == np.diff(offs.astype(np.int64))).all()
+        gk = got.columns[0].data
+        for p in range(n_parts):
+            seg = gk[int(offs[p]):int(offs[p + 1])]
+            assert (np.clip((seg - mn) // width, 0, n_parts - 1) == p).all()
+        assert table_rows(got) == table_rows(th)
+    finally:
+        out.destroy(); rel.destroy()
+
+
 # ------------------------------------------------------------- K0 staging
 def test_stage_block_decoders(engine, oracle):
     """Compressed-column-store codes (dictionary / truncation) and SplitRowStore slots decode to the

@@ -33,9 +33,13 @@ ap.add_argument("--build-rows", type=int, default=1 << 26)
 ap.add_argument("--probe-rows", type=int, default=1 << 30)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--radix", type=int, default=0, help="radix join: range-partition both sides into this many key ranges "
+                "so that every probe partition's slice of the dense table and of the build relation fits in L2 (implies --dense)")
 ap.add_argument("--dense", action="store_true", help="dense (collision-free vector style) join table over the key range")
 args = ap.parse_args()
 
+if args.radix:
+    args.dense = True
 sys.stdout.flush()
 real_stdout = os.dup(1)
 os.dup2(2, 1)
@@ -90,6 +94,11 @@ if world > 1:
     recv_b, recv_p = [buf(cap_b), buf(cap_b)], [buf(cap_p)]
 out_cap = cap_p if world > 1 else npr
 out_rel = E.Relation.create([LONG], out_cap, dev=local)
+if args.radix:
+    rcap_b, rcap_p = (cap_b, cap_p) if world > 1 else (nb, npr)
+    rad_b, rad_p = [buf(rcap_b), buf(rcap_b)], [buf(rcap_p)]
+    rad_b_rel, rad_p_rel = wrap(rad_b, rcap_b), wrap(rad_p, rcap_p)
+    part_width = -(-B // args.radix)
 
 
 def ev():
@@ -129,20 +138,33 @@ def step():
         lb, lp = wrap(recv_b, n_b), wrap(recv_p, n_p)
     else:
         lb, lp, n_b, n_p = build_rel, probe_rel, nb, npr
+    ranges = [(0, A.UINT64_MAX)]
+    if args.radix:
+        # radix join: both sides regrouped by key range; partition p of the probe side only touches slice p of
+        # the dense table (heads) and rows of partition p of the build relation -> L2-resident random accesses
+        w2 = time.perf_counter()
+        E.range_partition(lb, 0, 0, part_width, args.radix, rad_b_rel)
+        offs = E.range_partition(lp, 0, 0, part_width, args.radix, rad_p_rel)
+        E.synchronize(local)
+        t["radix_partition_ms"] = (time.perf_counter() - w2) * 1e3
+        lb, lp = rad_b_rel, rad_p_rel
+        ranges = [(int(offs[i]), int(offs[i + 1])) for i in range(args.radix) if offs[i + 1] > offs[i]]
     E.set_timing(True)
     jt = E.JoinTable(A.QS_LONG, max(n_b, 1024), dev=local, dense_range=(0, B - 1) if args.dense else None)
     jt.build(lb, None, -1, 0)
     t["build_ms"] = E.last_kernel_ms(A.QS_K_JOIN_BUILD)
     A.check(A.load().qsgpu_relation_set_num_rows(out_rel.h, 0))
-    jt.probe(lp, es, -1, 0, A.QS_JOIN_INNER, -1, proj, out_rel)
-    t["probe_ms"] = E.last_kernel_ms(A.QS_K_JOIN_PROBE)
+    t["probe_ms"] = 0.0
+    for lo, hi in ranges:
+        jt.probe(lp, es, -1, 0, A.QS_JOIN_INNER, -1, proj, out_rel, row_begin=lo, row_end=hi)
+        t["probe_ms"] += E.last_kernel_ms(A.QS_K_JOIN_PROBE)
     E.set_timing(False)
     st = E.AggState(A.QS_AGG_SINGLE_STATE, es_sum, -1, [(A.QS_AGG_SUM, sum_arg), (A.QS_AGG_COUNT, -1)], [], dev=local)
     st.run(out_rel)
     fin, _ = E.finalize_relation(st, [], [LONG, LONG])
     total, count = int(fin.read(0)[0]), int(fin.read(1)[0])
     fin.destroy(); st.destroy(); jt.destroy()
-    if world > 1:
+    if world > 1 and not args.radix:
         lb.destroy(); lp.destroy()
     t["total_ms"] = (time.perf_counter() - w0) * 1e3
     t["n_build"], t["n_probe"] = n_b, n_p
@@ -156,7 +178,7 @@ for i in range(args.warmup + args.steps):
         res = t if res is None else {k: (res[k] + v) for k, v in t.items()}
 res = {k: v / args.steps for k, v in res.items()}
 chk = torch.tensor([total, count, expected_local, npr], dtype=torch.int64, device=dev)
-tm = torch.tensor([res.get("partition_ms", 0.0), res.get("exchange_ms", 0.0), res["build_ms"], res["probe_ms"], res["total_ms"]],
+tm = torch.tensor([res.get("partition_ms", 0.0) + res.get("radix_partition_ms", 0.0), res.get("exchange_ms", 0.0), res["build_ms"], res["probe_ms"], res["total_ms"]],
                   dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(chk, op=dist.ReduceOp.SUM)
@@ -170,6 +192,7 @@ if rank == 0:
     line = {"metric": "hash_join_microbench_ms", "value": tot, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "config": {"workload": f"{B} build rows x {P} probe rows, int64 keys, payload int64, 100% hit",
                        "join_table": "dense heads[key-min] + next[row] chains" if args.dense else "open addressing, 16 B slots, load factor <= 0.5",
+                       "radix_partitions": args.radix,
                        "build_rows_per_gpu": nb, "probe_rows_per_gpu": npr},
             "rows_per_s": (B + P) / (tot * 1e-3),
             "phases_ms": {"partition": part, "exchange": exch, "build": build, "probe": probe},
