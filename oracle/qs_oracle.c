@@ -986,5 +986,5 @@ uint32_t qso_partition_of(int64_t key, uint32_t n_parts) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
   x ^= x >> 31;
-  return (uint32_t)(x % n_parts);
+  return (uint32_t)(((x >> 32) * (uint64_t)n_parts) >> 32);   /* multiply-shift range reduction of the high word */
 }

@@ -31,6 +31,7 @@ struct PartDesc {
   uint32_t range_mode;           // 0: mix64(key) % n_parts;  1: (key - min_key) / part_width (clamped)
   int64_t min_key;
   uint64_t part_width;
+  uint32_t width_shift;          // log2(part_width) when it is a power of two, else 64
   uint64_t n_rows;
   unsigned long long *hist;      // [n_parts]
   unsigned long long *cursor;    // [n_parts] absolute write positions
@@ -40,12 +41,16 @@ __device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
   const int64_t k = static_cast<int64_t>(load_native(D.key + row * native_width(D.key_ltype), D.key_ltype));
   if (D.range_mode) {
     // key-range partitions: partition p holds keys [min + p*width, min + (p+1)*width), so the slice of a
-    // dense join table (and of the range-partitioned build relation) one partition touches is contiguous
+    // dense join table (and of the range-partitioned build relation) one partition touches is contiguous.
+    // A power-of-two width is a shift; any other width pays a 64-bit division per row (~100 instructions,
+    // which made the two partition passes of the 1 Gi-row microbench cost more than their memory traffic).
     if (k < D.min_key) return 0u;
-    const uint64_t p = static_cast<uint64_t>(k - D.min_key) / D.part_width;
+    const uint64_t off = static_cast<uint64_t>(k - D.min_key);
+    const uint64_t p = D.width_shift < 64 ? off >> D.width_shift : off / D.part_width;
     return p >= D.n_parts ? D.n_parts - 1 : static_cast<uint32_t>(p);
   }
-  return static_cast<uint32_t>(mix64(static_cast<uint64_t>(k)) % D.n_parts);
+  // multiply-shift range reduction of the hash's high word: uniform, and no 64-bit modulo per row
+  return __umulhi(static_cast<uint32_t>(mix64(static_cast<uint64_t>(k)) >> 32), D.n_parts);
 }
 
 __global__ void __launch_bounds__(kBlock) k_part_hist(const __grid_constant__ PartDesc D) {
@@ -60,40 +65,84 @@ __global__ void __launch_bounds__(kBlock) k_part_hist(const __grid_constant__ Pa
     if (s_hist[p]) atomicAdd(&D.hist[p], static_cast<unsigned long long>(s_hist[p]));
 }
 
-__global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__ PartDesc D) {
-  extern __shared__ unsigned int s_mem[];
-  unsigned int *s_count = s_mem;                                            // [n_parts]
-  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_mem + ((D.n_parts + 1) & ~1u));
-  const uint64_t n_tiles = (D.n_rows + kTileRows - 1) / kTileRows;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+// Scatter: a CTA takes kPartRows rows per thread (2048 rows per step), counts them per partition in shared
+// memory, reserves one contiguous output range per partition with ONE global atomic each, then moves the
+// step's rows column by column THROUGH shared memory: values are first placed in partition order in a
+// 32 KB buffer, and consecutive threads then copy consecutive buffer elements, i.e. consecutive output
+// addresses of one partition.  Writing straight from registers made every warp store touch up to 32
+// partitions (32 sectors per instruction): 19.6 ms per 1 Gi 8-byte rows for 32 partitions, growing with the
+// partition count (r01o).
+// 8 rows per thread and (partition, rank) packed in one register: the kernel is latency-bound (global loads,
+// the cursor reservation), so it needs many resident CTAs; the first version held 16 rows' partition and rank
+// in 128 registers, ran 2 CTAs per SM and spent 79 % of its issue slots with no eligible warp (r01p ncu).
+constexpr int kPartRows = 8;
+constexpr uint32_t kPartStep = kBlock * kPartRows;            // 2048 rows per CTA step
+__global__ void __launch_bounds__(kBlock, 6) k_part_scatter(const __grid_constant__ PartDesc D) {
+  extern __shared__ __align__(16) unsigned char s_part_raw[];
+  uint64_t *s_buf = reinterpret_cast<uint64_t *>(s_part_raw);                               // [kPartStep] staged values
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_part_raw + kPartStep * 8);   // [n_parts] global start
+  unsigned int *s_count = reinterpret_cast<unsigned int *>(s_base + D.n_parts);             // [n_parts]
+  unsigned int *s_off = s_count + D.n_parts;                                                // [n_parts + 1] start inside the step
+  unsigned short *s_pid = reinterpret_cast<unsigned short *>(s_off + D.n_parts + 1);        // [kPartStep] partition of each staged element
+  const uint64_t n_steps = (D.n_rows + kPartStep - 1) / kPartStep;
+  for (uint64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
     for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x) s_count[p] = 0;
     __syncthreads();
-    uint32_t part[kRows], rank[kRows];
+    const uint64_t row0 = step * kPartStep;
+    const uint32_t n_here = static_cast<uint32_t>(min(static_cast<uint64_t>(kPartStep), D.n_rows - row0));
+    uint32_t pr[kPartRows];                 // partition << 16 | rank inside the step's share of it; ~0 = no row
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const uint64_t row = tile * kTileRows + tile_row(r, threadIdx.x);
-      part[r] = 0xffffffffu;
-      if (row < D.n_rows) {
-        part[r] = part_of(D, row);
-        rank[r] = atomicAdd(&s_count[part[r]], 1u);
-      }
+    for (int r = 0; r < kPartRows; ++r) {
+      const uint32_t i = static_cast<uint32_t>(r) * kBlock + threadIdx.x;
+      pr[r] = i < n_here ? part_of(D, row0 + i) : 0xffffffffu;
     }
+#pragma unroll
+    for (int r = 0; r < kPartRows; ++r)
+      if (pr[r] != 0xffffffffu) pr[r] = (pr[r] << 16) | atomicAdd(&s_count[pr[r]], 1u);
     __syncthreads();
+    if (threadIdx.x == 0) {          // exclusive scan of the per-partition counts (n_parts <= 1024)
+      unsigned int acc = 0;
+      for (uint32_t p = 0; p < D.n_parts; ++p) { s_off[p] = acc; acc += s_count[p]; }
+      s_off[D.n_parts] = acc;
+    }
     for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x)
       s_base[p] = s_count[p] ? atomicAdd(&D.cursor[p], static_cast<unsigned long long>(s_count[p])) : 0ull;
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      if (part[r] == 0xffffffffu) continue;
-      const uint64_t row = tile * kTileRows + tile_row(r, threadIdx.x);
-      const uint64_t dst = s_base[part[r]] + rank[r];
-      for (uint32_t c = 0; c < D.n_cols; ++c) {
-        const uint32_t w = D.in[c].width;
-        const char *src = D.in[c].ptr + row * w;
-        char *o = D.out[c] + dst * w;
-        if (w == 8) *reinterpret_cast<uint64_t *>(o) = *reinterpret_cast<const uint64_t *>(src);
-        else if (w == 4) *reinterpret_cast<uint32_t *>(o) = *reinterpret_cast<const uint32_t *>(src);
-        else for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+    for (int r = 0; r < kPartRows; ++r)
+      if (pr[r] != 0xffffffffu) s_pid[s_off[pr[r] >> 16] + (pr[r] & 0xffffu)] = static_cast<unsigned short>(pr[r] >> 16);
+    for (uint32_t c = 0; c < D.n_cols; ++c) {
+      const uint32_t w = D.in[c].width;
+      if (w == 8 || w == 4) {
+        // place in partition order ...
+#pragma unroll
+        for (int r = 0; r < kPartRows; ++r) {
+          if (pr[r] == 0xffffffffu) continue;
+          const uint64_t row = row0 + static_cast<uint32_t>(r) * kBlock + threadIdx.x;
+          const uint32_t pos = s_off[pr[r] >> 16] + (pr[r] & 0xffffu);
+          if (w == 8) s_buf[pos] = *reinterpret_cast<const uint64_t *>(D.in[c].ptr + row * 8);
+          else reinterpret_cast<uint32_t *>(s_buf)[pos] = *reinterpret_cast<const uint32_t *>(D.in[c].ptr + row * 4);
+        }
+        __syncthreads();
+        // ... and copy out: element i of the buffer belongs to the partition whose [s_off[p], s_off[p+1]) holds i
+        for (uint32_t i = threadIdx.x; i < n_here; i += kBlock) {
+          const uint32_t lo = s_pid[i];
+          const uint64_t dst = s_base[lo] + (i - s_off[lo]);
+          if (w == 8) *reinterpret_cast<uint64_t *>(D.out[c] + dst * 8) = s_buf[i];
+          else *reinterpret_cast<uint32_t *>(D.out[c] + dst * 4) = reinterpret_cast<const uint32_t *>(s_buf)[i];
+        }
+        __syncthreads();
+      } else {
+        // odd widths (CHAR(n)): straight from global to global
+#pragma unroll
+        for (int r = 0; r < kPartRows; ++r) {
+          if (pr[r] == 0xffffffffu) continue;
+          const uint64_t row = row0 + static_cast<uint32_t>(r) * kBlock + threadIdx.x;
+          const uint64_t dst = s_base[pr[r] >> 16] + (pr[r] & 0xffffu);
+          const char *src = D.in[c].ptr + row * w;
+          char *o = D.out[c] + dst * w;
+          for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+        }
       }
     }
     __syncthreads();
@@ -280,6 +329,8 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   D.range_mode = range_mode;
   D.min_key = min_key;
   D.part_width = part_width;
+  D.width_shift = 64;
+  if ((part_width & (part_width - 1)) == 0) { D.width_shift = 0; while ((1ull << D.width_shift) < part_width) ++D.width_shift; }
   D.n_rows = n;
   unsigned long long *d_buf = nullptr;
   QS_CUDA(dev_malloc(&d_buf, 2ull * n_parts * 8 + 64));
@@ -301,7 +352,7 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
     host_offsets[n_parts] = acc;
     e = cudaMemcpyAsync(D.cursor, cur.data(), n_parts * 8, cudaMemcpyHostToDevice, d->stream);
     if (e != cudaSuccess) { dev_free(d_buf); return cuda_fail(e, "partition cursors"); }
-    const size_t smem = ((n_parts + 1) & ~1u) * 4 + n_parts * 8;
+    const size_t smem = static_cast<size_t>(kPartStep) * 8 + n_parts * 8 + (2 * n_parts + 2) * 4 + kPartStep * 2 + 16;
     k_part_scatter<<<grid, kBlock, smem, d->stream>>>(D);
     count_launch(2);
     if (on) {

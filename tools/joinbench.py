@@ -98,7 +98,7 @@ if args.radix:
     rcap_b, rcap_p = (cap_b, cap_p) if world > 1 else (nb, npr)
     rad_b, rad_p = [buf(rcap_b), buf(rcap_b)], [buf(rcap_p)]
     rad_b_rel, rad_p_rel = wrap(rad_b, rcap_b), wrap(rad_p, rcap_p)
-    part_width = -(-B // args.radix)
+    part_width = 1 << max(0, (-(-B // args.radix) - 1).bit_length())     # power of two: the partition id is a shift
 
 
 def ev():
