@@ -440,6 +440,29 @@ int qsgpu_range_partition(qsgpu_relation_t input, uint32_t key_attr, int64_t min
                           uint64_t part_width, uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets);
 
+/*
+ * K8 fused with the all-to-all that follows it (one process per GPU, peers mapped over NVLink with CUDA IPC):
+ *   1. every rank counts its rows per destination      qsgpu_partition_count      (partition id = hash, as above)
+ *   2. the ranks exchange the counts (a few words) and derive, for every destination, the first row each
+ *      sender writes at (exclusive prefix over the senders)
+ *   3. every rank scatters its rows STRAIGHT INTO the destinations' receive relations
+ *                                                      qsgpu_partition_scatter_peers
+ *      peer_cols[p * n_attrs + a] = device address of attribute a of destination p's receive relation (the
+ *      local one for p == own rank, an IPC mapping otherwise); rows of destination p start at first_rows[p].
+ *   4. a barrier across ranks; the receive relations then hold the shuffled rows.
+ * The partition kernel IS the transfer: no send buffers, no separate collective, NVLink traffic overlapped with
+ * the partitioning itself.  qsgpu_ipc_* give device memory other processes can map.
+ */
+typedef struct qs_ipc_handle { unsigned char bytes[64]; } qs_ipc_handle;
+int qsgpu_ipc_alloc(int dev, size_t bytes, void **dptr, qs_ipc_handle *handle);
+int qsgpu_ipc_open(int dev, const qs_ipc_handle *handle, void **dptr);
+int qsgpu_ipc_close(int dev, void *dptr);
+int qsgpu_ipc_free(int dev, void *dptr);
+int qsgpu_partition_count(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts,
+                          uint64_t *host_counts);
+int qsgpu_partition_scatter_peers(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts,
+                                  void *const *peer_cols, const uint64_t *first_rows);
+
 /* ---------------------------------------------------------- instrumentation */
 /* CUDA-event time (ms) of the most recent kernel of the given family launched
  * by the calling thread's last call, for bench.py's roofline block. */

@@ -68,6 +68,10 @@ class qs_block_image(C.Structure):
                 ("descs", C.POINTER(qs_stage_desc))]
 
 
+class qs_ipc_handle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 class qs_lip_ref(C.Structure):
     _fields_ = [("lip", C.c_void_p), ("attr", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -156,6 +160,12 @@ SIGNATURES = {
     "qsgpu_topk": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_sort_key), C.c_uint64, _VPP]),
     "qsgpu_radix_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
     "qsgpu_range_partition": (C.c_int, [_VP, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, _VP, _U64P]),
+    "qsgpu_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, _VPP, C.POINTER(qs_ipc_handle)]),
+    "qsgpu_ipc_open": (C.c_int, [C.c_int, C.POINTER(qs_ipc_handle), _VPP]),
+    "qsgpu_ipc_close": (C.c_int, [C.c_int, _VP]),
+    "qsgpu_ipc_free": (C.c_int, [C.c_int, _VP]),
+    "qsgpu_partition_count": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _U64P]),
+    "qsgpu_partition_scatter_peers": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VPP, _U64P]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),

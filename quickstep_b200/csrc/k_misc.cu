@@ -12,6 +12,7 @@
 //       radix-select the k-th primary sort key, gather the <= k + ties
 //       candidates, sort them with the full multi-attribute comparator in one CTA.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "qs_host.h"
@@ -35,6 +36,9 @@ struct PartDesc {
   uint64_t n_rows;
   unsigned long long *hist;      // [n_parts]
   unsigned long long *cursor;    // [n_parts] absolute write positions
+  // Fused partition + all-to-all: when set, partition p's rows go to out_table[p * n_cols + c], which may be
+  // the receive relation of ANOTHER GPU mapped over NVLink (CUDA IPC), at the rows reserved from cursor[p].
+  char *const *out_table;
 };
 
 __device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
@@ -128,8 +132,9 @@ __global__ void __launch_bounds__(kBlock, 6) k_part_scatter(const __grid_constan
         for (uint32_t i = threadIdx.x; i < n_here; i += kBlock) {
           const uint32_t lo = s_pid[i];
           const uint64_t dst = s_base[lo] + (i - s_off[lo]);
-          if (w == 8) *reinterpret_cast<uint64_t *>(D.out[c] + dst * 8) = s_buf[i];
-          else *reinterpret_cast<uint32_t *>(D.out[c] + dst * 4) = reinterpret_cast<const uint32_t *>(s_buf)[i];
+          char *ob = D.out_table ? D.out_table[lo * D.n_cols + c] : D.out[c];
+          if (w == 8) *reinterpret_cast<uint64_t *>(ob + dst * 8) = s_buf[i];
+          else *reinterpret_cast<uint32_t *>(ob + dst * 4) = reinterpret_cast<const uint32_t *>(s_buf)[i];
         }
         __syncthreads();
       } else {
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_part_scatter(const __grid_constan
           const uint64_t row = row0 + static_cast<uint32_t>(r) * kBlock + threadIdx.x;
           const uint64_t dst = s_base[pr[r] >> 16] + (pr[r] & 0xffffu);
           const char *src = D.in[c].ptr + row * w;
-          char *o = D.out[c] + dst * w;
+          char *o = (D.out_table ? D.out_table[(pr[r] >> 16) * D.n_cols + c] : D.out[c]) + dst * w;
           for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
         }
       }
@@ -367,6 +372,122 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
     if (e != cudaSuccess) return cuda_fail(e, "partition scatter");
   }
   return qsgpu_relation_set_num_rows(output, n);
+}
+
+// ---- K8 fused with the exchange: count, then scatter straight into the peers' receive relations
+static int fill_part_desc(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, PartDesc *D, uint64_t *n_rows) {
+  int st = qsgpu_relation_num_rows(input, n_rows);
+  if (st) return st;
+  if (n_parts == 0 || n_parts > 1024 || key_attr >= input->attrs.size() || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
+    set_error(QSGPU_ERR_INVALID, "bad partition arguments");
+    return QSGPU_ERR_INVALID;
+  }
+  const uint8_t lt = vtype_of(input->attrs[key_attr].type);
+  if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "partition key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  D->n_cols = static_cast<uint32_t>(input->attrs.size());
+  for (uint32_t c = 0; c < D->n_cols; ++c) { D->in[c].ptr = input->cols[c]; D->in[c].width = input->attrs[c].width; }
+  D->key = input->cols[key_attr];
+  D->key_ltype = lt;
+  D->n_parts = n_parts;
+  D->part_width = 1;
+  D->width_shift = 0;
+  D->n_rows = *n_rows;
+  return QSGPU_OK;
+}
+
+int qsgpu_partition_count(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, uint64_t *host_counts) {
+  Device *d = device(input->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  PartDesc D{};
+  uint64_t n = 0;
+  int st = fill_part_desc(input, key_attr, n_parts, &D, &n);
+  if (st) return st;
+  unsigned long long *d_hist = nullptr;
+  QS_CUDA(dev_malloc(&d_hist, n_parts * 8 + 64));
+  QS_CUDA(cudaMemsetAsync(d_hist, 0, n_parts * 8, d->stream));
+  D.hist = d_hist;
+  k_part_hist<<<std::min(grid_for(n), d->sm_count * 8), kBlock, n_parts * 4, d->stream>>>(D);
+  count_launch();
+  std::vector<unsigned long long> h(n_parts);
+  cudaError_t e = cudaMemcpyAsync(h.data(), d_hist, n_parts * 8, cudaMemcpyDeviceToHost, d->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  dev_free(d_hist);
+  if (e != cudaSuccess) return cuda_fail(e, "partition count");
+  for (uint32_t p = 0; p < n_parts; ++p) host_counts[p] = h[p];
+  return QSGPU_OK;
+}
+
+int qsgpu_partition_scatter_peers(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, void *const *peer_cols,
+                                  const uint64_t *first_rows) {
+  Device *d = device(input->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  PartDesc D{};
+  uint64_t n = 0;
+  int st = fill_part_desc(input, key_attr, n_parts, &D, &n);
+  if (st) return st;
+  if (!peer_cols || !first_rows) { set_error(QSGPU_ERR_INVALID, "scatter to peers needs the destination columns and first rows"); return QSGPU_ERR_INVALID; }
+  const size_t n_ptrs = static_cast<size_t>(n_parts) * D.n_cols;
+  char *d_buf = nullptr;
+  QS_CUDA(dev_malloc(&d_buf, n_parts * 8 + n_ptrs * 8 + 64));
+  D.cursor = reinterpret_cast<unsigned long long *>(d_buf);
+  D.out_table = reinterpret_cast<char *const *>(d_buf + n_parts * 8);
+  cudaError_t e = cudaMemcpyAsync(d_buf, first_rows, n_parts * 8, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_buf + n_parts * 8, peer_cols, n_ptrs * 8, cudaMemcpyHostToDevice, d->stream);
+  if (e != cudaSuccess) { dev_free(d_buf); return cuda_fail(e, "scatter to peers: descriptors"); }
+  const bool on = timing_enabled();
+  if (on) cudaEventRecord(d->ev0, d->stream);
+  const size_t smem = static_cast<size_t>(kPartStep) * 8 + n_parts * 8 + (2 * n_parts + 2) * 4 + kPartStep * 2 + 16;
+  k_part_scatter<<<std::min(grid_for(n), d->sm_count * 8), kBlock, smem, d->stream>>>(D);
+  count_launch();
+  if (on) {
+    cudaEventRecord(d->ev1, d->stream);
+    cudaEventSynchronize(d->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+    record_ms(QS_K_PARTITION, ms);
+  }
+  e = cudaStreamSynchronize(d->stream);       // the caller's barrier across ranks follows
+  dev_free(d_buf);
+  if (e != cudaSuccess) return cuda_fail(e, "scatter to peers");
+  return QSGPU_OK;
+}
+
+// ---- device memory other processes can map (CUDA IPC): the receive relations of the fused exchange
+int qsgpu_ipc_alloc(int dev, size_t bytes, void **dptr, qs_ipc_handle *handle) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaMalloc(dptr, bytes ? bytes : 256));          // not from the pool: IPC handles need their own allocation
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(qs_ipc_handle), "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+  if (e != cudaSuccess) { cudaFree(*dptr); *dptr = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  std::memset(handle, 0, sizeof(*handle));
+  std::memcpy(handle, &h, sizeof(h));
+  return QSGPU_OK;
+}
+
+int qsgpu_ipc_open(int dev, const qs_ipc_handle *handle, void **dptr) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  QS_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return QSGPU_OK;
+}
+
+int qsgpu_ipc_close(int dev, void *dptr) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaIpcCloseMemHandle(dptr));
+  return QSGPU_OK;
+}
+
+int qsgpu_ipc_free(int dev, void *dptr) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  QS_CUDA(cudaFree(dptr));
+  return QSGPU_OK;
 }
 
 int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys, uint64_t limit,

@@ -428,6 +428,43 @@ def topk(rel: Relation, keys, limit) -> Relation:
     return Relation(out, rel.schema, rel.names, rel.dev)
 
 
+def ipc_alloc(nbytes: int, dev=0):
+    """Device memory other processes can map -> (device pointer, 64-byte handle as bytes)."""
+    p, h = C.c_void_p(), A.qs_ipc_handle()
+    A.check(A.load().qsgpu_ipc_alloc(dev, nbytes, C.byref(p), C.byref(h)))
+    return p.value, bytes(h.bytes)
+
+
+def ipc_open(handle: bytes, dev=0) -> int:
+    h = A.qs_ipc_handle()
+    C.memmove(C.byref(h), handle, 64)
+    p = C.c_void_p()
+    A.check(A.load().qsgpu_ipc_open(dev, C.byref(h), C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int, dev=0):
+    A.check(A.load().qsgpu_ipc_close(dev, ptr))
+
+
+def ipc_free(ptr: int, dev=0):
+    A.check(A.load().qsgpu_ipc_free(dev, ptr))
+
+
+def partition_count(rel: Relation, key_attr, n_parts) -> np.ndarray:
+    counts = np.zeros(n_parts, dtype=np.uint64)
+    A.check(A.load().qsgpu_partition_count(rel.h, key_attr, n_parts, counts.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return counts
+
+
+def partition_scatter_peers(rel: Relation, key_attr, n_parts, peer_cols, first_rows):
+    """peer_cols: [n_parts][n_attrs] device addresses (own or IPC-mapped); first_rows: [n_parts]."""
+    flat = [p for row in peer_cols for p in row]
+    ptrs = (C.c_void_p * len(flat))(*flat)
+    fr = np.ascontiguousarray(first_rows, dtype=np.uint64)
+    A.check(A.load().qsgpu_partition_scatter_peers(rel.h, key_attr, n_parts, ptrs, fr.ctypes.data_as(C.POINTER(C.c_uint64))))
+
+
 def range_partition(rel: Relation, key_attr, min_key, part_width, n_parts, output: Relation) -> np.ndarray:
     offs = np.zeros(n_parts + 1, dtype=np.uint64)
     A.check(A.load().qsgpu_range_partition(rel.h, key_attr, min_key, part_width, n_parts, output.h,

@@ -35,6 +35,8 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--radix", type=int, default=0, help="radix join: range-partition both sides into this many key ranges "
                 "so that every probe partition's slice of the dense table and of the build relation fits in L2 (implies --dense)")
+ap.add_argument("--fused", action="store_true", help="N > 1: the partition kernel writes straight into the peers' receive "
+                "relations over NVLink (CUDA IPC) instead of partition -> NCCL all-to-all")
 ap.add_argument("--dense", action="store_true", help="dense (collision-free vector style) join table over the key range")
 args = ap.parse_args()
 
@@ -88,7 +90,17 @@ es_sum = ExprSet()
 sum_arg = es_sum.attr(0, A.QS_LONG, 8)
 slack = 1.0 if world == 1 else 1.02            # hash partitions are balanced to well under 2 %
 cap_b, cap_p = int(nb * slack) + 4096, int(npr * slack) + 4096
-if world > 1:
+ipc = None
+if world > 1 and args.fused:
+    # receive relations in IPC-exportable memory; every rank maps every other rank's columns
+    mine = [E.ipc_alloc((cap_b + PAD) * 8, local), E.ipc_alloc((cap_b + PAD) * 8, local), E.ipc_alloc((cap_p + PAD) * 8, local)]
+    handles = [None] * world
+    dist.all_gather_object(handles, [h for (_p, h) in mine])
+    peer = [[(mine[c][0] if r == rank else E.ipc_open(handles[r][c], local)) for c in range(3)] for r in range(world)]
+    ipc = dict(mine=[p for (p, _h) in mine], peer=peer)
+    recv_b_rel = E.Relation.wrap([LONG, LONG], ipc["mine"][:2], cap_b, dev=local)
+    recv_p_rel = E.Relation.wrap([LONG], ipc["mine"][2:], cap_p, dev=local)
+elif world > 1:
     part_b, part_p = [buf(nb), buf(nb)], [buf(npr)]
     part_b_rel, part_p_rel = wrap(part_b, nb), wrap(part_p, npr)
     recv_b, recv_p = [buf(cap_b), buf(cap_b)], [buf(cap_p)]
@@ -110,7 +122,33 @@ def step():
     t = {}
     E.synchronize(local); torch.cuda.synchronize()
     w0 = time.perf_counter()
-    if world > 1:
+    if world > 1 and args.fused:
+        # 1. counts per destination, 2. exchange them, 3. scatter straight into the peers, 4. barrier
+        cb, cp = E.partition_count(build_rel, 0, world), E.partition_count(probe_rel, 0, world)
+        t["partition_ms"] = (time.perf_counter() - w0) * 1e3
+        w1 = time.perf_counter()
+        send = torch.tensor([[int(cb[i]), int(cp[i])] for i in range(world)], dtype=torch.int64, device=dev)
+        allc = torch.zeros(world, world, 2, dtype=torch.int64, device=dev)           # [sender][destination][side]
+        dist.all_gather_into_tensor(allc.view(-1), send.view(-1))
+        allc = allc.cpu()
+        first_b = [int(allc[:rank, p, 0].sum()) for p in range(world)]
+        first_p = [int(allc[:rank, p, 1].sum()) for p in range(world)]
+        n_b, n_p = int(allc[:, rank, 0].sum()), int(allc[:, rank, 1].sum())
+        assert n_b <= cap_b and n_p <= cap_p, (n_b, cap_b, n_p, cap_p)
+        E.set_timing(True)
+        E.partition_scatter_peers(build_rel, 0, world, [ipc["peer"][p][:2] for p in range(world)], first_b)
+        xb = E.last_kernel_ms(A.QS_K_PARTITION)
+        E.partition_scatter_peers(probe_rel, 0, world, [ipc["peer"][p][2:] for p in range(world)], first_p)
+        xp = E.last_kernel_ms(A.QS_K_PARTITION)
+        E.set_timing(False)
+        dist.barrier()
+        t["exchange_ms"] = xb + xp
+        t["exchange_wall_ms"] = (time.perf_counter() - w1) * 1e3
+        t["sent_bytes"] = 16 * (nb - int(cb[rank])) + 8 * (npr - int(cp[rank]))
+        A.check(A.load().qsgpu_relation_set_num_rows(recv_b_rel.h, n_b))
+        A.check(A.load().qsgpu_relation_set_num_rows(recv_p_rel.h, n_p))
+        lb, lp = recv_b_rel, recv_p_rel
+    elif world > 1:
         offs_b = E.radix_partition(build_rel, 0, world, part_b_rel)
         offs_p = E.radix_partition(probe_rel, 0, world, part_p_rel)
         E.synchronize(local)
@@ -164,7 +202,7 @@ def step():
     fin, _ = E.finalize_relation(st, [], [LONG, LONG])
     total, count = int(fin.read(0)[0]), int(fin.read(1)[0])
     fin.destroy(); st.destroy(); jt.destroy()
-    if world > 1 and not args.radix:
+    if world > 1 and not args.radix and not args.fused:
         lb.destroy(); lp.destroy()
     t["total_ms"] = (time.perf_counter() - w0) * 1e3
     t["n_build"], t["n_probe"] = n_b, n_p
@@ -193,6 +231,7 @@ if rank == 0:
             "config": {"workload": f"{B} build rows x {P} probe rows, int64 keys, payload int64, 100% hit",
                        "join_table": "dense heads[key-min] + next[row] chains" if args.dense else "open addressing, 16 B slots, load factor <= 0.5",
                        "radix_partitions": args.radix,
+                       "exchange": "none" if world == 1 else ("partition kernel writes into the peers' receive relations over NVLink (CUDA IPC)" if args.fused else "K8 partition, then NCCL all_to_all_single per column"),
                        "build_rows_per_gpu": nb, "probe_rows_per_gpu": npr},
             "rows_per_s": (B + P) / (tot * 1e-3),
             "phases_ms": {"partition": part, "exchange": exch, "build": build, "probe": probe},
@@ -204,4 +243,13 @@ if rank == 0:
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 if world > 1:
     dist.barrier()
+    if ipc:
+        for r in range(world):
+            if r != rank:
+                for p in ipc["peer"][r]:
+                    E.ipc_close(p, local)
+        dist.barrier()
+        recv_b_rel.destroy(); recv_p_rel.destroy()
+        for p in ipc["mine"]:
+            E.ipc_free(p, local)
     dist.destroy_process_group()
