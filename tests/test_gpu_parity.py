@@ -605,6 +605,47 @@ def test_radix_partition(engine, oracle, n_parts):
         out.destroy(); rel.destroy()
 
 
+def test_partition_scatter_to_destinations(engine, oracle):
+    """The fused partition + exchange path on one device: every "destination" is its own relation (in
+    IPC-exportable memory, as the receive relations of the multi-GPU join are), two senders write their
+    partitions at the first rows derived from the exchanged counts; each destination ends up with exactly the
+    rows whose key hashes to it."""
+    rng = np.random.default_rng(31)
+    n_parts, n = 3, 30000
+    senders = []
+    for sidx in range(2):
+        keys = rng.integers(-10**6, 10**6, size=n).astype(np.int64)
+        senders.append(HostTable(f"s{sidx}", [Column("k", A.QS_LONG, keys), Column("v", A.QS_LONG, keys * 7 + sidx)]))
+    rels = [engine.Relation.from_host(t) for t in senders]
+    counts = [engine.partition_count(r, 0, n_parts) for r in rels]
+    totals = [int(counts[0][p] + counts[1][p]) for p in range(n_parts)]
+    for sidx, t in enumerate(senders):
+        want = np.bincount([oracle.partition_of(int(k), n_parts) for k in t.columns[0].data[:2000]], minlength=n_parts)
+        got_prefix = engine.partition_count(engine.Relation.from_host(HostTable("p", [Column("k", A.QS_LONG, t.columns[0].data[:2000])])), 0, n_parts)
+        assert (want == got_prefix.astype(np.int64)).all()
+    bufs = [[engine.ipc_alloc((totals[p] + 64) * 8)[0] for _c in range(2)] for p in range(n_parts)]
+    dests = [engine.Relation.wrap([(A.QS_LONG, 8), (A.QS_LONG, 8)], bufs[p], totals[p]) for p in range(n_parts)]
+    try:
+        engine.partition_scatter_peers(rels[0], 0, n_parts, bufs, [0] * n_parts)
+        engine.partition_scatter_peers(rels[1], 0, n_parts, bufs, [int(c) for c in counts[0]])
+        allk = np.concatenate([t.columns[0].data for t in senders])
+        allv = np.concatenate([t.columns[1].data for t in senders])
+        part = np.array([oracle.partition_of(int(k), n_parts) for k in allk])
+        for p in range(n_parts):
+            got = dests[p].to_host("d")
+            exp = HostTable("e", [Column("k", A.QS_LONG, allk[part == p]), Column("v", A.QS_LONG, allv[part == p])])
+            assert got.n_rows == exp.n_rows == totals[p]
+            assert table_rows(got) == table_rows(exp)
+    finally:
+        for d in dests:
+            d.destroy()
+        for row in bufs:
+            for ptr in row:
+                engine.ipc_free(ptr)
+        for r in rels:
+            r.destroy()
+
+
 def test_range_partition(engine):
     """qsgpu_range_partition: partition p holds exactly the keys of [min + p*width, min + (p+1)*width) (clamped at
     both ends), partitions are contiguous and ordered, and the multiset of rows is unchanged."""
