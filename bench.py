@@ -402,7 +402,12 @@ def main():
             "query_wall_ms": {"q1": q1_wall, **{k: v[1] for k, v in results.items()}},
             "kernel_ms": {"q1_scan_agg": k_q1, "q6_scan_agg": k_q6},
             "hbm_frac": {"q1": roofline["frac"],
-                         "q6": (n * T.Q6_BYTES_PER_ROW / (k_q6 * 1e-3) / 1e9 / peak) if k_q6 else None},
+                         "q6": (n * T.Q6_BYTES_PER_ROW / (k_q6 * 1e-3) / 1e9 / peak) if k_q6 else None,
+                         # Q3 is a chain of ten operators: algorithmic input bytes of the three relations over
+                         # the WHOLE query's time (host round trips included), not one kernel
+                         "q3_whole_query": ((n * T.Q3_LINEITEM_BYTES_PER_ROW + stats["orders_rows"] * T.Q3_ORDERS_BYTES_PER_ROW +
+                                             stats["customer_rows"] * T.Q3_CUSTOMER_BYTES_PER_ROW) /
+                                            (results["q3"][0] * 1e-3) / 1e9 / peak) if "q3" in results else None},
             "operator_layer_ms": oplayer,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": q1_launches,
