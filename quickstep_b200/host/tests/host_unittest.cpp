@@ -1,0 +1,238 @@
+// Device-free unit tests of the host layer: expression-set plumbing and the scheduling contracts the GPU
+// operators rely on (the reference checks the same contracts with a MockOperator in
+// query_execution/tests/QueryManagerSingleNode_unittest.cpp).  Exit code 0 = all passed; prints one line per case.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "ExprSet.hpp"
+#include "QueryManager.hpp"
+#include "WorkOrder.hpp"
+
+using namespace quickstep;
+
+static int g_failed = 0;
+#define EXPECT(cond)                                                                  \
+  do {                                                                                \
+    if (!(cond)) { std::printf("  FAILED %s (%s:%d)\n", #cond, __FILE__, __LINE__); ++g_failed; } \
+  } while (0)
+
+// ------------------------------------------------------------------ ExprSet
+static void testExprSetAppend() {
+  const qs_attr kInt{QS_INT, 4}, kChar{QS_CHAR, 10}, kDouble{QS_DOUBLE, 8};
+  ExprSet pred;       // c_mktsegment = 'BUILDING' AND c_custkey > 5
+  const int p = pred.conj({pred.cmp(QS_EQ, pred.attr(1, kChar), pred.lit_char("BUILDING")),
+                           pred.cmp(QS_GT, pred.attr(0, kInt), pred.lit_int(5))});
+  ExprSet sel;        // a3 * (1 - b.a4), 'X'
+  const int s0 = sel.binary(QS_MUL, sel.attr(3, kDouble), sel.binary(QS_SUB, sel.lit_int(1), sel.attr(4, kDouble, 2)));
+  const int s1 = sel.lit_char("X");
+  ExprSet all;
+  const int off_p = all.append(pred), off_s = all.append(sel);
+  EXPECT(off_p == 0 && off_s == static_cast<int>(pred.size()));
+  const qs_expr_set v = all.view();
+  EXPECT(v.n_nodes == pred.size() + sel.size());
+  // children of appended nodes are rebased, attribute ids are not
+  const qs_node &mul = v.nodes[s0 + off_s];
+  EXPECT(mul.kind == QS_N_BINARY && mul.op == QS_MUL);
+  EXPECT(v.nodes[mul.a].kind == QS_N_ATTRIBUTE && v.nodes[mul.a].a == 3);
+  const qs_node &sub = v.nodes[mul.b];
+  EXPECT(sub.kind == QS_N_BINARY && sub.op == QS_SUB && v.nodes[sub.a].kind == QS_N_LITERAL && v.nodes[sub.b].a == 4 && v.nodes[sub.b].b == 2);
+  // CHAR literals keep pointing at their own bytes in the merged pool
+  const qs_node &x = v.nodes[s1 + off_s];
+  EXPECT(x.kind == QS_N_LITERAL && x.type == QS_CHAR && x.width == 1 && v.str_pool[x.lit.pool_offset] == 'X');
+  const qs_node &conj = v.nodes[p + off_p];
+  EXPECT(conj.kind == QS_N_CONJUNCTION);
+  const qs_node &eq = v.nodes[conj.a];
+  EXPECT(eq.kind == QS_N_COMPARISON && std::strncmp(v.str_pool + v.nodes[eq.b].lit.pool_offset, "BUILDING", 8) == 0);
+  // attribute masks per join side
+  EXPECT(pred.referencedAttributes(0) == 0b11 && pred.referencedAttributes(2) == 0);
+  EXPECT(sel.referencedAttributes(0) == (1ull << 3) && sel.referencedAttributes(2) == (1ull << 4));
+  EXPECT(all.referencedAttributes(0) == (0b11 | (1ull << 3)));
+  std::printf("expr_set_append ok\n");
+}
+
+// ------------------------------------------------------------- scheduling
+struct Trace {
+  std::mutex mu;
+  std::vector<std::string> events;            // "<op>:<what>"
+  void add(const std::string &e) { std::lock_guard<std::mutex> lk(mu); events.push_back(e); }
+  int index(const std::string &e) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (std::size_t i = 0; i < events.size(); ++i) if (events[i] == e) return static_cast<int>(i);
+    return -1;
+  }
+  int count(const std::string &prefix) {
+    std::lock_guard<std::mutex> lk(mu);
+    int n = 0;
+    for (const auto &e : events) n += e.rfind(prefix, 0) == 0;
+    return n;
+  }
+};
+
+class MockWorkOrder : public WorkOrder {
+ public:
+  MockWorkOrder(Trace *t, std::string tag, std::atomic<int> *running, std::atomic<int> *max_running)
+      : WorkOrder(1), trace_(t), tag_(std::move(tag)), running_(running), max_running_(max_running) {}
+  void execute() override {
+    const int now = ++*running_;
+    int seen = max_running_->load();
+    while (now > seen && !max_running_->compare_exchange_weak(seen, now)) {}
+    trace_->add(tag_);
+    --*running_;
+  }
+ private:
+  Trace *trace_;
+  std::string tag_;
+  std::atomic<int> *running_, *max_running_;
+};
+
+// Emits `own_work_orders` work orders on its first call (a stored input) plus one per block it is fed (a
+// streamed input); with a streamed input it is done only after doneFeedingInputBlocks.
+class MockOperator : public RelationalOperator {
+ public:
+  MockOperator(std::string name, Trace *t, int own_work_orders, bool has_streamed_input, relation_id output_rel,
+               std::atomic<int> *running, std::atomic<int> *max_running)
+      : RelationalOperator(1), name_(std::move(name)), trace_(t), own_(own_work_orders), streamed_(has_streamed_input),
+        output_rel_(output_rel), running_(running), max_running_(max_running) {}
+  OperatorType getOperatorType() const override { return kSelect; }
+  std::string getName() const override { return name_; }
+  bool getAllWorkOrders(WorkOrdersContainer *container, QueryContext *, StorageManager *, const tmb::client_id, tmb::MessageBus *) override {
+    ++calls_;
+    trace_->add(name_ + ":generate");
+    if (!started_) {
+      started_ = true;
+      for (int i = 0; i < own_; ++i)
+        container->addNormalWorkOrder(new MockWorkOrder(trace_, name_ + ":wo", running_, max_running_), getOperatorIndex());
+    }
+    for (block_id b : fed_) {
+      (void)b;
+      container->addNormalWorkOrder(new MockWorkOrder(trace_, name_ + ":wo_fed", running_, max_running_), getOperatorIndex());
+    }
+    fed_.clear();
+    return streamed_ ? done_feeding_input_relation_ : true;
+  }
+  void feedInputBlock(const block_id b, const relation_id rel, const partition_id) override {
+    trace_->add(name_ + ":fed");
+    fed_rel_ = rel;
+    fed_.push_back(b);
+  }
+  void doneFeedingInputBlocks(const relation_id rel) override {
+    trace_->add(name_ + ":done_feeding");
+    RelationalOperator::doneFeedingInputBlocks(rel);
+  }
+  QueryContext::insert_destination_id getInsertDestinationID() const override { return dest_; }
+  const relation_id getOutputRelationID() const override { return output_rel_; }
+  void setDestination(QueryContext::insert_destination_id d) { dest_ = d; }
+  int calls() const { return calls_; }
+  relation_id fedRelation() const { return fed_rel_; }
+ private:
+  std::string name_;
+  Trace *trace_;
+  int own_;
+  bool streamed_, started_ = false;
+  relation_id output_rel_, fed_rel_ = -1;
+  QueryContext::insert_destination_id dest_ = QueryContext::kInvalidInsertDestinationId;
+  std::vector<block_id> fed_;
+  int calls_ = 0;
+  std::atomic<int> *running_, *max_running_;
+};
+
+static void testBlockingDependency() {
+  Trace t;
+  std::atomic<int> running{0}, max_running{0};
+  QueryContext ctx(nullptr, 0);
+  QueryPlan plan;
+  const auto a = plan.addRelationalOperator(new MockOperator("A", &t, 40, false, -1, &running, &max_running));
+  const auto b = plan.addRelationalOperator(new MockOperator("B", &t, 3, false, -1, &running, &max_running));
+  plan.addDirectDependency(b, a, /*is_pipeline_breaker=*/true);
+  WorkerPool pool(4);
+  QueryManager qm(&plan, &ctx, nullptr, &pool);
+  qm.run();
+  EXPECT(qm.numWorkOrdersExecuted(a) == 40 && qm.numWorkOrdersExecuted(b) == 3);
+  EXPECT(t.count("A:wo") == 40 && t.count("B:wo") == 3);
+  // B generates (and therefore runs) only after every work order of A completed
+  int last_a = -1, first_b = 1 << 30;
+  {
+    std::lock_guard<std::mutex> lk(t.mu);
+    for (std::size_t i = 0; i < t.events.size(); ++i) {
+      if (t.events[i] == "A:wo") last_a = static_cast<int>(i);
+      if (t.events[i] == "B:generate" || t.events[i] == "B:wo") first_b = std::min(first_b, static_cast<int>(i));
+    }
+  }
+  EXPECT(last_a >= 0 && last_a < first_b);
+  EXPECT(max_running.load() >= 1 && max_running.load() <= 4);
+  std::printf("blocking_dependency ok (max concurrent work orders %d)\n", max_running.load());
+}
+
+static void testPipelinedFeed() {
+  // Without a GPU there is no real InsertDestination; a destination over a temporary relation needs the storage
+  // manager only when blocks are asked for, so the producer here has no destination and the consumer is fed by
+  // hand through the same calls QueryManager::markOperatorFinished makes.
+  Trace t;
+  std::atomic<int> running{0}, max_running{0};
+  QueryContext ctx(nullptr, 0);
+  QueryPlan plan;
+  auto *prod = new MockOperator("P", &t, 5, false, 77, &running, &max_running);
+  auto *cons = new MockOperator("C", &t, 0, true, -1, &running, &max_running);
+  const auto p = plan.addRelationalOperator(prod), c = plan.addRelationalOperator(cons);
+  plan.addDirectDependency(c, p, /*is_pipeline_breaker=*/false);
+  // consumer asked before anything was fed: no work orders, not done
+  WorkOrdersContainer probe_container(plan.size());
+  EXPECT(cons->getAllWorkOrders(&probe_container, &ctx, nullptr, 0, nullptr) == false);
+  EXPECT(!probe_container.hasNormalWorkOrder(c));
+  cons->feedInputBlock(1001, 77, 0);
+  cons->feedInputBlock(1002, 77, 0);
+  EXPECT(cons->getAllWorkOrders(&probe_container, &ctx, nullptr, 0, nullptr) == false);      // more may come
+  EXPECT(probe_container.getNumNormalWorkOrders(c) == 2 && cons->fedRelation() == 77);
+  cons->doneFeedingInputBlocks(77);
+  EXPECT(cons->getAllWorkOrders(&probe_container, &ctx, nullptr, 0, nullptr) == true);
+  EXPECT(probe_container.getNumNormalWorkOrders(c) == 2);                                      // nothing new
+  while (WorkOrder *w = probe_container.getNormalWorkOrder(c)) { w->execute(); delete w; }
+  EXPECT(t.count("C:wo_fed") == 2);
+  std::printf("pipelined_feed ok (%d getAllWorkOrders calls on the consumer)\n", cons->calls());
+}
+
+static void testDiamondAndRepeatedCalls() {
+  Trace t;
+  std::atomic<int> running{0}, max_running{0};
+  QueryContext ctx(nullptr, 0);
+  QueryPlan plan;
+  // S -> (L, R) -> J : J blocks on both L and R; L and R block on S
+  const auto s = plan.addRelationalOperator(new MockOperator("S", &t, 8, false, -1, &running, &max_running));
+  const auto l = plan.addRelationalOperator(new MockOperator("L", &t, 6, false, -1, &running, &max_running));
+  const auto r = plan.addRelationalOperator(new MockOperator("R", &t, 7, false, -1, &running, &max_running));
+  const auto j = plan.addRelationalOperator(new MockOperator("J", &t, 2, false, -1, &running, &max_running));
+  plan.addDirectDependency(l, s, true);
+  plan.addDirectDependency(r, s, true);
+  plan.addDirectDependency(j, l, true);
+  plan.addDirectDependency(j, r, true);
+  WorkerPool pool(3);
+  QueryManager qm(&plan, &ctx, nullptr, &pool);
+  qm.run();
+  EXPECT(qm.totalWorkOrdersExecuted() == 23);
+  EXPECT(t.index("S:generate") < t.index("L:generate") && t.index("S:generate") < t.index("R:generate"));
+  int last_lr = -1;
+  {
+    std::lock_guard<std::mutex> lk(t.mu);
+    for (std::size_t i = 0; i < t.events.size(); ++i)
+      if (t.events[i] == "L:wo" || t.events[i] == "R:wo") last_lr = static_cast<int>(i);
+  }
+  EXPECT(last_lr < t.index("J:wo"));
+  const std::string prof = qm.profile();
+  EXPECT(prof.find("work_orders=8") != std::string::npos && prof.find("work_orders=2") != std::string::npos);
+  std::printf("diamond ok\n");
+}
+
+int main() {
+  testExprSetAppend();
+  testBlockingDependency();
+  testPipelinedFeed();
+  testDiamondAndRepeatedCalls();
+  if (g_failed) { std::printf("%d check(s) failed\n", g_failed); return 1; }
+  std::printf("all host unit tests passed\n");
+  return 0;
+}
