@@ -158,7 +158,7 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   size_t budget = per_block_max;
   for (int c = 4; c >= 2; --c) {
     const size_t b = per_sm / c - 1024;                     // 1 KB per CTA is reserved by the driver
-    if (fixed + (c >= 3 ? 3ull : 2ull) * stage <= b) { ctas = c; budget = b; break; }
+    if (fixed + 2ull * stage <= b) { ctas = c; budget = b; break; }     // double buffering is the minimum
   }
   if (fixed + 2ull * stage > budget) {
     set_error(QSGPU_ERR_UNSUPPORTED, "scan references too many bytes per row for the shared-memory tile ring");
