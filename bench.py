@@ -92,6 +92,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run this process (and first-touch its pinned block slab) on the CPUs of the NUMA
+    node the GPU hangs off, so that eight ranks staging blocks at once do not pull them across the socket
+    interconnect.  Best effort: returns the node, or None when the topology cannot be read."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- reference arm
 def cpu_q1(O, OT, table, steps, warmup):
     for _ in range(warmup):
@@ -176,6 +199,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
@@ -394,7 +418,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": q1_wall, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload,
-                       "rows_per_gpu": n, "total_rows": n * world, "partitioning": f"lineitem block-partitioned over {world} GPU(s)",
+                       "rows_per_gpu": n, "total_rows": n * world, "numa_node_of_rank0": numa, "partitioning": f"lineitem block-partitioned over {world} GPU(s)",
                        "l2": "inputs (2.5 GB per GPU) larger than L2 (126 MB); no flush needed",
                        "timing": "CUDA events on the library stream around K whole queries; max over ranks"},
             "rows_per_s": n * world / (q1_ms * 1e-3),
