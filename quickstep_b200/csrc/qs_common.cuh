@@ -16,7 +16,10 @@ namespace qs {
 
 // ------------------------------------------------------------ tile geometry
 constexpr int kBlock = 256;                      // threads per CTA
-constexpr int kRows = 4;                         // rows per thread per tile
+#ifndef QS_ROWS
+#define QS_ROWS 4
+#endif
+constexpr int kRows = QS_ROWS;                   // rows per thread per tile
 constexpr int kTileRows = kBlock * kRows;        // 1024 rows per tile
 constexpr int kMaxCols = 12;                     // staged columns per scan
 constexpr int kMaxStages = 8;                    // ring depth upper bound
@@ -32,7 +35,7 @@ constexpr int kMaxOut = 12;                      // projected columns
 constexpr int kCompactMaxGroups = 256;           // K2 per-CTA / global cap
 constexpr int kCompactLocalSlots = 512;          // smem open-addressing slots
 constexpr uint32_t kBarBytes = 128;              // mbarrier area at the head of dynamic smem
-constexpr uint32_t kCompactSmemBytes = (kRows * (kBlock / 32) + 4) * 4;
+constexpr uint32_t kCompactSmemBytes = (32 + 4) * 4;      // per-(row, warp) counts (<= 32) + base / overflow words
 
 // ------------------------------------------------------------ VM value types
 // Compute types of the scalar VM.  Native column types map onto them at leaf

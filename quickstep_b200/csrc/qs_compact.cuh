@@ -14,7 +14,8 @@ namespace qs {
 __device__ __forceinline__ void cta_compact(const bool (&flag)[kRows], uint32_t *s,
                                             unsigned long long *counter, uint64_t capacity,
                                             uint32_t *error_flag, uint64_t (&idx)[kRows]) {
-  static_assert(kRows * (kBlock / 32) == 32, "one warp scans the per-warp counts");
+  constexpr int kCounts = kRows * (kBlock / 32);
+  static_assert(kCounts <= 32, "one warp scans the per-warp counts");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t ball[kRows];
   __syncthreads();                               // previous users of `s` are done
@@ -25,14 +26,14 @@ __device__ __forceinline__ void cta_compact(const bool (&flag)[kRows], uint32_t 
   }
   __syncthreads();
   if (warp == 0) {
-    const uint32_t v = s[lane];
+    const uint32_t v = lane < kCounts ? s[lane] : 0u;
     uint32_t inc = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
       if (lane >= off) inc += t;
     }
-    s[lane] = inc - v;                           // exclusive prefix in (r, warp) order
+    if (lane < kCounts) s[lane] = inc - v;       // exclusive prefix in (r, warp) order
     if (lane == 31) {
       unsigned long long base = 0;
       uint32_t overflow = 0;
