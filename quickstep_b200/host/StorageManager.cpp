@@ -1,6 +1,7 @@
 #include "StorageManager.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <type_traits>
@@ -128,7 +129,7 @@ void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, co
 StorageManager::~StorageManager() {
   for (auto &kv : resident_) if (kv.second.handle) qsgpu_relation_destroy(kv.second.handle);
   for (auto &kv : temporaries_) if (kv.second) qsgpu_relation_destroy(kv.second);
-  for (auto &kv : slabs_) for (Slab &s : kv.second) if (s.base) qsgpu_host_free(s.base);
+  for (auto &kv : slabs_) for (Slab &s : kv.second) if (s.base) { if (pinned_) qsgpu_host_free(s.base); else std::free(s.base); }
 }
 
 void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const void *> &columns, std::uint64_t n_rows,
@@ -174,7 +175,9 @@ void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const 
   Slab slab;
   slab.bytes = total;
   void *hp = nullptr;
-  QS_CHECK_GPU(qsgpu_host_alloc(std::max<std::size_t>(total, 16), &hp));
+  if (pinned_) QS_CHECK_GPU(qsgpu_host_alloc(std::max<std::size_t>(total, 16), &hp));
+  else hp = std::aligned_alloc(4096, (std::max<std::size_t>(total, 16) + 4095) & ~static_cast<std::size_t>(4095));
+  QS_CHECK(hp != nullptr);
   slab.base = static_cast<char *>(hp);
 
   // ---- pass 2 (parallel): write the images

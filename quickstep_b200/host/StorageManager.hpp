@@ -52,7 +52,9 @@ struct DeviceExtent {
 
 class StorageManager {
  public:
-  explicit StorageManager(int device = 0) : device_(device) {}
+  // pinned_blocks = false keeps the block images in ordinary host memory: what the device-free unit tests of
+  // the block builder use (staging from unpinned memory works too, only slower).
+  explicit StorageManager(int device = 0, bool pinned_blocks = true) : device_(device), pinned_(pinned_blocks) {}
   ~StorageManager();
   int device() const { return device_; }
 
@@ -88,6 +90,7 @@ class StorageManager {
     std::uint64_t staged_attrs = 0;      // bit a: attribute a of every staged block is in HBM
   };
   int device_;
+  bool pinned_;
   mutable std::mutex mu_;
   block_id next_block_ = 1;
   std::unordered_map<block_id, StorageBlock> blocks_;

@@ -11,6 +11,7 @@
 
 #include "ExprSet.hpp"
 #include "QueryManager.hpp"
+#include "StorageManager.hpp"
 #include "WorkOrder.hpp"
 
 using namespace quickstep;
@@ -227,8 +228,94 @@ static void testDiamondAndRepeatedCalls() {
   std::printf("diamond ok\n");
 }
 
+// ------------------------------------------------------------ block builder
+// Decodes one stripe of a block image back to native values (independent of the CUDA decoders).
+template <class T>
+static std::vector<T> decodeStripe(const qs_stage_desc &s, std::uint64_t n) {
+  std::vector<T> out(n);
+  const unsigned char *h = static_cast<const unsigned char *>(s.host);
+  for (std::uint64_t i = 0; i < n; ++i) {
+    std::uint32_t code = 0;
+    switch (s.encoding) {
+      case QS_ENC_PLAIN: std::memcpy(&out[i], h + i * sizeof(T), sizeof(T)); break;
+      case QS_ENC_STRIDED: std::memcpy(&out[i], h + i * s.stride, sizeof(T)); break;
+      case QS_ENC_DICT:
+        std::memcpy(&code, h + i * s.code_width, s.code_width);
+        std::memcpy(&out[i], static_cast<const char *>(s.dict) + static_cast<std::size_t>(code) * sizeof(T), sizeof(T));
+        break;
+      default: {   // QS_ENC_TRUNCATED
+        std::memcpy(&code, h + i * s.code_width, s.code_width);
+        const T v = static_cast<T>(code);
+        out[i] = v;
+      }
+    }
+  }
+  return out;
+}
+
+static void testBlockBuilder() {
+  // 10,000 tuples: few distinct doubles (dictionary, 1-byte codes), small non-negative ints (truncation to one
+  // byte), ~2,500 distinct dates-as-longs (dictionary, 2-byte codes), all-distinct doubles (kept native).
+  const std::uint64_t n = 10000, rows_per_block = 4096;
+  std::vector<double> few(n), distinct(n);
+  std::vector<std::int32_t> small(n);
+  std::vector<std::int64_t> mid(n);
+  std::uint64_t x = 88172645463325252ull;
+  auto rnd = [&] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  for (std::uint64_t i = 0; i < n; ++i) {
+    few[i] = static_cast<double>(rnd() % 11) / 100.0;
+    small[i] = static_cast<std::int32_t>(rnd() % 200);
+    mid[i] = static_cast<std::int64_t>(rnd() % 2500) * 7 - 10000;        // some values negative: truncation is out
+    distinct[i] = static_cast<double>(i) * 1.25 + 0.5;
+  }
+  const qs_attr kInt{QS_INT, 4}, kLong{QS_LONG, 8}, kDouble{QS_DOUBLE, 8};
+  for (int layout = 0; layout < 3; ++layout) {
+    CatalogRelation rel(1, "t", {{"few", kDouble}, {"small", kInt}, {"mid", kLong}, {"distinct", kDouble}});
+    StorageManager sm(0, /*pinned_blocks=*/false);
+    sm.loadRelation(&rel, {few.data(), small.data(), mid.data(), distinct.data()}, n, rows_per_block,
+                    static_cast<TupleStoreLayout>(layout));
+    const std::vector<block_id> ids = rel.getBlocksSnapshot();
+    EXPECT(ids.size() == 3);
+    std::uint64_t row = 0;
+    for (block_id id : ids) {
+      const StorageBlock &B = sm.getBlock(id);
+      const std::uint64_t m = static_cast<std::uint64_t>(B.num_tuples);
+      EXPECT(m == std::min<std::uint64_t>(rows_per_block, n - row) && B.stripes.size() == 4 && B.size % 16 == 0);
+      if (layout == static_cast<int>(TupleStoreLayout::kCompressedColumnStore)) {
+        // CompressedBlockBuilder's rule: the smaller of truncation / dictionary / native wins
+        EXPECT(B.stripes[0].encoding == QS_ENC_DICT && B.stripes[0].code_width == 1 && B.stripes[0].dict_entries <= 11);
+        EXPECT(B.stripes[1].encoding == QS_ENC_TRUNCATED && B.stripes[1].code_width == 1);
+        EXPECT(B.stripes[2].encoding == QS_ENC_DICT && B.stripes[2].code_width == 2);
+        EXPECT(B.stripes[3].encoding == QS_ENC_PLAIN);
+        EXPECT(B.size < m * 24 * 6 / 10);            // 24 native bytes per tuple -> well under 60 %
+      } else if (layout == static_cast<int>(TupleStoreLayout::kSplitRowStore)) {
+        for (const qs_stage_desc &s : B.stripes) EXPECT(s.encoding == QS_ENC_STRIDED && s.stride == 28);
+      } else {
+        for (const qs_stage_desc &s : B.stripes) EXPECT(s.encoding == QS_ENC_PLAIN);
+      }
+      for (const qs_stage_desc &s : B.stripes) {     // every stripe / dictionary lies inside the block image
+        const char *p = static_cast<const char *>(s.host);
+        EXPECT(p >= B.memory && p < B.memory + B.size);
+        if (s.encoding == QS_ENC_DICT) EXPECT(static_cast<const char *>(s.dict) >= B.memory && static_cast<const char *>(s.dict) < B.memory + B.size);
+      }
+      const auto d0 = decodeStripe<double>(B.stripes[0], m), d3 = decodeStripe<double>(B.stripes[3], m);
+      const auto d1 = decodeStripe<std::int32_t>(B.stripes[1], m);
+      const auto d2 = decodeStripe<std::int64_t>(B.stripes[2], m);
+      bool same = true;
+      for (std::uint64_t i = 0; i < m; ++i)
+        same = same && std::memcmp(&d0[i], &few[row + i], 8) == 0 && d1[i] == small[row + i] && d2[i] == mid[row + i] &&
+               std::memcmp(&d3[i], &distinct[row + i], 8) == 0;
+      EXPECT(same);
+      row += m;
+    }
+    EXPECT(row == n);
+  }
+  std::printf("block_builder ok\n");
+}
+
 int main() {
   testExprSetAppend();
+  testBlockBuilder();
   testBlockingDependency();
   testPipelinedFeed();
   testDiamondAndRepeatedCalls();
