@@ -287,7 +287,7 @@ static void testBlockBuilder() {
         EXPECT(B.stripes[1].encoding == QS_ENC_TRUNCATED && B.stripes[1].code_width == 1);
         EXPECT(B.stripes[2].encoding == QS_ENC_DICT && B.stripes[2].code_width == 2);
         EXPECT(B.stripes[3].encoding == QS_ENC_PLAIN);
-        EXPECT(B.size < m * 24 * 6 / 10);            // 24 native bytes per tuple -> well under 60 %
+        EXPECT(B.size < m * 24 * 3 / 4);             // 24 native bytes per tuple -> 12 of codes + the dictionaries
       } else if (layout == static_cast<int>(TupleStoreLayout::kSplitRowStore)) {
         for (const qs_stage_desc &s : B.stripes) EXPECT(s.encoding == QS_ENC_STRIDED && s.stride == 28);
       } else {
