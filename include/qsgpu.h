@@ -463,6 +463,13 @@ int qsgpu_partition_count(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
 int qsgpu_partition_scatter_peers(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts,
                                   void *const *peer_cols, const uint64_t *first_rows);
 
+/* The partitioning that makes a join on `table` cache-resident (radix join): rows are grouped by the slice of
+ * the table their key lands in -- leading bits of the home slot for an open-addressing table, equal key ranges
+ * for a dense one.  Partition the build relation before qsgpu_join_build and the probe relation before
+ * probing one partition (row range) at a time; n_parts must be a power of two. */
+int qsgpu_join_partition(qsgpu_join_table_t table, qsgpu_relation_t input, uint32_t key_attr,
+                         uint32_t n_parts, qsgpu_relation_t output, uint64_t *host_offsets);
+
 /* ---------------------------------------------------------- instrumentation */
 /* CUDA-event time (ms) of the most recent kernel of the given family launched
  * by the calling thread's last call, for bench.py's roofline block. */

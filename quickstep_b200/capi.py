@@ -166,6 +166,7 @@ SIGNATURES = {
     "qsgpu_ipc_free": (C.c_int, [C.c_int, _VP]),
     "qsgpu_partition_count": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _U64P]),
     "qsgpu_partition_scatter_peers": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VPP, _U64P]),
+    "qsgpu_join_partition": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),

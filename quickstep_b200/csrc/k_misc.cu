@@ -32,7 +32,8 @@ struct PartDesc {
   uint32_t range_mode;           // 0: mix64(key) % n_parts;  1: (key - min_key) / part_width (clamped)
   int64_t min_key;
   uint64_t part_width;
-  uint32_t width_shift;          // log2(part_width) when it is a power of two, else 64
+  uint32_t width_shift;          // log2(part_width) when it is a power of two, else 64 (slot mode: log2(cap / n_parts))
+  uint64_t slot_mask;            // != 0: partition by the home slot of a join table with slot_mask + 1 slots
   uint64_t n_rows;
   unsigned long long *hist;      // [n_parts]
   unsigned long long *cursor;    // [n_parts] absolute write positions
@@ -52,6 +53,12 @@ __device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
     const uint64_t off = static_cast<uint64_t>(k - D.min_key);
     const uint64_t p = D.width_shift < 64 ? off >> D.width_shift : off / D.part_width;
     return p >= D.n_parts ? D.n_parts - 1 : static_cast<uint32_t>(p);
+  }
+  if (D.slot_mask) {
+    // partition = leading bits of the row's home slot in an open-addressing join table of slot_mask+1 slots:
+    // one partition's keys probe one contiguous slice of the table (plus the few slots linear probing spills
+    // into the next slice), so a partition-at-a-time probe keeps its slice in L2
+    return static_cast<uint32_t>((mix64(static_cast<uint64_t>(k)) & D.slot_mask) >> D.width_shift);
   }
   // multiply-shift range reduction of the hash's high word: uniform, and no 64-bit modulo per row
   return __umulhi(static_cast<uint32_t>(mix64(static_cast<uint64_t>(k)) >> 32), D.n_parts);
@@ -293,7 +300,21 @@ int qsgpu_relation_num_rows(qsgpu_relation_t, uint64_t *);
 int qsgpu_relation_set_num_rows(qsgpu_relation_t, uint64_t);
 
 static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, uint32_t range_mode, int64_t min_key,
-                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets);
+                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets, uint64_t slot_mask = 0);
+
+int qsgpu_join_partition(qsgpu_join_table_t table, qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts,
+                         qsgpu_relation_t output, uint64_t *host_offsets) {
+  if (!table || n_parts == 0 || (n_parts & (n_parts - 1)) != 0) { set_error(QSGPU_ERR_INVALID, "join partitioning needs a power-of-two partition count"); return QSGPU_ERR_INVALID; }
+  if (table->J.dense) {
+    // dense table: contiguous key ranges of equal width
+    const uint64_t width = (table->J.cap + n_parts - 1) / n_parts;
+    uint64_t w2 = 1;
+    while (w2 < width) w2 <<= 1;
+    return partition_impl(input, key_attr, n_parts, 1, table->J.min_key, w2, output, host_offsets);
+  }
+  if (table->J.cap < n_parts) { set_error(QSGPU_ERR_INVALID, "more partitions than table slots"); return QSGPU_ERR_INVALID; }
+  return partition_impl(input, key_attr, n_parts, 0, 0, table->J.cap / n_parts, output, host_offsets, table->J.cap - 1);
+}
 
 int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets) {
@@ -307,7 +328,7 @@ int qsgpu_range_partition(qsgpu_relation_t input, uint32_t key_attr, int64_t min
 }
 
 static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, uint32_t range_mode, int64_t min_key,
-                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets) {
+                          uint64_t part_width, qsgpu_relation_t output, uint64_t *host_offsets, uint64_t slot_mask) {
   Device *d = device(input->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   uint64_t n = 0;
@@ -336,6 +357,7 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   D.part_width = part_width;
   D.width_shift = 64;
   if ((part_width & (part_width - 1)) == 0) { D.width_shift = 0; while ((1ull << D.width_shift) < part_width) ++D.width_shift; }
+  D.slot_mask = slot_mask;
   D.n_rows = n;
   unsigned long long *d_buf = nullptr;
   QS_CUDA(dev_malloc(&d_buf, 2ull * n_parts * 8 + 64));

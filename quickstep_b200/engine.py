@@ -412,6 +412,13 @@ class JoinTable:
                                                     join_type, residual_root, len(project_roots), _i32(project_roots),
                                                     output.h))
 
+    def partition(self, rel, key_attr, n_parts, output: "Relation") -> np.ndarray:
+        """Group rows by the slice of this table their key lands in (qsgpu_join_partition) -> offsets."""
+        offs = np.zeros(n_parts + 1, dtype=np.uint64)
+        A.check(A.load().qsgpu_join_partition(self.h, rel.h, key_attr, n_parts, output.h,
+                                              offs.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return offs
+
     def destroy(self):
         if self.h:
             A.load().qsgpu_join_destroy(self.h)

@@ -646,6 +646,35 @@ def test_partition_scatter_to_destinations(engine, oracle):
             r.destroy()
 
 
+@pytest.mark.parametrize("table", ["open_addressing", "dense"])
+def test_radix_join_partitioned_probe(engine, OB, table):
+    """qsgpu_join_partition: build and probe sides grouped by the slice of the join table their keys land in, the
+    probe run one partition (row range) at a time: same rows as the oracle's join of the unpartitioned inputs."""
+    rng = np.random.default_rng(41)
+    nb, npr, n_parts = 20000, 60000, 8
+    build = HostTable("b", [Column("k", A.QS_LONG, rng.permutation(40000)[:nb].astype(np.int64)), Column("p", A.QS_LONG, np.arange(nb, dtype=np.int64))])
+    probe = HostTable("p", [Column("k", A.QS_LONG, rng.integers(0, 45000, size=npr).astype(np.int64)), Column("v", A.QS_DOUBLE, rng.normal(size=npr))])
+    es = ExprSet()
+    roots, schema = [es.attr(0, A.QS_LONG), es.attr(1, A.QS_LONG, 8, 2), es.attr(1, A.QS_DOUBLE)], [(A.QS_LONG, 8), (A.QS_LONG, 8), (A.QS_DOUBLE, 8)]
+    o = OB.hash_join(build, -1, 0, probe, es, -1, 0, A.QS_JOIN_INNER, -1, roots, schema, npr)
+    brel, prel = engine.Relation.from_host(build), engine.Relation.from_host(probe)
+    bpart, ppart = engine.Relation.create(brel.schema, nb), engine.Relation.create(prel.schema, npr)
+    out = engine.Relation.create(schema, npr)
+    jt = engine.JoinTable(A.QS_LONG, nb, dense_range=(0, 39999) if table == "dense" else None)
+    try:
+        boffs = jt.partition(brel, 0, n_parts, bpart)
+        poffs = jt.partition(prel, 0, n_parts, ppart)
+        assert boffs[-1] == nb and poffs[-1] == npr and (np.diff(poffs.astype(np.int64)) > 0).all()
+        jt.build(bpart, None, -1, 0)
+        for p in range(n_parts):
+            jt.probe(ppart, es, -1, 0, A.QS_JOIN_INNER, -1, roots, out, row_begin=int(poffs[p]), row_end=int(poffs[p + 1]))
+        g = out.to_host("join")
+        # build payload p is the ORIGINAL build row id: partitioning moved the rows but not their values
+        assert g.n_rows == o.n_rows and table_rows(g) == table_rows(o)
+    finally:
+        jt.destroy(); out.destroy(); bpart.destroy(); ppart.destroy(); brel.destroy(); prel.destroy()
+
+
 def test_range_partition(engine):
     """qsgpu_range_partition: partition p holds exactly the keys of [min + p*width, min + (p+1)*width) (clamped at
     both ends), partitions are contiguous and ordered, and the multiset of rows is unchanged."""

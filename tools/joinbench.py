@@ -33,15 +33,14 @@ ap.add_argument("--build-rows", type=int, default=1 << 26)
 ap.add_argument("--probe-rows", type=int, default=1 << 30)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
-ap.add_argument("--radix", type=int, default=0, help="radix join: range-partition both sides into this many key ranges "
-                "so that every probe partition's slice of the dense table and of the build relation fits in L2 (implies --dense)")
+ap.add_argument("--radix", type=int, default=0, help="radix join: both sides are grouped by the slice of the join table "
+                "their keys land in (qsgpu_join_partition: home-slot prefix for open addressing, key range for --dense; "
+                "a power of two), so that every probe partition's slice of the table and of the build relation fits in L2")
 ap.add_argument("--fused", action="store_true", help="N > 1: the partition kernel writes straight into the peers' receive "
                 "relations over NVLink (CUDA IPC) instead of partition -> NCCL all-to-all")
 ap.add_argument("--dense", action="store_true", help="dense (collision-free vector style) join table over the key range")
 args = ap.parse_args()
 
-if args.radix:
-    args.dense = True
 sys.stdout.flush()
 real_stdout = os.dup(1)
 os.dup2(2, 1)
@@ -110,7 +109,6 @@ if args.radix:
     rcap_b, rcap_p = (cap_b, cap_p) if world > 1 else (nb, npr)
     rad_b, rad_p = [buf(rcap_b), buf(rcap_b)], [buf(rcap_p)]
     rad_b_rel, rad_p_rel = wrap(rad_b, rcap_b), wrap(rad_p, rcap_p)
-    part_width = 1 << max(0, (-(-B // args.radix) - 1).bit_length())     # power of two: the partition id is a shift
 
 
 def ev():
@@ -177,18 +175,18 @@ def step():
     else:
         lb, lp, n_b, n_p = build_rel, probe_rel, nb, npr
     ranges = [(0, A.UINT64_MAX)]
+    jt = E.JoinTable(A.QS_LONG, max(n_b, 1024), dev=local, dense_range=(0, B - 1) if args.dense else None)
     if args.radix:
-        # radix join: both sides regrouped by key range; partition p of the probe side only touches slice p of
-        # the dense table (heads) and rows of partition p of the build relation -> L2-resident random accesses
+        # radix join: both sides regrouped by the slice of the join table their keys land in; partition p of the
+        # probe side only touches slice p of the table and the rows of partition p of the build relation
         w2 = time.perf_counter()
-        E.range_partition(lb, 0, 0, part_width, args.radix, rad_b_rel)
-        offs = E.range_partition(lp, 0, 0, part_width, args.radix, rad_p_rel)
+        jt.partition(lb, 0, args.radix, rad_b_rel)
+        offs = jt.partition(lp, 0, args.radix, rad_p_rel)
         E.synchronize(local)
         t["radix_partition_ms"] = (time.perf_counter() - w2) * 1e3
         lb, lp = rad_b_rel, rad_p_rel
         ranges = [(int(offs[i]), int(offs[i + 1])) for i in range(args.radix) if offs[i + 1] > offs[i]]
     E.set_timing(True)
-    jt = E.JoinTable(A.QS_LONG, max(n_b, 1024), dev=local, dense_range=(0, B - 1) if args.dense else None)
     jt.build(lb, None, -1, 0)
     t["build_ms"] = E.last_kernel_ms(A.QS_K_JOIN_BUILD)
     A.check(A.load().qsgpu_relation_set_num_rows(out_rel.h, 0))
