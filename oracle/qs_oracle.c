@@ -943,6 +943,11 @@ static int sort_compare(const void *pa, const void *pb) {
       case QS_FLOAT: { float x = ((const float *)col->data)[a], y = ((const float *)col->data)[b]; c = (x > y) - (x < y); break; }
       case QS_DOUBLE: { double x = ((const double *)col->data)[a], y = ((const double *)col->data)[b]; c = (x > y) - (x < y); break; }
       case QS_DATE: c = date_cmp((const date_lit *)col->data + a, (const date_lit *)col->data + b); break;
+      case QS_CHAR: {   /* strncmp order (types/operations/comparisons/AsciiStringComparators.hpp:218-251) */
+        const int r = strncmp((const char *)col->data + a * col->width, (const char *)col->data + b * col->width, col->width);
+        c = (r > 0) - (r < 0);
+        break;
+      }
       default: c = 0;
     }
     if (c) return g_sort_keys[k].descending ? -c : c;

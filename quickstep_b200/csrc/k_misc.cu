@@ -163,8 +163,23 @@ __global__ void __launch_bounds__(kBlock, 6) k_part_scatter(const __grid_constan
 
 // ------------------------------------------------------------------- K9
 // Order-preserving map of a native value to an unsigned 64-bit key.
+constexpr uint8_t kSortChar = 0x40;      // key_ltype = kSortChar | width for CHAR(n), n <= 8
+
 __device__ __forceinline__ uint64_t sort_key(const char *p, uint8_t ltype, bool desc) {
   uint64_t k;
+  if (ltype & kSortChar) {
+    // CHAR(n), n <= 8: strncmp order of NUL-padded strings == order of the bytes read big-endian
+    // (types/operations/comparisons/AsciiStringComparators.hpp:218-251); bytes after the first NUL are ignored
+    const uint32_t w = ltype & 0x0f;
+    k = 0;
+    bool ended = false;
+    for (uint32_t b = 0; b < 8; ++b) {
+      unsigned char c = (b < w && !ended) ? static_cast<unsigned char>(p[b]) : 0;
+      if (c == 0) ended = true;
+      k = (k << 8) | c;
+    }
+    return desc ? ~k : k;
+  }
   switch (ltype) {
     case V_F32: {
       const double d = static_cast<double>(*reinterpret_cast<const float *>(p));
@@ -529,10 +544,15 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   for (uint32_t q = 0; q < n_keys; ++q) {
     if (keys[q].attr >= input->attrs.size()) { set_error(QSGPU_ERR_INVALID, "sort attribute out of range"); return QSGPU_ERR_INVALID; }
     const uint8_t lt = vtype_of(input->attrs[keys[q].attr].type);
-    if (lt == 0xff) { set_error(QSGPU_ERR_UNSUPPORTED, "CHAR sort keys are not lowered"); return QSGPU_ERR_UNSUPPORTED; }
+    uint8_t klt = lt;
+    if (lt == 0xff) {
+      const qs_attr &ka = input->attrs[keys[q].attr];
+      if (ka.type != QS_CHAR || ka.width > 8) { set_error(QSGPU_ERR_UNSUPPORTED, "sort keys: numeric, DATE or CHAR(n <= 8) attributes"); return QSGPU_ERR_UNSUPPORTED; }
+      klt = static_cast<uint8_t>(kSortChar | ka.width);
+    }
     D.key_col[q].ptr = input->cols[keys[q].attr];
     D.key_col[q].width = input->attrs[keys[q].attr].width;
-    D.key_ltype[q] = lt;
+    D.key_ltype[q] = klt;
     D.desc[q] = keys[q].descending ? 1 : 0;
   }
   qsgpu_relation *rel = nullptr;

@@ -239,19 +239,26 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
                  e.binary(QS_DIV, a(6), a(7)), a(7), a(6)};
   }
   const auto sel_id = ctx.addScalarGroup(std::move(sel));
+  // ORDER BY l_returnflag, l_linestatus: the sort operators collapse into one top-k work order (<= 6 groups)
+  CatalogRelation *t_sorted = db->temp(anon({kChar1, kChar1, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kDouble, kLong, kDouble}));
+  const auto d_sorted = ctx.addInsertDestination(t_sorted, 64);
+  QueryContext::SortConfig sc; sc.keys = {{0, 0}, {1, 0}};
+  const auto sort_id = ctx.addSortConfig(sc);
 
   QueryPlan plan;
   const auto agg = plan.addRelationalOperator(new AggregationOperator(query_id, lineitem, true, state, 1));
   const auto fin = plan.addRelationalOperator(new FinalizeAggregationOperator(query_id, state, 1, false, 1, *t_fin, d_fin));
   const auto select = plan.addRelationalOperator(new SelectOperator(query_id, *t_fin, false, *t_out, d_out, QueryContext::kInvalidPredicateId, sel_id, false));
   const auto destroy = plan.addRelationalOperator(new DestroyAggregationStateOperator(query_id, state));
+  const auto sort = plan.addRelationalOperator(new SortMergeRunOperator(query_id, *t_out, *t_sorted, d_sorted, sort_id, 64, false));
   plan.addDirectDependency(fin, agg, true);
   plan.addDirectDependency(select, fin, false);
   plan.addDirectDependency(destroy, fin, true);
+  plan.addDirectDependency(sort, select, true);
   QueryManager qm(&plan, &ctx, db->sm.get(), db->workers.get());
   qm.run();
 
-  qsgpu_relation_t out = db->sm->temporary(*t_out);
+  qsgpu_relation_t out = db->sm->temporary(*t_sorted);
   const std::uint64_t n = numRows(out);
   std::vector<char> flag(n + 1), status(n + 1);
   std::array<std::vector<double>, 7> d;
@@ -273,11 +280,6 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
     r.count_order = count[i];
     r.sum_disc = sum_disc[i];
   }
-  // ORDER BY l_returnflag, l_linestatus (<= 6 rows; the sort operators are outside the path)
-  std::sort(res.begin(), res.end(), [](const qshost_q1_row &x, const qshost_q1_row &y) {
-    return x.l_returnflag != y.l_returnflag ? static_cast<unsigned char>(x.l_returnflag) < static_cast<unsigned char>(y.l_returnflag)
-                                            : static_cast<unsigned char>(x.l_linestatus) < static_cast<unsigned char>(y.l_linestatus);
-  });
   const std::uint32_t cap = *n_rows;
   *n_rows = static_cast<std::uint32_t>(n);
   for (std::uint32_t i = 0; i < std::min<std::uint64_t>(cap, n); ++i) rows[i] = res[i];

@@ -587,6 +587,23 @@ def test_topk(G, OB, n, limit):
         assert (np.ascontiguousarray(g.columns[c].data).view(np.uint8) == np.ascontiguousarray(o.columns[c].data).view(np.uint8)).all()
 
 
+def test_topk_char_and_date_keys(G, OB):
+    """ORDER BY on CHAR(n <= 8) attributes (Q1's l_returnflag, l_linestatus) and DATE, mixed directions."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    words = np.array([b"N", b"NO", b"NOPE", b"A", b"AF", b"R", b"RF", b"", b"ZZZZZZZZ"], dtype="S8")
+    th = HostTable("t", [Column("c", A.QS_CHAR, words[rng.integers(0, len(words), size=n)], 8),
+                         Column("f", A.QS_CHAR, np.array([b"A", b"N", b"R"], dtype="S1")[rng.integers(0, 3, size=n)], 1),
+                         Column("d", A.QS_DATE, K.random_table(n, 5).col("d").data),
+                         Column("i", A.QS_LONG, rng.permutation(n).astype(np.int64))])
+    for keys, limit in (([(1, False), (0, True), (3, False)], 40), ([(0, False), (2, True), (3, True)], 100)):
+        g = G.topk(G.relation(th), keys, limit)
+        o = OB.topk(th, keys, limit)
+        assert g.n_rows == o.n_rows == limit
+        for cg, co in zip(g.columns, o.columns):
+            assert (np.ascontiguousarray(cg.data).view(np.uint8) == np.ascontiguousarray(co.data).view(np.uint8)).all()
+
+
 @pytest.mark.parametrize("n_parts", [2, 8])
 def test_radix_partition(engine, oracle, n_parts):
     th = K.random_table(50000, seed=12).project(["i64", "f64", "c4"])
