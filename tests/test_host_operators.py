@@ -141,3 +141,16 @@ def test_sf1_reference_answers_through_operator_layer():
         assert top[0][0] == f["l_orderkey"] and abs(top[0][1] - f["revenue"]) < 1e-4
     finally:
         db.destroy()
+
+
+@pytest.mark.gpu
+def test_operator_classes_outside_tpch():
+    """quickstep_b200/host/tests/host_gputest.cpp: HashJoinOperator as a LEFT OUTER join on a composite key and
+    BuildAggregationExistenceMapOperator + collision-free aggregation, scheduled by the QueryManager over multi-block
+    relations, against plain-loop expectations computed in the binary."""
+    import subprocess
+    exe = os.path.join(ROOT, "quickstep_b200", "lib", "qshost_gputest")
+    assert os.path.exists(exe), "build it: make -C quickstep_b200/host"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "outer_join_composite_key ok" in r.stdout and "existence_map_aggregation ok" in r.stdout, r.stdout
