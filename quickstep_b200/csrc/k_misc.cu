@@ -296,6 +296,111 @@ __global__ void __launch_bounds__(1024) k_topk_sort(const __grid_constant__ Topk
   }
 }
 
+// Whole top-k in ONE launch for inputs of up to kTopkSingleMax rows (Q3's ~1e5 groups, Q1's 4): one CTA does
+// the radix select of the limit-th primary key (byte passes, stopping as soon as the candidates fit), collects
+// the candidates, sorts them with the full comparator and writes the result and its row count.  The multi-kernel
+// path below needs a host round trip per pass; here the host never waits.
+constexpr uint64_t kTopkSingleMax = 1ull << 20;
+__global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ TopkDesc D, uint32_t limit,
+                                                      unsigned long long *rows_out, uint32_t *error_flag) {
+  extern __shared__ __align__(16) char s_topk_raw[];
+  SortElem *e = reinterpret_cast<SortElem *>(s_topk_raw);
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned long long s_prefix, s_remaining;
+  __shared__ unsigned int s_m;
+  __shared__ int s_done;
+  const uint64_t n = D.n_rows;
+  const uint64_t k = min(static_cast<uint64_t>(limit), n);
+  const char *kp = D.key_col[0].ptr;
+  const uint32_t kw = D.key_col[0].width;
+  const uint8_t klt = D.key_ltype[0];
+  const bool kdesc = D.desc[0] != 0;
+  if (threadIdx.x == 0) { s_prefix = 0; s_remaining = k; s_done = 0; s_m = 0; }
+  __syncthreads();
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
+    const uint64_t prefix = s_prefix;
+    for (uint64_t row = threadIdx.x; row < n; row += blockDim.x) {
+      const uint64_t key = sort_key(kp + row * kw, klt, kdesc);
+      if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t acc = 0, remaining = s_remaining;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (acc + s_hist[b] >= remaining) break;
+        acc += s_hist[b];
+      }
+      if (b == 256) b = 255;
+      const uint64_t below_or_in = (k - remaining) + acc + s_hist[b];
+      s_remaining = remaining - acc;
+      uint64_t p = prefix | (static_cast<uint64_t>(b) << shift);
+      if (below_or_in <= static_cast<uint64_t>(kTopkMaxCand) || shift == 0) {
+        if (shift > 0) p |= (1ull << shift) - 1;       // take the whole bucket
+        s_done = 1;
+      }
+      s_prefix = p;
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  const uint64_t threshold = s_prefix;
+  for (uint64_t row = threadIdx.x; row < n; row += blockDim.x) {
+    if (sort_key(kp + row * kw, klt, kdesc) <= threshold) {
+      const unsigned int pos = atomicAdd(&s_m, 1u);
+      if (pos < static_cast<unsigned int>(kTopkMaxCand)) {
+        SortElem x;
+        x.row = row;
+        for (uint32_t q = 0; q < 4; ++q)
+          x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
+        e[pos] = x;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t m = s_m;
+  if (m > static_cast<uint32_t>(kTopkMaxCand)) {       // more than kTopkMaxCand rows tie on the primary key at the cut
+    if (threadIdx.x == 0) atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+    m = kTopkMaxCand;
+  }
+  uint32_t N = 1;
+  while (N < m) N <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < N; i += blockDim.x) {
+    SortElem x;
+    x.row = ~0ull;
+    for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
+    e[i] = x;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const SortElem a = e[i], b = e[j];
+          if (elem_less(b, a) == up) { e[i] = b; e[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = min(limit, m);
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const uint64_t row = e[i].row;
+    for (uint32_t c = 0; c < D.n_cols; ++c) {
+      const uint32_t w = D.in[c].width;
+      const char *src = D.in[c].ptr + row * w;
+      char *o = D.out[c] + static_cast<uint64_t>(i) * w;
+      for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+    }
+  }
+  if (threadIdx.x == 0) *rows_out = n_out;
+}
+
 static int grid_for(uint64_t n) {
   uint64_t g = (n + 255) / 256;
   if (g > 148ull * 8) g = 148ull * 8;
@@ -566,6 +671,27 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     D.out[c] = rel->cols[c];
   }
   if (n == 0) { *out = rel; return qsgpu_relation_set_num_rows(rel, 0); }
+  if (n <= kTopkSingleMax) {
+    // one launch, no host round trip: the result's row count stays on the device until somebody asks
+    const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(SortElem);
+    cudaFuncSetAttribute(k_topk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));   // per device
+    const bool on = timing_enabled();
+    if (on) cudaEventRecord(d->ev0, d->stream);
+    k_topk_single<<<1, 1024, smem, d->stream>>>(D, static_cast<uint32_t>(limit), rel->d_rows, d->d_error);
+    count_launch();
+    cudaError_t ke = cudaGetLastError();
+    if (ke != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(ke, "top-k"); }
+    if (on) {
+      cudaEventRecord(d->ev1, d->stream);
+      cudaEventSynchronize(d->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+      record_ms(QS_K_TOPK, ms);
+    }
+    rel->dirty = true;
+    *out = rel;
+    return QSGPU_OK;
+  }
 
   uint64_t *pk = nullptr, *cand = nullptr;
   unsigned long long *hist = nullptr;

@@ -587,6 +587,22 @@ def test_topk(G, OB, n, limit):
         assert (np.ascontiguousarray(g.columns[c].data).view(np.uint8) == np.ascontiguousarray(o.columns[c].data).view(np.uint8)).all()
 
 
+def test_topk_large_input_multi_pass_path(G, OB):
+    """More than 2^20 rows take the multi-kernel radix-select path (one host round trip per byte pass); same
+    answer as the oracle's full sort.  Also a LIMIT where thousands of rows tie on the primary key away from the
+    cut (ties AT the cut beyond 2048 rows are an error by design)."""
+    rng = np.random.default_rng(19)
+    n = (1 << 20) + 12345
+    th = HostTable("t", [Column("a", A.QS_DOUBLE, np.round(rng.normal(0, 1000, size=n), 1)),
+                         Column("b", A.QS_LONG, rng.permutation(n).astype(np.int64))])
+    for keys, limit in (([(0, True), (1, False)], 50), ([(0, False), (1, True)], 1000)):
+        g = G.topk(G.relation(th), keys, limit)
+        o = OB.topk(th, keys, limit)
+        assert g.n_rows == o.n_rows == limit
+        for cg, co in zip(g.columns, o.columns):
+            assert (np.ascontiguousarray(cg.data).view(np.uint8) == np.ascontiguousarray(co.data).view(np.uint8)).all()
+
+
 def test_topk_char_and_date_keys(G, OB):
     """ORDER BY on CHAR(n <= 8) attributes (Q1's l_returnflag, l_linestatus) and DATE, mixed directions."""
     rng = np.random.default_rng(3)
