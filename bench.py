@@ -148,16 +148,18 @@ def run_reference(args):
     n = args.cpu_sample_rows
     table = numpy_lineitem(n, 11)
     ms, _ = cpu_q1(O, OT, table, max(1, args.steps), max(1, min(args.warmup, 2)))
-    scaled = ms * (args.rows / n)
+    total_rows = args.rows * max(1, args.gpus)      # the same whole job as our arm at N GPUs (weak scaling)
+    scaled = ms * (total_rows / n)
     line = {
         "impl": "reference", "metric": "tpch_q1_sf10_query_ms", "value": scaled, "unit": "ms", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)",
-                   "rows": args.rows},
+        "config": {"workload": "TPC-H Q1 at SF10 (lineitem 59,986,052 rows, 42 B/row, 4 groups x 6 states)" if total_rows == SF10_LINEITEM_ROWS
+                   else f"TPC-H Q1, lineitem {total_rows:,} rows in total ({args.gpus} x {args.rows:,}), 42 B/row, 4 groups x 6 states",
+                   "rows": total_rows},
         "cpu_baseline": {"value": scaled, "unit": "ms", "cores": cores, "kind": "port",
                          "sample": f"Q1 over {n} synthetic lineitem rows ({ms:.2f} ms/step, {cores} threads, 63k-row "
-                                   f"work orders), scaled x{args.rows / n:.2f} to {args.rows} rows"},
+                                   f"work orders), scaled x{total_rows / n:.2f} to {total_rows} rows"},
         "e2e": {"value": scaled, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
