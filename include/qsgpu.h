@@ -146,6 +146,35 @@ int qsgpu_relation_wrap(int dev, uint32_t n_attrs, const qs_attr *attrs,
 int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
                         uint64_t n_rows, void *host_out);
 
+/*
+ * Dictionary-coded attributes: the compressed block format as a device format.
+ *
+ * The reference evaluates a comparison against a literal directly on the codes of a dictionary-compressed
+ * stripe: CompressedTupleStorageSubBlock::getMatchesForPredicate turns the literal into limit codes of the
+ * block's sorted dictionary and scans the 1/2/4-byte codes (storage/CompressedTupleStorageSubBlock.cpp:160-251,
+ * compression/CompressionDictionary.hpp:241-318); values are materialised through
+ * CompressionDictionaryLite::getUntypedValueForCode only where a scalar needs them
+ * (compression/CompressionDictionaryLite.hpp:40-51).
+ *
+ * qsgpu_relation_set_dictionary declares that attribute `attr` of `rel` is resident in HBM as `code_width`-byte
+ * codes (1, 2 or 4) into ONE relation-wide dictionary of `n_entries` native values, strictly increasing in the
+ * attribute's order (CompressionDictionaryBuilder order: numeric / DateLit / strncmp).  Call it on an empty
+ * relation from qsgpu_relation_create (its column is re-allocated at code width; qsgpu_stage_blocks then re-codes
+ * the blocks' QS_ENC_DICT stripes from their per-block dictionaries into relation codes), or on a relation from
+ * qsgpu_relation_wrap whose buffer for `attr` already holds the codes.  From then on every scan of the relation
+ * (select, aggregation, join build / probe, LIP build) moves code_width bytes per row of that attribute:
+ * comparisons with literals run on the codes (one unsigned range test per row), scalar expressions look values
+ * up in the dictionary, and group-by keys / pass-through projections / join keys are decoded per tile in shared
+ * memory.  Results are bit-identical to the native column's.  qsgpu_relation_read returns native values;
+ * qsgpu_relation_column returns the code buffer.  Operators that read whole native columns of their input
+ * (top-k, partitioning, build-side projections of a join) refuse coded attributes with QSGPU_ERR_UNSUPPORTED.
+ */
+int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t code_width,
+                                  const void *dict_values, uint32_t n_entries);
+/* code_width 0 = native attribute; dict_out (optional) receives n_entries native values. */
+int qsgpu_relation_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t *code_width, uint32_t *n_entries,
+                              void *dict_out);
+
 /* NULL mask of rows [row_begin, row_begin+n_rows): bit j of word i = attribute j of row row_begin+i is NULL
  * (its stored bytes are zero).  Only the output of a LEFT OUTER join can hold NULLs; all zeros otherwise. */
 int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows,

@@ -126,6 +126,8 @@ SIGNATURES = {
     "qsgpu_relation_column": (C.c_int, [_VP, C.c_uint32, _VPP]),
     "qsgpu_relation_wrap": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), _VPP, C.c_uint64, _VPP]),
     "qsgpu_relation_read": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, _VP]),
+    "qsgpu_relation_set_dictionary": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint32]),
+    "qsgpu_relation_dictionary": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _VP]),
     "qsgpu_relation_read_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
@@ -172,7 +174,7 @@ SIGNATURES = {
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }
-JIT_SELFCHECK_CASES = 12
+JIT_SELFCHECK_CASES = 15
 
 
 class QsGpuError(RuntimeError):

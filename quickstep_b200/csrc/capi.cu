@@ -141,8 +141,14 @@ struct KernelTimer {
 int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   uint32_t stage = 0;
   for (uint32_t c = 0; c < S->n_cols; ++c) {
-    S->cols[c].smem_off = stage;
-    stage += static_cast<uint32_t>(kTileRows) * S->cols[c].width;   // multiple of 16 by construction
+    ColDesc &C = S->cols[c];
+    if (C.cw != 0) {                      // coded attribute: the code tile is what travels
+      C.code_off = stage;
+      stage += static_cast<uint32_t>(kTileRows) * C.cw;
+      if (!C.expand) { C.smem_off = 0; continue; }
+    }
+    C.smem_off = stage;
+    stage += static_cast<uint32_t>(kTileRows) * C.width;   // multiple of 16 by construction
   }
   stage = (stage + 127u) & ~127u;
   if (stage == 0) stage = 128;
@@ -257,6 +263,12 @@ static int fill_scan(const qsgpu_relation *rel, uint64_t row_begin, uint64_t row
     const uint32_t a = L.staged_attrs[c];
     S->cols[c].ptr = rel->cols[a];
     S->cols[c].width = rel->attrs[a].width;
+    if (const uint32_t cw = rel->code_width(a)) {
+      S->cols[c].cw = static_cast<uint8_t>(cw);
+      S->cols[c].dict = rel->coded[a].d_dict;
+      S->cols[c].dict_entries = rel->coded[a].n_entries;
+      S->cols[c].expand = (L.staged_use[c] & Lowering::USE_RAW) ? 1 : 0;
+    }
   }
   return QSGPU_OK;
 }
@@ -269,6 +281,17 @@ static int fill_lips(uint32_t n, const qs_lip_ref *refs, const qsgpu_relation *r
     S->lip[i] = refs[i].lip->d;
   }
   (void)rel;
+  return QSGPU_OK;
+}
+
+// Native values of rows [row_begin, row_begin + n_rows) of a coded attribute in a fresh device buffer.
+static int decode_coded(Device *d, const qsgpu_relation *rel, uint32_t attr, uint64_t row_begin, uint64_t n_rows,
+                        char **out) {
+  const qs_coded_attr &C = rel->coded[attr];
+  const uint32_t w = rel->attrs[attr].width;
+  QS_CUDA(dev_malloc(out, n_rows * w + 16));
+  QS_CUDA(launch_decode_dict(*out, rel->cols[attr] + row_begin * C.cw, C.d_dict, n_rows, C.cw, w, C.n_entries, d->stream));
+  if (n_rows) count_launch();
   return QSGPU_OK;
 }
 
@@ -538,6 +561,7 @@ int qsgpu_relation_destroy(qsgpu_relation_t rel) {
   // them as soon as this returns
   if (d && !rel->owns_memory) cudaStreamSynchronize(d->stream);
   if (rel->owns_memory) for (char *p : rel->cols) dev_free(p);
+  for (auto &c : rel->coded) dev_free(c.d_dict);
   dev_free(rel->d_nulls);
   dev_free(rel->d_rows);
   delete rel;
@@ -576,8 +600,72 @@ int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
   if (attr >= rel->cols.size() || row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
   Device *d = device(rel->dev);
   const uint32_t w = rel->attrs[attr].width;
-  QS_CUDA(cudaMemcpyAsync(host_out, rel->cols[attr] + row_begin * w, n_rows * w, cudaMemcpyDeviceToHost, d->stream));
+  char *tmp = nullptr;
+  const char *src = rel->cols[attr] + row_begin * w;
+  if (rel->code_width(attr) != 0) {         // coded attribute: callers always see native values
+    int rc = decode_coded(d, rel, attr, row_begin, n_rows, &tmp);
+    if (rc) return rc;
+    src = tmp;
+  }
+  cudaError_t e = cudaSuccess;
+  if (n_rows) e = cudaMemcpyAsync(host_out, src, n_rows * w, cudaMemcpyDeviceToHost, d->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  dev_free(tmp);
+  if (e != cudaSuccess) return cuda_fail(e, "qsgpu_relation_read");
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t code_width, const void *dict_values,
+                                  uint32_t n_entries) {
+  if (!rel) { set_error(QSGPU_ERR_INVALID, "null relation"); return QSGPU_ERR_INVALID; }
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  int st = sync_rows(rel);
+  if (st) return st;
+  if (attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "attribute id out of range"); return QSGPU_ERR_INVALID; }
+  if (code_width != 1 && code_width != 2 && code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); return QSGPU_ERR_INVALID; }
+  if (!dict_values || n_entries == 0 || (code_width < 4 && n_entries > (1u << (8 * code_width)))) {
+    set_error(QSGPU_ERR_INVALID, "dictionary is empty or has more entries than the code width can address");
+    return QSGPU_ERR_INVALID;
+  }
+  if (rel->code_width(attr) != 0) { set_error(QSGPU_ERR_INVALID, "attribute already has a dictionary"); return QSGPU_ERR_INVALID; }
+  if (rel->owns_memory && rel->host_rows != 0) { set_error(QSGPU_ERR_INVALID, "a dictionary must be declared before rows are staged"); return QSGPU_ERR_INVALID; }
+  const uint32_t w = rel->attrs[attr].width;
+  const char *dv = static_cast<const char *>(dict_values);
+  for (uint32_t e = 1; e < n_entries; ++e) {
+    if (dict_compare(rel->attrs[attr].type, w, dv + static_cast<size_t>(e - 1) * w, dv + static_cast<size_t>(e) * w) != -1) {
+      set_error(QSGPU_ERR_INVALID, "dictionary entries must be strictly increasing in the attribute's order");
+      return QSGPU_ERR_INVALID;
+    }
+  }
+  if (rel->coded.empty()) rel->coded.resize(rel->attrs.size());
+  qs_coded_attr &C = rel->coded[attr];
+  // readable for every value a 1/2-byte code can take: rows past the end of a ragged tile need no clamp
+  const size_t slots = code_width < 4 ? (static_cast<size_t>(1) << (8 * code_width)) : n_entries;
+  const size_t bytes = slots * w + 16;
+  QS_CUDA(dev_malloc(&C.d_dict, bytes));
+  QS_CUDA(cudaMemsetAsync(C.d_dict, 0, bytes, d->stream));
+  C.h_dict.assign(dv, dv + static_cast<size_t>(n_entries) * w);
+  QS_CUDA(cudaMemcpyAsync(C.d_dict, C.h_dict.data(), C.h_dict.size(), cudaMemcpyHostToDevice, d->stream));
   QS_CUDA(cudaStreamSynchronize(d->stream));
+  if (rel->owns_memory) {   // the column now holds codes: give the native-width buffer back
+    char *p = nullptr;
+    QS_CUDA(dev_malloc(&p, padded_bytes(rel->capacity, code_width)));
+    dev_free(rel->cols[attr]);
+    rel->cols[attr] = p;
+  }
+  C.cw = code_width;
+  C.n_entries = n_entries;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t *code_width, uint32_t *n_entries,
+                              void *dict_out) {
+  if (!rel || attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "attribute id out of range"); return QSGPU_ERR_INVALID; }
+  const uint32_t cw = rel->code_width(attr);
+  if (code_width) *code_width = cw;
+  if (n_entries) *n_entries = cw ? rel->coded[attr].n_entries : 0;
+  if (dict_out && cw) std::memcpy(dict_out, rel->coded[attr].h_dict.data(), rel->coded[attr].h_dict.size());
   return QSGPU_OK;
 }
 
@@ -596,6 +684,13 @@ int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n
   Device *d = device(rel->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   if (n_rows == 0) return QSGPU_OK;
+  if (rel->has_codes()) {   // base relations only; results of operators are always native
+    for (uint32_t a = 0; a < rel->cols.size(); ++a) {
+      st = qsgpu_relation_read(rel, a, row_begin, n_rows, host_out[a]);
+      if (st) return st;
+    }
+    return QSGPU_OK;
+  }
   size_t total = 0;
   for (size_t a = 0; a < rel->cols.size(); ++a) total += (n_rows * rel->attrs[a].width + 15) & ~static_cast<size_t>(15);
   if (total <= kReadScratchBytes && d->read_scratch) {
@@ -634,6 +729,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
   if (!rel->owns_memory) { set_error(QSGPU_ERR_INVALID, "cannot stage into a wrapped relation"); return QSGPU_ERR_INVALID; }
   if (rel->host_rows + n_rows > rel->capacity) { set_error(QSGPU_ERR_CAPACITY, "relation capacity exceeded while staging"); return QSGPU_ERR_CAPACITY; }
   if (n_desc != rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "qsgpu_stage_block must stage every attribute of the relation"); return QSGPU_ERR_INVALID; }
+  if (rel->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "relations with dictionary-coded attributes are staged with qsgpu_stage_blocks"); return QSGPU_ERR_UNSUPPORTED; }
   KernelTimer timer(d, QS_K_STAGE);
   std::vector<void *> scratch;
   int rc = QSGPU_OK;
@@ -726,6 +822,9 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   Chunk cur{0, 0, 0, 0, 0};
   int rc = QSGPU_OK;
   std::vector<std::pair<uint64_t, uint64_t>> need;          // (offset, bytes) inside one block image
+  std::vector<char> remap;                                  // re-coding tables of coded attributes, all blocks
+  std::vector<std::pair<size_t, size_t>> remap_fix;         // (segment, offset of its table in `remap`)
+  char *d_remap = nullptr;
   for (uint32_t b = 0; b < n_blocks && rc == QSGPU_OK; ++b) {
     const qs_block_image &B = blocks[b];
     const char *h0 = static_cast<const char *>(B.host);
@@ -737,6 +836,54 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
       const uint32_t w = rel->attrs[s.attr].width;
       const char *hs = static_cast<const char *>(s.host);
       uint64_t bytes = 0;
+      if (const uint32_t gcw = rel->code_width(s.attr)) {
+        // Attribute held as codes of the relation-wide dictionary: the block's codes are re-coded through a
+        // per-block table (block code -> relation code) built here from the two sorted dictionaries; the decode
+        // kernel sees it as a dictionary whose "values" are gcw-byte codes.  The block's own dictionary stays on
+        // the host.
+        if (s.encoding != QS_ENC_DICT) { set_error(QSGPU_ERR_UNSUPPORTED, "a dictionary-coded attribute is staged from dictionary-compressed stripes only"); rc = QSGPU_ERR_UNSUPPORTED; break; }
+        if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; break; }
+        const char *hd = static_cast<const char *>(s.dict);
+        bytes = B.n_rows * s.code_width;
+        if (!hs || hs < h0 || hs + bytes > h0 + B.bytes || !hd || s.dict_entries == 0) { set_error(QSGPU_ERR_INVALID, "stage: stripe lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+        const qs_coded_attr &C = rel->coded[s.attr];
+        remap.resize((remap.size() + 3) & ~static_cast<size_t>(3));
+        const size_t roff = remap.size();
+        remap.resize(roff + static_cast<size_t>(s.dict_entries) * gcw);
+        uint32_t g_lo = 0;                       // both dictionaries are sorted: the search window only moves up
+        for (uint32_t e = 0; e < s.dict_entries && rc == QSGPU_OK; ++e) {
+          const char *v = hd + static_cast<size_t>(e) * w;
+          uint32_t lo = g_lo, hi = C.n_entries;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (dict_compare(rel->attrs[s.attr].type, w, C.h_dict.data() + static_cast<size_t>(mid) * w, v) == -1) lo = mid + 1; else hi = mid;
+          }
+          if (lo >= C.n_entries || dict_compare(rel->attrs[s.attr].type, w, C.h_dict.data() + static_cast<size_t>(lo) * w, v) != 0) {
+            set_error(QSGPU_ERR_INVALID, "stage: a block dictionary value is missing from the relation's dictionary");
+            rc = QSGPU_ERR_INVALID;
+            break;
+          }
+          std::memcpy(&remap[roff + static_cast<size_t>(e) * gcw], &lo, gcw);   // little endian
+          g_lo = lo;
+        }
+        if (rc != QSGPU_OK) break;
+        StageSeg g{};
+        g.dst = rel->cols[s.attr] + row_base * gcw;
+        g.src = d_img + img_off[b] + (hs - h0);
+        g.n_rows = B.n_rows;
+        g.tile_begin = cur.tiles;
+        g.encoding = QS_ENC_DICT;
+        g.cw = s.code_width; g.vw = gcw; g.dict_entries = s.dict_entries;
+        const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
+        g.aligned = ((reinterpret_cast<uintptr_t>(g.dst) % gcw) == 0 ? 1u : 0u) | (code_al ? 2u : 0u);
+        if (B.n_rows) {
+          remap_fix.emplace_back(segs.size(), roff);
+          segs.push_back(g);
+          cur.tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows;
+          need.emplace_back(static_cast<uint64_t>(hs - h0), bytes);
+        }
+        continue;
+      }
       switch (s.encoding) {
         case QS_ENC_PLAIN: bytes = B.n_rows * w; break;
         case QS_ENC_STRIDED: bytes = B.n_rows ? (B.n_rows - 1) * s.stride + w : 0; break;
@@ -814,7 +961,13 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   }
   cudaEvent_t ev = nullptr;
   if (rc == QSGPU_OK && !segs.empty()) {
-    cudaError_t ce = dev_malloc(&d_segs, segs.size() * sizeof(StageSeg));
+    cudaError_t ce = cudaSuccess;
+    if (!remap.empty()) {
+      ce = dev_malloc(&d_remap, remap.size() + 16);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_remap, remap.data(), remap.size(), cudaMemcpyHostToDevice, d->stream);
+      for (const auto &f : remap_fix) segs[f.first].dict = d_remap + f.second;
+    }
+    if (ce == cudaSuccess) ce = dev_malloc(&d_segs, segs.size() * sizeof(StageSeg));
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(StageSeg), cudaMemcpyHostToDevice, d->stream);
     // the image buffer may be a recycled block that earlier work on the library stream still reads
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -841,6 +994,7 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   }
   dev_free(d_img);
   dev_free(d_segs);
+  dev_free(d_remap);
   if (rc != QSGPU_OK) return rc;
   const uint64_t rows_after = std::max<uint64_t>(rel->host_rows, first_row + total_rows);
   if (!append && rows_after == rel->host_rows) return QSGPU_OK;
@@ -1656,6 +1810,11 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
   J.n_build_cols = static_cast<uint32_t>(L.build_attrs.size());
   for (uint32_t c = 0; c < J.n_build_cols; ++c) {
     const uint32_t a = L.build_attrs[c];
+    if (const uint32_t bcw = table->build_rel->code_width(a)) {
+      J.build_cols[c].cw = static_cast<uint8_t>(bcw);
+      J.build_cols[c].dict = table->build_rel->coded[a].d_dict;
+      J.build_cols[c].dict_entries = table->build_rel->coded[a].n_entries;
+    }
     J.build_cols[c].ptr = table->build_rel->cols[a];
     J.build_cols[c].width = table->build_rel->attrs[a].width;
   }

@@ -454,6 +454,7 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   uint64_t n = 0;
   int st = qsgpu_relation_num_rows(input, &n);
   if (st) return st;
+  if (input->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "this operator reads native columns; its input holds dictionary-coded attributes (select them into a temporary relation first)"); return QSGPU_ERR_UNSUPPORTED; }
   if (n_parts == 0 || n_parts > 1024 || key_attr >= input->attrs.size() || output->dev != input->dev ||
       output->attrs.size() != input->attrs.size() || output->capacity < n || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
     set_error(QSGPU_ERR_INVALID, "bad radix partition arguments");
@@ -520,6 +521,7 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
 static int fill_part_desc(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, PartDesc *D, uint64_t *n_rows) {
   int st = qsgpu_relation_num_rows(input, n_rows);
   if (st) return st;
+  if (input->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "this operator reads native columns; its input holds dictionary-coded attributes (select them into a temporary relation first)"); return QSGPU_ERR_UNSUPPORTED; }
   if (n_parts == 0 || n_parts > 1024 || key_attr >= input->attrs.size() || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
     set_error(QSGPU_ERR_INVALID, "bad partition arguments");
     return QSGPU_ERR_INVALID;
@@ -639,6 +641,7 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   uint64_t n = 0;
   int st = qsgpu_relation_num_rows(input, &n);
   if (st) return st;
+  if (input->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "this operator reads native columns; its input holds dictionary-coded attributes (select them into a temporary relation first)"); return QSGPU_ERR_UNSUPPORTED; }
   if (n_keys == 0 || n_keys > 4 || limit == 0 || limit > 1024 || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
     set_error(QSGPU_ERR_UNSUPPORTED, "top-k supports 1..4 sort attributes and LIMIT <= 1024");
     return QSGPU_ERR_UNSUPPORTED;

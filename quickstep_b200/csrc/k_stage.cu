@@ -72,6 +72,7 @@ __device__ __forceinline__ uint32_t load_code_any(const unsigned char *codes, ui
 __device__ __forceinline__ void copy_vw(char *d, const char *src, uint32_t vw, bool aligned) {
   if (aligned && vw == 8) *reinterpret_cast<uint64_t *>(d) = *reinterpret_cast<const uint64_t *>(src);
   else if (aligned && vw == 4) *reinterpret_cast<uint32_t *>(d) = *reinterpret_cast<const uint32_t *>(src);
+  else if (aligned && vw == 2) *reinterpret_cast<uint16_t *>(d) = *reinterpret_cast<const uint16_t *>(src);
   else for (uint32_t b = 0; b < vw; ++b) d[b] = src[b];
 }
 

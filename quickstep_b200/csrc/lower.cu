@@ -63,15 +63,16 @@ const qs_node *Lowering::node(int i) {
   return &ex->nodes[i];
 }
 
-int Lowering::stage_attr(uint32_t attr) {
+int Lowering::stage_attr(uint32_t attr, uint8_t use) {
   if (!rel || attr >= rel->attrs.size()) { fail(QSGPU_ERR_INVALID, "attribute id out of range"); return 0; }
-  if (slot_of_attr[attr] >= 0) return slot_of_attr[attr];
+  if (slot_of_attr[attr] >= 0) { staged_use[slot_of_attr[attr]] |= use; return slot_of_attr[attr]; }
   if (staged_attrs.size() >= static_cast<size_t>(kMaxCols)) {
     fail(QSGPU_ERR_UNSUPPORTED, "more than kMaxCols attributes referenced by one scan");
     return 0;
   }
   slot_of_attr[attr] = static_cast<int>(staged_attrs.size());
   staged_attrs.push_back(attr);
+  staged_use.push_back(use);
   return slot_of_attr[attr];
 }
 
@@ -160,7 +161,7 @@ bool Lowering::leaf_ref(int i, uint8_t want, Instr *in) {
     if (own == 0xff) return fail(QSGPU_ERR_UNSUPPORTED, "CHAR attribute in arithmetic context");
     in->ltype = own;
     if (n->b == 2) { in->leaf = LEAF_BUILD; in->arg = static_cast<uint16_t>(build_attr(static_cast<uint32_t>(n->a))); }
-    else { in->leaf = LEAF_COL; in->arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(n->a))); }
+    else { in->leaf = LEAF_COL; in->arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(n->a), USE_VALUE)); }
     return true;
   }
   if (n->kind == QS_N_SHARED) {
@@ -284,6 +285,93 @@ static uint8_t flip_cmp(uint8_t c) {
   }
 }
 
+// Three-way comparison of a dictionary entry with a literal, both in the comparison's compute type
+// (LiteralComparators.hpp:36-72); 2 = unordered (NaN).
+static int host_cmp3(uint8_t T, uint64_t a, uint64_t b) {
+  switch (T) {
+    case V_F64: { double x, y; std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8); return x < y ? -1 : x > y ? 1 : x == y ? 0 : 2; }
+    case V_F32: { float x, y; uint32_t ua = static_cast<uint32_t>(a), ub = static_cast<uint32_t>(b); std::memcpy(&x, &ua, 4); std::memcpy(&y, &ub, 4); return x < y ? -1 : x > y ? 1 : x == y ? 0 : 2; }
+    case V_I32: { const int32_t x = static_cast<int32_t>(a), y = static_cast<int32_t>(b); return x < y ? -1 : x > y ? 1 : 0; }
+    default: { const int64_t x = static_cast<int64_t>(a), y = static_cast<int64_t>(b); return x < y ? -1 : x > y ? 1 : 0; }
+  }
+}
+
+static uint64_t dict_raw(const char *p, uint16_t type) {
+  switch (type) {
+    case QS_INT: { int32_t v; std::memcpy(&v, p, 4); return static_cast<uint64_t>(static_cast<int64_t>(v)); }
+    case QS_FLOAT: { uint32_t v; std::memcpy(&v, p, 4); return v; }
+    case QS_DATE: {   // DateLit bytes -> the order-preserving key of date_key()
+      int32_t year; std::memcpy(&year, p, 4);
+      const uint8_t month = static_cast<uint8_t>(p[4]), day = static_cast<uint8_t>(p[5]);
+      return (static_cast<uint64_t>(static_cast<uint32_t>(year)) << 32) | (static_cast<uint64_t>(month) << 8) | day;
+    }
+    default: { uint64_t v; std::memcpy(&v, p, 8); return v; }
+  }
+}
+
+// Order of two dictionary entries of an attribute (the type's less-than, as the reference's
+// CompressionDictionaryBuilder sorts them, compression/CompressionDictionaryBuilder.cpp:120-160).
+int dict_compare(uint16_t type, uint32_t width, const char *a, const char *b) {
+  if (type == QS_CHAR) { const int r = std::strncmp(a, b, width); return r < 0 ? -1 : r > 0 ? 1 : 0; }
+  const uint8_t T = vtype_of(type) == V_DATE ? V_I64 : vtype_of(type);
+  return host_cmp3(T, dict_raw(a, type), dict_raw(b, type));
+}
+
+/*
+ * attribute <cmp> literal where the attribute is held as codes of a sorted relation-wide dictionary: count the
+ * dictionary entries below / equal to / above the literal and compare codes against those bounds.  This is
+ * what CompressedTupleStorageSubBlock::getMatchesForPredicate does per block with
+ * CompressionDictionary::getLimitCodesForComparisonTyped (storage/CompressedTupleStorageSubBlock.cpp:160-251,
+ * compression/CompressionDictionary.hpp:241-318); here once per work order.  The satisfying codes always form
+ * one range [lo, lo+span) or its complement, so the kernel runs one unsigned range test per row; the bounds
+ * travel as literals (the kernel does not depend on their values).
+ */
+bool Lowering::lower_code_compare(const qs_node *attr, const qs_node *lit, uint8_t cmp) {
+  const uint32_t a = static_cast<uint32_t>(attr->a);
+  const qs_coded_attr &C = rel->coded[a];
+  const uint32_t w = rel->attrs[a].width;
+  uint64_t n_lt = 0, n_eq = 0, n_gt = 0;
+  if (attr->type == QS_CHAR) {
+    // strncmp over the attribute width, literal NUL-padded / cut like the native CHAR path
+    std::string l(w, '\0');
+    for (uint32_t b = 0; b < w && b < lit->width; ++b) l[b] = ex->str_pool[lit->lit.pool_offset + b];
+    for (uint32_t e = 0; e < C.n_entries; ++e) {
+      const int r = std::strncmp(C.h_dict.data() + static_cast<size_t>(e) * w, l.data(), w);
+      (r < 0 ? n_lt : r > 0 ? n_gt : n_eq)++;
+    }
+  } else {
+    const uint8_t own = vtype_of(attr->type), lown = vtype_of(lit->type);
+    if (own == 0xff || lown == 0xff) return fail(QSGPU_ERR_UNSUPPORTED, "comparison of a coded attribute with a non-numeric literal");
+    const uint8_t T = unify(own, lown);
+    const uint64_t lv = host_cvt(literal_raw(lit), lown, T);
+    for (uint32_t e = 0; e < C.n_entries; ++e) {
+      const uint64_t dv = host_cvt(dict_raw(C.h_dict.data() + static_cast<size_t>(e) * w, attr->type), own, T);
+      const int r = host_cmp3(T, dv, lv);
+      if (r < 0) ++n_lt; else if (r == 0) ++n_eq; else if (r == 1) ++n_gt;
+    }
+  }
+  // codes [0, n_lt) are below the literal, [n_lt, n_lt + n_eq) equal, the last n_gt above
+  const uint64_t n = C.n_entries;
+  uint64_t lo = 0, span = 0;
+  bool negate = false;
+  switch (cmp) {
+    case QS_EQ: lo = n_lt; span = n_eq; break;
+    case QS_NE: lo = n_lt; span = n_eq; negate = true; break;   // NaN literal: span 0, every row differs
+    case QS_LT: lo = 0; span = n_lt; break;
+    case QS_LE: lo = 0; span = n_lt + n_eq; break;
+    case QS_GT: lo = n - n_gt; span = n_gt; break;
+    default: lo = n - n_gt - n_eq; span = n_gt + n_eq; break;   // QS_GE
+  }
+  Instr in{};
+  in.op = OP_CMP_CODE;
+  in.arg = static_cast<uint16_t>(stage_attr(a, USE_CODE));
+  in.flags = negate ? 1 : 0;
+  in.aux = static_cast<uint8_t>(add_lit(lo));
+  add_lit(span);
+  push(in);
+  return ok();
+}
+
 void Lowering::lower_pred(int i) {
   const qs_node *n = node(i);
   if (!n || !ok()) return;
@@ -303,6 +391,18 @@ void Lowering::lower_pred(int i) {
       const qs_node *l = node(n->a), *r = node(n->b);
       if (!l || !r) return;
       if (n->op > QS_GE) { fail(QSGPU_ERR_UNSUPPORTED, "LIKE / regex comparisons are not lowered"); return; }
+      {
+        // coded attribute vs literal (either order): evaluated on the codes
+        const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
+        const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
+        if (attr->kind == QS_N_ATTRIBUTE && lit->kind == QS_N_LITERAL && attr->b != 2 && rel &&
+            static_cast<uint32_t>(attr->a) < rel->attrs.size() && rel->code_width(static_cast<uint32_t>(attr->a)) != 0 &&
+            ((attr->type == QS_CHAR) == (lit->type == QS_CHAR)) &&
+            (attr->type != QS_CHAR || lit->lit.pool_offset + lit->width <= ex->str_pool_bytes)) {
+          lower_code_compare(attr, lit, attr == l ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op)));
+          return;
+        }
+      }
       if (l->type == QS_CHAR || r->type == QS_CHAR) {
         // attribute vs literal only; the literal is NUL-padded to the attribute width
         const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;

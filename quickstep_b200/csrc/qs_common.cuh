@@ -56,6 +56,8 @@ enum Op : uint8_t {
   OP_EMIT,        // sink.emit(arg, acc)
   OP_EMIT_RAW,    // sink.emit_raw(arg, column[flags])  (pass-through attribute)
   OP_EMIT_RAW_BUILD, // sink.emit_raw_build(arg, build column[flags])
+  OP_CMP_CODE,    // push((code(col[arg]) - lits[aux]) < lits[aux+1], unsigned) ^ (flags&1): a comparison of a
+                  // dictionary-coded attribute with a literal, translated by the host into a code range
 };
 
 enum Leaf : uint8_t { LEAF_COL = 0, LEAF_LIT = 1, LEAF_TMP = 2, LEAF_BUILD = 3 /*join build side*/ };
@@ -89,9 +91,18 @@ struct Program {
 };
 
 struct ColDesc {
-  const char *ptr;      // device base pointer (row 0 of the relation)
-  uint32_t width;       // bytes per value
-  uint32_t smem_off;    // byte offset of this column's tile inside a stage
+  const char *ptr;      // device base pointer (row 0 of the relation): native values, or codes when cw != 0
+  uint32_t width;       // bytes per native value
+  uint32_t smem_off;    // byte offset of this column's native-value tile inside a stage
+  // Dictionary-coded attribute (cw = 1, 2 or 4 bytes per row in HBM; 0 = native column).  The tile the TMA
+  // unit brings in holds codes at code_off; scalar leaves look values up in `dict` (sorted, native width,
+  // readable for every code value of a 1/2-byte code), comparisons with literals run on the codes, and
+  // only uses that need the native bytes in place (group-by keys, pass-through projections, join / LIP keys)
+  // make the CTA expand the tile into smem_off first (expand != 0).
+  const char *dict;
+  uint32_t dict_entries;
+  uint32_t code_off;
+  uint8_t cw, expand, pad[6];
 };
 
 struct LipDesc {

@@ -12,10 +12,22 @@
 #include "qs_ops.cuh"
 #include "qsgpu.h"
 
+// Relation-wide dictionary of an attribute held as codes (qsgpu_relation_set_dictionary).
+struct qs_coded_attr {
+  uint32_t cw = 0;                 // bytes per code in HBM: 1, 2 or 4; 0 = native column
+  uint32_t n_entries = 0;
+  char *d_dict = nullptr;          // device copy, readable for every code value of a 1/2-byte code
+  std::vector<char> h_dict;        // host copy: literals are translated into code ranges at lowering time
+};
+
 struct qsgpu_relation {
   int dev = 0;
   std::vector<qs_attr> attrs;
   std::vector<char *> cols;
+  std::vector<qs_coded_attr> coded;   // empty, or one per attribute
+  uint32_t code_width(uint32_t a) const { return a < coded.size() ? coded[a].cw : 0u; }
+  uint32_t stored_width(uint32_t a) const { const uint32_t c = code_width(a); return c ? c : attrs[a].width; }
+  bool has_codes() const { for (const auto &c : coded) if (c.cw) return true; return false; }
   bool owns_memory = true;
   uint64_t capacity = 0;
   // Row count: authoritative copy lives on the device (kernels append with

@@ -68,6 +68,9 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
     << ", stage_bytes = " << S.stage_bytes << ";\n";
   table(o, "uint32_t", "col_w", S.n_cols, S.cols, [](const ColDesc &c) { return c.width; });
   table(o, "uint32_t", "col_off", S.n_cols, S.cols, [](const ColDesc &c) { return c.smem_off; });
+  table(o, "uint32_t", "col_cw", S.n_cols, S.cols, [](const ColDesc &c) { return c.cw; });
+  table(o, "uint32_t", "col_coff", S.n_cols, S.cols, [](const ColDesc &c) { return c.code_off; });
+  table(o, "uint32_t", "col_expand", S.n_cols, S.cols, [](const ColDesc &c) { return c.expand; });
   o << "  static constexpr int n_pred = " << P.n_pred << ", n_mid = " << P.n_mid << ", n_total = " << P.n_total
     << ";\n";
   o << "  QSC Instr code(int pc) { constexpr Instr t[] = {";
@@ -113,6 +116,7 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
     o << "  static constexpr bool j_key2 = " << (J.key2_present ? "true" : "false") << ";\n";
     o << "  static constexpr uint32_t j_key2_col = " << J.key2_col << ";\n";
     table(o, "uint32_t", "build_w", J.n_build_cols, J.build_cols, [](const ColDesc &c) { return c.width; });
+    table(o, "uint32_t", "build_cw", J.n_build_cols, J.build_cols, [](const ColDesc &c) { return c.cw; });
   }
   o << "};\n}  // namespace qs\n";
   // kernel name = family + hash of the description, so launch lists and ncu reports tell queries apart

@@ -26,7 +26,7 @@
 //   n_agg words hot grouped strategy n_key_cols key_words  aggregation
 //   agg_kind(j) key_col(k) key_w(k) key_off(k)
 //   n_out out_w(j) n_lip_build lb_col(i) lb_ltype(i) lb_kind(i)   output side
-//   j_key_col j_key_ltype j_type build_w(c)                join
+//   j_key_col j_key_ltype j_type build_w(c) build_cw(c)    join
 #pragma once
 
 #include "qs_compact.cuh"
@@ -712,13 +712,26 @@ struct JoinSink : SinkBase {
         }
         continue;
       }
-      copy_value<W>(K->out[JJ] + idx[r] * W, J->build_cols[COL].ptr + brow[r] * W);
+      copy_value<W>(K->out[JJ] + idx[r] * W, build_value<COL, W>(brow[r]));
+    }
+  }
+  // Address of build row `row`'s value of build column COL: the native column, or -- for a dictionary-coded
+  // build attribute -- the dictionary entry its code selects (the TupleReference gather goes through the code).
+  template <int COL, int W>
+  __device__ __forceinline__ const char *build_value(uint64_t row) const {
+    const ColDesc &C = J->build_cols[COL];
+    if constexpr (Q::build_cw(COL) != 0) {
+      uint32_t c = load_code_w<Q::build_cw(COL)>(C.ptr + row * Q::build_cw(COL));
+      if constexpr (Q::build_cw(COL) == 4) c = c < C.dict_entries ? c : C.dict_entries - 1;
+      return C.dict + static_cast<uint64_t>(c) * W;
+    } else {
+      return C.ptr + row * W;
     }
   }
   template <int COL, int LTYPE, int W>
   __device__ __forceinline__ uint64_t build_leaf(int r) {
     if (brow[r] == kEmptyRow) return 0;
-    return load_native(J->build_cols[COL].ptr + brow[r] * W, LTYPE);
+    return load_native(build_value<COL, W>(brow[r]), LTYPE);
   }
 };
 

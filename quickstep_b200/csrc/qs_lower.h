@@ -29,6 +29,10 @@ struct Lowering {
   Program P;
   std::vector<int> slot_of_attr;              // scanned attr -> staged column slot
   std::vector<uint32_t> staged_attrs;         // slot -> attr
+  // How a staged attribute is used (matters for dictionary-coded attributes only): USE_CODE comparisons on
+  // codes, USE_VALUE scalar leaves (dictionary lookup in registers), USE_RAW native bytes needed in the tile.
+  enum : uint8_t { USE_CODE = 1, USE_VALUE = 2, USE_RAW = 4 };
+  std::vector<uint8_t> staged_use;            // slot -> OR of the uses
   std::vector<int> bslot_of_attr;             // build attr -> JoinDesc::build_cols slot
   std::vector<uint32_t> build_attrs;
   uint32_t n_code = 0, n_lits = 0, n_str = 0;
@@ -43,7 +47,8 @@ struct Lowering {
   bool fail(int st, const std::string &m) { if (status == QSGPU_OK) { status = st; err = m; } return false; }
   bool ok() const { return status == QSGPU_OK; }
 
-  int stage_attr(uint32_t attr);              // staged slot of a scanned attribute
+  int stage_attr(uint32_t attr, uint8_t use = USE_RAW);   // staged slot of a scanned attribute
+  bool lower_code_compare(const qs_node *attr, const qs_node *lit, uint8_t cmp);   // coded attribute <cmp> literal
   int build_attr(uint32_t attr);
   void push(Instr in);
   int add_lit(uint64_t v);
@@ -63,5 +68,6 @@ struct Lowering {
 
 uint8_t vtype_of(uint16_t qs_type);           // native VType (QS_DATE -> V_DATE)
 uint8_t unify(uint8_t a, uint8_t b);
+int dict_compare(uint16_t qs_type, uint32_t width, const char *a, const char *b);   // -1 / 0 / 1, 2 = unordered
 
 }  // namespace qs

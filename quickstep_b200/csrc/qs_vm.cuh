@@ -59,6 +59,24 @@ __device__ __forceinline__ uint32_t native_width(uint8_t ltype) {
   return (ltype == V_I32 || ltype == V_F32) ? 4u : 8u;
 }
 
+// Dictionary code of a row (CompressedTupleStorageSubBlock codes are 1, 2 or 4 bytes,
+// storage/CompressedTupleStorageSubBlock.hpp:93-120).
+template <uint32_t CW>
+__device__ __forceinline__ uint32_t load_code_w(const char *p) {
+  if constexpr (CW == 1) return *reinterpret_cast<const uint8_t *>(p);
+  else if constexpr (CW == 2) return *reinterpret_cast<const uint16_t *>(p);
+  else return *reinterpret_cast<const uint32_t *>(p);
+}
+// Row `row` of a coded column tile -> byte offset of its value inside the dictionary.  1/2-byte codes index a
+// dictionary buffer that is readable for every code value; 4-byte codes are clamped (rows past the end of a
+// ragged tile hold whatever the shared memory held before).
+template <uint32_t CW, uint32_t W>
+__device__ __forceinline__ uint32_t dict_offset(const char *codes, uint32_t row, uint32_t dict_entries) {
+  uint32_t c = load_code_w<CW>(codes + row * CW);
+  if constexpr (CW == 4) c = c < dict_entries ? c : dict_entries - 1;
+  return c * W;
+}
+
 // Value conversion with C++ static_cast semantics (types/*Type.cpp coerceValue).
 __device__ __forceinline__ uint64_t vcvt(uint64_t raw, uint8_t from, uint8_t to) {
   if (from == V_DATE) from = V_I64;
@@ -194,11 +212,22 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
     constexpr bool wants_leaf = (in.op <= OP_MOD) || in.op == OP_CMP;
     if constexpr (wants_leaf) {
       if constexpr (in.leaf == LEAF_COL) {
-        const char *base = stage + Q::col_off(in.arg);
         constexpr uint32_t w = (in.ltype == V_I32 || in.ltype == V_F32) ? 4u : 8u;
+        if constexpr (Q::col_cw(in.arg) != 0 && !Q::col_expand(in.arg)) {
+          // dictionary-coded attribute: value = dict[code], the code tile is all that came from HBM
+          const char *codes = stage + Q::col_coff(in.arg);
+          const char *dict = S.cols[in.arg].dict;
+          const uint32_t n = S.cols[in.arg].dict_entries;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r)
-          leaf[r] = vcvt(load_native(base + tile_row(r, tid) * w, in.ltype), in.ltype, in.type);
+          for (int r = 0; r < kRows; ++r)
+            leaf[r] = vcvt(load_native(dict + dict_offset<Q::col_cw(in.arg), w>(codes, tile_row(r, tid), n), in.ltype),
+                           in.ltype, in.type);
+        } else {
+          const char *base = stage + Q::col_off(in.arg);
+#pragma unroll
+          for (int r = 0; r < kRows; ++r)
+            leaf[r] = vcvt(load_native(base + tile_row(r, tid) * w, in.ltype), in.ltype, in.type);
+        }
       } else if constexpr (in.leaf == LEAF_LIT) {
         const uint64_t v = L.lits[in.arg];
 #pragma unroll
@@ -247,6 +276,19 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const bool b = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit);
+        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
+      }
+    } else if constexpr (in.op == OP_CMP_CODE) {
+      // attribute <cmp> literal on a dictionary-coded attribute: the host turned the literal into the range
+      // of codes that satisfy it (the dictionary is sorted), CompressedTupleStorageSubBlock::getMatchesForPredicate
+      // (storage/CompressedTupleStorageSubBlock.cpp:160-251); one unsigned range test per row, no value load
+      const char *codes = stage + Q::col_coff(in.arg);
+      const uint32_t lo = static_cast<uint32_t>(L.lits[in.aux]);
+      const uint32_t span = static_cast<uint32_t>(L.lits[in.aux + 1]);
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const uint32_t c = load_code_w<Q::col_cw(in.arg)>(codes + tile_row(r, tid) * Q::col_cw(in.arg));
+        const bool b = ((c - lo) < span) != ((in.flags & 1) != 0);
         bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
       }
     } else if constexpr (in.op == OP_AND) {
@@ -317,12 +359,52 @@ __device__ __forceinline__ void issue_tile(const ScanDesc &S, const ScanRt &rt, 
   const uint64_t row0 = S.first_row + static_cast<uint64_t>(tile) * kTileRows;
   uint64_t rows64 = rt.row_end - row0;
   const uint32_t rows = rows64 > kTileRows ? kTileRows : static_cast<uint32_t>(rows64);
+  // a coded attribute travels as codes (col_cw bytes per row) into its code tile
   uint32_t total = 0;
-  static_for<0, Q::n_cols>([&](auto c) { total += (rows * Q::col_w(QS_IDX(c)) + 15u) & ~15u; });
+  static_for<0, Q::n_cols>([&](auto c) {
+    constexpr uint32_t w = Q::col_cw(QS_IDX(c)) ? Q::col_cw(QS_IDX(c)) : Q::col_w(QS_IDX(c));
+    total += (rows * w + 15u) & ~15u;
+  });
   mbar_expect_tx(bar, total);
   static_for<0, Q::n_cols>([&](auto c) {
-    constexpr uint32_t w = Q::col_w(QS_IDX(c));
-    bulk_g2s(stage + Q::col_off(QS_IDX(c)), S.cols[QS_IDX(c)].ptr + row0 * w, (rows * w + 15u) & ~15u, bar);
+    constexpr bool coded = Q::col_cw(QS_IDX(c)) != 0;
+    constexpr uint32_t w = coded ? Q::col_cw(QS_IDX(c)) : Q::col_w(QS_IDX(c));
+    constexpr uint32_t off = coded ? Q::col_coff(QS_IDX(c)) : Q::col_off(QS_IDX(c));
+    bulk_g2s(stage + off, S.cols[QS_IDX(c)].ptr + row0 * w, (rows * w + 15u) & ~15u, bar);
+  });
+}
+
+// Coded attributes whose native bytes are needed in place (group-by keys, pass-through projections, join and
+// LIP keys, CHAR comparisons against non-literals): the CTA decodes the code tile into the attribute's native
+// tile once per tile.  Attributes that are only compared with literals or read as scalar leaves never get here.
+template <class Q>
+__device__ __forceinline__ constexpr bool any_expand() {
+  bool any = false;
+  for (int c = 0; c < static_cast<int>(Q::n_cols); ++c) any = any || (Q::col_cw(c) != 0 && Q::col_expand(c));
+  return any;
+}
+template <class Q>
+__device__ __forceinline__ void expand_tile(const ScanDesc &S, char *stage, int tid) {
+  static_for<0, Q::n_cols>([&](auto cc) {
+    constexpr int c = QS_IDX(cc);
+    if constexpr (Q::col_cw(c) != 0 && Q::col_expand(c)) {
+      constexpr uint32_t w = Q::col_w(c);
+      const char *codes = stage + Q::col_coff(c);
+      const char *dict = S.cols[c].dict;
+      const uint32_t n = S.cols[c].dict_entries;
+      char *out = stage + Q::col_off(c);
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const uint32_t row = tile_row(r, tid);
+        const char *src = dict + dict_offset<Q::col_cw(c), w>(codes, row, n);
+        if constexpr (w == 8) *reinterpret_cast<uint64_t *>(out + row * 8u) = *reinterpret_cast<const uint64_t *>(src);
+        else if constexpr (w == 4) *reinterpret_cast<uint32_t *>(out + row * 4u) = *reinterpret_cast<const uint32_t *>(src);
+        else {
+#pragma unroll
+          for (uint32_t b = 0; b < w; ++b) out[row * w + b] = src[b];
+        }
+      }
+    }
   });
 }
 
@@ -353,6 +435,10 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
   for (uint32_t tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
     char *stage = stages + s * Q::stage_bytes;
     mbar_wait(&bars[s], parity);
+    if constexpr (any_expand<Q>()) {
+      expand_tile<Q>(S, stage, tid);
+      __syncthreads();
+    }
     body(tile, stage, rt);
     __syncthreads();
     if (tid == 0) {

@@ -126,6 +126,67 @@ class Relation:
         A.check(L.qsgpu_relation_wrap(dev, len(schema), _attrs(schema), ptrs, n_rows, C.byref(out)))
         return cls(out, schema, names, dev, keep=keep)
 
+    def set_dictionary(self, attr: int, code_width: int, dict_values: np.ndarray):
+        """qsgpu_relation_set_dictionary: attribute `attr` is resident as `code_width`-byte codes into the sorted
+        relation-wide dictionary `dict_values` (native values)."""
+        t, w = self.schema[attr]
+        d = np.ascontiguousarray(dict_values)
+        assert d.dtype.itemsize == np_dtype(t, w).itemsize
+        A.check(A.load().qsgpu_relation_set_dictionary(self.h, attr, code_width, d.ctypes.data, len(d)))
+
+    def dictionary(self, attr: int):
+        """-> (code_width, dictionary values) ; code_width 0 = native attribute."""
+        cw, n = C.c_uint32(0), C.c_uint32(0)
+        A.check(A.load().qsgpu_relation_dictionary(self.h, attr, C.byref(cw), C.byref(n), None))
+        t, w = self.schema[attr]
+        out = np.zeros(max(n.value, 1), dtype=np_dtype(t, w))
+        if cw.value:
+            A.check(A.load().qsgpu_relation_dictionary(self.h, attr, None, None, out.ctypes.data))
+        return cw.value, out[: n.value]
+
+    @classmethod
+    def from_host_coded(cls, table: HostTable, coded: dict, dev=0, block_rows=None):
+        """Stage a host table as compressed-column-store style blocks of `block_rows` tuples: attributes in
+        `coded` ({attr index: code width}) are declared dictionary-coded relation-wide and arrive as
+        QS_ENC_DICT stripes with PER-BLOCK dictionaries (re-coded by qsgpu_stage_blocks); the others as plain
+        stripes.  Test / bench harness helper: the host side only builds the block images."""
+        schema = [(c.type, c.width) for c in table.columns]
+        rel = cls.create(schema, max(table.n_rows, 1), [c.name for c in table.columns], dev)
+        for a, cw in coded.items():
+            rel.set_dictionary(a, cw, np.unique(table.columns[a].data))
+        step = block_rows or max(table.n_rows, 1)
+        images = []
+        for lo in range(0, table.n_rows, step):
+            hi = min(table.n_rows, lo + step)
+            parts, descs, off = [], [], 0
+
+            def put(arr):
+                nonlocal off
+                b = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+                pad = (-len(b)) % 16
+                start = off
+                parts.append(b)
+                if pad:
+                    parts.append(np.zeros(pad, dtype=np.uint8))
+                off += len(b) + pad
+                return start
+
+            for a, c in enumerate(table.columns):
+                data = c.data[lo:hi]
+                if a in coded:
+                    d, inv = np.unique(data, return_inverse=True)
+                    bcw = 1 if len(d) <= 256 else 2 if len(d) <= 65536 else 4
+                    doff = put(d)
+                    coff = put(inv.astype({1: np.uint8, 2: np.uint16, 4: np.uint32}[bcw]))
+                    descs.append(dict(attr=a, encoding=A.QS_ENC_DICT, offset=coff, code_width=bcw, dict_offset=doff,
+                                      dict_entries=len(d)))
+                else:
+                    descs.append(dict(attr=a, encoding=A.QS_ENC_PLAIN, offset=put(data)))
+            images.append((np.concatenate(parts) if parts else np.zeros(16, np.uint8), hi - lo, descs))
+        if images:
+            rel.stage_blocks(images)
+        return rel
+
     def stage_plain(self, arrays):
         descs = (A.qs_stage_desc * len(arrays))()
         keep = []

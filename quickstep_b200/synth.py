@@ -106,6 +106,52 @@ def wrap_relations(E, cols: dict, dev: int):
     return rels
 
 
+# CHAR(1) flags stay native: a 1-byte code saves nothing
+LINEITEM_CODED = ("l_quantity", "l_discount", "l_tax", "l_shipdate")
+
+
+def wrap_lineitem_coded(E, cols: dict, dev: int, coded=LINEITEM_CODED):
+    """lineitem with the low-cardinality attributes resident as dictionary codes (what the reference's
+    compressed-column-store blocks of lineitem hold, benchmarks/tpch/create.sql): the sorted dictionary and the
+    code column of each attribute are derived on the device with torch.unique (harness plumbing, like the
+    generator itself) and handed over with qsgpu_relation_wrap + qsgpu_relation_set_dictionary.
+    -> (relation, {name: (code width, dictionary entries)})"""
+    import numpy as np
+    schema = T.LINEITEM
+    bufs, dicts, info = [], {}, {}
+    for a, (name, t, w) in enumerate(schema):
+        col = cols[name]
+        if name not in coded:
+            bufs.append(_padded(col))
+            continue
+        if t == A.QS_DATE:      # packed DateLit -> order-preserving key (year, month, day) for the sort
+            key = ((col & 0xFFFFFFFF) << 16) | (((col >> 32) & 0xFF) << 8) | ((col >> 40) & 0xFF)
+            uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+            d = ((uniq >> 16) & 0xFFFFFFFF) | (((uniq >> 8) & 0xFF) << 32) | ((uniq & 0xFF) << 40)
+            del key
+        else:
+            d, inv = torch.unique(col.reshape(col.shape[0], -1)[:, 0] if col.dim() > 1 else col, sorted=True, return_inverse=True)
+        n = d.numel()
+        cw = 1 if n <= 256 else 2 if n <= 65536 else 4
+        codes = inv.to({1: torch.uint8, 2: torch.int16, 4: torch.int32}[cw])   # int16 holds the u16 bit pattern
+        del inv
+        bufs.append(_padded(codes))
+        dicts[a] = (cw, d.cpu().numpy())
+        info[name] = (cw, n)
+    n_rows = cols[schema[0][0]].shape[0]
+    rel = E.Relation.wrap([(t, w) for (_n, t, w) in schema], [b.data_ptr() for b in bufs], n_rows,
+                          [n for (n, _t, _w) in schema], dev, keep=bufs)
+    for a, (cw, d) in dicts.items():
+        t, w = schema[a][1], schema[a][2]
+        if t == A.QS_DATE:
+            from .table import DATE_DTYPE
+            d = d.view(DATE_DTYPE)
+        elif t == A.QS_CHAR:
+            d = np.ascontiguousarray(d).view(f"S{w}")
+        rel.set_dictionary(a, cw, d)
+    return rel, info
+
+
 def host_table(cols: dict, schema, n: int | None = None):
     """Host (numpy) copy of one relation's columns, for the CPU baseline and the e2e legs."""
     from .table import Column, HostTable, DATE_DTYPE

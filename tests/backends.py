@@ -211,6 +211,34 @@ class GpuBackend:
         self._live = []
 
 
+class CodedGpuBackend(GpuBackend):
+    """GpuBackend whose base relations hold every eligible attribute as dictionary codes (the compressed block
+    format as a device format): blocks of `block_rows` tuples with per-block dictionaries are re-coded into
+    one relation-wide dictionary by qsgpu_stage_blocks, and every operator then scans the codes.  `min_cw`
+    forces wider codes than the cardinality needs (covers the 2- and 4-byte paths on small inputs)."""
+    name = "gpu-coded"
+
+    def __init__(self, engine, block_rows=1000, min_cw=1):
+        super().__init__(engine, block_rows)
+        self.min_cw = min_cw
+        self.n_coded = 0
+
+    def relation(self, table: HostTable):
+        coded = {}
+        for a, c in enumerate(table.columns):
+            d = c.data
+            if len(d) == 0:
+                continue
+            if d.dtype.kind == "f" and (np.isnan(d).any() or (np.signbit(d) & (d == 0)).any()):
+                continue            # NaN has no place in a sorted dictionary; -0.0 == 0.0 would share an entry
+            n = len(np.unique(d))
+            coded[a] = max(self.min_cw, 1 if n <= 256 else 2 if n <= 65536 else 4)
+        self.n_coded += len(coded)
+        r = self.E.Relation.from_host_coded(table, coded, block_rows=self.block_rows)
+        self._live.append(r)
+        return r
+
+
 def table_rows(t: HostTable):
     """Order-insensitive comparison helper: rows as a sorted list of byte strings."""
     n = t.n_rows
