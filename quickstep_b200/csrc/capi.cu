@@ -138,7 +138,7 @@ struct KernelTimer {
 };
 
 // Picks ring depth, shared memory size and grid for a scan.
-int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
+int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan, int max_ctas) {
   uint32_t stage = 0;
   for (uint32_t c = 0; c < S->n_cols; ++c) {
     ColDesc &C = S->cols[c];
@@ -153,7 +153,15 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   stage = (stage + 127u) & ~127u;
   if (stage == 0) stage = 128;
   S->stage_bytes = stage;
-  const size_t fixed = kBarBytes + extra_smem + 256;
+  // shared-memory copies of the dictionaries of 1-byte-coded attributes whose values the kernel looks up
+  size_t dict_bytes = 0;
+  for (uint32_t c = 0; c < S->n_cols; ++c)
+    if (S->cols[c].dict_smem) dict_bytes += 256u * S->cols[c].width;
+  if (dict_bytes > 16384) {   // CHAR(n) dictionaries can be wide: leave those in global memory (L1-cached)
+    for (uint32_t c = 0; c < S->n_cols; ++c) S->cols[c].dict_smem = 0;
+    dict_bytes = 0;
+  }
+  const size_t fixed = kBarBytes + extra_smem + 256 + dict_bytes;
   const size_t per_sm = d->smem_per_sm;                     // 228 KB on B200
   const size_t per_block_max = d->smem_per_block_optin;     // 227 KB
   // Resident CTAs per SM the shared-memory ring allows: narrow scans (join keys, LIP builds: a few KB per
@@ -162,7 +170,7 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   // compiled kernel (launch_query_kernel).
   int ctas = 1;
   size_t budget = per_block_max;
-  for (int c = 4; c >= 2; --c) {
+  for (int c = std::min(4, std::max(1, max_ctas)); c >= 2; --c) {
     const size_t b = per_sm / c - 1024;                     // 1 KB per CTA is reserved by the driver
     if (fixed + 2ull * stage <= b) { ctas = c; budget = b; break; }     // double buffering is the minimum
   }
@@ -174,6 +182,12 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan) {
   if (n_stages > static_cast<uint32_t>(kMaxStages)) n_stages = kMaxStages;
   S->n_stages = n_stages;
   plan->smem = kBarBytes + static_cast<size_t>(n_stages) * stage + extra_smem + 64;
+  plan->smem = (plan->smem + 15) & ~static_cast<size_t>(15);
+  for (uint32_t c = 0; c < S->n_cols; ++c) {
+    if (!S->cols[c].dict_smem) continue;
+    S->cols[c].dict_soff = static_cast<uint32_t>(plan->smem);
+    plan->smem += 256u * S->cols[c].width;
+  }
   plan->ctas = ctas;
   int grid = d->sm_count * ctas;
   if (S->d_row_end == nullptr && S->n_tiles < static_cast<uint32_t>(grid)) grid = std::max<int>(1, S->n_tiles);
@@ -268,6 +282,8 @@ static int fill_scan(const qsgpu_relation *rel, uint64_t row_begin, uint64_t row
       S->cols[c].dict = rel->coded[a].d_dict;
       S->cols[c].dict_entries = rel->coded[a].n_entries;
       S->cols[c].expand = (L.staged_use[c] & Lowering::USE_RAW) ? 1 : 0;
+      S->cols[c].dict_smem = (cw == 1 && rel->attrs[a].width <= 16 &&
+                              (L.staged_use[c] & (Lowering::USE_RAW | Lowering::USE_VALUE))) ? 1 : 0;
     }
   }
   return QSGPU_OK;
@@ -1281,7 +1297,10 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
   QS_CUDA(dev_malloc(&s->d_idx_count, 256));
   if (spec->strategy == QS_AGG_SINGLE_STATE || spec->strategy == QS_AGG_COMPACT_KEY) {
-    s->max_ctas = static_cast<uint32_t>(d->sm_count) * 2;
+    // one partial row set per CTA of the persistent grid: up to 4 resident CTAs per SM for states with a few
+    // partial rows (Q6 on dictionary codes: 12 KB tiles, 32 registers), 2 for the 256-group compact-key states
+    // (their kernels hold the hot groups' sums in registers and never fit more than 2)
+    s->max_ctas = static_cast<uint32_t>(d->sm_count) * (A.partial_rows <= 8 ? 4u : 2u);
     const size_t prow = static_cast<size_t>(A.partial_rows) * A.words * 8;
     QS_CUDA(dev_malloc(&A.partials, prow * s->max_ctas));
     // every partial row starts as (and is reset to, by k_merge_partials) the identity, so rows of
@@ -1391,10 +1410,22 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     const int hot = agg_hot_groups(A);
     st = plan_scan(d, &S, agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words), &plan);
     if (st) return st;
-    if (static_cast<uint32_t>(plan.grid) > state->max_ctas) plan.grid = static_cast<int>(state->max_ctas);
+    // wide tiles (native Q6: 32 KB) measured best with 2 resident CTAs per SM (0.269 vs 0.279 ms with 3); narrow
+    // code tiles take all 4 (Q6 on codes: 0.143 -> 0.128 ms)
+    const uint32_t grid_cap = std::min<uint32_t>(state->max_ctas, static_cast<uint32_t>(d->sm_count) * (S.stage_bytes <= 16384 ? 4u : 2u));
+    if (static_cast<uint32_t>(plan.grid) > grid_cap) plan.grid = static_cast<int>(grid_cap);
     JitKernel *kern = nullptr;
     st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern);
     if (st) return st;
+    // The ring was sized for the CTAs the shared memory allows; when the compiled kernel's registers allow fewer
+    // (Q1: 2), give each resident CTA the deeper ring its share of the SM's shared memory affords.
+    if (const int occ = jit_occupancy(kern, plan.smem); occ > 0 && occ < plan.ctas) {
+      st = plan_scan(d, &S, agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words), &plan, occ);
+      if (st) return st;
+      if (static_cast<uint32_t>(plan.grid) > grid_cap) plan.grid = static_cast<int>(grid_cap);
+      st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern);
+      if (st) return st;
+    }
     {
       KernelTimer timer(d, QS_K_SCAN_AGG);      // the scan kernel alone (roofline numerator)
       QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, &A, nullptr, nullptr));

@@ -102,7 +102,11 @@ struct ColDesc {
   const char *dict;
   uint32_t dict_entries;
   uint32_t code_off;
-  uint8_t cw, expand, pad[6];
+  uint8_t cw, expand;
+  // dict_smem: the CTA keeps a copy of the dictionary in shared memory at byte dict_soff of its dynamic shared
+  // memory (1-byte codes only: 256 entries, so any code value stays inside the copy)
+  uint8_t dict_smem, pad;
+  uint32_t dict_soff;
 };
 
 struct LipDesc {

@@ -144,7 +144,7 @@ struct ScanPlan {
   int ctas = 2;        // resident CTAs per SM the shared-memory budget allows
   size_t smem = 0;
 };
-int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan);
+int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan, int max_ctas = 4);
 
 }  // namespace qs
 

@@ -71,6 +71,8 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
   table(o, "uint32_t", "col_cw", S.n_cols, S.cols, [](const ColDesc &c) { return c.cw; });
   table(o, "uint32_t", "col_coff", S.n_cols, S.cols, [](const ColDesc &c) { return c.code_off; });
   table(o, "uint32_t", "col_expand", S.n_cols, S.cols, [](const ColDesc &c) { return c.expand; });
+  table(o, "uint32_t", "col_dsmem", S.n_cols, S.cols, [](const ColDesc &c) { return c.dict_smem; });
+  table(o, "uint32_t", "col_doff", S.n_cols, S.cols, [](const ColDesc &c) { return c.dict_soff; });
   o << "  static constexpr int n_pred = " << P.n_pred << ", n_mid = " << P.n_mid << ", n_total = " << P.n_total
     << ";\n";
   o << "  QSC Instr code(int pc) { constexpr Instr t[] = {";

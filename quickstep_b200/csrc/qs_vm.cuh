@@ -77,6 +77,15 @@ __device__ __forceinline__ uint32_t dict_offset(const char *codes, uint32_t row,
   return c * W;
 }
 
+// The kernel's dynamic shared memory (every extern __shared__ array starts at the same address): dictionaries
+// of 1-byte-coded attributes are copied to Q::col_doff(c) by scan_tiles before the first tile.
+extern __shared__ __align__(128) char qs_dyn_smem[];
+template <class Q, int C>
+__device__ __forceinline__ const char *dict_of(const ScanDesc &S) {
+  if constexpr (Q::col_dsmem(C) != 0) return qs_dyn_smem + Q::col_doff(C);
+  else return S.cols[C].dict;
+}
+
 // Value conversion with C++ static_cast semantics (types/*Type.cpp coerceValue).
 __device__ __forceinline__ uint64_t vcvt(uint64_t raw, uint8_t from, uint8_t to) {
   if (from == V_DATE) from = V_I64;
@@ -216,7 +225,7 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
         if constexpr (Q::col_cw(in.arg) != 0 && !Q::col_expand(in.arg)) {
           // dictionary-coded attribute: value = dict[code], the code tile is all that came from HBM
           const char *codes = stage + Q::col_coff(in.arg);
-          const char *dict = S.cols[in.arg].dict;
+          const char *dict = dict_of<Q, in.arg>(S);
           const uint32_t n = S.cols[in.arg].dict_entries;
 #pragma unroll
           for (int r = 0; r < kRows; ++r)
@@ -390,7 +399,7 @@ __device__ __forceinline__ void expand_tile(const ScanDesc &S, char *stage, int 
     if constexpr (Q::col_cw(c) != 0 && Q::col_expand(c)) {
       constexpr uint32_t w = Q::col_w(c);
       const char *codes = stage + Q::col_coff(c);
-      const char *dict = S.cols[c].dict;
+      const char *dict = dict_of<Q, c>(S);
       const uint32_t n = S.cols[c].dict_entries;
       char *out = stage + Q::col_off(c);
 #pragma unroll
@@ -424,6 +433,16 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
     for (uint32_t s = 0; s < Q::n_stages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
+  // shared-memory copies of the small dictionaries (256 entries each; the device buffer is that long)
+  static_for<0, Q::n_cols>([&](auto cc) {
+    constexpr int c = QS_IDX(cc);
+    if constexpr (Q::col_cw(c) != 0 && Q::col_dsmem(c) != 0) {
+      constexpr uint32_t n16 = 256u * Q::col_w(c) / 16u;
+      const uint4 *src = reinterpret_cast<const uint4 *>(S.cols[c].dict);
+      uint4 *dst = reinterpret_cast<uint4 *>(smem + Q::col_doff(c));
+      for (uint32_t i = tid; i < n16; i += kBlock) dst[i] = src[i];
+    }
+  });
   __syncthreads();
   if (tid == 0) {
     uint32_t tile = blockIdx.x;

@@ -266,7 +266,7 @@ def test_q1_q6_codes_equal_native_full_blocks(engine, oracle):
     """2 M synthetic lineitem rows in 63k-tuple blocks: Q1 / Q6 over codes == over native columns == oracle
     (counts exact, sums 1e-9); quantity / discount / tax take 1-byte codes, shipdate 2-byte codes."""
     arrays, _ = D.synthetic_lineitem_arrays(2_000_000, 11)
-    li = D.tables_from_arrays(arrays)["lineitem"]
+    li = D._table("lineitem", T.LINEITEM, arrays)
     nat = engine.Relation.from_host(li)
     rel = _coded_lineitem(engine, li)
     try:
