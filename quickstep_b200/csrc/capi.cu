@@ -838,7 +838,7 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   Chunk cur{0, 0, 0, 0, 0};
   int rc = QSGPU_OK;
   std::vector<std::pair<uint64_t, uint64_t>> need;          // (offset, bytes) inside one block image
-  std::vector<char> remap;                                  // re-coding tables of coded attributes, all blocks
+  size_t remap_bytes = 0;                                   // re-coding tables of coded attributes, all blocks
   std::vector<std::pair<size_t, size_t>> remap_fix;         // (segment, offset of its table in `remap`)
   char *d_remap = nullptr;
   for (uint32_t b = 0; b < n_blocks && rc == QSGPU_OK; ++b) {
@@ -854,35 +854,21 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
       uint64_t bytes = 0;
       if (const uint32_t gcw = rel->code_width(s.attr)) {
         // Attribute held as codes of the relation-wide dictionary: the block's codes are re-coded through a
-        // per-block table (block code -> relation code) built here from the two sorted dictionaries; the decode
-        // kernel sees it as a dictionary whose "values" are gcw-byte codes.  The block's own dictionary stays on
-        // the host.
+        // per-block table (block code -> relation code).  The table is built ON THE DEVICE (k_build_recode: one
+        // binary search of the relation's dictionary per entry of the block's dictionary, which travels inside the
+        // block image), so the host does no per-value work; the decode kernel then sees the table as a dictionary
+        // whose "values" are gcw-byte codes.
         if (s.encoding != QS_ENC_DICT) { set_error(QSGPU_ERR_UNSUPPORTED, "a dictionary-coded attribute is staged from dictionary-compressed stripes only"); rc = QSGPU_ERR_UNSUPPORTED; break; }
         if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; break; }
         const char *hd = static_cast<const char *>(s.dict);
         bytes = B.n_rows * s.code_width;
         if (!hs || hs < h0 || hs + bytes > h0 + B.bytes || !hd || s.dict_entries == 0) { set_error(QSGPU_ERR_INVALID, "stage: stripe lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
         const qs_coded_attr &C = rel->coded[s.attr];
-        remap.resize((remap.size() + 3) & ~static_cast<size_t>(3));
-        const size_t roff = remap.size();
-        remap.resize(roff + static_cast<size_t>(s.dict_entries) * gcw);
-        uint32_t g_lo = 0;                       // both dictionaries are sorted: the search window only moves up
-        for (uint32_t e = 0; e < s.dict_entries && rc == QSGPU_OK; ++e) {
-          const char *v = hd + static_cast<size_t>(e) * w;
-          uint32_t lo = g_lo, hi = C.n_entries;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (dict_compare(rel->attrs[s.attr].type, w, C.h_dict.data() + static_cast<size_t>(mid) * w, v) == -1) lo = mid + 1; else hi = mid;
-          }
-          if (lo >= C.n_entries || dict_compare(rel->attrs[s.attr].type, w, C.h_dict.data() + static_cast<size_t>(lo) * w, v) != 0) {
-            set_error(QSGPU_ERR_INVALID, "stage: a block dictionary value is missing from the relation's dictionary");
-            rc = QSGPU_ERR_INVALID;
-            break;
-          }
-          std::memcpy(&remap[roff + static_cast<size_t>(e) * gcw], &lo, gcw);   // little endian
-          g_lo = lo;
-        }
-        if (rc != QSGPU_OK) break;
+        const uint64_t dbytes = static_cast<uint64_t>(s.dict_entries) * w;
+        if (hd < h0 || hd + dbytes > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: dictionary lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+        remap_bytes = (remap_bytes + 3) & ~static_cast<size_t>(3);
+        const size_t roff = remap_bytes;
+        remap_bytes += static_cast<size_t>(s.dict_entries) * gcw;
         StageSeg g{};
         g.dst = rel->cols[s.attr] + row_base * gcw;
         g.src = d_img + img_off[b] + (hs - h0);
@@ -890,6 +876,8 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
         g.tile_begin = cur.tiles;
         g.encoding = QS_ENC_DICT;
         g.cw = s.code_width; g.vw = gcw; g.dict_entries = s.dict_entries;
+        g.bdict = d_img + img_off[b] + (hd - h0);
+        g.gdict = C.d_dict; g.g_entries = C.n_entries; g.qtype = rel->attrs[s.attr].type; g.bw = w;
         const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
         g.aligned = ((reinterpret_cast<uintptr_t>(g.dst) % gcw) == 0 ? 1u : 0u) | (code_al ? 2u : 0u);
         if (B.n_rows) {
@@ -897,6 +885,7 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
           segs.push_back(g);
           cur.tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows;
           need.emplace_back(static_cast<uint64_t>(hs - h0), bytes);
+          need.emplace_back(static_cast<uint64_t>(hd - h0), dbytes);
         }
         continue;
       }
@@ -978,9 +967,8 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   cudaEvent_t ev = nullptr;
   if (rc == QSGPU_OK && !segs.empty()) {
     cudaError_t ce = cudaSuccess;
-    if (!remap.empty()) {
-      ce = dev_malloc(&d_remap, remap.size() + 16);
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_remap, remap.data(), remap.size(), cudaMemcpyHostToDevice, d->stream);
+    if (remap_bytes) {
+      ce = dev_malloc(&d_remap, remap_bytes + 16);
       for (const auto &f : remap_fix) segs[f.first].dict = d_remap + f.second;
     }
     if (ce == cudaSuccess) ce = dev_malloc(&d_segs, segs.size() * sizeof(StageSeg));
@@ -997,6 +985,10 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
       if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
       if (ce == cudaSuccess) ce = cudaEventRecord(done[c], d->copy_stream);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(d->stream, done[c], 0);
+      if (ce == cudaSuccess && C.seg_end > C.seg_begin && remap_bytes) {   // block codes -> relation codes tables
+        ce = launch_build_recode(d_segs + C.seg_begin, C.seg_end - C.seg_begin, d->d_error, d->stream);
+        count_launch();
+      }
       if (ce == cudaSuccess && C.seg_end > C.seg_begin) {
         ce = launch_decode_segments(d_segs + C.seg_begin, C.seg_end - C.seg_begin, C.tiles, d->sm_count, d->stream);
         count_launch();
@@ -1011,6 +1003,10 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   dev_free(d_img);
   dev_free(d_segs);
   dev_free(d_remap);
+  if (rc == QSGPU_OK && remap_bytes) {
+    rc = check_device_error(d);
+    if (rc) set_error(rc, "stage: a block dictionary value is missing from the relation's dictionary");
+  }
   if (rc != QSGPU_OK) return rc;
   const uint64_t rows_after = std::max<uint64_t>(rel->host_rows, first_row + total_rows);
   if (!append && rows_after == rel->host_rows) return QSGPU_OK;

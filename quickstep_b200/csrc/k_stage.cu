@@ -125,6 +125,70 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
   }
 }
 
+// ---- re-coding tables of dictionary-coded attributes -------------------------------------------------------
+// Block dictionaries sit wherever the block builder put them: assemble values byte by byte.
+template <class T>
+__device__ __forceinline__ T load_unaligned(const char *p) {
+  T v;
+  char *d = reinterpret_cast<char *>(&v);
+  for (uint32_t b = 0; b < sizeof(T); ++b) d[b] = p[b];
+  return v;
+}
+template <class T>
+__device__ __forceinline__ int cmp3(T a, T b) { return a < b ? -1 : a > b ? 1 : a == b ? 0 : 2; }
+
+// Order of two dictionary entries in the attribute's own order (same as dict_compare on the host, lower.cu).
+__device__ int dev_dict_compare(uint32_t qtype, uint32_t w, const char *a, const char *b) {
+  switch (qtype) {
+    case QS_INT: return cmp3(load_unaligned<int32_t>(a), load_unaligned<int32_t>(b));
+    case QS_LONG: return cmp3(load_unaligned<int64_t>(a), load_unaligned<int64_t>(b));
+    case QS_FLOAT: return cmp3(load_unaligned<float>(a), load_unaligned<float>(b));
+    case QS_DOUBLE: return cmp3(load_unaligned<double>(a), load_unaligned<double>(b));
+    case QS_DATE: {   // DateLit {int32 year; u8 month; u8 day}: lexicographic (types/DatetimeLit.hpp:65-93)
+      const int y = cmp3(load_unaligned<int32_t>(a), load_unaligned<int32_t>(b));
+      if (y) return y;
+      const int m = cmp3(static_cast<unsigned char>(a[4]), static_cast<unsigned char>(b[4]));
+      return m ? m : cmp3(static_cast<unsigned char>(a[5]), static_cast<unsigned char>(b[5]));
+    }
+    default:          // CHAR(w): strncmp
+      for (uint32_t i = 0; i < w; ++i) {
+        const unsigned char x = static_cast<unsigned char>(a[i]), y = static_cast<unsigned char>(b[i]);
+        if (x != y) return x < y ? -1 : 1;
+        if (x == 0) break;
+      }
+      return 0;
+  }
+}
+
+// One CTA per coded stripe: entry e of the block's dictionary -> its position in the relation-wide dictionary
+// (binary search; both are sorted).  A value the relation's dictionary does not hold raises the sticky error.
+__global__ void __launch_bounds__(128) k_build_recode(const StageSeg *segs, uint32_t n_segs, uint32_t *error_flag) {
+  for (uint32_t s = blockIdx.x; s < n_segs; s += gridDim.x) {
+    const StageSeg sg = segs[s];
+    if (sg.gdict == nullptr) continue;
+    char *table = const_cast<char *>(sg.dict);
+    for (uint32_t e = threadIdx.x; e < sg.dict_entries; e += blockDim.x) {
+      const char *v = sg.bdict + static_cast<uint64_t>(e) * sg.bw;
+      uint32_t lo = 0, hi = sg.g_entries;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (dev_dict_compare(sg.qtype, sg.bw, sg.gdict + static_cast<uint64_t>(mid) * sg.bw, v) == -1) lo = mid + 1; else hi = mid;
+      }
+      if (lo >= sg.g_entries || dev_dict_compare(sg.qtype, sg.bw, sg.gdict + static_cast<uint64_t>(lo) * sg.bw, v) != 0) {
+        atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_INVALID));
+        lo = 0;
+      }
+      for (uint32_t b = 0; b < sg.vw; ++b) table[static_cast<uint64_t>(e) * sg.vw + b] = static_cast<char>(lo >> (8 * b));
+    }
+  }
+}
+
+cudaError_t launch_build_recode(const StageSeg *d_segs, uint32_t n_segs, uint32_t *error_flag, cudaStream_t st) {
+  if (n_segs == 0) return cudaSuccess;
+  k_build_recode<<<n_segs < 148u * 16 ? n_segs : 148u * 16, 128, 0, st>>>(d_segs, n_segs, error_flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_decode_segments(const StageSeg *d_segs, uint32_t n_segs, uint64_t n_tiles, int sm_count,
                                    cudaStream_t st) {
   if (n_segs == 0 || n_tiles == 0) return cudaSuccess;

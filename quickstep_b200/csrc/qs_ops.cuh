@@ -80,6 +80,13 @@ struct __align__(16) StageSeg {
   uint32_t encoding;           // QS_ENC_*
   uint32_t cw, vw, stride, dict_entries;
   uint32_t aligned;            // src (and dict) are vw-aligned: whole-value loads are legal
+  // Stripe of an attribute the relation holds as codes (qsgpu_relation_set_dictionary): `dict` is this block's
+  // re-coding table (block code -> relation code, vw bytes each), filled on the device by k_build_recode from
+  // the block's own sorted dictionary `bdict` (native values of bw bytes, inside the block image) and the
+  // relation-wide dictionary `gdict`.  gdict == nullptr for every other stripe.
+  const char *bdict;
+  const char *gdict;
+  uint32_t g_entries, qtype, bw, pad;
 };
 constexpr uint32_t kStageTileRows = 4096;
 
@@ -112,6 +119,7 @@ cudaError_t launch_decode_truncated(void *dst, const void *codes, uint64_t n, ui
                                     uint32_t value_width, cudaStream_t st);
 cudaError_t launch_decode_strided(void *dst, const void *slots, uint64_t n, uint32_t stride,
                                   uint32_t value_width, cudaStream_t st);
+cudaError_t launch_build_recode(const StageSeg *d_segs, uint32_t n_segs, uint32_t *error_flag, cudaStream_t st);
 cudaError_t launch_decode_segments(const StageSeg *d_segs, uint32_t n_segs, uint64_t n_tiles, int sm_count,
                                    cudaStream_t st);
 #endif  // !__CUDACC_RTC__
