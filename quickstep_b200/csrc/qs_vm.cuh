@@ -207,15 +207,41 @@ __device__ __forceinline__ uint32_t tile_row(int r, int tid) { return r * kBlock
 
 /*
  * Run Q::code[PC,END) for this thread's kRows rows.
- *   bits[r]  predicate bit stack (bit 0 = top)
+ *   bits[r]  bit 0 = the predicate value on top of the stack when the section starts / ends
  *   Sink     provides emit<J,TYPE>(acc), emit_raw<J,COL,W>(col tile),
  *            emit_raw_build<J,COL,W>() and build_leaf<COL,LTYPE,W>(r).
+ *
+ * The predicate stack lives in `pst[depth][row]` with a COMPILE-TIME stack pointer SP (the program is a
+ * compile-time constant, so the depth before every instruction is too): a comparison writes one predicate
+ * register, AND / OR / NOT are predicate-logic instructions.  (The first version kept the stack as a shifted
+ * bit word per row; ncu showed SEL + SHF + LOP3 per comparison and per connective, 18 of Q6's 50 instructions
+ * per row once the scan on dictionary codes had made that kernel issue-bound.)
  */
-template <class Q, int PC, int END, class Sink>
-__device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const char *stage, int tid,
-                                       VmRegs &regs, uint32_t (&bits)[kRows], Sink &sink) {
-  if constexpr (PC < END) {
+__host__ __device__ constexpr bool op_pushes(uint8_t op) {
+  return op == OP_CMP || op == OP_CMP_CHAR || op == OP_CMP_CODE || op == OP_PUSH_TRUE || op == OP_PUSH_FALSE || op == OP_LIP;
+}
+template <class Q>
+__host__ __device__ constexpr int pred_depth(int pc, int end) {
+  int sp = 1, mx = 1;
+  for (int i = pc; i < end; ++i) {
+    const uint8_t op = Q::code(i).op;
+    if (op_pushes(op)) ++sp;
+    else if (op == OP_AND || op == OP_OR) --sp;
+    if (sp > mx) mx = sp;
+  }
+  return mx;
+}
+
+template <class Q, int PC, int END, int SP, int D, class Sink>
+__device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const char *stage, int tid,
+                                        VmRegs &regs, bool (&pst)[D][kRows], uint32_t (&bits)[kRows], Sink &sink) {
+  if constexpr (PC >= END) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) bits[r] = pst[SP - 1][r] ? 1u : 0u;
+  } else {
     constexpr Instr in = Q::code(PC);
+    constexpr int NSP = op_pushes(in.op) ? SP + 1 : (in.op == OP_AND || in.op == OP_OR) ? SP - 1 : SP;
+    static_assert(SP >= 1 && NSP >= 1 && NSP <= D, "predicate stack out of bounds");
     uint64_t (&acc)[kRows] = regs.acc;
     uint64_t leaf[kRows];
     constexpr bool wants_leaf = (in.op <= OP_MOD) || in.op == OP_CMP;
@@ -273,20 +299,14 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
       for (int r = 0; r < kRows; ++r) regs.tmp[in.arg == 0 ? 0 : kMaxTmp - 1][r] = acc[r];
     } else if constexpr (in.op == OP_CMP) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const bool b = (in.flags & 1) ? vcmp(in.aux, in.type, leaf[r], acc[r])
-                                      : vcmp(in.aux, in.type, acc[r], leaf[r]);
-        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
-      }
+      for (int r = 0; r < kRows; ++r)
+        pst[SP][r] = (in.flags & 1) ? vcmp(in.aux, in.type, leaf[r], acc[r]) : vcmp(in.aux, in.type, acc[r], leaf[r]);
     } else if constexpr (in.op == OP_CMP_CHAR) {
       const char *base = stage + Q::col_off(in.arg);
       constexpr uint32_t w = Q::col_w(in.arg);
       const char *lit = L.str_pool + in.ltype;    // ltype doubles as pool offset
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const bool b = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit);
-        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
-      }
+      for (int r = 0; r < kRows; ++r) pst[SP][r] = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit);
     } else if constexpr (in.op == OP_CMP_CODE) {
       // attribute <cmp> literal on a dictionary-coded attribute: the host turned the literal into the range
       // of codes that satisfy it (the dictionary is sorted), CompressedTupleStorageSubBlock::getMatchesForPredicate
@@ -297,34 +317,33 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const uint32_t c = load_code_w<Q::col_cw(in.arg)>(codes + tile_row(r, tid) * Q::col_cw(in.arg));
-        const bool b = ((c - lo) < span) != ((in.flags & 1) != 0);
-        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
+        pst[SP][r] = ((c - lo) < span) != ((in.flags & 1) != 0);
       }
     } else if constexpr (in.op == OP_AND) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) & (bits[r] | ~1u);
+      for (int r = 0; r < kRows; ++r) pst[SP - 2][r] = pst[SP - 2][r] && pst[SP - 1][r];
     } else if constexpr (in.op == OP_OR) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] >> 1) | (bits[r] & 1u);
+      for (int r = 0; r < kRows; ++r) pst[SP - 2][r] = pst[SP - 2][r] || pst[SP - 1][r];
     } else if constexpr (in.op == OP_NOT) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) bits[r] ^= 1u;
+      for (int r = 0; r < kRows; ++r) pst[SP - 1][r] = !pst[SP - 1][r];
     } else if constexpr (in.op == OP_PUSH_TRUE) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) bits[r] = (bits[r] << 1) | 1u;
+      for (int r = 0; r < kRows; ++r) pst[SP][r] = true;
     } else if constexpr (in.op == OP_PUSH_FALSE) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) bits[r] = bits[r] << 1;
+      for (int r = 0; r < kRows; ++r) pst[SP][r] = false;
     } else if constexpr (in.op == OP_LIP) {
       // LIP probes are always AND-ed right after (flags&2), so rows whose
-      // current top bit is 0 skip the (random) memory access.
+      // current top value is false skip the (random) memory access.
       const LipDesc &f = S.lip[in.arg];
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         bool b = false;
-        if ((in.flags & 2) == 0 || (bits[r] & 1u))
+        if ((in.flags & 2) == 0 || pst[SP - 1][r])
           b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, static_cast<int64_t>(acc[r]));
-        bits[r] = (bits[r] << 1) | (b ? 1u : 0u);
+        pst[SP][r] = b;
       }
     } else if constexpr (in.op == OP_EMIT) {
       sink.template emit<in.arg, in.type>(acc);
@@ -333,7 +352,19 @@ __device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const c
     } else if constexpr (in.op == OP_EMIT_RAW_BUILD) {
       sink.template emit_raw_build<in.arg, in.flags, Q::build_w(in.flags)>();
     }
-    vm_run<Q, PC + 1, END>(L, S, stage, tid, regs, bits, sink);
+    vm_step<Q, PC + 1, END, NSP, D>(L, S, stage, tid, regs, pst, bits, sink);
+  }
+}
+
+template <class Q, int PC, int END, class Sink>
+__device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const char *stage, int tid,
+                                       VmRegs &regs, uint32_t (&bits)[kRows], Sink &sink) {
+  if constexpr (PC < END) {
+    constexpr int D = pred_depth<Q>(PC, END);
+    bool pst[D][kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) pst[0][r] = (bits[r] & 1u) != 0;
+    vm_step<Q, PC, END, 1, D>(L, S, stage, tid, regs, pst, bits, sink);
   }
 }
 
