@@ -414,6 +414,25 @@ def main():
         o3 = timed(lambda: db.q3()[0], max(1, args.steps // 2), 3)
         oplayer = {"q1": o1[0], "q6": o6[0], "q3": o3[0], "q1_wall": o1[1], "q6_wall": o6[1], "q3_wall": o3[1],
                    "note": "whole queries through libqshost.so (C++ operators + Foreman/4 Workers), blocks resident in HBM"}
+        if "coded" in want:
+            # the same DAGs with the storage manager in code-resident mode: dictionary-compressed attributes of the
+            # blocks stay 1/2-byte codes in HBM (re-coded to one relation-wide dictionary while staging)
+            db.set_code_resident(True)
+            c1 = timed(lambda: db.q1()[0], args.steps, 3)
+            c6 = timed(lambda: db.q6()[0], args.steps, 3)
+            c3 = timed(lambda: db.q3()[0], max(1, args.steps // 2), 3)
+            assert [r["count_order"] for r in c1[3]] == [r["count_order"] for r in o1[3]]
+            assert abs(c6[3] - o6[3]) <= 1e-9 * abs(o6[3])
+            assert [t[0] for t in c3[3]] == [t[0] for t in o3[3]]
+
+            def step_e2e_coded():
+                db.evict(H.LINEITEM)
+                rows = db.q1()[0]
+                return rows if world == 1 else M.gather_merge_q1(rows, device)
+            ce = timed(step_e2e_coded, e_steps, 2)
+            oplayer["code_resident"] = {"q1": c1[0], "q6": c6[0], "q3": c3[0], "e2e_q1_wall": ce[1],
+                                        "lineitem_coding": {nm: db.resident_coding(H.LINEITEM, i) for i, (nm, _t, _w) in enumerate(T.LINEITEM)}}
+            db.set_code_resident(False)
         db.destroy()
 
     # ---- CPU baseline (oracle port) on the host cores, bounded sample, rank 0 at N=1

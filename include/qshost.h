@@ -39,6 +39,13 @@ int qshost_db_load(qshost_db_t db, int which, const void *const *columns, uint64
                    uint64_t rows_per_block, int layout);
 /* Drop the HBM image of a relation: the next query stages its blocks again (cold run). */
 int qshost_db_evict(qshost_db_t db, int which);
+/* Keep dictionary-compressed attributes of the base relations as codes in HBM (qsgpu_relation_set_dictionary) instead
+ * of decoding them to native columns while staging: scans then run on the codes
+ * (CompressedTupleStorageSubBlock::getMatchesForPredicate, storage/CompressedTupleStorageSubBlock.cpp:160-251).  Drops
+ * the HBM images so that the next query stages in the new form.  Off by default. */
+int qshost_db_set_code_resident(qshost_db_t db, int on);
+/* Code width (0 = native) and dictionary entries attribute `attr` of a relation's current HBM image uses. */
+int qshost_db_resident_coding(qshost_db_t db, int which, uint32_t attr, uint32_t *code_width, uint32_t *n_entries);
 /* Bytes of the relation's block images on the host / number of blocks. */
 int qshost_db_stats(qshost_db_t db, int which, uint64_t *host_bytes, uint64_t *n_blocks, uint64_t *n_rows);
 /* Cap on the rows one GPU work order covers (0 = one work order per run of blocks). */

@@ -1106,7 +1106,12 @@ static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *root
     if (!n) break;
     K->out[j] = output->cols[j];
     K->out_width[j] = static_cast<uint8_t>(output->attrs[j].width);
-    if (n->kind == QS_N_ATTRIBUTE) {
+    // a pass-through projection of a dictionary-coded numeric attribute is emitted as a value (dictionary look-up in
+    // registers) rather than copied out of a native tile, so the tile need not be decoded in shared memory
+    const bool coded_value = n->kind == QS_N_ATTRIBUTE && n->b != 2 && L.rel && static_cast<uint32_t>(n->a) < L.rel->attrs.size() &&
+                             L.rel->code_width(static_cast<uint32_t>(n->a)) != 0 && n->type <= QS_DOUBLE &&
+                             output->attrs[j].type == L.rel->attrs[n->a].type;
+    if (n->kind == QS_N_ATTRIBUTE && !coded_value) {
       const qsgpu_relation *src = n->b == 2 ? L.build_rel : L.rel;
       if (!src || static_cast<uint32_t>(n->a) >= src->attrs.size() ||
           src->attrs[n->a].width != output->attrs[j].width) { set_error(QSGPU_ERR_INVALID, "projected attribute does not match the output column width"); return QSGPU_ERR_INVALID; }

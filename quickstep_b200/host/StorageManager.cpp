@@ -248,6 +248,77 @@ std::uint64_t StorageManager::hostBytes(const CatalogRelation &rel) const {
   return n;
 }
 
+namespace {
+
+// a < b in the attribute's own order (the order CompressionDictionaryBuilder sorts a block dictionary in,
+// compression/CompressionDictionaryBuilder.cpp:120-160): numeric, DateLit lexicographic, strncmp
+bool valueLess(std::uint16_t type, std::uint32_t width, const char *a, const char *b) {
+  switch (type) {
+    case QS_INT: { std::int32_t x, y; std::memcpy(&x, a, 4); std::memcpy(&y, b, 4); return x < y; }
+    case QS_LONG: { std::int64_t x, y; std::memcpy(&x, a, 8); std::memcpy(&y, b, 8); return x < y; }
+    case QS_FLOAT: { float x, y; std::memcpy(&x, a, 4); std::memcpy(&y, b, 4); return x < y; }
+    case QS_DOUBLE: { double x, y; std::memcpy(&x, a, 8); std::memcpy(&y, b, 8); return x < y; }
+    case QS_DATE: {
+      std::int32_t x, y; std::memcpy(&x, a, 4); std::memcpy(&y, b, 4);
+      if (x != y) return x < y;
+      if (a[4] != b[4]) return static_cast<unsigned char>(a[4]) < static_cast<unsigned char>(b[4]);
+      return static_cast<unsigned char>(a[5]) < static_cast<unsigned char>(b[5]);
+    }
+    default: return std::strncmp(a, b, width) < 0;
+  }
+}
+
+}  // namespace
+
+const std::vector<StorageManager::RelationDictionary> &StorageManager::relationDictionaries(
+    const CatalogRelation &rel, const std::vector<block_id> &ids) {
+  const auto key = std::make_pair(rel.getID(), ids.size());
+  auto it = dictionaries_.find(key);
+  if (it != dictionaries_.end()) return it->second;
+  const std::vector<qs_attr> schema = rel.schema();
+  std::vector<RelationDictionary> out(schema.size());
+  for (std::size_t a = 0; a < schema.size() && !ids.empty(); ++a) {
+    const std::uint32_t w = schema[a].width;
+    bool all_dict = true;
+    std::size_t total = 0;
+    for (block_id id : ids) {
+      const qs_stage_desc &s = blocks_.at(id).stripes[a];
+      if (s.encoding != QS_ENC_DICT) { all_dict = false; break; }
+      total += s.dict_entries;
+    }
+    if (!all_dict || w <= 1) continue;            // a CHAR(1) code is no narrower than its value
+    std::vector<const char *> entries;
+    entries.reserve(total);
+    for (block_id id : ids) {
+      const qs_stage_desc &s = blocks_.at(id).stripes[a];
+      for (std::uint32_t e = 0; e < s.dict_entries; ++e) entries.push_back(static_cast<const char *>(s.dict) + static_cast<std::size_t>(e) * w);
+    }
+    const std::uint16_t type = schema[a].type;
+    std::sort(entries.begin(), entries.end(), [&](const char *x, const char *y) { return valueLess(type, w, x, y); });
+    entries.erase(std::unique(entries.begin(), entries.end(),
+                              [&](const char *x, const char *y) { return !valueLess(type, w, x, y) && !valueLess(type, w, y, x); }),
+                  entries.end());
+    if (entries.size() > 65536) continue;          // 4-byte codes into a multi-megabyte dictionary: a random gather per row
+    const std::uint32_t cw = entries.size() <= 256 ? 1 : 2;
+    if (cw >= w) continue;
+    RelationDictionary &D = out[a];
+    D.code_width = cw;
+    D.n_entries = static_cast<std::uint32_t>(entries.size());
+    D.values.resize(entries.size() * w);
+    for (std::size_t e = 0; e < entries.size(); ++e) std::memcpy(&D.values[e * w], entries[e], w);
+  }
+  return dictionaries_.emplace(key, std::move(out)).first->second;
+}
+
+std::pair<std::uint32_t, std::uint32_t> StorageManager::residentCoding(const CatalogRelation &rel, std::uint32_t attr) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = resident_.find(rel.getID());
+  if (it == resident_.end() || !it->second.handle) return {0, 0};
+  std::uint32_t cw = 0, n = 0;
+  QS_CHECK_GPU(qsgpu_relation_dictionary(it->second.handle, attr, &cw, &n, nullptr));
+  return {cw, n};
+}
+
 qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std::uint64_t needed_attrs) {
   std::lock_guard<std::mutex> lk(mu_);
   const std::vector<block_id> ids = rel.getBlocksSnapshot();
@@ -265,6 +336,13 @@ qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std:
     for (block_id id : ids) rows += static_cast<std::uint64_t>(blocks_.at(id).num_tuples);
     QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
                                        std::max<std::uint64_t>(rows, 1), &R.handle));
+    if (code_resident_) {
+      const std::vector<RelationDictionary> &dicts = relationDictionaries(rel, ids);
+      for (std::size_t a = 0; a < dicts.size(); ++a)
+        if (dicts[a].code_width)
+          QS_CHECK_GPU(qsgpu_relation_set_dictionary(R.handle, static_cast<std::uint32_t>(a), dicts[a].code_width,
+                                                     dicts[a].values.data(), dicts[a].n_entries));
+    }
     R.n_blocks_staged = 0;
     R.rows = 0;
     R.staged_attrs = 0;

@@ -74,6 +74,15 @@ class StorageManager {
   DeviceExtent blockExtent(block_id id);                           // rows of one block inside it
   void evict(const CatalogRelation &rel);                          // drop the HBM image
 
+  // Keep dictionary-compressed attributes as CODES in HBM: an attribute whose stripe
+  // is dictionary-compressed in every block and whose block dictionaries union to <= 65,536 values narrower than
+  // their codes is declared with qsgpu_relation_set_dictionary, and qsgpu_stage_blocks re-codes the blocks into that
+  // relation-wide dictionary instead of decoding them.  Takes effect the next time a relation's image is built.
+  void setCodeResident(bool on) { code_resident_ = on; }
+  bool codeResident() const { return code_resident_; }
+  // (code width, dictionary entries) the image of `rel` uses for attribute `attr`; (0, 0) = native
+  std::pair<std::uint32_t, std::uint32_t> residentCoding(const CatalogRelation &rel, std::uint32_t attr);
+
   // Device-only temporary relation (output of Select / HashJoin / Finalize);
   // its single pseudo block id stands for "every row produced so far".
   block_id createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows);
@@ -89,6 +98,12 @@ class StorageManager {
     std::uint64_t rows = 0;
     std::uint64_t staged_attrs = 0;      // bit a: attribute a of every staged block is in HBM
   };
+  // union of the block dictionaries of one attribute, sorted in the attribute's order (cached per relation and
+  // block count: blocks are immutable once built)
+  struct RelationDictionary { std::uint32_t code_width = 0, n_entries = 0; std::vector<char> values; };
+  const std::vector<RelationDictionary> &relationDictionaries(const CatalogRelation &rel, const std::vector<block_id> &ids);
+  std::map<std::pair<relation_id, std::size_t>, std::vector<RelationDictionary>> dictionaries_;
+  bool code_resident_ = false;
   int device_;
   bool pinned_;
   mutable std::mutex mu_;

@@ -149,6 +149,20 @@ int qshost_db_evict(qshost_db_t db, int which) {
   return 0;
 }
 
+int qshost_db_set_code_resident(qshost_db_t db, int on) {
+  db->sm->setCodeResident(on != 0);
+  for (int which = 0; which < 3; ++which) if (db->rel[which]) db->sm->evict(*db->rel[which]);
+  return 0;
+}
+
+int qshost_db_resident_coding(qshost_db_t db, int which, uint32_t attr, uint32_t *code_width, uint32_t *n_entries) {
+  if (which < 0 || which > 2 || !db->rel[which] || attr >= db->rel[which]->schema().size()) return QSGPU_ERR_INVALID;
+  const auto c = db->sm->residentCoding(*db->rel[which], attr);
+  if (code_width) *code_width = c.first;
+  if (n_entries) *n_entries = c.second;
+  return 0;
+}
+
 int qshost_db_stats(qshost_db_t db, int which, uint64_t *host_bytes, uint64_t *n_blocks, uint64_t *n_rows) {
   if (which < 0 || which > 2 || !db->rel[which]) return QSGPU_ERR_INVALID;
   if (host_bytes) *host_bytes = db->sm->hostBytes(*db->rel[which]);

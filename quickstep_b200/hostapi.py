@@ -33,6 +33,8 @@ SIGNATURES = {
     "qshost_db_load": [_VP, C.c_int, C.POINTER(_VP), C.c_uint64, C.c_uint64, C.c_int],
     "qshost_db_evict": [_VP, C.c_int],
     "qshost_db_stats": [_VP, C.c_int, _U64P, _U64P, _U64P],
+    "qshost_db_set_code_resident": [_VP, C.c_int],
+    "qshost_db_resident_coding": [_VP, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
     "qshost_set_rows_per_workorder": [C.c_uint64],
     "qshost_q1": [_VP, C.POINTER(q1_row), C.POINTER(C.c_uint32), _U64P],
     "qshost_q6": [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int), _U64P],
@@ -76,6 +78,15 @@ class Database:
 
     def evict(self, which):
         A.check(load().qshost_db_evict(self.h, which))
+
+    def set_code_resident(self, on: bool):
+        """Dictionary-compressed attributes stay codes in HBM (scans run on the codes); re-stages on next use."""
+        A.check(load().qshost_db_set_code_resident(self.h, 1 if on else 0))
+
+    def resident_coding(self, which, attr):
+        cw, n = C.c_uint32(0), C.c_uint32(0)
+        A.check(load().qshost_db_resident_coding(self.h, which, attr, C.byref(cw), C.byref(n)))
+        return cw.value, n.value
 
     def stats(self, which):
         b, n, r = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

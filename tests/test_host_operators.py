@@ -89,6 +89,53 @@ def test_tpch_through_operator_layer(golden, layout, rows_per_block):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows_per_block", [4096, 63000])
+def test_tpch_through_operator_layer_on_dictionary_codes(golden, rows_per_block):
+    """Code-resident mode of the storage manager: dictionary-compressed attributes of the compressed-column-store
+    blocks stay 1/2-byte codes in HBM (one relation-wide dictionary per attribute, block dictionaries re-coded on
+    the device) and every operator of the three DAGs scans the codes.  Same answers as the oracle (and as the
+    decode-at-staging mode: integer results identical, double sums 1e-9); many small work orders too."""
+    db = H.Database(0, num_workers=4)
+    try:
+        for which, name in ((H.CUSTOMER, "customer"), (H.ORDERS, "orders"), (H.LINEITEM, "lineitem")):
+            db.load_table(which, golden[name], rows_per_block, H.COMPRESSED_COLUMN_STORE)
+        base_rev, _, _ = db.q6()
+        base_rows, _ = db.q1()
+        base_top, _ = db.q3()
+        assert db.resident_coding(H.LINEITEM, 7) == (0, 0)
+        db.set_code_resident(True)
+        rev, is_null, wo = db.q6()
+        orev, onull = OT.q6(golden["lineitem"])
+        assert is_null == onull and close(rev, orev) and close(rev, base_rev) and wo == 3
+        # l_shipdate 2-byte codes; l_quantity / l_discount / l_tax 1-byte codes; CHAR(1) flags stay native
+        assert db.resident_coding(H.LINEITEM, 7)[0] == 2
+        for a in (1, 3, 4):
+            cw, n = db.resident_coding(H.LINEITEM, a)
+            assert cw == 1 and 0 < n <= 50
+        assert db.resident_coding(H.LINEITEM, 5) == (0, 0)
+        rows, _ = db.q1()
+        _check_q1(rows, OT.q1(golden["lineitem"]))
+        _check_q1(rows, base_rows)
+        top, _ = db.q3()
+        _check_q3(top, OT.q3(golden, D.q3_stats(golden)))
+        _check_q3(top, base_top)
+        assert db.resident_coding(H.ORDERS, 2)[0] in (0, 2)       # o_orderdate: coded when every block compressed it
+        H.set_rows_per_workorder(8192)
+        try:
+            rows2, _ = db.q1()
+            _check_q1(rows2, base_rows)
+            top2, _ = db.q3()
+            _check_q3(top2, base_top)
+        finally:
+            H.set_rows_per_workorder(0)
+        db.set_code_resident(False)
+        rev3, _, _ = db.q6()
+        assert rev3 == base_rev and db.resident_coding(H.LINEITEM, 7) == (0, 0)
+    finally:
+        db.destroy()
+
+
+@pytest.mark.gpu
 def test_many_work_orders_and_cold_restage(golden):
     """gpu_rows_per_workorder forces one work order per ~2 blocks; evicting the HBM image makes the next
     query stage the blocks again.  Integer results are identical, double sums within 1e-9."""
