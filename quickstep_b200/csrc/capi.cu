@@ -210,9 +210,9 @@ static int check_device_error(Device *d) {
 
 // Fetches (compiling on first use) the kernel specialised for this work order.
 static int query_kernel(JitFamily fam, const ScanDesc &S, const Program &P, const ScanPlan &plan, const AggDesc *A,
-                        const SinkDesc *K, const JoinDesc *J, int hot, JitKernel **out) {
+                        const SinkDesc *K, const JoinDesc *J, int hot, JitKernel **out, int priv = 0) {
   JitSpec sp;
-  sp.family = fam; sp.S = &S; sp.P = &P; sp.A = A; sp.K = K; sp.J = J; sp.hot = hot; sp.ctas_per_sm = plan.ctas;
+  sp.family = fam; sp.S = &S; sp.P = &P; sp.A = A; sp.K = K; sp.J = J; sp.hot = hot; sp.priv = priv; sp.ctas_per_sm = plan.ctas;
   if (t_sc) {
     std::string cubin;
     t_sc->reached = true;
@@ -1409,22 +1409,32 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
   ScanPlan plan;
   if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
     const int hot = agg_hot_groups(A);
-    st = plan_scan(d, &S, agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words), &plan);
+    // Grouped states over narrow tiles (scans of dictionary codes) keep the hot groups' value accumulators as
+    // per-thread shared-memory slots instead of registers (scan_agg_body, Q::priv): taken when two CTAs per SM
+    // still fit with a double-buffered ring.  Wide native tiles (Q1 on native columns: 43 KB per stage) do not.
+    bool priv = false;
+    if (A.n_key_cols > 0 && A.n_agg > 0) {
+      ScanDesc S2 = S;
+      ScanPlan p2;
+      priv = plan_scan(d, &S2, agg_smem_extra(hot, static_cast<int>(A.n_agg), true, A.words, true), &p2, 2) == QSGPU_OK && p2.ctas >= 2;
+    }
+    const size_t agg_extra = agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words, priv);
+    st = plan_scan(d, &S, agg_extra, &plan, priv ? 2 : 4);
     if (st) return st;
     // wide tiles (native Q6: 32 KB) measured best with 2 resident CTAs per SM (0.269 vs 0.279 ms with 3); narrow
     // code tiles take all 4 (Q6 on codes: 0.143 -> 0.128 ms)
     const uint32_t grid_cap = std::min<uint32_t>(state->max_ctas, static_cast<uint32_t>(d->sm_count) * (S.stage_bytes <= 16384 ? 4u : 2u));
     if (static_cast<uint32_t>(plan.grid) > grid_cap) plan.grid = static_cast<int>(grid_cap);
     JitKernel *kern = nullptr;
-    st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern);
+    st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern, priv ? 1 : 0);
     if (st) return st;
     // The ring was sized for the CTAs the shared memory allows; when the compiled kernel's registers allow fewer
     // (Q1: 2), give each resident CTA the deeper ring its share of the SM's shared memory affords.
     if (const int occ = jit_occupancy(kern, plan.smem); occ > 0 && occ < plan.ctas) {
-      st = plan_scan(d, &S, agg_smem_extra(hot, static_cast<int>(A.n_agg), A.n_key_cols > 0, A.words), &plan, occ);
+      st = plan_scan(d, &S, agg_extra, &plan, occ);
       if (st) return st;
       if (static_cast<uint32_t>(plan.grid) > grid_cap) plan.grid = static_cast<int>(grid_cap);
-      st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern);
+      st = query_kernel(JF_AGG, S, L.P, plan, &A, nullptr, nullptr, hot, &kern, priv ? 1 : 0);
       if (st) return st;
     }
     {

@@ -70,10 +70,12 @@ __global__ void k_merge_foreign_compact(const __grid_constant__ AggDesc A, const
 }
 
 // ------------------------------------------------------------------ launchers
-size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words) {
+size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words, bool priv) {
   const size_t NA = n_agg > 0 ? n_agg : 1;
   const size_t LG = grouped ? kCompactMaxGroups : 1, LS = grouped ? kCompactLocalSlots : 0;
-  return static_cast<size_t>(8) * hot * (NA + 1) * 8 + LG * words * 8 + LG * 8 + LS * 8 + LS * 4 + LG * 4 + 16;
+  // priv: hot groups x NA value words x one 8-byte slot per thread (row counts stay in registers)
+  const size_t pv = priv ? static_cast<size_t>(hot) * NA * kBlock * 8 : 0;
+  return static_cast<size_t>(8) * hot * (NA + 1) * 8 + LG * words * 8 + LG * 8 + LS * 8 + LS * 4 + LG * 4 + 16 + pv;
 }
 
 int agg_hot_groups(const AggDesc &A) { return A.n_key_cols > 0 ? 4 : 1; }

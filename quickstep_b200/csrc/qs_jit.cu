@@ -89,7 +89,7 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
   {
     AggDesc Z{};
     const AggDesc &A = sp.A ? *sp.A : Z;
-    o << "  static constexpr int n_agg = " << A.n_agg << ", hot = " << sp.hot << ";\n";
+    o << "  static constexpr int n_agg = " << A.n_agg << ", hot = " << sp.hot << ", priv = " << sp.priv << ";\n";
     o << "  static constexpr uint32_t words = " << (A.n_agg + 1) << ", strategy = " << A.strategy
       << ", n_key_cols = " << A.n_key_cols << ", key_words = " << (A.key_words ? A.key_words : 1) << ";\n";
     o << "  static constexpr bool grouped = " << (A.n_key_cols > 0 ? "true" : "false") << ";\n";

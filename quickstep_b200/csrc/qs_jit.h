@@ -38,6 +38,7 @@ struct JitSpec {
   const SinkDesc *K = nullptr;
   const JoinDesc *J = nullptr;
   int hot = 1;                  // register-resident groups (JF_AGG)
+  int priv = 0;                 // JF_AGG: the hot groups' accumulators are per-thread shared-memory slots, not registers
   int ctas_per_sm = 2;
 };
 

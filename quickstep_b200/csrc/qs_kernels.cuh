@@ -117,6 +117,7 @@ struct AggSmem {
   int *lslot;            // [LS]
   uint32_t *lready;      // [LG]  1 once lkey_by_id[id] is published
   uint32_t *nlocal;
+  uint64_t *priv;        // Q::priv: [HOT][NA][kBlock] per-thread value accumulators of the hot groups
 };
 
 // hv (+)= v when slot == G, as ONE predicated instruction (ptxas shares the
@@ -154,6 +155,22 @@ struct AggSink : SinkBase {
   uint32_t mh[kRows][HOT];
   bool cold;            // warp-uniform: some row of this warp's tile slice is in a non-hot group
   uint64_t *lstate;
+  // Q::priv form: the hot groups' value accumulators are per-thread slots in SHARED memory, addressed by the row's
+  // group id -- LDS + op + STS per (row, aggregate) instead of one masked DFMA (plus a mask move) per (row,
+  // aggregate, hot group), and ~55 registers fewer.  prow[r] = this thread's slot of row r's group (value word 0);
+  // a row that fails the predicate or belongs to a cold group computes against the last hot group's slot and its
+  // store is predicated off.  Slot (g, j, tid) sits at ((g * NA + j) * kBlock + tid) * 8: the 32 lanes of a warp
+  // always touch 32 consecutive 8-byte words, whatever their groups.  Row counts stay in registers (hc).
+  char *prow[kRows];
+  bool pok[kRows];
+  __device__ __forceinline__ void set_private_rows(uint64_t *priv, int tid) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      pok[r] = static_cast<uint32_t>(slot[r]) < static_cast<uint32_t>(HOT);
+      const uint32_t g = pok[r] ? static_cast<uint32_t>(slot[r]) : static_cast<uint32_t>(HOT - 1);
+      prow[r] = reinterpret_cast<char *>(priv + (g * NA) * kBlock + tid);
+    }
+  }
 
   __device__ __forceinline__ void set_masks() {
 #pragma unroll
@@ -165,6 +182,20 @@ struct AggSink : SinkBase {
   template <int J, int TYPE>
   __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
     constexpr uint8_t kind = Q::agg_kind(J);
+    if constexpr (Q::priv != 0) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        uint64_t *p = reinterpret_cast<uint64_t *>(prow[r] + J * kBlock * 8);
+        const uint64_t x = agg_combine(kind, *p, acc[r]);
+        if (pok[r]) *p = x;
+      }
+      if (cold) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (slot[r] >= HOT) atomic_update<kind>(&lstate[slot[r] * Q::words + 1 + J], acc[r]);
+      }
+      return;
+    }
     bool fast = false;
     if constexpr (kind == AK_SUM_F64 && (HOT > 1)) {
       // inf * 0 and NaN * 0 are NaN: a non-finite value must not reach the other groups' accumulators, so
@@ -272,7 +303,13 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
     M.lkeys = reinterpret_cast<uint64_t *>(p); p += LS * 8;
     M.lslot = reinterpret_cast<int *>(p); p += LS * 4;
     M.lready = reinterpret_cast<uint32_t *>(p); p += LG * 4;
-    M.nlocal = reinterpret_cast<uint32_t *>(p);
+    M.nlocal = reinterpret_cast<uint32_t *>(p); p += 16;
+    M.priv = reinterpret_cast<uint64_t *>(p);
+  }
+  if constexpr (Q::priv != 0) {     // every thread initialises its own slots
+#pragma unroll
+    for (int g = 0; g < HOT; ++g)
+      static_for<0, Q::n_agg>([&](auto j) { M.priv[(g * NA + QS_IDX(j)) * kBlock + tid] = agg_identity(Q::agg_kind(QS_IDX(j))); });
   }
   if constexpr (Q::grouped) {
     for (uint32_t i = tid; i < LG * W; i += kBlock) {
@@ -293,7 +330,8 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
 #pragma unroll
   for (int g = 0; g < HOT; ++g) {
     sink.hc[g] = 0;
-    static_for<0, Q::n_agg>([&](auto j) { sink.hv[g][QS_IDX(j)] = agg_identity(Q::agg_kind(QS_IDX(j))); });
+    if constexpr (Q::priv == 0)
+      static_for<0, Q::n_agg>([&](auto j) { sink.hv[g][QS_IDX(j)] = agg_identity(Q::agg_kind(QS_IDX(j))); });
   }
   VmRegs regs;
   uint64_t hk[HOT];          // keys of the register-resident groups (ids 0..nhot-1)
@@ -349,7 +387,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
         sink.slot[r] = s;
       }
     }
-    sink.set_masks();
+    if constexpr (Q::priv == 0) sink.set_masks();
     // row counts
     sink.cold = false;
     if constexpr (Q::grouped) {
@@ -358,6 +396,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
       for (int r = 0; r < kRows; ++r) c |= sink.slot[r] >= HOT;
       sink.cold = __any_sync(0xffffffffu, c);
     }
+    if constexpr (Q::priv != 0) sink.set_private_rows(M.priv, tid);
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
       static_for<0, HOT>([&](auto gg) { hot_count<QS_IDX(gg)>(sink.hc[QS_IDX(gg)], sink.slot[r]); });
@@ -383,7 +422,9 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
     static_for<0, Q::n_agg>([&](auto jj) {
       constexpr int j = QS_IDX(jj);
       constexpr uint8_t kind = Q::agg_kind(j);
-      uint64_t x = sink.hv[g][j];
+      uint64_t x;
+      if constexpr (Q::priv != 0) x = M.priv[(g * NA + j) * kBlock + tid];
+      else x = sink.hv[g][j];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         const uint64_t y = __shfl_xor_sync(0xffffffffu, x, off);

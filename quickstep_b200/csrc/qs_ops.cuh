@@ -92,7 +92,7 @@ constexpr uint32_t kStageTileRows = 4096;
 
 #ifndef __CUDACC_RTC__
 // k_agg.cu
-size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words);
+size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words, bool priv = false);
 int agg_hot_groups(const AggDesc &A);
 cudaError_t launch_fill_identity(uint64_t *states, uint64_t n_rows, const AggDesc &A, cudaStream_t st);
 cudaError_t launch_merge_partials(const AggDesc &A, uint32_t n_ctas, cudaStream_t st);
