@@ -339,7 +339,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
 #pragma unroll
   for (int g = 0; g < HOT; ++g) hk[g] = 0;
 
-  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
+  scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *__restrict__ stage, const ScanRt &rt) {
     bool valid[kRows];
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];

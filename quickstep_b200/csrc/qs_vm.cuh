@@ -233,7 +233,7 @@ __host__ __device__ constexpr int pred_depth(int pc, int end) {
 }
 
 template <class Q, int PC, int END, int SP, int D, class Sink>
-__device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const char *stage, int tid,
+__device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const char *__restrict__ stage, int tid,
                                         VmRegs &regs, bool (&pst)[D][kRows], uint32_t (&bits)[kRows], Sink &sink) {
   if constexpr (PC >= END) {
 #pragma unroll
@@ -357,7 +357,7 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
 }
 
 template <class Q, int PC, int END, class Sink>
-__device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const char *stage, int tid,
+__device__ __forceinline__ void vm_run(const Lits &L, const ScanDesc &S, const char *__restrict__ stage, int tid,
                                        VmRegs &regs, uint32_t (&bits)[kRows], Sink &sink) {
   if constexpr (PC < END) {
     constexpr int D = pred_depth<Q>(PC, END);
