@@ -1413,7 +1413,7 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     // per-thread shared-memory slots instead of registers (scan_agg_body, Q::priv): taken when two CTAs per SM
     // still fit with a double-buffered ring.  Wide native tiles (Q1 on native columns: 43 KB per stage) do not.
     bool priv = false;
-    if (A.n_key_cols > 0 && A.n_agg > 0) {
+    if (A.n_key_cols > 0 && A.n_agg > 0 && A.n_agg <= 6) {   // a tile's values wait in registers: 8 per aggregate
       ScanDesc S2 = S;
       ScanPlan p2;
       priv = plan_scan(d, &S2, agg_smem_extra(hot, static_cast<int>(A.n_agg), true, A.words, true), &p2, 2) == QSGPU_OK && p2.ctas >= 2;

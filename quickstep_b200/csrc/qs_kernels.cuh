@@ -161,8 +161,42 @@ struct AggSink : SinkBase {
   // a row that fails the predicate or belongs to a cold group computes against the last hot group's slot and its
   // store is predicated off.  Slot (g, j, tid) sits at ((g * NA + j) * kBlock + tid) * 8: the 32 lanes of a warp
   // always touch 32 consecutive 8-byte words, whatever their groups.  Row counts stay in registers (hc).
+  // The values of a tile's rows are first parked in registers (pv) and applied after the emit section, row by row
+  // with the aggregates of one row side by side: the NA slots of a row are distinct addresses, so their loads issue
+  // back to back and the dependent chain per tile is kRows read-modify-writes long instead of kRows x NA (rows of
+  // one thread may share a group, i.e. a slot, so rows stay ordered; the order of additions per slot is unchanged).
   char *prow[kRows];
   bool pok[kRows];
+  uint64_t pv[NA][kRows];
+  __device__ __forceinline__ void flush_private() {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      uint64_t x[NA];
+      static_for<0, Q::n_agg>([&](auto jj) {
+        constexpr int j = QS_IDX(jj);
+        x[j] = *reinterpret_cast<const uint64_t *>(prow[r] + j * kBlock * 8);
+      });
+      static_for<0, Q::n_agg>([&](auto jj) {
+        constexpr int j = QS_IDX(jj);
+        x[j] = agg_combine(Q::agg_kind(j), x[j], pv[j][r]);
+      });
+      if (pok[r]) {
+        static_for<0, Q::n_agg>([&](auto jj) {
+          constexpr int j = QS_IDX(jj);
+          *reinterpret_cast<uint64_t *>(prow[r] + j * kBlock * 8) = x[j];
+        });
+      }
+    }
+    if (cold) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        if (slot[r] >= HOT)
+          static_for<0, Q::n_agg>([&](auto jj) {
+            constexpr int j = QS_IDX(jj);
+            atomic_update<Q::agg_kind(j)>(&lstate[slot[r] * Q::words + 1 + j], pv[j][r]);
+          });
+    }
+  }
   __device__ __forceinline__ void set_private_rows(uint64_t *priv, int tid) {
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -184,16 +218,7 @@ struct AggSink : SinkBase {
     constexpr uint8_t kind = Q::agg_kind(J);
     if constexpr (Q::priv != 0) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        uint64_t *p = reinterpret_cast<uint64_t *>(prow[r] + J * kBlock * 8);
-        const uint64_t x = agg_combine(kind, *p, acc[r]);
-        if (pok[r]) *p = x;
-      }
-      if (cold) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r)
-          if (slot[r] >= HOT) atomic_update<kind>(&lstate[slot[r] * Q::words + 1 + J], acc[r]);
-      }
+      for (int r = 0; r < kRows; ++r) pv[J][r] = acc[r];
       return;
     }
     bool fast = false;
@@ -409,6 +434,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
       }
     }
     vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+    if constexpr (Q::priv != 0) sink.flush_private();
   });
 
   // ---- CTA reduction of the register-resident (hot) groups, fixed tree.
