@@ -171,6 +171,18 @@ int qsgpu_relation_read(qsgpu_relation_t rel, uint32_t attr, uint64_t row_begin,
  */
 int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t code_width,
                                   const void *dict_values, uint32_t n_entries);
+/*
+ * The codes of a sorted dictionary that satisfy `attribute <cmp> literal` (cmp = QS_EQ..QS_GE, `literal` a
+ * QS_N_LITERAL node; CHAR literals take their bytes from str_pool): the range [*first, *first + *count), or its
+ * complement when *negate is set.  Host arithmetic only, no device needed -- it is what the lowering applies to every
+ * comparison on a coded attribute, with the reference's type promotion (an INT attribute against a DOUBLE literal
+ * compares as DOUBLE) and NaN semantics; a binding can use it to prune blocks the way
+ * CompressedTupleStorageSubBlock::getMatchesForPredicate short-cuts an always-false comparison
+ * (storage/CompressedTupleStorageSubBlock.cpp:183-199): *count == 0 without *negate means no tuple can match.
+ */
+int qsgpu_dictionary_code_range(uint16_t attr_type, uint16_t attr_width, const void *dict_values, uint32_t n_entries,
+                                uint32_t cmp, const qs_node *literal, const char *str_pool, uint32_t str_pool_bytes,
+                                uint32_t *first, uint32_t *count, int *negate);
 /* code_width 0 = native attribute; dict_out (optional) receives n_entries native values. */
 int qsgpu_relation_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t *code_width, uint32_t *n_entries,
                               void *dict_out);

@@ -127,6 +127,8 @@ SIGNATURES = {
     "qsgpu_relation_wrap": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(qs_attr), _VPP, C.c_uint64, _VPP]),
     "qsgpu_relation_read": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint64, _VP]),
     "qsgpu_relation_set_dictionary": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint32]),
+    "qsgpu_dictionary_code_range": (C.c_int, [C.c_uint16, C.c_uint16, _VP, C.c_uint32, C.c_uint32, C.POINTER(qs_node), C.c_char_p,
+                                              C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
     "qsgpu_relation_dictionary": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _VP]),
     "qsgpu_relation_read_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),

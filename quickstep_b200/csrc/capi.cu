@@ -675,6 +675,20 @@ int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t 
   return QSGPU_OK;
 }
 
+int qsgpu_dictionary_code_range(uint16_t attr_type, uint16_t attr_width, const void *dict_values, uint32_t n_entries,
+                                uint32_t cmp, const qs_node *literal, const char *str_pool, uint32_t str_pool_bytes,
+                                uint32_t *first, uint32_t *count, int *negate) {
+  if (!dict_values || !literal || !first || !count || !negate || literal->kind != QS_N_LITERAL) { set_error(QSGPU_ERR_INVALID, "qsgpu_dictionary_code_range: bad arguments"); return QSGPU_ERR_INVALID; }
+  uint64_t lo = 0, span = 0;
+  bool neg = false;
+  std::string why;
+  const int st = dict_code_range(attr_type, qs::attr_width(attr_type, attr_width), static_cast<const char *>(dict_values), n_entries,
+                                 static_cast<uint8_t>(cmp), literal, str_pool ? str_pool : "", str_pool_bytes, &lo, &span, &neg, &why);
+  if (st != QSGPU_OK) { set_error(st, why); return st; }
+  *first = static_cast<uint32_t>(lo); *count = static_cast<uint32_t>(span); *negate = neg ? 1 : 0;
+  return QSGPU_OK;
+}
+
 int qsgpu_relation_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t *code_width, uint32_t *n_entries,
                               void *dict_out) {
   if (!rel || attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "attribute id out of range"); return QSGPU_ERR_INVALID; }

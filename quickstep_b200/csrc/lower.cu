@@ -326,32 +326,33 @@ int dict_compare(uint16_t type, uint32_t width, const char *a, const char *b) {
  * one range [lo, lo+span) or its complement, so the kernel runs one unsigned range test per row; the bounds
  * travel as literals (the kernel does not depend on their values).
  */
-bool Lowering::lower_code_compare(const qs_node *attr, const qs_node *lit, uint8_t cmp) {
-  const uint32_t a = static_cast<uint32_t>(attr->a);
-  const qs_coded_attr &C = rel->coded[a];
-  const uint32_t w = rel->attrs[a].width;
+int dict_code_range(uint16_t attr_type, uint32_t w, const char *dict, uint32_t n_entries, uint8_t cmp,
+                    const qs_node *lit, const char *str_pool, uint32_t str_pool_bytes, uint64_t *lo_out,
+                    uint64_t *span_out, bool *negate_out, std::string *err) {
   uint64_t n_lt = 0, n_eq = 0, n_gt = 0;
-  if (attr->type == QS_CHAR) {
+  if ((attr_type == QS_CHAR) != (lit->type == QS_CHAR)) { *err = "comparison of a coded attribute with a literal of another kind"; return QSGPU_ERR_UNSUPPORTED; }
+  if (attr_type == QS_CHAR) {
     // strncmp over the attribute width, literal NUL-padded / cut like the native CHAR path
+    if (lit->lit.pool_offset + lit->width > str_pool_bytes) { *err = "CHAR literal outside pool"; return QSGPU_ERR_INVALID; }
     std::string l(w, '\0');
-    for (uint32_t b = 0; b < w && b < lit->width; ++b) l[b] = ex->str_pool[lit->lit.pool_offset + b];
-    for (uint32_t e = 0; e < C.n_entries; ++e) {
-      const int r = std::strncmp(C.h_dict.data() + static_cast<size_t>(e) * w, l.data(), w);
+    for (uint32_t b = 0; b < w && b < lit->width; ++b) l[b] = str_pool[lit->lit.pool_offset + b];
+    for (uint32_t e = 0; e < n_entries; ++e) {
+      const int r = std::strncmp(dict + static_cast<size_t>(e) * w, l.data(), w);
       (r < 0 ? n_lt : r > 0 ? n_gt : n_eq)++;
     }
   } else {
-    const uint8_t own = vtype_of(attr->type), lown = vtype_of(lit->type);
-    if (own == 0xff || lown == 0xff) return fail(QSGPU_ERR_UNSUPPORTED, "comparison of a coded attribute with a non-numeric literal");
+    const uint8_t own = vtype_of(attr_type), lown = vtype_of(lit->type);
+    if (own == 0xff || lown == 0xff) { *err = "comparison of a coded attribute with a non-numeric literal"; return QSGPU_ERR_UNSUPPORTED; }
     const uint8_t T = unify(own, lown);
     const uint64_t lv = host_cvt(literal_raw(lit), lown, T);
-    for (uint32_t e = 0; e < C.n_entries; ++e) {
-      const uint64_t dv = host_cvt(dict_raw(C.h_dict.data() + static_cast<size_t>(e) * w, attr->type), own, T);
+    for (uint32_t e = 0; e < n_entries; ++e) {
+      const uint64_t dv = host_cvt(dict_raw(dict + static_cast<size_t>(e) * w, attr_type), own, T);
       const int r = host_cmp3(T, dv, lv);
       if (r < 0) ++n_lt; else if (r == 0) ++n_eq; else if (r == 1) ++n_gt;
     }
   }
   // codes [0, n_lt) are below the literal, [n_lt, n_lt + n_eq) equal, the last n_gt above
-  const uint64_t n = C.n_entries;
+  const uint64_t n = n_entries;
   uint64_t lo = 0, span = 0;
   bool negate = false;
   switch (cmp) {
@@ -360,8 +361,22 @@ bool Lowering::lower_code_compare(const qs_node *attr, const qs_node *lit, uint8
     case QS_LT: lo = 0; span = n_lt; break;
     case QS_LE: lo = 0; span = n_lt + n_eq; break;
     case QS_GT: lo = n - n_gt; span = n_gt; break;
-    default: lo = n - n_gt - n_eq; span = n_gt + n_eq; break;   // QS_GE
+    case QS_GE: lo = n - n_gt - n_eq; span = n_gt + n_eq; break;
+    default: *err = "not a comparison id"; return QSGPU_ERR_INVALID;
   }
+  *lo_out = lo; *span_out = span; *negate_out = negate;
+  return QSGPU_OK;
+}
+
+bool Lowering::lower_code_compare(const qs_node *attr, const qs_node *lit, uint8_t cmp) {
+  const uint32_t a = static_cast<uint32_t>(attr->a);
+  const qs_coded_attr &C = rel->coded[a];
+  uint64_t lo = 0, span = 0;
+  bool negate = false;
+  std::string why;
+  const int st = dict_code_range(attr->type, rel->attrs[a].width, C.h_dict.data(), C.n_entries, cmp, lit, ex->str_pool,
+                                 ex->str_pool_bytes, &lo, &span, &negate, &why);
+  if (st != QSGPU_OK) return fail(st, why);
   Instr in{};
   in.op = OP_CMP_CODE;
   in.arg = static_cast<uint16_t>(stage_attr(a, USE_CODE));

@@ -69,5 +69,9 @@ struct Lowering {
 uint8_t vtype_of(uint16_t qs_type);           // native VType (QS_DATE -> V_DATE)
 uint8_t unify(uint8_t a, uint8_t b);
 int dict_compare(uint16_t qs_type, uint32_t width, const char *a, const char *b);   // -1 / 0 / 1, 2 = unordered
+// Codes of a sorted dictionary that satisfy `attribute <cmp> literal`: [lo, lo + span), or the complement (negate).
+int dict_code_range(uint16_t attr_type, uint32_t width, const char *dict, uint32_t n_entries, uint8_t cmp,
+                    const qs_node *lit, const char *str_pool, uint32_t str_pool_bytes, uint64_t *lo, uint64_t *span,
+                    bool *negate, std::string *err);
 
 }  // namespace qs
