@@ -1019,7 +1019,7 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
   dev_free(d_remap);
   if (rc == QSGPU_OK && remap_bytes) {
     rc = check_device_error(d);
-    if (rc) set_error(rc, "stage: a block dictionary value is missing from the relation's dictionary");
+    if (rc == QSGPU_ERR_INVALID) set_error(rc, "stage: a block dictionary value is missing from the relation's dictionary");
   }
   if (rc != QSGPU_OK) return rc;
   const uint64_t rows_after = std::max<uint64_t>(rel->host_rows, first_row + total_rows);
@@ -1124,7 +1124,7 @@ static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *root
     // registers) rather than copied out of a native tile, so the tile need not be decoded in shared memory
     const bool coded_value = n->kind == QS_N_ATTRIBUTE && n->b != 2 && L.rel && static_cast<uint32_t>(n->a) < L.rel->attrs.size() &&
                              L.rel->code_width(static_cast<uint32_t>(n->a)) != 0 && n->type <= QS_DOUBLE &&
-                             output->attrs[j].type == L.rel->attrs[n->a].type;
+                             n->type == L.rel->attrs[n->a].type && output->attrs[j].type == n->type;
     if (n->kind == QS_N_ATTRIBUTE && !coded_value) {
       const qsgpu_relation *src = n->b == 2 ? L.build_rel : L.rel;
       if (!src || static_cast<uint32_t>(n->a) >= src->attrs.size() ||
