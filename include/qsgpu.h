@@ -511,9 +511,50 @@ int qsgpu_partition_scatter_peers(qsgpu_relation_t input, uint32_t key_attr, uin
 int qsgpu_join_partition(qsgpu_join_table_t table, qsgpu_relation_t input, uint32_t key_attr,
                          uint32_t n_parts, qsgpu_relation_t output, uint64_t *host_offsets);
 
+/* ----------------------------------------------------------------- multi-GPU */
+/*
+ * One process per GPU; partition id <-> device id.  The reference keeps ONE aggregation state / hash table / LIP
+ * filter per query (or per partition) inside one process (query_execution/QueryContext.cpp:66-97) and merges
+ * per-thread partial states with AggregationHandle*::mergeStates
+ * (expressions/aggregation/AggregationHandleSum.cpp:109-117) and ThreadPrivateCompactKeyHashTable::mergeFrom
+ * (storage/ThreadPrivateCompactKeyHashTable.cpp:306-363).  Across GPUs the same merges are collectives over
+ * NVLink (NCCL, resolved at run time: libnccl.so.2, or the path in QSGPU_NCCL_LIB), queued on the library
+ * stream behind the kernels that produce their input.  Every rank must issue the same collectives in the same
+ * order.  A NULL communicator (or one of a single rank) turns each call into a no-op / local copy.
+ */
+typedef struct qs_comm_id { unsigned char bytes[128]; } qs_comm_id;    /* an ncclUniqueId */
+typedef struct qsgpu_comm *qsgpu_comm_t;
+/* Rank 0 creates the id; the caller carries it to the other ranks (any host channel), then every rank creates
+ * its communicator for its device.  qsgpu_init must have been called for `dev`. */
+int qsgpu_comm_unique_id(qs_comm_id *id);
+int qsgpu_comm_create(int dev, int rank, int n_ranks, const qs_comm_id *id, qsgpu_comm_t *out);
+int qsgpu_comm_destroy(qsgpu_comm_t comm);
+int qsgpu_comm_rank(qsgpu_comm_t comm, int *rank, int *n_ranks);
+/* All ranks have finished the work queued so far (device-side all-reduce of one word, then a host wait). */
+int qsgpu_comm_barrier(qsgpu_comm_t comm);
+/* Host values reduced over all ranks in place (op: 0 = sum, 1 = min, 2 = max): global row counts and the exact
+ * min / max statistics \analyze records, when every rank loaded only its partition. */
+int qsgpu_comm_allreduce_i64(qsgpu_comm_t comm, int64_t *values, uint32_t n, uint32_t op);
+/*
+ * mergeStates across GPUs.  SINGLE_STATE / COMPACT_KEY: one all-gather of the state's fixed-size
+ * [states | packed keys] block and ONE kernel that folds all ranks' blocks in rank order, keyed by the packed
+ * group key (the same group may sit in a different row on every rank) -- every rank ends with bit-identical
+ * totals, no host synchronisation.  SEPARATE_CHAINING / COLLISION_FREE: the live groups of every rank are
+ * all-gathered (padded to the largest rank) and the foreign ones upserted into the local table.
+ * After the call every rank holds the merged state; finalize as usual.
+ */
+int qsgpu_agg_merge_all(qsgpu_agg_state_t state, qsgpu_comm_t comm);
+/* Bitwise OR of a LIP filter's words over all ranks, in place (every GPU filled its copy from its share of the
+ * build side; utility/lip_filter/BitVectorExactFilter.hpp:152-176 inserts into ONE shared filter). */
+int qsgpu_lip_allreduce(qsgpu_lip_t lip, qsgpu_comm_t comm);
+/* *out (created by the call) = the rows of `local` of rank 0, then rank 1, ...: the broadcast build side of a
+ * hash join (every GPU builds its own copy of the table and probes its lineitem partition locally), or the
+ * top-k candidates of every rank.  Row counts are exchanged first (one host synchronisation). */
+int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t comm, qsgpu_relation_t *out);
+
 /* ---------------------------------------------------------- instrumentation */
-/* CUDA-event time (ms) of the most recent kernel of the given family launched
- * by the calling thread's last call, for bench.py's roofline block. */
+/* CUDA-event time (ms) of the most recent kernel of the given family (launched by any thread of the process)
+ * while timing is on, for bench.py's roofline block.  Timing makes every launch wait for its kernel. */
 enum { QS_K_SCAN_AGG = 0, QS_K_SELECT = 1, QS_K_LIP = 2, QS_K_JOIN_BUILD = 3,
        QS_K_JOIN_PROBE = 4, QS_K_GROUPBY = 5, QS_K_PARTITION = 6, QS_K_TOPK = 7,
        QS_K_STAGE = 8, QS_K_FAMILIES = 9 };
@@ -523,6 +564,9 @@ int qsgpu_set_timing(int enabled);
 int qsgpu_timer_start(int dev);
 int qsgpu_timer_stop(int dev, float *ms);
 int qsgpu_last_kernel_ms(uint32_t family, float *ms);
+/* The same, accumulated over every launch of the family (by any thread) since timing was last switched on:
+ * the last launch, the longest one, their sum and their number.  Any output pointer may be NULL. */
+int qsgpu_kernel_ms_stats(uint32_t family, float *last, float *max, float *sum, uint32_t *count);
 
 
 /* ------------------------------------------------------------ query compiler */

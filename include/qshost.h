@@ -32,6 +32,13 @@ enum { QSHOST_BASIC_COLUMN_STORE = 0, QSHOST_COMPRESSED_COLUMN_STORE = 1, QSHOST
 /* dev: CUDA device (qsgpu_init is called for it); num_workers: Worker threads. */
 int qshost_db_create(int dev, int num_workers, qshost_db_t *out);
 int qshost_db_destroy(qshost_db_t db);
+/* Several GPUs, one process per GPU: `comm` is a qsgpu_comm_t (include/qsgpu.h) of this process's device.  Set it
+ * BEFORE loading: every relation loaded afterwards is this rank's PARTITION of the relation (lineitem block-partitioned
+ * on l_orderkey boundaries, orders and customer in shares), statistics and row counts are reduced over the ranks,
+ * and the query entry points return the COMPLETE answer on every rank: partial aggregation states are merged
+ * (Q1, Q6), LIP filters OR-reduced, the filtered orders all-gathered for a broadcast join and the per-rank top-k
+ * candidates gathered (Q3) -- all inside the C++ operator layer, through the collectives of the C ABI. */
+int qshost_db_set_comm(qshost_db_t db, void *comm);
 /* COPY ... + \analyze: cut native-width columns into storage blocks of rows_per_block
  * tuples in `layout`, and record min/max of the key attributes.  May be called again
  * for the same relation to replace it. */

@@ -72,6 +72,10 @@ class qs_ipc_handle(C.Structure):
     _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
+class qs_comm_id(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 128)]
+
+
 class qs_lip_ref(C.Structure):
     _fields_ = [("lip", C.c_void_p), ("attr", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -171,8 +175,18 @@ SIGNATURES = {
     "qsgpu_partition_count": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _U64P]),
     "qsgpu_partition_scatter_peers": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VPP, _U64P]),
     "qsgpu_join_partition": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
+    "qsgpu_comm_unique_id": (C.c_int, [C.POINTER(qs_comm_id)]),
+    "qsgpu_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(qs_comm_id), _VPP]),
+    "qsgpu_comm_destroy": (C.c_int, [_VP]),
+    "qsgpu_comm_rank": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "qsgpu_comm_barrier": (C.c_int, [_VP]),
+    "qsgpu_comm_allreduce_i64": (C.c_int, [_VP, C.POINTER(C.c_int64), C.c_uint32, C.c_uint32]),
+    "qsgpu_agg_merge_all": (C.c_int, [_VP, _VP]),
+    "qsgpu_lip_allreduce": (C.c_int, [_VP, _VP]),
+    "qsgpu_relation_allgather": (C.c_int, [_VP, _VP, _VPP]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
+    "qsgpu_kernel_ms_stats": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _U32P]),
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }

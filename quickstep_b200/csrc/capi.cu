@@ -30,7 +30,11 @@ struct SelfCheck {
 };
 static thread_local SelfCheck *t_sc = nullptr;
 static constexpr int kSelfCheckStop = 1000;
-static thread_local float t_ms[QS_K_FAMILIES];
+// Per-family kernel times since qsgpu_set_timing(1).  Process-wide, not thread-local: the kernels of a query that
+// runs through an operator layer are launched by Worker threads, the reader is the thread that submitted the query.
+struct FamilyMs { float last = 0, max = 0, sum = 0; uint32_t count = 0; };
+static FamilyMs g_ms[QS_K_FAMILIES];
+static std::mutex g_ms_mu;
 
 void set_error(int status, const std::string &msg) {
   char buf[32];
@@ -46,7 +50,12 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
 bool timing_enabled() { return g_timing.load(); }
-void record_ms(uint32_t family, float ms) { if (family < QS_K_FAMILIES) t_ms[family] = ms; }
+void record_ms(uint32_t family, float ms) {
+  if (family >= QS_K_FAMILIES) return;
+  std::lock_guard<std::mutex> lk(g_ms_mu);
+  FamilyMs &f = g_ms[family];
+  f.last = ms; f.max = std::max(f.max, ms); f.sum += ms; ++f.count;
+}
 
 // Device the calling thread last resolved through device(): where dev_malloc / dev_free go.
 static thread_local Device *t_dev = nullptr;
@@ -122,10 +131,12 @@ Device *device(int dev) {
 }
 
 // Times one kernel family with CUDA events on the launching stream.
+static std::mutex g_timer_mu;      // the two events are per device: one timed launch at a time
 struct KernelTimer {
   Device *d; uint32_t family; bool on;
+  std::unique_lock<std::mutex> lk;
   KernelTimer(Device *dev, uint32_t fam) : d(dev), family(fam), on(timing_enabled()) {
-    if (on) cudaEventRecord(d->ev0, d->stream);
+    if (on) { lk = std::unique_lock<std::mutex>(g_timer_mu); cudaEventRecord(d->ev0, d->stream); }
   }
   ~KernelTimer() {
     if (!on) return;
@@ -437,10 +448,23 @@ int qsgpu_stream(int dev, void **stream) {
 
 int qsgpu_launch_count(uint64_t *n) { *n = g_launches.load(); return QSGPU_OK; }
 
-int qsgpu_set_timing(int enabled) { g_timing.store(enabled != 0); return QSGPU_OK; }
+int qsgpu_set_timing(int enabled) {
+  if (enabled) { std::lock_guard<std::mutex> lk(g_ms_mu); for (FamilyMs &f : g_ms) f = FamilyMs{}; }
+  g_timing.store(enabled != 0);
+  return QSGPU_OK;
+}
+int qsgpu_kernel_ms_stats(uint32_t family, float *last, float *max, float *sum, uint32_t *count) {
+  if (family >= QS_K_FAMILIES) { set_error(QSGPU_ERR_INVALID, "unknown kernel family"); return QSGPU_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(g_ms_mu);
+  if (last) *last = g_ms[family].last;
+  if (max) *max = g_ms[family].max;
+  if (sum) *sum = g_ms[family].sum;
+  if (count) *count = g_ms[family].count;
+  return QSGPU_OK;
+}
 int qsgpu_last_kernel_ms(uint32_t family, float *ms) {
   if (family >= QS_K_FAMILIES) { set_error(QSGPU_ERR_INVALID, "bad kernel family"); return QSGPU_ERR_INVALID; }
-  *ms = t_ms[family];
+  { std::lock_guard<std::mutex> lk(g_ms_mu); *ms = g_ms[family].last; }
   return QSGPU_OK;
 }
 
@@ -1216,7 +1240,12 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   if (!d) return QSGPU_ERR_NO_DEVICE;
   std::unique_ptr<qsgpu_agg_state> s(new qsgpu_agg_state);
   s->dev = spec->dev;
-  s->strategy = spec->strategy;
+  // ThreadPrivateCompactKeyHashTable is chosen by the reference for up to 10,000 estimated groups
+  // (StarSchemaSimpleCostModel.cpp:722); the compact-key kernels keep at most kCompactMaxGroups (256) groups
+  // per CTA and per state, so a larger estimate takes the hash-table strategy (any key <= 8 bytes fits it).
+  const uint32_t strategy = (spec->strategy == QS_AGG_COMPACT_KEY && spec->estimated_num_entries > static_cast<uint64_t>(kCompactMaxGroups))
+                                ? static_cast<uint32_t>(QS_AGG_SEPARATE_CHAINING) : spec->strategy;
+  s->strategy = strategy;
   if (spec->exprs) {
     s->nodes.assign(spec->exprs->nodes, spec->exprs->nodes + spec->exprs->n_nodes);
     s->str_pool.assign(spec->exprs->str_pool ? spec->exprs->str_pool : "", spec->exprs->str_pool ? spec->exprs->str_pool_bytes : 0);
@@ -1232,7 +1261,7 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   if (spec->n_aggregates > static_cast<uint32_t>(kMaxOut)) { set_error(QSGPU_ERR_UNSUPPORTED, "too many aggregates"); return QSGPU_ERR_UNSUPPORTED; }
 
   AggDesc &A = s->A;
-  A.strategy = spec->strategy;
+  A.strategy = strategy;
   A.error_flag = d->d_error;
   // ---- value words: one per SUM/AVG/MIN/MAX, COUNT reads the row-count word
   Lowering typer(&s->exprs, nullptr);
@@ -1277,7 +1306,7 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   }
   A.key_words = std::max<uint32_t>(1, (key_bytes + 7) / 8);
 
-  switch (spec->strategy) {
+  switch (strategy) {
     case QS_AGG_SINGLE_STATE:
       if (A.n_key_cols != 0) { set_error(QSGPU_ERR_INVALID, "SINGLE_STATE with GROUP BY"); return QSGPU_ERR_INVALID; }
       A.partial_rows = 1;
@@ -1311,7 +1340,7 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   QS_CUDA(dev_malloc(&s->d_done, 256));
   QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
   QS_CUDA(dev_malloc(&s->d_idx_count, 256));
-  if (spec->strategy == QS_AGG_SINGLE_STATE || spec->strategy == QS_AGG_COMPACT_KEY) {
+  if (strategy == QS_AGG_SINGLE_STATE || strategy == QS_AGG_COMPACT_KEY) {
     // one partial row set per CTA of the persistent grid: up to 4 resident CTAs per SM for states with a few
     // partial rows (Q6 on dictionary codes: 12 KB tiles, 32 registers), 2 for the 256-group compact-key states
     // (their kernels hold the hot groups' sums in registers and never fit more than 2)
@@ -1326,14 +1355,16 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     QS_CUDA(dev_malloc(&A.dir_keys, A.dir_cap * 8));
     QS_CUDA(dev_malloc(&A.dir_gid, A.dir_cap * 4));
     QS_CUDA(cudaMemsetAsync(A.dir_gid, 0xff, A.dir_cap * 4, d->stream));
-    QS_CUDA(dev_malloc(&A.gid_keys, kCompactMaxGroups * 8));
-    QS_CUDA(cudaMemsetAsync(A.gid_keys, 0, kCompactMaxGroups * 8, d->stream));
-    QS_CUDA(dev_malloc(&A.states, prow));
+    // [states: partial_rows x words | packed keys: partial_rows] in ONE block: it is the send buffer of the
+    // cross-GPU merge (qsgpu_agg_merge_all all-gathers it as it lies, no packing pass)
+    QS_CUDA(dev_malloc(&A.states, prow + static_cast<size_t>(A.partial_rows) * 8));
+    A.gid_keys = A.states + static_cast<size_t>(A.partial_rows) * A.words;
+    QS_CUDA(cudaMemsetAsync(A.gid_keys, 0, static_cast<size_t>(A.partial_rows) * 8, d->stream));
     A.cap = A.partial_rows;
     QS_CUDA(launch_fill_identity(A.states, A.partial_rows, A, d->stream));
     count_launch();
   } else {
-    if (spec->strategy == QS_AGG_COLLISION_FREE) A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
+    if (strategy == QS_AGG_COLLISION_FREE) A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
     else {
       uint64_t want = std::max<uint64_t>(1024, spec->estimated_num_entries * 2);
       uint64_t cap = 1024;
@@ -1672,7 +1703,7 @@ int qsgpu_agg_destroy(qsgpu_agg_state_t s) {
   if (s->existence) qsgpu_lip_destroy(s->existence);
   device(s->dev);
   AggDesc &A = s->A;
-  dev_free(A.partials); dev_free(A.dir_keys); dev_free(A.dir_gid); dev_free(A.n_groups); dev_free(A.gid_keys);
+  dev_free(A.partials); dev_free(A.dir_keys); dev_free(A.dir_gid); dev_free(A.n_groups);   // gid_keys lives inside the states block
   dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
   dev_free(s->d_done); dev_free(s->d_idx); dev_free(s->d_idx_count); dev_free(s->d_exp_states); dev_free(s->d_exp_keys);
   delete s;

@@ -1,0 +1,401 @@
+// Multi-GPU collectives behind the C ABI (include/qsgpu.h, "multi-GPU"): one process per GPU, NCCL over
+// NVLink / NVSwitch.  What crosses GPUs on this path:
+//   * partial aggregation states            AggregationHandle*::mergeStates
+//                                           (expressions/aggregation/AggregationHandleSum.cpp:109-117),
+//                                           ThreadPrivateCompactKeyHashTable::mergeFrom
+//                                           (storage/ThreadPrivateCompactKeyHashTable.cpp:306-363)
+//   * LIP filter bit words (OR)             one filter per query in the reference (QueryContext.cpp:66-97);
+//                                           here every GPU fills its copy from its share of the build side
+//   * rows of a small relation (all-gather) the broadcast build side of a hash join, top-k candidates
+// The reference instantiates one state / hash table per partition inside ONE process
+// (query_execution/QueryContext.cpp:66-97); "partition id <-> device id" is the mapping used here.
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2): a process that already loaded it (torch) shares that
+// copy, and a single-GPU process never needs it.  Every collective is queued on the library stream of the
+// device, behind the kernels that produce its input, and is followed by ONE kernel that consumes the gathered
+// buffer: the host never waits between the scan and the finalize.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "qs_host.h"
+#include "qs_kernels.cuh"
+
+struct qsgpu_comm {
+  int dev = 0, rank = 0, n_ranks = 1;
+  ncclComm_t comm = nullptr;
+  std::mutex mu;                       // one collective at a time per communicator
+  char *scratch = nullptr;             // receive buffer of the gather-type collectives
+  size_t scratch_bytes = 0;
+  unsigned long long *d_counts = nullptr;     // [n_ranks] row counts on the device
+  unsigned long long *h_counts = nullptr;     // pinned landing buffer
+};
+
+namespace qs {
+
+namespace {
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) return QSGPU_OK;
+  const char *names[] = {std::getenv("QSGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    if (!n || !*n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    set_error(QSGPU_ERR_UNSUPPORTED, "libnccl.so.2 not found (set QSGPU_NCCL_LIB): the multi-GPU entry points need NCCL");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  bool ok = true;
+  auto sym = [&](const char *name) { void *p = dlsym(h, name); ok = ok && p != nullptr; return p; };
+  NcclApi a;
+  a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+  a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+  a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
+  a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+  a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+  a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+  a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+  if (!ok) { set_error(QSGPU_ERR_UNSUPPORTED, "libnccl.so.2 lacks a required symbol"); return QSGPU_ERR_UNSUPPORTED; }
+  a.handle = h;
+  g_nccl = a;
+  return QSGPU_OK;
+}
+
+int nccl_fail(ncclResult_t r, const char *what) {
+  set_error(QSGPU_ERR_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error"));
+  return QSGPU_ERR_CUDA;
+}
+#define QS_NCCL(call)                                                  \
+  do {                                                                 \
+    ncclResult_t r__ = (call);                                         \
+    if (r__ != ncclSuccess) return nccl_fail(r__, #call);              \
+  } while (0)
+
+int ensure_scratch(qsgpu_comm *c, size_t bytes) {
+  if (bytes <= c->scratch_bytes) return QSGPU_OK;
+  if (c->scratch) dev_free(c->scratch);
+  c->scratch = nullptr;
+  c->scratch_bytes = 0;
+  const size_t want = std::max<size_t>(bytes, 1u << 20);
+  QS_CUDA(dev_malloc(&c->scratch, want));
+  c->scratch_bytes = want;
+  return QSGPU_OK;
+}
+
+constexpr uint32_t kMaxMergeRanks = 16;
+
+// ---- kernels ---------------------------------------------------------------------------------------------
+// Fold the gathered [states | keys] blocks of all ranks, IN RANK ORDER, into this rank's state (the own block
+// is part of `gathered`, so the state is rebuilt from scratch): every rank computes the same additions in the
+// same order and ends with bit-identical totals.  One CTA; partial_rows <= 256 threads do the work.
+__global__ void __launch_bounds__(256) k_merge_gathered_compact(const __grid_constant__ AggDesc A, const uint64_t *gathered,
+                                                                uint32_t n_ranks) {
+  __shared__ short inv[kMaxMergeRanks][kCompactMaxGroups];     // inv[r][local group id] = row of rank r's block, -1 = none
+  const uint32_t t = threadIdx.x;
+  const uint32_t rows = A.partial_rows, W = A.words;
+  const uint64_t block_words = static_cast<uint64_t>(rows) * (W + 1);
+  for (uint32_t i = t; i < kMaxMergeRanks * kCompactMaxGroups; i += blockDim.x) (&inv[0][0])[i] = -1;
+  __syncthreads();
+  for (uint32_t r = 0; r < n_ranks; ++r) {
+    const uint64_t *st = gathered + r * block_words;
+    const uint64_t *keys = st + static_cast<uint64_t>(rows) * W;
+    if (t < rows && st[static_cast<uint64_t>(t) * W] != 0) {        // a group exists where its row count is non-zero
+      const int gid = A.n_key_cols == 0 ? 0 : dir_insert(keys[t], A);
+      if (gid >= 0) inv[r][gid] = static_cast<short>(t);
+    }
+    __syncthreads();       // ids are handed out rank by rank: the order of dense ids is the same run to run
+  }
+  const uint32_t n_groups = A.n_key_cols == 0 ? 1u : min(*reinterpret_cast<volatile uint32_t *>(A.n_groups), rows);
+  if (t < n_groups) {
+    for (uint32_t w = 0; w < W; ++w) {
+      const uint8_t kind = w == 0 ? AK_SUM_I64 : A.kind[w - 1];
+      uint64_t x = w == 0 ? 0 : agg_identity(kind);
+      for (uint32_t r = 0; r < n_ranks; ++r) {
+        const int g = inv[r][t];
+        if (g >= 0) x = agg_combine(kind, x, gathered[r * block_words + static_cast<uint64_t>(g) * W + w]);
+      }
+      A.states[static_cast<uint64_t>(t) * W + w] = x;
+    }
+  }
+}
+
+// words[i] = OR over ranks of gathered[r][i]  (LIP filter bit words; BarrieredReadWriteConcurrentBitVector layout)
+__global__ void k_or_gathered(uint64_t *words, const uint64_t *gathered, uint64_t n_words, uint32_t n_ranks) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t x = 0;
+    for (uint32_t r = 0; r < n_ranks; ++r) x |= gathered[r * n_words + i];
+    words[i] = x;
+  }
+}
+
+// dst[i] |= src[r][i] for the received chunks of the reduce-scatter form (large filters)
+__global__ void k_or_chunks(uint64_t *dst, const uint64_t *src, uint64_t n_words, uint32_t n_src) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t x = dst[i];
+    for (uint32_t r = 0; r < n_src; ++r) x |= src[r * n_words + i];
+    dst[i] = x;
+  }
+}
+
+}  // namespace
+}  // namespace qs
+
+using namespace qs;
+
+extern "C" {
+
+int qsgpu_comm_unique_id(qs_comm_id *id) {
+  static_assert(sizeof(qs_comm_id) == sizeof(ncclUniqueId), "qs_comm_id must hold an ncclUniqueId");
+  int st = load_nccl();
+  if (st) return st;
+  ncclUniqueId u;
+  QS_NCCL(g_nccl.GetUniqueId(&u));
+  std::memcpy(id->bytes, &u, sizeof(u));
+  return QSGPU_OK;
+}
+
+int qsgpu_comm_create(int dev, int rank, int n_ranks, const qs_comm_id *id, qsgpu_comm_t *out) {
+  Device *d = device(dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id) { set_error(QSGPU_ERR_INVALID, "bad rank / n_ranks / id"); return QSGPU_ERR_INVALID; }
+  int st = load_nccl();
+  if (st) return st;
+  std::unique_ptr<qsgpu_comm> c(new qsgpu_comm);
+  c->dev = dev; c->rank = rank; c->n_ranks = n_ranks;
+  ncclUniqueId u;
+  std::memcpy(&u, id->bytes, sizeof(u));
+  QS_NCCL(g_nccl.CommInitRank(&c->comm, n_ranks, u, rank));
+  QS_CUDA(cudaMalloc(&c->d_counts, sizeof(unsigned long long) * static_cast<size_t>(n_ranks) * 2));
+  QS_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts), sizeof(unsigned long long) * static_cast<size_t>(n_ranks) * 2, cudaHostAllocPortable));
+  *out = c.release();
+  return QSGPU_OK;
+}
+
+int qsgpu_comm_destroy(qsgpu_comm_t c) {
+  if (!c) return QSGPU_OK;
+  Device *d = device(c->dev);
+  if (d) cudaStreamSynchronize(d->stream);
+  if (c->scratch) dev_free(c->scratch);
+  if (c->d_counts) cudaFree(c->d_counts);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+  return QSGPU_OK;
+}
+
+int qsgpu_comm_rank(qsgpu_comm_t c, int *rank, int *n_ranks) {
+  if (!c) { if (rank) *rank = 0; if (n_ranks) *n_ranks = 1; return QSGPU_OK; }
+  if (rank) *rank = c->rank;
+  if (n_ranks) *n_ranks = c->n_ranks;
+  return QSGPU_OK;
+}
+
+int qsgpu_comm_barrier(qsgpu_comm_t c) {
+  if (!c || c->n_ranks == 1) return QSGPU_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Device *d = device(c->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  QS_NCCL(g_nccl.AllReduce(c->d_counts, c->d_counts, 1, ncclUint64, ncclMax, c->comm, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  return QSGPU_OK;
+}
+
+int qsgpu_comm_allreduce_i64(qsgpu_comm_t c, int64_t *values, uint32_t n, uint32_t op) {
+  if (!c || c->n_ranks == 1 || n == 0) return QSGPU_OK;
+  if (op > 2) { set_error(QSGPU_ERR_INVALID, "op: 0 = sum, 1 = min, 2 = max"); return QSGPU_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  Device *d = device(c->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  int64_t *dbuf = nullptr;
+  QS_CUDA(dev_malloc(&dbuf, static_cast<size_t>(n) * 8));
+  QS_CUDA(cudaMemcpyAsync(dbuf, values, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, d->stream));
+  QS_NCCL(g_nccl.AllReduce(dbuf, dbuf, n, ncclInt64, op == 0 ? ncclSum : op == 1 ? ncclMin : ncclMax, c->comm, d->stream));
+  QS_CUDA(cudaMemcpyAsync(values, dbuf, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  dev_free(dbuf);
+  return QSGPU_OK;
+}
+
+// rows of every rank (host), via an all-gather of one word per rank
+static int gather_counts(qsgpu_comm *c, Device *d, unsigned long long mine, std::vector<uint64_t> *counts) {
+  c->h_counts[c->n_ranks] = mine;
+  QS_CUDA(cudaMemcpyAsync(c->d_counts + c->n_ranks, c->h_counts + c->n_ranks, 8, cudaMemcpyHostToDevice, d->stream));
+  QS_NCCL(g_nccl.AllGather(c->d_counts + c->n_ranks, c->d_counts, 1, ncclUint64, c->comm, d->stream));
+  QS_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, 8 * static_cast<size_t>(c->n_ranks), cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  counts->assign(c->h_counts, c->h_counts + c->n_ranks);
+  return QSGPU_OK;
+}
+
+int qsgpu_agg_merge_all(qsgpu_agg_state_t state, qsgpu_comm_t c) {
+  if (!c || c->n_ranks == 1) return QSGPU_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Device *d = device(state->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (state->dev != c->dev) { set_error(QSGPU_ERR_INVALID, "state and communicator on different devices"); return QSGPU_ERR_INVALID; }
+  const AggDesc &A = state->A;
+  if (state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY) {
+    std::lock_guard<std::mutex> state_lock(state->mu);
+    if (static_cast<uint32_t>(c->n_ranks) > kMaxMergeRanks) { set_error(QSGPU_ERR_UNSUPPORTED, "more than 16 ranks"); return QSGPU_ERR_UNSUPPORTED; }
+    // the state's [states | keys] block is contiguous (qsgpu_agg_create): gathered as it lies
+    const size_t block_words = static_cast<size_t>(A.partial_rows) * (A.words + 1);
+    int st = ensure_scratch(c, block_words * 8 * c->n_ranks);
+    if (st) return st;
+    QS_NCCL(g_nccl.AllGather(A.states, c->scratch, block_words, ncclUint64, c->comm, d->stream));
+    k_merge_gathered_compact<<<1, 256, 0, d->stream>>>(A, reinterpret_cast<const uint64_t *>(c->scratch), static_cast<uint32_t>(c->n_ranks));
+    QS_CUDA(cudaGetLastError());
+    count_launch();
+    return QSGPU_OK;
+  }
+  // hash / dense tables: export the live groups, all-gather them padded to the largest rank, fold the foreign ones
+  void *d_states = nullptr, *d_keys = nullptr;
+  uint64_t n = 0;
+  uint32_t words = 0, kw = 0;
+  int st = qsgpu_agg_partial(state, &d_states, &d_keys, &n, &words, &kw);
+  if (st) return st;
+  std::vector<uint64_t> counts;
+  st = gather_counts(c, d, n, &counts);
+  if (st) return st;
+  uint64_t mx = 0;
+  for (uint64_t x : counts) mx = std::max(mx, x);
+  if (mx == 0) return QSGPU_OK;
+  const size_t row_words = static_cast<size_t>(words) + kw;
+  st = ensure_scratch(c, (static_cast<size_t>(c->n_ranks) + 1) * mx * row_words * 8);
+  if (st) return st;
+  uint64_t *send = reinterpret_cast<uint64_t *>(c->scratch) + static_cast<size_t>(c->n_ranks) * mx * row_words;
+  QS_CUDA(cudaMemcpyAsync(send, d_states, n * words * 8, cudaMemcpyDeviceToDevice, d->stream));
+  QS_CUDA(cudaMemcpyAsync(send + mx * words, d_keys, n * kw * 8, cudaMemcpyDeviceToDevice, d->stream));
+  QS_NCCL(g_nccl.AllGather(send, c->scratch, mx * row_words, ncclUint64, c->comm, d->stream));
+  for (int r = 0; r < c->n_ranks; ++r) {
+    if (r == c->rank || counts[r] == 0) continue;
+    const uint64_t *blk = reinterpret_cast<const uint64_t *>(c->scratch) + static_cast<size_t>(r) * mx * row_words;
+    st = qsgpu_agg_merge_partial(state, blk, blk + mx * words, counts[r]);
+    if (st) return st;
+  }
+  return QSGPU_OK;
+}
+
+int qsgpu_lip_allreduce(qsgpu_lip_t lip, qsgpu_comm_t c) {
+  if (!c || c->n_ranks == 1) return QSGPU_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Device *d = device(lip->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  const uint64_t nw = lip->n_words;
+  const uint32_t R = static_cast<uint32_t>(c->n_ranks);
+  if (nw * 8 <= (8u << 20) || nw < R) {
+    // small filter (Q3's customer filter: 188 KB at SF10): latency-bound, one all-gather + one OR kernel
+    int st = ensure_scratch(c, nw * 8 * R);
+    if (st) return st;
+    QS_NCCL(g_nccl.AllGather(lip->d.words, c->scratch, nw, ncclUint64, c->comm, d->stream));
+    const int grid = static_cast<int>(std::min<uint64_t>((nw + 255) / 256, 148 * 8));
+    k_or_gathered<<<std::max(grid, 1), 256, 0, d->stream>>>(lip->d.words, reinterpret_cast<const uint64_t *>(c->scratch), nw, R);
+    QS_CUDA(cudaGetLastError());
+    count_launch();
+    return QSGPU_OK;
+  }
+  // large filter: bandwidth-optimal form.  Rank j owns words [j*chunk, (j+1)*chunk): every rank sends chunk j of
+  // its filter to rank j (one grouped exchange), ORs what it received into its own chunk, and the reduced chunks
+  // are all-gathered in place.
+  const uint64_t chunk = (nw + R - 1) / R;
+  auto len = [&](uint32_t j) { const uint64_t b = j * chunk; return b >= nw ? 0ull : std::min<uint64_t>(chunk, nw - b); };
+  int st = ensure_scratch(c, chunk * 8 * R);
+  if (st) return st;
+  uint64_t *recv = reinterpret_cast<uint64_t *>(c->scratch);
+  const uint64_t my_len = len(c->rank);
+  QS_NCCL(g_nccl.GroupStart());
+  uint32_t slot = 0;
+  for (uint32_t p = 0; p < R; ++p) {
+    if (static_cast<int>(p) == c->rank) continue;
+    if (len(p)) QS_NCCL(g_nccl.Send(lip->d.words + p * chunk, len(p), ncclUint64, static_cast<int>(p), c->comm, d->stream));
+    if (my_len) QS_NCCL(g_nccl.Recv(recv + static_cast<uint64_t>(slot) * my_len, my_len, ncclUint64, static_cast<int>(p), c->comm, d->stream));
+    ++slot;
+  }
+  QS_NCCL(g_nccl.GroupEnd());
+  if (my_len) {
+    const int grid = static_cast<int>(std::min<uint64_t>((my_len + 255) / 256, 148 * 8));
+    k_or_chunks<<<std::max(grid, 1), 256, 0, d->stream>>>(lip->d.words + c->rank * chunk, recv, my_len, R - 1);
+    QS_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  QS_NCCL(g_nccl.GroupStart());
+  for (uint32_t p = 0; p < R; ++p)
+    if (len(p)) QS_NCCL(g_nccl.Broadcast(lip->d.words + p * chunk, lip->d.words + p * chunk, len(p), ncclUint64, static_cast<int>(p), c->comm, d->stream));
+  QS_NCCL(g_nccl.GroupEnd());
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t c, qsgpu_relation_t *out) {
+  if (!local || !out) { set_error(QSGPU_ERR_INVALID, "null relation"); return QSGPU_ERR_INVALID; }
+  Device *d = device(local->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (local->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "all-gather of a dictionary-coded relation"); return QSGPU_ERR_UNSUPPORTED; }
+  uint64_t mine = 0;
+  int st = qsgpu_relation_num_rows(local, &mine);      // the row count of a temporary may still be device-only
+  if (st) return st;
+  const int R = c ? c->n_ranks : 1;
+  std::vector<uint64_t> counts(1, mine);
+  std::unique_lock<std::mutex> lk;
+  if (R > 1) {
+    lk = std::unique_lock<std::mutex>(c->mu);
+    st = gather_counts(c, d, mine, &counts);
+    if (st) return st;
+  }
+  uint64_t total = 0;
+  for (uint64_t x : counts) total += x;
+  qsgpu_relation *rel = nullptr;
+  st = qsgpu_relation_create(local->dev, static_cast<uint32_t>(local->attrs.size()), local->attrs.data(), std::max<uint64_t>(total, 1), &rel);
+  if (st) return st;
+  if (R == 1) {
+    for (size_t a = 0; a < local->attrs.size(); ++a)
+      if (mine) QS_CUDA(cudaMemcpyAsync(rel->cols[a], local->cols[a], mine * local->attrs[a].width, cudaMemcpyDeviceToDevice, d->stream));
+  } else {
+    // all-gather with per-rank counts: one broadcast per (rank, attribute), all in ONE NCCL group
+    QS_NCCL(g_nccl.GroupStart());
+    uint64_t first = 0;
+    for (int r = 0; r < R; ++r) {
+      if (counts[r]) {
+        for (size_t a = 0; a < local->attrs.size(); ++a) {
+          const size_t w = local->attrs[a].width;
+          QS_NCCL(g_nccl.Broadcast(local->cols[a], rel->cols[a] + first * w, counts[r] * w, ncclChar, r, c->comm, d->stream));
+        }
+      }
+      first += counts[r];
+    }
+    QS_NCCL(g_nccl.GroupEnd());
+  }
+  st = qsgpu_relation_set_num_rows(rel, total);
+  if (st) { qsgpu_relation_destroy(rel); return st; }
+  *out = rel;
+  return QSGPU_OK;
+}
+
+}  // extern "C"

@@ -62,6 +62,7 @@ __global__ void k_merge_foreign_compact(const __grid_constant__ AggDesc A, const
   if (g >= f_groups) return;
   if (f_states[static_cast<uint64_t>(g) * A.words] == 0) return;   // empty group
   const int gid = dir_insert(f_keys[g], A);
+  if (gid < 0) return;                      // group limit exceeded: QSGPU_ERR_CAPACITY was raised
   for (uint32_t w = 0; w < A.words; ++w) {
     const uint8_t kind = w == 0 ? AK_SUM_I64 : A.kind[w - 1];
     uint64_t *dst = &A.states[static_cast<uint64_t>(gid) * A.words + w];

@@ -253,53 +253,62 @@ struct AggSink : SinkBase {
 };
 
 // Per-CTA key -> local group id table (shared memory, open addressing).  Ids
-// are handed out in arrival order; ids < HOT live in registers.
+// are handed out in arrival order; ids < HOT live in registers.  At most LG (= LS / 2) keys are ever
+// installed, so the probe always reaches an empty slot; a key that arrives when all LG ids are taken is NOT
+// installed: the row is dropped (-1) and QSGPU_ERR_CAPACITY is raised (the call fails at its next sync).
 __device__ __forceinline__ int local_lookup(uint64_t key, const AggSmem &M, uint32_t LS, uint32_t LG,
                                             uint32_t *error_flag) {
   uint32_t h = static_cast<uint32_t>(mix64(key)) & (LS - 1);
   volatile int *lslot = M.lslot;
   volatile uint64_t *lkeys = M.lkeys;
-  while (true) {
+  for (uint32_t moved = 0; moved < LS;) {
     const int s = lslot[h];
     if (s >= 0) {
       if (lkeys[h] == key) return s;
       h = (h + 1) & (LS - 1);
+      ++moved;
       continue;
     }
     if (s == -1 && atomicCAS(&M.lslot[h], -1, -2) == -1) {
-      uint32_t id = atomicAdd(M.nlocal, 1u);
+      const uint32_t id = atomicAdd(M.nlocal, 1u);
       if (id >= LG) {
         atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-        id = 0;
-      } else {
-        M.lkey_by_id[id] = key;
+        lslot[h] = -1;                       // release the slot: nothing was installed
+        return -1;
       }
+      M.lkey_by_id[id] = key;
       lkeys[h] = key;
       __threadfence_block();
-      if (id < LG) *reinterpret_cast<volatile uint32_t *>(&M.lready[id]) = 1u;
+      *reinterpret_cast<volatile uint32_t *>(&M.lready[id]) = 1u;
       lslot[h] = static_cast<int>(id);
       return static_cast<int>(id);
     }
+    // busy (another thread is publishing this slot): look again
   }
+  atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+  return -1;
 }
 
-// Global key -> dense group id directory (persists across work orders).
+// Global key -> dense group id directory (persists across work orders).  Same rule: at most partial_rows
+// (<= dir_cap / 4) keys are installed; one group too many raises QSGPU_ERR_CAPACITY and returns -1.
 __device__ __forceinline__ int dir_insert(uint64_t key, const AggDesc &A) {
   uint32_t h = static_cast<uint32_t>(mix64(key)) & (A.dir_cap - 1);
   volatile int *gid = A.dir_gid;
   volatile uint64_t *keys = A.dir_keys;
-  while (true) {
+  for (uint32_t moved = 0; moved < A.dir_cap;) {
     const int g = gid[h];
     if (g >= 0) {
       if (keys[h] == key) return g;
       h = (h + 1) & (A.dir_cap - 1);
+      ++moved;
       continue;
     }
     if (g == -1 && atomicCAS(&A.dir_gid[h], -1, -2) == -1) {
-      uint32_t id = atomicAdd(A.n_groups, 1u);
+      const uint32_t id = atomicAdd(A.n_groups, 1u);
       if (id >= A.partial_rows) {
         atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-        id = A.partial_rows - 1;
+        gid[h] = -1;
+        return -1;
       }
       keys[h] = key;
       A.gid_keys[id] = key;
@@ -308,6 +317,8 @@ __device__ __forceinline__ int dir_insert(uint64_t key, const AggDesc &A) {
       return static_cast<int>(id);
     }
   }
+  atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+  return -1;
 }
 
 template <class Q>
@@ -478,6 +489,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
   // ---- publish this CTA's partial state, one row per group it met.
   for (uint32_t l = tid; l < nlocal; l += kBlock) {
     const int gid = Q::grouped ? dir_insert(M.lkey_by_id[l], A) : 0;
+    if (gid < 0) continue;                  // more than partial_rows groups: error raised, nothing written
     uint64_t *dst = A.partials + (static_cast<uint64_t>(blockIdx.x) * A.partial_rows + gid) * W;
     for (uint32_t w = 0; w < W; ++w) dst[w] = M.lstate[l * W + w];
   }

@@ -75,6 +75,12 @@ def set_timing(on: bool):
     A.check(A.load().qsgpu_set_timing(1 if on else 0))
 
 
+def kernel_ms_stats(family: int) -> dict:
+    last, mx, sm, n = C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint32(0)
+    A.check(A.load().qsgpu_kernel_ms_stats(family, C.byref(last), C.byref(mx), C.byref(sm), C.byref(n)))
+    return dict(last=last.value, max=mx.value, sum=sm.value, count=n.value)
+
+
 def last_kernel_ms(family: int) -> float:
     ms = C.c_float(0)
     A.check(A.load().qsgpu_last_kernel_ms(family, C.byref(ms)))
@@ -545,3 +551,59 @@ def radix_partition(rel: Relation, key_attr, n_parts, output: Relation) -> np.nd
     A.check(A.load().qsgpu_radix_partition(rel.h, key_attr, n_parts, output.h,
                                            offs.ctypes.data_as(C.POINTER(C.c_uint64))))
     return offs
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU (NCCL in C)
+class Comm:
+    """qsgpu_comm_t: the communicator behind qsgpu_agg_merge_all / qsgpu_lip_allreduce / qsgpu_relation_allgather.
+    The data-path collectives live in the C ABI; the harness only carries the 128-byte id from rank 0 to the others."""
+
+    def __init__(self, dev: int, rank: int, world: int, id_bytes: bytes):
+        cid = A.qs_comm_id()
+        C.memmove(cid.bytes, id_bytes, 128)
+        self.h = C.c_void_p()
+        self.rank, self.world = rank, world
+        A.check(A.load().qsgpu_comm_create(dev, rank, world, C.byref(cid), C.byref(self.h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        cid = A.qs_comm_id()
+        A.check(A.load().qsgpu_comm_unique_id(C.byref(cid)))
+        return bytes(cid.bytes)
+
+    @classmethod
+    def from_torch_distributed(cls, dev: int):
+        """One communicator per rank of the initialised torch.distributed group (plumbing: broadcasts the id)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", dev) if on_gpu else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(dev, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def barrier(self):
+        A.check(A.load().qsgpu_comm_barrier(self.h))
+
+    def allreduce_i64(self, values, op: int = 0):
+        arr = (C.c_int64 * len(values))(*values)
+        A.check(A.load().qsgpu_comm_allreduce_i64(self.h, arr, len(values), op))
+        return list(arr)
+
+    def merge_all(self, state: "AggState"):
+        A.check(A.load().qsgpu_agg_merge_all(state.h, self.h))
+
+    def lip_allreduce(self, lip: "LipFilter"):
+        A.check(A.load().qsgpu_lip_allreduce(lip.h, self.h))
+
+    def allgather(self, rel: "Relation") -> "Relation":
+        out = C.c_void_p()
+        A.check(A.load().qsgpu_relation_allgather(rel.h, self.h, C.byref(out)))
+        return Relation(out, rel.schema, rel.names, rel.dev)
+
+    def destroy(self):
+        if self.h:
+            A.load().qsgpu_comm_destroy(self.h)
+        self.h = None

@@ -78,6 +78,8 @@ bool SelectOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryConte
                          attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe));
   if (simple_projection_) { for (attribute_id a : simple_selection_) needed |= 1ull << a; }
   else needed |= query_context->getScalarGroup(selection_index_).exprs.referencedAttributes(0);
+  // several devices: a row-by-row operator keeps its input's distribution
+  storage_manager->setPartitioned(output_relation_.getID(), storage_manager->isPartitioned(feed_.relation().getID()));
   for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new SelectWorkOrder(query_id_, feed_.relation(), e, query_context->getPredicate(predicate_index_),
@@ -109,6 +111,7 @@ bool BuildLIPFilterOperator::getAllWorkOrders(WorkOrdersContainer *container, Qu
   const std::uint64_t needed = attrsOf(query_context->getPredicate(build_side_predicate_index_)) |
                                attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe)) |
                                attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kBuild));
+  query_context->noteLIPFiltersBuiltFrom(lip_deployment_index_, storage_manager->isPartitioned(feed_.relation().getID()));
   for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new BuildLIPFilterWorkOrder(query_id_, e, query_context->getPredicate(build_side_predicate_index_),
@@ -130,7 +133,21 @@ void BuildLIPFilterWorkOrder::execute() {
 // --------------------------------------------------------------- BuildHash
 bool BuildHashOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                          StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
-  for (const DeviceExtent &e : feed_.take(storage_manager)) {
+  std::vector<DeviceExtent> extents = feed_.take(storage_manager);
+  if (!extents.empty() && storage_manager->multiDevice() && storage_manager->isPartitioned(feed_.relation().getID())) {
+    // Broadcast join (SURVEY.md section 8e "Join, small build"): the build side was filtered in shares; its rows
+    // are all-gathered so that every device builds its own copy of the table and probes its partition of the
+    // probe side locally, with no shuffle.  The reference builds ONE table all probing threads share
+    // (query_execution/QueryContext.cpp:78-97).  Needs the complete input: blocking edge in the plan.
+    QS_CHECK(feed_.relation().isTemporary() && done_feeding_input_relation_);
+    DeviceExtent all;
+    all.relation = storage_manager->replicated(feed_.relation());
+    extents.assign(1, all);
+    query_context->noteLIPFiltersBuiltFrom(lip_deployment_index_, false);     // built from every device's rows
+  } else if (!extents.empty()) {
+    query_context->noteLIPFiltersBuiltFrom(lip_deployment_index_, storage_manager->isPartitioned(feed_.relation().getID()));
+  }
+  for (const DeviceExtent &e : extents) {
     container->addNormalWorkOrder(
         new BuildHashWorkOrder(query_id_, e, join_key_attributes_, query_context->getPredicate(build_predicate_index_),
                                query_context->getJoinHashTable(hash_table_index_),
@@ -155,6 +172,7 @@ void BuildHashWorkOrder::execute() {
 bool HashJoinOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                         StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   InsertDestination *dest = query_context->getInsertDestination(output_destination_index_);
+  storage_manager->setPartitioned(output_relation_.getID(), storage_manager->isPartitioned(feed_.relation().getID()));
   for (const DeviceExtent &e : feed_.take(storage_manager)) {
     container->addNormalWorkOrder(
         new HashJoinWorkOrder(query_id_, e, join_key_attributes_, query_context->getPredicate(residual_predicate_index_),
@@ -194,6 +212,7 @@ bool AggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, Query
                                            StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   const std::uint64_t needed = query_context->getAggregationSpec(aggr_state_index_).exprs.referencedAttributes(0) |
                                attrsOf(query_context->lipRefs(lip_deployment_index_, QueryContext::LIPAction::kProbe));
+  if (storage_manager->isPartitioned(feed_.relation().getID())) query_context->noteAggregationInput(aggr_state_index_, true);
   for (const DeviceExtent &e : feed_.take(storage_manager, needed)) {
     container->addNormalWorkOrder(
         new AggregationWorkOrder(query_id_, e, query_context->getAggregationState(aggr_state_index_),
@@ -230,12 +249,19 @@ void BuildAggregationExistenceMapWorkOrder::execute() {
 }
 
 bool FinalizeAggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
-                                                   StorageManager *, const tmb::client_id, tmb::MessageBus *) {
+                                                   StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   if (!started_) {
     started_ = true;
+    // several devices: per-device partial states are merged first (AggregationHandle::mergeStates across
+    // GPUs) unless the input is partitioned on the group-by key, in which case every device finalizes its own
+    // groups and the result stays partitioned
+    const bool partial = query_context->aggregationIsPartial(aggr_state_index_);
+    const bool merge = partial && !query_context->getAggregationSpec(aggr_state_index_).partitioned_on_group_by;
+    storage_manager->setPartitioned(output_relation_.getID(), partial && !merge);
     container->addNormalWorkOrder(
         new FinalizeAggregationWorkOrder(query_id_, query_context->getAggregationState(aggr_state_index_),
-                                         query_context->getInsertDestination(output_destination_index_)),
+                                         query_context->getInsertDestination(output_destination_index_),
+                                         merge ? query_context->comm() : nullptr),
         op_index_);
   }
   return true;
@@ -244,6 +270,7 @@ bool FinalizeAggregationOperator::getAllWorkOrders(WorkOrdersContainer *containe
 void FinalizeAggregationWorkOrder::execute() {
   qsgpu_relation_t out = nullptr;
   std::uint64_t mask = 0;
+  if (merge_comm_) QS_CHECK_GPU(qsgpu_agg_merge_all(state_, merge_comm_));
   QS_CHECK_GPU(qsgpu_agg_finalize(state_, &out, &mask));
   output_destination_->adopt(out);
   output_destination_->null_mask = mask;
@@ -274,9 +301,14 @@ bool DestroyHashOperator::getAllWorkOrders(WorkOrdersContainer *container, Query
 // ------------------------------------------------------------------- top-k
 bool SortMergeRunOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                             StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
+  // several devices, partitioned input: every device selects its own top k, the candidates are all-gathered and
+  // the final k are selected from them on every device (SortMergeRunOperator's last merge pass); the result is replicated
+  const bool gather = storage_manager->multiDevice() && storage_manager->isPartitioned(feed_.relation().getID());
+  storage_manager->setPartitioned(output_relation_.getID(), false);
   for (const DeviceExtent &e : feed_.take(storage_manager)) {
     container->addNormalWorkOrder(new TopKWorkOrder(query_id_, e, &query_context->getSortConfig(sort_config_index_), top_k_,
-                                                    query_context->getInsertDestination(output_destination_index_)),
+                                                    query_context->getInsertDestination(output_destination_index_),
+                                                    gather ? query_context->comm() : nullptr),
                                   op_index_);
   }
   return feed_.exhausted(done_feeding_input_relation_);
@@ -285,6 +317,14 @@ bool SortMergeRunOperator::getAllWorkOrders(WorkOrdersContainer *container, Quer
 void TopKWorkOrder::execute() {
   qsgpu_relation_t out = nullptr;
   QS_CHECK_GPU(qsgpu_topk(input_.relation, static_cast<std::uint32_t>(config_->keys.size()), config_->keys.data(), top_k_, &out));
+  if (gather_comm_) {
+    qsgpu_relation_t all = nullptr, top = nullptr;
+    QS_CHECK_GPU(qsgpu_relation_allgather(out, gather_comm_, &all));
+    QS_CHECK_GPU(qsgpu_topk(all, static_cast<std::uint32_t>(config_->keys.size()), config_->keys.data(), top_k_, &top));
+    QS_CHECK_GPU(qsgpu_relation_destroy(all));
+    QS_CHECK_GPU(qsgpu_relation_destroy(out));
+    out = top;
+  }
   output_destination_->adopt(out);
 }
 

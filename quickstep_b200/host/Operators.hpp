@@ -365,13 +365,15 @@ class FinalizeAggregationOperator : public RelationalOperator {
 
 class FinalizeAggregationWorkOrder : public WorkOrder {
  public:
-  FinalizeAggregationWorkOrder(const std::size_t query_id, qsgpu_agg_state_t state, InsertDestination *output_destination)
-      : WorkOrder(query_id), state_(state), output_destination_(output_destination) {}
+  FinalizeAggregationWorkOrder(const std::size_t query_id, qsgpu_agg_state_t state, InsertDestination *output_destination,
+                               qsgpu_comm_t merge_comm = nullptr)
+      : WorkOrder(query_id), state_(state), output_destination_(output_destination), merge_comm_(merge_comm) {}
   void execute() override;      // FinalizeAggregationOperator.cpp:99 -> finalizeAggregate
 
  private:
   qsgpu_agg_state_t state_;
   InsertDestination *output_destination_;
+  qsgpu_comm_t merge_comm_;     // non-null: merge the per-device partial states first (qsgpu_agg_merge_all)
 };
 
 class DestroyAggregationStateOperator : public RelationalOperator {
@@ -444,8 +446,9 @@ class SortMergeRunOperator : public RelationalOperator {
 class TopKWorkOrder : public WorkOrder {
  public:
   TopKWorkOrder(const std::size_t query_id, const DeviceExtent &input, const QueryContext::SortConfig *config,
-                std::size_t top_k, InsertDestination *output_destination)
-      : WorkOrder(query_id), input_(input), config_(config), top_k_(top_k), output_destination_(output_destination) {}
+                std::size_t top_k, InsertDestination *output_destination, qsgpu_comm_t gather_comm = nullptr)
+      : WorkOrder(query_id), input_(input), config_(config), top_k_(top_k), output_destination_(output_destination),
+        gather_comm_(gather_comm) {}
   void execute() override;
 
  private:
@@ -453,6 +456,7 @@ class TopKWorkOrder : public WorkOrder {
   const QueryContext::SortConfig *config_;
   const std::size_t top_k_;
   InsertDestination *output_destination_;
+  qsgpu_comm_t gather_comm_;    // non-null: all-gather every device's candidates and select again
 };
 
 }  // namespace quickstep

@@ -69,6 +69,11 @@ class QueryContext {
     std::uint32_t strategy = QS_AGG_SINGLE_STATE;
     std::uint64_t estimated_num_entries = 1024;
     std::int64_t collision_free_max_key = -1;
+    // Several devices: the input is partitioned on (a prefix of) the group-by attributes, so no group spans two
+    // devices and every device finalizes its own groups -- what the reference does per partition when
+    // `is_partitioned_on_group_by` holds (query_optimizer/ExecutionGenerator.cpp, aggregation state per partition).
+    // false: the per-device partial states are merged (qsgpu_agg_merge_all) before FinalizeAggregation.
+    bool partitioned_on_group_by = false;
   };
   // utility/lip_filter/LIPFilterDeployment.hpp: which filters an operator builds or probes, on which attribute
   // (LIPFilter.proto:50-62: a deployment carries build entries and probe entries)
@@ -79,6 +84,17 @@ class QueryContext {
   struct SortConfig { std::vector<qs_sort_key> keys; };
 
   QueryContext(StorageManager *sm, int device) : sm_(sm), device_(device) {}
+  qsgpu_comm_t comm() const { return sm_->communicator(); }
+  // ---- several devices: which per-device objects still hold only this device's share
+  // A LIP filter filled from a partitioned input is all-reduced (bitwise OR over the devices) the first time
+  // an operator asks for it as a probe filter; one filled from a replicated input is complete everywhere.
+  void noteLIPFiltersBuiltFrom(lip_deployment_id id, bool input_partitioned) {
+    const LIPDeployment *d = getLIPDeployment(id);
+    if (!d) return;
+    for (const LIPEntry &e : d->build_entries) lip_partial_[e.filter] = input_partitioned && sm_->multiDevice();
+  }
+  void noteAggregationInput(aggregation_state_id id, bool input_partitioned) { agg_partial_[id] = input_partitioned && sm_->multiDevice(); }
+  bool aggregationIsPartial(aggregation_state_id id) const { return agg_partial_[id]; }
   ~QueryContext() {
     for (auto h : agg_states_) if (h) qsgpu_agg_destroy(h);
     for (auto h : join_tables_) if (h) qsgpu_join_destroy(h);
@@ -92,6 +108,7 @@ class QueryContext {
   aggregation_state_id addAggregationState(AggregationSpec spec) {
     agg_specs_.push_back(std::move(spec));
     agg_states_.push_back(nullptr);
+    agg_partial_.push_back(false);
     const AggregationSpec &s = agg_specs_.back();
     const qs_expr_set es = s.exprs.view();
     qs_agg_spec c{};
@@ -113,6 +130,7 @@ class QueryContext {
     qsgpu_lip_t f = nullptr;
     QS_CHECK_GPU(qsgpu_lip_create(device_, kind, attr_type, min_value, max_value, cardinality, is_anti ? 1 : 0, &f));
     lip_filters_.push_back(f);
+    lip_partial_.push_back(false);
     return static_cast<lip_filter_id>(lip_filters_.size()) - 1;
   }
   lip_deployment_id addLIPDeployment(LIPDeployment d) { lip_deployments_.push_back(std::move(d)); return static_cast<lip_deployment_id>(lip_deployments_.size()) - 1; }
@@ -142,11 +160,18 @@ class QueryContext {
   const SortConfig &getSortConfig(sort_config_id id) const { return sort_configs_[id]; }
 
   // LIPFilterUtil: the C-ABI references of a deployment (filter handle + attribute)
-  std::vector<qs_lip_ref> lipRefs(lip_deployment_id id, LIPAction action) const {
+  // (Foreman thread only: called from getAllWorkOrders.)
+  std::vector<qs_lip_ref> lipRefs(lip_deployment_id id, LIPAction action) {
     std::vector<qs_lip_ref> refs;
     const LIPDeployment *d = getLIPDeployment(id);
     if (d)
-      for (const LIPEntry &e : (action == LIPAction::kBuild ? d->build_entries : d->probe_entries)) { qs_lip_ref r{}; r.lip = lip_filters_[e.filter]; r.attr = static_cast<std::uint32_t>(e.attr); refs.push_back(r); }
+      for (const LIPEntry &e : (action == LIPAction::kBuild ? d->build_entries : d->probe_entries)) {
+        if (action == LIPAction::kProbe && lip_partial_[e.filter]) {
+          QS_CHECK_GPU(qsgpu_lip_allreduce(lip_filters_[e.filter], sm_->communicator()));
+          lip_partial_[e.filter] = false;
+        }
+        qs_lip_ref r{}; r.lip = lip_filters_[e.filter]; r.attr = static_cast<std::uint32_t>(e.attr); refs.push_back(r);
+      }
     return refs;
   }
 
@@ -159,6 +184,7 @@ class QueryContext {
   std::vector<qsgpu_agg_state_t> agg_states_;
   std::vector<qsgpu_join_table_t> join_tables_;
   std::vector<qsgpu_lip_t> lip_filters_;
+  std::vector<bool> lip_partial_, agg_partial_;
   std::vector<LIPDeployment> lip_deployments_;
   std::vector<std::unique_ptr<InsertDestination>> destinations_;
   std::vector<SortConfig> sort_configs_;

@@ -127,6 +127,7 @@ void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, co
 }  // namespace
 
 StorageManager::~StorageManager() {
+  for (auto &kv : replicas_) if (kv.second) qsgpu_relation_destroy(kv.second);
   for (auto &kv : resident_) if (kv.second.handle) qsgpu_relation_destroy(kv.second.handle);
   for (auto &kv : temporaries_) if (kv.second) qsgpu_relation_destroy(kv.second);
   for (auto &kv : slabs_) for (Slab &s : kv.second) if (s.base) { if (pinned_) qsgpu_host_free(s.base); else std::free(s.base); }
@@ -430,8 +431,37 @@ qsgpu_relation_t StorageManager::temporary(const CatalogRelation &rel) {
   return it->second;
 }
 
+void StorageManager::setPartitioned(relation_id id, bool partitioned) {
+  std::lock_guard<std::mutex> lk(mu_);
+  partitioned_[id] = partitioned;
+}
+
+bool StorageManager::isPartitioned(relation_id id) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = partitioned_.find(id);
+  return it != partitioned_.end() && it->second;
+}
+
+qsgpu_relation_t StorageManager::replicated(const CatalogRelation &rel) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = replicas_.find(rel.getID());
+  if (it != replicas_.end()) return it->second;
+  auto t = temporaries_.find(rel.getID());
+  QS_CHECK(t != temporaries_.end());
+  qsgpu_relation_t all = nullptr;
+  QS_CHECK_GPU(qsgpu_relation_allgather(t->second, comm_, &all));
+  replicas_[rel.getID()] = all;
+  return all;
+}
+
 void StorageManager::dropTemporary(const CatalogRelation &rel) {
   std::lock_guard<std::mutex> lk(mu_);
+  partitioned_.erase(rel.getID());
+  auto rp = replicas_.find(rel.getID());
+  if (rp != replicas_.end()) {
+    if (rp->second) QS_CHECK_GPU(qsgpu_relation_destroy(rp->second));
+    replicas_.erase(rp);
+  }
   auto it = temporaries_.find(rel.getID());
   if (it == temporaries_.end()) return;
   if (it->second) QS_CHECK_GPU(qsgpu_relation_destroy(it->second));

@@ -83,6 +83,21 @@ class StorageManager {
   // (code width, dictionary entries) the image of `rel` uses for attribute `attr`; (0, 0) = native
   std::pair<std::uint32_t, std::uint32_t> residentCoding(const CatalogRelation &rel, std::uint32_t attr);
 
+  // ---- several devices (one process per GPU; partition id <-> device id) ----------
+  // The reference keeps one block list per partition of a relation (catalog/PartitionScheme.hpp) and one
+  // state / hash table per partition (query_execution/QueryContext.cpp:66-97).  Here every process holds ONE
+  // partition of each partitioned relation; a relation is either PARTITIONED across the devices (base
+  // relations loaded while a communicator is set, and whatever is derived from them row by row) or
+  // REPLICATED (the same rows on every device: merged aggregation results, all-gathered build sides).
+  void setCommunicator(qsgpu_comm_t comm) { comm_ = comm; }
+  qsgpu_comm_t communicator() const { return comm_; }
+  bool multiDevice() const { int r = 0, n = 1; qsgpu_comm_rank(comm_, &r, &n); return n > 1; }
+  void setPartitioned(relation_id id, bool partitioned);
+  bool isPartitioned(relation_id id) const;
+  // All-gathered copy of a partitioned temporary relation (the broadcast build side of a hash join); built on
+  // first use, owned by the manager, dropped together with the temporary.
+  qsgpu_relation_t replicated(const CatalogRelation &rel);
+
   // Device-only temporary relation (output of Select / HashJoin / Finalize);
   // its single pseudo block id stands for "every row produced so far".
   block_id createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows);
@@ -113,6 +128,9 @@ class StorageManager {
   std::map<relation_id, std::vector<Slab>> slabs_;
   std::map<relation_id, Resident> resident_;
   std::map<relation_id, qsgpu_relation_t> temporaries_;
+  std::map<relation_id, qsgpu_relation_t> replicas_;
+  std::map<relation_id, bool> partitioned_;
+  qsgpu_comm_t comm_ = nullptr;
   std::map<relation_id, block_id> temporary_block_;
 };
 

@@ -49,7 +49,9 @@ struct qshost_db {
   std::unique_ptr<StorageManager> sm;
   std::unique_ptr<WorkerPool> workers;
   std::unique_ptr<CatalogRelation> rel[3];
-  std::uint64_t rows[3] = {0, 0, 0};
+  std::uint64_t rows[3] = {0, 0, 0};          // this rank's rows
+  std::uint64_t global_rows[3] = {0, 0, 0};   // rows of the whole relation (== rows[] on one device)
+  qsgpu_comm_t comm = nullptr;
   // what \analyze records and AttachLIPFilters / InjectJoinFilters read (exact min/max statistics)
   std::int64_t c_custkey_min = 0, c_custkey_max = 0, o_orderkey_min = 0, o_orderkey_max = 0;
   std::string last_profile;
@@ -115,6 +117,12 @@ int qshost_db_destroy(qshost_db_t db) {
   return 0;
 }
 
+int qshost_db_set_comm(qshost_db_t db, void *comm) {
+  db->comm = static_cast<qsgpu_comm_t>(comm);
+  db->sm->setCommunicator(db->comm);
+  return 0;
+}
+
 int qshost_set_rows_per_workorder(uint64_t rows) { FLAGS_gpu_rows_per_workorder = rows; return 0; }
 
 int qshost_db_load(qshost_db_t db, int which, const void *const *columns, uint64_t n_rows, uint64_t rows_per_block,
@@ -134,6 +142,21 @@ int qshost_db_load(qshost_db_t db, int which, const void *const *columns, uint64
   };
   if (which == QSHOST_CUSTOMER) minmax(columns[C_CUSTKEY], &db->c_custkey_min, &db->c_custkey_max);
   if (which == QSHOST_ORDERS) minmax(columns[O_ORDERKEY], &db->o_orderkey_min, &db->o_orderkey_max);
+  db->global_rows[which] = n_rows;
+  if (db->sm->multiDevice()) {
+    // this rank loaded its partition: \analyze's statistics are those of the whole relation
+    db->sm->setPartitioned(db->rel[which]->getID(), true);
+    std::int64_t total = static_cast<std::int64_t>(n_rows);
+    QS_CHECK_GPU(qsgpu_comm_allreduce_i64(db->comm, &total, 1, 0));
+    db->global_rows[which] = static_cast<std::uint64_t>(total);
+    if (which != QSHOST_LINEITEM) {
+      std::int64_t *mn = which == QSHOST_CUSTOMER ? &db->c_custkey_min : &db->o_orderkey_min;
+      std::int64_t *mx = which == QSHOST_CUSTOMER ? &db->c_custkey_max : &db->o_orderkey_max;
+      if (n_rows == 0) { *mn = INT64_MAX; *mx = INT64_MIN; }
+      QS_CHECK_GPU(qsgpu_comm_allreduce_i64(db->comm, mn, 1, 1));
+      QS_CHECK_GPU(qsgpu_comm_allreduce_i64(db->comm, mx, 1, 2));
+    }
+  }
   return 0;
 }
 
@@ -341,7 +364,8 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   const auto dst2 = ctx.addInsertDestination(t2, n_orders), dst0 = ctx.addInsertDestination(t0, n_lineitem),
              dst4 = ctx.addInsertDestination(t4, n_lineitem), dst7 = ctx.addInsertDestination(t7, 1),
              dst9 = ctx.addInsertDestination(t9, 10);
-  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, n_orders / 4));
+  // the build side is replicated on every device (broadcast join): sized for the whole relation
+  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, db->global_rows[QSHOST_ORDERS] / 4));
 
   QueryContext::ScalarGroup s4;     // l_orderkey, o_orderdate, o_shippriority, l_extendedprice, l_discount
   s4.roots = {s4.exprs.attr(0, kInt), s4.exprs.attr(1, kDate, 2), s4.exprs.attr(2, kInt, 2), s4.exprs.attr(1, kDouble),
@@ -354,6 +378,9 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
     spec.aggregates.push_back({QS_AGG_SUM, e.binary(QS_MUL, e.attr(3, kDouble), e.binary(QS_SUB, e.lit_int(1), e.attr(4, kDouble)))});
     spec.group_by_roots = {e.attr(0, kInt), e.attr(1, kDate), e.attr(2, kInt)};
     spec.strategy = QS_AGG_SEPARATE_CHAINING;
+    // lineitem is partitioned on l_orderkey boundaries (it is sorted on it, benchmarks/tpch/create.sql:112):
+    // no group spans two devices
+    spec.partitioned_on_group_by = true;
     // the optimizer's group estimate (StarSchemaSimpleCostModel::estimateNumGroupsForAggregate): ~ #orders / 8
     spec.estimated_num_entries = std::max<std::uint64_t>(1u << 16, n_orders / 8);
   }

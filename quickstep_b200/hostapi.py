@@ -30,6 +30,7 @@ _VP, _U64P = C.c_void_p, C.POINTER(C.c_uint64)
 SIGNATURES = {
     "qshost_db_create": [C.c_int, C.c_int, C.POINTER(_VP)],
     "qshost_db_destroy": [_VP],
+    "qshost_db_set_comm": [_VP, _VP],
     "qshost_db_load": [_VP, C.c_int, C.POINTER(_VP), C.c_uint64, C.c_uint64, C.c_int],
     "qshost_db_evict": [_VP, C.c_int],
     "qshost_db_stats": [_VP, C.c_int, _U64P, _U64P, _U64P],
@@ -75,6 +76,10 @@ class Database:
 
     def load_table(self, which, table, rows_per_block=0, layout=BASIC_COLUMN_STORE):
         self.load(which, [c.data for c in table.columns], rows_per_block, layout)
+
+    def set_comm(self, comm):
+        """comm: a qsgpu_comm_t (engine.Comm.h); relations loaded afterwards are this rank's partitions."""
+        A.check(load().qshost_db_set_comm(self.h, comm))
 
     def evict(self, which):
         A.check(load().qshost_db_evict(self.h, which))

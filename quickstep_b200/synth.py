@@ -165,3 +165,119 @@ def host_table(cols: dict, schema, n: int | None = None):
             a = a.reshape(a.shape[0], -1).view(f"S{w}").reshape(-1)
         out.append(Column(name, t, a, w))
     return HostTable(schema[0][0].split("_")[0], out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ONE database, cut into chunks any rank can regenerate (bench.py at SF100, 1 / 2 / 4 / 8 GPUs).
+#
+# The database of `n_lineitem` rows is a fixed sequence of N chunks; chunk c holds orders [o_lo, o_hi), the lineitem
+# rows of exactly those orders, and customers [c_lo, c_hi), all drawn from a generator seeded with (seed, c).  The
+# content of the database therefore does not depend on how many ranks there are: rank r of `world` owns the chunks
+# [r*N/world, (r+1)*N/world) -- lineitem block-partitioned on l_orderkey boundaries (it is sorted on it,
+# benchmarks/tpch/create.sql:112), orders and customer in matching shares -- and rank 0 can regenerate every chunk
+# for the CPU oracle.  Same value domains and correlations as generate() above.
+
+def db_shape(n_lineitem: int, n_chunks: int | None = None):
+    n_orders = max(8, n_lineitem // 4)
+    n_cust = max(3, n_orders // 10)
+    if n_chunks is None:
+        n_chunks = 256 if n_orders >= 256 * 4096 else 8
+    return dict(n_lineitem=n_lineitem, n_orders=n_orders, n_cust=n_cust, n_chunks=n_chunks)
+
+
+def _cut(total: int, n: int, i: int) -> int:
+    return (i * total) // n
+
+
+def rank_chunks(shape, world: int, rank: int):
+    n = shape["n_chunks"]
+    return range(_cut(n, world, rank), _cut(n, world, rank + 1))
+
+
+def chunk_rows(shape, c: int):
+    """-> ((o_lo, o_hi), (l_lo, l_hi), (c_lo, c_hi)) global row ranges of chunk c."""
+    n = shape["n_chunks"]
+    return ((_cut(shape["n_orders"], n, c), _cut(shape["n_orders"], n, c + 1)),
+            (_cut(shape["n_lineitem"], n, c), _cut(shape["n_lineitem"], n, c + 1)),
+            (_cut(shape["n_cust"], n, c), _cut(shape["n_cust"], n, c + 1)))
+
+
+def generate_chunk(shape, c: int, seed: int, device):
+    """-> dict of device tensors: the orders, lineitem and customer rows of chunk c."""
+    (o_lo, o_hi), (l_lo, l_hi), (c_lo, c_hi) = chunk_rows(shape, c)
+    n_o, n_l, n_c, n_cust = o_hi - o_lo, l_hi - l_lo, c_hi - c_lo, shape["n_cust"]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1_000_003 + c)
+    ri = lambda lo, hi, n: torch.randint(lo, hi, (n,), generator=g, device=device, dtype=torch.int64)
+    out = {}
+    dense = torch.arange(o_lo, o_hi, device=device, dtype=torch.int64)
+    out["o_orderkey"] = ((((dense >> 3) << 5) | (dense & 7)) + 1).to(torch.int32)
+    ck = ri(0, max(1, (n_cust * 2) // 3), n_o)
+    out["o_custkey"] = (ck + torch.div(ck, 2, rounding_mode="floor") + 1).clamp_(max=n_cust).to(torch.int32)
+    o_days = _EPOCH_1992 + ri(0, 2406, n_o)
+    out["o_orderdate"] = datelit_from_days(o_days)
+    out["o_shippriority"] = torch.zeros(n_o, device=device, dtype=torch.int32)
+    oidx, _ = torch.sort(ri(0, max(1, n_o), n_l))
+    out["l_orderkey"] = out["o_orderkey"][oidx].contiguous() if n_o else torch.zeros(0, device=device, dtype=torch.int32)
+    ship = (o_days[oidx] if n_o else torch.zeros(0, device=device, dtype=torch.int64)) + ri(1, 122, n_l)
+    out["l_shipdate"] = datelit_from_days(ship)
+    receipt = ship + ri(1, 31, n_l)
+    qty = ri(1, 51, n_l)
+    out["l_quantity"] = qty.to(torch.float64)
+    out["l_extendedprice"] = (ri(90000, 210001, n_l) * qty).to(torch.float64) / 100.0
+    out["l_discount"] = ri(0, 11, n_l).to(torch.float64) / 100.0
+    out["l_tax"] = ri(0, 9, n_l).to(torch.float64) / 100.0
+    ra = torch.where(ri(0, 2, n_l) == 0, ord("R"), ord("A"))
+    out["l_returnflag"] = torch.where(receipt <= _CUTOFF, ra, torch.full_like(ra, ord("N"))).to(torch.uint8)
+    out["l_linestatus"] = torch.where(ship > _CUTOFF, ord("O"), ord("F")).to(torch.uint8)
+    out["c_custkey"] = torch.arange(c_lo + 1, c_hi + 1, device=device, dtype=torch.int32)
+    seg = torch.tensor([list(s.ljust(10, b"\0")) for s in SEGMENTS], dtype=torch.uint8, device=device)
+    out["c_mktsegment"] = seg[ri(0, 5, n_c)].contiguous()
+    return out
+
+
+def generate_host(shape, chunks, seed: int, device):
+    """The rows of `chunks` (a contiguous range) as HOST numpy columns in Quickstep's native layouts:
+    -> {"customer": [arrays in schema order], "orders": [...], "lineitem": [...]}.  Generated chunk by chunk on the
+    device (torch) and copied straight into preallocated host arrays."""
+    import numpy as np
+    from .table import DATE_DTYPE
+    chunks = list(chunks)
+    first, last = (chunks[0], chunks[-1]) if chunks else (0, -1)
+    (o0, _), (l0, _), (c0, _) = chunk_rows(shape, first) if chunks else ((0, 0), (0, 0), (0, 0))
+    (_, o1), (_, l1), (_, c1) = chunk_rows(shape, last) if chunks else ((0, 0), (0, 0), (0, 0))
+    n = {"customer": c1 - c0, "orders": o1 - o0, "lineitem": l1 - l0}
+    base = {"customer": c0, "orders": o0, "lineitem": l0}
+    np_raw = {A.QS_INT: np.int32, A.QS_DOUBLE: np.float64, A.QS_DATE: np.int64}
+    host = {}
+    for rel, schema in (("customer", T.CUSTOMER), ("orders", T.ORDERS), ("lineitem", T.LINEITEM)):
+        for (name, t, w) in schema:
+            host[name] = np.empty((n[rel], w), dtype=np.uint8) if t == A.QS_CHAR else np.empty(n[rel], dtype=np_raw[t])
+    for c in chunks:
+        cols = generate_chunk(shape, c, seed, device)
+        rows = dict(zip(("orders", "lineitem", "customer"), chunk_rows(shape, c)))
+        for rel, schema in (("customer", T.CUSTOMER), ("orders", T.ORDERS), ("lineitem", T.LINEITEM)):
+            lo, hi = rows[rel][0] - base[rel], rows[rel][1] - base[rel]
+            for (name, _t, w) in schema:
+                src = cols[name].reshape(hi - lo, -1) if host[name].ndim == 2 else cols[name]
+                torch.from_numpy(host[name][lo:hi]).copy_(src)
+        del cols
+    out = {}
+    for rel, schema in (("customer", T.CUSTOMER), ("orders", T.ORDERS), ("lineitem", T.LINEITEM)):
+        arrs = []
+        for (name, t, w) in schema:
+            a = host[name]
+            if t == A.QS_DATE:
+                a = a.view(DATE_DTYPE)
+            elif t == A.QS_CHAR:
+                a = a.view(f"S{w}").reshape(-1)
+            arrs.append(a)
+        out[rel] = arrs
+    return out
+
+
+def host_tables(host):
+    """generate_host() columns -> {"customer" | "orders" | "lineitem": HostTable} for the CPU oracle (no copy)."""
+    from .table import Column, HostTable
+    return {rel: HostTable(rel, [Column(nm, t, a, w) for (nm, t, w), a in zip(schema, host[rel])])
+            for rel, schema in (("customer", T.CUSTOMER), ("orders", T.ORDERS), ("lineitem", T.LINEITEM))}

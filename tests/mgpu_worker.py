@@ -1,0 +1,183 @@
+"""Worker of tests/test_multigpu_nccl.py: one process per GPU (torchrun), NCCL collectives inside the C ABI.
+
+Every check compares the merged result of the ranks with the CPU oracle over the union of the partitions:
+  * Q1 / Q6 / Q3 through the C++ operator layer (libqshost.so) with a communicator set: partial aggregation states
+    merged (qsgpu_agg_merge_all), LIP filter OR-reduced, filtered orders all-gathered (broadcast join), top-k gathered
+  * qsgpu_agg_merge_all on a SEPARATE_CHAINING and a COLLISION_FREE state (generic table path)
+  * qsgpu_lip_allreduce, small (all-gather + OR) and large (reduce-scatter form) filters
+  * qsgpu_relation_allgather
+  * the shuffled join of BASELINE.json configs[4] at a small size: K8 partition written straight into the peers
+    (qsgpu_partition_scatter_peers), local build + probe, output rows compared with the oracle join as a multiset
+Prints "MGPU OK" on rank 0 when everything passed."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench as B
+from quickstep_b200 import capi as A
+from quickstep_b200 import engine as E
+from quickstep_b200 import hostapi as H
+from quickstep_b200 import synth as S
+from quickstep_b200.expr import ExprSet
+from quickstep_b200.table import Column, HostTable
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    E.init([local])
+    comm = E.Comm.from_torch_distributed(local)
+    import qs_oracle as O
+    import oracle_tpch as OT
+    import tpch_data as D
+    O.load(); O.set_workers(4)
+
+    # ---------------------------------------------------------------- whole queries through the operator layer
+    n = int(os.environ.get("MGPU_ROWS", "1500000"))
+    shape = S.db_shape(n)
+    full = S.generate_host(shape, range(shape["n_chunks"]), 77, dev)
+    mine = S.generate_host(shape, S.rank_chunks(shape, world, rank), 77, dev)
+    tables = S.host_tables(full)
+    db = H.Database(local, num_workers=3)
+    db.set_comm(comm.h)
+    for which, rel in ((H.CUSTOMER, "customer"), (H.ORDERS, "orders"), (H.LINEITEM, "lineitem")):
+        db.load(which, mine[rel], 20_000, H.COMPRESSED_COLUMN_STORE)
+    for coded in (False, True):
+        db.set_code_resident(coded)
+        for _ in range(2):          # twice: the second run reuses every cached object
+            B.check_q1(db.q1()[0], OT.q1(tables["lineitem"]))
+            B.check_q6(db.q6()[:2], OT.q6(tables["lineitem"]))
+            B.check_q3(db.q3()[0], OT.q3(tables, D.q3_stats(tables)))
+    db.destroy()
+
+    # ---------------------------------------------------------------- qsgpu_agg_merge_all, table strategies
+    li_full, li_mine = tables["lineitem"], S.host_tables(mine)["lineitem"]
+    rel = E.Relation.from_host(li_mine, dev=local)
+    from quickstep_b200 import tpch as T
+    for strategy, key_attr, max_key in ((A.QS_AGG_SEPARATE_CHAINING, "l_shipdate", -1), (A.QS_AGG_COLLISION_FREE, "l_orderkey", None)):
+        es = ExprSet()
+        a = lambda nm: T._attr(es, T.LINEITEM, nm)
+        aggs = [(A.QS_AGG_SUM, a("l_quantity")), (A.QS_AGG_COUNT, -1), (A.QS_AGG_MIN, a("l_extendedprice"))]
+        if strategy == A.QS_AGG_COLLISION_FREE:
+            aggs = aggs[:2]
+            max_key = int(li_full.col("l_orderkey").data.max())
+        gb = [a(key_attr)]
+        st = E.AggState(strategy, es, -1, aggs, gb, estimated=4096, max_key=max_key if max_key is not None else -1, dev=local)
+        st.run(rel)
+        comm.merge_all(st)
+        t_i = T._idx(T.LINEITEM, key_attr)
+        out_types = [(A.QS_DOUBLE, 8), (A.QS_LONG, 8), (A.QS_DOUBLE, 8)][:len(aggs)]
+        fin, _ = E.finalize_relation(st, [(T.LINEITEM[t_i][1], T.LINEITEM[t_i][2])], out_types)
+        got_keys = fin.read(0)
+        got_vals = [fin.read(1 + j) for j in range(len(aggs))]
+        r = O.aggregate(es, -1, aggs, gb, li_full)
+        want_keys = r.keys[:, :got_keys.dtype.itemsize].copy().view(got_keys.dtype).reshape(-1)
+        go, wo = np.argsort(got_keys, kind="stable", order=None if got_keys.dtype.names is None else list(got_keys.dtype.names)), \
+            np.argsort(want_keys, kind="stable", order=None if want_keys.dtype.names is None else list(want_keys.dtype.names))
+        assert len(got_keys) == r.n_groups, (len(got_keys), r.n_groups)
+        assert (got_keys[go] == want_keys[wo]).all()
+        for j in range(len(aggs)):
+            g, w = np.asarray(got_vals[j])[go].astype(np.float64), np.asarray(r.values[j])[wo].astype(np.float64)
+            assert np.allclose(g, w, rtol=1e-9, atol=0), (strategy, j)
+        fin.destroy(); st.destroy()
+    rel.destroy()
+
+    # ---------------------------------------------------------------- qsgpu_lip_allreduce (both forms) + allgather
+    for bits in (100_000, 80_000_000):            # 12.5 KB -> all-gather + OR; 10 MB -> reduce-scatter form
+        keys = np.arange(rank, bits, world * 7, dtype=np.int64)          # every rank sets its own residue class
+        krel = E.Relation.from_host(HostTable("k", [Column("k", A.QS_LONG, keys)]), dev=local)
+        f = E.LipFilter(A.QS_LIP_BITVECTOR_EXACT, A.QS_LONG, 0, bits - 1, dev=local)
+        E.build_lip_filter(krel, None, -1, None, [(f, 0)])
+        comm.lip_allreduce(f)
+        words = f.words()
+        want = np.zeros((bits + 63) // 64, dtype=np.uint64)
+        for r_ in range(world):
+            k = np.arange(r_, bits, world * 7, dtype=np.int64)
+            np.bitwise_or.at(want, k >> 6, np.uint64(1) << (np.uint64(63) - (k & 63).astype(np.uint64)))
+        assert (words.view(np.uint64) == want).all(), bits
+        g = comm.allgather(krel)
+        allk = g.read(0)
+        assert (allk == np.concatenate([np.arange(r_, bits, world * 7, dtype=np.int64) for r_ in range(world)])).all()
+        g.destroy(); f.destroy(); krel.destroy()
+
+    # ---------------------------------------------------------------- shuffled join, row-level parity with the oracle
+    nb, npr = 40_000, 300_000
+    rng = np.random.default_rng(5)
+    bkeys_all = rng.integers(0, 30_000, size=nb * world).astype(np.int64)          # duplicates on the build side
+    bpay_all = np.arange(nb * world, dtype=np.int64) * 3 + 1
+    pkeys_all = rng.integers(0, 36_000, size=npr * world).astype(np.int64)          # ~17 % of the probe rows miss
+    pid_all = np.arange(npr * world, dtype=np.int64)
+    LONG = (A.QS_LONG, 8)
+    brel = E.Relation.from_host(HostTable("b", [Column("k", A.QS_LONG, bkeys_all[rank * nb:(rank + 1) * nb]),
+                                                 Column("p", A.QS_LONG, bpay_all[rank * nb:(rank + 1) * nb])]), dev=local)
+    prel = E.Relation.from_host(HostTable("p", [Column("k", A.QS_LONG, pkeys_all[rank * npr:(rank + 1) * npr]),
+                                                 Column("i", A.QS_LONG, pid_all[rank * npr:(rank + 1) * npr])]), dev=local)
+    cap_b, cap_p = nb * world, npr * world
+    mine_ipc = [E.ipc_alloc((cap_b + 64) * 8, local) for _ in range(2)] + [E.ipc_alloc((cap_p + 64) * 8, local) for _ in range(2)]
+    handles = [None] * world
+    dist.all_gather_object(handles, [h for (_p, h) in mine_ipc])
+    peer = [[(mine_ipc[c][0] if r_ == rank else E.ipc_open(handles[r_][c], local)) for c in range(4)] for r_ in range(world)]
+    cb, cp = E.partition_count(brel, 0, world), E.partition_count(prel, 0, world)
+    send = torch.tensor([[int(cb[i]), int(cp[i])] for i in range(world)], dtype=torch.int64, device=dev)
+    allc = torch.zeros(world, world, 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc.view(-1), send.view(-1))
+    allc = allc.cpu()
+    first_b = [int(allc[:rank, p, 0].sum()) for p in range(world)]
+    first_p = [int(allc[:rank, p, 1].sum()) for p in range(world)]
+    n_b, n_p = int(allc[:, rank, 0].sum()), int(allc[:, rank, 1].sum())
+    E.partition_scatter_peers(brel, 0, world, [peer[p][:2] for p in range(world)], first_b)
+    E.partition_scatter_peers(prel, 0, world, [peer[p][2:] for p in range(world)], first_p)
+    E.synchronize(local)
+    dist.barrier()
+    rb = E.Relation.wrap([LONG, LONG], [p for (p, _h) in mine_ipc[:2]], n_b, dev=local)
+    rp = E.Relation.wrap([LONG, LONG], [p for (p, _h) in mine_ipc[2:]], n_p, dev=local)
+    jt = E.JoinTable(A.QS_LONG, max(1024, n_b), dev=local)
+    jt.build(rb, None, -1, 0)
+    es = ExprSet()
+    proj = [es.attr(1, A.QS_LONG, 8), es.attr(0, A.QS_LONG, 8), es.attr(1, A.QS_LONG, 8, 2)]      # probe id, key, build payload
+    out = E.Relation.create([LONG, LONG, LONG], max(1, n_p * 4), dev=local)
+    jt.probe(rp, es, -1, 0, A.QS_JOIN_INNER, -1, proj, out)
+    rows = np.stack([out.read(0), out.read(1), out.read(2)], axis=1)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, rows)
+    if rank == 0:
+        got = np.concatenate(gathered)
+        bt = HostTable("b", [Column("k", A.QS_LONG, bkeys_all), Column("p", A.QS_LONG, bpay_all)])
+        pt = HostTable("p", [Column("k", A.QS_LONG, pkeys_all), Column("i", A.QS_LONG, pid_all)])
+        schema = [LONG, LONG, LONG]
+        oc = O.hash_join(es, bt, -1, 0, pt, -1, 0, None, A.QS_JOIN_INNER, -1, proj, schema, max(1, len(got) + 16))
+        want = np.stack([np.asarray(c) for c in oc], axis=1)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        gs = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))]
+        ws = want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
+        assert (gs == ws).all()
+    dist.barrier()
+    for o in (out, jt, rb, rp, brel, prel):
+        o.destroy()
+    for r_ in range(world):
+        if r_ != rank:
+            for p in peer[r_]:
+                E.ipc_close(p, local)
+    dist.barrier()
+    for (p, _h) in mine_ipc:
+        E.ipc_free(p, local)
+
+    comm.destroy()
+    dist.barrier()
+    if rank == 0:
+        print("MGPU OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

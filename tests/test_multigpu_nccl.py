@@ -1,0 +1,28 @@
+"""N > 1 on real GPUs: the cross-GPU merges of the C ABI (NCCL) and the multi-device operator layer, checked
+against the CPU oracle over the union of the partitions (tests/mgpu_worker.py).  Needs >= 2 GPUs in the box
+(`gpurun --gpus 2`); skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_merges_match_oracle(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29600 + (os.getpid() % 300) + world
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")],
+                       capture_output=True, text=True, timeout=850)
+    assert r.returncode == 0 and "MGPU OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
