@@ -198,6 +198,17 @@ int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n
                             void *const *host_out);
 
 /*
+ * A small RESULT relation in one round trip: up to max_rows rows of every attribute (host_out[a] has room for
+ * max_rows values), the relation's row count (*n_rows; may exceed max_rows, in which case only max_rows rows were
+ * copied) and, when null_masks != NULL, the rows' NULL masks -- packed by one kernel, moved by ONE device-to-host
+ * copy and waited for once.  Operators upstream only enqueue (the row count of a temporary relation lives on the
+ * device), so this is the single host wait of a query; an error a kernel raised on the way (QSGPU_ERR_CAPACITY)
+ * is reported here.  Limited to results of <= 256 KB; larger ones are read with qsgpu_relation_read.
+ */
+int qsgpu_relation_read_rows(qsgpu_relation_t rel, uint64_t max_rows, void *const *host_out, uint64_t *n_rows,
+                             uint64_t *null_masks);
+
+/*
  * K0 -- staging of one storage block's attribute into a device relation,
  * appended at the relation's current end.  Physical encodings of the
  * reference's sub-blocks:
@@ -401,7 +412,11 @@ int qsgpu_agg_existence_map(qsgpu_agg_state_t state, qsgpu_lip_t *out);
  * SUM(float/double)->DOUBLE, AVG->DOUBLE, COUNT->LONG, MIN/MAX->argument
  * type).  `*out` is created by the call.  For an aggregate over zero rows
  * (SQL NULL, AggregationHandleSum.cpp:134-143) the value is 0 and the
- * matching bit of *null_mask (bit j = aggregate j, SINGLE_STATE only) is set.
+ * matching bit of *null_mask (bit j = aggregate j, SINGLE_STATE only) is set; the same information is in the
+ * output relation's per-row NULL mask (qsgpu_relation_read_nulls / read_rows: bit = output column).
+ * With null_mask == NULL the call only enqueues for SINGLE_STATE / COMPACT_KEY states (the live group count is
+ * read on the device; the output's row count stays device-side until somebody asks), so a query's tail --
+ * finalize, the wrapping Select, the sort -- is queued while the scan kernel is still running.
  */
 int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out,
                        uint64_t *null_mask);

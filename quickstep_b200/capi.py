@@ -136,6 +136,7 @@ SIGNATURES = {
     "qsgpu_relation_dictionary": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _VP]),
     "qsgpu_relation_read_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
+    "qsgpu_relation_read_rows": (C.c_int, [_VP, C.c_uint64, _VPP, _U64P, _U64P]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
     "qsgpu_stage_blocks": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),
     "qsgpu_stage_columns": (C.c_int, [_VP, C.c_uint64, C.c_uint32, C.POINTER(qs_block_image), C.c_uint32]),

@@ -775,6 +775,49 @@ int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n
   return QSGPU_OK;
 }
 
+int qsgpu_relation_read_rows(qsgpu_relation_t rel, uint64_t max_rows, void *const *host_out, uint64_t *n_rows,
+                             uint64_t *null_masks) {
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (rel->has_codes() || rel->cols.size() > static_cast<size_t>(kMaxCols)) { set_error(QSGPU_ERR_UNSUPPORTED, "read_rows: result relations only (native columns, <= 12 attributes)"); return QSGPU_ERR_UNSUPPORTED; }
+  max_rows = std::min<uint64_t>(max_rows, rel->capacity);
+  size_t total = 16 + (null_masks ? ((max_rows * 8 + 15) & ~static_cast<size_t>(15)) : 0);
+  for (size_t a = 0; a < rel->cols.size(); ++a) total += (max_rows * rel->attrs[a].width + 15) & ~static_cast<size_t>(15);
+  if (total > kReadScratchBytes || !d->read_scratch) { set_error(QSGPU_ERR_CAPACITY, "read_rows: result larger than the 256 KB landing buffer; use qsgpu_relation_read"); return QSGPU_ERR_CAPACITY; }
+  ColDesc cols[kMaxCols];
+  for (size_t a = 0; a < rel->cols.size(); ++a) { cols[a] = ColDesc{}; cols[a].ptr = rel->cols[a]; cols[a].width = rel->attrs[a].width; }
+  std::lock_guard<std::mutex> lk(*d->read_mu);
+  // one pack launch, one transfer into pinned memory, one wait: row count, error word, NULL masks and rows together
+  QS_CUDA(launch_pack_rows(d->read_scratch, cols, static_cast<uint32_t>(rel->cols.size()), max_rows, rel->d_rows,
+                           null_masks ? rel->d_nulls : nullptr, d->d_error, d->stream));
+  count_launch();
+  QS_CUDA(cudaMemcpyAsync(d->read_pinned, d->read_scratch, total, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  uint64_t n = 0;
+  uint32_t flag = 0;
+  std::memcpy(&n, d->read_pinned, 8);
+  std::memcpy(&flag, d->read_pinned + 8, 4);
+  if (flag != 0) {
+    set_error(static_cast<int>(flag), "a kernel reported a capacity overflow (hash table, group limit or output relation too small)");
+    return static_cast<int>(flag);
+  }
+  rel->host_rows = std::min<uint64_t>(n, rel->capacity);
+  rel->dirty = false;
+  const uint64_t got = std::min<uint64_t>(rel->host_rows, max_rows);
+  size_t off = 16;
+  if (null_masks) {
+    if (rel->d_nulls) std::memcpy(null_masks, d->read_pinned + off, got * 8);
+    else std::memset(null_masks, 0, got * 8);
+    off += (max_rows * 8 + 15) & ~static_cast<size_t>(15);
+  }
+  for (size_t a = 0; a < rel->cols.size(); ++a) {
+    std::memcpy(host_out[a], d->read_pinned + off, got * rel->attrs[a].width);
+    off += (max_rows * rel->attrs[a].width + 15) & ~static_cast<size_t>(15);
+  }
+  *n_rows = rel->host_rows;
+  return QSGPU_OK;
+}
+
 int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc *descs, uint32_t n_desc) {
   int st = sync_rows(rel);
   if (st) return st;
@@ -1335,11 +1378,6 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   }
 
   if (t_sc) { *out = s.release(); return QSGPU_OK; }   // selfcheck: description only, no device memory
-  QS_CUDA(dev_malloc(&A.n_groups, 256));
-  QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 256, d->stream));
-  QS_CUDA(dev_malloc(&s->d_done, 256));
-  QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
-  QS_CUDA(dev_malloc(&s->d_idx_count, 256));
   if (strategy == QS_AGG_SINGLE_STATE || strategy == QS_AGG_COMPACT_KEY) {
     // one partial row set per CTA of the persistent grid: up to 4 resident CTAs per SM for states with a few
     // partial rows (Q6 on dictionary codes: 12 KB tiles, 32 registers), 2 for the 256-group compact-key states
@@ -1347,23 +1385,33 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     s->max_ctas = static_cast<uint32_t>(d->sm_count) * (A.partial_rows <= 8 ? 4u : 2u);
     const size_t prow = static_cast<size_t>(A.partial_rows) * A.words * 8;
     QS_CUDA(dev_malloc(&A.partials, prow * s->max_ctas));
-    // every partial row starts as (and is reset to, by k_merge_partials) the identity, so rows of
-    // groups a CTA never met contribute nothing to the fold
-    QS_CUDA(launch_fill_identity(A.partials, static_cast<uint64_t>(A.partial_rows) * s->max_ctas, A, d->stream));
-    count_launch();
+    // Everything else lives in ONE control block, brought to its initial contents by ONE launch (this call is on
+    // the critical path of the query: the scan cannot start before its state exists):
+    //   [n_groups 256 B][done ticket 256 B][index count 256 B][dir_keys][dir_gid][states | packed keys]
+    // The [states | packed keys] tail is contiguous on purpose: it is the send buffer of the cross-GPU merge
+    // (qsgpu_agg_merge_all all-gathers it as it lies, no packing pass).
     A.dir_cap = 1024;
-    QS_CUDA(dev_malloc(&A.dir_keys, A.dir_cap * 8));
-    QS_CUDA(dev_malloc(&A.dir_gid, A.dir_cap * 4));
-    QS_CUDA(cudaMemsetAsync(A.dir_gid, 0xff, A.dir_cap * 4, d->stream));
-    // [states: partial_rows x words | packed keys: partial_rows] in ONE block: it is the send buffer of the
-    // cross-GPU merge (qsgpu_agg_merge_all all-gathers it as it lies, no packing pass)
-    QS_CUDA(dev_malloc(&A.states, prow + static_cast<size_t>(A.partial_rows) * 8));
+    const size_t ctl_bytes = 768 + A.dir_cap * 8 + A.dir_cap * 4 + prow + static_cast<size_t>(A.partial_rows) * 8;
+    QS_CUDA(dev_malloc(&s->ctl, ctl_bytes));
+    char *p = s->ctl;
+    A.n_groups = reinterpret_cast<uint32_t *>(p); p += 256;
+    s->d_done = reinterpret_cast<unsigned int *>(p); p += 256;
+    s->d_idx_count = reinterpret_cast<unsigned long long *>(p); p += 256;
+    A.dir_keys = reinterpret_cast<uint64_t *>(p); p += A.dir_cap * 8;
+    A.dir_gid = reinterpret_cast<int *>(p); p += A.dir_cap * 4;
+    A.states = reinterpret_cast<uint64_t *>(p);
     A.gid_keys = A.states + static_cast<size_t>(A.partial_rows) * A.words;
-    QS_CUDA(cudaMemsetAsync(A.gid_keys, 0, static_cast<size_t>(A.partial_rows) * 8, d->stream));
     A.cap = A.partial_rows;
-    QS_CUDA(launch_fill_identity(A.states, A.partial_rows, A, d->stream));
+    // every partial row starts as (and is reset to, by k_merge_partials) the identity, so rows of groups a CTA
+    // never met contribute nothing to the fold
+    QS_CUDA(launch_agg_init(A, s->max_ctas, s->ctl, d->stream));
     count_launch();
   } else {
+    QS_CUDA(dev_malloc(&A.n_groups, 256));
+    QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 256, d->stream));
+    QS_CUDA(dev_malloc(&s->d_done, 256));
+    QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
+    QS_CUDA(dev_malloc(&s->d_idx_count, 256));
     if (strategy == QS_AGG_COLLISION_FREE) A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
     else {
       uint64_t want = std::max<uint64_t>(1024, spec->estimated_num_entries * 2);
@@ -1625,9 +1673,11 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   if (!d) return QSGPU_ERR_NO_DEVICE;
   AggDesc &A = state->A;
   const bool dense = state->strategy == QS_AGG_SINGLE_STATE || state->strategy == QS_AGG_COMPACT_KEY;
-  uint64_t n = 1;                     // a single state is one row; no need to ask the device
-  int st = state->strategy == QS_AGG_SINGLE_STATE ? QSGPU_OK
-           : dense ? agg_num_groups_locked(state, &n) : collect_groups(state, d, &n);
+  // Fixed-size states: the output relation is sized for the state's row limit and the kernel reads the live group
+  // count on the device, so the call only ENQUEUES (no host wait; a capacity error of the scan surfaces at the
+  // next read of the result).  Tables: the groups are collected first and their number sizes the output.
+  uint64_t n = dense ? A.partial_rows : 0;
+  int st = dense ? QSGPU_OK : collect_groups(state, d, &n);
   if (st) return st;
   // output schema: group-by attributes, then one column per aggregate
   std::vector<qs_attr> attrs = state->key_attrs;
@@ -1665,11 +1715,22 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   for (uint32_t j = 0; j < F.n_out; ++j) F.out[j] = rel->cols[A.n_key_cols + j];
   const uint64_t *keys = dense ? A.gid_keys : A.keys;
   F.rows_out = rel->d_rows;
+  F.d_n_groups = state->strategy == QS_AGG_COMPACT_KEY ? A.n_groups : nullptr;
+  if (state->strategy == QS_AGG_SINGLE_STATE) {
+    // aggregates over zero rows are SQL NULL: recorded in the output relation's per-row NULL mask
+    if (!rel->d_nulls) {
+      cudaError_t ne = dev_malloc(&rel->d_nulls, 8 * std::max<uint64_t>(rel->capacity, 1));
+      if (ne != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(ne, "finalize null mask"); }
+    }
+    F.null_out = rel->d_nulls;
+    for (size_t j = 0; j < state->aggregates.size(); ++j)
+      if (state->aggregates[j].function != QS_AGG_COUNT) F.null_bits |= 1ull << (A.n_key_cols + j);
+  }
   KernelTimer timer(d, QS_K_GROUPBY);
   cudaError_t e = launch_finalize(A.states, keys, A.words, dense ? nullptr : state->d_idx, n, F, d->stream);
   count_launch();
   if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "finalize"); }
-  if (null_mask) {
+  if (null_mask) {                    // asked for on the host: this (and only this) waits for the queued work
     *null_mask = 0;
     if (state->strategy == QS_AGG_SINGLE_STATE) {
       uint64_t count = 0;
@@ -1680,8 +1741,12 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
           if (state->aggregates[j].function != QS_AGG_COUNT) *null_mask |= 1ull << j;
     }
   }
-  rel->host_rows = n;                 // the kernel stored n in the relation's device counter
-  rel->dirty = false;
+  if (state->strategy == QS_AGG_COMPACT_KEY) {
+    rel->dirty = true;                // the kernel stored the live group count in the relation's device counter
+  } else {
+    rel->host_rows = n;
+    rel->dirty = false;
+  }
   *out = rel;
   return QSGPU_OK;
 }
@@ -1703,9 +1768,13 @@ int qsgpu_agg_destroy(qsgpu_agg_state_t s) {
   if (s->existence) qsgpu_lip_destroy(s->existence);
   device(s->dev);
   AggDesc &A = s->A;
-  dev_free(A.partials); dev_free(A.dir_keys); dev_free(A.dir_gid); dev_free(A.n_groups);   // gid_keys lives inside the states block
-  dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
-  dev_free(s->d_done); dev_free(s->d_idx); dev_free(s->d_idx_count); dev_free(s->d_exp_states); dev_free(s->d_exp_keys);
+  if (s->ctl) {             // fixed-size strategies: counters, key directory, states and keys are one block
+    dev_free(A.partials); dev_free(s->ctl);
+  } else {
+    dev_free(A.n_groups); dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
+    dev_free(s->d_done); dev_free(s->d_idx_count);
+  }
+  dev_free(s->d_idx); dev_free(s->d_exp_states); dev_free(s->d_exp_keys);
   delete s;
   return QSGPU_OK;
 }
@@ -1721,14 +1790,47 @@ int qsgpu_join_create(int dev, uint32_t key_type, uint64_t estimated_num_entries
   uint64_t cap = 1024;
   while (cap < estimated_num_entries * 2) cap <<= 1;
   t->J.cap = cap;
+  t->alloc_cap = cap;
   t->J.error_flag = d->d_error;
   t->J.key_ltype = key_type == QS_INT ? V_I32 : V_I64;
   QS_CUDA(dev_malloc(&t->J.slots, cap * sizeof(JoinSlot)));
   QS_CUDA(dev_malloc(&t->J.n_entries, 256));
   QS_CUDA(cudaMemsetAsync(t->J.n_entries, 0, 256, d->stream));
-  QS_CUDA(launch_join_clear(t->J, d->stream));
-  count_launch();
+  // cleared (and its mask fixed) by the first build work order, see qsgpu_join_table
   *out = t.release();
+  return QSGPU_OK;
+}
+
+// Open addressing: make room for `rows` more entries before a build work order is queued (table->mu held).
+static int join_reserve(qsgpu_join_table *t, Device *d, uint64_t rows) {
+  if (t->J.dense) return QSGPU_OK;
+  uint64_t need = 1024;
+  while (need < (t->upper_entries + rows) * 2) need <<= 1;
+  if (!t->cleared) {
+    if (t->cap_frozen) need = std::max(need, t->J.cap);
+    if (need > t->alloc_cap) {
+      dev_free(t->J.slots);
+      t->J.slots = nullptr;
+      QS_CUDA(dev_malloc(&t->J.slots, need * sizeof(JoinSlot)));
+      t->alloc_cap = need;
+    }
+    t->J.cap = need;
+    QS_CUDA(launch_join_clear(t->J, d->stream));
+    count_launch();
+    t->cleared = true;
+  } else if (need > t->J.cap) {
+    JoinDesc B = t->J;
+    B.cap = need;
+    B.slots = nullptr;
+    QS_CUDA(dev_malloc(&B.slots, need * sizeof(JoinSlot)));
+    QS_CUDA(launch_join_clear(B, d->stream));
+    QS_CUDA(launch_join_rehash(t->J.slots, t->J.cap, B.slots, B.cap, d->stream));
+    count_launch(2);
+    dev_free(t->J.slots);            // stream-ordered: freed after the re-hash ran
+    t->J = B;
+    t->alloc_cap = need;
+  }
+  t->upper_entries += rows;
   return QSGPU_OK;
 }
 
@@ -1788,11 +1890,21 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
   }
   const uint32_t key_attr = key_attrs[0];
   if (n_keys == 1 && rel->attrs[key_attr].type != table->key_type) { set_error(QSGPU_ERR_INVALID, "build key attribute does not match the table"); return QSGPU_ERR_INVALID; }
+  // build work orders of one operator run concurrently: sizing (which may re-hash into a new slot array) and the
+  // launch that uses the array are one unit in stream order
+  std::lock_guard<std::mutex> lk(table->mu);
   {
-    std::lock_guard<std::mutex> lk(table->mu);      // build work orders of one operator run concurrently
     if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
     table->build_rel = rel;
     if (table->J.dense && !table->J.next && !t_sc) QS_CUDA(dev_malloc(&table->J.next, std::max<uint64_t>(rel->capacity, 1) * 8));
+    if (!table->J.dense && !t_sc) {
+      // the rows this work order can insert (the count of a temporary relation may still be device-side)
+      int rs = sync_rows(rel);
+      if (rs) return rs;
+      const uint64_t hi = std::min<uint64_t>(scan->row_end, rel->host_rows);
+      rs = join_reserve(table, d, hi > scan->row_begin ? hi - scan->row_begin : 0);
+      if (rs) return rs;
+    }
   }
   Lowering L(scan->exprs, rel);
   int st = lower_scan_predicate(L, scan);
@@ -1888,6 +2000,10 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
       QS_CUDA(cudaMemsetAsync(output->d_nulls, 0, std::max<uint64_t>(output->capacity, 1) * 8, d->stream));
     }
     K.null_out = output->d_nulls;
+  }
+  if (!t_sc) {     // probing a table no build work order ever touched (empty build side): give it its (empty) slots
+    std::lock_guard<std::mutex> lk(table->mu);
+    if (!table->J.dense && !table->cleared) { const int rs = join_reserve(table, d, 0); if (rs) return rs; }
   }
   JoinDesc J = table->J;
   J.join_type = static_cast<uint8_t>(join_type);

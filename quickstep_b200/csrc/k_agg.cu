@@ -14,6 +14,8 @@
 // in a fixed order (lane-strided over CTAs, then a lane-ordered shuffle tree),
 // so a run is reproducible bit for bit -- the reference's own result depends on
 // work-order completion order.
+#include <algorithm>
+
 #include "qs_jit.h"
 #include "qs_kernels.cuh"
 
@@ -70,7 +72,70 @@ __global__ void k_merge_foreign_compact(const __grid_constant__ AggDesc A, const
   }
 }
 
+// Initial contents of a fresh fixed-size state in ONE launch (qsgpu_agg_create is on the critical path of every
+// query: the scan cannot start before its state exists).
+__global__ void k_agg_init(const __grid_constant__ AggDesc A, uint64_t partial_sets, unsigned long long *ctl) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t t0 = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  const uint64_t n_partial = partial_sets * A.partial_rows * A.words;
+  for (uint64_t i = t0; i < n_partial; i += stride) {
+    const uint32_t w = static_cast<uint32_t>(i % A.words);
+    A.partials[i] = w == 0 ? 0 : agg_identity(A.kind[w - 1]);
+  }
+  const uint64_t n_states = static_cast<uint64_t>(A.partial_rows) * A.words;
+  for (uint64_t i = t0; i < n_states; i += stride) {
+    const uint32_t w = static_cast<uint32_t>(i % A.words);
+    A.states[i] = w == 0 ? 0 : agg_identity(A.kind[w - 1]);
+  }
+  for (uint64_t i = t0; i < A.partial_rows; i += stride) A.gid_keys[i] = 0;
+  for (uint64_t i = t0; i < A.dir_cap; i += stride) A.dir_gid[i] = -1;
+  for (uint64_t i = t0; i < 96; i += stride) ctl[i] = 0;          // 3 x 256 bytes of counters
+}
+
+struct PackDesc { ColDesc cols[kMaxCols]; };
+// dst: [u64 rows][u32 error, u32 0][nulls: max_rows x u64 when d_nulls][column 0: max_rows x w0, padded to 16]...
+__global__ void k_pack_rows(char *dst, const __grid_constant__ PackDesc P, uint32_t n_cols, uint64_t max_rows,
+                            const unsigned long long *d_rows, const unsigned long long *d_nulls, uint32_t *error_flag) {
+  const uint64_t n = min(static_cast<uint64_t>(*d_rows), max_rows);
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    *reinterpret_cast<uint64_t *>(dst) = *d_rows;
+    reinterpret_cast<uint32_t *>(dst)[2] = *error_flag;
+    reinterpret_cast<uint32_t *>(dst)[3] = 0;
+    *error_flag = 0;                                 // reported with this result
+  }
+  size_t off = 16;
+  const uint64_t t0 = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  if (d_nulls) {
+    for (uint64_t i = t0; i < n; i += stride) reinterpret_cast<unsigned long long *>(dst + off)[i] = d_nulls[i];
+    off += (max_rows * 8 + 15) & ~static_cast<size_t>(15);
+  }
+  for (uint32_t c = 0; c < n_cols; ++c) {
+    const uint64_t bytes = n * P.cols[c].width;
+    for (uint64_t i = t0; i < bytes; i += stride) dst[off + i] = P.cols[c].ptr[i];
+    off += (max_rows * P.cols[c].width + 15) & ~static_cast<size_t>(15);
+  }
+}
+
 // ------------------------------------------------------------------ launchers
+cudaError_t launch_agg_init(const AggDesc &A, uint64_t partial_sets, void *ctl, cudaStream_t st) {
+  const uint64_t n = std::max<uint64_t>(partial_sets * A.partial_rows * A.words, A.dir_cap);
+  int grid = static_cast<int>(std::min<uint64_t>((n + 255) / 256, 148 * 8));
+  k_agg_init<<<std::max(grid, 1), 256, 0, st>>>(A, partial_sets, static_cast<unsigned long long *>(ctl));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rows(char *dst, const ColDesc *cols, uint32_t n_cols, uint64_t max_rows,
+                             const unsigned long long *d_rows, const unsigned long long *d_nulls,
+                             uint32_t *error_flag, cudaStream_t st) {
+  PackDesc P{};
+  uint64_t bytes = 0;
+  for (uint32_t c = 0; c < n_cols; ++c) { P.cols[c] = cols[c]; bytes += max_rows * cols[c].width; }
+  const int grid = static_cast<int>(std::min<uint64_t>((bytes + 255) / 256, 148));
+  k_pack_rows<<<std::max(grid, 1), 256, 0, st>>>(dst, P, n_cols, max_rows, d_rows, d_nulls, error_flag);
+  return cudaGetLastError();
+}
+
 size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words, bool priv) {
   const size_t NA = n_agg > 0 ? n_agg : 1;
   const size_t LG = grouped ? kCompactMaxGroups : 1, LS = grouped ? kCompactLocalSlots : 0;

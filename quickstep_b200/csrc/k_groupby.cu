@@ -128,6 +128,7 @@ __global__ void k_gather_rows(const uint64_t *states, const uint64_t *keys, uint
 
 __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_t words, const uint64_t *idx,
                            uint64_t n, const __grid_constant__ FinalizeDesc F) {
+  if (F.d_n_groups) { const uint64_t live = *F.d_n_groups; if (live < n) n = live; }
   if (blockIdx.x == 0 && threadIdx.x == 0 && F.rows_out) *F.rows_out = n;
   for (uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; g < n;
        g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
@@ -146,6 +147,7 @@ __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_
       }
     }
     const uint64_t count = states[s * words];
+    if (F.null_out) F.null_out[g] = count == 0 ? F.null_bits : 0ull;
     for (uint32_t j = 0; j < F.n_out; ++j) {
       const uint64_t v = states[s * words + F.word[j]];
       uint64_t o;

@@ -26,6 +26,27 @@ cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long lon
   return cudaGetLastError();
 }
 
+// Re-insert every entry of an open-addressing table into a larger one (HashTable::resize,
+// storage/HashTable.hpp: the reference resizes under an exclusive lock; here growth happens between work orders).
+__global__ void k_join_rehash(const JoinSlot *from, uint64_t from_cap, JoinSlot *to, uint64_t to_cap) {
+  const uint64_t mask = to_cap - 1;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < from_cap;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const JoinSlot s = from[i];
+    if (s.row == kEmptyRow) continue;
+    uint64_t h = mix64(static_cast<uint64_t>(s.key)) & mask;
+    while (atomicCAS(&to[h].row, kEmptyRow, s.row) != kEmptyRow) h = (h + 1) & mask;
+    to[h].key = s.key;
+  }
+}
+
+cudaError_t launch_join_rehash(const JoinSlot *from, uint64_t from_cap, JoinSlot *to, uint64_t to_cap, cudaStream_t st) {
+  uint64_t g = (from_cap + 255) / 256;
+  if (g > 148ull * 16) g = 148ull * 16;
+  k_join_rehash<<<static_cast<unsigned>(g), 256, 0, st>>>(from, from_cap, to, to_cap);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st) {
   if (J.dense) return launch_fill_u64(J.heads, J.cap, kEmptyRow, st);
   uint64_t g = (J.cap + 255) / 256;

@@ -204,6 +204,7 @@ struct TopkDesc {
   uint8_t key_ltype[4];
   uint8_t desc[4];
   uint64_t n_rows;
+  const unsigned long long *d_n_rows;   // optional device-side row count of the input (min with n_rows)
   uint32_t n_cols;
   ColDesc in[kMaxCols];
   char *out[kMaxCols];
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
   __shared__ unsigned long long s_prefix, s_remaining;
   __shared__ unsigned int s_m;
   __shared__ int s_done;
-  const uint64_t n = D.n_rows;
+  const uint64_t n = D.d_n_rows ? min(D.n_rows, static_cast<uint64_t>(*D.d_n_rows)) : D.n_rows;
   const uint64_t k = min(static_cast<uint64_t>(limit), n);
   const char *kp = D.key_col[0].ptr;
   const uint32_t kw = D.key_col[0].width;
@@ -433,6 +434,7 @@ int qsgpu_join_partition(qsgpu_join_table_t table, qsgpu_relation_t input, uint3
     return partition_impl(input, key_attr, n_parts, 1, table->J.min_key, w2, output, host_offsets);
   }
   if (table->J.cap < n_parts) { set_error(QSGPU_ERR_INVALID, "more partitions than table slots"); return QSGPU_ERR_INVALID; }
+  table->cap_frozen = true;      // rows are grouped by slices of THIS mask: the first build must not pick a smaller one
   return partition_impl(input, key_attr, n_parts, 0, 0, table->J.cap / n_parts, output, host_offsets, table->J.cap - 1);
 }
 
@@ -639,7 +641,12 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   Device *d = device(input->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   uint64_t n = 0;
-  int st = qsgpu_relation_num_rows(input, &n);
+  int st = QSGPU_OK;
+  // A small input whose row count is still device-side (the output of the operator before): the one-launch kernel
+  // reads the count itself, the host does not wait for the producer.
+  const bool device_count = input->dirty && input->capacity <= kTopkSingleMax && input->capacity > 0;
+  if (device_count) n = input->capacity;
+  else st = qsgpu_relation_num_rows(input, &n);
   if (st) return st;
   if (input->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "this operator reads native columns; its input holds dictionary-coded attributes (select them into a temporary relation first)"); return QSGPU_ERR_UNSUPPORTED; }
   if (n_keys == 0 || n_keys > 4 || limit == 0 || limit > 1024 || input->attrs.size() > static_cast<size_t>(kMaxCols)) {
@@ -649,6 +656,7 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   TopkDesc D{};
   D.n_keys = n_keys;
   D.n_rows = n;
+  D.d_n_rows = device_count ? input->d_rows : nullptr;
   for (uint32_t q = 0; q < n_keys; ++q) {
     if (keys[q].attr >= input->attrs.size()) { set_error(QSGPU_ERR_INVALID, "sort attribute out of range"); return QSGPU_ERR_INVALID; }
     const uint8_t lt = vtype_of(input->attrs[keys[q].attr].type);

@@ -67,6 +67,7 @@ struct qsgpu_agg_state {
   std::vector<qs_attr> key_attrs;     // group-by attribute types
   std::vector<uint32_t> key_attr_ids;
   qs::AggDesc A{};
+  char *ctl = nullptr;                // fixed-size strategies: the one block behind counters, directory, states, keys
   uint32_t max_ctas = 0;
   unsigned int *d_done = nullptr;     // last-CTA-merges ticket
   // dense export buffers (hash / collision-free partials, finalize index)
@@ -87,6 +88,15 @@ struct qsgpu_join_table {
   uint32_t key_type = QS_INT;
   qs::JoinDesc J{};
   const qsgpu_relation *build_rel = nullptr;
+  // Open addressing: slots are allocated from the optimizer's estimate, but the table is CLEARED and its mask
+  // chosen at the first build work order, from the rows that work order really holds (2x, power of two): an
+  // over-estimate must not spread 15 M entries over 2 GB of slots (every insert and probe is a random access,
+  // and the smaller table is cleared 4x faster).  Later work orders that would push the load factor above 1/2
+  // re-hash into a larger array (HashTable::resize); an under-estimate therefore grows instead of failing.
+  uint64_t alloc_cap = 0;          // slots allocated
+  uint64_t upper_entries = 0;      // rows handed to build work orders so far (>= entries)
+  bool cleared = false;            // J.cap slots are initialised
+  bool cap_frozen = false;         // qsgpu_join_partition already grouped rows by slices of J.cap
 };
 
 namespace qs {

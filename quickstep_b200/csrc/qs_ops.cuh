@@ -68,6 +68,13 @@ struct FinalizeDesc {
   char *out[kMaxOut];
   int keys_are_slots;          // collision free: key value == slot index
   unsigned long long *rows_out;   // device row counter of the output relation (set to n by the kernel)
+  // Fixed-size states: the live group count stays on the device (no host wait before the launch); the kernel
+  // finalizes min(n, *d_n_groups) rows.  nullptr: n is exact.
+  const uint32_t *d_n_groups;
+  // SQL NULL of an aggregate over zero rows (AggregationHandleSum.cpp:134-143): per-row mask of the output
+  // relation, bit j = output column j is NULL; null_bits = the mask of a group whose row count is zero.
+  unsigned long long *null_out;
+  uint64_t null_bits;
 };
 
 // One (block, attribute) stripe of a batched staging call (qsgpu_stage_blocks).
@@ -95,6 +102,14 @@ constexpr uint32_t kStageTileRows = 4096;
 size_t agg_smem_extra(int hot, int n_agg, bool grouped, uint32_t words, bool priv = false);
 int agg_hot_groups(const AggDesc &A);
 cudaError_t launch_fill_identity(uint64_t *states, uint64_t n_rows, const AggDesc &A, cudaStream_t st);
+// one launch that brings a fresh SINGLE_STATE / COMPACT_KEY state to its initial contents: per-CTA partial rows and
+// totals = identities, key directory empty, counters zero (ctl = the 3 x 256-byte counter block)
+cudaError_t launch_agg_init(const AggDesc &A, uint64_t partial_sets, void *ctl, cudaStream_t st);
+// rows [0, min(max_rows, *d_rows)) of every column, the row count, the device error word and (optionally) the
+// per-row NULL masks packed into one buffer: what one device-to-host copy brings back (qsgpu_relation_read_rows)
+cudaError_t launch_pack_rows(char *dst, const ColDesc *cols, uint32_t n_cols, uint64_t max_rows,
+                             const unsigned long long *d_rows, const unsigned long long *d_nulls,
+                             uint32_t *error_flag, cudaStream_t st);
 cudaError_t launch_merge_partials(const AggDesc &A, uint32_t n_ctas, cudaStream_t st);
 cudaError_t launch_merge_foreign_compact(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
                                          uint32_t f_groups, cudaStream_t st);
@@ -111,6 +126,7 @@ cudaError_t launch_finalize(const uint64_t *states, const uint64_t *keys, uint32
                             uint64_t n, const FinalizeDesc &F, cudaStream_t st);
 // k_join.cu
 cudaError_t launch_join_clear(const JoinDesc &J, cudaStream_t st);
+cudaError_t launch_join_rehash(const JoinSlot *from, uint64_t from_cap, JoinSlot *to, uint64_t to_cap, cudaStream_t st);
 cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st);
 // k_misc.cu
 cudaError_t launch_decode_dict(void *dst, const void *codes, const void *dict, uint64_t n, uint32_t code_width,

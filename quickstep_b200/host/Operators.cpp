@@ -9,20 +9,8 @@ std::vector<DeviceExtent> InputFeed::take(StorageManager *sm, std::uint64_t need
   if (stored_) {
     if (started_) return out;
     started_ = true;
-    sm->deviceRelation(relation_, needed_attrs);   // K0: stage whatever is not resident yet (one batch)
-    DeviceExtent cur;
-    for (block_id b : relation_.getBlocksSnapshot()) {
-      const DeviceExtent e = sm->blockExtent(b);
-      if (cur.relation && cur.row_end == e.row_begin &&
-          (FLAGS_gpu_rows_per_workorder == 0 || e.row_end - cur.row_begin <= FLAGS_gpu_rows_per_workorder)) {
-        cur.row_end = e.row_end;                   // grow the run of adjacent blocks
-      } else {
-        if (cur.relation) out.push_back(cur);
-        cur = e;
-      }
-    }
-    if (cur.relation) out.push_back(cur);
-    return out;
+    // K0: stage whatever is not resident yet (one batch), then one work order per run of adjacent blocks
+    return sm->stagedExtents(relation_, needed_attrs, FLAGS_gpu_rows_per_workorder);
   }
   for (block_id b : pending_) out.push_back(sm->blockExtent(b));
   pending_.clear();
@@ -269,11 +257,10 @@ bool FinalizeAggregationOperator::getAllWorkOrders(WorkOrdersContainer *containe
 
 void FinalizeAggregationWorkOrder::execute() {
   qsgpu_relation_t out = nullptr;
-  std::uint64_t mask = 0;
   if (merge_comm_) QS_CHECK_GPU(qsgpu_agg_merge_all(state_, merge_comm_));
-  QS_CHECK_GPU(qsgpu_agg_finalize(state_, &out, &mask));
+  // enqueue only: NULLs of aggregates over zero rows travel in the output relation's per-row NULL mask
+  QS_CHECK_GPU(qsgpu_agg_finalize(state_, &out, nullptr));
   output_destination_->adopt(out);
-  output_destination_->null_mask = mask;
 }
 
 bool DestroyAggregationStateOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,

@@ -28,9 +28,6 @@ class InsertDestination {
   InsertDestination(const CatalogRelation *relation, std::uint64_t capacity_rows, StorageManager *sm)
       : relation_(relation), capacity_(capacity_rows), sm_(sm) {}
   const CatalogRelation &getRelation() const { return *relation_; }
-  // bit j set: aggregate j of a single-state aggregation saw no rows, its value is SQL NULL
-  // (AggregationHandleSum.cpp:134-143); written by FinalizeAggregationWorkOrder
-  std::uint64_t null_mask = 0;
   qsgpu_relation_t deviceRelation() { sm_->createTemporary(*relation_, capacity_); return sm_->temporary(*relation_); }
   // FinalizeAggregation / top-k create their output relation themselves
   void adopt(qsgpu_relation_t handle) { sm_->adoptTemporary(*relation_, handle); }

@@ -36,24 +36,48 @@ WorkerPool::~WorkerPool() {
   {
     std::lock_guard<std::mutex> lk(mu_);
     shutdown_ = true;
+    shutdown_flag_.store(true, std::memory_order_release);
   }
   work_cv_.notify_all();
   for (auto &t : threads_) t.join();
 }
 
+// A GPU work order is a few tens of microseconds of host work (lower, look the kernel up, enqueue), so the
+// latency of waking a sleeping thread (20-50 us each way) would dominate a query of five operators.  Both sides
+// therefore poll an atomic counter for a bounded time before they fall back to the condition variable: Workers for
+// kSpinUs after their last work order (they stay hot for the length of a query and sleep between queries), the
+// Foreman while it waits for a completion.
+namespace {
+constexpr int kSpinUs = 300;
+template <class Pred>
+bool spinUntil(Pred &&ready) {
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(kSpinUs);
+  for (int i = 0;; ++i) {
+    if (ready()) return true;
+    if ((i & 63) == 63 && std::chrono::steady_clock::now() > deadline) return false;
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+}  // namespace
+
 void WorkerPool::submit(WorkOrder *w, std::size_t op_index) {
   {
     std::lock_guard<std::mutex> lk(mu_);
     work_queue_.push({w, op_index});
+    n_work_.fetch_add(1, std::memory_order_release);
   }
   work_cv_.notify_one();
 }
 
 std::size_t WorkerPool::waitForCompletion(double *execute_ms) {
+  spinUntil([&] { return n_done_.load(std::memory_order_acquire) != 0; });
   std::unique_lock<std::mutex> lk(mu_);
   done_cv_.wait(lk, [&] { return !done_queue_.empty(); });
   const std::pair<std::size_t, double> m = done_queue_.front();
   done_queue_.pop();
+  n_done_.fetch_sub(1, std::memory_order_release);
   if (execute_ms) *execute_ms = m.second;
   return m.first;
 }
@@ -61,12 +85,14 @@ std::size_t WorkerPool::waitForCompletion(double *execute_ms) {
 void WorkerPool::workerLoop() {
   for (;;) {
     Message m;
+    spinUntil([&] { return n_work_.load(std::memory_order_acquire) != 0 || shutdown_flag_.load(std::memory_order_acquire); });
     {
       std::unique_lock<std::mutex> lk(mu_);
       work_cv_.wait(lk, [&] { return shutdown_ || !work_queue_.empty(); });
       if (work_queue_.empty()) return;
       m = work_queue_.front();
       work_queue_.pop();
+      n_work_.fetch_sub(1, std::memory_order_release);
     }
     std::unique_ptr<WorkOrder> wo(m.work_order);     // Worker.cpp:127-139: executed, then destroyed
     const auto t0 = std::chrono::steady_clock::now();
@@ -76,6 +102,7 @@ void WorkerPool::workerLoop() {
     {
       std::lock_guard<std::mutex> lk(mu_);
       done_queue_.push({m.op_index, ms});
+      n_done_.fetch_add(1, std::memory_order_release);
     }
     done_cv_.notify_one();
   }

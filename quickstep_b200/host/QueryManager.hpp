@@ -11,6 +11,7 @@
 // In an in-tree build none of this file is used: the GPU operators sit in the reference's own DAG.
 #pragma once
 
+#include <atomic>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -66,6 +67,8 @@ class WorkerPool {
   std::queue<Message> work_queue_;
   std::queue<std::pair<std::size_t, double>> done_queue_;
   bool shutdown_ = false;
+  std::atomic<int> n_work_{0}, n_done_{0};       // queue lengths, polled without the lock (bounded spinning)
+  std::atomic<bool> shutdown_flag_{false};
   std::vector<std::thread> threads_;
 };
 

@@ -347,6 +347,7 @@ qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std:
     R.n_blocks_staged = 0;
     R.rows = 0;
     R.staged_attrs = 0;
+    R.runs.clear();
     for (block_id id : ids) {
       const StorageBlock &B = blocks_.at(id);
       block_first_row_[B.id] = {rel.getID(), R.rows};
@@ -375,6 +376,30 @@ qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std:
   R.n_blocks_staged = ids.size();
   R.staged_attrs |= to_stage;
   return R.handle;
+}
+
+std::vector<DeviceExtent> StorageManager::stagedExtents(const CatalogRelation &rel, std::uint64_t needed_attrs,
+                                                        std::uint64_t max_rows) {
+  qsgpu_relation_t h = deviceRelation(rel, needed_attrs);
+  std::lock_guard<std::mutex> lk(mu_);
+  Resident &R = resident_[rel.getID()];
+  if (R.runs_max_rows == max_rows && !R.runs.empty() && R.runs.front().relation == h) return R.runs;
+  R.runs.clear();
+  DeviceExtent cur;
+  std::uint64_t row = 0;
+  for (block_id b : rel.getBlocksSnapshot()) {
+    const std::uint64_t n = static_cast<std::uint64_t>(blocks_.at(b).num_tuples);
+    if (cur.relation && (max_rows == 0 || row + n - cur.row_begin <= max_rows)) {
+      cur.row_end = row + n;                       // grow the run of adjacent blocks
+    } else {
+      if (cur.relation) R.runs.push_back(cur);
+      cur.relation = h; cur.row_begin = row; cur.row_end = row + n;
+    }
+    row += n;
+  }
+  if (cur.relation) R.runs.push_back(cur);
+  R.runs_max_rows = max_rows;
+  return R.runs;
 }
 
 DeviceExtent StorageManager::blockExtent(block_id id) {

@@ -72,6 +72,10 @@ class StorageManager {
   // (qsgpu_stage_blocks / qsgpu_stage_columns with QS_ENC_SKIP for the rest).
   qsgpu_relation_t deviceRelation(const CatalogRelation &rel, std::uint64_t needed_attrs = ~0ull);
   DeviceExtent blockExtent(block_id id);                           // rows of one block inside it
+  // deviceRelation() + the row ranges a scan of the whole stored relation is cut into: runs of adjacent blocks of at
+  // most `max_rows` rows (0 = one run).  Cached with the image: a query over 9,525 resident blocks (lineitem at
+  // SF100) costs one map lookup here, not one per block.
+  std::vector<DeviceExtent> stagedExtents(const CatalogRelation &rel, std::uint64_t needed_attrs, std::uint64_t max_rows);
   void evict(const CatalogRelation &rel);                          // drop the HBM image
 
   // Keep dictionary-compressed attributes as CODES in HBM: an attribute whose stripe
@@ -112,6 +116,8 @@ class StorageManager {
     std::size_t n_blocks_staged = 0;
     std::uint64_t rows = 0;
     std::uint64_t staged_attrs = 0;      // bit a: attribute a of every staged block is in HBM
+    std::vector<DeviceExtent> runs;      // stagedExtents() cache, valid for runs_max_rows while the image stands
+    std::uint64_t runs_max_rows = ~0ull;
   };
   // union of the block dictionaries of one attribute, sorted in the attribute's order (cached per relation and
   // block count: blocks are immutable once built)

@@ -70,24 +70,6 @@ struct qshost_db {
   }
 };
 
-namespace {
-
-template <class T>
-std::vector<T> readColumn(qsgpu_relation_t rel, std::uint32_t attr, std::uint64_t n) {
-  std::vector<T> v(std::max<std::uint64_t>(n, 1));
-  if (n) QS_CHECK_GPU(qsgpu_relation_read(rel, attr, 0, n, v.data()));
-  v.resize(n);
-  return v;
-}
-
-std::uint64_t numRows(qsgpu_relation_t rel) {
-  std::uint64_t n = 0;
-  QS_CHECK_GPU(qsgpu_relation_num_rows(rel, &n));
-  return n;
-}
-
-}  // namespace
-
 extern "C" {
 
 static void backtraceOnSegv(int sig) {
@@ -228,10 +210,14 @@ int qshost_q6(qshost_db_t db, double *revenue, int *is_null, uint64_t *work_orde
   QueryManager qm(&plan, &ctx, db->sm.get(), db->workers.get());
   qm.run();
 
+  // the query's single host wait: value, row count and NULL mask in one transfer
   qsgpu_relation_t out = db->sm->temporary(*result);
-  const std::vector<double> v = readColumn<double>(out, 0, numRows(out));
-  *revenue = v.empty() ? 0.0 : v[0];
-  if (is_null) *is_null = (ctx.getInsertDestination(dest)->null_mask & 1) ? 1 : 0;
+  double v = 0.0;
+  void *cols[1] = {&v};
+  std::uint64_t n = 0, nulls = 0;
+  QS_CHECK_GPU(qsgpu_relation_read_rows(out, 1, cols, &n, &nulls));
+  *revenue = n ? v : 0.0;
+  if (is_null) *is_null = (n == 0 || (nulls & 1)) ? 1 : 0;
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
   db->last_profile = qm.profile();
   db->dropTemps();
@@ -296,16 +282,19 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
   qm.run();
 
   qsgpu_relation_t out = db->sm->temporary(*t_sorted);
-  const std::uint64_t n = numRows(out);
-  std::vector<char> flag(n + 1), status(n + 1);
+  constexpr std::uint64_t kMaxRows = 64;         // the sort's LIMIT
+  std::vector<char> flag(kMaxRows), status(kMaxRows);
   std::array<std::vector<double>, 7> d;
-  for (auto &v : d) v.resize(n + 1);
-  std::vector<std::int64_t> count(n + 1);
-  std::vector<double> sum_disc(n + 1);
+  for (auto &v : d) v.resize(kMaxRows);
+  std::vector<std::int64_t> count(kMaxRows);
+  std::vector<double> sum_disc(kMaxRows);
+  std::uint64_t n = 0;
   {
+    // the query's single host wait: rows and row count in one transfer
     void *cols[11] = {flag.data(), status.data(), d[0].data(), d[1].data(), d[2].data(), d[3].data(), d[4].data(),
                       d[5].data(), d[6].data(), count.data(), sum_disc.data()};
-    QS_CHECK_GPU(qsgpu_relation_read_all(out, 0, n, cols));
+    QS_CHECK_GPU(qsgpu_relation_read_rows(out, kMaxRows, cols, &n, nullptr));
+    n = std::min(n, kMaxRows);
   }
   std::vector<qshost_q1_row> res(n);
   for (std::uint64_t i = 0; i < n; ++i) {
@@ -419,13 +408,15 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   qm.run();
 
   qsgpu_relation_t out = db->sm->temporary(*t9);
-  const std::uint64_t n = numRows(out);
-  std::vector<std::int32_t> ok(n + 1), sp(n + 1);
-  std::vector<std::uint64_t> od(n + 1);
-  std::vector<double> rev(n + 1);
+  constexpr std::uint64_t kMaxRows = 10;         // LIMIT 10
+  std::vector<std::int32_t> ok(kMaxRows), sp(kMaxRows);
+  std::vector<std::uint64_t> od(kMaxRows);
+  std::vector<double> rev(kMaxRows);
+  std::uint64_t n = 0;
   {
     void *cols[4] = {ok.data(), od.data(), sp.data(), rev.data()};
-    QS_CHECK_GPU(qsgpu_relation_read_all(out, 0, n, cols));
+    QS_CHECK_GPU(qsgpu_relation_read_rows(out, kMaxRows, cols, &n, nullptr));
+    n = std::min(n, kMaxRows);
   }
   const std::uint32_t cap = *n_rows;
   *n_rows = static_cast<std::uint32_t>(n);
