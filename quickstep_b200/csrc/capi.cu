@@ -181,7 +181,7 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan, int max
   // compiled kernel (launch_query_kernel).
   int ctas = 1;
   size_t budget = per_block_max;
-  for (int c = std::min(4, std::max(1, max_ctas)); c >= 2; --c) {
+  for (int c = std::min(8, std::max(1, max_ctas)); c >= 2; --c) {
     const size_t b = per_sm / c - 1024;                     // 1 KB per CTA is reserved by the driver
     if (fixed + 2ull * stage <= b) { ctas = c; budget = b; break; }     // double buffering is the minimum
   }
@@ -789,7 +789,7 @@ int qsgpu_relation_read_rows(qsgpu_relation_t rel, uint64_t max_rows, void *cons
   std::lock_guard<std::mutex> lk(*d->read_mu);
   // one pack launch, one transfer into pinned memory, one wait: row count, error word, NULL masks and rows together
   QS_CUDA(launch_pack_rows(d->read_scratch, cols, static_cast<uint32_t>(rel->cols.size()), max_rows, rel->d_rows,
-                           null_masks ? rel->d_nulls : nullptr, d->d_error, d->stream));
+                           rel->d_nulls, null_masks != nullptr, d->d_error, d->stream));
   count_launch();
   QS_CUDA(cudaMemcpyAsync(d->read_pinned, d->read_scratch, total, cudaMemcpyDeviceToHost, d->stream));
   QS_CUDA(cudaStreamSynchronize(d->stream));
@@ -806,8 +806,7 @@ int qsgpu_relation_read_rows(qsgpu_relation_t rel, uint64_t max_rows, void *cons
   const uint64_t got = std::min<uint64_t>(rel->host_rows, max_rows);
   size_t off = 16;
   if (null_masks) {
-    if (rel->d_nulls) std::memcpy(null_masks, d->read_pinned + off, got * 8);
-    else std::memset(null_masks, 0, got * 8);
+    std::memcpy(null_masks, d->read_pinned + off, got * 8);
     off += (max_rows * 8 + 15) & ~static_cast<size_t>(15);
   }
   for (size_t a = 0; a < rel->cols.size(); ++a) {
@@ -1412,19 +1411,15 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     QS_CUDA(dev_malloc(&s->d_done, 256));
     QS_CUDA(cudaMemsetAsync(s->d_done, 0, 256, d->stream));
     QS_CUDA(dev_malloc(&s->d_idx_count, 256));
-    if (strategy == QS_AGG_COLLISION_FREE) A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
-    else {
-      uint64_t want = std::max<uint64_t>(1024, spec->estimated_num_entries * 2);
-      uint64_t cap = 1024;
-      while (cap < want) cap <<= 1;
-      A.cap = cap;
-      QS_CUDA(dev_malloc(&A.tags, cap * 4));
-      QS_CUDA(cudaMemsetAsync(A.tags, 0, cap * 4, d->stream));
-      QS_CUDA(dev_malloc(&A.keys, cap * A.key_words * 8));
+    if (strategy == QS_AGG_COLLISION_FREE) {
+      A.cap = static_cast<uint64_t>(spec->collision_free_max_key) + 1;
+      QS_CUDA(dev_malloc(&A.states, A.cap * A.words * 8));
+      QS_CUDA(launch_fill_identity(A.states, A.cap, A, d->stream));
+      count_launch();
     }
-    QS_CUDA(dev_malloc(&A.states, A.cap * A.words * 8));
-    QS_CUDA(launch_fill_identity(A.states, A.cap, A, d->stream));
-    count_launch();
+    // SEPARATE_CHAINING: the table is allocated by the first work order (maybe_grow), sized from the rows that work
+    // order really holds and the estimate together -- an optimizer estimate 10x too high must not make every query
+    // initialise, probe and finally scan a table of gigabytes (Q3 at SF100: 64 M slots for 1.5 M groups)
   }
   *out = s.release();
   return QSGPU_OK;
@@ -1437,13 +1432,15 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
 static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
   AggDesc &A = s->A;
   uint32_t n = 0;
-  QS_CUDA(cudaMemcpyAsync(&n, A.n_groups, 4, cudaMemcpyDeviceToHost, d->stream));
-  QS_CUDA(cudaStreamSynchronize(d->stream));
+  if (A.cap != 0) {          // (a table that does not exist yet holds no groups: nothing to ask the device)
+    QS_CUDA(cudaMemcpyAsync(&n, A.n_groups, 4, cudaMemcpyDeviceToHost, d->stream));
+    QS_CUDA(cudaStreamSynchronize(d->stream));
+  }
   // worst case every row opens a group, but never plan for more than 8x the optimizer's estimate at once
   // (a kernel that still overflows raises QSGPU_ERR_CAPACITY; nothing is silently dropped)
   uint64_t worst = n + std::min<uint64_t>(extra_rows, std::max<uint64_t>(8 * s->estimated, 1u << 20));
-  if (worst * 3 / 2 <= A.cap) return QSGPU_OK;
-  uint64_t cap = A.cap;
+  if (A.cap != 0 && worst * 3 / 2 <= A.cap) return QSGPU_OK;
+  uint64_t cap = std::max<uint64_t>(A.cap, 1024);
   while (cap < worst * 2) cap <<= 1;
   AggDesc B = A;
   B.cap = cap;
@@ -1452,11 +1449,14 @@ static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
   QS_CUDA(dev_malloc(&B.keys, cap * A.key_words * 8));
   QS_CUDA(dev_malloc(&B.states, cap * A.words * 8));
   QS_CUDA(launch_fill_identity(B.states, cap, B, d->stream));
-  QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 4, d->stream));
-  QS_CUDA(launch_rehash(A, B, d->stream));
-  count_launch(2);
-  QS_CUDA(cudaStreamSynchronize(d->stream));
-  dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
+  count_launch();
+  if (A.cap != 0) {
+    QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 4, d->stream));
+    QS_CUDA(launch_rehash(A, B, d->stream));
+    count_launch();
+    QS_CUDA(cudaStreamSynchronize(d->stream));
+    dev_free(A.tags); dev_free(A.keys); dev_free(A.states);
+  }
   A = B;
   return QSGPU_OK;
 }
@@ -1563,6 +1563,7 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
 
 static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
   AggDesc &A = s->A;
+  if (A.cap == 0) { *n_out = 0; return check_device_error(d); }      // no work order ever ran: no groups
   if (s->idx_cap < A.cap) {
     if (s->d_idx) dev_free(s->d_idx);
     QS_CUDA(dev_malloc(&s->d_idx, A.cap * 8 + 64));
@@ -1923,7 +1924,7 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
   st = fill_lips(scan->n_lip_probe, scan->lip_probe, rel, rel->dev, &S);
   if (st) return st;
   ScanPlan plan;
-  st = plan_scan(d, &S, 0, &plan);
+  st = plan_scan(d, &S, 0, &plan, 8);      // a key tile is a few KB and the kernel ~25 registers: all the warps an SM holds
   if (st) return st;
   JitKernel *kern = nullptr;
   st = query_kernel(JF_JOIN_BUILD, S, L.P, plan, nullptr, &K, &J, 1, &kern);

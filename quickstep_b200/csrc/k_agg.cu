@@ -95,7 +95,8 @@ __global__ void k_agg_init(const __grid_constant__ AggDesc A, uint64_t partial_s
 struct PackDesc { ColDesc cols[kMaxCols]; };
 // dst: [u64 rows][u32 error, u32 0][nulls: max_rows x u64 when d_nulls][column 0: max_rows x w0, padded to 16]...
 __global__ void k_pack_rows(char *dst, const __grid_constant__ PackDesc P, uint32_t n_cols, uint64_t max_rows,
-                            const unsigned long long *d_rows, const unsigned long long *d_nulls, uint32_t *error_flag) {
+                            const unsigned long long *d_rows, const unsigned long long *d_nulls, int with_nulls,
+                            uint32_t *error_flag) {
   const uint64_t n = min(static_cast<uint64_t>(*d_rows), max_rows);
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *reinterpret_cast<uint64_t *>(dst) = *d_rows;
@@ -106,8 +107,8 @@ __global__ void k_pack_rows(char *dst, const __grid_constant__ PackDesc P, uint3
   size_t off = 16;
   const uint64_t t0 = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  if (d_nulls) {
-    for (uint64_t i = t0; i < n; i += stride) reinterpret_cast<unsigned long long *>(dst + off)[i] = d_nulls[i];
+  if (with_nulls) {        // a relation without a NULL mask holds no NULLs
+    for (uint64_t i = t0; i < n; i += stride) reinterpret_cast<unsigned long long *>(dst + off)[i] = d_nulls ? d_nulls[i] : 0ull;
     off += (max_rows * 8 + 15) & ~static_cast<size_t>(15);
   }
   for (uint32_t c = 0; c < n_cols; ++c) {
@@ -126,13 +127,13 @@ cudaError_t launch_agg_init(const AggDesc &A, uint64_t partial_sets, void *ctl, 
 }
 
 cudaError_t launch_pack_rows(char *dst, const ColDesc *cols, uint32_t n_cols, uint64_t max_rows,
-                             const unsigned long long *d_rows, const unsigned long long *d_nulls,
+                             const unsigned long long *d_rows, const unsigned long long *d_nulls, bool with_nulls,
                              uint32_t *error_flag, cudaStream_t st) {
   PackDesc P{};
   uint64_t bytes = 0;
   for (uint32_t c = 0; c < n_cols; ++c) { P.cols[c] = cols[c]; bytes += max_rows * cols[c].width; }
   const int grid = static_cast<int>(std::min<uint64_t>((bytes + 255) / 256, 148));
-  k_pack_rows<<<std::max(grid, 1), 256, 0, st>>>(dst, P, n_cols, max_rows, d_rows, d_nulls, error_flag);
+  k_pack_rows<<<std::max(grid, 1), 256, 0, st>>>(dst, P, n_cols, max_rows, d_rows, d_nulls, with_nulls ? 1 : 0, error_flag);
   return cudaGetLastError();
 }
 

@@ -210,38 +210,6 @@ struct TopkDesc {
   char *out[kMaxCols];
 };
 
-__global__ void k_topk_primary(const __grid_constant__ TopkDesc D, uint64_t *pk) {
-  for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < D.n_rows;
-       row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    pk[row] = sort_key(D.key_col[0].ptr + row * D.key_col[0].width, D.key_ltype[0], D.desc[0] != 0);
-}
-
-// Histogram of byte `shift/8` among keys whose higher bytes equal `prefix`.
-__global__ void k_topk_hist(const uint64_t *pk, uint64_t n, uint64_t prefix, int shift, unsigned long long *hist) {
-  __shared__ unsigned int s[256];
-  s[threadIdx.x] = 0;
-  __syncthreads();
-  const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t k = pk[i];
-    if ((k & hi_mask) == (prefix & hi_mask)) atomicAdd(&s[(k >> shift) & 0xff], 1u);
-  }
-  __syncthreads();
-  if (s[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(s[threadIdx.x]));
-}
-
-__global__ void k_topk_collect(const uint64_t *pk, uint64_t n, uint64_t threshold, uint64_t *cand,
-                               unsigned long long *count, uint64_t cap) {
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    if (pk[i] <= threshold) {
-      const unsigned long long pos = atomicAdd(count, 1ull);
-      if (pos < cap) cand[pos] = i;
-    }
-  }
-}
-
 constexpr int kTopkMaxCand = 2048;
 
 struct SortElem { uint64_t k[4]; uint64_t row; };
@@ -252,11 +220,102 @@ __device__ __forceinline__ bool elem_less(const SortElem &a, const SortElem &b) 
   return a.row < b.row;
 }
 
-// One CTA: bitonic sort of <= kTopkMaxCand candidates, then gather the first `limit` rows.
-__global__ void __launch_bounds__(1024) k_topk_sort(const __grid_constant__ TopkDesc D, const uint64_t *cand,
-                                                    uint32_t m, uint32_t limit) {
+// ---- multi-block top-k whose selection state never leaves the device -------------------------------------------
+// (the first version read every pass's histogram back to choose the bucket: up to eight host round trips in the
+// middle of Q3's tail).  Primary keys -> up to 8 histogram passes, each closed by the LAST block to finish (ticket):
+// it picks the bucket holding the k-th key, extends the prefix and raises `done` once the keys at or below the
+// bucket fit the sorting CTA; later passes see `done` and return at once -> collect -> sort.  All launches are
+// queued back to back; nothing waits.
+struct TopkState {
+  unsigned long long prefix, remaining, k, n_cand;
+  unsigned int done, ticket;
+  unsigned long long hist[256];
+};
+
+__device__ __forceinline__ uint64_t topk_rows(const TopkDesc &D) {
+  return D.d_n_rows ? min(D.n_rows, static_cast<uint64_t>(*D.d_n_rows)) : D.n_rows;
+}
+
+__global__ void k_topk_primary_dev(const __grid_constant__ TopkDesc D, uint64_t *pk, TopkState *S, uint64_t limit) {
+  const uint64_t n = topk_rows(D);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) { S->prefix = 0; S->k = min(limit, n); S->remaining = S->k; S->n_cand = 0; S->done = 0; S->ticket = 0; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) S->hist[i] = 0;
+  }
+  for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < n;
+       row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    pk[row] = sort_key(D.key_col[0].ptr + row * D.key_col[0].width, D.key_ltype[0], D.desc[0] != 0);
+}
+
+__global__ void __launch_bounds__(256) k_topk_hist_dev(const __grid_constant__ TopkDesc D, const uint64_t *pk, TopkState *S, int shift) {
+  if (*reinterpret_cast<volatile unsigned int *>(&S->done)) return;
+  __shared__ unsigned int s[256];
+  __shared__ bool last;
+  s[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t n = topk_rows(D);
+  const uint64_t prefix = S->prefix;
+  const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t k = pk[i];
+    if ((k & hi_mask) == (prefix & hi_mask)) atomicAdd(&s[(k >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  if (s[threadIdx.x]) atomicAdd(&S->hist[threadIdx.x], static_cast<unsigned long long>(s[threadIdx.x]));
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    volatile unsigned long long *h = S->hist;
+    const uint64_t k = S->k;
+    uint64_t acc = 0, remaining = S->remaining;
+    int b = 0;
+    for (; b < 256; ++b) {
+      if (acc + h[b] >= remaining) break;
+      acc += h[b];
+    }
+    if (b == 256) b = 255;
+    const uint64_t below_or_in = (k - remaining) + acc + h[b];     // keys <= every key of bucket b
+    uint64_t p = prefix | (static_cast<uint64_t>(b) << shift);
+    S->remaining = remaining - acc;
+    if (below_or_in <= static_cast<uint64_t>(kTopkMaxCand) || shift == 0) {
+      if (shift > 0) p |= (1ull << shift) - 1;                      // take the whole bucket
+      S->done = 1;
+    }
+    S->prefix = p;
+    S->ticket = 0;
+  }
+  __syncthreads();
+  S->hist[threadIdx.x] = 0;
+}
+
+__global__ void k_topk_collect_dev(const __grid_constant__ TopkDesc D, const uint64_t *pk, TopkState *S, uint64_t *cand) {
+  const uint64_t n = topk_rows(D);
+  const uint64_t threshold = S->prefix;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (pk[i] <= threshold) {
+      const unsigned long long pos = atomicAdd(&S->n_cand, 1ull);
+      if (pos < static_cast<unsigned long long>(kTopkMaxCand)) cand[pos] = i;
+    }
+  }
+}
+
+// k_topk_sort with the candidate count read on the device; more than kTopkMaxCand rows tying on the primary key at
+// the cut raise QSGPU_ERR_CAPACITY (reported at the next read of the result).
+__global__ void __launch_bounds__(1024) k_topk_sort_dev(const __grid_constant__ TopkDesc D, const uint64_t *cand, TopkState *S,
+                                                        uint32_t limit, unsigned long long *rows_out, uint32_t *error_flag) {
   extern __shared__ __align__(16) char s_raw[];
   SortElem *e = reinterpret_cast<SortElem *>(s_raw);
+  uint32_t m = static_cast<uint32_t>(min(S->n_cand, static_cast<unsigned long long>(kTopkMaxCand) + 1));
+  if (m > static_cast<uint32_t>(kTopkMaxCand)) {
+    if (threadIdx.x == 0) atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+    m = kTopkMaxCand;
+  }
   uint32_t N = 1;
   while (N < m) N <<= 1;
   for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
@@ -295,13 +354,15 @@ __global__ void __launch_bounds__(1024) k_topk_sort(const __grid_constant__ Topk
       for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
     }
   }
+  if (threadIdx.x == 0) *rows_out = n_out;
 }
 
-// Whole top-k in ONE launch for inputs of up to kTopkSingleMax rows (Q3's ~1e5 groups, Q1's 4): one CTA does
+// Whole top-k in ONE launch for inputs of up to kTopkSingleCta rows (Q3's ~1e5 groups, Q1's 4): one CTA does
 // the radix select of the limit-th primary key (byte passes, stopping as soon as the candidates fit), collects
 // the candidates, sorts them with the full comparator and writes the result and its row count.  The multi-kernel
 // path below needs a host round trip per pass; here the host never waits.
-constexpr uint64_t kTopkSingleMax = 1ull << 20;
+// beyond this many rows one CTA is slower than the multi-block passes (120 us for Q3's 1.5e5 groups at SF10)
+constexpr uint64_t kTopkSingleCta = 1ull << 14;
 __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ TopkDesc D, uint32_t limit,
                                                       unsigned long long *rows_out, uint32_t *error_flag) {
   extern __shared__ __align__(16) char s_topk_raw[];
@@ -316,9 +377,12 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
   const uint32_t kw = D.key_col[0].width;
   const uint8_t klt = D.key_ltype[0];
   const bool kdesc = D.desc[0] != 0;
-  if (threadIdx.x == 0) { s_prefix = 0; s_remaining = k; s_done = 0; s_m = 0; }
+  if (threadIdx.x == 0) { s_prefix = ~0ull; s_remaining = k; s_done = 0; s_m = 0; }
   __syncthreads();
-  for (int shift = 56; shift >= 0; shift -= 8) {
+  // every row is a candidate when they all fit the sorting buffer (Q1's 4 groups, a gathered top-10 per GPU):
+  // no selection passes, the threshold stays at the largest key
+  for (int shift = n <= static_cast<uint64_t>(kTopkMaxCand) ? -1 : 56; shift >= 0; shift -= 8) {
+    if (shift == 56 && threadIdx.x == 0) s_prefix = 0;
     if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
@@ -644,7 +708,7 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   int st = QSGPU_OK;
   // A small input whose row count is still device-side (the output of the operator before): the one-launch kernel
   // reads the count itself, the host does not wait for the producer.
-  const bool device_count = input->dirty && input->capacity <= kTopkSingleMax && input->capacity > 0;
+  const bool device_count = input->dirty && input->capacity > 0;
   if (device_count) n = input->capacity;
   else st = qsgpu_relation_num_rows(input, &n);
   if (st) return st;
@@ -682,7 +746,7 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     D.out[c] = rel->cols[c];
   }
   if (n == 0) { *out = rel; return qsgpu_relation_set_num_rows(rel, 0); }
-  if (n <= kTopkSingleMax) {
+  if (n <= kTopkSingleCta) {
     // one launch, no host round trip: the result's row count stays on the device until somebody asks
     const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(SortElem);
     cudaFuncSetAttribute(k_topk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));   // per device
@@ -705,64 +769,25 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   }
 
   uint64_t *pk = nullptr, *cand = nullptr;
-  unsigned long long *hist = nullptr;
-  auto cleanup = [&]() { dev_free(pk); dev_free(cand); dev_free(hist); };
+  TopkState *state = nullptr;
+  auto cleanup = [&]() { dev_free(pk); dev_free(cand); dev_free(state); };     // stream-ordered: after the launches below
   cudaError_t e = dev_malloc(&pk, n * 8 + 64);
   if (e == cudaSuccess) e = dev_malloc(&cand, kTopkMaxCand * 8);
-  if (e == cudaSuccess) e = dev_malloc(&hist, 257 * 8);
+  if (e == cudaSuccess) e = dev_malloc(&state, sizeof(TopkState));
   if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k scratch"); }
   const bool on = timing_enabled();
   if (on) cudaEventRecord(d->ev0, d->stream);
   const int grid = grid_for(n);
-  k_topk_primary<<<grid, 256, 0, d->stream>>>(D, pk);
-  count_launch();
-  // radix select of the k-th smallest primary key, one byte per pass -- stopped as soon as the keys at or
-  // below the current bucket fit the final sorting CTA (for Q3's ~1e5 groups that is after 2-3 of the 8
-  // passes, and every pass costs a host round trip)
-  const uint64_t k = std::min<uint64_t>(limit, n);
-  uint64_t prefix = 0, remaining = k;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    cudaMemsetAsync(hist, 0, 256 * 8, d->stream);
-    k_topk_hist<<<grid, 256, 0, d->stream>>>(pk, n, prefix, shift, hist);
-    count_launch();
-    unsigned long long h[256];
-    e = cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k select"); }
-    uint64_t acc = 0;
-    int b = 0;
-    for (; b < 256; ++b) {
-      if (acc + h[b] >= remaining) break;
-      acc += h[b];
-    }
-    if (b == 256) b = 255;
-    const uint64_t below_or_in = (k - remaining) + acc + h[b];     // keys <= every key of bucket b
-    remaining -= acc;
-    prefix |= static_cast<uint64_t>(b) << shift;
-    if (below_or_in <= static_cast<uint64_t>(kTopkMaxCand)) {
-      if (shift > 0) prefix |= (1ull << shift) - 1;                // take the whole bucket
-      break;
-    }
-  }
-  cudaMemsetAsync(hist + 256, 0, 8, d->stream);
-  k_topk_collect<<<grid, 256, 0, d->stream>>>(pk, n, prefix, cand, hist + 256, kTopkMaxCand);
-  count_launch();
-  unsigned long long m = 0;
-  e = cudaMemcpyAsync(&m, hist + 256, 8, cudaMemcpyDeviceToHost, d->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-  if (e != cudaSuccess) { cleanup(); qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k collect"); }
-  if (m > static_cast<unsigned long long>(kTopkMaxCand)) {
-    cleanup();
-    qsgpu_relation_destroy(rel);
-    set_error(QSGPU_ERR_UNSUPPORTED, "top-k: more than 2048 rows tie on the primary sort key at the cut");
-    return QSGPU_ERR_UNSUPPORTED;
-  }
-  uint32_t N = 1;
-  while (N < m) N <<= 1;
-  const size_t smem = static_cast<size_t>(N) * sizeof(SortElem);
-  cudaFuncSetAttribute(k_topk_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  k_topk_sort<<<1, 1024, smem, d->stream>>>(D, cand, static_cast<uint32_t>(m), static_cast<uint32_t>(limit));
-  count_launch();
+  k_topk_primary_dev<<<grid, 256, 0, d->stream>>>(D, pk, state, limit);
+  // radix select of the k-th smallest primary key, one byte per pass; the passes after the one that raised `done`
+  // (for Q3's 1e5..1e6 groups: the 2nd or 3rd) return immediately
+  for (int shift = 56; shift >= 0; shift -= 8) k_topk_hist_dev<<<grid, 256, 0, d->stream>>>(D, pk, state, shift);
+  k_topk_collect_dev<<<grid, 256, 0, d->stream>>>(D, pk, state, cand);
+  const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(SortElem);
+  cudaFuncSetAttribute(k_topk_sort_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  k_topk_sort_dev<<<1, 1024, smem, d->stream>>>(D, cand, state, static_cast<uint32_t>(limit), rel->d_rows, d->d_error);
+  count_launch(11);
+  e = cudaGetLastError();
   if (on) {
     cudaEventRecord(d->ev1, d->stream);
     cudaEventSynchronize(d->ev1);
@@ -770,11 +795,9 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     cudaEventElapsedTime(&ms, d->ev0, d->ev1);
     record_ms(QS_K_TOPK, ms);
   }
-  e = cudaStreamSynchronize(d->stream);
   cleanup();
-  if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k sort"); }
-  st = qsgpu_relation_set_num_rows(rel, std::min<uint64_t>(limit, m));
-  if (st) { qsgpu_relation_destroy(rel); return st; }
+  if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "top-k"); }
+  rel->dirty = true;                  // the row count stays on the device until somebody asks
   *out = rel;
   return QSGPU_OK;
 }

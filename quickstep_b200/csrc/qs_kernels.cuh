@@ -694,6 +694,7 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
   const int tid = threadIdx.x;
   VmRegs regs;
   const uint64_t mask = J.cap - 1;
+  uint32_t inserted = 0;       // this thread's inserts over ALL its tiles: one counter update per warp per kernel
   scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
     bool valid[kRows];
     tile_valid(S, rt, tile, tid, valid);
@@ -707,13 +708,12 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
 #pragma unroll
     for (int r = 0; r < kRows; ++r) pass[r] = valid[r] && (bits[r] & 1u);
     lip_build_rows<Q, SinkBase>(K, stage, tid, pass);
-    uint32_t inserted = 0;
+    if constexpr (Q::j_dense) {
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      if (!pass[r]) continue;
-      const int64_t key = join_key<Q>(stage, tile_row(r, tid));
-      const unsigned long long row = row0 + tile_row(r, tid);
-      if constexpr (Q::j_dense) {
+      for (int r = 0; r < kRows; ++r) {
+        if (!pass[r]) continue;
+        const int64_t key = join_key<Q>(stage, tile_row(r, tid));
+        const unsigned long long row = row0 + tile_row(r, tid);
         // push the row on the front of its key's chain: one exchange, one store
         const uint64_t k = static_cast<uint64_t>(key - J.min_key);
         if (key < J.min_key || k >= J.cap) { atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_INVALID)); continue; }
@@ -725,26 +725,45 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
         J.next[row] = old == kEmptyRow ? kEmptyRow : (old & ~kChainBit);
         if (old != kEmptyRow) atomicOr(&J.heads[k], kChainBit);
         ++inserted;
-        continue;
       }
-      uint64_t h = mix64(static_cast<uint64_t>(key)) & mask;
-      bool done = false;
-      for (uint64_t probes = 0; probes <= mask; ++probes) {
-        if (atomicCAS(&J.slots[h].row, kEmptyRow, row) == kEmptyRow) {
-          J.slots[h].key = key;
-          done = true;
-          break;
-        }
-        h = (h + 1) & mask;
-      }
-      if (done) ++inserted;
-      else atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-    }
-    // one counter update per warp instead of one per row
+    } else {
+      // Open addressing, in ROUNDS: every round issues one compare-and-swap for each of the thread's rows that is
+      // still looking for a slot -- back to back, so up to kRows random atomics per thread are in flight -- and
+      // only then looks at what came back.  (The row-after-row loop it replaces kept ONE atomic in flight per
+      // thread: ncu showed 7 % issue utilisation with 72 long-scoreboard stall cycles per issued instruction.)
+      int64_t key[kRows];
+      uint64_t h[kRows];
+      uint32_t pend = 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, off);
-    if ((tid & 31) == 0 && inserted) atomicAdd(J.n_entries, static_cast<unsigned long long>(inserted));
+      for (int r = 0; r < kRows; ++r) {
+        key[r] = join_key<Q>(stage, tile_row(r, tid));
+        h[r] = mix64(static_cast<uint64_t>(key[r])) & mask;
+        if (pass[r]) pend |= 1u << r;
+      }
+      for (uint64_t probes = 0; pend != 0; ++probes) {
+        if (probes > mask) { atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY)); break; }
+        unsigned long long old[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if ((pend >> r) & 1u) old[r] = atomicCAS(&J.slots[h[r]].row, kEmptyRow, row0 + tile_row(r, tid));
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (!((pend >> r) & 1u)) continue;
+          if (old[r] == kEmptyRow) {
+            J.slots[h[r]].key = key[r];
+            pend &= ~(1u << r);
+            ++inserted;
+          } else {
+            h[r] = (h[r] + 1) & mask;
+          }
+        }
+      }
+    }
   });
+  // (a per-tile update put one same-address atomic per warp per 1024 rows on the table's entry counter)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, off);
+  if ((tid & 31) == 0 && inserted) atomicAdd(J.n_entries, static_cast<unsigned long long>(inserted));
 }
 
 // ============================================================== K6 join probe

@@ -108,7 +108,7 @@ cudaError_t launch_agg_init(const AggDesc &A, uint64_t partial_sets, void *ctl, 
 // rows [0, min(max_rows, *d_rows)) of every column, the row count, the device error word and (optionally) the
 // per-row NULL masks packed into one buffer: what one device-to-host copy brings back (qsgpu_relation_read_rows)
 cudaError_t launch_pack_rows(char *dst, const ColDesc *cols, uint32_t n_cols, uint64_t max_rows,
-                             const unsigned long long *d_rows, const unsigned long long *d_nulls,
+                             const unsigned long long *d_rows, const unsigned long long *d_nulls, bool with_nulls,
                              uint32_t *error_flag, cudaStream_t st);
 cudaError_t launch_merge_partials(const AggDesc &A, uint32_t n_ctas, cudaStream_t st);
 cudaError_t launch_merge_foreign_compact(const AggDesc &A, const uint64_t *f_states, const uint64_t *f_keys,
