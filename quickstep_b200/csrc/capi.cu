@@ -1444,14 +1444,19 @@ static int maybe_grow(qsgpu_agg_state *s, Device *d, uint64_t extra_rows) {
   while (cap < worst * 2) cap <<= 1;
   AggDesc B = A;
   B.cap = cap;
-  QS_CUDA(dev_malloc(&B.tags, cap * 4));
-  QS_CUDA(cudaMemsetAsync(B.tags, 0, cap * 4, d->stream));
-  QS_CUDA(dev_malloc(&B.keys, cap * A.key_words * 8));
-  QS_CUDA(dev_malloc(&B.states, cap * A.words * 8));
-  QS_CUDA(launch_fill_identity(B.states, cap, B, d->stream));
+  // cap + 1 rows: the last one is the reserved row of the all-ones key (CAS-claimed keys, qs_kernels.cuh K7)
+  B.tags = nullptr;
+  if (A.key_words > 2) {
+    QS_CUDA(dev_malloc(&B.tags, (cap + 1) * 4));
+    QS_CUDA(cudaMemsetAsync(B.tags, 0, (cap + 1) * 4, d->stream));
+  }
+  QS_CUDA(dev_malloc(&B.keys, (cap + 1) * A.key_words * 8));
+  QS_CUDA(cudaMemsetAsync(B.keys, 0xff, (cap + 1) * A.key_words * 8, d->stream));     // "empty" = all ones
+  QS_CUDA(dev_malloc(&B.states, (cap + 1) * A.words * 8));
+  QS_CUDA(launch_fill_identity(B.states, cap + 1, B, d->stream));
   count_launch();
   if (A.cap != 0) {
-    QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 4, d->stream));
+    QS_CUDA(cudaMemsetAsync(A.n_groups, 0, 8, d->stream));        // group counter + "reserved row in use" flag
     QS_CUDA(launch_rehash(A, B, d->stream));
     count_launch();
     QS_CUDA(cudaStreamSynchronize(d->stream));
@@ -1570,7 +1575,8 @@ static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
     s->idx_cap = A.cap;
   }
   QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
-  QS_CUDA(launch_collect_slots(A.states, A.words, A.cap, s->d_idx, s->d_idx_count,
+  const uint64_t table_rows = A.cap + (s->strategy == QS_AGG_SEPARATE_CHAINING ? 1 : 0);
+  QS_CUDA(launch_collect_slots(A.states, A.words, table_rows, s->d_idx, s->d_idx_count,
                                s->existence ? s->existence->d.words : nullptr, d->stream));
   count_launch();
   unsigned long long n = 0;

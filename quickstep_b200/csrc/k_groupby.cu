@@ -4,7 +4,8 @@
 //   generic keys (<= 32 B)  PackedPayloadHashTable::upsertValueAccessorCompositeKeyInternal
 //                           (storage/PackedPayloadHashTable.hpp:780-909)  -- the
 //                           reference chains buckets under a SpinMutex; here
-//                           open addressing with a per-slot tag (CAS claim) and
+//                           open addressing, keys claimed by one 64 / 128-bit CAS
+//                           (a per-slot tag for keys wider than 16 bytes) and
 //                           native global RED atomics on the state words.   (TPC-H Q3)
 //   dense INT/LONG key      CollisionFreeVectorTable::upsertValueAccessor*
 //                           (storage/CollisionFreeVectorTable.hpp:530-645): slot = key,
@@ -39,9 +40,11 @@ __device__ __forceinline__ int64_t table_upsert_rt(const uint64_t *key, uint32_t
 
 // Rehash every ready slot of `from` into `to` (table growth between work orders).
 __global__ void k_rehash(const __grid_constant__ AggDesc from, const __grid_constant__ AggDesc to) {
-  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < from.cap;
+  // (a slot is occupied iff its row count is non-zero: holds between kernels for both key protocols; the table has
+  // cap + 1 rows, the last one reserved for the all-ones key of the CAS-claimed protocol)
+  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s <= from.cap;
        s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    if (from.tags[s] != 2u) continue;
+    if (from.states[s * from.words] == 0) continue;
     uint64_t key[kMaxKeyWords];
     for (uint32_t i = 0; i < from.key_words; ++i) key[i] = from.keys[s * from.key_words + i];
     const int64_t d = table_upsert_rt(key, from.key_words, to);

@@ -35,8 +35,12 @@ __global__ void k_join_rehash(const JoinSlot *from, uint64_t from_cap, JoinSlot 
     const JoinSlot s = from[i];
     if (s.row == kEmptyRow) continue;
     uint64_t h = mix64(static_cast<uint64_t>(s.key)) & mask;
-    while (atomicCAS(&to[h].row, kEmptyRow, s.row) != kEmptyRow) h = (h + 1) & mask;
-    to[h].key = s.key;
+    for (;;) {
+      uint64_t ok, orow;
+      cas128(&to[h], 0ull, kEmptyRow, static_cast<uint64_t>(s.key), s.row, ok, orow);
+      if (orow == kEmptyRow) break;
+      h = (h + 1) & mask;
+    }
   }
 }
 

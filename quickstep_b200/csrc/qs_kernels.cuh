@@ -496,36 +496,96 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
 }
 
 // ============================================================ K7  scan_groupby
-// Find-or-insert `key` (kw words); returns the slot or -1 when the table is full.
+// The hash GROUP BY table is an open-addressing array of cap + 1 rows: keys[slot][KW], states[slot][words].
+//
+// Keys of one or two words (<= 16 bytes: Q3's (l_orderkey, o_orderdate, o_shippriority)) are claimed AND published by
+// ONE compare-and-swap on the key itself -- 64-bit, or the 128-bit ATOMG.CAS.128 of sm_90+ -- from the all-ones
+// "empty" pattern: the value that comes back says empty-now-mine / same key / other key, so a probe step is a single
+// atomic with no tag word, no separate key read and no fence.  (The tag protocol it replaces -- CAS a tag, write the
+// key words, __threadfence, publish the tag -- showed 43 membar and 76 long-scoreboard stall cycles per issued
+// instruction in ncu, at 4 % issue utilisation.)  A key that IS all ones lives in the reserved row `cap`.
+// Wider keys (3-4 words) keep the tag protocol.
+constexpr uint64_t kEmptyKeyWord = ~0ull;
+
+// One probe step of a CAS-claimed table: 0 = the key now sits in `slot` (newly inserted: *inserted = true), 1 = `slot`
+// holds another key.
 template <uint32_t KW>
-__device__ __forceinline__ int64_t table_upsert(const uint64_t *key, const AggDesc &A) {
+__device__ __forceinline__ int key_claim(const uint64_t *key, uint64_t slot, const AggDesc &A, bool *inserted) {
+  static_assert(KW == 1 || KW == 2, "CAS-claimed keys are one or two words");
+  if constexpr (KW == 1) {
+    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&A.keys[slot]),
+                                             static_cast<unsigned long long>(kEmptyKeyWord), static_cast<unsigned long long>(key[0]));
+    *inserted = old == kEmptyKeyWord;
+    return (old == kEmptyKeyWord || old == key[0]) ? 0 : 1;
+  } else {
+    uint64_t o0, o1;
+    cas128(&A.keys[slot * 2], kEmptyKeyWord, kEmptyKeyWord, key[0], key[1], o0, o1);
+    *inserted = o0 == kEmptyKeyWord && o1 == kEmptyKeyWord;
+    return (*inserted || (o0 == key[0] && o1 == key[1])) ? 0 : 1;
+  }
+}
+
+template <uint32_t KW>
+__device__ __forceinline__ bool key_is_empty_pattern(const uint64_t *key) {
+  bool e = true;
+#pragma unroll
+  for (uint32_t i = 0; i < KW; ++i) e &= key[i] == kEmptyKeyWord;
+  return e;
+}
+
+template <uint32_t KW>
+__device__ __forceinline__ uint64_t key_home(const uint64_t *key, uint64_t mask) {
   uint64_t h = 0x9e3779b97f4a7c15ull;
 #pragma unroll
   for (uint32_t i = 0; i < KW; ++i) h = mix64(h ^ key[i]);
+  return h & mask;
+}
+
+// The reserved row of the all-ones key: counted as a group the first time anybody lands on it.
+__device__ __forceinline__ int64_t reserved_slot(const AggDesc &A) {
+  if (atomicCAS(&A.n_groups[1], 0u, 1u) == 0u) atomicAdd(A.n_groups, 1u);
+  return static_cast<int64_t>(A.cap);
+}
+
+// Find-or-insert `key` (kw words); returns the slot or -1 when the table is full.
+template <uint32_t KW>
+__device__ __forceinline__ int64_t table_upsert(const uint64_t *key, const AggDesc &A) {
   const uint64_t mask = A.cap - 1;
-  uint64_t slot = h & mask;
-  volatile uint32_t *tags = A.tags;
-  volatile uint64_t *keys = A.keys;
-  for (uint64_t probes = 0; probes <= mask;) {
-    const uint32_t t = tags[slot];
-    if (t == 2u) {
-      bool eq = true;
-#pragma unroll
-      for (uint32_t i = 0; i < KW; ++i) eq &= keys[slot * KW + i] == key[i];
-      if (eq) return static_cast<int64_t>(slot);
+  uint64_t slot = key_home<KW>(key, mask);
+  if constexpr (KW <= 2) {
+    if (key_is_empty_pattern<KW>(key)) return reserved_slot(A);
+    for (uint64_t probes = 0; probes <= mask; ++probes) {
+      bool inserted;
+      if (key_claim<KW>(key, slot, A, &inserted) == 0) {
+        if (inserted) atomicAdd(A.n_groups, 1u);
+        return static_cast<int64_t>(slot);
+      }
       slot = (slot + 1) & mask;
-      ++probes;
-      continue;
     }
-    if (t == 0u && atomicCAS(&A.tags[slot], 0u, 1u) == 0u) {
+  } else {
+    volatile uint32_t *tags = A.tags;
+    volatile uint64_t *keys = A.keys;
+    for (uint64_t probes = 0; probes <= mask;) {
+      const uint32_t t = tags[slot];
+      if (t == 2u) {
+        bool eq = true;
 #pragma unroll
-      for (uint32_t i = 0; i < KW; ++i) keys[slot * KW + i] = key[i];
-      __threadfence();
-      tags[slot] = 2u;
-      atomicAdd(A.n_groups, 1u);
-      return static_cast<int64_t>(slot);
+        for (uint32_t i = 0; i < KW; ++i) eq &= keys[slot * KW + i] == key[i];
+        if (eq) return static_cast<int64_t>(slot);
+        slot = (slot + 1) & mask;
+        ++probes;
+        continue;
+      }
+      if (t == 0u && atomicCAS(&A.tags[slot], 0u, 1u) == 0u) {
+#pragma unroll
+        for (uint32_t i = 0; i < KW; ++i) keys[slot * KW + i] = key[i];
+        __threadfence();
+        tags[slot] = 2u;
+        atomicAdd(A.n_groups, 1u);
+        return static_cast<int64_t>(slot);
+      }
+      // busy (or lost the race): look at the same slot again
     }
-    // busy (or lost the race): look at the same slot again
   }
   atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
   return -1;
@@ -549,6 +609,7 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
   GlobalAggSink<Q> sink;
   sink.A = &A;
   VmRegs regs;
+  uint32_t new_groups = 0;       // groups this thread opened, over all its tiles: one counter update per warp per kernel
   scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
     bool valid[kRows];
     tile_valid(S, rt, tile, tid, valid);
@@ -557,32 +618,81 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
     for (int r = 0; r < kRows; ++r) bits[r] = 1u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
+    bool pass[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { pass[r] = valid[r] && (bits[r] & 1u); sink.slot[r] = -1; }
+    if constexpr (Q::strategy == QS_AGG_COLLISION_FREE) {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (!pass[r]) continue;
+        constexpr uint32_t w = Q::key_w(0);
+        const char *src = stage + Q::col_off(Q::key_col(0)) + tile_row(r, tid) * w;
+        const int64_t k = w == 4 ? static_cast<int64_t>(*reinterpret_cast<const int32_t *>(src))
+                                 : *reinterpret_cast<const int64_t *>(src);
+        if (k >= 0 && static_cast<uint64_t>(k) < A.cap) sink.slot[r] = k;
+        else atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+      }
+    } else if constexpr (Q::key_words <= 2) {
+      // CAS-claimed keys, in ROUNDS: one compare-and-swap per still-searching row per round, issued back to back,
+      // so up to kRows random atomics per thread are in flight instead of one
+      constexpr uint32_t KW = Q::key_words;
+      uint64_t key[kRows][KW];
+      uint64_t h[kRows];
+      uint32_t pend = 0;
+      const uint64_t mask = A.cap - 1;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        uint64_t full[kMaxKeyWords];
+        pack_key<Q>(stage, tile_row(r, tid), full);
+#pragma unroll
+        for (uint32_t i = 0; i < KW; ++i) key[r][i] = full[i];
+        h[r] = key_home<KW>(key[r], mask);
+        if (pass[r]) {
+          if (key_is_empty_pattern<KW>(key[r])) sink.slot[r] = reserved_slot(A);
+          else pend |= 1u << r;
+        }
+      }
+      for (uint64_t probes = 0; pend != 0; ++probes) {
+        if (probes > mask) { atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY)); break; }
+        int res[kRows];
+        bool ins[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if ((pend >> r) & 1u) res[r] = key_claim<KW>(key[r], h[r], A, &ins[r]);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (!((pend >> r) & 1u)) continue;
+          if (res[r] == 0) {
+            sink.slot[r] = static_cast<int64_t>(h[r]);
+            pend &= ~(1u << r);
+            if (ins[r]) ++new_groups;
+          } else {
+            h[r] = (h[r] + 1) & mask;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (!pass[r]) continue;
+        uint64_t key[kMaxKeyWords];
+        pack_key<Q>(stage, tile_row(r, tid), key);
+        sink.slot[r] = table_upsert<Q::key_words>(key, A);
+      }
+    }
     bool any = false;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const bool pass = valid[r] && (bits[r] & 1u);
-      sink.slot[r] = -1;
-      if (pass) {
-        if constexpr (Q::strategy == QS_AGG_COLLISION_FREE) {
-          constexpr uint32_t w = Q::key_w(0);
-          const char *src = stage + Q::col_off(Q::key_col(0)) + tile_row(r, tid) * w;
-          const int64_t k = w == 4 ? static_cast<int64_t>(*reinterpret_cast<const int32_t *>(src))
-                                   : *reinterpret_cast<const int64_t *>(src);
-          if (k >= 0 && static_cast<uint64_t>(k) < A.cap) sink.slot[r] = k;
-          else atomicExch(A.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
-        } else {
-          uint64_t key[kMaxKeyWords];
-          pack_key<Q>(stage, tile_row(r, tid), key);
-          sink.slot[r] = table_upsert<Q::key_words>(key, A);
-        }
-        if (sink.slot[r] >= 0)
-          atomicAdd(reinterpret_cast<unsigned long long *>(&A.states[sink.slot[r] * Q::words]), 1ull);
-      }
+      if (sink.slot[r] >= 0)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&A.states[sink.slot[r] * Q::words]), 1ull);
       any |= sink.slot[r] >= 0;
     }
     if (!__any_sync(0xffffffffu, any)) return;
     vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
   });
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, off);
+  if ((tid & 31) == 0 && new_groups) atomicAdd(A.n_groups, new_groups);
 }
 
 // ======================================================= K3 / K4  scan_select
@@ -688,6 +798,17 @@ __device__ __forceinline__ int64_t join_key(const char *stage, uint32_t row) {
 constexpr unsigned long long kEmptyRow = ~0ull;
 constexpr unsigned long long kChainBit = 1ull << 63;     // dense join heads: "more rows follow in next[]"
 
+// 128-bit compare-and-swap (ATOMG.CAS.128, sm_90+) on a 16-byte aligned pair of words: (o0, o1) = old value; the
+// pair becomes (v0, v1) iff it was (c0, c1).
+__device__ __forceinline__ void cas128(void *addr, uint64_t c0, uint64_t c1, uint64_t v0, uint64_t v1, uint64_t &o0, uint64_t &o1) {
+  asm volatile(
+      "{\n.reg .b128 c, v, o;\nmov.b128 c, {%2, %3};\nmov.b128 v, {%4, %5};\n"
+      "atom.global.cas.b128 o, [%6], c, v;\nmov.b128 {%0, %1}, o;\n}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(addr)
+      : "memory");
+}
+
 template <class Q>
 __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K,
                                                 const JoinDesc &J) {
@@ -695,6 +816,7 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
   VmRegs regs;
   const uint64_t mask = J.cap - 1;
   uint32_t inserted = 0;       // this thread's inserts over ALL its tiles: one counter update per warp per kernel
+  bool dup = false;            // met an equal key on the way to a free slot
   scan_tiles<Q>(S, smem, [&](uint32_t tile, const char *stage, const ScanRt &rt) {
     bool valid[kRows];
     tile_valid(S, rt, tile, tid, valid);
@@ -742,18 +864,21 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
       }
       for (uint64_t probes = 0; pend != 0; ++probes) {
         if (probes > mask) { atomicExch(J.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY)); break; }
-        unsigned long long old[kRows];
+        // {key, row} goes in with ONE 128-bit compare-and-swap against the empty slot {0, ~0}: no separate key store,
+        // and what comes back on a collision is the occupant's key -- an equal one means the table holds duplicates
+        uint64_t ok[kRows], orow[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
-          if ((pend >> r) & 1u) old[r] = atomicCAS(&J.slots[h[r]].row, kEmptyRow, row0 + tile_row(r, tid));
+          if ((pend >> r) & 1u)
+            cas128(&J.slots[h[r]], 0ull, kEmptyRow, static_cast<uint64_t>(key[r]), row0 + tile_row(r, tid), ok[r], orow[r]);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
           if (!((pend >> r) & 1u)) continue;
-          if (old[r] == kEmptyRow) {
-            J.slots[h[r]].key = key[r];
+          if (orow[r] == kEmptyRow) {
             pend &= ~(1u << r);
             ++inserted;
           } else {
+            dup |= static_cast<int64_t>(ok[r]) == key[r];
             h[r] = (h[r] + 1) & mask;
           }
         }
@@ -764,6 +889,9 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, off);
   if ((tid & 31) == 0 && inserted) atomicAdd(J.n_entries, static_cast<unsigned long long>(inserted));
+  // n_entries[1]: "some key occurs more than once".  While it is 0 a probe stops at its first match instead of walking
+  // on to the end of the (non-existent) duplicate run -- half the random accesses of a primary-key join.
+  if (__any_sync(0xffffffffu, dup) && (tid & 31) == 0) J.n_entries[1] = 1ull;
 }
 
 // ============================================================== K6 join probe
@@ -846,6 +974,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
   const uint64_t mask = J.cap - 1;
   constexpr bool has_residual = Q::n_mid > Q::n_pred;
   constexpr bool outer = Q::j_type == QS_JOIN_LEFT_OUTER;
+  const bool unique_keys = !Q::j_dense && *reinterpret_cast<const volatile unsigned long long *>(&J.n_entries[1]) == 0ull;
   // a LEFT OUTER join emits its matches exactly like an inner join, then the probe rows that never matched
   constexpr bool inner = Q::j_type == QS_JOIN_INNER || outer;
 
@@ -893,15 +1022,36 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
             // never carry the bit, so the walk ends at the kEmptyRow stored by the first insert)
             h[r] = (first_step && !(h[r] & kChainBit)) ? kEmptyRow : J.next[h[r] & ~kChainBit];
           }
-        } else
-        for (uint64_t probes = 0; probes <= mask; ++probes) {
-          const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(&J.slots[h[r]]);
-          if (s.y == kEmptyRow) { active[r] = false; break; }
-          h[r] = (h[r] + 1) & mask;
-          if (static_cast<int64_t>(s.x) == key[r]) { found[r] = true; sink.brow[r] = s.y; break; }
         }
-        if (!found[r]) active[r] = false;
-        any |= found[r];
+        if constexpr (Q::j_dense) {
+          if (!found[r]) active[r] = false;
+          any |= found[r];
+        }
+      }
+      if constexpr (!Q::j_dense) {
+        // open addressing, step by step: every step loads the next slot of EACH row that is still searching (up to
+        // kRows independent 16-byte loads in flight), then looks at what came back
+        uint32_t search = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) if (active[r]) search |= 1u << r;
+        for (uint64_t probes = 0; search != 0 && probes <= mask; ++probes) {
+          ulonglong2 s[kRows];
+#pragma unroll
+          for (int r = 0; r < kRows; ++r)
+            if ((search >> r) & 1u) s[r] = *reinterpret_cast<const ulonglong2 *>(&J.slots[h[r]]);
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            if (!((search >> r) & 1u)) continue;
+            if (s[r].y == kEmptyRow) { active[r] = false; search &= ~(1u << r); continue; }
+            h[r] = (h[r] + 1) & mask;
+            if (static_cast<int64_t>(s[r].x) == key[r]) { found[r] = true; sink.brow[r] = s[r].y; search &= ~(1u << r); }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (!found[r] || unique_keys) active[r] = false;     // unique keys: the first match is the only one
+          any |= found[r];
+        }
       }
       first_step = false;
       if (!__syncthreads_or(any)) break;
