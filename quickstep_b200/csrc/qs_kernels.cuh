@@ -36,6 +36,17 @@
 namespace qs {
 
 // ------------------------------------------------------------ small helpers
+// 128-bit compare-and-swap (ATOMG.CAS.128, sm_90+) on a 16-byte aligned pair of words: (o0, o1) = old value; the
+// pair becomes (v0, v1) iff it was (c0, c1).
+__device__ __forceinline__ void cas128(void *addr, uint64_t c0, uint64_t c1, uint64_t v0, uint64_t v1, uint64_t &o0, uint64_t &o1) {
+  asm volatile(
+      "{\n.reg .b128 c, v, o;\nmov.b128 c, {%2, %3};\nmov.b128 v, {%4, %5};\n"
+      "atom.global.cas.b128 o, [%6], c, v;\nmov.b128 {%0, %1}, o;\n}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(addr)
+      : "memory");
+}
+
 template <uint32_t W>
 __device__ __forceinline__ uint64_t load_bytes(const char *p) {
   if constexpr (W == 1) return static_cast<uint64_t>(*reinterpret_cast<const unsigned char *>(p));
@@ -797,17 +808,6 @@ __device__ __forceinline__ int64_t join_key(const char *stage, uint32_t row) {
 // warp-ballot compaction and the VM stay CTA-uniform even with duplicate keys.
 constexpr unsigned long long kEmptyRow = ~0ull;
 constexpr unsigned long long kChainBit = 1ull << 63;     // dense join heads: "more rows follow in next[]"
-
-// 128-bit compare-and-swap (ATOMG.CAS.128, sm_90+) on a 16-byte aligned pair of words: (o0, o1) = old value; the
-// pair becomes (v0, v1) iff it was (c0, c1).
-__device__ __forceinline__ void cas128(void *addr, uint64_t c0, uint64_t c1, uint64_t v0, uint64_t v1, uint64_t &o0, uint64_t &o1) {
-  asm volatile(
-      "{\n.reg .b128 c, v, o;\nmov.b128 c, {%2, %3};\nmov.b128 v, {%4, %5};\n"
-      "atom.global.cas.b128 o, [%6], c, v;\nmov.b128 {%0, %1}, o;\n}"
-      : "=l"(o0), "=l"(o1)
-      : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(addr)
-      : "memory");
-}
 
 template <class Q>
 __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, const Lits &L, const SinkDesc &K,
