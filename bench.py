@@ -12,8 +12,9 @@ lineitem is block-partitioned on l_orderkey boundaries over the ranks and orders
 (STRONG scaling: the job is the same at every N).  A "step" is one complete query, admit -> result rows on the
 host, with the relations resident in HBM:
   Q1, Q6   per-rank scan + aggregate, partial states merged with NCCL inside the C ABI (qsgpu_agg_merge_all)
-  Q3       customer LIP filter OR-reduced over the ranks, filtered orders all-gathered (broadcast join), lineitem
-           probed locally, per-rank top-10 candidates gathered
+  Q3       customer LIP filter OR-reduced over the ranks, orders joined with lineitem partition-wise (they are
+           co-partitioned on the order key) or, as `q3_broadcast_join`, with the filtered orders all-gathered to every
+           rank; per-rank top-10 candidates gathered
 Every query's answer is compared with the CPU oracle run over the WHOLE database (rank 0; all rows of all three
 answers; counts and keys exact, double sums to 1e-9 relative).  Prints ONE JSON line (rank 0).
 """
@@ -290,7 +291,10 @@ def main():
     my_rows = len(host["lineitem"][0])
     log(f"generated: {n:,} lineitem rows in the database, {my_rows:,} on this rank")
 
-    db = H.Database(local, num_workers=args.workers)
+    # Worker threads per rank: they poll for work while a query is in flight, so never more than this rank's share of
+    # the host cores (8 ranks x 4 workers would oversubscribe a 32-core host)
+    n_workers = max(1, min(args.workers, (os.cpu_count() or 4) // world - 2))
+    db = H.Database(local, num_workers=n_workers)
     if comm is not None:
         db.set_comm(comm.h)
     t_load = time.perf_counter()
@@ -336,6 +340,15 @@ def main():
         t3 = timed(q3, q3_steps, args.warmup)
     clocks = clk.summary()
     log(f"timed: q1 {t1[0]:.3f} ms, q6 {t6[0]:.3f} ms, q3 {t3[0]:.3f} ms")
+    # N > 1: Q3 again with the build side BROADCAST (filtered orders all-gathered, every GPU builds the whole table)
+    # instead of joined partition-wise: what a build side that is not co-partitioned with lineitem needs
+    t3b = None
+    if world > 1:
+        db.set_join_mode(1)
+        t3b = timed(q3, q3_steps, args.warmup)
+        db.set_join_mode(0)
+        check_q3(t3b[3], t3[3])
+        log(f"q3 with a broadcast build side: {t3b[0]:.3f} ms")
 
     # ---- kernel-only times, CUDA events around each launch (timing mode: every launch waits for its kernel)
     peak, peak_src = measured_peak()
@@ -508,13 +521,15 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t1[1], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, n), "total_rows": n, "rows_per_gpu": my_rows,
-                       "partitioning": f"lineitem block-partitioned on l_orderkey boundaries over {world} GPU(s); orders / customer in shares",
+                       "partitioning": f"lineitem block-partitioned on l_orderkey boundaries over {world} GPU(s); orders / customer in shares "
+                                       "(orders co-partitioned with lineitem: Q3 joins partition-wise; q3_broadcast_join all-gathers the build side instead)",
                        "path": "libqshost.so (C++ RelationalOperator / WorkOrder layer, Foreman + Workers) -> libqsgpu.so C ABI; "
                                "cross-GPU merges inside the C ABI (NCCL)",
+                       "host_workers_per_rank": n_workers,
                        "l2": f"inputs ({my_rows * T.Q1_BYTES_PER_ROW / 1e9:.1f} GB per GPU) larger than L2 (126 MB); no flush needed",
                        "timing": "CUDA events on the library stream around K whole queries (kernels + collectives + result read); max over ranks"},
             "rows_per_s": n / (t1[0] * 1e-3),
-            "query_ms": {"q1": t1[0], "q6": t6[0], "q3": t3[0]},
+            "query_ms": {"q1": t1[0], "q6": t6[0], "q3": t3[0], **({"q3_broadcast_join": t3b[0]} if t3b else {})},
             "query_wall_ms": {"q1": t1[1], "q6": t6[1], "q3": t3[1]},
             "kernels_ms": {"q1": k1, "q6": k6, "q3": k3},
             "hbm_frac": {"q1": roof_q1["frac"], "q6": roof_q6["frac"], "q3_lineitem_select": roof_q3["frac"],

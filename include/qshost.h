@@ -39,6 +39,12 @@ int qshost_db_destroy(qshost_db_t db);
  * (Q1, Q6), LIP filters OR-reduced, the filtered orders all-gathered for a broadcast join and the per-rank top-k
  * candidates gathered (Q3) -- all inside the C++ operator layer, through the collectives of the C ABI. */
 int qshost_db_set_comm(qshost_db_t db, void *comm);
+/* Q3's join with several GPUs.  0 (default): partition-wise -- orders and lineitem are partitioned on the order key by the
+ * same scheme (the caller loads, on every rank, the lineitem rows of exactly the orders it loads there), so every GPU
+ * builds and probes the hash table of its own partition (the reference's per-partition hash tables,
+ * query_execution/QueryContext.cpp:78-97).  1: broadcast -- the filtered orders of all ranks are all-gathered and every
+ * GPU builds the whole table (what a build side partitioned any other way needs). */
+int qshost_db_set_join_mode(qshost_db_t db, int mode);
 /* COPY ... + \analyze: cut native-width columns into storage blocks of rows_per_block
  * tuples in `layout`, and record min/max of the key attributes.  May be called again
  * for the same relation to replace it. */

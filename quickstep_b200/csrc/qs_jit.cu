@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <sstream>
 #include <vector>
@@ -221,12 +222,80 @@ int jit_compile_only(const std::string &source, std::string *cubin, std::string 
   return QSGPU_OK;
 }
 
+// Binary description of everything jit_source() prints, field for field: the key of the hot in-memory cache.  Printing
+// the source (a few KB through an ostringstream) and looking a multi-KB string up cost ~20 us per launch, on the
+// critical path of every query (the scan cannot start before its kernel is found); this is a few hundred bytes.
+// QSGPU_JIT_VERIFY=1 re-prints the source on every hit and checks it is the one the kernel was compiled from (the
+// test suite runs with it): the two descriptions cannot drift apart unnoticed.
+static std::string jit_key(const JitSpec &sp) {
+  std::string k;
+  k.reserve(512);
+  auto put = [&](uint64_t v, int bytes) { k.append(reinterpret_cast<const char *>(&v), static_cast<size_t>(bytes)); };
+  const ScanDesc &S = *sp.S;
+  const Program &P = *sp.P;
+  put(static_cast<uint64_t>(sp.family), 1); put(static_cast<uint64_t>(sp.hot), 2); put(static_cast<uint64_t>(sp.priv), 1);
+  put(static_cast<uint64_t>(sp.ctas_per_sm > 2 ? 2 : sp.ctas_per_sm), 1);
+  put(S.n_cols, 4); put(S.n_stages, 4); put(S.stage_bytes, 4);
+  for (uint32_t c = 0; c < S.n_cols; ++c) {
+    const ColDesc &C = S.cols[c];
+    put(C.width, 4); put(C.smem_off, 4); put(C.cw, 1); put(C.code_off, 4); put(C.expand, 1); put(C.dict_smem, 1); put(C.dict_soff, 4);
+  }
+  put(P.n_pred, 4); put(P.n_mid, 4); put(P.n_total, 4);
+  for (uint32_t i = 0; i < P.n_total; ++i) {
+    const Instr &in = P.code[i];
+    put(in.op, 1); put(in.type, 1); put(in.leaf, 1); put(in.ltype, 1); put(in.arg, 2); put(in.flags, 1); put(in.aux, 1);
+  }
+  put(S.n_lip, 4);
+  for (uint32_t i = 0; i < S.n_lip; ++i) { put(S.lip[i].kind, 4); put(S.lip[i].is_anti, 4); }
+  if (sp.A) {
+    const AggDesc &A = *sp.A;
+    put(1, 1); put(A.n_agg, 4); put(A.strategy, 4); put(A.n_key_cols, 4); put(A.key_words, 4);
+    for (uint32_t i = 0; i < A.n_agg; ++i) put(A.kind[i], 1);
+    for (uint32_t i = 0; i < A.n_key_cols; ++i) { put(A.key_col[i], 2); put(A.key_width[i], 1); put(A.key_off[i], 1); }
+  } else put(0, 1);
+  if (sp.K) {
+    const SinkDesc &K = *sp.K;
+    put(1, 1); put(K.n_out, 4); put(K.n_lip_build, 4);
+    for (uint32_t i = 0; i < K.n_out; ++i) put(K.out_width[i], 1);
+    for (uint32_t i = 0; i < K.n_lip_build; ++i) { put(K.lip_build_col[i], 2); put(K.lip_build_ltype[i], 1); put(K.lip_build[i].kind, 4); }
+  } else put(0, 1);
+  if (sp.J) {
+    const JoinDesc &J = *sp.J;
+    put(1, 1); put(J.key_col, 2); put(J.join_type, 1); put(J.key_ltype, 1); put(J.dense, 4); put(J.key2_present, 1); put(J.key2_col, 2);
+    put(J.n_build_cols, 4);
+    for (uint32_t i = 0; i < J.n_build_cols; ++i) { put(J.build_cols[i].width, 4); put(J.build_cols[i].cw, 1); }
+  } else put(0, 1);
+  return k;
+}
+
+static std::unordered_map<std::string, std::pair<JitKernel *, std::string>> g_by_key;   // key -> (kernel, its source)
+
 int jit_get(const JitSpec &spec, JitKernel **out) {
+  const std::string key = jit_key(spec);
+  {
+    std::lock_guard<std::mutex> lk(g_jit_mutex);
+    auto hit = g_by_key.find(key);
+    if (hit != g_by_key.end()) {
+      static const bool verify = std::getenv("QSGPU_JIT_VERIFY") != nullptr;
+      if (verify && jit_source(spec) != hit->second.second) {
+        set_error(QSGPU_ERR_INVALID, "internal: jit_key() and jit_source() disagree (a field printed by one is missing in the other)");
+        return QSGPU_ERR_INVALID;
+      }
+      ++g_mem_hits;
+      *out = hit->second.first;
+      return QSGPU_OK;
+    }
+  }
   std::string kernel_name;
   const std::string source = jit_source(spec, &kernel_name);
   std::lock_guard<std::mutex> lk(g_jit_mutex);
   auto it = g_kernels.find(source);
-  if (it != g_kernels.end()) { ++g_mem_hits; *out = it->second.get(); return QSGPU_OK; }
+  if (it != g_kernels.end()) {
+    ++g_mem_hits;
+    *out = it->second.get();
+    g_by_key.emplace(key, std::make_pair(it->second.get(), source));
+    return QSGPU_OK;
+  }
 
   const std::string name = cache_name(source);
   const std::string dir = cache_dir();
@@ -255,6 +324,7 @@ int jit_get(const JitSpec &spec, JitKernel **out) {
   e = cudaLibraryGetKernel(&k->fn, k->lib, kernel_name.c_str());
   if (e != cudaSuccess) return cuda_fail(e, "cudaLibraryGetKernel(query kernel)");
   *out = k.get();
+  g_by_key.emplace(key, std::make_pair(k.get(), source));
   g_kernels.emplace(source, std::move(k));
   return QSGPU_OK;
 }

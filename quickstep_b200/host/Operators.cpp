@@ -122,11 +122,19 @@ void BuildLIPFilterWorkOrder::execute() {
 bool BuildHashOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,
                                          StorageManager *storage_manager, const tmb::client_id, tmb::MessageBus *) {
   std::vector<DeviceExtent> extents = feed_.take(storage_manager);
-  if (!extents.empty() && storage_manager->multiDevice() && storage_manager->isPartitioned(feed_.relation().getID())) {
-    // Broadcast join (SURVEY.md section 8e "Join, small build"): the build side was filtered in shares; its rows
-    // are all-gathered so that every device builds its own copy of the table and probes its partition of the
-    // probe side locally, with no shuffle.  The reference builds ONE table all probing threads share
-    // (query_execution/QueryContext.cpp:78-97).  Needs the complete input: blocking edge in the plan.
+  const bool partitioned_input = storage_manager->multiDevice() && storage_manager->isPartitioned(feed_.relation().getID());
+  if (!extents.empty() && partitioned_input && num_partitions_ > 1) {
+    // Partition-wise join: build and probe side are partitioned on the join key by the same scheme, so every
+    // device builds the table of ITS partition and probes it with its partition of the probe side -- the
+    // reference's own mechanism for partitioned relations (num_partitions hash tables, one per partition,
+    // query_execution/QueryContext.cpp:78-97; BuildHashOperator.hpp `num_partitions`).  No rows cross devices, and
+    // a LIP filter filled here is complete for every probe row this device will ever see.
+    query_context->noteLIPFiltersBuiltFrom(lip_deployment_index_, false);
+  } else if (!extents.empty() && partitioned_input) {
+    // Broadcast join (SURVEY.md section 8e "Join, small build"): ONE logical table (num_partitions == 1) whose
+    // build side was filtered in shares; its rows are all-gathered so that every device builds its own copy of
+    // the table and probes its partition of the probe side locally, with no shuffle.  Needs the complete input:
+    // the operator runs once its producer has finished.
     QS_CHECK(feed_.relation().isTemporary() && done_feeding_input_relation_);
     DeviceExtent all;
     all.relation = storage_manager->replicated(feed_.relation());

@@ -52,6 +52,10 @@ struct qshost_db {
   std::uint64_t rows[3] = {0, 0, 0};          // this rank's rows
   std::uint64_t global_rows[3] = {0, 0, 0};   // rows of the whole relation (== rows[] on one device)
   qsgpu_comm_t comm = nullptr;
+  // Several devices: orders and lineitem are partitioned on the order key by the same scheme (every rank holds the
+  // lineitem rows of exactly the orders it holds), so Q3's join can run partition-wise.  0 = use that (default),
+  // 1 = ignore it and broadcast the build side (what a build side partitioned any other way needs).
+  int join_mode = 0;
   // what \analyze records and AttachLIPFilters / InjectJoinFilters read (exact min/max statistics)
   std::int64_t c_custkey_min = 0, c_custkey_max = 0, o_orderkey_min = 0, o_orderkey_max = 0;
   std::string last_profile;
@@ -102,6 +106,12 @@ int qshost_db_destroy(qshost_db_t db) {
 int qshost_db_set_comm(qshost_db_t db, void *comm) {
   db->comm = static_cast<qsgpu_comm_t>(comm);
   db->sm->setCommunicator(db->comm);
+  return 0;
+}
+
+int qshost_db_set_join_mode(qshost_db_t db, int mode) {
+  if (mode < 0 || mode > 1) return QSGPU_ERR_INVALID;
+  db->join_mode = mode;
   return 0;
 }
 
@@ -353,8 +363,14 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   const auto dst2 = ctx.addInsertDestination(t2, n_orders), dst0 = ctx.addInsertDestination(t0, n_lineitem),
              dst4 = ctx.addInsertDestination(t4, n_lineitem), dst7 = ctx.addInsertDestination(t7, 1),
              dst9 = ctx.addInsertDestination(t9, 10);
-  // the build side is replicated on every device (broadcast join): sized for the whole relation
-  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, db->global_rows[QSHOST_ORDERS] / 4));
+  // Several devices: partition-wise join (one hash table per partition = per device, the reference's num_partitions)
+  // when orders and lineitem are co-partitioned on the order key, else ONE logical table whose build side is
+  // all-gathered to every device (broadcast join) and therefore sized for the whole relation.
+  int n_ranks = 1;
+  QS_CHECK_GPU(qsgpu_comm_rank(db->comm, nullptr, &n_ranks));
+  const std::size_t join_partitions = (n_ranks > 1 && db->join_mode == 0) ? static_cast<std::size_t>(n_ranks) : 1u;
+  const std::uint64_t build_rows = join_partitions > 1 ? n_orders : db->global_rows[QSHOST_ORDERS];
+  const auto ht = ctx.addJoinHashTable(QS_INT, std::max<std::uint64_t>(1024, build_rows / 4));
 
   QueryContext::ScalarGroup s4;     // l_orderkey, o_orderdate, o_shippriority, l_extendedprice, l_discount
   s4.roots = {s4.exprs.attr(0, kInt), s4.exprs.attr(1, kDate, 2), s4.exprs.attr(2, kInt, 2), s4.exprs.attr(1, kDouble),
@@ -382,11 +398,11 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
   op1->deployLIPFilters(d1, {f_cust});
   auto *op2 = new SelectOperator(query_id, orders, false, *t2, dst2, pid2, std::vector<attribute_id>{O_ORDERKEY, O_ORDERDATE, O_SHIPPRIORITY}, true);
   op2->deployLIPFilters(d2, {f_cust});
-  auto *op3 = new BuildHashOperator(query_id, *t2, false, {0}, false, 1, ht);
+  auto *op3 = new BuildHashOperator(query_id, *t2, false, {0}, false, join_partitions, ht);
   op3->deployLIPFilters(d3, {f_ord});
   auto *op0 = new SelectOperator(query_id, lineitem, false, *t0, dst0, pid0, std::vector<attribute_id>{L_ORDERKEY, L_EXTENDEDPRICE, L_DISCOUNT}, true);
   op0->deployLIPFilters(d0, {f_ord});
-  auto *op4 = new HashJoinOperator(query_id, *t2, *t0, false, {0}, false, 1, false, *t4, dst4, ht, QueryContext::kInvalidPredicateId, sel4);
+  auto *op4 = new HashJoinOperator(query_id, *t2, *t0, false, {0}, false, join_partitions, false, *t4, dst4, ht, QueryContext::kInvalidPredicateId, sel4);
   const auto i1 = plan.addRelationalOperator(op1), i2 = plan.addRelationalOperator(op2), i3 = plan.addRelationalOperator(op3),
              i0 = plan.addRelationalOperator(op0), i4 = plan.addRelationalOperator(op4);
   const auto i5 = plan.addRelationalOperator(new DestroyHashOperator(query_id, 1, ht));

@@ -31,6 +31,7 @@ SIGNATURES = {
     "qshost_db_create": [C.c_int, C.c_int, C.POINTER(_VP)],
     "qshost_db_destroy": [_VP],
     "qshost_db_set_comm": [_VP, _VP],
+    "qshost_db_set_join_mode": [_VP, C.c_int],
     "qshost_db_load": [_VP, C.c_int, C.POINTER(_VP), C.c_uint64, C.c_uint64, C.c_int],
     "qshost_db_evict": [_VP, C.c_int],
     "qshost_db_stats": [_VP, C.c_int, _U64P, _U64P, _U64P],
@@ -80,6 +81,10 @@ class Database:
     def set_comm(self, comm):
         """comm: a qsgpu_comm_t (engine.Comm.h); relations loaded afterwards are this rank's partitions."""
         A.check(load().qshost_db_set_comm(self.h, comm))
+
+    def set_join_mode(self, mode: int):
+        """0: partition-wise join of co-partitioned orders / lineitem (default); 1: broadcast the build side."""
+        A.check(load().qshost_db_set_join_mode(self.h, mode))
 
     def evict(self, which):
         A.check(load().qshost_db_evict(self.h, which))

@@ -9,6 +9,10 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+# every in-memory hit of the query compiler's fast cache re-prints the kernel source and compares (qs_jit.cu jit_key)
+os.environ.setdefault("QSGPU_JIT_VERIFY", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 

@@ -57,7 +57,10 @@ def main():
         for _ in range(2):          # twice: the second run reuses every cached object
             B.check_q1(db.q1()[0], OT.q1(tables["lineitem"]))
             B.check_q6(db.q6()[:2], OT.q6(tables["lineitem"]))
-            B.check_q3(db.q3()[0], OT.q3(tables, D.q3_stats(tables)))
+            for join_mode in (0, 1):        # partition-wise join, then the broadcast build side
+                db.set_join_mode(join_mode)
+                B.check_q3(db.q3()[0], OT.q3(tables, D.q3_stats(tables)))
+            db.set_join_mode(0)
     db.destroy()
 
     # ---------------------------------------------------------------- qsgpu_agg_merge_all, table strategies
