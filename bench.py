@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle: no parity check, no cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true", help="skip the hash-join microbench (configs[4])")
+    ap.add_argument("--no-ref-engine", action="store_true", help="skip the run of the unmodified reference engine at SF1")
     ap.add_argument("--no-coded", action="store_true", help="skip the code-resident (dictionary codes in HBM) runs")
     ap.add_argument("--join-build-rows", type=int, default=1 << 26)
     ap.add_argument("--join-probe-rows", type=int, default=1 << 30)
@@ -514,6 +515,50 @@ def main():
             join = {"error": repr(ex)}
         log("join microbench done")
 
+    # ---- the UNMODIFIED reference engine on this host's cores (north_star: "the reference's own multi-threaded CPU path
+    # timed on the B200 host's cores in the same run").  SF100 does not fit its loader in a bench run (75 GB of .tbl
+    # text), so it is run at SF1 -- BASELINE.json configs[0]'s size -- with benchmarks/tpch/run-benchmark.sh's procedure
+    # (5 runs, mean of the middle 3), next to the oracle port on an SF1-sized relation: the pair calibrates the port
+    # the SF100 cpu_baseline is measured with.  Nothing is extrapolated.
+    ref_engine = None
+    if rank == 0 and world == 1 and not args.no_ref_engine:
+        try:
+            import shutil
+            import tempfile
+            import ref_engine as R
+            if R.available():
+                cores = os.cpu_count() or 1
+                store = tempfile.mkdtemp(prefix="qs_store_")
+                try:
+                    w0 = time.perf_counter()
+                    R.load("1", store, workers=cores)
+                    load_s = time.perf_counter() - w0
+                    tm = R.time_queries(store, workers=cores)
+                    q6_rows, _ = R.run_query(store, "06", workers=cores)
+                finally:
+                    shutil.rmtree(store, ignore_errors=True)
+                import qs_oracle as O
+                import oracle_tpch as OT
+                O.load(); O.set_workers(cores); O.set_block_rows(BLOCK_ROWS)
+                sh1 = S.db_shape(SF_ROWS[1])
+                t1h = S.host_tables(S.generate_host(sh1, range(sh1["n_chunks"]), SEED, device))
+                port = {}
+                for nm, fn in (("q1", lambda: OT.q1(t1h["lineitem"])), ("q6", lambda: OT.q6(t1h["lineitem"]))):
+                    fn()
+                    w0 = time.perf_counter()
+                    for _ in range(5):
+                        fn()
+                    port[nm] = (time.perf_counter() - w0) * 1e3 / 5
+                ref_engine = {"binary": "oracle/_ref/quickstep_cli_shell (unmodified reference, Release, built by oracle/build_ref.sh)",
+                              "sf": 1, "cores": cores, "load_s": load_s, "query_ms": {"q1": tm["01"]["ms"], "q6": tm["06"]["ms"], "q3": tm["03"]["ms"]},
+                              "runs_ms": {k: v["runs_ms"] for k, v in tm.items()}, "q6_revenue_printed": q6_rows[0][0] if q6_rows else None,
+                              "procedure": "dbgen -s 1 -> COPY -> \\analyze -> each query 5x, printing off, mean of the middle 3 (benchmarks/tpch/process.py)",
+                              "oracle_port_sf1_ms": port,
+                              "port_speedup_over_engine": {k: tm[{"q1": "01", "q6": "06"}[k]]["ms"] / port[k] for k in port}}
+                log(f"reference engine at SF1 on {cores} cores: q1 {tm['01']['ms']:.1f} ms, q6 {tm['06']['ms']:.1f} ms, q3 {tm['03']['ms']:.1f} ms")
+        except Exception as ex:
+            ref_engine = {"error": repr(ex)}
+
     if rank == 0:
         sf100 = n == SF_ROWS[100]
         line = {
@@ -540,7 +585,7 @@ def main():
                          "q6_whole_query": my_rows * T.Q6_BYTES_PER_ROW / (t6[0] * 1e-3) / 1e9 / peak},
             "roofline": roof_q1, "rooflines": {"q1": roof_q1, "q6": roof_q6, "q3": roof_q3},
             "dictionary_coded": coded, "join_microbench": join,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "cpu_baseline": cpu, "reference_engine": ref_engine, "e2e": e2e, "clocks": clocks,
             "gpu_launches": t1[2], "gpu_launches_per_query": launches_per_query,
             "result_check": {"parity": parity, "q1_groups": len(t1[3]), "q1_count": sum(int(r["count_order"]) for r in t1[3]),
                              "q6_revenue": t6[3][0], "q3_first_row": list(t3[3][0]) if t3[3] else None,

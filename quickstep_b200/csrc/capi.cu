@@ -686,6 +686,13 @@ int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t 
   QS_CUDA(dev_malloc(&C.d_dict, bytes));
   QS_CUDA(cudaMemsetAsync(C.d_dict, 0, bytes, d->stream));
   C.h_dict.assign(dv, dv + static_cast<size_t>(n_entries) * w);
+  if (rel->attrs[attr].type == QS_DATE)      // DateLit padding is not initialised by the reference: canonical zeros
+    for (uint32_t e = 0; e < n_entries; ++e) { C.h_dict[static_cast<size_t>(e) * 8 + 6] = 0; C.h_dict[static_cast<size_t>(e) * 8 + 7] = 0; }
+  if (rel->attrs[attr].type == QS_CHAR)      // ... nor the bytes behind a CHAR(n) value's terminator
+    for (uint32_t e = 0; e < n_entries; ++e) {
+      bool ended = false;
+      for (uint32_t b = 0; b < w; ++b) { char &c = C.h_dict[static_cast<size_t>(e) * w + b]; if (ended) c = 0; else ended = c == 0; }
+    }
   QS_CUDA(cudaMemcpyAsync(C.d_dict, C.h_dict.data(), C.h_dict.size(), cudaMemcpyHostToDevice, d->stream));
   QS_CUDA(cudaStreamSynchronize(d->stream));
   if (rel->owns_memory) {   // the column now holds codes: give the native-width buffer back
@@ -869,6 +876,10 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
         set_error(QSGPU_ERR_INVALID, "unknown staging encoding");
         rc = QSGPU_ERR_INVALID;
     }
+    // DateLit padding bytes are not initialised by the reference: canonicalise (see k_decode_segments)
+    if (rc == QSGPU_OK && e == cudaSuccess && rel->attrs[s.attr].type == QS_DATE) { e = launch_zero_date_padding(dst, n_rows, d->stream); count_launch(); }
+    // ... and CHAR(n) bytes behind the terminating NUL are not part of the value
+    if (rc == QSGPU_OK && e == cudaSuccess && rel->attrs[s.attr].type == QS_CHAR && w > 1) { e = launch_zero_after_nul(dst, n_rows, w, d->stream); count_launch(); }
     if (rc == QSGPU_OK && e != cudaSuccess) rc = cuda_fail(e, "qsgpu_stage_block");
   }
   cudaStreamSynchronize(d->stream);     // host stripes may be unpinned / reused by the caller
@@ -1000,7 +1011,8 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
         need.emplace_back(static_cast<uint64_t>(hd - h0), dbytes);
       }
       const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
-      g.aligned = (val_al ? 1u : 0u) | (code_al ? 2u : 0u);
+      g.aligned = (val_al ? 1u : 0u) | (code_al ? 2u : 0u) | (rel->attrs[s.attr].type == QS_DATE ? 4u : 0u) |
+                  ((rel->attrs[s.attr].type == QS_CHAR && w > 1) ? 8u : 0u);
       if (B.n_rows) {
         segs.push_back(g);
         cur.tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows;

@@ -92,8 +92,15 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
     const uint64_t r0 = (tile - sg.tile_begin) * kStageTileRows;
     const uint64_t r1 = min(sg.n_rows, r0 + kStageTileRows);
     const bool al = (sg.aligned & 1) != 0;
+    // DATE values are DateLit structs {int32 year; u8 month; u8 day; 2 padding bytes}: the reference never initialises
+    // the padding (its block files carry garbage there), and a group-by / join key is compared as 8 raw bytes on the
+    // device -- so staging canonicalises every date to zero padding
+    const bool date = (sg.aligned & 4) != 0;
+    // CHAR(n) values end at their first NUL (the reference compares them with strncmp and leaves whatever was in memory
+    // behind the terminator): bytes after it are zeroed, so that equal strings are equal bytes
+    const bool chr = (sg.aligned & 8) != 0;
     const uint32_t vw = sg.vw;
-    if (sg.encoding == QS_ENC_PLAIN && al && ((vw * r0) & 15) == 0 &&
+    if (sg.encoding == QS_ENC_PLAIN && al && !date && !chr && ((vw * r0) & 15) == 0 &&
         ((reinterpret_cast<uintptr_t>(sg.src) | reinterpret_cast<uintptr_t>(sg.dst)) & 15) == 0) {
       // 16-byte vector copy of the tile, byte tail
       const uint64_t b0 = r0 * vw, b1 = r1 * vw;
@@ -121,8 +128,42 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
           else *reinterpret_cast<int32_t *>(d) = static_cast<int32_t>(c);
         }
       }
+      if (date) { d[6] = 0; d[7] = 0; }
+      if (chr) {
+        bool ended = false;
+        for (uint32_t b = 0; b < vw; ++b) { if (ended) d[b] = 0; else ended = d[b] == 0; }
+      }
     }
   }
+}
+
+__global__ void k_zero_after_nul(char *col, uint64_t n, uint32_t w) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    char *d = col + i * w;
+    bool ended = false;
+    for (uint32_t b = 0; b < w; ++b) { if (ended) d[b] = 0; else ended = d[b] == 0; }
+  }
+}
+
+cudaError_t launch_zero_after_nul(void *col, uint64_t n, uint32_t w, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int grid = static_cast<int>(std::min<uint64_t>((n + 255) / 256, 148 * 8));
+  k_zero_after_nul<<<grid, 256, 0, st>>>(static_cast<char *>(col), n, w);
+  return cudaGetLastError();
+}
+
+__global__ void k_zero_date_padding(char *col, uint64_t n) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    *reinterpret_cast<uint16_t *>(col + i * 8 + 6) = 0;
+}
+
+cudaError_t launch_zero_date_padding(void *col, uint64_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int grid = static_cast<int>(std::min<uint64_t>((n + 255) / 256, 148 * 8));
+  k_zero_date_padding<<<grid, 256, 0, st>>>(static_cast<char *>(col), n);
+  return cudaGetLastError();
 }
 
 // ---- re-coding tables of dictionary-coded attributes -------------------------------------------------------

@@ -135,6 +135,8 @@ cudaError_t launch_decode_truncated(void *dst, const void *codes, uint64_t n, ui
                                     uint32_t value_width, cudaStream_t st);
 cudaError_t launch_decode_strided(void *dst, const void *slots, uint64_t n, uint32_t stride,
                                   uint32_t value_width, cudaStream_t st);
+cudaError_t launch_zero_date_padding(void *col, uint64_t n, cudaStream_t st);
+cudaError_t launch_zero_after_nul(void *col, uint64_t n, uint32_t w, cudaStream_t st);
 cudaError_t launch_build_recode(const StageSeg *d_segs, uint32_t n_segs, uint32_t *error_flag, cudaStream_t st);
 cudaError_t launch_decode_segments(const StageSeg *d_segs, uint32_t n_segs, uint64_t n_tiles, int sm_count,
                                    cudaStream_t st);

@@ -255,6 +255,20 @@ def _q3_device(engine, tables, stats, info=None):
             r.destroy()
 
 
+def test_tpch_sf001_reference_engine_tables(engine, golden):
+    """dbgen -s 0.01 (committed columns): every cell of the Q1 / Q6 / Q3 tables the unmodified reference engine printed."""
+    import ref_golden as RG
+    rels = {k: engine.Relation.from_host(v) for k, v in golden.items()}
+    try:
+        rev, is_null = T.run_q6(rels["lineitem"])
+        RG.check_q6(rev, is_null, "sf0.01")
+        RG.check_q1(T.run_q1(rels["lineitem"]), "sf0.01")
+        RG.check_q3(T.run_q3(rels["customer"], rels["orders"], rels["lineitem"], D.q3_stats(golden)), "sf0.01")
+    finally:
+        for r in rels.values():
+            r.destroy()
+
+
 def test_tpch_q3_sf001(engine, golden):
     stats = D.q3_stats(golden)
     ginfo, oinfo = {}, {}
@@ -291,6 +305,11 @@ def test_tpch_sf1_reference_answers(engine):
         assert top[0][0] == f["l_orderkey"] and abs(top[0][1] - f["revenue"]) < 1e-4
         otop = OT.q3(tb, D.q3_stats(tb))
         assert [t[0] for t in top] == [t[0] for t in otop]
+        # every cell of the three result tables the reference engine printed for this database
+        import ref_golden as RG
+        RG.check_q6(rev, False, "sf1")
+        RG.check_q1(rows, "sf1")
+        RG.check_q3(top, "sf1")
     finally:
         for r in rels.values():
             r.destroy()

@@ -168,3 +168,24 @@ def test_tpch_sf1_matches_reference_binary(oracle):
     assert top[0][0] == f["l_orderkey"] and abs(top[0][1] - f["revenue"]) < 1e-4
     assert "%04d-%02d-%02d" % top[0][2] == f["o_orderdate"] and top[0][3] == f["o_shippriority"]
     assert len(top) == 10
+
+
+def test_oracle_matches_reference_engine_tables_sf001(golden):
+    """Every cell of the result tables the UNMODIFIED reference engine printed for Q1 / Q3 / Q6 on dbgen -s 0.01
+    (tests/golden/reference_engine_results.json) against the oracle over the committed dbgen columns."""
+    import ref_golden as RG
+    RG.check_q1(OT.q1(golden["lineitem"]), "sf0.01")
+    rev, is_null = OT.q6(golden["lineitem"])
+    RG.check_q6(rev, is_null, "sf0.01")
+    RG.check_q3(OT.q3(golden, D.q3_stats(golden)), "sf0.01")
+
+
+@pytest.mark.skipif(not D.have_dbgen(), reason="oracle/_ref/dbgen not built (reference tree absent)")
+def test_oracle_matches_reference_engine_tables_sf1(oracle):
+    """The same at SF1 (BASELINE.json configs[0]'s size): 4 x 10 cells of Q1, 10 x 4 of Q3, Q6."""
+    import ref_golden as RG
+    tb = D.dbgen_tables(1)
+    RG.check_q1(OT.q1(tb["lineitem"]), "sf1")
+    rev, is_null = OT.q6(tb["lineitem"])
+    RG.check_q6(rev, is_null, "sf1")
+    RG.check_q3(OT.q3(tb, D.q3_stats(tb)), "sf1")
