@@ -253,10 +253,12 @@ uint8_t Lowering::lower_scalar(int i) {
         leaf_ref(n->a, T, &in);
         in.flags = 1;
       } else {
+        // The temporary is chosen AFTER the right operand is lowered: a ScalarSharedExpression that is first used
+        // inside it takes a temporary for the rest of the program, and must not end up sharing this one.
+        const uint8_t t_b = lower_scalar(n->b);
         int k = -1;
         for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
         if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "expression too deep for the VM temporaries"); return T; }
-        const uint8_t t_b = lower_scalar(n->b);
         tmp_busy[k] = true;
         Instr st{};
         st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);
@@ -336,8 +338,13 @@ int dict_code_range(uint16_t attr_type, uint32_t w, const char *dict, uint32_t n
     if (lit->lit.pool_offset + lit->width > str_pool_bytes) { *err = "CHAR literal outside pool"; return QSGPU_ERR_INVALID; }
     std::string l(w, '\0');
     for (uint32_t b = 0; b < w && b < lit->width; ++b) l[b] = str_pool[lit->lit.pool_offset + b];
+    // literal longer than the attribute: the reference compares the full strings ('abc' < 'abcdef'), so an entry that
+    // fills all w bytes and equals the literal's first w bytes is BELOW the literal, never equal to it
+    const bool lit_longer = lit->width > w && str_pool[lit->lit.pool_offset + w] != 0;
     for (uint32_t e = 0; e < n_entries; ++e) {
-      const int r = std::strncmp(dict + static_cast<size_t>(e) * w, l.data(), w);
+      const char *v = dict + static_cast<size_t>(e) * w;
+      int r = std::strncmp(v, l.data(), w);
+      if (r == 0 && lit_longer && std::memchr(v, 0, w) == nullptr) r = -1;
       (r < 0 ? n_lt : r > 0 ? n_gt : n_eq)++;
     }
   } else {
@@ -429,10 +436,9 @@ void Lowering::lower_pred(int i) {
         }
         const uint32_t w = attr->width;
         if (lit->lit.pool_offset + lit->width > ex->str_pool_bytes) { fail(QSGPU_ERR_INVALID, "CHAR literal outside pool"); return; }
-        if (lit->width > w && ex->str_pool[lit->lit.pool_offset + w] != 0) {
-          fail(QSGPU_ERR_UNSUPPORTED, "CHAR literal longer than the attribute");
-          return;
-        }
+        // A literal longer than the attribute (col CHAR(3) vs 'abcdef'): the reference compares the full strings, so
+        // a value equal to the literal's first w bytes is LESS than the literal; flag 4 tells the kernel
+        const bool lit_longer = lit->width > w && ex->str_pool[lit->lit.pool_offset + w] != 0;
         if (n_str + w > static_cast<uint32_t>(kStrPool)) { fail(QSGPU_ERR_UNSUPPORTED, "string pool full"); return; }
         const uint32_t off = n_str;
         for (uint32_t b = 0; b < w; ++b)
@@ -442,6 +448,7 @@ void Lowering::lower_pred(int i) {
         in.arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(attr->a)));
         in.ltype = static_cast<uint8_t>(off);
         in.aux = (attr == l) ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op));
+        in.flags = lit_longer ? 4 : 0;
         push(in);
         return;
       }
@@ -455,10 +462,10 @@ void Lowering::lower_pred(int i) {
         leaf_ref(n->a, T, &in);
         in.flags = 1;
       } else {
+        const uint8_t t_b = lower_scalar(n->b);      // first (see lower_scalar): nested shared expressions claim theirs
         int k = -1;
         for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
         if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "comparison too deep for the VM temporaries"); return; }
-        const uint8_t t_b = lower_scalar(n->b);
         tmp_busy[k] = true;
         Instr st{};
         st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);

@@ -164,15 +164,17 @@ __device__ __forceinline__ bool vcmp(uint8_t c, uint8_t type, uint64_t a, uint64
 
 // strncmp(col, lit, n) <cmp> 0 for fixed-width NUL-padded CHAR(n)
 // (types/operations/comparisons/AsciiStringComparators.hpp:218-251).
+// lit_longer: the literal continues past the attribute's N bytes, so a value that fills all N bytes and equals the
+// literal's first N is less than the literal (the reference compares the full strings: 'abc' < 'abcdef').
 template <uint32_t N>
-__device__ __forceinline__ bool char_cmp(uint8_t c, const char *v, const char *lit) {
-  int res = 0;
+__device__ __forceinline__ bool char_cmp(uint8_t c, const char *v, const char *lit, bool lit_longer = false) {
+  int res = lit_longer ? -1 : 0;
 #pragma unroll
   for (uint32_t i = 0; i < N; ++i) {
     const unsigned char a = static_cast<unsigned char>(v[i]);
     const unsigned char b = static_cast<unsigned char>(lit[i]);
     if (a != b) { res = a < b ? -1 : 1; break; }
-    if (a == 0) break;
+    if (a == 0) { res = 0; break; }
   }
   return cmp_t<int>(c, res, 0);
 }
@@ -306,7 +308,7 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
       constexpr uint32_t w = Q::col_w(in.arg);
       const char *lit = L.str_pool + in.ltype;    // ltype doubles as pool offset
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) pst[SP][r] = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit);
+      for (int r = 0; r < kRows; ++r) pst[SP][r] = char_cmp<w>(in.aux, base + tile_row(r, tid) * w, lit, (in.flags & 4) != 0);
     } else if constexpr (in.op == OP_CMP_CODE) {
       // attribute <cmp> literal on a dictionary-coded attribute: the host turned the literal into the range
       // of codes that satisfy it (the dictionary is sorted), CompressedTupleStorageSubBlock::getMatchesForPredicate

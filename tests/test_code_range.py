@@ -92,3 +92,16 @@ def test_rejects_mixed_kinds():
     li = es.lit_char(b"x")
     with pytest.raises(A.QsGpuError):
         code_range(A.QS_INT, 0, np.array([1, 2], dtype=np.int32), A.QS_EQ, es, li)
+
+
+@pytest.mark.parametrize("cmp", CMPS)
+def test_char_literal_longer_than_the_attribute(cmp):
+    """col CHAR(3) <cmp> 'abcdef' compares the FULL strings (AsciiStringComparators.hpp:218-251): the entry
+    'abc' is less than the literal, never equal to its first three bytes."""
+    d = np.array([b"ab", b"abc", b"abd", b"b"], dtype="S3")
+    for lit in (b"abcdef", b"abc", b"abcd", b"ab", b"abz9"):
+        es = ExprSet()
+        li = es.lit_char(lit)
+        got = code_range(A.QS_CHAR, 3, d, cmp, es, li)
+        want = np.array([PY[cmp](bytes(x), lit) for x in d])       # Python bytes compare like strcmp on NUL-free strings
+        assert (got == want).all(), (cmp, lit, got, want)

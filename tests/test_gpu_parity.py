@@ -380,6 +380,51 @@ def test_random_scalars_bit_exact(G, OB, seed):
         assert (gb == ob).all(), c
 
 
+def test_shared_expression_first_used_inside_a_right_operand(G, OB):
+    """(x + 1) * (SHARED#7(y + 2) + 3), then SHARED#7 again: the shared value's temporary must survive the
+    binary node whose right operand first materialised it."""
+    th = K.random_table(5000, seed=5)
+    es = ExprSet()
+    x, y = th.attr(es, "f64"), th.attr(es, "i64")
+    sh = lambda: es.shared(es.add(th.attr(es, "i64"), es.lit_int(2)), 7)
+    first = es.mul(es.add(x, es.lit_int(1)), es.add(sh(), es.lit_int(3)))
+    again = es.add(sh(), es.lit_int(10))
+    third = es.mul(es.sub(th.attr(es, "f64"), es.lit_int(4)), es.add(sh(), th.attr(es, "i32")))
+    pred = es.cmp(A.QS_GT, es.mul(es.add(th.attr(es, "i32"), es.lit_int(1)), es.add(sh(), es.lit_int(1))), es.lit_int(0))
+    schema = [(A.QS_DOUBLE, 8), (A.QS_LONG, 8), (A.QS_DOUBLE, 8)]
+    g = G.select(G.relation(th), es, pred, None, [first, again, third], schema)
+    o = OB.select(th, es, pred, None, [first, again, third], schema)
+    assert g.n_rows == o.n_rows > 0
+    assert table_rows(g) == table_rows(o)
+
+
+@pytest.mark.parametrize("coded", [False, True])
+def test_char_literal_longer_than_the_attribute(engine, OB, coded):
+    """col CHAR(3) <cmp> 'abcdef' compares the full strings, the same on native and on dictionary-coded relations."""
+    vals = np.array([b"ab", b"abc", b"abd", b"b", b"abc", b"a"], dtype="S3")
+    rng = np.random.default_rng(2)
+    th = HostTable("t", [Column("c", A.QS_CHAR, vals[rng.integers(0, len(vals), size=3000)], 3), Column("i", A.QS_INT, np.arange(3000, dtype=np.int32))])
+    if coded:
+        rel = engine.Relation.from_host_coded(th, {0: 1})
+    else:
+        rel = engine.Relation.from_host(th)
+    try:
+        for lit in (b"abcdef", b"abc", b"abz"):
+            for cmp in (A.QS_EQ, A.QS_NE, A.QS_LT, A.QS_LE, A.QS_GT, A.QS_GE):
+                es = ExprSet()
+                pred = es.cmp(cmp, th.attr(es, "c"), es.lit_char(lit))
+                out = engine.Relation.create([(A.QS_INT, 4)], 3000)
+                try:
+                    engine.select(rel, es, pred, None, [th.attr(es, "i")], out)
+                    got = sorted(out.read(0).tolist())
+                finally:
+                    out.destroy()
+                o = OB.select(th, es, pred, None, [th.attr(es, "i")], [(A.QS_INT, 4)])
+                assert got == sorted(o.columns[0].data.tolist()), (lit, cmp)
+    finally:
+        rel.destroy()
+
+
 def test_div_mod(G, OB):
     th = K.random_table(3000, seed=5)
     es = ExprSet()
