@@ -292,6 +292,14 @@ int qsgpu_lip_num_words(qsgpu_lip_t lip, uint64_t *n_words);
 int qsgpu_lip_read(qsgpu_lip_t lip, uint64_t *host_words);
 /* Device address of the bit words (for NCCL all-reduce(BOR) across GPUs). */
 int qsgpu_lip_device_words(qsgpu_lip_t lip, void **dptr);
+/*
+ * LIPFilterAdaptiveProber (utility/lip_filter/LIPFilterAdaptiveProber.hpp:89-232) keeps, per filter, how many tuples
+ * probed it and how many it rejected, and re-sorts the filters by miss rate between batches.  Every scan kernel
+ * that probes a filter adds its counts to the filter (rows already rejected by an earlier filter of the same scan
+ * are not probed and not counted); a caller with several probe filters passes them most-selective-first in the
+ * qs_scan of its next work order.  The order never changes a result.  Waits for the queued work.
+ */
+int qsgpu_lip_probe_stats(qsgpu_lip_t lip, uint64_t *probes, uint64_t *misses);
 
 /* A filter bound to the attribute it is built from / probed with
  * (LIPFilterDeployment, utility/lip_filter/LIPFilterDeployment.cpp). */

@@ -145,6 +145,7 @@ SIGNATURES = {
     "qsgpu_lip_num_words": (C.c_int, [_VP, _U64P]),
     "qsgpu_lip_read": (C.c_int, [_VP, _U64P]),
     "qsgpu_lip_device_words": (C.c_int, [_VP, _VPP]),
+    "qsgpu_lip_probe_stats": (C.c_int, [_VP, _U64P, _U64P]),
     "qsgpu_build_lip_filter": (C.c_int, [C.POINTER(qs_scan), C.c_uint32, C.POINTER(qs_lip_ref)]),
     "qsgpu_select": (C.c_int, [C.POINTER(qs_scan), C.c_uint32, C.POINTER(C.c_int32), _VP]),
     "qsgpu_agg_create": (C.c_int, [C.POINTER(qs_agg_spec), _VPP]),

@@ -1144,6 +1144,7 @@ int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type, int64_t min_val
   f->d.is_anti = is_anti ? 1 : 0;
   QS_CUDA(dev_malloc(&f->d.words, f->n_words * 8 + 64));
   QS_CUDA(cudaMemsetAsync(f->d.words, 0, f->n_words * 8 + 64, d->stream));
+  f->d.stats = reinterpret_cast<unsigned long long *>(f->d.words + f->n_words);      // the 64 bytes behind the bit words
   *out = f.release();
   return QSGPU_OK;
 }
@@ -1159,6 +1160,16 @@ int qsgpu_lip_read(qsgpu_lip_t lip, uint64_t *host_words) {
   return qsgpu_memcpy_d2h(lip->dev, host_words, lip->d.words, lip->n_words * 8);
 }
 int qsgpu_lip_device_words(qsgpu_lip_t lip, void **dptr) { *dptr = lip->d.words; return QSGPU_OK; }
+int qsgpu_lip_probe_stats(qsgpu_lip_t lip, uint64_t *probes, uint64_t *misses) {
+  Device *d = device(lip->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  unsigned long long v[2] = {0, 0};
+  QS_CUDA(cudaMemcpyAsync(v, lip->d.stats, 16, cudaMemcpyDeviceToHost, d->stream));
+  QS_CUDA(cudaStreamSynchronize(d->stream));
+  if (probes) *probes = v[0];
+  if (misses) *misses = v[1];
+  return QSGPU_OK;
+}
 
 /* --------------------------------------------- shared scan-side lowering */
 static int lower_scan_predicate(Lowering &L, const qs_scan *scan) {

@@ -115,6 +115,9 @@ struct LipDesc {
   uint64_t cardinality;
   uint32_t kind;        // QS_LIP_*
   uint32_t is_anti;
+  // [0] = rows that probed this filter, [1] = rows it rejected, accumulated by every scan that probes it: what
+  // LIPFilterAdaptiveProber keeps per filter (cnt / miss, utility/lip_filter/LIPFilterAdaptiveProber.hpp:103-127)
+  unsigned long long *stats;
 };
 
 // What a scan kernel iterates over.

@@ -459,6 +459,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
     if constexpr (Q::priv != 0) sink.flush_private();
   });
 
+  flush_lip_stats<Q>(S, regs);
   // ---- CTA reduction of the register-resident (hot) groups, fixed tree.
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -701,6 +702,7 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
     if (!__any_sync(0xffffffffu, any)) return;
     vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
   });
+  flush_lip_stats<Q>(S, regs);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, off);
   if ((tid & 31) == 0 && new_groups) atomicAdd(A.n_groups, new_groups);
@@ -780,6 +782,7 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
       vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
     }
   });
+  flush_lip_stats<Q>(S, regs);
 }
 
 // Join key of row `row` of the staged tile: one INT/LONG attribute, or two INT attributes packed into 64 bits.
@@ -885,6 +888,7 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
       }
     }
   });
+  flush_lip_stats<Q>(S, regs);
   // (a per-tile update put one same-address atomic per warp per 1024 rows on the table's entry counter)
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) inserted += __shfl_xor_sync(0xffffffffu, inserted, off);
@@ -1100,6 +1104,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       }
     }
   });
+  flush_lip_stats<Q>(S, regs);
 }
 
 }  // namespace qs

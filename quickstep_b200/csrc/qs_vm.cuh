@@ -202,6 +202,8 @@ struct SinkBase {
 struct VmRegs {
   uint64_t tmp[kMaxTmp][kRows];
   uint64_t acc[kRows];
+  // per-thread LIP probe statistics over all tiles (dead registers in kernels that probe no filter)
+  uint32_t lip_cnt[kMaxLip] = {0, 0, 0, 0}, lip_miss[kMaxLip] = {0, 0, 0, 0};
 };
 
 // Row i of the tile that thread `tid` owns in its r-th lane: r*kBlock + tid.
@@ -343,8 +345,11 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         bool b = false;
-        if ((in.flags & 2) == 0 || pst[SP - 1][r])
+        if ((in.flags & 2) == 0 || pst[SP - 1][r]) {
           b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, static_cast<int64_t>(acc[r]));
+          ++regs.lip_cnt[in.arg];
+          regs.lip_miss[in.arg] += b ? 0u : 1u;
+        }
         pst[SP][r] = b;
       }
     } else if constexpr (in.op == OP_EMIT) {
@@ -499,6 +504,29 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
     }
     if (++s == Q::n_stages) { s = 0; parity ^= 1; }
   }
+}
+
+// End of a scan kernel: this CTA's probe / miss counts go to the filters' statistics words (one atomic pair per warp
+// and filter per kernel).  The host reads them to order the filters of later work orders by miss rate
+// (LIPFilterAdaptiveProber, utility/lip_filter/LIPFilterAdaptiveProber.hpp:89-232); results never depend on them.
+template <class Q>
+__device__ __forceinline__ void flush_lip_stats(const ScanDesc &S, const VmRegs &regs) {
+  static_for<0, kMaxLip>([&](auto ff) {
+    constexpr int f = QS_IDX(ff);
+    bool probed = false;
+    for (int pc = 0; pc < Q::n_total; ++pc) probed = probed || (Q::code(pc).op == OP_LIP && Q::code(pc).arg == f);
+    if (!probed) return;
+    uint32_t c = regs.lip_cnt[f], m = regs.lip_miss[f];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, off);
+      m += __shfl_xor_sync(0xffffffffu, m, off);
+    }
+    if ((threadIdx.x & 31) == 0 && c != 0 && S.lip[f].stats != nullptr) {
+      atomicAdd(&S.lip[f].stats[0], static_cast<unsigned long long>(c));
+      if (m) atomicAdd(&S.lip[f].stats[1], static_cast<unsigned long long>(m));
+    }
+  });
 }
 
 // Validity of this thread's rows in `tile` (row range may start/end mid-tile).  Only the first and the

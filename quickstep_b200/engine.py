@@ -309,6 +309,12 @@ class LipFilter:
         A.check(A.load().qsgpu_lip_read(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out[: n.value]
 
+    def probe_stats(self):
+        """(rows that probed the filter, rows it rejected) over every scan so far."""
+        p, m = C.c_uint64(0), C.c_uint64(0)
+        A.check(A.load().qsgpu_lip_probe_stats(self.h, C.byref(p), C.byref(m)))
+        return p.value, m.value
+
     def device_words(self):
         p = C.c_void_p()
         A.check(A.load().qsgpu_lip_device_words(self.h, C.byref(p)))

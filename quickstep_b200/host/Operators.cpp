@@ -44,6 +44,13 @@ std::uint64_t attrsOf(const std::vector<qs_lip_ref> &refs) {
   return m;
 }
 
+// Probe filters of a work order that is about to run, most selective first by what the kernels have seen so far.
+std::vector<qs_lip_ref> rankedNow(const std::vector<qs_lip_ref> &lip_probe) {
+  std::vector<qs_lip_ref> refs = lip_probe;
+  RankLIPFiltersByMissRate(&refs);
+  return refs;
+}
+
 qs_scan makeScan(const DeviceExtent &in, const qs_expr_set *es, int predicate_root, const std::vector<qs_lip_ref> &lip_probe) {
   qs_scan s{};
   s.input = in.relation;
@@ -88,7 +95,8 @@ void SelectWorkOrder::execute() {
     addScalars(&L, selection_);
   }
   const qs_expr_set es = L.es.view();
-  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  const std::vector<qs_lip_ref> probe = rankedNow(lip_probe_);
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, probe);
   QS_CHECK_GPU(qsgpu_select(&scan, static_cast<std::uint32_t>(L.roots.size()), L.roots.data(),
                             output_destination_->deviceRelation()));
 }
@@ -114,7 +122,8 @@ void BuildLIPFilterWorkOrder::execute() {
   Lowered L;
   addPredicate(&L, build_side_predicate_);
   const qs_expr_set es = L.es.view();
-  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  const std::vector<qs_lip_ref> probe = rankedNow(lip_probe_);
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, probe);
   QS_CHECK_GPU(qsgpu_build_lip_filter(&scan, static_cast<std::uint32_t>(lip_build_.size()), lip_build_.data()));
 }
 
@@ -158,7 +167,8 @@ void BuildHashWorkOrder::execute() {
   Lowered L;
   addPredicate(&L, predicate_);
   const qs_expr_set es = L.es.view();
-  const qs_scan scan = makeScan(input_, &es, L.predicate_root, lip_probe_);
+  const std::vector<qs_lip_ref> probe = rankedNow(lip_probe_);
+  const qs_scan scan = makeScan(input_, &es, L.predicate_root, probe);
   QS_CHECK_GPU(qsgpu_join_build_composite(hash_table_, &scan, static_cast<std::uint32_t>(join_key_attributes_.size()),
                                           join_key_attributes_.data(), static_cast<std::uint32_t>(lip_build_.size()),
                                           lip_build_.empty() ? nullptr : lip_build_.data()));
@@ -189,7 +199,8 @@ void HashJoinWorkOrder::execute() {
   }
   addScalars(&L, selection_);
   const qs_expr_set es = L.es.view();
-  const qs_scan scan = makeScan(probe_, &es, -1, lip_probe_);
+  const std::vector<qs_lip_ref> probe = rankedNow(lip_probe_);
+  const qs_scan scan = makeScan(probe_, &es, -1, probe);
   std::uint32_t jt = QS_JOIN_INNER;
   switch (join_type_) {
     case JoinType::kInnerJoin: jt = QS_JOIN_INNER; break;
@@ -219,8 +230,9 @@ bool AggregationOperator::getAllWorkOrders(WorkOrdersContainer *container, Query
 }
 
 void AggregationWorkOrder::execute() {
+  const std::vector<qs_lip_ref> probe = rankedNow(lip_probe_);
   QS_CHECK_GPU(qsgpu_agg_run(state_, input_.relation, input_.row_begin, input_.row_end,
-                             static_cast<std::uint32_t>(lip_probe_.size()), lip_probe_.empty() ? nullptr : lip_probe_.data()));
+                             static_cast<std::uint32_t>(probe.size()), probe.empty() ? nullptr : probe.data()));
 }
 
 bool BuildAggregationExistenceMapOperator::getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context,

@@ -11,6 +11,7 @@
 // context, as in the reference.
 #pragma once
 
+#include <algorithm>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -39,6 +40,22 @@ class InsertDestination {
   std::uint64_t capacity_;
   StorageManager *sm_;
 };
+
+// The adaptive part of LIPFilterAdaptiveProber: most selective filter first, from the probe / miss counts the scan
+// kernels have accumulated in each filter so far.  Called when work orders are generated and again when a work order
+// with several probe filters starts executing (so the order adapts between the work orders of one operator).
+inline void RankLIPFiltersByMissRate(std::vector<qs_lip_ref> *refs) {
+  if (refs->size() < 2) return;
+  std::vector<std::pair<double, qs_lip_ref>> ranked;
+  for (const qs_lip_ref &r : *refs) {
+    std::uint64_t probes = 0, misses = 0;
+    QS_CHECK_GPU(qsgpu_lip_probe_stats(r.lip, &probes, &misses));
+    ranked.emplace_back(probes ? static_cast<double>(misses) / static_cast<double>(probes) : 0.0, r);
+  }
+  std::stable_sort(ranked.begin(), ranked.end(),
+                   [](const std::pair<double, qs_lip_ref> &a, const std::pair<double, qs_lip_ref> &b) { return a.first > b.first; });
+  for (std::size_t i = 0; i < refs->size(); ++i) (*refs)[i] = ranked[i].second;
+}
 
 class QueryContext {
  public:
@@ -169,6 +186,11 @@ class QueryContext {
         }
         qs_lip_ref r{}; r.lip = lip_filters_[e.filter]; r.attr = static_cast<std::uint32_t>(e.attr); refs.push_back(r);
       }
+    // LIPFilterAdaptiveProber: with several probe filters, the ones that rejected the larger share of what they have
+    // seen so far go first (the kernels skip rows an earlier filter rejected).  The statistics come from the work
+    // orders executed so far -- of this or of any earlier operator probing the same filter -- so the order adapts
+    // between the work orders of a streamed / row-capped operator.  Result-neutral.
+    if (action == LIPAction::kProbe) RankLIPFiltersByMissRate(&refs);
     return refs;
   }
 

@@ -639,6 +639,43 @@ def test_lip_hash_filter_and_anti(G, OB):
     assert (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()
 
 
+def test_lip_probe_statistics_and_order_neutrality(engine, OB):
+    """LIPFilterAdaptiveProber's bookkeeping: every scan adds (probed, rejected) to the filters it probes -- rows an
+    earlier filter of the same scan rejected are not probed -- and the order of the filters never changes the result."""
+    n = 20000
+    rng = np.random.default_rng(21)
+    a, b = rng.integers(0, 1000, size=n).astype(np.int32), rng.integers(0, 1000, size=n).astype(np.int32)
+    th = HostTable("t", [Column("a", A.QS_INT, a), Column("b", A.QS_INT, b), Column("v", A.QS_LONG, np.arange(n, dtype=np.int64))])
+    wide = HostTable("w", [Column("k", A.QS_INT, np.arange(0, 900, dtype=np.int32))])        # rejects ~10 % of a
+    narrow = HostTable("n", [Column("k", A.QS_INT, np.arange(0, 50, dtype=np.int32))])        # rejects ~95 % of b
+    rel = engine.Relation.from_host(th)
+    rw, rn = engine.Relation.from_host(wide), engine.Relation.from_host(narrow)
+    fw = engine.LipFilter(A.QS_LIP_BITVECTOR_EXACT, A.QS_INT, 0, 999)
+    fn = engine.LipFilter(A.QS_LIP_BITVECTOR_EXACT, A.QS_INT, 0, 999)
+    outs = []
+    try:
+        engine.build_lip_filter(rw, None, -1, None, [(fw, 0)])
+        engine.build_lip_filter(rn, None, -1, None, [(fn, 0)])
+        assert fw.probe_stats() == (0, 0) and fn.probe_stats() == (0, 0)
+        es = ExprSet()
+        for order in ([(fw, 0), (fn, 1)], [(fn, 1), (fw, 0)]):
+            out = engine.Relation.create([(A.QS_LONG, 8)], n)
+            engine.select(rel, es, -1, order, [th.attr(es, "v")], out)
+            outs.append(sorted(out.read(0).tolist()))
+            out.destroy()
+        keep_a, keep_b = a < 900, b < 50
+        assert outs[0] == outs[1] == np.nonzero(keep_a & keep_b)[0].tolist()
+        # first scan: fw saw every row, fn only the rows fw kept; second scan: fn saw every row, fw only what fn kept
+        pw, mw = fw.probe_stats()
+        pn, mn = fn.probe_stats()
+        assert pw == n + int(keep_b.sum()) and mw == int((~keep_a).sum()) + int((keep_b & ~keep_a).sum())
+        assert pn == int(keep_a.sum()) + n and mn == int((keep_a & ~keep_b).sum()) + int((~keep_b).sum())
+        assert mn / pn > mw / pw          # the narrow filter ranks first from now on
+    finally:
+        for o in (fw, fn, rw, rn, rel):
+            o.destroy()
+
+
 @pytest.mark.parametrize("n,limit", [(5, 10), (1000, 10), (100000, 100)])
 def test_topk(G, OB, n, limit):
     th = K.random_table(n, seed=n)
