@@ -88,6 +88,12 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
 int qshost_q6(qshost_db_t db, double *revenue, int *is_null, uint64_t *work_orders);
 int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *work_orders);
 
+/* The result relation of the last query as the InsertDestination wrote it on the host: block `index` (0, 1, ...) of
+ * SplitRowStore blocks in the reference's own layout ([int header_len][StorageBlockHeader proto][sub-block header]
+ * [occupancy bitmap][tuple slots], storage/SplitRowStoreTupleStorageSubBlock.cpp:103-179), valid until the next query.
+ * Returns non-zero when there is no such block. */
+int qshost_result_block(qshost_db_t db, uint32_t index, const void **memory, uint64_t *bytes, uint64_t *n_tuples);
+
 /* Per-operator profile of the last query: one text line per operator (index, name, work orders, ms inside
  * execute(), ms inside getAllWorkOrders()); the analogue of -profile_and_report_workorder_perf. */
 int qshost_last_profile(qshost_db_t db, char *buf, uint64_t buf_bytes);

@@ -30,6 +30,13 @@ class InsertDestination {
       : relation_(relation), capacity_(capacity_rows), sm_(sm) {}
   const CatalogRelation &getRelation() const { return *relation_; }
   qsgpu_relation_t deviceRelation() { sm_->createTemporary(*relation_, capacity_); return sm_->temporary(*relation_); }
+  // InsertDestination::bulkInsertTuples (storage/InsertDestination.cpp:202-216): rows that leave the device, given as
+  // host column vectors, go into SplitRowStore blocks of the output relation (the reference's layout for temporaries);
+  // called on the thread that runs the work order / reads the result, like the reference requires
+  // (storage/InsertDestination.cpp:403-406).  The blocks are what getTouchedBlocks() hands to a CPU consumer.
+  std::vector<block_id> bulkInsertTuples(const std::vector<const void *> &columns, std::uint64_t n_rows) {
+    return sm_->insertTuples(*relation_, columns, n_rows);
+  }
   // FinalizeAggregation / top-k create their output relation themselves
   void adopt(qsgpu_relation_t handle) { sm_->adoptTemporary(*relation_, handle); }
   // QueryManagerBase::markOperatorFinished -> getPartiallyFilledBlocks: the blocks to feed downstream

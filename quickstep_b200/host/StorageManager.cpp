@@ -126,7 +126,109 @@ void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, co
 
 }  // namespace
 
+namespace {
+
+// SplitRowStore geometry of a fixed-length, non-nullable schema inside a one-slot block
+struct SplitRowStoreGeometry {
+  std::size_t header_len = 17;                       // serialized StorageBlockHeader (see writeBlockHeader)
+  std::size_t sub_block = 4 + 17;                    // offset of the tuple-store sub-block
+  std::size_t sub_block_bytes = 0, slot_bytes = 0, max_tuples = 0, occupancy_bytes = 0, slots = 0;
+  std::vector<std::size_t> offsets;
+  explicit SplitRowStoreGeometry(const std::vector<qs_attr> &schema) {
+    for (const qs_attr &a : schema) { offsets.push_back(slot_bytes); slot_bytes += a.width; }
+    if (slot_bytes == 0) slot_bytes = 1;
+    sub_block_bytes = kSlotSizeBytes - sub_block;
+    max_tuples = (sub_block_bytes - 16) / slot_bytes;                    // sizeof(Header) = 16
+    occupancy_bytes = ((max_tuples + 63) / 64) * 8;                      // BitVector<false>::BytesNeeded
+    slots = sub_block + 16 + occupancy_bytes;
+    max_tuples = std::min(max_tuples, (kSlotSizeBytes - slots) / slot_bytes);
+  }
+};
+
+// StorageBlockHeader{layout{num_slots = 1, tuple_store_description{sub_block_type = SPLIT_ROW_STORE}},
+// tuple_store_size (fixed64)} in protobuf wire format, preceded by its length
+void writeBlockHeader(char *block, std::uint64_t tuple_store_size) {
+  const unsigned char hdr[9] = {0x0A, 0x06, 0x08, 0x01, 0x12, 0x02, 0x08, 0x03, 0x11};
+  const std::int32_t len = 17;
+  std::memcpy(block, &len, 4);
+  std::memcpy(block + 4, hdr, 9);
+  std::memcpy(block + 13, &tuple_store_size, 8);
+}
+
+}  // namespace
+
+SplitRowStoreReader::SplitRowStoreReader(const char *block_memory, const std::vector<qs_attr> &schema) {
+  const SplitRowStoreGeometry g(schema);
+  std::int32_t n = 0;
+  std::memcpy(&n, block_memory + g.sub_block, 4);
+  num_tuples_ = static_cast<std::uint64_t>(n);
+  slots_ = block_memory + g.slots;
+  slot_bytes_ = g.slot_bytes;
+  offsets_ = g.offsets;
+}
+
+std::vector<block_id> StorageManager::insertTuples(const CatalogRelation &rel, const std::vector<const void *> &columns,
+                                                   std::uint64_t n_rows) {
+  const std::vector<qs_attr> schema = rel.schema();
+  QS_CHECK(columns.size() == schema.size());
+  const SplitRowStoreGeometry g(schema);
+  std::vector<block_id> out;
+  std::uint64_t row = 0;
+  do {
+    const std::uint64_t n = std::min<std::uint64_t>(n_rows - row, g.max_tuples);
+    char *mem = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (!block_pool_.empty()) { mem = block_pool_.back(); block_pool_.pop_back(); }
+    }
+    if (!mem) { mem = static_cast<char *>(std::calloc(1, kSlotSizeBytes)); QS_CHECK(mem != nullptr); }
+    // a recycled buffer may hold an older block: clear what this one will use (headers, occupancy bits, its slots)
+    std::memset(mem, 0, g.slots + n * g.slot_bytes);
+    writeBlockHeader(mem, g.sub_block_bytes);
+    const std::int32_t num = static_cast<std::int32_t>(n), max_tid = num - 1;
+    const std::uint32_t var_bytes = 0;
+    std::memcpy(mem + g.sub_block, &num, 4);
+    std::memcpy(mem + g.sub_block + 4, &max_tid, 4);
+    std::memcpy(mem + g.sub_block + 8, &var_bytes, 4);
+    mem[g.sub_block + 12] = 1;                                            // variable_length_storage_compact
+    std::uint64_t *occ = reinterpret_cast<std::uint64_t *>(mem + g.sub_block + 16);   // unaligned by design (memcpy below)
+    for (std::uint64_t w = 0; w * 64 < n; ++w) {
+      const std::uint64_t bits = std::min<std::uint64_t>(64, n - w * 64);
+      const std::uint64_t word = bits == 64 ? ~0ull : (~0ull << (64 - bits));      // MSB-first (utility/BitVector.hpp:934)
+      std::memcpy(reinterpret_cast<char *>(occ) + w * 8, &word, 8);
+    }
+    for (std::size_t a = 0; a < schema.size(); ++a) {
+      const std::size_t w = schema[a].width;
+      const char *src = static_cast<const char *>(columns[a]) + row * w;
+      char *dst = mem + g.slots + g.offsets[a];
+      for (std::uint64_t i = 0; i < n; ++i) std::memcpy(dst + i * g.slot_bytes, src + i * w, w);
+    }
+    StorageBlock B;
+    B.relation = rel.getID();
+    B.num_tuples = static_cast<tuple_id>(n);
+    B.memory = mem;
+    B.size = kSlotSizeBytes;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      B.id = next_block_++;
+      out.push_back(B.id);
+      result_blocks_[rel.getID()].push_back(B.id);
+      blocks_.emplace(B.id, std::move(B));
+    }
+    row += n;
+  } while (row < n_rows);
+  return out;
+}
+
+std::vector<block_id> StorageManager::hostBlocksOf(const CatalogRelation &rel) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = result_blocks_.find(rel.getID());
+  return it == result_blocks_.end() ? std::vector<block_id>() : it->second;
+}
+
 StorageManager::~StorageManager() {
+  for (auto &kv : result_blocks_) for (block_id b : kv.second) std::free(const_cast<char *>(blocks_.at(b).memory));
+  for (char *p : block_pool_) std::free(p);
   for (auto &kv : replicas_) if (kv.second) qsgpu_relation_destroy(kv.second);
   for (auto &kv : resident_) if (kv.second.handle) qsgpu_relation_destroy(kv.second.handle);
   for (auto &kv : temporaries_) if (kv.second) qsgpu_relation_destroy(kv.second);
@@ -482,6 +584,14 @@ qsgpu_relation_t StorageManager::replicated(const CatalogRelation &rel) {
 void StorageManager::dropTemporary(const CatalogRelation &rel) {
   std::lock_guard<std::mutex> lk(mu_);
   partitioned_.erase(rel.getID());
+  auto rb = result_blocks_.find(rel.getID());
+  if (rb != result_blocks_.end()) {          // host blocks written by insertTuples(): buffers go back to the pool
+    for (block_id b : rb->second) {
+      block_pool_.push_back(const_cast<char *>(blocks_.at(b).memory));
+      blocks_.erase(b);
+    }
+    result_blocks_.erase(rb);
+  }
   auto rp = replicas_.find(rel.getID());
   if (rp != replicas_.end()) {
     if (rp->second) QS_CHECK_GPU(qsgpu_relation_destroy(rp->second));

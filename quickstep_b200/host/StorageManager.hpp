@@ -50,6 +50,23 @@ struct DeviceExtent {
   std::uint64_t row_begin = 0, row_end = UINT64_MAX;
 };
 
+constexpr std::size_t kSlotSizeBytes = 0x200000;     // storage/StorageConstants.hpp:50
+
+// Read side of a SplitRowStore block of fixed-length, non-nullable attributes (what
+// SplitRowStoreTupleStorageSubBlock::getAttributeValue does): where tuple t's attribute a lives.
+class SplitRowStoreReader {
+ public:
+  SplitRowStoreReader(const char *block_memory, const std::vector<qs_attr> &schema);
+  std::uint64_t numTuples() const { return num_tuples_; }
+  const char *value(std::uint64_t tuple, std::size_t attr) const { return slots_ + tuple * slot_bytes_ + offsets_[attr]; }
+
+ private:
+  std::uint64_t num_tuples_ = 0;
+  const char *slots_ = nullptr;
+  std::size_t slot_bytes_ = 0;
+  std::vector<std::size_t> offsets_;
+};
+
 class StorageManager {
  public:
   // pinned_blocks = false keeps the block images in ordinary host memory: what the device-free unit tests of
@@ -102,6 +119,17 @@ class StorageManager {
   // first use, owned by the manager, dropped together with the temporary.
   qsgpu_relation_t replicated(const CatalogRelation &rel);
 
+  // ---- InsertDestination::bulkInsertTuples (storage/InsertDestination.cpp:202-216), the GPU -> host hand-off -------
+  // Rows that leave the device (the result relation of a query, or the input of an operator that stays on the CPU)
+  // arrive as host column vectors and are written into blocks of the output relation in the layout the reference
+  // gives temporary relations: SplitRowStore inside a one-slot (2 MB) StorageBlock,
+  //   [int header_len][StorageBlockHeader proto][Header{num_tuples, max_tid, var_bytes, compact}][occupancy bitmap][slots]
+  // (storage/StorageBlockLayout.proto:103-124, storage/SplitRowStoreTupleStorageSubBlock.cpp:103-179, .hpp:356-361),
+  // bit-compatible with what the reference's own accessors read.  Block buffers come from a small pool and are
+  // recycled by dropTemporary().  Returns the ids of the blocks filled, in order.
+  std::vector<block_id> insertTuples(const CatalogRelation &rel, const std::vector<const void *> &columns, std::uint64_t n_rows);
+  std::vector<block_id> hostBlocksOf(const CatalogRelation &rel) const;
+
   // Device-only temporary relation (output of Select / HashJoin / Finalize);
   // its single pseudo block id stands for "every row produced so far".
   block_id createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows);
@@ -135,6 +163,8 @@ class StorageManager {
   std::map<relation_id, Resident> resident_;
   std::map<relation_id, qsgpu_relation_t> temporaries_;
   std::map<relation_id, qsgpu_relation_t> replicas_;
+  std::map<relation_id, std::vector<block_id>> result_blocks_;     // host blocks written by insertTuples()
+  std::vector<char *> block_pool_;                                  // recycled 2 MB block buffers
   std::map<relation_id, bool> partitioned_;
   qsgpu_comm_t comm_ = nullptr;
   std::map<relation_id, block_id> temporary_block_;

@@ -68,8 +68,15 @@ struct qshost_db {
     temps.emplace_back(new CatalogRelation(next_relation_id++, "tmp", std::move(attrs), true));
     return temps.back().get();
   }
-  void dropTemps() {
-    for (auto &t : temps) sm->dropTemporary(*t);
+  // the result relation of the last query: its host blocks (InsertDestination::bulkInsertTuples) stay readable
+  // (qshost_result_block) until the next query starts
+  std::unique_ptr<CatalogRelation> last_result;
+  void dropTemps(const CatalogRelation *keep = nullptr) {
+    if (last_result) { sm->dropTemporary(*last_result); last_result.reset(); }
+    for (auto &t : temps) {
+      if (t.get() == keep) last_result = std::move(t);
+      else sm->dropTemporary(*t);
+    }
     temps.clear();
   }
 };
@@ -99,6 +106,7 @@ int qshost_db_create(int dev, int num_workers, qshost_db_t *out) {
 int qshost_db_destroy(qshost_db_t db) {
   if (!db) return 0;
   db->dropTemps();
+  db->dropTemps();     // ... and the result relation kept from the last query
   delete db;
   return 0;
 }
@@ -112,6 +120,17 @@ int qshost_db_set_comm(qshost_db_t db, void *comm) {
 int qshost_db_set_join_mode(qshost_db_t db, int mode) {
   if (mode < 0 || mode > 1) return QSGPU_ERR_INVALID;
   db->join_mode = mode;
+  return 0;
+}
+
+int qshost_result_block(qshost_db_t db, uint32_t index, const void **memory, uint64_t *bytes, uint64_t *n_tuples) {
+  if (!db->last_result) return QSGPU_ERR_INVALID;
+  const std::vector<block_id> blocks = db->sm->hostBlocksOf(*db->last_result);
+  if (index >= blocks.size()) return QSGPU_ERR_INVALID;
+  const StorageBlock &B = db->sm->getBlock(blocks[index]);
+  if (memory) *memory = B.memory;
+  if (bytes) *bytes = B.size;
+  if (n_tuples) *n_tuples = static_cast<uint64_t>(B.num_tuples);
   return 0;
 }
 
@@ -226,11 +245,16 @@ int qshost_q6(qshost_db_t db, double *revenue, int *is_null, uint64_t *work_orde
   void *cols[1] = {&v};
   std::uint64_t n = 0, nulls = 0;
   QS_CHECK_GPU(qsgpu_relation_read_rows(out, 1, cols, &n, &nulls));
-  *revenue = n ? v : 0.0;
+  // the result relation's rows leave the device through its InsertDestination: host blocks in the reference's layout
+  const std::vector<const void *> ccols = {&v};
+  const std::vector<block_id> blocks = ctx.getInsertDestination(dest)->bulkInsertTuples(ccols, n);
+  const SplitRowStoreReader rd(db->sm->getBlock(blocks[0]).memory, result->schema());
+  *revenue = 0.0;
+  if (rd.numTuples()) std::memcpy(revenue, rd.value(0, 0), 8);
   if (is_null) *is_null = (n == 0 || (nulls & 1)) ? 1 : 0;
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
   db->last_profile = qm.profile();
-  db->dropTemps();
+  db->dropTemps(result);
   return 0;
 }
 
@@ -306,22 +330,28 @@ int qshost_q1(qshost_db_t db, qshost_q1_row *rows, uint32_t *n_rows, uint64_t *w
     QS_CHECK_GPU(qsgpu_relation_read_rows(out, kMaxRows, cols, &n, nullptr));
     n = std::min(n, kMaxRows);
   }
+  // InsertDestination::bulkInsertTuples: the result rows become SplitRowStore blocks of the result relation on the host
+  // (what the reference's PrintToScreen reads); the rows handed back are read from those blocks
+  const std::vector<const void *> ccols = {flag.data(), status.data(), d[0].data(), d[1].data(), d[2].data(), d[3].data(), d[4].data(),
+                                           d[5].data(), d[6].data(), count.data(), sum_disc.data()};
+  const std::vector<block_id> blocks = ctx.getInsertDestination(d_sorted)->bulkInsertTuples(ccols, n);
+  const SplitRowStoreReader rd(db->sm->getBlock(blocks[0]).memory, t_sorted->schema());
   std::vector<qshost_q1_row> res(n);
   for (std::uint64_t i = 0; i < n; ++i) {
     qshost_q1_row &r = res[i];
     std::memset(&r, 0, sizeof(r));
-    r.l_returnflag = flag[i]; r.l_linestatus = status[i];
-    r.sum_qty = d[0][i]; r.sum_base_price = d[1][i]; r.sum_disc_price = d[2][i]; r.sum_charge = d[3][i];
-    r.avg_qty = d[4][i]; r.avg_price = d[5][i]; r.avg_disc = d[6][i];
-    r.count_order = count[i];
-    r.sum_disc = sum_disc[i];
+    r.l_returnflag = *rd.value(i, 0); r.l_linestatus = *rd.value(i, 1);
+    double *dst[7] = {&r.sum_qty, &r.sum_base_price, &r.sum_disc_price, &r.sum_charge, &r.avg_qty, &r.avg_price, &r.avg_disc};
+    for (int k = 0; k < 7; ++k) std::memcpy(dst[k], rd.value(i, 2 + k), 8);
+    std::memcpy(&r.count_order, rd.value(i, 9), 8);
+    std::memcpy(&r.sum_disc, rd.value(i, 10), 8);
   }
   const std::uint32_t cap = *n_rows;
   *n_rows = static_cast<std::uint32_t>(n);
   for (std::uint32_t i = 0; i < std::min<std::uint64_t>(cap, n); ++i) rows[i] = res[i];
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
   db->last_profile = qm.profile();
-  db->dropTemps();
+  db->dropTemps(t_sorted);
   return n > cap ? QSGPU_ERR_CAPACITY : 0;
 }
 
@@ -434,19 +464,26 @@ int qshost_q3(qshost_db_t db, qshost_q3_row *rows, uint32_t *n_rows, uint64_t *w
     QS_CHECK_GPU(qsgpu_relation_read_rows(out, kMaxRows, cols, &n, nullptr));
     n = std::min(n, kMaxRows);
   }
+  const std::vector<const void *> ccols = {ok.data(), od.data(), sp.data(), rev.data()};
+  const std::vector<block_id> blocks = ctx.getInsertDestination(dst9)->bulkInsertTuples(ccols, n);
+  const SplitRowStoreReader rd(db->sm->getBlock(blocks[0]).memory, t9->schema());
   const std::uint32_t cap = *n_rows;
   *n_rows = static_cast<std::uint32_t>(n);
   for (std::uint32_t i = 0; i < std::min<std::uint64_t>(cap, n); ++i) {
     qshost_q3_row &r = rows[i];
     std::memset(&r, 0, sizeof(r));
-    r.l_orderkey = ok[i]; r.o_shippriority = sp[i]; r.revenue = rev[i];
-    r.year = static_cast<std::int32_t>(od[i] & 0xffffffffu);
-    r.month = static_cast<std::uint8_t>((od[i] >> 32) & 0xff);
-    r.day = static_cast<std::uint8_t>((od[i] >> 40) & 0xff);
+    std::uint64_t date = 0;
+    std::memcpy(&r.l_orderkey, rd.value(i, 0), 4);
+    std::memcpy(&date, rd.value(i, 1), 8);
+    std::memcpy(&r.o_shippriority, rd.value(i, 2), 4);
+    std::memcpy(&r.revenue, rd.value(i, 3), 8);
+    r.year = static_cast<std::int32_t>(date & 0xffffffffu);
+    r.month = static_cast<std::uint8_t>((date >> 32) & 0xff);
+    r.day = static_cast<std::uint8_t>((date >> 40) & 0xff);
   }
   if (work_orders) *work_orders = qm.totalWorkOrdersExecuted();
   db->last_profile = qm.profile();
-  db->dropTemps();
+  db->dropTemps(t9);
   return n > cap ? QSGPU_ERR_CAPACITY : 0;
 }
 

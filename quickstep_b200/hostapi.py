@@ -42,6 +42,7 @@ SIGNATURES = {
     "qshost_q6": [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int), _U64P],
     "qshost_q3": [_VP, C.POINTER(q3_row), C.POINTER(C.c_uint32), _U64P],
     "qshost_last_profile": [_VP, C.c_char_p, C.c_uint64],
+    "qshost_result_block": [_VP, C.c_uint32, C.POINTER(_VP), _U64P, _U64P],
 }
 _lib = None
 
@@ -125,6 +126,16 @@ class Database:
         n, wo = C.c_uint32(16), C.c_uint64(0)
         A.check(load().qshost_q3(self.h, rows, C.byref(n), C.byref(wo)))
         return [(r.l_orderkey, r.revenue, (r.year, r.month, r.day), r.o_shippriority) for r in rows[: n.value]], wo.value
+
+    def result_blocks(self):
+        """The last query's result relation as host SplitRowStore blocks (reference layout): [(bytes, n_tuples)]."""
+        out, i = [], 0
+        while True:
+            mem, nb, nt = _VP(), C.c_uint64(0), C.c_uint64(0)
+            if load().qshost_result_block(self.h, i, C.byref(mem), C.byref(nb), C.byref(nt)) != 0:
+                return out
+            out.append((C.string_at(mem.value, nb.value), nt.value))
+            i += 1
 
     def last_profile(self) -> str:
         buf = C.create_string_buffer(8192)

@@ -201,3 +201,44 @@ def test_operator_classes_outside_tpch():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "outer_join_composite_key ok" in r.stdout and "existence_map_aggregation ok" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_result_relation_leaves_through_insert_destination_blocks(golden):
+    """InsertDestination::bulkInsertTuples hand-off (storage/InsertDestination.cpp:202-216): the result rows of a query
+    are written on the host as SplitRowStore blocks in the reference's own layout -- parsed here with the reader that
+    parses the reference engine's block files (oracle/ref_blocks.py) -- and what the entry point returns is read from them."""
+    import struct
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_blocks as RB
+    db = H.Database(0, num_workers=2)
+    try:
+        for which, rel in ((H.CUSTOMER, "customer"), (H.ORDERS, "orders"), (H.LINEITEM, "lineitem")):
+            db.load_table(which, golden[rel], 20000, H.COMPRESSED_COLUMN_STORE)
+        rows, _ = db.q1()
+        blocks = db.result_blocks()
+        assert len(blocks) == 1 and blocks[0][1] == len(rows) == 4 and len(blocks[0][0]) == 2 << 20
+        mem = blocks[0][0]
+        d = RB.read_split_row_store(mem, [1, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8], 0, 0)
+        assert d["n_rows"] == 4 and d["contiguous"] and d["slot_bytes"] == 74
+        for i, r in enumerate(rows):
+            base = d["first_slot"] + i * d["slot_bytes"]
+            assert mem[base:base + 1] == r["l_returnflag"] and mem[base + 1:base + 2] == r["l_linestatus"]
+            vals = struct.unpack_from("<7dqd", mem, base + 2)
+            assert vals[0] == r["sum_qty"] and vals[3] == r["sum_charge"] and vals[6] == r["avg_disc"]
+            assert vals[7] == r["count_order"] and vals[8] == r["sum_disc"]
+        top, _ = db.q3()
+        (mem3, n3), = db.result_blocks()
+        d3 = RB.read_split_row_store(mem3, [4, 8, 4, 8], 0, 0)
+        assert n3 == d3["n_rows"] == len(top) == 10
+        for i, t in enumerate(top):
+            ok, = struct.unpack_from("<i", mem3, d3["first_slot"] + i * d3["slot_bytes"])
+            rev, = struct.unpack_from("<d", mem3, d3["first_slot"] + i * d3["slot_bytes"] + 16)
+            assert ok == t[0] and rev == t[1]
+        rev6, is_null, _ = db.q6()
+        (mem6, n6), = db.result_blocks()
+        d6 = RB.read_split_row_store(mem6, [8], 0, 0)
+        assert n6 == 1 and struct.unpack_from("<d", mem6, d6["first_slot"])[0] == rev6 and not is_null
+    finally:
+        db.destroy()
