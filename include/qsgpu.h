@@ -497,6 +497,14 @@ int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr,
                           uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets);
 
+/* Same regrouping with the reference's OWN partition function for a relation hash-partitioned on one INT / LONG
+ * attribute (HashPartitionSchemeHeader::getPartitionId, catalog/PartitionSchemeHeader.hpp:200-214, over the identity
+ * hash of an inline scalar, types/TypedValue.hpp:575-607): partition = value & (n_parts - 1) when n_parts is a power of
+ * two, value % n_parts otherwise.  What a PartitionAwareInsertDestination (storage/InsertDestination.cpp:471-722)
+ * does tuple by tuple; rows land in the partition the reference would put them in. */
+int qsgpu_hash_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
+                         uint64_t *host_offsets);
+
 /* Same regrouping by KEY RANGE: partition p = clamp((key - min_key) / part_width, 0, n_parts-1).  Used to make
  * a large join cache-resident (radix join): build and probe sides are range-partitioned, so the slice of the
  * dense join table and of the build relation that one probe partition touches is contiguous and fits in L2. */

@@ -169,6 +169,7 @@ SIGNATURES = {
     "qsgpu_join_destroy": (C.c_int, [_VP]),
     "qsgpu_topk": (C.c_int, [_VP, C.c_uint32, C.POINTER(qs_sort_key), C.c_uint64, _VPP]),
     "qsgpu_radix_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
+    "qsgpu_hash_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, _U64P]),
     "qsgpu_range_partition": (C.c_int, [_VP, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, _VP, _U64P]),
     "qsgpu_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, _VPP, C.POINTER(qs_ipc_handle)]),
     "qsgpu_ipc_open": (C.c_int, [C.c_int, C.POINTER(qs_ipc_handle), _VPP]),

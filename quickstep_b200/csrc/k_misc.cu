@@ -29,7 +29,8 @@ struct PartDesc {
   const char *key;
   uint8_t key_ltype;
   uint32_t n_parts;
-  uint32_t range_mode;           // 0: mix64(key) % n_parts;  1: (key - min_key) / part_width (clamped)
+  uint32_t range_mode;           // 0: mix64(key) % n_parts;  1: (key - min_key) / part_width (clamped);
+                                 // 2: HashPartitionSchemeHeader::getPartitionId (identity hash, & or % n_parts)
   int64_t min_key;
   uint64_t part_width;
   uint32_t width_shift;          // log2(part_width) when it is a power of two, else 64 (slot mode: log2(cap / n_parts))
@@ -44,6 +45,14 @@ struct PartDesc {
 
 __device__ __forceinline__ uint32_t part_of(const PartDesc &D, uint64_t row) {
   const int64_t k = static_cast<int64_t>(load_native(D.key + row * native_width(D.key_ltype), D.key_ltype));
+  if (D.range_mode == 2) {
+    // The reference's own hash partitioning of a relation on one INT / LONG attribute: TypedValue::getHash() is the
+    // bit pattern of an inline scalar (types/TypedValue.hpp:575-607), the partition is hash & (n - 1) for a power of
+    // two and hash % n otherwise (catalog/PartitionSchemeHeader.hpp:207-214) -- so rows land in the partition the
+    // reference's PartitionAwareInsertDestination would put them in
+    const uint64_t h = D.key_ltype == V_I32 ? static_cast<uint64_t>(static_cast<uint32_t>(k)) : static_cast<uint64_t>(k);
+    return static_cast<uint32_t>((D.n_parts & (D.n_parts - 1)) == 0 ? (h & (D.n_parts - 1)) : (h % D.n_parts));
+  }
   if (D.range_mode) {
     // key-range partitions: partition p holds keys [min + p*width, min + (p+1)*width), so the slice of a
     // dense join table (and of the range-partitioned build relation) one partition touches is contiguous.
@@ -505,6 +514,11 @@ int qsgpu_join_partition(qsgpu_join_table_t table, qsgpu_relation_t input, uint3
 int qsgpu_radix_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
                           uint64_t *host_offsets) {
   return partition_impl(input, key_attr, n_parts, 0, 0, 1, output, host_offsets);
+}
+
+int qsgpu_hash_partition(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_parts, qsgpu_relation_t output,
+                         uint64_t *host_offsets) {
+  return partition_impl(input, key_attr, n_parts, 2, 0, 1, output, host_offsets);
 }
 
 int qsgpu_range_partition(qsgpu_relation_t input, uint32_t key_attr, int64_t min_key, uint64_t part_width, uint32_t n_parts,

@@ -552,6 +552,13 @@ def range_partition(rel: Relation, key_attr, min_key, part_width, n_parts, outpu
     return offs
 
 
+def hash_partition(rel: Relation, key_attr, n_parts, output: Relation) -> np.ndarray:
+    """HashPartitionSchemeHeader's partition function (value & (n - 1) / value % n) -> partition start offsets."""
+    offs = (C.c_uint64 * (n_parts + 1))()
+    A.check(A.load().qsgpu_hash_partition(rel.h, key_attr, n_parts, output.h, offs))
+    return np.array(list(offs), dtype=np.uint64)
+
+
 def radix_partition(rel: Relation, key_attr, n_parts, output: Relation) -> np.ndarray:
     offs = np.zeros(n_parts + 1, dtype=np.uint64)
     A.check(A.load().qsgpu_radix_partition(rel.h, key_attr, n_parts, output.h,

@@ -28,6 +28,7 @@ class InsertDestination {
  public:
   InsertDestination(const CatalogRelation *relation, std::uint64_t capacity_rows, StorageManager *sm)
       : relation_(relation), capacity_(capacity_rows), sm_(sm) {}
+  virtual ~InsertDestination() {}
   const CatalogRelation &getRelation() const { return *relation_; }
   qsgpu_relation_t deviceRelation() { sm_->createTemporary(*relation_, capacity_); return sm_->temporary(*relation_); }
   // InsertDestination::bulkInsertTuples (storage/InsertDestination.cpp:202-216): rows that leave the device, given as
@@ -40,12 +41,45 @@ class InsertDestination {
   // FinalizeAggregation / top-k create their output relation themselves
   void adopt(qsgpu_relation_t handle) { sm_->adoptTemporary(*relation_, handle); }
   // QueryManagerBase::markOperatorFinished -> getPartiallyFilledBlocks: the blocks to feed downstream
-  std::vector<block_id> getTouchedBlocks() { return {sm_->createTemporary(*relation_, capacity_)}; }
+  // (block, partition id) pairs: what feedInputBlock(block_id, relation_id, partition_id) receives downstream
+  virtual std::vector<std::pair<block_id, partition_id>> getTouchedBlocks() {
+    return {{sm_->createTemporary(*relation_, capacity_), 0}};
+  }
 
- private:
+ protected:
   const CatalogRelation *relation_;
   std::uint64_t capacity_;
   StorageManager *sm_;
+};
+
+// catalog/PartitionSchemeHeader.hpp:170-218: hash partitioning on one attribute.
+struct HashPartitionSchemeHeader {
+  std::size_t num_partitions = 1;
+  attribute_id partition_attribute = 0;
+};
+
+// storage/InsertDestination.cpp:471-722.  The reference routes every tuple to the blocks of its partition as it is
+// inserted; on the device the operator writes its output rows once, and when it has finished K8 regroups them by
+// HashPartitionSchemeHeader's partition function (qsgpu_hash_partition: one histogram pass + one scatter pass).
+// Downstream operators are fed one block per partition together with its partition id, exactly what the reference's
+// scheduler does with the blocks of a partitioned relation (QueryManagerBase.cpp: feedInputBlock(block, rel, part_id)).
+class PartitionAwareInsertDestination : public InsertDestination {
+ public:
+  PartitionAwareInsertDestination(const HashPartitionSchemeHeader &header, const CatalogRelation *relation,
+                                  std::uint64_t capacity_rows, StorageManager *sm)
+      : InsertDestination(relation, capacity_rows, sm), header_(header) {}
+  const HashPartitionSchemeHeader &getPartitionSchemeHeader() const { return header_; }
+  std::vector<std::pair<block_id, partition_id>> getTouchedBlocks() override {
+    sm_->createTemporary(*relation_, capacity_);
+    if (blocks_.empty()) blocks_ = sm_->repartitionTemporary(*relation_, header_.partition_attribute, header_.num_partitions);
+    std::vector<std::pair<block_id, partition_id>> out;
+    for (std::size_t p = 0; p < blocks_.size(); ++p) out.emplace_back(blocks_[p], p);
+    return out;
+  }
+
+ private:
+  HashPartitionSchemeHeader header_;
+  std::vector<block_id> blocks_;
 };
 
 // The adaptive part of LIPFilterAdaptiveProber: most selective filter first, from the probe / miss counts the scan
@@ -157,6 +191,13 @@ class QueryContext {
   lip_deployment_id addLIPDeployment(LIPDeployment d) { lip_deployments_.push_back(std::move(d)); return static_cast<lip_deployment_id>(lip_deployments_.size()) - 1; }
   insert_destination_id addInsertDestination(const CatalogRelation *rel, std::uint64_t capacity_rows) {
     destinations_.emplace_back(new InsertDestination(rel, capacity_rows, sm_));
+    return static_cast<insert_destination_id>(destinations_.size()) - 1;
+  }
+  // serialization::InsertDestination with a partition scheme (query_execution/QueryContext.cpp:99-123 builds a
+  // PartitionAwareInsertDestination for it)
+  insert_destination_id addPartitionAwareInsertDestination(const HashPartitionSchemeHeader &header, const CatalogRelation *rel,
+                                                           std::uint64_t capacity_rows) {
+    destinations_.emplace_back(new PartitionAwareInsertDestination(header, rel, capacity_rows, sm_));
     return static_cast<insert_destination_id>(destinations_.size()) - 1;
   }
   sort_config_id addSortConfig(SortConfig c) { sort_configs_.push_back(std::move(c)); return static_cast<sort_config_id>(sort_configs_.size()) - 1; }

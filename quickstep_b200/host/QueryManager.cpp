@@ -20,7 +20,7 @@ void QueryManager::markOperatorFinished(std::size_t op) {
   for (const QueryPlan::Edge &e : plan_->consumers(op)) {
     RelationalOperator *consumer = plan_->op(e.consumer);
     if (dest != nullptr && out_rel >= 0) {
-      for (block_id b : dest->getTouchedBlocks()) consumer->feedInputBlock(b, out_rel, 0);
+      for (const std::pair<block_id, partition_id> &b : dest->getTouchedBlocks()) consumer->feedInputBlock(b.first, out_rel, b.second);
       consumer->doneFeedingInputBlocks(out_rel);
     }
     if (e.is_pipeline_breaker) --blocking_deps_[e.consumer];

@@ -504,8 +504,40 @@ std::vector<DeviceExtent> StorageManager::stagedExtents(const CatalogRelation &r
   return R.runs;
 }
 
+std::vector<block_id> StorageManager::repartitionTemporary(const CatalogRelation &rel, attribute_id partition_attribute,
+                                                           std::size_t num_partitions) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = temporaries_.find(rel.getID());
+  QS_CHECK(it != temporaries_.end());
+  std::uint64_t n = 0;
+  QS_CHECK_GPU(qsgpu_relation_num_rows(it->second, &n));            // the producer has finished: its count is final
+  const std::vector<qs_attr> schema = rel.schema();
+  qsgpu_relation_t out = nullptr;
+  QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(), std::max<std::uint64_t>(n, 1), &out));
+  std::vector<std::uint64_t> offsets(num_partitions + 1, 0);
+  QS_CHECK_GPU(qsgpu_hash_partition(it->second, static_cast<std::uint32_t>(partition_attribute), static_cast<std::uint32_t>(num_partitions),
+                                    out, offsets.data()));
+  QS_CHECK_GPU(qsgpu_relation_set_num_rows(out, n));
+  QS_CHECK_GPU(qsgpu_relation_destroy(it->second));
+  it->second = out;                                                  // the temporary IS the partitioned relation from now on
+  std::vector<block_id> blocks;
+  for (std::size_t p = 0; p < num_partitions; ++p) {
+    DeviceExtent e;
+    e.relation = out;
+    e.row_begin = offsets[p];
+    e.row_end = offsets[p + 1];
+    const block_id b = next_block_++;
+    partition_extents_[b] = e;
+    blocks.push_back(b);
+  }
+  partition_blocks_[rel.getID()] = blocks;
+  return blocks;
+}
+
 DeviceExtent StorageManager::blockExtent(block_id id) {
   std::lock_guard<std::mutex> lk(mu_);
+  auto pe = partition_extents_.find(id);
+  if (pe != partition_extents_.end()) return pe->second;
   auto t = blocks_.find(id);
   if (t == blocks_.end()) {          // pseudo block of a temporary relation: every row produced so far
     for (auto &kv : temporary_block_)
@@ -584,6 +616,11 @@ qsgpu_relation_t StorageManager::replicated(const CatalogRelation &rel) {
 void StorageManager::dropTemporary(const CatalogRelation &rel) {
   std::lock_guard<std::mutex> lk(mu_);
   partitioned_.erase(rel.getID());
+  auto pb = partition_blocks_.find(rel.getID());
+  if (pb != partition_blocks_.end()) {
+    for (block_id b : pb->second) partition_extents_.erase(b);
+    partition_blocks_.erase(pb);
+  }
   auto rb = result_blocks_.find(rel.getID());
   if (rb != result_blocks_.end()) {          // host blocks written by insertTuples(): buffers go back to the pool
     for (block_id b : rb->second) {

@@ -135,6 +135,10 @@ class StorageManager {
   block_id createTemporary(const CatalogRelation &rel, std::uint64_t capacity_rows);
   void adoptTemporary(const CatalogRelation &rel, qsgpu_relation_t handle);   // takes ownership
   qsgpu_relation_t temporary(const CatalogRelation &rel);
+  // PartitionAwareInsertDestination: regroup the rows of a temporary relation by HashPartitionSchemeHeader's
+  // partition function on `partition_attribute` (K8, qsgpu_hash_partition) and hand back one pseudo block per
+  // partition; blockExtent() of block p is the row range of partition p.
+  std::vector<block_id> repartitionTemporary(const CatalogRelation &rel, attribute_id partition_attribute, std::size_t num_partitions);
   void dropTemporary(const CatalogRelation &rel);
 
  private:
@@ -168,6 +172,8 @@ class StorageManager {
   std::map<relation_id, bool> partitioned_;
   qsgpu_comm_t comm_ = nullptr;
   std::map<relation_id, block_id> temporary_block_;
+  std::map<block_id, DeviceExtent> partition_extents_;                 // pseudo blocks of repartitioned temporaries
+  std::map<relation_id, std::vector<block_id>> partition_blocks_;
 };
 
 }  // namespace quickstep

@@ -140,6 +140,66 @@ static void testExistenceMapAggregation(StorageManager *sm, WorkerPool *pool) {
   std::printf("existence_map_aggregation %s (%llu groups)\n", got == want ? "ok" : "MISMATCH", static_cast<unsigned long long>(n));
 }
 
+// SelectOperator writing through a PartitionAwareInsertDestination (hash partition scheme on the key, 4 and 3
+// partitions), an AggregationOperator consuming the partitions: one work order per partition, every row in the
+// partition HashPartitionSchemeHeader::getPartitionId assigns it to, and the same aggregate as without repartitioning.
+static void testPartitionAwareInsertDestination(StorageManager *sm, WorkerPool *pool, std::size_t num_partitions) {
+  const std::uint64_t n = 50000;
+  std::vector<std::int32_t> k(n);
+  std::vector<std::int64_t> v(n);
+  for (std::uint64_t i = 0; i < n; ++i) { k[i] = static_cast<std::int32_t>(rnd() % 5000) - 100; v[i] = static_cast<std::int64_t>(rnd() % 1000); }
+  CatalogRelation in(21, "in", {{"k", kInt}, {"v", kLong}});
+  CatalogRelation mid(22, "mid", {{"k", kInt}, {"v", kLong}}, true);
+  CatalogRelation out(23, "out", {{"c", kLong}, {"s", kLong}}, true);
+  sm->loadRelation(&in, {k.data(), v.data()}, n, 9000, TupleStoreLayout::kCompressedColumnStore);
+  QueryContext ctx(sm, sm->device());
+  QueryContext::Predicate pred;
+  pred.root = pred.exprs.cmp(QS_LT, pred.exprs.attr(1, kLong), pred.exprs.lit_int(900));
+  const auto pid = ctx.addPredicate(std::move(pred));
+  HashPartitionSchemeHeader header;
+  header.num_partitions = num_partitions;
+  header.partition_attribute = 0;
+  const auto d_mid = ctx.addPartitionAwareInsertDestination(header, &mid, n);
+  QueryContext::AggregationSpec spec;
+  spec.aggregates = {{QS_AGG_COUNT, -1}, {QS_AGG_SUM, spec.exprs.attr(1, kLong)}};
+  spec.strategy = QS_AGG_SINGLE_STATE;
+  const auto state = ctx.addAggregationState(std::move(spec));
+  const auto d_out = ctx.addInsertDestination(&out, 1);
+  QueryPlan plan;
+  const auto i_sel = plan.addRelationalOperator(new SelectOperator(1, in, /*has_repartition=*/true, mid, d_mid, pid, std::vector<attribute_id>{0, 1}, true));
+  const auto i_agg = plan.addRelationalOperator(new AggregationOperator(1, mid, false, state, num_partitions));
+  const auto i_fin = plan.addRelationalOperator(new FinalizeAggregationOperator(1, state, 1, false, 1, out, d_out));
+  plan.addDirectDependency(i_agg, i_sel, true);          // the repartitioned relation must be complete
+  plan.addDirectDependency(i_fin, i_agg, true);
+  QueryManager qm(&plan, &ctx, sm, pool);
+  qm.run();
+  EXPECT(qm.numWorkOrdersExecuted(i_agg) == num_partitions);
+  // every row sits in the partition the reference's scheme assigns it to
+  std::uint64_t rows_seen = 0;
+  bool placed = true;
+  for (const std::pair<block_id, partition_id> &b : ctx.getInsertDestination(d_mid)->getTouchedBlocks()) {
+    const DeviceExtent e = sm->blockExtent(b.first);
+    std::vector<std::int32_t> keys(std::max<std::uint64_t>(e.row_end - e.row_begin, 1));
+    if (e.row_end > e.row_begin) QS_CHECK_GPU(qsgpu_relation_read(e.relation, 0, e.row_begin, e.row_end - e.row_begin, keys.data()));
+    for (std::uint64_t i = 0; i < e.row_end - e.row_begin; ++i) {
+      const std::uint64_t h = static_cast<std::uint32_t>(keys[i]);        // identity hash of the INT's bit pattern
+      const std::uint64_t p = (num_partitions & (num_partitions - 1)) == 0 ? (h & (num_partitions - 1)) : (h % num_partitions);
+      placed = placed && p == b.second;
+    }
+    rows_seen += e.row_end - e.row_begin;
+  }
+  std::int64_t want_c = 0, want_s = 0;
+  for (std::uint64_t i = 0; i < n; ++i) if (v[i] < 900) { ++want_c; want_s += v[i]; }
+  qsgpu_relation_t rel = sm->temporary(out);
+  const auto c = readColumn<std::int64_t>(rel, 0, 1), s2 = readColumn<std::int64_t>(rel, 1, 1);
+  EXPECT(placed);
+  EXPECT(rows_seen == static_cast<std::uint64_t>(want_c));
+  EXPECT(c[0] == want_c && s2[0] == want_s);
+  sm->dropTemporary(mid);
+  sm->dropTemporary(out);
+  std::printf("partition_aware_insert_destination(%zu) %s\n", num_partitions, (placed && c[0] == want_c && s2[0] == want_s) ? "ok" : "MISMATCH");
+}
+
 int main() {
   int dev = 0;
   if (qsgpu_init(1, &dev) != 0) { std::printf("no CUDA device: %s\n", qsgpu_last_error()); return 2; }
@@ -148,6 +208,8 @@ int main() {
     WorkerPool pool(4);
     testOuterJoinCompositeKey(&sm, &pool);
     testExistenceMapAggregation(&sm, &pool);
+    testPartitionAwareInsertDestination(&sm, &pool, 4);
+    testPartitionAwareInsertDestination(&sm, &pool, 3);
   }
   if (g_failed) { std::printf("%d check(s) failed\n", g_failed); return 1; }
   std::printf("all host GPU tests passed\n");
