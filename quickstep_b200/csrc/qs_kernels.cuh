@@ -391,7 +391,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    for (int r = 0; r < kRows; ++r) bits[r] = valid[r] ? 1u : 0u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
     bool any = false;
@@ -627,7 +627,7 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    for (int r = 0; r < kRows; ++r) bits[r] = valid[r] ? 1u : 0u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
     bool pass[kRows];
@@ -768,7 +768,7 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    for (int r = 0; r < kRows; ++r) bits[r] = valid[r] ? 1u : 0u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
     bool pass[kRows];
@@ -825,7 +825,7 @@ __device__ __forceinline__ void join_build_body(char *smem, const ScanDesc &S, c
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    for (int r = 0; r < kRows; ++r) bits[r] = valid[r] ? 1u : 0u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
     const uint64_t row0 = S.first_row + static_cast<uint64_t>(tile) * kTileRows;
@@ -987,7 +987,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
     tile_valid(S, rt, tile, tid, valid);
     uint32_t bits[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) bits[r] = 1u;
+    for (int r = 0; r < kRows; ++r) bits[r] = valid[r] ? 1u : 0u;
     SinkBase ns;
     vm_run<Q, 0, Q::n_pred>(L, S, stage, tid, regs, bits, ns);
 

@@ -236,6 +236,16 @@ __host__ __device__ constexpr int pred_depth(int pc, int end) {
   return mx;
 }
 
+// LIP probe statistics are kept only by scans that probe SEVERAL filters: the order of a single filter cannot be
+// adapted, and the per-row counters cost the lineitem select of Q3 (one filter) 20 % when they were unconditional
+// (70 -> 80+ registers: one resident CTA per SM fewer).
+template <class Q>
+__host__ __device__ constexpr int lip_ops() {
+  int n = 0;
+  for (int i = 0; i < Q::n_total; ++i) n += Q::code(i).op == OP_LIP ? 1 : 0;
+  return n;
+}
+
 template <class Q, int PC, int END, int SP, int D, class Sink>
 __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const char *__restrict__ stage, int tid,
                                         VmRegs &regs, bool (&pst)[D][kRows], uint32_t (&bits)[kRows], Sink &sink) {
@@ -345,10 +355,14 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         bool b = false;
-        if ((in.flags & 2) == 0 || pst[SP - 1][r]) {
+        // pst[0] starts as the row's validity (rows of a ragged first / last tile outside the scanned range) and only
+        // ever gets AND-ed: invalid rows are never probed
+        if (pst[0][r] && ((in.flags & 2) == 0 || pst[SP - 1][r])) {
           b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, static_cast<int64_t>(acc[r]));
-          ++regs.lip_cnt[in.arg];
-          regs.lip_miss[in.arg] += b ? 0u : 1u;
+          if constexpr (lip_ops<Q>() >= 2) {
+            ++regs.lip_cnt[in.arg];
+            regs.lip_miss[in.arg] += b ? 0u : 1u;
+          }
         }
         pst[SP][r] = b;
       }
@@ -511,6 +525,7 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
 // (LIPFilterAdaptiveProber, utility/lip_filter/LIPFilterAdaptiveProber.hpp:89-232); results never depend on them.
 template <class Q>
 __device__ __forceinline__ void flush_lip_stats(const ScanDesc &S, const VmRegs &regs) {
+  if constexpr (lip_ops<Q>() >= 2)
   static_for<0, kMaxLip>([&](auto ff) {
     constexpr int f = QS_IDX(ff);
     bool probed = false;
