@@ -187,10 +187,33 @@ int qsgpu_dictionary_code_range(uint16_t attr_type, uint16_t attr_width, const v
 int qsgpu_relation_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t *code_width, uint32_t *n_entries,
                               void *dict_out);
 
-/* NULL mask of rows [row_begin, row_begin+n_rows): bit j of word i = attribute j of row row_begin+i is NULL
- * (its stored bytes are zero).  Only the output of a LEFT OUTER join can hold NULLs; all zeros otherwise. */
+/* NULL mask of rows [row_begin, row_begin+n_rows): bit j of word i = attribute j of row row_begin+i is NULL.
+ * All zeros for a relation without NULL-able attributes. */
 int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows,
                               uint64_t *host_out);
+/*
+ * NULL-able attributes of a base relation.  The reference types every attribute as nullable or not
+ * (types/Type.hpp:129 isNullable) and picks NULL-checking code paths from that; qsgpu_relation_set_nullable declares
+ * the set (bit a = attribute a may be NULL) before the relation is staged or written.  From then on every operator
+ * that reads one of these attributes also reads the relation's per-row NULL mask (8 bytes per row, moved by the same
+ * TMA pipeline as the columns):
+ *   - a comparison with a NULL operand is false (LiteralComparators-inl.hpp:168-223), NOT complements it
+ *     (NegationPredicate::getAllMatches), arithmetic over a NULL is NULL;
+ *   - SUM / AVG / MIN / MAX / COUNT(x) skip NULL arguments (AggregationHandleSum.hpp:117-127) and are NULL (COUNT: 0)
+ *     for a group without a non-NULL argument -- declare such aggregates in qs_agg_spec.nullable_arguments;
+ *   - rows with a NULL join key neither enter a join table nor match (storage/HashTable.hpp:1384,1903), and are not
+ *     inserted into / are rejected by LIP filters;
+ *   - Select and the probe side of an inner join carry the NULL-ness of what they project into the output relation.
+ * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): GROUP BY, sort, partitioning, anti / outer join keys and
+ * build-side projections on a NULL-able attribute, and NULL-able attributes held as relation-wide dictionary codes.
+ * qsgpu_relation_write_nulls sets the masks of rows written through qsgpu_relation_column / qsgpu_relation_wrap
+ * (their stored values should be zero bytes); qsgpu_stage_blocks fills them from the block formats' own NULL
+ * representations (qs_stage_desc.null_kind).
+ */
+int qsgpu_relation_set_nullable(qsgpu_relation_t rel, uint64_t attr_mask);
+int qsgpu_relation_nullable(qsgpu_relation_t rel, uint64_t *attr_mask);
+int qsgpu_relation_write_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, const uint64_t *masks);
+
 /* All attributes at once: host_out[a] receives rows [row_begin, row_begin+n_rows) of attribute a; the
  * copies are queued back to back and waited for once (result relations are a handful of rows wide and
  * tall: one synchronisation instead of one per column). */
@@ -235,7 +258,15 @@ typedef struct qs_stage_desc {
   uint32_t stride;       /* STRIDED: tuple slot bytes                          */
   const void *dict;      /* DICT: values array (native width, sorted)          */
   uint32_t dict_entries; /* DICT: number of codes                              */
+  /* NULL values of the stripe (QS_NULL_*, qsgpu_types.h; batched staging only).  The attribute must have been
+   * declared with qsgpu_relation_set_nullable.  A NULL value is stored as zero bytes and its bit is set in the
+   * relation's per-row NULL mask. */
+  uint32_t null_kind;
+  uint32_t null_arg;        /* CODE: the NULL code; BITMAP: bit of row 0; SLOT_WORD: bit inside the word, from the MSB */
+  uint32_t null_stride;     /* BITMAP: bits from one row to the next; SLOT_WORD: bytes from one row's word to the next */
+  uint32_t null_width;      /* SLOT_WORD: bytes of the word (1, 2, 4 or 8)                                             */
   uint32_t reserved;
+  const void *null_bitmap;  /* BITMAP / SLOT_WORD: inside the block image                                              */
 } qs_stage_desc;
 
 /* Stage `n_desc` attributes of one block of `n_rows` tuples; all attributes
@@ -374,6 +405,11 @@ typedef struct qs_agg_spec {
   const int32_t *group_by_roots;     /* attribute nodes                       */
   uint64_t estimated_num_entries;    /* table sizing (proto field 5)          */
   int64_t collision_free_max_key;    /* QS_AGG_COLLISION_FREE: num_entries-1  */
+  /* bit j: the argument of aggregate j has a NULL-able type.  The reference picks the handle's code path from the
+   * argument type (AggregateFunctionSum::createHandle; AggregationHandleSum.hpp:117-127 skips NULL values, the AVG
+   * and COUNT(x) handles count the non-NULL ones); here such an aggregate gets one more state word, its count of
+   * non-NULL arguments, which finalization uses instead of the group's row count.                             */
+  uint64_t nullable_arguments;
 } qs_agg_spec;
 
 typedef struct qsgpu_agg_state *qsgpu_agg_state_t;
@@ -608,12 +644,13 @@ int qsgpu_kernel_ms_stats(uint32_t family, float *last, float *max, float *sum, 
  * `which` (0..QSGPU_JIT_SELFCHECK_CASES-1: Q6-style single-state aggregate,
  * Q1-style compact-key group-by, select with LIP probes, BuildLIPFilter, join
  * build, inner probe with residual, anti probe, hash group-by, dense group-by,
- * dense join build, dense inner probe, LEFT OUTER probe)
+ * dense join build, dense inner probe, LEFT OUTER probe, Q6 / Q1 / a join probe over dictionary codes, and
+ * aggregates / Select / an inner join probe over NULL-able attributes)
  * WITHOUT a device -- the "does every kernel family still compile" check of
  * build() and the CPU test suite.  The generated CUDA source and the NVRTC log
  * are copied into the optional buffers.
  */
-#define QSGPU_JIT_SELFCHECK_CASES 12
+#define QSGPU_JIT_SELFCHECK_CASES 19
 int qsgpu_jit_selfcheck(uint32_t which, char *source_out, size_t source_bytes,
                         char *log_out, size_t log_bytes);
 /* NVRTC compilations / disk-cache hits / in-memory hits since load. */

@@ -57,6 +57,20 @@ enum {
 enum { QS_ENC_PLAIN = 0, QS_ENC_STRIDED = 1, QS_ENC_DICT = 2, QS_ENC_TRUNCATED = 3,
        QS_ENC_SKIP = 4 /* batched staging only: leave this attribute on the host (column pruning) */ };
 
+/* How a staged stripe marks NULL values (qs_stage_desc.null_kind):
+ *   QS_NULL_CODE       dictionary-compressed stripe: the code null_arg means NULL (CompressionDictionaryLite keeps it
+ *                      behind the number of codes, compression/CompressionDictionaryLite.hpp:40-51; the builder
+ *                      assigns it in CompressionDictionaryBuilder::buildDictionary)
+ *   QS_NULL_BITMAP     a BitVector<false> (64-bit words, most significant bit first, utility/BitVector.hpp:934): bit
+ *                      null_arg + row * null_stride.  Column stores keep one bitmap per NULL-able uncompressed
+ *                      attribute (stride 1; storage/BasicColumnStoreTupleStorageSubBlock.hpp:230,
+ *                      storage/CompressedColumnStoreTupleStorageSubBlock.cpp:252-312)
+ *   QS_NULL_SLOT_WORD  SplitRowStore: every tuple slot starts with a BitVector<true> over the relation's NULL-able
+ *                      attributes (a 1/2/4-byte word up to 32 of them, 64-bit words beyond;
+ *                      storage/SplitRowStoreTupleStorageSubBlock.cpp:130,348): bit null_arg, counted from the most
+ *                      significant bit, of the null_width-byte word at null_bitmap + row * null_stride           */
+enum { QS_NULL_NONE = 0, QS_NULL_CODE = 1, QS_NULL_BITMAP = 2, QS_NULL_SLOT_WORD = 3 };
+
 /* Join types (relational_operators/HashJoinOperator.hpp:82-87). */
 enum { QS_JOIN_INNER = 0, QS_JOIN_LEFT_SEMI = 1, QS_JOIN_LEFT_ANTI = 2, QS_JOIN_LEFT_OUTER = 3 };
 

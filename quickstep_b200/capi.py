@@ -24,6 +24,7 @@ QS_N_TRUE, QS_N_FALSE, QS_N_COMPARISON, QS_N_NEGATION, QS_N_CONJUNCTION, QS_N_DI
 QS_ENC_PLAIN, QS_ENC_STRIDED, QS_ENC_DICT, QS_ENC_TRUNCATED, QS_ENC_SKIP = range(5)
 QS_LIP_BITVECTOR_EXACT, QS_LIP_SINGLE_IDENTITY_HASH = 0, 1
 QS_AGG_SINGLE_STATE, QS_AGG_COMPACT_KEY, QS_AGG_SEPARATE_CHAINING, QS_AGG_COLLISION_FREE = range(4)
+QS_NULL_NONE, QS_NULL_CODE, QS_NULL_BITMAP, QS_NULL_SLOT_WORD = range(4)
 QS_JOIN_INNER, QS_JOIN_LEFT_SEMI, QS_JOIN_LEFT_ANTI, QS_JOIN_LEFT_OUTER = range(4)
 (QS_K_SCAN_AGG, QS_K_SELECT, QS_K_LIP, QS_K_JOIN_BUILD, QS_K_JOIN_PROBE, QS_K_GROUPBY,
  QS_K_PARTITION, QS_K_TOPK, QS_K_STAGE) = range(9)
@@ -60,7 +61,9 @@ class qs_attr(C.Structure):
 class qs_stage_desc(C.Structure):
     _fields_ = [("attr", C.c_uint32), ("encoding", C.c_uint32), ("host", C.c_void_p),
                 ("code_width", C.c_uint32), ("stride", C.c_uint32), ("dict", C.c_void_p),
-                ("dict_entries", C.c_uint32), ("reserved", C.c_uint32)]
+                ("dict_entries", C.c_uint32), ("null_kind", C.c_uint32), ("null_arg", C.c_uint32),
+                ("null_stride", C.c_uint32), ("null_width", C.c_uint32), ("reserved", C.c_uint32),
+                ("null_bitmap", C.c_void_p)]
 
 
 class qs_block_image(C.Structure):
@@ -95,7 +98,7 @@ class qs_agg_spec(C.Structure):
                 ("predicate_root", C.c_int32), ("n_aggregates", C.c_uint32),
                 ("aggregates", C.POINTER(qs_aggregate)), ("n_group_by", C.c_uint32),
                 ("group_by_roots", C.POINTER(C.c_int32)), ("estimated_num_entries", C.c_uint64),
-                ("collision_free_max_key", C.c_int64)]
+                ("collision_free_max_key", C.c_int64), ("nullable_arguments", C.c_uint64)]
 
 
 class qs_sort_key(C.Structure):
@@ -135,6 +138,9 @@ SIGNATURES = {
                                               C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
     "qsgpu_relation_dictionary": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _VP]),
     "qsgpu_relation_read_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
+    "qsgpu_relation_set_nullable": (C.c_int, [_VP, C.c_uint64]),
+    "qsgpu_relation_nullable": (C.c_int, [_VP, _U64P]),
+    "qsgpu_relation_write_nulls": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _U64P]),
     "qsgpu_relation_read_all": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VPP]),
     "qsgpu_relation_read_rows": (C.c_int, [_VP, C.c_uint64, _VPP, _U64P, _U64P]),
     "qsgpu_stage_block": (C.c_int, [_VP, C.c_uint64, C.POINTER(qs_stage_desc), C.c_uint32]),
@@ -193,7 +199,7 @@ SIGNATURES = {
     "qsgpu_jit_selfcheck": (C.c_int, [C.c_uint32, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "qsgpu_jit_stats": (C.c_int, [_U64P, _U64P, _U64P]),
 }
-JIT_SELFCHECK_CASES = 15
+JIT_SELFCHECK_CASES = 19
 
 
 class QsGpuError(RuntimeError):

@@ -286,6 +286,11 @@ static int fill_scan(const qsgpu_relation *rel, uint64_t row_begin, uint64_t row
   S->n_cols = static_cast<uint32_t>(L.staged_attrs.size());
   for (uint32_t c = 0; c < S->n_cols; ++c) {
     const uint32_t a = L.staged_attrs[c];
+    if (a == Lowering::kNullMaskAttr) {       // the per-row NULL mask, staged like a LONG column
+      S->cols[c].ptr = reinterpret_cast<const char *>(rel->d_nulls);
+      S->cols[c].width = 8;
+      continue;
+    }
     S->cols[c].ptr = rel->cols[a];
     S->cols[c].width = rel->attrs[a].width;
     if (const uint32_t cw = rel->code_width(a)) {
@@ -332,6 +337,16 @@ static uint16_t attr_width(uint16_t type, uint16_t width) {
 
 static size_t padded_bytes(uint64_t rows, uint32_t width) {
   return ((rows * width + 255) & ~static_cast<uint64_t>(255)) + 256;   // 16+ readable bytes past the end
+}
+
+// The per-row NULL mask of a relation (bit a = attribute a is NULL), allocated on first need, all zeros.  Scans
+// stage it like a LONG column, so it is padded like one.
+int ensure_null_mask(qsgpu_relation *rel, Device *d) {
+  if (rel->d_nulls) return QSGPU_OK;
+  const size_t bytes = padded_bytes(std::max<uint64_t>(rel->capacity, 1), 8);
+  QS_CUDA(dev_malloc(&rel->d_nulls, bytes));
+  QS_CUDA(cudaMemsetAsync(rel->d_nulls, 0, bytes, d->stream));
+  return QSGPU_OK;
 }
 
 }  // namespace qs
@@ -663,6 +678,7 @@ int qsgpu_relation_set_dictionary(qsgpu_relation_t rel, uint32_t attr, uint32_t 
   int st = sync_rows(rel);
   if (st) return st;
   if (attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "attribute id out of range"); return QSGPU_ERR_INVALID; }
+  if (attr < 64 && ((rel->nullable_mask >> attr) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "a NULL-able attribute is held at native width, not as codes of a relation-wide dictionary"); return QSGPU_ERR_UNSUPPORTED; }
   if (code_width != 1 && code_width != 2 && code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); return QSGPU_ERR_INVALID; }
   if (!dict_values || n_entries == 0 || (code_width < 4 && n_entries > (1u << (8 * code_width)))) {
     set_error(QSGPU_ERR_INVALID, "dictionary is empty or has more entries than the code width can address");
@@ -736,6 +752,29 @@ int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t
   if (row_begin + n_rows > rel->host_rows) { set_error(QSGPU_ERR_INVALID, "read outside relation"); return QSGPU_ERR_INVALID; }
   if (!rel->d_nulls) { std::memset(host_out, 0, n_rows * 8); return QSGPU_OK; }
   return qsgpu_memcpy_d2h(rel->dev, host_out, rel->d_nulls + row_begin, n_rows * 8);
+}
+
+int qsgpu_relation_set_nullable(qsgpu_relation_t rel, uint64_t attr_mask) {
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (rel->attrs.size() < 64 && (attr_mask >> rel->attrs.size()) != 0) { set_error(QSGPU_ERR_INVALID, "NULL-able attribute out of range"); return QSGPU_ERR_INVALID; }
+  for (size_t a = 0; a < rel->attrs.size() && a < 64; ++a)
+    if (((attr_mask >> a) & 1ull) && rel->code_width(static_cast<uint32_t>(a))) { set_error(QSGPU_ERR_UNSUPPORTED, "a NULL-able attribute is held at native width, not as codes of a relation-wide dictionary"); return QSGPU_ERR_UNSUPPORTED; }
+  if (attr_mask) { const int st = ensure_null_mask(rel, d); if (st) return st; }
+  rel->nullable_mask |= attr_mask;
+  return QSGPU_OK;
+}
+
+int qsgpu_relation_nullable(qsgpu_relation_t rel, uint64_t *attr_mask) { *attr_mask = rel->nullable_mask; return QSGPU_OK; }
+
+int qsgpu_relation_write_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, const uint64_t *masks) {
+  Device *d = device(rel->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (row_begin + n_rows > rel->capacity) { set_error(QSGPU_ERR_INVALID, "write_nulls out of range"); return QSGPU_ERR_INVALID; }
+  if (!rel->d_nulls) { set_error(QSGPU_ERR_INVALID, "write_nulls on a relation without NULL-able attributes (qsgpu_relation_set_nullable first)"); return QSGPU_ERR_INVALID; }
+  for (uint64_t i = 0; i < n_rows; ++i)
+    if (masks[i] & ~rel->nullable_mask) { set_error(QSGPU_ERR_INVALID, "NULL bit of an attribute that is not NULL-able"); return QSGPU_ERR_INVALID; }
+  return qsgpu_memcpy_h2d(rel->dev, rel->d_nulls + row_begin, masks, n_rows * 8);
 }
 
 int qsgpu_relation_read_all(qsgpu_relation_t rel, uint64_t row_begin, uint64_t n_rows, void *const *host_out) {
@@ -839,6 +878,7 @@ int qsgpu_stage_block(qsgpu_relation_t rel, uint64_t n_rows, const qs_stage_desc
   for (uint32_t i = 0; i < n_desc && rc == QSGPU_OK; ++i) {
     const qs_stage_desc &s = descs[i];
     if (s.attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "stage: attribute out of range"); rc = QSGPU_ERR_INVALID; break; }
+    if (s.null_kind != QS_NULL_NONE) { set_error(QSGPU_ERR_UNSUPPORTED, "stripes with NULLs are staged with qsgpu_stage_blocks"); rc = QSGPU_ERR_UNSUPPORTED; break; }
     const uint32_t w = rel->attrs[s.attr].width;
     char *dst = rel->cols[s.attr] + rel->host_rows * w;
     cudaError_t e = cudaSuccess;
@@ -950,6 +990,7 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
         // block image), so the host does no per-value work; the decode kernel then sees the table as a dictionary
         // whose "values" are gcw-byte codes.
         if (s.encoding != QS_ENC_DICT) { set_error(QSGPU_ERR_UNSUPPORTED, "a dictionary-coded attribute is staged from dictionary-compressed stripes only"); rc = QSGPU_ERR_UNSUPPORTED; break; }
+        if (s.null_kind != QS_NULL_NONE) { set_error(QSGPU_ERR_UNSUPPORTED, "a NULL-able attribute is held at native width, not as codes of a relation-wide dictionary"); rc = QSGPU_ERR_UNSUPPORTED; break; }
         if (s.code_width != 1 && s.code_width != 2 && s.code_width != 4) { set_error(QSGPU_ERR_INVALID, "code width must be 1, 2 or 4"); rc = QSGPU_ERR_INVALID; break; }
         const char *hd = static_cast<const char *>(s.dict);
         bytes = B.n_rows * s.code_width;
@@ -1013,6 +1054,34 @@ static int stage_impl(qsgpu_relation *rel, uint64_t first_row, bool append, uint
       const bool code_al = s.code_width <= 1 || (reinterpret_cast<uintptr_t>(g.src) % s.code_width) == 0;
       g.aligned = (val_al ? 1u : 0u) | (code_al ? 2u : 0u) | (rel->attrs[s.attr].type == QS_DATE ? 4u : 0u) |
                   ((rel->attrs[s.attr].type == QS_CHAR && w > 1) ? 8u : 0u);
+      if (s.null_kind != QS_NULL_NONE && B.n_rows) {
+        // the stripe's own NULL representation -> the relation's per-row mask (+ zero bytes for the value)
+        if (s.attr >= 64 || !((rel->nullable_mask >> s.attr) & 1ull) || !rel->d_nulls) { set_error(QSGPU_ERR_INVALID, "stage: NULL information for an attribute not declared with qsgpu_relation_set_nullable"); rc = QSGPU_ERR_INVALID; break; }
+        const char *hb = static_cast<const char *>(s.null_bitmap);
+        uint64_t nbytes = 0;
+        switch (s.null_kind) {
+          case QS_NULL_CODE:
+            if (s.encoding != QS_ENC_DICT) { set_error(QSGPU_ERR_INVALID, "stage: a NULL code belongs to a dictionary-compressed stripe"); rc = QSGPU_ERR_INVALID; }
+            break;
+          case QS_NULL_BITMAP:
+            nbytes = (((s.null_arg + (B.n_rows - 1) * static_cast<uint64_t>(s.null_stride)) >> 6) + 1) * 8;
+            break;
+          case QS_NULL_SLOT_WORD:
+            if ((s.null_width != 1 && s.null_width != 2 && s.null_width != 4 && s.null_width != 8) || s.null_arg >= 8 * s.null_width) { set_error(QSGPU_ERR_INVALID, "stage: bad NULL word width / bit"); rc = QSGPU_ERR_INVALID; }
+            nbytes = (B.n_rows - 1) * static_cast<uint64_t>(s.null_stride) + s.null_width;
+            break;
+          default: set_error(QSGPU_ERR_INVALID, "unknown NULL representation"); rc = QSGPU_ERR_INVALID;
+        }
+        if (rc != QSGPU_OK) break;
+        if (nbytes) {
+          if (!hb || hb < h0 || hb + nbytes > h0 + B.bytes) { set_error(QSGPU_ERR_INVALID, "stage: NULL bitmap lies outside the block image"); rc = QSGPU_ERR_INVALID; break; }
+          g.null_src = reinterpret_cast<const unsigned char *>(d_img + img_off[b] + (hb - h0));
+          need.emplace_back(static_cast<uint64_t>(hb - h0), nbytes);
+        }
+        g.null_kind = s.null_kind; g.null_arg = s.null_arg; g.null_stride = s.null_stride; g.null_width = s.null_width;
+        g.null_dst = rel->d_nulls + row_base;
+        g.null_bit = 1ull << s.attr;
+      }
       if (B.n_rows) {
         segs.push_back(g);
         cur.tiles += (B.n_rows + kStageTileRows - 1) / kStageTileRows;
@@ -1172,11 +1241,19 @@ int qsgpu_lip_probe_stats(qsgpu_lip_t lip, uint64_t *probes, uint64_t *misses) {
 }
 
 /* --------------------------------------------- shared scan-side lowering */
-static int lower_scan_predicate(Lowering &L, const qs_scan *scan) {
+// key_attrs: attributes whose NULL rows take no part in the operator (join / LIP-build keys: HashTable::
+// putValueAccessor and getAllFromValueAccessor skip NULL keys, storage/HashTable.hpp:1384,1903).
+static int lower_scan_predicate(Lowering &L, const qs_scan *scan, uint64_t key_attrs = 0) {
   bool have = false;
   if (scan->predicate_root >= 0) { L.lower_pred(scan->predicate_root); have = true; }
+  if (const uint64_t nb = key_attrs & scan->input->nullable_mask) { L.push_notnull(nb, have); have = true; }
   for (uint32_t i = 0; i < scan->n_lip_probe; ++i) {
-    L.lower_lip_probe(i, scan->lip_probe[i].attr, have);
+    const uint32_t pa = scan->lip_probe[i].attr;
+    if (scan->lip_probe[i].lip && scan->lip_probe[i].lip->d.is_anti && pa < 64 && ((scan->input->nullable_mask >> pa) & 1ull)) {
+      set_error(QSGPU_ERR_UNSUPPORTED, "anti LIP filter probed with a NULL-able attribute");
+      return QSGPU_ERR_UNSUPPORTED;
+    }
+    L.lower_lip_probe(i, pa, have);
     have = true;
   }
   L.mark_pred_end();
@@ -1191,6 +1268,9 @@ static int fill_lip_build(uint32_t n, const qs_lip_ref *refs, Lowering &L, const
     if (!refs[i].lip || refs[i].lip->dev != rel->dev || refs[i].attr >= rel->attrs.size()) { set_error(QSGPU_ERR_INVALID, "bad LIP build reference"); return QSGPU_ERR_INVALID; }
     const uint8_t lt = vtype_of(rel->attrs[refs[i].attr].type);
     if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "LIP filters take INT/LONG attributes"); return QSGPU_ERR_UNSUPPORTED; }
+    // one target: the caller AND-ed "attribute is not NULL" into the scan predicate; several targets over different
+    // NULL-able attributes would each need their own row set
+    if (n > 1 && refs[i].attr < 64 && ((rel->nullable_mask >> refs[i].attr) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "several LIP filters built from NULL-able attributes by one scan"); return QSGPU_ERR_UNSUPPORTED; }
     K->lip_build[i] = refs[i].lip->d;
     K->lip_build_col[i] = static_cast<uint16_t>(L.stage_attr(refs[i].attr));
     K->lip_build_ltype[i] = lt;
@@ -1204,6 +1284,7 @@ static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *root
   if (n_project > static_cast<uint32_t>(kMaxOut)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxOut projected columns"); return QSGPU_ERR_UNSUPPORTED; }
   if (n_project != output->attrs.size()) { set_error(QSGPU_ERR_INVALID, "projection list does not match the output relation"); return QSGPU_ERR_INVALID; }
   K->n_out = n_project;
+  uint64_t null_cols = 0;
   for (uint32_t j = 0; j < n_project; ++j) {
     const qs_node *n = L.node(roots[j]);
     if (!n) break;
@@ -1232,9 +1313,20 @@ static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *root
       in.op = OP_EMIT; in.type = to; in.arg = static_cast<uint16_t>(j);
       L.push(in);
     }
+    // NULL-ness of the projected column: a scalar over a NULL attribute is NULL (its stored bytes are whatever
+    // the arithmetic on the zero bytes gave; the mask is what counts, as in the reference's ColumnVector)
+    if (const uint64_t nb = L.null_bits(roots[j])) {
+      L.lower_emit_null(j, nb);
+      null_cols |= 1ull << j;
+    }
   }
   L.finish();
   if (!L.ok()) { set_error(L.status, L.err); return L.status; }
+  if (null_cols) {
+    if (!t_sc) { const int ns = ensure_null_mask(output, device(output->dev)); if (ns) return ns; }
+    output->nullable_mask |= null_cols;
+    K->null_out = output->d_nulls;
+  }
   return QSGPU_OK;
 }
 
@@ -1243,7 +1335,9 @@ int qsgpu_build_lip_filter(const qs_scan *scan, uint32_t n_build, const qs_lip_r
   Device *d = device(rel->dev);
   if (!d) return QSGPU_ERR_NO_DEVICE;
   Lowering L(scan->exprs, rel);
-  int st = lower_scan_predicate(L, scan);
+  uint64_t key_mask = 0;
+  for (uint32_t i = 0; i < n_build; ++i) if (build[i].attr < 64) key_mask |= 1ull << build[i].attr;
+  int st = lower_scan_predicate(L, scan, key_mask);
   if (st) return st;
   SinkDesc K{};
   K.error_flag = d->d_error;
@@ -1331,6 +1425,7 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
   // ---- value words: one per SUM/AVG/MIN/MAX, COUNT reads the row-count word
   Lowering typer(&s->exprs, nullptr);
   uint32_t n_agg = 0;
+  s->nn_word.assign(s->aggregates.size(), 0);
   for (const qs_aggregate &a : s->aggregates) {
     if (a.function == QS_AGG_COUNT) { s->value_word.push_back(0); s->arg_vtype.push_back(V_I64); continue; }
     if (a.argument_root < 0) { set_error(QSGPU_ERR_INVALID, "aggregate without an argument"); return QSGPU_ERR_INVALID; }
@@ -1352,6 +1447,21 @@ int qsgpu_agg_create(const qs_agg_spec *spec, qsgpu_agg_state_t *out) {
     s->value_word.push_back(static_cast<int>(1 + n_agg));
     s->arg_vtype.push_back(own);
     ++n_agg;
+  }
+  // NULL-able arguments: one SUM_I64 word per distinct argument counts the rows whose argument is not NULL
+  // (aggregates over the same argument share it); COUNT(x) reads that word, AVG divides by it, and SUM / MIN / MAX
+  // are NULL where it is zero.  It merges across CTAs, work orders and GPUs like any other integer sum.
+  for (size_t j = 0; j < s->aggregates.size(); ++j) {
+    if (j >= 64 || !((spec->nullable_arguments >> j) & 1ull) || s->aggregates[j].argument_root < 0) continue;
+    for (size_t i = 0; i < j; ++i)
+      if (s->nn_word[i] && s->aggregates[i].argument_root == s->aggregates[j].argument_root) { s->nn_word[j] = s->nn_word[i]; break; }
+    if (!s->nn_word[j]) {
+      if (n_agg >= static_cast<uint32_t>(kMaxAgg)) { set_error(QSGPU_ERR_UNSUPPORTED, "more than kMaxAgg state words (value aggregates + non-NULL counts) in one state"); return QSGPU_ERR_UNSUPPORTED; }
+      A.kind[n_agg] = AK_SUM_I64;
+      s->nn_word[j] = static_cast<int>(1 + n_agg);
+      ++n_agg;
+    }
+    if (s->aggregates[j].function == QS_AGG_COUNT) s->value_word[j] = s->nn_word[j];
   }
   A.n_agg = n_agg;
   A.words = n_agg + 1;
@@ -1510,16 +1620,39 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     if (attr >= input->attrs.size() || input->attrs[attr].width != A.key_width[k]) { set_error(QSGPU_ERR_INVALID, "group-by attribute does not match the input relation"); return QSGPU_ERR_INVALID; }
     A.key_col[k] = static_cast<uint16_t>(L.stage_attr(attr));
   }
+  if (input->nullable_mask)
+    for (uint32_t k = 0; k < A.n_key_cols; ++k)
+      if (state->key_attr_ids[k] < 64 && ((input->nullable_mask >> state->key_attr_ids[k]) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "GROUP BY a NULL-able attribute"); return QSGPU_ERR_UNSUPPORTED; }
+  std::vector<bool> nn_done(A.n_agg + 1, false);
   for (size_t i = 0; i < state->aggregates.size(); ++i) {
     const int w = state->value_word[i];
-    if (w == 0) continue;
-    const uint8_t t = L.lower_scalar(state->aggregates[i].argument_root);
-    const uint8_t kind = A.kind[w - 1];
-    const uint8_t to = (kind == AK_SUM_F64 || kind == AK_MIN_F64 || kind == AK_MAX_F64) ? V_F64 : V_I64;
-    L.lower_cast_acc(t, to);
-    Instr in{};
-    in.op = OP_EMIT; in.type = to; in.arg = static_cast<uint16_t>(w - 1);
-    L.push(in);
+    const int nw = state->nn_word[i];
+    const int32_t root = state->aggregates[i].argument_root;
+    const uint64_t nb = root >= 0 ? L.null_bits(root) : 0;
+    if (nb && !nw) { set_error(QSGPU_ERR_INVALID, "aggregate over a NULL-able attribute not declared in qs_agg_spec.nullable_arguments"); return QSGPU_ERR_INVALID; }
+    if (w != 0 && w != nw) {
+      const uint8_t t = L.lower_scalar(root);
+      const uint8_t kind = A.kind[w - 1];
+      const uint8_t to = (kind == AK_SUM_F64 || kind == AK_MIN_F64 || kind == AK_MAX_F64) ? V_F64 : V_I64;
+      L.lower_cast_acc(t, to);
+      // a NULL argument leaves the state as it is (AggregationHandleSum.hpp:117-127 `if (value.isNull()) return;`):
+      // the row contributes the identity of the combine (x + 0 = x bit for bit: the accumulators start at +0.0)
+      if (nb) L.lower_null_select(nb, agg_identity(kind));
+      Instr in{};
+      in.op = OP_EMIT; in.type = to; in.arg = static_cast<uint16_t>(w - 1);
+      L.push(in);
+    }
+    if (nw && !nn_done[nw]) {
+      nn_done[nw] = true;
+      Instr ld{};
+      ld.op = OP_LOAD; ld.type = V_I64; ld.leaf = LEAF_LIT; ld.ltype = V_I64;
+      ld.arg = static_cast<uint16_t>(L.add_lit(1));
+      L.push(ld);
+      if (nb) L.lower_null_select(nb, 0);
+      Instr in{};
+      in.op = OP_EMIT; in.type = V_I64; in.arg = static_cast<uint16_t>(nw - 1);
+      L.push(in);
+    }
   }
   L.finish();
   if (!L.ok()) { set_error(L.status, L.err); return L.status; }
@@ -1717,11 +1850,14 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   F.keys_are_slots = state->strategy == QS_AGG_COLLISION_FREE;
   for (uint32_t k = 0; k < A.n_key_cols; ++k) { F.key_width[k] = A.key_width[k]; F.key_off[k] = A.key_off[k]; }
   F.n_out = static_cast<uint32_t>(state->aggregates.size());
+  bool any_nn = false;
   for (size_t j = 0; j < state->aggregates.size(); ++j) {
     const qs_aggregate &a = state->aggregates[j];
     const int w = state->value_word[j];
     F.function[j] = static_cast<uint8_t>(a.function);
     F.word[j] = static_cast<uint8_t>(w);
+    F.nn_word[j] = static_cast<uint8_t>(state->nn_word[j]);
+    any_nn = any_nn || state->nn_word[j] != 0;
     uint8_t kind = w ? A.kind[w - 1] : AK_SUM_I64;
     F.word_is_f64[j] = (kind == AK_SUM_F64 || kind == AK_MIN_F64 || kind == AK_MAX_F64) ? 1 : 0;
     qs_attr oa{};
@@ -1746,15 +1882,15 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   const uint64_t *keys = dense ? A.gid_keys : A.keys;
   F.rows_out = rel->d_rows;
   F.d_n_groups = state->strategy == QS_AGG_COMPACT_KEY ? A.n_groups : nullptr;
-  if (state->strategy == QS_AGG_SINGLE_STATE) {
-    // aggregates over zero rows are SQL NULL: recorded in the output relation's per-row NULL mask
-    if (!rel->d_nulls) {
-      cudaError_t ne = dev_malloc(&rel->d_nulls, 8 * std::max<uint64_t>(rel->capacity, 1));
-      if (ne != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(ne, "finalize null mask"); }
-    }
+  if (state->strategy == QS_AGG_SINGLE_STATE || any_nn) {
+    // aggregates over zero rows -- or, for a NULL-able argument, over zero non-NULL values -- are SQL NULL:
+    // recorded in the output relation's per-row NULL mask
+    if (const int ns = ensure_null_mask(rel, d)) { qsgpu_relation_destroy(rel); return ns; }
     F.null_out = rel->d_nulls;
     for (size_t j = 0; j < state->aggregates.size(); ++j)
-      if (state->aggregates[j].function != QS_AGG_COUNT) F.null_bits |= 1ull << (A.n_key_cols + j);
+      if (state->aggregates[j].function != QS_AGG_COUNT && (state->strategy == QS_AGG_SINGLE_STATE || state->nn_word[j]))
+        F.null_bits |= 1ull << (A.n_key_cols + j);
+    rel->nullable_mask = F.null_bits;
   }
   KernelTimer timer(d, QS_K_GROUPBY);
   cudaError_t e = launch_finalize(A.states, keys, A.words, dense ? nullptr : state->d_idx, n, F, d->stream);
@@ -1763,12 +1899,11 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   if (null_mask) {                    // asked for on the host: this (and only this) waits for the queued work
     *null_mask = 0;
     if (state->strategy == QS_AGG_SINGLE_STATE) {
-      uint64_t count = 0;
-      QS_CUDA(cudaMemcpyAsync(&count, A.states, 8, cudaMemcpyDeviceToHost, d->stream));
+      uint64_t row[kMaxAgg + 1] = {0};
+      QS_CUDA(cudaMemcpyAsync(row, A.states, 8 * A.words, cudaMemcpyDeviceToHost, d->stream));
       QS_CUDA(cudaStreamSynchronize(d->stream));
-      if (count == 0)
-        for (size_t j = 0; j < state->aggregates.size(); ++j)
-          if (state->aggregates[j].function != QS_AGG_COUNT) *null_mask |= 1ull << j;
+      for (size_t j = 0; j < state->aggregates.size(); ++j)
+        if (state->aggregates[j].function != QS_AGG_COUNT && row[state->nn_word[j]] == 0) *null_mask |= 1ull << j;
     }
   }
   if (state->strategy == QS_AGG_COMPACT_KEY) {
@@ -1937,7 +2072,14 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
     }
   }
   Lowering L(scan->exprs, rel);
-  int st = lower_scan_predicate(L, scan);
+  uint64_t key_mask = 0;
+  for (uint32_t i = 0; i < n_keys; ++i) if (key_attrs[i] < 64) key_mask |= 1ull << key_attrs[i];
+  if (n_lip_build == 1 && lip_build[0].attr < 64) {
+    // the filter is built from the rows that enter the table: fine when its attribute is the key (the usual
+    // deployment), otherwise its NULL rows would have to be skipped for the filter alone
+    if (((rel->nullable_mask & ~key_mask) >> lip_build[0].attr) & 1ull) { set_error(QSGPU_ERR_UNSUPPORTED, "LIP filter built from a NULL-able non-key attribute by a join build"); return QSGPU_ERR_UNSUPPORTED; }
+  }
+  int st = lower_scan_predicate(L, scan, key_mask);
   if (st) return st;
   SinkDesc K{};
   K.error_flag = d->d_error;
@@ -2001,7 +2143,15 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
   const uint8_t klt = vtype_of(rel->attrs[probe_key_attr].type);
   if (klt != V_I32 && klt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "probe key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
   Lowering L(probe->exprs, rel, table->build_rel);
-  int st = lower_scan_predicate(L, probe);
+  uint64_t key_mask = 0;
+  for (uint32_t i = 0; i < n_keys; ++i) if (probe_key_attrs[i] < 64) key_mask |= 1ull << probe_key_attrs[i];
+  if ((key_mask & rel->nullable_mask) && (join_type == QS_JOIN_LEFT_ANTI || join_type == QS_JOIN_LEFT_OUTER)) {
+    // such a row counts as "no match found" and IS emitted (HashTable::runOverKeysFromValueAccessor, :1999-2003);
+    // the probe kernel has no "passes but does not search" state yet
+    set_error(QSGPU_ERR_UNSUPPORTED, "anti / outer join probed with a NULL-able key attribute");
+    return QSGPU_ERR_UNSUPPORTED;
+  }
+  int st = lower_scan_predicate(L, probe, key_mask);
   if (st) return st;
   if (residual_root >= 0) { L.lower_pred(residual_root); L.mark_mid_end(); }
   SinkDesc K{};
@@ -2025,11 +2175,9 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
       }
     };
     for (uint32_t j = 0; j < n_project; ++j) if (on_build(project_roots[j])) K.null_bits |= 1ull << j;
-    if (!output->d_nulls && !t_sc) {
-      QS_CUDA(dev_malloc(&output->d_nulls, std::max<uint64_t>(output->capacity, 1) * 8));
-      QS_CUDA(cudaMemsetAsync(output->d_nulls, 0, std::max<uint64_t>(output->capacity, 1) * 8, d->stream));
-    }
+    if (!t_sc) { const int ns = ensure_null_mask(output, d); if (ns) return ns; }
     K.null_out = output->d_nulls;
+    output->nullable_mask |= K.null_bits;
   }
   if (!t_sc) {     // probing a table no build work order ever touched (empty build side): give it its (empty) slots
     std::lock_guard<std::mutex> lk(table->mu);

@@ -374,9 +374,17 @@ int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t c, qsgpu_relat
   qsgpu_relation *rel = nullptr;
   st = qsgpu_relation_create(local->dev, static_cast<uint32_t>(local->attrs.size()), local->attrs.data(), std::max<uint64_t>(total, 1), &rel);
   if (st) return st;
+  // NULL-able attributes: the per-row masks travel like one more column.  Every rank must take the same branch, so
+  // it hangs on the relation's declared set (the same on all ranks of a plan), not on the rows at hand.
+  if (local->nullable_mask) {
+    st = ensure_null_mask(rel, d);
+    if (st) { qsgpu_relation_destroy(rel); return st; }
+    rel->nullable_mask = local->nullable_mask;
+  }
   if (R == 1) {
     for (size_t a = 0; a < local->attrs.size(); ++a)
       if (mine) QS_CUDA(cudaMemcpyAsync(rel->cols[a], local->cols[a], mine * local->attrs[a].width, cudaMemcpyDeviceToDevice, d->stream));
+    if (mine && local->nullable_mask) QS_CUDA(cudaMemcpyAsync(rel->d_nulls, local->d_nulls, mine * 8, cudaMemcpyDeviceToDevice, d->stream));
   } else {
     // all-gather with per-rank counts: one broadcast per (rank, attribute), all in ONE NCCL group
     QS_NCCL(g_nccl.GroupStart());
@@ -387,6 +395,8 @@ int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t c, qsgpu_relat
           const size_t w = local->attrs[a].width;
           QS_NCCL(g_nccl.Broadcast(local->cols[a], rel->cols[a] + first * w, counts[r] * w, ncclChar, r, c->comm, d->stream));
         }
+        if (local->nullable_mask)
+          QS_NCCL(g_nccl.Broadcast(local->d_nulls, rel->d_nulls + first, counts[r] * 8, ncclChar, r, c->comm, d->stream));
       }
       first += counts[r];
     }

@@ -149,10 +149,12 @@ __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_
         }
       }
     }
-    const uint64_t count = states[s * words];
-    if (F.null_out) F.null_out[g] = count == 0 ? F.null_bits : 0ull;
+    uint64_t nulls = 0;
     for (uint32_t j = 0; j < F.n_out; ++j) {
       const uint64_t v = states[s * words + F.word[j]];
+      // rows that count for this aggregate: the group's rows, or those whose (NULL-able) argument was not NULL
+      const uint64_t count = states[s * words + F.nn_word[j]];
+      if (count == 0) nulls |= 1ull << (F.n_key_cols + j);
       uint64_t o;
       uint8_t from;
       if (F.function[j] == QS_AGG_COUNT) { o = count; from = V_I64; }
@@ -171,6 +173,7 @@ __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_
       else
         *reinterpret_cast<uint64_t *>(F.out[j] + g * 8) = o;
     }
+    if (F.null_out) F.null_out[g] = nulls & F.null_bits;
   }
 }
 

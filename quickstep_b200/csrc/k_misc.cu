@@ -542,6 +542,7 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   }
   const uint8_t lt = vtype_of(input->attrs[key_attr].type);
   if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "partition key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  if (key_attr < 64 && ((input->nullable_mask >> key_attr) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "partitioning on a NULL-able attribute"); return QSGPU_ERR_UNSUPPORTED; }
   PartDesc D{};
   D.n_cols = static_cast<uint32_t>(input->attrs.size());
   for (uint32_t c = 0; c < D.n_cols; ++c) {
@@ -549,6 +550,16 @@ static int partition_impl(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
     D.in[c].ptr = input->cols[c];
     D.in[c].width = input->attrs[c].width;
     D.out[c] = output->cols[c];
+  }
+  if (input->nullable_mask) {      // the rows' NULL masks move with them, as one more 8-byte column
+    if (D.n_cols >= static_cast<uint32_t>(kMaxCols)) { set_error(QSGPU_ERR_UNSUPPORTED, "too many attributes to partition along with the NULL mask"); return QSGPU_ERR_UNSUPPORTED; }
+    st = ensure_null_mask(output, d);
+    if (st) return st;
+    output->nullable_mask |= input->nullable_mask;
+    D.in[D.n_cols].ptr = reinterpret_cast<const char *>(input->d_nulls);
+    D.in[D.n_cols].width = 8;
+    D.out[D.n_cols] = reinterpret_cast<char *>(output->d_nulls);
+    ++D.n_cols;
   }
   D.key = input->cols[key_attr];
   D.key_ltype = lt;
@@ -608,6 +619,7 @@ static int fill_part_desc(qsgpu_relation_t input, uint32_t key_attr, uint32_t n_
   }
   const uint8_t lt = vtype_of(input->attrs[key_attr].type);
   if (lt != V_I32 && lt != V_I64) { set_error(QSGPU_ERR_UNSUPPORTED, "partition key must be INT/LONG"); return QSGPU_ERR_UNSUPPORTED; }
+  if (input->nullable_mask) { set_error(QSGPU_ERR_UNSUPPORTED, "peer scatter of a relation with NULL-able attributes"); return QSGPU_ERR_UNSUPPORTED; }
   D->n_cols = static_cast<uint32_t>(input->attrs.size());
   for (uint32_t c = 0; c < D->n_cols; ++c) { D->in[c].ptr = input->cols[c]; D->in[c].width = input->attrs[c].width; }
   D->key = input->cols[key_attr];
@@ -737,6 +749,7 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   D.d_n_rows = device_count ? input->d_rows : nullptr;
   for (uint32_t q = 0; q < n_keys; ++q) {
     if (keys[q].attr >= input->attrs.size()) { set_error(QSGPU_ERR_INVALID, "sort attribute out of range"); return QSGPU_ERR_INVALID; }
+    if (keys[q].attr < 64 && ((input->nullable_mask >> keys[q].attr) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "sorting on a NULL-able attribute (NULLS FIRST / LAST) is not lowered"); return QSGPU_ERR_UNSUPPORTED; }
     const uint8_t lt = vtype_of(input->attrs[keys[q].attr].type);
     uint8_t klt = lt;
     if (lt == 0xff) {
@@ -758,6 +771,16 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     D.in[c].ptr = input->cols[c];
     D.in[c].width = input->attrs[c].width;
     D.out[c] = rel->cols[c];
+  }
+  if (input->nullable_mask) {      // the rows' NULL masks move with them, as one more 8-byte column
+    if (D.n_cols >= static_cast<uint32_t>(kMaxCols)) { qsgpu_relation_destroy(rel); set_error(QSGPU_ERR_UNSUPPORTED, "too many attributes to sort along with the NULL mask"); return QSGPU_ERR_UNSUPPORTED; }
+    st = ensure_null_mask(rel, d);
+    if (st) { qsgpu_relation_destroy(rel); return st; }
+    rel->nullable_mask = input->nullable_mask;
+    D.in[D.n_cols].ptr = reinterpret_cast<const char *>(input->d_nulls);
+    D.in[D.n_cols].width = 8;
+    D.out[D.n_cols] = reinterpret_cast<char *>(rel->d_nulls);
+    ++D.n_cols;
   }
   if (n == 0) { *out = rel; return qsgpu_relation_set_num_rows(rel, 0); }
   if (n <= kTopkSingleCta) {

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
     // behind the terminator): bytes after it are zeroed, so that equal strings are equal bytes
     const bool chr = (sg.aligned & 8) != 0;
     const uint32_t vw = sg.vw;
-    if (sg.encoding == QS_ENC_PLAIN && al && !date && !chr && ((vw * r0) & 15) == 0 &&
+    if (sg.encoding == QS_ENC_PLAIN && al && !date && !chr && sg.null_kind == QS_NULL_NONE && ((vw * r0) & 15) == 0 &&
         ((reinterpret_cast<uintptr_t>(sg.src) | reinterpret_cast<uintptr_t>(sg.dst)) & 15) == 0) {
       // 16-byte vector copy of the tile, byte tail
       const uint64_t b0 = r0 * vw, b1 = r1 * vw;
@@ -113,11 +113,13 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
     }
     for (uint64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
       char *d = sg.dst + i * vw;
+      bool is_null = false;
       switch (sg.encoding) {
         case QS_ENC_PLAIN: copy_vw(d, sg.src + i * vw, vw, al); break;
         case QS_ENC_STRIDED: copy_vw(d, sg.src + i * sg.stride, vw, false); break;
         case QS_ENC_DICT: {
           uint32_t c = load_code_any(reinterpret_cast<const unsigned char *>(sg.src), i, sg.cw, (sg.aligned & 2) != 0);
+          is_null = sg.null_kind == QS_NULL_CODE && c == sg.null_arg;
           if (c >= sg.dict_entries) c = sg.dict_entries - 1;
           copy_vw(d, sg.dict + static_cast<uint64_t>(c) * vw, vw, al);
           break;
@@ -132,6 +134,22 @@ __global__ void __launch_bounds__(256) k_decode_segments(const StageSeg *segs, u
       if (chr) {
         bool ended = false;
         for (uint32_t b = 0; b < vw; ++b) { if (ended) d[b] = 0; else ended = d[b] == 0; }
+      }
+      if (sg.null_kind != QS_NULL_NONE) {
+        // both bitmap forms are most-significant-bit-first bit strings inside little-endian words: one byte load
+        if (sg.null_kind == QS_NULL_BITMAP) {
+          const uint64_t g = sg.null_arg + i * sg.null_stride;
+          is_null = (sg.null_src[(g >> 6) * 8 + 7 - ((g & 63) >> 3)] >> (7 - (g & 7))) & 1;
+        } else if (sg.null_kind == QS_NULL_SLOT_WORD) {
+          is_null = (sg.null_src[i * sg.null_stride + (sg.null_width - 1 - (sg.null_arg >> 3))] >> (7 - (sg.null_arg & 7))) & 1;
+        }
+        // rows of one relation row are decoded by different CTAs (one stripe each): atomics on the shared mask word
+        if (is_null) {
+          for (uint32_t b = 0; b < vw; ++b) d[b] = 0;
+          atomicOr(&sg.null_dst[i], static_cast<unsigned long long>(sg.null_bit));
+        } else {
+          atomicAnd(&sg.null_dst[i], ~static_cast<unsigned long long>(sg.null_bit));
+        }
       }
     }
   }

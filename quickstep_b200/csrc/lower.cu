@@ -76,9 +76,72 @@ int Lowering::stage_attr(uint32_t attr, uint8_t use) {
   return slot_of_attr[attr];
 }
 
+int Lowering::stage_null_mask() {
+  if (null_slot >= 0) return null_slot;
+  if (!rel || !rel->d_nulls) { fail(QSGPU_ERR_INVALID, "relation without a NULL mask"); return 0; }
+  if (staged_attrs.size() >= static_cast<size_t>(kMaxCols)) {
+    fail(QSGPU_ERR_UNSUPPORTED, "more than kMaxCols attributes referenced by one scan");
+    return 0;
+  }
+  null_slot = static_cast<int>(staged_attrs.size());
+  staged_attrs.push_back(kNullMaskAttr);
+  staged_use.push_back(USE_RAW);
+  return null_slot;
+}
+
+// A scalar is NULL when any attribute it reads is (every operation of the path propagates NULL:
+// ArithmeticBinaryOperators.hpp:178-186 applyToTypedValues returns a NULL of the result type).
+uint64_t Lowering::null_bits(int i) {
+  const qs_node *n = node(i);
+  if (!n || !rel) return 0;
+  switch (n->kind) {
+    case QS_N_ATTRIBUTE:
+      if (n->b == 2) {
+        if (build_rel && static_cast<uint32_t>(n->a) < 64 && ((build_rel->nullable_mask >> n->a) & 1ull))
+          fail(QSGPU_ERR_UNSUPPORTED, "NULL-able build-side attribute read through a join");
+        return 0;
+      }
+      return static_cast<uint32_t>(n->a) < 64 ? (rel->nullable_mask & (1ull << n->a)) : 0ull;
+    case QS_N_UNARY: case QS_N_SHARED: return null_bits(n->a);
+    case QS_N_BINARY: return null_bits(n->a) | null_bits(n->b);
+    default: return 0;
+  }
+}
+
+void Lowering::push_notnull(uint64_t bits, bool and_it) {
+  Instr in{};
+  in.op = OP_NOTNULL;
+  in.arg = static_cast<uint16_t>(stage_null_mask());
+  in.aux = static_cast<uint8_t>(add_lit(bits));
+  push(in);
+  if (and_it) { Instr a{}; a.op = OP_AND; push(a); }
+}
+
+void Lowering::lower_null_select(uint64_t bits, uint64_t identity) {
+  Instr in{};
+  in.op = OP_NULLSEL;
+  in.arg = static_cast<uint16_t>(stage_null_mask());
+  in.aux = static_cast<uint8_t>(add_lit(bits));
+  add_lit(identity);
+  push(in);
+}
+
+void Lowering::lower_emit_null(uint32_t out_col, uint64_t bits) {
+  Instr in{};
+  in.op = OP_EMIT_NULL;
+  in.arg = static_cast<uint16_t>(out_col);
+  in.flags = static_cast<uint8_t>(stage_null_mask());
+  in.aux = static_cast<uint8_t>(add_lit(bits));
+  push(in);
+}
+
 int Lowering::build_attr(uint32_t attr) {
   if (!build_rel || attr >= build_rel->attrs.size()) {
     fail(QSGPU_ERR_INVALID, "build-side attribute without a build relation");
+    return 0;
+  }
+  if (attr < 64 && ((build_rel->nullable_mask >> attr) & 1ull)) {
+    fail(QSGPU_ERR_UNSUPPORTED, "NULL-able build-side attribute read through a join");
     return 0;
   }
   if (bslot_of_attr[attr] >= 0) return bslot_of_attr[attr];
@@ -413,73 +476,84 @@ void Lowering::lower_pred(int i) {
       const qs_node *l = node(n->a), *r = node(n->b);
       if (!l || !r) return;
       if (n->op > QS_GE) { fail(QSGPU_ERR_UNSUPPORTED, "LIKE / regex comparisons are not lowered"); return; }
-      {
-        // coded attribute vs literal (either order): evaluated on the codes
-        const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
-        const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
-        if (attr->kind == QS_N_ATTRIBUTE && lit->kind == QS_N_LITERAL && attr->b != 2 && rel &&
-            static_cast<uint32_t>(attr->a) < rel->attrs.size() && rel->code_width(static_cast<uint32_t>(attr->a)) != 0 &&
-            ((attr->type == QS_CHAR) == (lit->type == QS_CHAR)) &&
-            (attr->type != QS_CHAR || lit->lit.pool_offset + lit->width <= ex->str_pool_bytes)) {
-          lower_code_compare(attr, lit, attr == l ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op)));
-          return;
-        }
-      }
-      if (l->type == QS_CHAR || r->type == QS_CHAR) {
-        // attribute vs literal only; the literal is NUL-padded to the attribute width
-        const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
-        const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
-        if (attr->kind != QS_N_ATTRIBUTE || lit->kind != QS_N_LITERAL || attr->type != QS_CHAR ||
-            lit->type != QS_CHAR || attr->b == 2) {
-          fail(QSGPU_ERR_UNSUPPORTED, "CHAR comparison other than attribute-vs-literal");
-          return;
-        }
-        const uint32_t w = attr->width;
-        if (lit->lit.pool_offset + lit->width > ex->str_pool_bytes) { fail(QSGPU_ERR_INVALID, "CHAR literal outside pool"); return; }
-        // A literal longer than the attribute (col CHAR(3) vs 'abcdef'): the reference compares the full strings, so
-        // a value equal to the literal's first w bytes is LESS than the literal; flag 4 tells the kernel
-        const bool lit_longer = lit->width > w && ex->str_pool[lit->lit.pool_offset + w] != 0;
-        if (n_str + w > static_cast<uint32_t>(kStrPool)) { fail(QSGPU_ERR_UNSUPPORTED, "string pool full"); return; }
-        const uint32_t off = n_str;
-        for (uint32_t b = 0; b < w; ++b)
-          P.L.str_pool[off + b] = b < lit->width ? ex->str_pool[lit->lit.pool_offset + b] : 0;
-        n_str += w;
-        in.op = OP_CMP_CHAR;
-        in.arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(attr->a)));
-        in.ltype = static_cast<uint8_t>(off);
-        in.aux = (attr == l) ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op));
-        in.flags = lit_longer ? 4 : 0;
-        push(in);
-        return;
-      }
-      const uint8_t T = unify(scalar_vtype(n->a), scalar_vtype(n->b));
-      in.op = OP_CMP; in.type = T; in.aux = static_cast<uint8_t>(n->op);
-      if (is_leaf(n->b)) {
-        lower_cast_acc(lower_scalar(n->a), T);
-        leaf_ref(n->b, T, &in);
-      } else if (is_leaf(n->a)) {
-        lower_cast_acc(lower_scalar(n->b), T);
-        leaf_ref(n->a, T, &in);
-        in.flags = 1;
-      } else {
-        const uint8_t t_b = lower_scalar(n->b);      // first (see lower_scalar): nested shared expressions claim theirs
-        int k = -1;
-        for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
-        if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "comparison too deep for the VM temporaries"); return; }
-        tmp_busy[k] = true;
-        Instr st{};
-        st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);
-        push(st);
-        lower_cast_acc(lower_scalar(n->a), T);
-        in.leaf = LEAF_TMP; in.ltype = t_b; in.arg = static_cast<uint16_t>(k);
-        tmp_busy[k] = false;
-      }
-      push(in);
+      // a comparison with a NULL operand is false (LiteralComparators-inl.hpp:168-223: `!(cv_nullable && value ==
+      // nullptr) && compare(...)`); NOT then complements it like NegationPredicate::getAllMatches does (no three-
+      // valued logic in the reference either).  The stored bytes of a NULL value are zero, so the comparison
+      // itself is well defined and its answer is AND-ed with "no operand is NULL".
+      lower_comparison(n, l, r);
+      if (const uint64_t nb = null_bits(n->a) | null_bits(n->b)) push_notnull(nb, true);
       return;
     }
     default:
       fail(QSGPU_ERR_INVALID, "scalar node used as predicate");
   }
+}
+
+void Lowering::lower_comparison(const qs_node *n, const qs_node *l, const qs_node *r) {
+  Instr in{};
+  {
+    // coded attribute vs literal (either order): evaluated on the codes
+    const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
+    const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
+    if (attr->kind == QS_N_ATTRIBUTE && lit->kind == QS_N_LITERAL && attr->b != 2 && rel &&
+        static_cast<uint32_t>(attr->a) < rel->attrs.size() && rel->code_width(static_cast<uint32_t>(attr->a)) != 0 &&
+        ((attr->type == QS_CHAR) == (lit->type == QS_CHAR)) &&
+        (attr->type != QS_CHAR || lit->lit.pool_offset + lit->width <= ex->str_pool_bytes)) {
+      lower_code_compare(attr, lit, attr == l ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op)));
+      return;
+    }
+  }
+  if (l->type == QS_CHAR || r->type == QS_CHAR) {
+    // attribute vs literal only; the literal is NUL-padded to the attribute width
+    const qs_node *attr = l->kind == QS_N_ATTRIBUTE ? l : r;
+    const qs_node *lit = l->kind == QS_N_ATTRIBUTE ? r : l;
+    if (attr->kind != QS_N_ATTRIBUTE || lit->kind != QS_N_LITERAL || attr->type != QS_CHAR ||
+        lit->type != QS_CHAR || attr->b == 2) {
+      fail(QSGPU_ERR_UNSUPPORTED, "CHAR comparison other than attribute-vs-literal");
+      return;
+    }
+    const uint32_t w = attr->width;
+    if (lit->lit.pool_offset + lit->width > ex->str_pool_bytes) { fail(QSGPU_ERR_INVALID, "CHAR literal outside pool"); return; }
+    // A literal longer than the attribute (col CHAR(3) vs 'abcdef'): the reference compares the full strings, so
+    // a value equal to the literal's first w bytes is LESS than the literal; flag 4 tells the kernel
+    const bool lit_longer = lit->width > w && ex->str_pool[lit->lit.pool_offset + w] != 0;
+    if (n_str + w > static_cast<uint32_t>(kStrPool)) { fail(QSGPU_ERR_UNSUPPORTED, "string pool full"); return; }
+    const uint32_t off = n_str;
+    for (uint32_t b = 0; b < w; ++b)
+      P.L.str_pool[off + b] = b < lit->width ? ex->str_pool[lit->lit.pool_offset + b] : 0;
+    n_str += w;
+    in.op = OP_CMP_CHAR;
+    in.arg = static_cast<uint16_t>(stage_attr(static_cast<uint32_t>(attr->a)));
+    in.ltype = static_cast<uint8_t>(off);
+    in.aux = (attr == l) ? static_cast<uint8_t>(n->op) : flip_cmp(static_cast<uint8_t>(n->op));
+    in.flags = lit_longer ? 4 : 0;
+    push(in);
+    return;
+  }
+  const uint8_t T = unify(scalar_vtype(n->a), scalar_vtype(n->b));
+  in.op = OP_CMP; in.type = T; in.aux = static_cast<uint8_t>(n->op);
+  if (is_leaf(n->b)) {
+    lower_cast_acc(lower_scalar(n->a), T);
+    leaf_ref(n->b, T, &in);
+  } else if (is_leaf(n->a)) {
+    lower_cast_acc(lower_scalar(n->b), T);
+    leaf_ref(n->a, T, &in);
+    in.flags = 1;
+  } else {
+    const uint8_t t_b = lower_scalar(n->b);      // first (see lower_scalar): nested shared expressions claim theirs
+    int k = -1;
+    for (int q = 0; q < kMaxTmp; ++q) if (!tmp_busy[q]) { k = q; break; }
+    if (k < 0) { fail(QSGPU_ERR_UNSUPPORTED, "comparison too deep for the VM temporaries"); return; }
+    tmp_busy[k] = true;
+    Instr st{};
+    st.op = OP_ST_TMP; st.type = t_b; st.arg = static_cast<uint16_t>(k);
+    push(st);
+    lower_cast_acc(lower_scalar(n->a), T);
+    in.leaf = LEAF_TMP; in.ltype = t_b; in.arg = static_cast<uint16_t>(k);
+    tmp_busy[k] = false;
+  }
+  push(in);
+  return;
 }
 
 // LIPFilterAdaptiveProber: probe attribute `attr` against filter `lip_index`
@@ -488,6 +562,12 @@ void Lowering::lower_lip_probe(uint32_t lip_index, uint32_t attr, bool have_pred
   if (!rel || attr >= rel->attrs.size()) { fail(QSGPU_ERR_INVALID, "LIP probe attribute out of range"); return; }
   const uint8_t lt = vtype_of(rel->attrs[attr].type);
   if (lt != V_I32 && lt != V_I64) { fail(QSGPU_ERR_UNSUPPORTED, "LIP filters take INT/LONG attributes"); return; }
+  // a NULL key joins with nothing (HashTable::getAllFromValueAccessor skips NULL keys of a nullable key attribute,
+  // storage/HashTable.hpp:1903), so the row is dropped here like a filter miss
+  if (attr < 64 && ((rel->nullable_mask >> attr) & 1ull)) {
+    push_notnull(1ull << attr, have_pred);
+    have_pred = true;
+  }
   Instr ld{};
   ld.op = OP_LOAD; ld.type = V_I64; ld.leaf = LEAF_COL; ld.ltype = lt;
   ld.arg = static_cast<uint16_t>(stage_attr(attr));

@@ -28,7 +28,7 @@ constexpr int kMaxLits = 32;
 constexpr int kStrPool = 96;
 constexpr int kMaxLip = 4;
 constexpr int kMaxTmp = 2;
-constexpr int kMaxAgg = 8;                       // value aggregates per state
+constexpr int kMaxAgg = 12;                      // state words per group besides the row count (values + non-NULL counts)
 constexpr int kMaxKeyCols = 8;
 constexpr int kMaxKeyWords = 4;                  // <= 32 byte composite keys
 constexpr int kMaxOut = 12;                      // projected columns
@@ -58,6 +58,13 @@ enum Op : uint8_t {
   OP_EMIT_RAW_BUILD, // sink.emit_raw_build(arg, build column[flags])
   OP_CMP_CODE,    // push((code(col[arg]) - lits[aux]) < lits[aux+1], unsigned) ^ (flags&1): a comparison of a
                   // dictionary-coded attribute with a literal, translated by the host into a code range
+  // NULL-able inputs.  col[arg] is the relation's per-row NULL mask (bit a = attribute a is NULL), staged like a
+  // LONG column; lits[aux] is the set of attributes the expression at hand reads.
+  OP_NOTNULL,     // push((col[arg] & lits[aux]) == 0): a comparison with a NULL operand is false
+                  // (LiteralComparators-inl.hpp:168-223)
+  OP_NULLSEL,     // acc = (col[arg] & lits[aux]) == 0 ? acc : lits[aux+1]: an aggregate skips NULL arguments
+                  // (AggregationHandleSum.hpp:117-127); lits[aux+1] is the identity of the aggregate's combine
+  OP_EMIT_NULL,   // sink.emit_null(arg, (col[flags] & lits[aux]) != 0): NULL-ness of projected column `arg`
 };
 
 enum Leaf : uint8_t { LEAF_COL = 0, LEAF_LIT = 1, LEAF_TMP = 2, LEAF_BUILD = 3 /*join build side*/ };

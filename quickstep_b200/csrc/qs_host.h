@@ -36,6 +36,9 @@ struct qsgpu_relation {
   // Per-row NULL mask (bit j = attribute j is NULL), allocated only for relations that can hold NULLs
   // (the output of a LEFT OUTER join); absent = no NULLs.
   unsigned long long *d_nulls = nullptr;
+  // attributes that may be NULL (bit j = attribute j; qsgpu_relation_set_nullable, or the columns a LEFT OUTER join /
+  // an aggregate finalization can leave NULL).  Scans read the mask only for attributes in this set.
+  uint64_t nullable_mask = 0;
   uint64_t host_rows = 0;
   bool dirty = false;
 };
@@ -63,6 +66,7 @@ struct qsgpu_agg_state {
   std::vector<qs_aggregate> aggregates;
   std::vector<int32_t> group_by_roots;
   std::vector<int> value_word;        // per aggregate: state word (0 = row count only)
+  std::vector<int> nn_word;           // per aggregate: state word counting its non-NULL arguments (0 = the row count)
   std::vector<uint8_t> arg_vtype;     // per aggregate: VType of the argument (V_I32.. ; 0 for COUNT(*))
   std::vector<qs_attr> key_attrs;     // group-by attribute types
   std::vector<uint32_t> key_attr_ids;
@@ -138,6 +142,8 @@ Device *device(int dev);               // nullptr (+ last error) when unavailabl
 // Stream-ordered allocation on the device the calling thread last resolved with device():
 // ordered on that device's library stream, served from its retained pool (no device sync).
 cudaError_t dev_malloc_bytes(void **p, size_t bytes);
+// The relation's per-row NULL mask, allocated (all zeros, padded like a LONG column) on first need.
+int ensure_null_mask(qsgpu_relation *rel, Device *d);
 template <class T> inline cudaError_t dev_malloc(T **p, size_t bytes) {
   return dev_malloc_bytes(reinterpret_cast<void **>(p), bytes);
 }

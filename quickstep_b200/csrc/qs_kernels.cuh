@@ -719,7 +719,13 @@ template <class Q>
 struct SelectSink : SinkBase {
   const SinkDesc *K;
   uint64_t idx[kRows];     // output row, ~0 when the row does not survive
+  uint64_t nm[kRows];      // NULL mask of the output row (bit = projected column), scans of NULL-able relations only
   int tid;
+  template <int J>
+  __device__ __forceinline__ void emit_null(const bool (&isnull)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) nm[r] |= isnull[r] ? (1ull << J) : 0ull;
+  }
   template <int J, int TYPE>
   __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
     constexpr uint32_t w = Q::out_w(J);
@@ -779,7 +785,16 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
     lip_build_rows<Q, SelectSink<Q>>(K, stage, tid, pass);
     if constexpr (Q::n_out > 0) {   // BuildLIPFilter has nothing to materialise
       cta_compact(pass, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+      if constexpr (emits_null<Q>()) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
+      }
       vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
+      if constexpr (emits_null<Q>()) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = sink.nm[r];
+      }
     }
   });
   flush_lip_stats<Q>(S, regs);
@@ -905,7 +920,13 @@ struct JoinSink : SinkBase {
   const JoinDesc *J;
   uint64_t idx[kRows];
   unsigned long long brow[kRows];
+  uint64_t nm[kRows];      // NULL-ness the probe side brings (probe relations with NULL-able attributes only)
   int tid;
+  template <int JJ>
+  __device__ __forceinline__ void emit_null(const bool (&isnull)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) nm[r] |= isnull[r] ? (1ull << JJ) : 0ull;
+  }
   template <int JJ, int TYPE>
   __device__ __forceinline__ void emit(const uint64_t (&acc)[kRows]) {
     constexpr uint32_t w = Q::out_w(JJ);
@@ -1073,12 +1094,14 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
       }
       if constexpr (inner) {
         cta_compact(ok, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
         vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
-        if constexpr (outer) {
+        if constexpr (outer || emits_null<Q>()) {
 #pragma unroll
           for (int r = 0; r < kRows; ++r) {
-            matched[r] |= ok[r];
-            if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = 0ull;
+            if constexpr (outer) matched[r] |= ok[r];
+            if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = sink.nm[r];
           }
         }
       } else {
@@ -1096,11 +1119,13 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         sink.brow[r] = kEmptyRow;
       }
       cta_compact(flag, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
       vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
-      if constexpr (outer) {
+      if constexpr (outer || emits_null<Q>()) {
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
-          if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = K.null_bits;
+          if (sink.idx[r] != ~0ull) K.null_out[sink.idx[r]] = sink.nm[r] | (outer ? K.null_bits : 0ull);
       }
     }
   });

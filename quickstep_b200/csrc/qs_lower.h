@@ -47,6 +47,16 @@ struct Lowering {
   bool fail(int st, const std::string &m) { if (status == QSGPU_OK) { status = st; err = m; } return false; }
   bool ok() const { return status == QSGPU_OK; }
 
+  // NULL-able inputs: the scanned relation's per-row NULL mask travels as one more staged column (pseudo attribute
+  // kNullMaskAttr, 8 bytes per row), staged only by programs that read a NULL-able attribute.
+  static constexpr uint32_t kNullMaskAttr = 0xffffffffu;
+  int null_slot = -1;
+  int stage_null_mask();
+  uint64_t null_bits(int i);                  // NULL-mask bits of the NULL-able scanned attributes scalar i reads
+  void push_notnull(uint64_t bits, bool and_it);          // push(no attribute of `bits` is NULL) [and AND it in]
+  void lower_null_select(uint64_t bits, uint64_t identity);   // acc = NULL ? identity : acc
+  void lower_emit_null(uint32_t out_col, uint64_t bits);
+
   int stage_attr(uint32_t attr, uint8_t use = USE_RAW);   // staged slot of a scanned attribute
   bool lower_code_compare(const qs_node *attr, const qs_node *lit, uint8_t cmp);   // coded attribute <cmp> literal
   int build_attr(uint32_t attr);
@@ -60,6 +70,7 @@ struct Lowering {
   uint8_t lower_scalar(int i);                // value left in acc; returns its VType
   void lower_cast_acc(uint8_t from, uint8_t to);
   void lower_pred(int i);
+  void lower_comparison(const qs_node *n, const qs_node *l, const qs_node *r);   // one comparison, operands not NULL
   void lower_lip_probe(uint32_t lip_index, uint32_t attr, bool have_pred);
   void mark_pred_end() { P.n_pred = n_code; P.n_mid = n_code; }
   void mark_mid_end() { P.n_mid = n_code; }

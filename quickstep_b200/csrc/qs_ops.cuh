@@ -63,6 +63,7 @@ struct FinalizeDesc {
   uint32_t n_out;
   uint8_t function[kMaxOut];   // QS_AGG_*
   uint8_t word[kMaxOut];       // state word holding the value (0 = row count)
+  uint8_t nn_word[kMaxOut];    // state word counting the aggregate's non-NULL arguments (0 = the row count)
   uint8_t out_vtype[kMaxOut];  // VType of the output column
   uint8_t word_is_f64[kMaxOut];
   char *out[kMaxOut];
@@ -94,6 +95,12 @@ struct __align__(16) StageSeg {
   const char *bdict;
   const char *gdict;
   uint32_t g_entries, qtype, bw, pad;
+  // NULL values of the stripe (QS_NULL_*): a NULL row's value is stored as zero bytes and `null_bit` is set in
+  // null_dst[row], the relation's per-row NULL mask
+  const unsigned char *null_src;
+  unsigned long long *null_dst;
+  uint64_t null_bit;
+  uint32_t null_kind, null_arg, null_stride, null_width;
 };
 constexpr uint32_t kStageTileRows = 4096;
 

@@ -196,6 +196,7 @@ struct SinkBase {
   template <int J, int COL, int W> __device__ __forceinline__ void emit_raw(const char *) {}
   template <int J, int COL, int W> __device__ __forceinline__ void emit_raw_build() {}
   template <int COL, int LTYPE, int W> __device__ __forceinline__ uint64_t build_leaf(int) { return 0; }
+  template <int J> __device__ __forceinline__ void emit_null(const bool (&)[kRows]) {}
 };
 
 // Per-thread VM state that survives between the predicate and emit sections.
@@ -222,7 +223,8 @@ __device__ __forceinline__ uint32_t tile_row(int r, int tid) { return r * kBlock
  * per row once the scan on dictionary codes had made that kernel issue-bound.)
  */
 __host__ __device__ constexpr bool op_pushes(uint8_t op) {
-  return op == OP_CMP || op == OP_CMP_CHAR || op == OP_CMP_CODE || op == OP_PUSH_TRUE || op == OP_PUSH_FALSE || op == OP_LIP;
+  return op == OP_CMP || op == OP_CMP_CHAR || op == OP_CMP_CODE || op == OP_PUSH_TRUE || op == OP_PUSH_FALSE || op == OP_LIP ||
+         op == OP_NOTNULL;
 }
 template <class Q>
 __host__ __device__ constexpr int pred_depth(int pc, int end) {
@@ -244,6 +246,13 @@ __host__ __device__ constexpr int lip_ops() {
   int n = 0;
   for (int i = 0; i < Q::n_total; ++i) n += Q::code(i).op == OP_LIP ? 1 : 0;
   return n;
+}
+
+// Does the program record NULL-ness of projected columns (a scan of a relation with NULL-able attributes)?
+template <class Q>
+__host__ __device__ constexpr bool emits_null() {
+  for (int i = 0; i < Q::n_total; ++i) if (Q::code(i).op == OP_EMIT_NULL) return true;
+  return false;
 }
 
 template <class Q, int PC, int END, int SP, int D, class Sink>
@@ -366,6 +375,26 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
         }
         pst[SP][r] = b;
       }
+    } else if constexpr (in.op == OP_NOTNULL) {
+      const char *base = stage + Q::col_off(in.arg);
+      const uint64_t m = L.lits[in.aux];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        pst[SP][r] = (*reinterpret_cast<const uint64_t *>(base + tile_row(r, tid) * 8u) & m) == 0ull;
+    } else if constexpr (in.op == OP_NULLSEL) {
+      const char *base = stage + Q::col_off(in.arg);
+      const uint64_t m = L.lits[in.aux], ident = L.lits[in.aux + 1];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        acc[r] = (*reinterpret_cast<const uint64_t *>(base + tile_row(r, tid) * 8u) & m) == 0ull ? acc[r] : ident;
+    } else if constexpr (in.op == OP_EMIT_NULL) {
+      const char *base = stage + Q::col_off(in.flags);
+      const uint64_t m = L.lits[in.aux];
+      bool isnull[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        isnull[r] = (*reinterpret_cast<const uint64_t *>(base + tile_row(r, tid) * 8u) & m) != 0ull;
+      sink.template emit_null<in.arg>(isnull);
     } else if constexpr (in.op == OP_EMIT) {
       sink.template emit<in.arg, in.type>(acc);
     } else if constexpr (in.op == OP_EMIT_RAW) {

@@ -132,6 +132,18 @@ class Relation:
         A.check(L.qsgpu_relation_wrap(dev, len(schema), _attrs(schema), ptrs, n_rows, C.byref(out)))
         return cls(out, schema, names, dev, keep=keep)
 
+    def set_nullable(self, attrs):
+        """qsgpu_relation_set_nullable: `attrs` (indices) may hold NULLs."""
+        mask = 0
+        for a in attrs:
+            mask |= 1 << a
+        A.check(A.load().qsgpu_relation_set_nullable(self.h, mask))
+
+    def write_nulls(self, masks: np.ndarray, lo=0):
+        """qsgpu_relation_write_nulls: per-row NULL masks (bit a = attribute a is NULL) of rows [lo, lo+len)."""
+        m = np.ascontiguousarray(masks, dtype=np.uint64)
+        A.check(A.load().qsgpu_relation_write_nulls(self.h, lo, len(m), m.ctypes.data_as(C.POINTER(C.c_uint64))))
+
     def set_dictionary(self, attr: int, code_width: int, dict_values: np.ndarray):
         """qsgpu_relation_set_dictionary: attribute `attr` is resident as `code_width`-byte codes into the sorted
         relation-wide dictionary `dict_values` (native values)."""
@@ -236,6 +248,13 @@ class Relation:
                 if d.get("dict_offset") is not None:
                     descs[i].dict = base + d["dict_offset"]
                     descs[i].dict_entries = d["dict_entries"]
+                if d.get("null_kind"):
+                    descs[i].null_kind = d["null_kind"]
+                    descs[i].null_arg = d.get("null_arg", 0)
+                    descs[i].null_stride = d.get("null_stride", 0)
+                    descs[i].null_width = d.get("null_width", 0)
+                    if d.get("null_offset") is not None:
+                        descs[i].null_bitmap = base + d["null_offset"]
             keep.append(descs)
             imgs[b].host, imgs[b].bytes, imgs[b].n_rows, imgs[b].descs = base, mem.nbytes, n_rows, descs
         A.check(A.load().qsgpu_stage_blocks(self.h, len(images), imgs, n_desc))
@@ -371,7 +390,8 @@ def select(rel, es, pred_root, lip_probe, project_roots, output: Relation, row_b
 class AggState:
     """qsgpu_agg_state_t (AggregationOperationState)."""
 
-    def __init__(self, strategy, es, pred_root, aggregates, group_by_roots, estimated=1024, max_key=-1, dev=0):
+    def __init__(self, strategy, es, pred_root, aggregates, group_by_roots, estimated=1024, max_key=-1, dev=0,
+                 nullable_args=()):
         L = init()
         self.es = es
         self.aggs = (A.qs_aggregate * max(1, len(aggregates)))()
@@ -386,6 +406,8 @@ class AggState:
         spec.n_group_by, spec.group_by_roots = len(group_by_roots), self.groups
         spec.estimated_num_entries = estimated
         spec.collision_free_max_key = max_key
+        for j in nullable_args:            # aggregates whose argument has a NULL-able type
+            spec.nullable_arguments |= 1 << j
         self.h = C.c_void_p()
         self.n_aggregates = len(aggregates)
         self.n_group_by = len(group_by_roots)

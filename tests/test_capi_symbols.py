@@ -27,7 +27,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(A.qs_node) == 24
     assert A.qs_node.lit.offset == 16
     assert ctypes.sizeof(A.qs_attr) == 4
-    assert ctypes.sizeof(A.qs_stage_desc) == 40
+    assert ctypes.sizeof(A.qs_stage_desc) == 64
     assert ctypes.sizeof(A.qs_lip_ref) == 16
     assert ctypes.sizeof(A.qs_aggregate) == 8
 

@@ -862,6 +862,11 @@ def test_stage_block_decoders(engine, oracle):
         exp = [oracle.decode_dict(codes16, dict_vals), oracle.decode_truncated(trunc8, np.int32),
                oracle.decode_dict(codes8, date_dict), plain,
                oracle.decode_strided(slots[3:], n, stride, np.dtype("S5"))]
+        # staging canonicalises CHAR values: bytes after the first NUL are zeroed (the engine leaves whatever the
+        # slot held before; strncmp never looks at them)
+        raw = np.ascontiguousarray(exp[4]).view(np.uint8).reshape(n, 5).copy()
+        raw[np.cumsum(raw == 0, axis=1) > 0] = 0
+        exp[4] = raw.reshape(-1).view("S5")
         for a in range(5):
             for blk in range(2):
                 got = rel.read(a, blk * n, n)

@@ -9,7 +9,8 @@ from quickstep_b200 import capi as A
 
 CASES = ["q6_single_state", "q1_compact_key", "select_lip_probe", "build_lip_filter", "join_build",
          "join_probe_inner_residual", "join_probe_anti", "groupby_hash", "groupby_dense", "join_build_dense", "join_probe_dense", "join_probe_left_outer",
-         "q6_on_dictionary_codes", "q1_on_dictionary_codes", "join_probe_coded_build_and_probe"]
+         "q6_on_dictionary_codes", "q1_on_dictionary_codes", "join_probe_coded_build_and_probe",
+         "nullable_single_state", "nullable_compact_key", "nullable_select", "nullable_join_probe"]
 
 
 @pytest.mark.parametrize("which", range(A.JIT_SELFCHECK_CASES), ids=CASES)
