@@ -148,9 +148,10 @@ static void testPartitionAwareInsertDestination(StorageManager *sm, WorkerPool *
   std::vector<std::int32_t> k(n);
   std::vector<std::int64_t> v(n);
   for (std::uint64_t i = 0; i < n; ++i) { k[i] = static_cast<std::int32_t>(rnd() % 5000) - 100; v[i] = static_cast<std::int64_t>(rnd() % 1000); }
-  CatalogRelation in(21, "in", {{"k", kInt}, {"v", kLong}});
-  CatalogRelation mid(22, "mid", {{"k", kInt}, {"v", kLong}}, true);
-  CatalogRelation out(23, "out", {{"c", kLong}, {"s", kLong}}, true);
+  const relation_id base_id = 20 + 10 * static_cast<relation_id>(num_partitions);    // every call loads its own relation
+  CatalogRelation in(base_id + 1, "in", {{"k", kInt}, {"v", kLong}});
+  CatalogRelation mid(base_id + 2, "mid", {{"k", kInt}, {"v", kLong}}, true);
+  CatalogRelation out(base_id + 3, "out", {{"c", kLong}, {"s", kLong}}, true);
   sm->loadRelation(&in, {k.data(), v.data()}, n, 9000, TupleStoreLayout::kCompressedColumnStore);
   QueryContext ctx(sm, sm->device());
   QueryContext::Predicate pred;

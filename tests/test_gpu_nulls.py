@@ -247,8 +247,8 @@ def test_join_null_keys(engine, table, join_type):
     pairs = NO.join_pairs(bk, bnull.astype(bool), pk, (pnull & np.uint64(1)).astype(bool))
     vnull = ((pnull >> np.uint64(1)) & np.uint64(1)).astype(bool)
     if inner:
-        exp = sorted((int(pk[p]), None if vnull[p] else float(pv[p]), int(b)) for p, b in pairs)
-        gotr = sorted((int(got[0][i]), None if (int(got_nulls[i]) >> 1) & 1 else float(got[1][i]), int(got[2][i])) for i in range(len(got_nulls)))
+        exp = sorted(((int(pk[p]), None if vnull[p] else float(pv[p]), int(b)) for p, b in pairs), key=repr)
+        gotr = sorted(((int(got[0][i]), None if (int(got_nulls[i]) >> 1) & 1 else float(got[1][i]), int(got[2][i])) for i in range(len(got_nulls))), key=repr)
     else:
         exp = sorted({p: (int(pk[p]), None if vnull[p] else float(pv[p])) for p, _b in pairs}.values(), key=repr)
         gotr = sorted(((int(got[0][i]), None if (int(got_nulls[i]) >> 1) & 1 else float(got[1][i])) for i in range(len(got_nulls))), key=repr)

@@ -97,8 +97,14 @@ def test_live_engine_blocks_sf001_queries_match_engine(engine):
         stats = dict(c_custkey_min=1, c_custkey_max=1500, o_orderkey_min=int(okeys.min()), o_orderkey_max=int(okeys.max()),
                      orders_rows=15000, lineitem_rows=60175, customer_rows=1500, t2_estimate=7500, groups_estimate=4096)
         RG.check_q3(T.run_q3(rels["customer"], rels["orders"], rels["lineitem"], stats), "live")
-        # and the committed golden tables are what this engine prints today
-        assert want["03"] == RG.ENGINE["sf0.01"]["q3"]["rows"]
+        # and the committed golden tables are what this engine prints today -- up to the last digits of its double sums,
+        # which depend on the order its worker threads finish their blocks in (243512.79810000001 in one run,
+        # 243512.79809999999 in the next)
+        gold = RG.ENGINE["sf0.01"]["q3"]["rows"]
+        assert len(want["03"]) == len(gold)
+        for wrow, grow in zip(want["03"], gold):
+            assert [wrow[0], wrow[2], wrow[3]] == [grow[0], grow[2], grow[3]]
+            assert abs(float(wrow[1]) - float(grow[1])) <= 1e-9 * abs(float(grow[1]))
     finally:
         for r in rels.values():
             r.destroy()
