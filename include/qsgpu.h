@@ -458,6 +458,10 @@ int qsgpu_agg_existence_map(qsgpu_agg_state_t state, qsgpu_lip_t *out);
  * (SQL NULL, AggregationHandleSum.cpp:134-143) the value is 0 and the
  * matching bit of *null_mask (bit j = aggregate j, SINGLE_STATE only) is set; the same information is in the
  * output relation's per-row NULL mask (qsgpu_relation_read_nulls / read_rows: bit = output column).
+ * NULL-able arguments (qs_agg_spec.nullable_arguments) follow what the reference engine prints: without GROUP BY an
+ * aggregate that saw no non-NULL value is NULL (COUNT(x): 0); with GROUP BY only MIN / MAX are, while SUM is 0 and
+ * AVG is 0 / 0.0 = NaN for such a group (the hash-table payload of SUM / AVG is the bare running sum,
+ * AggregationHandleSum.hpp:176-178, AggregationHandleAvg.hpp:180-189).
  * With null_mask == NULL the call only enqueues for SINGLE_STATE / COMPACT_KEY states (the live group count is
  * read on the device; the output's row count stays device-side until somebody asks), so a query's tail --
  * finalize, the wrapping Select, the sort -- is queued while the scan kernel is still running.

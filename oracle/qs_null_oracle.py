@@ -12,7 +12,9 @@ here is numpy on top of qs_oracle.predicate / qs_oracle.scalar (which see only t
     (`!(cv_nullable && cv_value == nullptr) && compare(...)`), :264-290 for two attributes;
   * NOT complements the operand's matches, AND / OR intersect / unite them -- no third truth value:
     NegationPredicate.cpp:75-94, ConjunctionPredicate.cpp:138, DisjunctionPredicate.cpp:145;
-  * SUM / AVG / MIN / MAX skip NULL arguments and are NULL when they saw no value:
+  * SUM / AVG / MIN / MAX skip NULL arguments and are NULL when they saw no value (under GROUP BY only MIN / MAX
+    are: the unmodified engine prints SUM = 0 and AVG = -nan for a group whose arguments are all NULL,
+    tests/golden/ref_null_results.json):
     AggregationHandleSum.hpp:117-127 (`if (value.isNull()) return;`), AggregationHandleSum.cpp:134-143,
     AggregationHandleAvg.hpp:121-131 (count of non-NULL values), AggregationHandleMin.hpp:188-200,
     AggregationHandleMax.hpp:188-200;
@@ -70,6 +72,8 @@ def aggregate(es, pred_root, aggregates, group_attr, table, nulls: np.ndarray):
     for f, r in aggregates:
         if r < 0:
             args.append((None, np.zeros(rows, dtype=bool)))
+        elif f == A.QS_AGG_COUNT:            # COUNT(x) needs only the argument's NULL-ness (x may be a CHAR attribute)
+            args.append((None, null_of(es, r, nulls)))
         else:
             args.append((O.scalar(es, r, table), null_of(es, r, nulls)))
     if group_attr is None:
@@ -94,7 +98,14 @@ def aggregate(es, pred_root, aggregates, group_attr, table, nulls: np.ndarray):
                 continue
             v = vals[idx][~isnull[idx]]
             if len(v) == 0:
-                res.append((0, True))
+                # no value: NULL -- except SUM / AVG under GROUP BY, whose hash-table payload is the bare running sum
+                # (AggregationHandleSum.hpp:176-178, AggregationHandleAvg.hpp:180-189): 0 and 0 / 0.0 = NaN
+                if group_attr is not None and f == A.QS_AGG_SUM:
+                    res.append((0.0 if vals.dtype.kind == "f" else 0, False))
+                elif group_attr is not None and f == A.QS_AGG_AVG:
+                    res.append((float("nan"), False))
+                else:
+                    res.append((0, True))
                 continue
             fp = v.dtype.kind == "f"
             if f == A.QS_AGG_SUM:

@@ -22,7 +22,7 @@ import struct
 
 import numpy as np
 
-COMPRESSED_COLUMN_STORE, SPLIT_ROW_STORE = 2, 3
+BASIC_COLUMN_STORE, COMPRESSED_COLUMN_STORE, SPLIT_ROW_STORE = 0, 2, 3
 
 
 def _varint(b, i):
@@ -105,16 +105,21 @@ def read_compressed_column_store(mem, attr_widths):
     for a in range(len(attr_size)):
         dict_at.append(pos if dict_size[a] else None)
         pos += dict_size[a]
+    # one BitVector<false> of null_bitmap_bits bits per uncompressed attribute that holds NULLs
+    # (CompressedColumnStoreTupleStorageSubBlock.cpp:755-775)
+    null_at = [None] * len(attr_size)
     if null_bits:
         for a in range(len(has_nulls)):
             if has_nulls[a]:
+                null_at[a] = pos
                 pos += ((null_bits + 63) // 64) * 8
     tuple_len = sum(attr_size)
     max_tuples = (sb + h.tuple_store_size - pos) // tuple_len
     stripes = []
     for a in range(len(attr_size)):
         w = attr_widths[a]
-        s = dict(offset=pos, code_width=int(attr_size[a]), dict_offset=None, dict_entries=0, encoding="skip")
+        s = dict(offset=pos, code_width=int(attr_size[a]), dict_offset=None, dict_entries=0, encoding="skip",
+                 null_offset=null_at[a])
         if w is not None:
             if dict_size[a]:
                 num_codes, null_code = struct.unpack_from("<II", mem, dict_at[a])
@@ -126,6 +131,32 @@ def read_compressed_column_store(mem, attr_widths):
         stripes.append(s)
         pos += max_tuples * attr_size[a]
     return dict(n_rows=n_rows, max_tuples=max_tuples, stripes=stripes, n_attrs=len(attr_size))
+
+
+def read_basic_column_store(mem, attr_widths, nullable):
+    """Uncompressed column store (storage/BasicColumnStoreTupleStorageSubBlock.cpp:100-183):
+    [Header{int num_tuples, int nulls_in_sort_column}][one BitVector<false>(max_tuples) per NULL-able attribute]
+    [stripe a: max_tuples x width(a)]...   -> dict(n_rows, stripes=[dict(offset, null_offset or None)])."""
+    h = BlockHeader(mem)
+    assert h.sub_block_type == BASIC_COLUMN_STORE
+    sb = h.header_bytes
+    n_rows, _nulls_in_sort = struct.unpack_from("<ii", mem, sb)
+    size, fixed, n_null = h.tuple_store_size, sum(attr_widths), sum(1 for x in nullable if x)
+    max_tuples = ((size - 8) << 3) // ((fixed << 3) + n_null)
+    bitmap_bytes = ((max_tuples + 63) // 64) * 8
+    max_tuples = (size - 8 - n_null * bitmap_bytes) // fixed
+    bitmap_bytes = ((max_tuples + 63) // 64) * 8
+    pos = sb + 8
+    null_at = []
+    for a in range(len(attr_widths)):
+        null_at.append(pos if nullable[a] else None)
+        if nullable[a]:
+            pos += bitmap_bytes
+    stripes = []
+    for a, w in enumerate(attr_widths):
+        stripes.append(dict(offset=pos, null_offset=null_at[a], encoding="plain"))
+        pos += max_tuples * w
+    return dict(n_rows=n_rows, max_tuples=max_tuples, stripes=stripes)
 
 
 def read_split_row_store(mem, fixed_widths, n_varlen, min_varlen_bytes, n_nullable=0):
@@ -148,7 +179,7 @@ def read_split_row_store(mem, fixed_widths, n_varlen, min_varlen_bytes, n_nullab
         offs.append(o)
         o += w
     return dict(n_rows=n_rows, first_slot=sb + header_bytes + occ_bytes, slot_bytes=slot, attr_offsets=offs, rows=rows,
-                contiguous=rows == list(range(n_rows)))
+                contiguous=rows == list(range(n_rows)), null_bytes=null_bytes)
 
 
 def load_blocks(storage_dir):

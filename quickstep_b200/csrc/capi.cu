@@ -1887,9 +1887,17 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
     // recorded in the output relation's per-row NULL mask
     if (const int ns = ensure_null_mask(rel, d)) { qsgpu_relation_destroy(rel); return ns; }
     F.null_out = rel->d_nulls;
-    for (size_t j = 0; j < state->aggregates.size(); ++j)
-      if (state->aggregates[j].function != QS_AGG_COUNT && (state->strategy == QS_AGG_SINGLE_STATE || state->nn_word[j]))
-        F.null_bits |= 1ull << (A.n_key_cols + j);
+    // Which aggregates can be NULL is the reference's rule, odd as it is: without GROUP BY every one except COUNT
+    // (AggregationHandleSum.cpp:134-143 and friends).  With GROUP BY the hash-table payload of SUM / AVG is the bare
+    // running sum (AggregationHandleSum.hpp:176-178, AggregationHandleAvg.hpp:180-189), so a group whose arguments
+    // were all NULL finalizes to SUM = 0 and AVG = NaN; only MIN / MAX, whose payload is a NULL-able TypedValue
+    // (AggregationHandleMin.hpp:152-155), come out NULL.
+    for (size_t j = 0; j < state->aggregates.size(); ++j) {
+      const uint32_t fn = state->aggregates[j].function;
+      const bool can_be_null = state->strategy == QS_AGG_SINGLE_STATE ? fn != QS_AGG_COUNT
+                                                                     : (state->nn_word[j] && (fn == QS_AGG_MIN || fn == QS_AGG_MAX));
+      if (can_be_null) F.null_bits |= 1ull << (A.n_key_cols + j);
+    }
     rel->nullable_mask = F.null_bits;
   }
   KernelTimer timer(d, QS_K_GROUPBY);

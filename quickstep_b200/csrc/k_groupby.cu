@@ -161,7 +161,10 @@ __global__ void k_finalize(const uint64_t *states, const uint64_t *keys, uint32_
       else if (F.function[j] == QS_AGG_AVG) {
         // sum / static_cast<double>(count)   (AggregationHandleAvg.cpp:144-155)
         const double sum = F.word_is_f64[j] ? u2d(v) : static_cast<double>(static_cast<int64_t>(v));
-        o = d2u(count ? sum / static_cast<double>(static_cast<int64_t>(count)) : 0.0);
+        // Without GROUP BY an AVG over no values is NULL (stored as 0).  With GROUP BY the reference divides whatever the
+        // entry holds, AggregationHandleAvg.hpp:180-189: a group whose arguments were all NULL prints 0 / 0.0 = NaN
+        // (verified on the unmodified engine, tests/golden/ref_null_results.json).
+        o = d2u((count || F.n_key_cols) ? sum / static_cast<double>(static_cast<int64_t>(count)) : 0.0);
         from = V_F64;
       } else {
         o = count ? v : 0;
