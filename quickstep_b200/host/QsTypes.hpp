@@ -53,6 +53,7 @@ namespace tmb = tmb_standin;
 struct CatalogAttribute {
   std::string name;
   qs_attr type;          // {QS_INT.., byte width}
+  bool nullable = false; // Type::isNullable() (types/Type.hpp:129)
 };
 
 typedef std::vector<block_id> BlocksInPartition;
@@ -72,6 +73,12 @@ class CatalogRelation {
     std::vector<qs_attr> s;
     for (const auto &a : attrs_) s.push_back(a.type);
     return s;
+  }
+  // bit a = attribute a has a NULL-able type (CatalogRelationSchema::hasNullableAttributes / numNullableAttributes)
+  std::uint64_t nullableMask() const {
+    std::uint64_t m = 0;
+    for (std::size_t a = 0; a < attrs_.size() && a < 64; ++a) if (attrs_[a].nullable) m |= 1ull << a;
+    return m;
   }
   std::size_t getNumPartitions() const { return 1u; }
   bool hasPartitionScheme() const { return false; }

@@ -124,6 +124,9 @@ class QueryContext {
     std::uint32_t strategy = QS_AGG_SINGLE_STATE;
     std::uint64_t estimated_num_entries = 1024;
     std::int64_t collision_free_max_key = -1;
+    // bit j: aggregate j's argument has a NULL-able type (the reference creates the handle from the argument types,
+    // AggregateFunctionSum::createHandle; NULL arguments are skipped, AggregationHandleSum.hpp:117-127)
+    std::uint64_t nullable_arguments = 0;
     // Several devices: the input is partitioned on (a prefix of) the group-by attributes, so no group spans two
     // devices and every device finalizes its own groups -- what the reference does per partition when
     // `is_partitioned_on_group_by` holds (query_optimizer/ExecutionGenerator.cpp, aggregation state per partition).
@@ -171,6 +174,7 @@ class QueryContext {
     c.n_aggregates = static_cast<std::uint32_t>(s.aggregates.size()); c.aggregates = s.aggregates.data();
     c.n_group_by = static_cast<std::uint32_t>(s.group_by_roots.size()); c.group_by_roots = s.group_by_roots.data();
     c.estimated_num_entries = s.estimated_num_entries; c.collision_free_max_key = s.collision_free_max_key;
+    c.nullable_arguments = s.nullable_arguments;
     QS_CHECK_GPU(qsgpu_agg_create(&c, &agg_states_.back()));
     return static_cast<aggregation_state_id>(agg_states_.size()) - 1;
   }

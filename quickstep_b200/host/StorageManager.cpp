@@ -18,6 +18,7 @@ struct StripePlan {
   std::uint32_t code_width = 0;
   std::vector<char> dict;            // sorted distinct values, native width
   std::size_t stripe_bytes = 0;
+  bool has_nulls = false;            // some value of the block is NULL: null code (dictionary) or a bitmap (native stripe)
 };
 
 // CompressedBlockBuilder's rule (storage/CompressedBlockBuilder.cpp:470-498): keep the
@@ -32,12 +33,22 @@ bool valueLess(const T &a, const T &b) {
 }
 
 template <class T>
-StripePlan planCompressed(const T *v, std::uint64_t n, bool is_integer) {
+StripePlan planCompressed(const T *v_all, std::uint64_t n_all, bool is_integer, const std::uint8_t *nulls) {
   StripePlan p;
   const std::size_t w = sizeof(T);
   std::size_t truncated = w;
+  // NULL rows take no part in the dictionary (their code is the number of codes) and rule truncation out
+  // (storage/CompressedBlockBuilder.cpp:357-381: "if the new value is null or less than zero, we can't truncate it")
+  std::vector<T> non_null;
+  bool any_null = false;
+  if (nulls) {
+    for (std::uint64_t i = 0; i < n_all; ++i) { if (nulls[i]) any_null = true; else non_null.push_back(v_all[i]); }
+  }
+  const T *v = any_null ? non_null.data() : v_all;
+  const std::uint64_t n = any_null ? non_null.size() : n_all;
+  p.has_nulls = any_null;
   if constexpr (std::is_integral<T>::value) {
-    if (is_integer && n > 0) {
+    if (is_integer && n > 0 && !any_null) {
       bool nonneg = true;
       std::uint64_t mx = 0;
       for (std::uint64_t i = 0; i < n; ++i) {
@@ -56,14 +67,14 @@ StripePlan planCompressed(const T *v, std::uint64_t n, bool is_integer) {
   d.erase(std::unique(d.begin(), d.end(), [](const T &a, const T &b) { return std::memcmp(&a, &b, sizeof(T)) == 0; }), d.end());
   const std::size_t codes = d.size() + 1;                    // one code is reserved for NULL
   const std::size_t cw = codes <= (1u << 8) ? 1 : codes <= (1u << 16) ? 2 : 4;
-  const std::size_t dict_bytes = 8 + d.size() * w + n * cw;   // [u32 num_codes][u32 null_code][values] + codes
-  if (truncated * n < dict_bytes) {
-    if (truncated < w) { p.encoding = QS_ENC_TRUNCATED; p.code_width = static_cast<std::uint32_t>(truncated); p.stripe_bytes = n * truncated; }
-    else { p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * w; }
+  const std::size_t dict_bytes = 8 + d.size() * w + n_all * cw;   // [u32 num_codes][u32 null_code][values] + codes
+  if (truncated * n_all < dict_bytes) {
+    if (truncated < w) { p.encoding = QS_ENC_TRUNCATED; p.code_width = static_cast<std::uint32_t>(truncated); p.stripe_bytes = n_all * truncated; }
+    else { p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n_all * w; }
   } else {
     p.encoding = QS_ENC_DICT;
     p.code_width = static_cast<std::uint32_t>(cw);
-    p.stripe_bytes = n * cw;
+    p.stripe_bytes = n_all * cw;
     p.dict.resize(d.size() * w);
     std::memcpy(p.dict.data(), d.data(), d.size() * w);
   }
@@ -71,7 +82,7 @@ StripePlan planCompressed(const T *v, std::uint64_t n, bool is_integer) {
 }
 
 template <class T>
-void writeCodes(char *dst, const T *v, std::uint64_t n, const StripePlan &p) {
+void writeCodes(char *dst, const T *v, std::uint64_t n, const StripePlan &p, const std::uint8_t *nulls) {
   if (p.encoding == QS_ENC_TRUNCATED) {
     if constexpr (std::is_integral<T>::value) {
       for (std::uint64_t i = 0; i < n; ++i) {
@@ -85,7 +96,9 @@ void writeCodes(char *dst, const T *v, std::uint64_t n, const StripePlan &p) {
   const std::size_t nd = p.dict.size() / sizeof(T);
   for (std::uint64_t i = 0; i < n; ++i) {
     // ordered dictionary: code = rank of the value (CompressionDictionaryLite: code order = value order)
-    const std::uint32_t c = static_cast<std::uint32_t>(std::lower_bound(d, d + nd, v[i], valueLess<T>) - d);
+    // a NULL is the code one past the dictionary (CompressionDictionaryBuilder assigns null_code = number of codes)
+    const std::uint32_t c = (nulls && nulls[i]) ? static_cast<std::uint32_t>(nd)
+                                                : static_cast<std::uint32_t>(std::lower_bound(d, d + nd, v[i], valueLess<T>) - d);
     std::memcpy(dst + i * p.code_width, &c, p.code_width);
   }
 }
@@ -99,29 +112,43 @@ struct DateKey {           // DateLit ordered as (year, month, day): types/Datet
   bool operator<(const DateKey &o) const { return key() < o.key(); }
 };
 
-StripePlan planAttr(const qs_attr &a, const char *col, std::uint64_t n) {
+StripePlan planAttr(const qs_attr &a, const char *col, std::uint64_t n, const std::uint8_t *nulls) {
   switch (a.type) {
-    case QS_INT: return planCompressed(reinterpret_cast<const std::int32_t *>(col), n, true);
-    case QS_LONG: return planCompressed(reinterpret_cast<const std::int64_t *>(col), n, true);
-    case QS_FLOAT: return planCompressed(reinterpret_cast<const float *>(col), n, false);
-    case QS_DOUBLE: return planCompressed(reinterpret_cast<const double *>(col), n, false);
-    case QS_DATE: return planCompressed(reinterpret_cast<const DateKey *>(col), n, false);
+    case QS_INT: return planCompressed(reinterpret_cast<const std::int32_t *>(col), n, true, nulls);
+    case QS_LONG: return planCompressed(reinterpret_cast<const std::int64_t *>(col), n, true, nulls);
+    case QS_FLOAT: return planCompressed(reinterpret_cast<const float *>(col), n, false, nulls);
+    case QS_DOUBLE: return planCompressed(reinterpret_cast<const double *>(col), n, false, nulls);
+    case QS_DATE: return planCompressed(reinterpret_cast<const DateKey *>(col), n, false, nulls);
     default: {            // CHAR(n): kept native here (the reference would dictionary-encode long strings)
-      StripePlan p; p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * a.width; return p;
+      StripePlan p; p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * a.width;
+      for (std::uint64_t i = 0; nulls && i < n; ++i) p.has_nulls = p.has_nulls || nulls[i] != 0;
+      return p;
     }
   }
 }
 
-void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, const StripePlan &p) {
+void writeAttr(const qs_attr &a, char *dst, const char *col, std::uint64_t n, const StripePlan &p, const std::uint8_t *nulls) {
   if (p.encoding == QS_ENC_PLAIN) { std::memcpy(dst, col, n * a.width); return; }
   switch (a.type) {
-    case QS_INT: writeCodes(dst, reinterpret_cast<const std::int32_t *>(col), n, p); break;
-    case QS_LONG: writeCodes(dst, reinterpret_cast<const std::int64_t *>(col), n, p); break;
-    case QS_FLOAT: writeCodes(dst, reinterpret_cast<const float *>(col), n, p); break;
-    case QS_DOUBLE: writeCodes(dst, reinterpret_cast<const double *>(col), n, p); break;
-    case QS_DATE: writeCodes(dst, reinterpret_cast<const DateKey *>(col), n, p); break;
+    case QS_INT: writeCodes(dst, reinterpret_cast<const std::int32_t *>(col), n, p, nulls); break;
+    case QS_LONG: writeCodes(dst, reinterpret_cast<const std::int64_t *>(col), n, p, nulls); break;
+    case QS_FLOAT: writeCodes(dst, reinterpret_cast<const float *>(col), n, p, nulls); break;
+    case QS_DOUBLE: writeCodes(dst, reinterpret_cast<const double *>(col), n, p, nulls); break;
+    case QS_DATE: writeCodes(dst, reinterpret_cast<const DateKey *>(col), n, p, nulls); break;
     default: QS_CHECK(false);
   }
+}
+
+// BitVector<false>::BytesNeeded (utility/BitVector.hpp:107-125) and BitVector<true> for the per-tuple bitmap
+std::size_t bitVectorBytes(std::size_t bits) { return ((bits + 63) / 64) * 8; }
+std::size_t shortBitVectorBytes(std::size_t bits) {
+  return bits == 0 ? 0 : bits < 9 ? 1 : bits < 17 ? 2 : bits < 33 ? 4 : bitVectorBytes(bits);
+}
+// bit i of a most-significant-bit-first bit string held in little-endian words of `word_bytes` bytes
+void setMsbFirstBit(char *words, std::size_t word_bytes, std::size_t i) {
+  const std::size_t word = i / (8 * word_bytes), k = i % (8 * word_bytes);
+  unsigned char *b = reinterpret_cast<unsigned char *>(words) + word * word_bytes + (word_bytes - 1 - (k >> 3));
+  *b = static_cast<unsigned char>(*b | (0x80u >> (k & 7)));
 }
 
 }  // namespace
@@ -236,12 +263,27 @@ StorageManager::~StorageManager() {
 }
 
 void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const void *> &columns, std::uint64_t n_rows,
-                                  std::uint64_t rows_per_block, TupleStoreLayout layout) {
+                                  std::uint64_t rows_per_block, TupleStoreLayout layout,
+                                  const std::vector<const std::uint8_t *> &null_flags) {
   const std::vector<qs_attr> schema = rel->schema();
   QS_CHECK(columns.size() == schema.size());
+  QS_CHECK(null_flags.empty() || null_flags.size() == schema.size());
   if (rows_per_block == 0) rows_per_block = std::max<std::uint64_t>(n_rows, 1);
   const std::uint64_t n_blocks = (n_rows + rows_per_block - 1) / rows_per_block;
-  std::size_t slot_bytes = 0;
+  // NULL-able attributes in catalog order: attribute a is bit nullable_index[a] of a tuple's NULL bitmap
+  const std::uint64_t nullable = rel->nullableMask();
+  std::vector<int> nullable_index(schema.size(), -1);
+  std::size_t n_nullable = 0;
+  for (std::size_t a = 0; a < schema.size(); ++a) {
+    if ((nullable >> a) & 1) nullable_index[a] = static_cast<int>(n_nullable++);
+    else QS_CHECK(null_flags.empty() || null_flags[a] == nullptr);       // NULLs only where the catalog allows them
+  }
+  auto flags_of = [&](std::size_t a, std::uint64_t r0) -> const std::uint8_t * {
+    return (null_flags.empty() || !null_flags[a]) ? nullptr : null_flags[a] + r0;
+  };
+  const std::size_t tuple_null_bytes = shortBitVectorBytes(n_nullable);
+  const std::size_t tuple_null_word = n_nullable > 32 ? 8 : tuple_null_bytes;
+  std::size_t slot_bytes = tuple_null_bytes;
   for (const qs_attr &a : schema) slot_bytes += a.width;
 
   // ---- pass 1 (parallel): decide the physical form of every stripe, size the images
@@ -258,13 +300,20 @@ void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const 
     const std::uint64_t r0 = b * rows_per_block, n = std::min(rows_per_block, n_rows - r0);
     std::size_t bytes = 0;
     if (layout == TupleStoreLayout::kSplitRowStore) {
-      bytes = n * slot_bytes;
+      bytes = n * slot_bytes + 8;        // (+8: the last slot's NULL word may be read as a whole 8-byte word)
     } else {
       for (std::size_t a = 0; a < schema.size(); ++a) {
         const char *col = static_cast<const char *>(columns[a]) + r0 * schema[a].width;
         StripePlan &p = plans[b][a];
-        if (layout == TupleStoreLayout::kCompressedColumnStore) p = planAttr(schema[a], col, n);
-        else { p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * schema[a].width; }
+        if (layout == TupleStoreLayout::kCompressedColumnStore) {
+          p = planAttr(schema[a], col, n, flags_of(a, r0));
+          // an uncompressed stripe with NULLs carries a bitmap (CompressedBlockBuilder.cpp:439-452)
+          if (p.has_nulls && p.encoding != QS_ENC_DICT) bytes += bitVectorBytes(n);
+        } else {
+          p.encoding = QS_ENC_PLAIN; p.stripe_bytes = n * schema[a].width;
+          // BasicColumnStore: one bitmap per NULL-able attribute, NULLs or not (…SubBlock.cpp:152-166)
+          if (nullable_index[a] >= 0) bytes += bitVectorBytes(n);
+        }
         bytes += p.dict.size() + p.stripe_bytes;
       }
     }
@@ -296,7 +345,9 @@ void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const 
     char *w = slab.base + off[b];
     std::memset(w, 0, image_bytes[b]);
     if (layout == TupleStoreLayout::kSplitRowStore) {
-      std::size_t attr_off = 0;
+      // slot = [BitVector<true> over the NULL-able attributes][fixed-length attributes back to back]
+      // (storage/SplitRowStoreTupleStorageSubBlock.cpp:130,348)
+      std::size_t attr_off = tuple_null_bytes;
       for (std::size_t a = 0; a < schema.size(); ++a) {
         const std::uint32_t vw = schema[a].width;
         const char *col = static_cast<const char *>(columns[a]) + r0 * vw;
@@ -305,24 +356,50 @@ void StorageManager::loadRelation(CatalogRelation *rel, const std::vector<const 
         s = qs_stage_desc{};
         s.attr = static_cast<std::uint32_t>(a); s.encoding = QS_ENC_STRIDED; s.host = w + attr_off;
         s.stride = static_cast<std::uint32_t>(slot_bytes);
+        if (nullable_index[a] >= 0) {
+          const std::size_t k = static_cast<std::size_t>(nullable_index[a]);
+          if (const std::uint8_t *f = flags_of(a, r0))
+            for (std::uint64_t i = 0; i < n; ++i) if (f[i]) setMsbFirstBit(w + i * slot_bytes, tuple_null_word, k);
+          s.null_kind = QS_NULL_SLOT_WORD;
+          s.null_bitmap = w + (k / (8 * tuple_null_word)) * tuple_null_word;
+          s.null_arg = static_cast<std::uint32_t>(k % (8 * tuple_null_word));
+          s.null_stride = static_cast<std::uint32_t>(slot_bytes);
+          s.null_width = static_cast<std::uint32_t>(tuple_null_word);
+        }
         attr_off += vw;
       }
       return;
     }
-    // dictionaries first, then the stripes (CompressedTupleStorageSubBlock.cpp:281-342 layout order)
+    // dictionaries first, then the NULL bitmaps, then the stripes (CompressedTupleStorageSubBlock.cpp:281-342,
+    // CompressedColumnStoreTupleStorageSubBlock.cpp:755-798; BasicColumnStoreTupleStorageSubBlock.cpp:152-175)
     std::vector<const char *> dict_at(schema.size(), nullptr);
     for (std::size_t a = 0; a < schema.size(); ++a) {
       const StripePlan &p = plans[b][a];
       if (!p.dict.empty()) { std::memcpy(w, p.dict.data(), p.dict.size()); dict_at[a] = w; w += p.dict.size(); }
     }
+    std::vector<const char *> bitmap_at(schema.size(), nullptr);
+    for (std::size_t a = 0; a < schema.size(); ++a) {
+      const StripePlan &p = plans[b][a];
+      const bool wants = layout == TupleStoreLayout::kCompressedColumnStore ? (p.has_nulls && p.encoding != QS_ENC_DICT)
+                                                                           : nullable_index[a] >= 0;
+      if (!wants) continue;
+      if (const std::uint8_t *f = flags_of(a, r0))
+        for (std::uint64_t i = 0; i < n; ++i) if (f[i]) setMsbFirstBit(w, 8, i);
+      bitmap_at[a] = w;
+      w += bitVectorBytes(n);
+    }
     for (std::size_t a = 0; a < schema.size(); ++a) {
       const StripePlan &p = plans[b][a];
       const char *col = static_cast<const char *>(columns[a]) + r0 * schema[a].width;
-      writeAttr(schema[a], w, col, n, p);
+      writeAttr(schema[a], w, col, n, p, flags_of(a, r0));
       qs_stage_desc &s = B.stripes[a];
       s = qs_stage_desc{};
       s.attr = static_cast<std::uint32_t>(a); s.encoding = p.encoding; s.host = w; s.code_width = p.code_width;
-      if (p.encoding == QS_ENC_DICT) { s.dict = dict_at[a]; s.dict_entries = static_cast<std::uint32_t>(p.dict.size() / schema[a].width); }
+      if (p.encoding == QS_ENC_DICT) {
+        s.dict = dict_at[a]; s.dict_entries = static_cast<std::uint32_t>(p.dict.size() / schema[a].width);
+        if (p.has_nulls) { s.null_kind = QS_NULL_CODE; s.null_arg = s.dict_entries; }
+      }
+      if (bitmap_at[a]) { s.null_kind = QS_NULL_BITMAP; s.null_bitmap = bitmap_at[a]; s.null_arg = 0; s.null_stride = 1; }
       w += p.stripe_bytes;
     }
   });
@@ -439,10 +516,11 @@ qsgpu_relation_t StorageManager::deviceRelation(const CatalogRelation &rel, std:
     for (block_id id : ids) rows += static_cast<std::uint64_t>(blocks_.at(id).num_tuples);
     QS_CHECK_GPU(qsgpu_relation_create(device_, static_cast<std::uint32_t>(schema.size()), schema.data(),
                                        std::max<std::uint64_t>(rows, 1), &R.handle));
+    if (rel.nullableMask()) QS_CHECK_GPU(qsgpu_relation_set_nullable(R.handle, rel.nullableMask()));
     if (code_resident_) {
       const std::vector<RelationDictionary> &dicts = relationDictionaries(rel, ids);
       for (std::size_t a = 0; a < dicts.size(); ++a)
-        if (dicts[a].code_width)
+        if (dicts[a].code_width && !((rel.nullableMask() >> a) & 1))      // NULL-able attributes stay at native width
           QS_CHECK_GPU(qsgpu_relation_set_dictionary(R.handle, static_cast<std::uint32_t>(a), dicts[a].code_width,
                                                      dicts[a].values.data(), dicts[a].n_entries));
     }

@@ -78,8 +78,13 @@ class StorageManager {
   // The loader's job in the reference (TextScan -> InsertDestination -> blocks):
   // cut `n_rows` tuples given as native-width columns into blocks of
   // `rows_per_block` tuples in the requested layout and register them with `rel`.
+  // null_flags (optional): one entry per attribute, nullptr or one byte per row (non-zero = the value is NULL) for
+  // the attributes the catalog declares NULL-able.  Each layout records NULLs the way the reference does: a per-tuple
+  // BitVector<true> at the head of a SplitRowStore slot, one BitVector<false> per NULL-able attribute in a column
+  // store, the dictionary's null code (= number of codes) in a dictionary-compressed stripe.
   void loadRelation(CatalogRelation *rel, const std::vector<const void *> &columns, std::uint64_t n_rows,
-                    std::uint64_t rows_per_block, TupleStoreLayout layout);
+                    std::uint64_t rows_per_block, TupleStoreLayout layout,
+                    const std::vector<const std::uint8_t *> &null_flags = {});
   const StorageBlock &getBlock(block_id id) const;
   std::uint64_t hostBytes(const CatalogRelation &rel) const;      // bytes of all block images
 

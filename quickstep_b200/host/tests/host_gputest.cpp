@@ -3,6 +3,7 @@
 // are built the way ExecutionGenerator builds them and run by the QueryManager with 4 workers over relations
 // stored as several blocks; expected results are computed right here with plain loops.  Needs a B200.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -201,6 +202,74 @@ static void testPartitionAwareInsertDestination(StorageManager *sm, WorkerPool *
   std::printf("partition_aware_insert_destination(%zu) %s\n", num_partitions, (placed && c[0] == want_c && s2[0] == want_s) ? "ok" : "MISMATCH");
 }
 
+// A relation with NULL-able attributes in each of the three block layouts (per-tuple bitmap, per-column bitmap,
+// dictionary null code), aggregated with GROUP BY through the operator DAG: NULL arguments are skipped
+// (AggregationHandleSum.hpp:117-127), comparisons with a NULL are false, a group without a non-NULL argument has
+// COUNT(x) = 0, SUM(x) = 0 and MIN(y) NULL -- as the reference engine prints (tests/golden/ref_null_results.json).
+static void testNullableAggregation(StorageManager *sm, WorkerPool *pool, TupleStoreLayout layout, relation_id base_id) {
+  const std::uint64_t n = 30000;
+  std::vector<std::int32_t> g(n), y(n);
+  std::vector<double> x(n);
+  std::vector<std::uint8_t> xn(n), yn(n);
+  for (std::uint64_t i = 0; i < n; ++i) {
+    g[i] = static_cast<std::int32_t>(rnd() % 6);
+    xn[i] = (rnd() % 10) < 3 || g[i] == 2;                 // group 2: x is always NULL
+    yn[i] = (rnd() % 10) < 1 || g[i] == 2;
+    x[i] = xn[i] ? 0.0 : static_cast<double>(rnd() % 100000) / 100.0;
+    y[i] = yn[i] ? 0 : static_cast<std::int32_t>(rnd() % 2000) - 1000;
+  }
+  CatalogRelation in(base_id, "tn", {{"g", kInt}, {"x", kDouble, true}, {"y", kInt, true}});
+  CatalogRelation out(base_id + 1, "tn_out", {{"g", kInt}, {"sx", kDouble}, {"cx", kLong}, {"my", kInt}, {"c", kLong}}, true);
+  sm->loadRelation(&in, {g.data(), x.data(), y.data()}, n, 7000, layout, {nullptr, xn.data(), yn.data()});
+  QueryContext ctx(sm, sm->device());
+  QueryContext::AggregationSpec spec;
+  spec.predicate_root = spec.exprs.disj({spec.exprs.cmp(QS_GT, spec.exprs.attr(2, kInt), spec.exprs.lit_int(-500)),
+                                         spec.exprs.cmp(QS_EQ, spec.exprs.attr(0, kInt), spec.exprs.lit_int(2))});
+  const int ax = spec.exprs.attr(1, kDouble), ay = spec.exprs.attr(2, kInt);
+  spec.aggregates = {{QS_AGG_SUM, ax}, {QS_AGG_COUNT, ax}, {QS_AGG_MIN, ay}, {QS_AGG_COUNT, -1}};
+  spec.nullable_arguments = 0b0111;
+  spec.group_by_roots = {spec.exprs.attr(0, kInt)};
+  spec.strategy = QS_AGG_COMPACT_KEY;
+  spec.estimated_num_entries = 8;
+  const auto state = ctx.addAggregationState(std::move(spec));
+  const auto dst = ctx.addInsertDestination(&out, 16);
+  QueryPlan plan;
+  const auto i_agg = plan.addRelationalOperator(new AggregationOperator(1, in, true, state, 1));
+  const auto i_fin = plan.addRelationalOperator(new FinalizeAggregationOperator(1, state, 1, false, 1, out, dst));
+  plan.addDirectDependency(i_fin, i_agg, true);
+  QueryManager qm(&plan, &ctx, sm, pool);
+  qm.run();
+  qsgpu_relation_t rel = sm->temporary(out);
+  std::uint64_t rows = 0;
+  QS_CHECK_GPU(qsgpu_relation_num_rows(rel, &rows));
+  const auto k = readColumn<std::int32_t>(rel, 0, rows);
+  const auto sx = readColumn<double>(rel, 1, rows);
+  const auto cx = readColumn<std::int64_t>(rel, 2, rows), c = readColumn<std::int64_t>(rel, 4, rows);
+  const auto my = readColumn<std::int32_t>(rel, 3, rows);
+  std::vector<std::uint64_t> nulls(std::max<std::uint64_t>(rows, 1));
+  QS_CHECK_GPU(qsgpu_relation_read_nulls(rel, 0, rows, nulls.data()));
+  struct Want { double sx = 0; std::int64_t cx = 0, c = 0; std::int32_t my = 0; bool any_y = false; };
+  std::map<std::int32_t, Want> want;
+  for (std::uint64_t i = 0; i < n; ++i) {
+    const bool pass = (!yn[i] && y[i] > -500) || g[i] == 2;          // a comparison with a NULL is false
+    if (!pass) continue;
+    Want &w = want[g[i]];
+    ++w.c;
+    if (!xn[i]) { w.sx += x[i]; ++w.cx; }
+    if (!yn[i]) { w.my = w.any_y ? std::min(w.my, y[i]) : y[i]; w.any_y = true; }
+  }
+  bool ok = rows == want.size();
+  for (std::uint64_t i = 0; ok && i < rows; ++i) {
+    const Want &w = want[k[i]];
+    const bool y_null = (nulls[i] >> 3) & 1, x_null = (nulls[i] >> 1) & 1;
+    ok = ok && cx[i] == w.cx && c[i] == w.c && std::fabs(sx[i] - w.sx) <= 1e-9 * std::fabs(w.sx) && !x_null &&
+         y_null == !w.any_y && (y_null || my[i] == w.my);
+  }
+  EXPECT(ok && want.count(2) && want[2].cx == 0 && !want[2].any_y);
+  sm->dropTemporary(out);
+  std::printf("nullable_aggregation(layout %d) %s (%llu groups)\n", static_cast<int>(layout), ok ? "ok" : "MISMATCH", static_cast<unsigned long long>(rows));
+}
+
 int main() {
   int dev = 0;
   if (qsgpu_init(1, &dev) != 0) { std::printf("no CUDA device: %s\n", qsgpu_last_error()); return 2; }
@@ -211,6 +280,9 @@ int main() {
     testExistenceMapAggregation(&sm, &pool);
     testPartitionAwareInsertDestination(&sm, &pool, 4);
     testPartitionAwareInsertDestination(&sm, &pool, 3);
+    testNullableAggregation(&sm, &pool, TupleStoreLayout::kSplitRowStore, 100);
+    testNullableAggregation(&sm, &pool, TupleStoreLayout::kBasicColumnStore, 110);
+    testNullableAggregation(&sm, &pool, TupleStoreLayout::kCompressedColumnStore, 120);
   }
   if (g_failed) { std::printf("%d check(s) failed\n", g_failed); return 1; }
   std::printf("all host GPU tests passed\n");
