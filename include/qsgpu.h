@@ -601,6 +601,11 @@ int qsgpu_comm_unique_id(qs_comm_id *id);
 int qsgpu_comm_create(int dev, int rank, int n_ranks, const qs_comm_id *id, qsgpu_comm_t *out);
 int qsgpu_comm_destroy(qsgpu_comm_t comm);
 int qsgpu_comm_rank(qsgpu_comm_t comm, int *rank, int *n_ranks);
+/* *enabled = 1 when the ranks of `comm` have mapped one another's mailbox (CUDA IPC over NVLink / NVSwitch, set up by
+ * qsgpu_comm_create when every rank can reach every other; QSGPU_PEER_MERGE=0 turns it off): qsgpu_agg_merge_all then
+ * merges SINGLE_STATE / COMPACT_KEY states with ONE kernel that stores its partial state into the peers' memory,
+ * waits for theirs and folds -- no NCCL call on that path.  0: every collective goes through NCCL. */
+int qsgpu_comm_peer_memory(qsgpu_comm_t comm, int *enabled);
 /* All ranks have finished the work queued so far (device-side all-reduce of one word, then a host wait). */
 int qsgpu_comm_barrier(qsgpu_comm_t comm);
 /* Host values reduced over all ranks in place (op: 0 = sum, 1 = min, 2 = max): global row counts and the exact

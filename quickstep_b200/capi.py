@@ -188,6 +188,7 @@ SIGNATURES = {
     "qsgpu_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(qs_comm_id), _VPP]),
     "qsgpu_comm_destroy": (C.c_int, [_VP]),
     "qsgpu_comm_rank": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "qsgpu_comm_peer_memory": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "qsgpu_comm_barrier": (C.c_int, [_VP]),
     "qsgpu_comm_allreduce_i64": (C.c_int, [_VP, C.POINTER(C.c_int64), C.c_uint32, C.c_uint32]),
     "qsgpu_agg_merge_all": (C.c_int, [_VP, _VP]),

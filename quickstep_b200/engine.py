@@ -619,6 +619,12 @@ class Comm:
         dist.broadcast(t, 0)
         return cls(dev, rank, world, bytes(t.cpu().numpy().tobytes()))
 
+    def peer_memory(self) -> bool:
+        """Have the ranks mapped one another's mailbox (the one-kernel merge over NVLink peer memory)?"""
+        on = C.c_int(0)
+        A.check(A.load().qsgpu_comm_peer_memory(self.h, C.byref(on)))
+        return bool(on.value)
+
     def barrier(self):
         A.check(A.load().qsgpu_comm_barrier(self.h))
 

@@ -25,8 +25,14 @@ struct StripePlan {
 // smaller of {truncated (or native) stripe} and {dictionary + code stripe}.
 // Value order first, bit pattern as the tie-break (-0.0 and 0.0 are distinct dictionary entries,
 // exactly one code per stored bit pattern, so decode(encode(x)) is bit-identical to x).
+// A strict weak order also in the presence of NaNs (they go last, ordered by bit pattern among themselves): std::sort
+// and std::lower_bound need one, and `a < b` alone is not (NaN is unordered with everything).
 template <class T>
 bool valueLess(const T &a, const T &b) {
+  if constexpr (std::is_floating_point<T>::value) {
+    const bool an = a != a, bn = b != b;
+    if (an || bn) return (an && bn) ? std::memcmp(&a, &b, sizeof(T)) < 0 : bn;
+  }
   if (a < b) return true;
   if (b < a) return false;
   return std::memcmp(&a, &b, sizeof(T)) < 0;
@@ -467,6 +473,22 @@ const std::vector<StorageManager::RelationDictionary> &StorageManager::relationD
       total += s.dict_entries;
     }
     if (!all_dict || w <= 1) continue;            // a CHAR(1) code is no narrower than its value
+    if (schema[a].type == QS_FLOAT || schema[a].type == QS_DOUBLE) {
+      // The relation-wide dictionary is ordered and searched NUMERICALLY (comparisons on codes need code order = value
+      // order): -0.0 would collapse onto 0.0 (decode no longer bit-identical) and a NaN never compares equal (its block
+      // entry would be "missing").  Such attributes stay at native width.
+      bool special = false;
+      for (block_id id : ids) {
+        const qs_stage_desc &s = blocks_.at(id).stripes[a];
+        for (std::uint32_t e = 0; e < s.dict_entries && !special; ++e) {
+          const char *v = static_cast<const char *>(s.dict) + static_cast<std::size_t>(e) * w;
+          if (w == 4) { float f; std::uint32_t u; std::memcpy(&f, v, 4); std::memcpy(&u, v, 4); special = f != f || u == 0x80000000u; }
+          else { double f; std::uint64_t u; std::memcpy(&f, v, 8); std::memcpy(&u, v, 8); special = f != f || u == 0x8000000000000000ull; }
+        }
+        if (special) break;
+      }
+      if (special) continue;
+    }
     std::vector<const char *> entries;
     entries.reserve(total);
     for (block_id id : ids) {

@@ -270,6 +270,31 @@ static void testNullableAggregation(StorageManager *sm, WorkerPool *pool, TupleS
   std::printf("nullable_aggregation(layout %d) %s (%llu groups)\n", static_cast<int>(layout), ok ? "ok" : "MISMATCH", static_cast<unsigned long long>(rows));
 }
 
+// Code-resident mode with FLOAT / DOUBLE values that have no place in a numerically ordered dictionary: -0.0 (equal to
+// 0.0 but a different bit pattern) and NaN (equal to nothing).  The block builder still dictionary-compresses them
+// (one code per bit pattern); the storage manager keeps such an attribute at native width, and what comes back from
+// the device is bit-identical to what was loaded.
+static void testSpecialFloatsStayNative(StorageManager *sm) {
+  const std::uint64_t n = 20000;
+  std::vector<double> v(n), plain(n);
+  std::vector<std::int32_t> k(n);
+  const double specials[4] = {0.0, -0.0, std::nan(""), 1.5};
+  for (std::uint64_t i = 0; i < n; ++i) { v[i] = specials[rnd() % 4]; plain[i] = static_cast<double>(rnd() % 7); k[i] = static_cast<std::int32_t>(i); }
+  CatalogRelation rel(130, "sf", {{"k", kInt}, {"v", kDouble}, {"p", kDouble}});
+  sm->loadRelation(&rel, {k.data(), v.data(), plain.data()}, n, 6000, TupleStoreLayout::kCompressedColumnStore);
+  sm->setCodeResident(true);
+  qsgpu_relation_t dev = sm->deviceRelation(rel);
+  sm->setCodeResident(false);
+  const auto cv = sm->residentCoding(rel, 1), cp = sm->residentCoding(rel, 2);
+  const auto got = readColumn<double>(dev, 1, n), gotp = readColumn<double>(dev, 2, n);
+  const bool same = std::memcmp(got.data(), v.data(), n * 8) == 0 && std::memcmp(gotp.data(), plain.data(), n * 8) == 0;
+  EXPECT(cv.first == 0);            // -0.0 / NaN: native
+  EXPECT(cp.first == 1);            // seven ordinary values: 1-byte codes
+  EXPECT(same);
+  sm->evict(rel);
+  std::printf("special_floats_stay_native %s\n", (cv.first == 0 && cp.first == 1 && same) ? "ok" : "MISMATCH");
+}
+
 int main() {
   int dev = 0;
   if (qsgpu_init(1, &dev) != 0) { std::printf("no CUDA device: %s\n", qsgpu_last_error()); return 2; }
@@ -283,6 +308,7 @@ int main() {
     testNullableAggregation(&sm, &pool, TupleStoreLayout::kSplitRowStore, 100);
     testNullableAggregation(&sm, &pool, TupleStoreLayout::kBasicColumnStore, 110);
     testNullableAggregation(&sm, &pool, TupleStoreLayout::kCompressedColumnStore, 120);
+    testSpecialFloatsStayNative(&sm);
   }
   if (g_failed) { std::printf("%d check(s) failed\n", g_failed); return 1; }
   std::printf("all host GPU tests passed\n");

@@ -37,6 +37,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     E.init([local])
     comm = E.Comm.from_torch_distributed(local)
+    peer_on = comm.peer_memory()
     import qs_oracle as O
     import oracle_tpch as OT
     import tpch_data as D
@@ -178,6 +179,7 @@ def main():
     comm.destroy()
     dist.barrier()
     if rank == 0:
+        print("peer mailbox:", "on" if peer_on else "off", flush=True)
         print("MGPU OK", flush=True)
     dist.destroy_process_group()
 

@@ -18,11 +18,16 @@ def _n_gpus():
 @pytest.mark.gpu
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("world", [2, 4])
-def test_nccl_merges_match_oracle(world):
+@pytest.mark.parametrize("peer_merge", ["1", "0"], ids=["peer_memory", "nccl_only"])
+def test_nccl_merges_match_oracle(world, peer_merge):
+    """peer_memory: the fixed-size aggregation states are merged by k_merge_peer_compact through the CUDA-IPC mailbox
+    (comm.cu); nccl_only (QSGPU_PEER_MERGE=0): the same merge as ncclAllGather + fold.  Both must give the oracle's answers."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29600 + (os.getpid() % 300) + world
+    port = 29600 + (os.getpid() % 300) + world + (10 if peer_merge == "0" else 0)
+    env = dict(os.environ, QSGPU_PEER_MERGE=peer_merge)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")],
-                       capture_output=True, text=True, timeout=850)
+                       capture_output=True, text=True, timeout=850, env=env)
     assert r.returncode == 0 and "MGPU OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
+    assert ("peer mailbox: on" in r.stdout) == (peer_merge == "1"), r.stdout[-2000:]
