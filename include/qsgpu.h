@@ -627,6 +627,12 @@ int qsgpu_lip_allreduce(qsgpu_lip_t lip, qsgpu_comm_t comm);
  * hash join (every GPU builds its own copy of the table and probes its lineitem partition locally), or the
  * top-k candidates of every rank.  Row counts are exchanged first (one host synchronisation). */
 int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t comm, qsgpu_relation_t *out);
+/* The same for a relation every rank contributes at most max_rows_per_rank rows to (the same value on every rank: the
+ * LIMIT of a top-k).  When the ranks have a peer-memory mailbox (qsgpu_comm_peer_memory) and a rank's share fits a
+ * slot, ONE kernel stores each rank's rows into the peers' memory, waits for theirs and assembles the result in rank
+ * order; the row counts stay on the device, so the call only enqueues.  Otherwise it is qsgpu_relation_allgather. */
+int qsgpu_relation_allgather_small(qsgpu_relation_t local, qsgpu_comm_t comm, uint64_t max_rows_per_rank,
+                                   qsgpu_relation_t *out);
 
 /* ---------------------------------------------------------- instrumentation */
 /* CUDA-event time (ms) of the most recent kernel of the given family (launched by any thread of the process)

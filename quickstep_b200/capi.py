@@ -194,6 +194,7 @@ SIGNATURES = {
     "qsgpu_agg_merge_all": (C.c_int, [_VP, _VP]),
     "qsgpu_lip_allreduce": (C.c_int, [_VP, _VP]),
     "qsgpu_relation_allgather": (C.c_int, [_VP, _VP, _VPP]),
+    "qsgpu_relation_allgather_small": (C.c_int, [_VP, _VP, C.c_uint64, _VPP]),
     "qsgpu_set_timing": (C.c_int, [C.c_int]),
     "qsgpu_last_kernel_ms": (C.c_int, [C.c_uint32, C.POINTER(C.c_float)]),
     "qsgpu_kernel_ms_stats": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _U32P]),

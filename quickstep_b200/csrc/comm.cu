@@ -211,6 +211,73 @@ __global__ void __launch_bounds__(256) k_merge_peer_compact(const __grid_constan
   fold_gathered_compact(A, gathered, kMailSlotBytes / 8, n_ranks, inv);
 }
 
+/*
+ * All-gather of a SMALL relation (the top-k rows of every rank, a few hundred bytes) over peer memory, again one kernel
+ * and no host wait: the rank's row count may still be device-only (the relation was just produced), so the kernel reads
+ * it, stores [count | column 0 | column 1 ...] (fixed capacity per column) into its slot of every peer's mailbox, raises
+ * its flag, waits for the others, and copies the ranks' rows -- in rank order -- into the output relation, whose row
+ * count it sets.  The NCCL form needs the counts on the HOST first (one synchronisation) and one broadcast per
+ * (rank, attribute).
+ */
+struct PeerGatherDesc {
+  uint32_t n_cols, cap;                 // rows every rank may contribute
+  uint32_t width[kMaxCols + 1];
+  uint32_t col_off[kMaxCols + 1];       // byte offset of the column inside a slot (8-byte aligned), after the count word
+  const char *in[kMaxCols + 1];
+  char *out[kMaxCols + 1];
+  const unsigned long long *in_rows;    // device row count of the local relation
+  unsigned long long *out_rows;
+  uint32_t *error_flag;
+};
+
+__global__ void __launch_bounds__(256) k_allgather_peer(const __grid_constant__ PeerGatherDesc G, char *const *peers, uint32_t rank,
+                                                        uint32_t n_ranks, unsigned long long epoch) {
+  __shared__ unsigned long long s_first[kMaxMergeRanks + 1];
+  const uint32_t t = threadIdx.x;
+  const uint32_t parity = static_cast<uint32_t>(epoch & 1ull);
+  const size_t my_slot = kMailFlagBytes + (static_cast<size_t>(parity) * n_ranks + rank) * kMailSlotBytes;
+  const unsigned long long have = *G.in_rows;
+  if (have > G.cap && t == 0) atomicExch(G.error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));   // more rows than the caller promised
+  const unsigned long long mine = min(have, static_cast<unsigned long long>(G.cap));
+  for (uint32_t r = 0; r < n_ranks; ++r) {
+    char *dst = peers[r] + my_slot;
+    if (t == 0) *reinterpret_cast<unsigned long long *>(dst) = mine;
+    for (uint32_t c = 0; c < G.n_cols; ++c) {
+      const uint64_t bytes = mine * G.width[c];
+      for (uint64_t b = t; b < bytes; b += blockDim.x) dst[8 + G.col_off[c] + b] = G.in[c][b];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < n_ranks)
+    st_release_sys(reinterpret_cast<unsigned long long *>(peers[t]) + parity * kMaxMergeRanks + rank, epoch);
+  if (t < n_ranks) {
+    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(peers[rank]) + parity * kMaxMergeRanks + t;
+    while (ld_acquire_sys(flag) != epoch) __nanosleep(20);
+  }
+  __syncthreads();
+  const char *base = peers[rank] + kMailFlagBytes + static_cast<size_t>(parity) * n_ranks * kMailSlotBytes;
+  if (t == 0) {
+    unsigned long long acc = 0;
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+      s_first[r] = acc;
+      acc += __ldcg(reinterpret_cast<const unsigned long long *>(base + static_cast<size_t>(r) * kMailSlotBytes));
+    }
+    s_first[n_ranks] = acc;
+    *G.out_rows = acc;
+  }
+  __syncthreads();
+  for (uint32_t r = 0; r < n_ranks; ++r) {
+    const char *src = base + static_cast<size_t>(r) * kMailSlotBytes + 8;
+    const unsigned long long n = s_first[r + 1] - s_first[r];
+    for (uint32_t c = 0; c < G.n_cols; ++c) {
+      const uint64_t bytes = n * G.width[c];
+      char *dst = G.out[c] + s_first[r] * G.width[c];
+      for (uint64_t b = t; b < bytes; b += blockDim.x) dst[b] = __ldcg(src + G.col_off[c] + b);
+    }
+  }
+}
+
 // words[i] = OR over ranks of gathered[r][i]  (LIP filter bit words; BarrieredReadWriteConcurrentBitVector layout)
 __global__ void k_or_gathered(uint64_t *words, const uint64_t *gathered, uint64_t n_words, uint32_t n_ranks) {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_words;
@@ -542,6 +609,57 @@ int qsgpu_relation_allgather(qsgpu_relation_t local, qsgpu_comm_t c, qsgpu_relat
   if (st) { qsgpu_relation_destroy(rel); return st; }
   *out = rel;
   return QSGPU_OK;
+}
+
+int qsgpu_relation_allgather_small(qsgpu_relation_t local, qsgpu_comm_t c, uint64_t max_rows_per_rank, qsgpu_relation_t *out) {
+  if (!local || !out) { set_error(QSGPU_ERR_INVALID, "null relation"); return QSGPU_ERR_INVALID; }
+  Device *d = device(local->dev);
+  if (!d) return QSGPU_ERR_NO_DEVICE;
+  if (local->has_codes()) { set_error(QSGPU_ERR_UNSUPPORTED, "all-gather of a dictionary-coded relation"); return QSGPU_ERR_UNSUPPORTED; }
+  // The choice between the two forms must come out the same on every rank: it depends only on the schema, on
+  // max_rows_per_rank (the caller passes the same value everywhere, e.g. a LIMIT) and on the communicator.
+  if (c && c->n_ranks > 1 && c->mailbox && local->attrs.size() <= static_cast<size_t>(kMaxCols)) {
+    // every rank's share fits a mailbox slot: one kernel over peer memory, row counts never leave the device
+    PeerGatherDesc G{};
+    size_t off = 0;
+    const uint64_t cap = max_rows_per_rank;
+    G.n_cols = static_cast<uint32_t>(local->attrs.size()) + (local->nullable_mask ? 1u : 0u);
+    for (uint32_t a = 0; a < G.n_cols; ++a) {
+      const bool mask_col = a == local->attrs.size();
+      G.width[a] = mask_col ? 8u : local->attrs[a].width;
+      G.col_off[a] = static_cast<uint32_t>(off);
+      off += (cap * G.width[a] + 7) & ~static_cast<size_t>(7);
+    }
+    if (8 + off <= kMailSlotBytes) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      qsgpu_relation *rel = nullptr;
+      int st = qsgpu_relation_create(local->dev, static_cast<uint32_t>(local->attrs.size()), local->attrs.data(), std::max<uint64_t>(cap * c->n_ranks, 1), &rel);
+      if (st) return st;
+      if (local->nullable_mask) {
+        st = ensure_null_mask(rel, d);
+        if (st) { qsgpu_relation_destroy(rel); return st; }
+        rel->nullable_mask = local->nullable_mask;
+      }
+      for (uint32_t a = 0; a < G.n_cols; ++a) {
+        const bool mask_col = a == local->attrs.size();
+        G.in[a] = mask_col ? reinterpret_cast<const char *>(local->d_nulls) : local->cols[a];
+        G.out[a] = mask_col ? reinterpret_cast<char *>(rel->d_nulls) : rel->cols[a];
+      }
+      G.cap = static_cast<uint32_t>(cap);
+      G.in_rows = local->d_rows;
+      G.out_rows = rel->d_rows;
+      G.error_flag = d->d_error;
+      ++c->epoch;
+      k_allgather_peer<<<1, 256, 0, d->stream>>>(G, c->d_peer_mailbox, static_cast<uint32_t>(c->rank), static_cast<uint32_t>(c->n_ranks), c->epoch);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { qsgpu_relation_destroy(rel); return cuda_fail(e, "k_allgather_peer"); }
+      count_launch();
+      rel->dirty = true;                 // the row count stays on the device until somebody asks
+      *out = rel;
+      return QSGPU_OK;
+    }
+  }
+  return qsgpu_relation_allgather(local, c, out);
 }
 
 }  // extern "C"

@@ -639,6 +639,11 @@ class Comm:
     def lip_allreduce(self, lip: "LipFilter"):
         A.check(A.load().qsgpu_lip_allreduce(lip.h, self.h))
 
+    def allgather_small(self, rel: "Relation", max_rows_per_rank: int) -> "Relation":
+        out = C.c_void_p()
+        A.check(A.load().qsgpu_relation_allgather_small(rel.h, self.h, max_rows_per_rank, C.byref(out)))
+        return Relation(out, rel.schema, rel.names, rel.dev)
+
     def allgather(self, rel: "Relation") -> "Relation":
         out = C.c_void_p()
         A.check(A.load().qsgpu_relation_allgather(rel.h, self.h, C.byref(out)))

@@ -326,7 +326,8 @@ void TopKWorkOrder::execute() {
   QS_CHECK_GPU(qsgpu_topk(input_.relation, static_cast<std::uint32_t>(config_->keys.size()), config_->keys.data(), top_k_, &out));
   if (gather_comm_) {
     qsgpu_relation_t all = nullptr, top = nullptr;
-    QS_CHECK_GPU(qsgpu_relation_allgather(out, gather_comm_, &all));
+    // every rank contributes at most top_k_ rows: the one-kernel gather over peer memory when the ranks have it
+    QS_CHECK_GPU(qsgpu_relation_allgather_small(out, gather_comm_, top_k_, &all));
     QS_CHECK_GPU(qsgpu_topk(all, static_cast<std::uint32_t>(config_->keys.size()), config_->keys.data(), top_k_, &top));
     QS_CHECK_GPU(qsgpu_relation_destroy(all));
     QS_CHECK_GPU(qsgpu_relation_destroy(out));

@@ -114,6 +114,30 @@ def main():
         assert (allk == np.concatenate([np.arange(r_, bits, world * 7, dtype=np.int64) for r_ in range(world)])).all()
         g.destroy(); f.destroy(); krel.destroy()
 
+    # ---------------------------------------------------------------- qsgpu_relation_allgather_small (peer-memory form)
+    # ragged shares (rank r holds 3 + 2 r rows; one rank holds none), INT / DOUBLE / CHAR(5) columns, twice in a row
+    # (both parities of the mailbox), the local relation being the output of a Select whose row count is device-only
+    for rep in range(3):
+        n_loc = 0 if (rank == 1 and rep == 1) else 3 + 2 * rank
+        src = HostTable("s", [Column("k", A.QS_INT, (np.arange(40, dtype=np.int32) + 1000 * rank + rep)),
+                              Column("v", A.QS_DOUBLE, np.arange(40, dtype=np.float64) * 0.5 + rank),
+                              Column("c", A.QS_CHAR, np.array([b"r%dx%02d" % (rank, i) for i in range(40)], dtype="S5"), 5)])
+        srel = E.Relation.from_host(src, dev=local)
+        sel = E.Relation.create(srel.schema, 16, dev=local)
+        es = ExprSet()
+        E.select(srel, es, es.cmp(A.QS_LT, es.attr(0, A.QS_INT), es.lit_int(1000 * rank + rep + n_loc)), None,
+                 [es.attr(0, A.QS_INT), es.attr(1, A.QS_DOUBLE), es.attr(2, A.QS_CHAR, 5)], sel)
+        g = comm.allgather_small(sel, 16)
+        gk, gv, gc = g.read(0), g.read(1), g.read(2)
+        wk, wv, wc = [], [], []
+        for r_ in range(world):
+            n_r = 0 if (r_ == 1 and rep == 1) else 3 + 2 * r_
+            wk += [i + 1000 * r_ + rep for i in range(n_r)]
+            wv += [i * 0.5 + r_ for i in range(n_r)]
+            wc += [b"r%dx%02d" % (r_, i) for i in range(n_r)]
+        assert gk.tolist() == wk and gv.tolist() == wv and [bytes(x) for x in gc] == wc, (rank, rep, gk.tolist(), wk)
+        g.destroy(); sel.destroy(); srel.destroy()
+
     # ---------------------------------------------------------------- shuffled join, row-level parity with the oracle
     nb, npr = 40_000, 300_000
     rng = np.random.default_rng(5)
