@@ -173,7 +173,8 @@ def main():
     jt.build(rb, None, -1, 0)
     es = ExprSet()
     proj = [es.attr(1, A.QS_LONG, 8), es.attr(0, A.QS_LONG, 8), es.attr(1, A.QS_LONG, 8, 2)]      # probe id, key, build payload
-    out = E.Relation.create([LONG, LONG, LONG], max(1, n_p * 4), dev=local)
+    # a probe row meets nb * world / 30,000 build rows on average (duplicate build keys): size the output for that
+    out = E.Relation.create([LONG, LONG, LONG], max(1, n_p * (nb * world // 30_000 + 3)), dev=local)
     jt.probe(rp, es, -1, 0, A.QS_JOIN_INNER, -1, proj, out)
     rows = np.stack([out.read(0), out.read(1), out.read(2)], axis=1)
     gathered = [None] * world

@@ -29,5 +29,12 @@ def test_nccl_merges_match_oracle(world, peer_merge):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")],
                        capture_output=True, text=True, timeout=850, env=env)
-    assert r.returncode == 0 and "MGPU OK" in r.stdout, (r.stdout[-2000:], r.stderr[-6000:])
+    if r.returncode != 0 or "MGPU OK" not in r.stdout:
+        # the interesting part of eight interleaved tracebacks does not survive pytest's repr: keep all of it
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        log = os.path.join(ROOT, "gpurun_out", f"mgpu_worker_w{world}_peer{peer_merge}.log")
+        with open(log, "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+        errs = [ln for ln in r.stderr.splitlines() if "Error" in ln or "assert" in ln.lower()]
+        pytest.fail(f"worker failed (full output in {log}): " + " | ".join(errs[:6])[:1500])
     assert ("peer mailbox: on" in r.stdout) == (peer_merge == "1"), r.stdout[-2000:]
