@@ -366,6 +366,144 @@ __global__ void __launch_bounds__(1024) k_topk_sort_dev(const __grid_constant__ 
   if (threadIdx.x == 0) *rows_out = n_out;
 }
 
+// ---- the same selection in ONE launch for inputs of any size ------------------------------------------------------
+// The multi-launch form above costs a launch per pass: 11 dependent launches, ~10 us each, 127 us for Q3's 1.4e5
+// groups per GPU at SF100 / 8 GPUs -- all of it latency, the data is a megabyte.  Here every pass is a phase of one
+// kernel, separated by a grid-wide barrier (~2 us): the grid is launched cooperatively with at most one CTA per SM,
+// so all CTAs are resident and the barrier (a monotonic arrival counter in global memory) cannot deadlock.  Because a
+// pass is cheap now, selection continues until at most kTopkFewCand candidates remain (or the key is exhausted), which
+// keeps the final sort in block 0 short.  Candidates are appended in arrival order and then sorted with the full
+// comparator (row id last), so the result is deterministic.
+constexpr uint64_t kTopkFewCand = 256;
+struct TopkCoopState {
+  unsigned long long prefix, remaining, n_cand;
+  unsigned int done, arrived;
+  unsigned long long hist[256];
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *arrived, unsigned int &generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int target = (generation + 1) * gridDim.x;
+    atomicAdd(arrived, 1u);
+    while (*reinterpret_cast<volatile unsigned int *>(arrived) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+  ++generation;
+}
+
+__global__ void __launch_bounds__(256) k_topk_coop(const __grid_constant__ TopkDesc D, TopkCoopState *S, uint64_t *cand, uint32_t limit,
+                                                   unsigned long long *rows_out, uint32_t *error_flag) {
+  extern __shared__ __align__(16) char s_coop_raw[];
+  __shared__ unsigned int s_hist[256];
+  unsigned int generation = 0;
+  const uint64_t n = topk_rows(D);
+  const uint64_t k = min(static_cast<uint64_t>(limit), n);
+  const char *kp = D.key_col[0].ptr;
+  const uint32_t kw = D.key_col[0].width;
+  const uint8_t klt = D.key_ltype[0];
+  const bool kdesc = D.desc[0] != 0;
+  const uint64_t first = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  // (S was zeroed by the host-side memset queued before the launch; remaining starts at k)
+  if (blockIdx.x == 0 && threadIdx.x == 0) S->remaining = k;
+  grid_barrier(&S->arrived, generation);
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t prefix = *reinterpret_cast<volatile unsigned long long *>(&S->prefix);
+    const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
+    for (uint64_t row = first; row < n; row += step) {
+      const uint64_t key = sort_key(kp + row * kw, klt, kdesc);
+      if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&S->hist[threadIdx.x], static_cast<unsigned long long>(s_hist[threadIdx.x]));
+    grid_barrier(&S->arrived, generation);
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        volatile unsigned long long *h = S->hist;
+        uint64_t acc = 0, remaining = S->remaining;
+        int b = 0;
+        for (; b < 256; ++b) {
+          if (acc + h[b] >= remaining) break;
+          acc += h[b];
+        }
+        if (b == 256) b = 255;
+        const uint64_t below_or_in = (k - remaining) + acc + h[b];     // keys <= every key of bucket b
+        uint64_t p = prefix | (static_cast<uint64_t>(b) << shift);
+        S->remaining = remaining - acc;
+        if (below_or_in <= kTopkFewCand || shift == 0) {
+          if (shift > 0) p |= (1ull << shift) - 1;                      // take the whole bucket
+          S->done = 1;
+        }
+        S->prefix = p;
+      }
+      __syncthreads();
+      S->hist[threadIdx.x] = 0;
+    }
+    grid_barrier(&S->arrived, generation);
+    if (*reinterpret_cast<volatile unsigned int *>(&S->done)) break;
+  }
+  const uint64_t threshold = *reinterpret_cast<volatile unsigned long long *>(&S->prefix);
+  for (uint64_t row = first; row < n; row += step) {
+    if (sort_key(kp + row * kw, klt, kdesc) <= threshold) {
+      const unsigned long long pos = atomicAdd(&S->n_cand, 1ull);
+      if (pos < static_cast<unsigned long long>(kTopkMaxCand)) cand[pos] = row;
+    }
+  }
+  grid_barrier(&S->arrived, generation);
+  if (blockIdx.x != 0) return;
+  // block 0: full-comparator sort of the candidates, output
+  SortElem *e = reinterpret_cast<SortElem *>(s_coop_raw);
+  uint32_t m = static_cast<uint32_t>(min(*reinterpret_cast<volatile unsigned long long *>(&S->n_cand), static_cast<unsigned long long>(kTopkMaxCand) + 1));
+  if (m > static_cast<uint32_t>(kTopkMaxCand)) {       // more than kTopkMaxCand rows tie on the primary key at the cut
+    if (threadIdx.x == 0) atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CAPACITY));
+    m = kTopkMaxCand;
+  }
+  uint32_t N = 1;
+  while (N < m) N <<= 1;
+  for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+    SortElem x;
+    if (i < m) {
+      x.row = __ldcg(&cand[i]);
+      for (uint32_t q = 0; q < 4; ++q)
+        x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + x.row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
+    } else {
+      x.row = ~0ull;
+      for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
+    }
+    e[i] = x;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const SortElem a = e[i], b = e[j];
+          if (elem_less(b, a) == up) { e[i] = b; e[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = min(limit, m);
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const uint64_t row = e[i].row;
+    for (uint32_t c = 0; c < D.n_cols; ++c) {
+      const uint32_t w = D.in[c].width;
+      const char *src = D.in[c].ptr + row * w;
+      char *o = D.out[c] + static_cast<uint64_t>(i) * w;
+      for (uint32_t b = 0; b < w; ++b) o[b] = src[b];
+    }
+  }
+  if (threadIdx.x == 0) *rows_out = n_out;
+}
+
 // Whole top-k in ONE launch for inputs of up to kTopkSingleCta rows (Q3's ~1e5 groups, Q1's 4): one CTA does
 // the radix select of the limit-th primary key (byte passes, stopping as soon as the candidates fit), collects
 // the candidates, sorts them with the full comparator and writes the result and its row count.  The multi-kernel
@@ -805,6 +943,49 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     return QSGPU_OK;
   }
 
+  {
+    // one cooperative launch: every pass is a phase of the same kernel (see k_topk_coop).  Falls through to the
+    // multi-launch form when the device refuses the cooperative launch or QSGPU_TOPK_COOP=0.
+    const char *coop_env = std::getenv("QSGPU_TOPK_COOP");          // read per call: tests switch between the two forms
+    const bool coop_enabled = !(coop_env && coop_env[0] == '0');
+    int coop_ok = 0;
+    cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, d->id);
+    if (coop_enabled && coop_ok) {
+      uint64_t *cand2 = nullptr;
+      TopkCoopState *st2 = nullptr;
+      cudaError_t ce = dev_malloc(&cand2, kTopkMaxCand * 8);
+      if (ce == cudaSuccess) ce = dev_malloc(&st2, sizeof(TopkCoopState));
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(st2, 0, sizeof(TopkCoopState), d->stream);
+      const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(SortElem);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_topk_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      const bool on = timing_enabled();
+      if (ce == cudaSuccess) {
+        if (on) cudaEventRecord(d->ev0, d->stream);
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(d->sm_count), (n + 1023) / 1024));
+        uint32_t lim32 = static_cast<uint32_t>(limit);
+        unsigned long long *rows_out = rel->d_rows;
+        uint32_t *err = d->d_error;
+        void *args[] = {&D, &st2, &cand2, &lim32, &rows_out, &err};
+        ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_topk_coop), dim3(static_cast<unsigned>(std::max(grid, 1))), dim3(256), args, smem, d->stream);
+      }
+      if (ce == cudaSuccess) {
+        count_launch();
+        if (on) {
+          cudaEventRecord(d->ev1, d->stream);
+          cudaEventSynchronize(d->ev1);
+          float ms = 0;
+          cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+          record_ms(QS_K_TOPK, ms);
+        }
+        dev_free(cand2); dev_free(st2);
+        rel->dirty = true;
+        *out = rel;
+        return QSGPU_OK;
+      }
+      cudaGetLastError();
+      dev_free(cand2); dev_free(st2);
+    }
+  }
   uint64_t *pk = nullptr, *cand = nullptr;
   TopkState *state = nullptr;
   auto cleanup = [&]() { dev_free(pk); dev_free(cand); dev_free(state); };     // stream-ordered: after the launches below

@@ -688,11 +688,21 @@ def test_topk(G, OB, n, limit):
         assert (np.ascontiguousarray(g.columns[c].data).view(np.uint8) == np.ascontiguousarray(o.columns[c].data).view(np.uint8)).all()
 
 
-def test_topk_large_input_multi_pass_path(G, OB):
-    """More than 2^20 rows take the multi-kernel radix-select path (one host round trip per byte pass); same
-    answer as the oracle's full sort.  Also a LIMIT where thousands of rows tie on the primary key away from the
-    cut (ties AT the cut beyond 2048 rows are an error by design)."""
+@pytest.mark.parametrize("form", ["one_cooperative_launch", "one_launch_per_pass"])
+def test_topk_large_input_multi_pass_path(G, OB, form, monkeypatch):
+    """More than 2^14 rows take the grid-wide radix select: all passes inside ONE cooperatively launched kernel
+    (k_topk_coop), or -- QSGPU_TOPK_COOP=0, the fallback -- one launch per pass.  Same answer as the oracle's full sort.
+    Also a LIMIT where thousands of rows tie on the primary key away from the cut (ties AT the cut beyond 2048 rows
+    are an error by design), and an input of 20,000 rows with few distinct keys."""
+    monkeypatch.setenv("QSGPU_TOPK_COOP", "1" if form == "one_cooperative_launch" else "0")
     rng = np.random.default_rng(19)
+    small = HostTable("s", [Column("a", A.QS_INT, rng.integers(0, 40, size=20000).astype(np.int32)),
+                            Column("b", A.QS_LONG, rng.permutation(20000).astype(np.int64))])
+    g = G.topk(G.relation(small), [(0, False), (1, True)], 700)
+    o = OB.topk(small, [(0, False), (1, True)], 700)
+    assert g.n_rows == o.n_rows == 700
+    for cg, co in zip(g.columns, o.columns):
+        assert (cg.data == co.data).all()
     n = (1 << 20) + 12345
     th = HostTable("t", [Column("a", A.QS_DOUBLE, np.round(rng.normal(0, 1000, size=n), 1)),
                          Column("b", A.QS_LONG, rng.permutation(n).astype(np.int64))])
