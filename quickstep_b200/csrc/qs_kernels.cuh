@@ -275,6 +275,7 @@ __device__ __forceinline__ int local_lookup(uint64_t key, const AggSmem &M, uint
   for (uint32_t moved = 0; moved < LS;) {
     const int s = lslot[h];
     if (s >= 0) {
+      __threadfence_block();                 // acquire side of the publication below: the id first, then the key it guards
       if (lkeys[h] == key) return s;
       h = (h + 1) & (LS - 1);
       ++moved;
@@ -410,6 +411,7 @@ __device__ __forceinline__ void scan_agg_body(char *smem, const ScanDesc &S, con
 #pragma unroll
         for (int g = 0; g < HOT; ++g) {
           if (nhot == g && *reinterpret_cast<volatile uint32_t *>(&M.lready[g]) != 0u) {
+            __threadfence_block();           // lready[g] was raised after lkey_by_id[g] was written (local_lookup)
             hk[g] = *reinterpret_cast<volatile uint64_t *>(&M.lkey_by_id[g]);
             nhot = g + 1;
           }
