@@ -172,7 +172,21 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan, int max
     for (uint32_t c = 0; c < S->n_cols; ++c) S->cols[c].dict_smem = 0;
     dict_bytes = 0;
   }
-  const size_t fixed = kBarBytes + extra_smem + 256 + dict_bytes;
+  // shared-memory copies of the small LIP filters the scan probes (north star: "LIP filters in shared memory"): a
+  // filter of <= 32 KB (48 KB for all of one scan) is copied into every CTA before its first tile; larger ones are
+  // probed where they are (L2 holds them; a 188 KB filter per CTA would leave one resident CTA per SM)
+  size_t lip_bytes = 0;
+  {
+    static const bool lip_smem_on = [] { const char *e = std::getenv("QSGPU_LIP_SMEM"); return !(e && e[0] == '0'); }();
+    for (uint32_t f = 0; f < S->n_lip; ++f) {
+      S->lip[f].smem_off = 0;
+      const size_t b = (S->lip[f].n_words * 8 + 15) & ~static_cast<size_t>(15);
+      if (!lip_smem_on || S->lip[f].n_words == 0 || b > kLipSmemBytes || lip_bytes + b > (48u << 10)) continue;
+      S->lip[f].smem_off = 1;             // marked; the offset is assigned below, once the ring is sized
+      lip_bytes += b;
+    }
+  }
+  const size_t fixed = kBarBytes + extra_smem + 256 + dict_bytes + lip_bytes;
   const size_t per_sm = d->smem_per_sm;                     // 228 KB on B200
   const size_t per_block_max = d->smem_per_block_optin;     // 227 KB
   // Resident CTAs per SM the shared-memory ring allows: narrow scans (join keys, LIP builds: a few KB per
@@ -198,6 +212,12 @@ int plan_scan(Device *d, ScanDesc *S, size_t extra_smem, ScanPlan *plan, int max
     if (!S->cols[c].dict_smem) continue;
     S->cols[c].dict_soff = static_cast<uint32_t>(plan->smem);
     plan->smem += 256u * S->cols[c].width;
+  }
+  for (uint32_t f = 0; f < S->n_lip; ++f) {
+    if (!S->lip[f].smem_off) continue;
+    plan->smem = (plan->smem + 15) & ~static_cast<size_t>(15);
+    S->lip[f].smem_off = static_cast<uint32_t>(plan->smem);
+    plan->smem += (S->lip[f].n_words * 8 + 15) & ~static_cast<size_t>(15);
   }
   plan->ctas = ctas;
   int grid = d->sm_count * ctas;
@@ -1214,6 +1234,7 @@ int qsgpu_lip_create(int dev, uint32_t kind, uint32_t attr_type, int64_t min_val
   QS_CUDA(dev_malloc(&f->d.words, f->n_words * 8 + 64));
   QS_CUDA(cudaMemsetAsync(f->d.words, 0, f->n_words * 8 + 64, d->stream));
   f->d.stats = reinterpret_cast<unsigned long long *>(f->d.words + f->n_words);      // the 64 bytes behind the bit words
+  f->d.n_words = f->n_words;
   *out = f.release();
   return QSGPU_OK;
 }

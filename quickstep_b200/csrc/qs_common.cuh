@@ -125,7 +125,13 @@ struct LipDesc {
   // [0] = rows that probed this filter, [1] = rows it rejected, accumulated by every scan that probes it: what
   // LIPFilterAdaptiveProber keeps per filter (cnt / miss, utility/lip_filter/LIPFilterAdaptiveProber.hpp:103-127)
   unsigned long long *stats;
+  // A probe filter of at most kLipSmemBytes is copied into the CTA's dynamic shared memory at byte smem_off before the
+  // first tile (plan_scan decides; 0 = probed in global memory / L2): SURVEY.md section 8 north star, "LIP filters in
+  // shared memory".  n_words = 64-bit words of the filter.
+  uint64_t n_words;
+  uint32_t smem_off, pad;
 };
+constexpr uint32_t kLipSmemBytes = 32u << 10;   // per filter; 48 KB for all filters of one scan
 
 // What a scan kernel iterates over.
 struct ScanDesc {
@@ -203,13 +209,13 @@ __device__ __forceinline__ void bv_set(uint64_t *words, uint64_t bit) {
 // KIND / ANTI are compile-time properties of the kernel (Q::lip_kind); bounds,
 // cardinality and the bit words are run-time.
 template <uint32_t KIND, uint32_t ANTI>
-__device__ __forceinline__ bool lip_contains(const LipDesc &f, int64_t v) {
+__device__ __forceinline__ bool lip_contains(const LipDesc &f, const uint64_t *words, int64_t v) {
   if constexpr (KIND == QS_LIP_BITVECTOR_EXACT) {
     if (v < f.min_value || v > f.max_value) return ANTI != 0;
-    const bool set = bv_get(f.words, static_cast<uint64_t>(v - f.min_value));
+    const bool set = bv_get(words, static_cast<uint64_t>(v - f.min_value));
     return ANTI ? !set : set;
   } else {
-    return bv_get(f.words, static_cast<uint64_t>(v) % f.cardinality);
+    return bv_get(words, static_cast<uint64_t>(v) % f.cardinality);
   }
 }
 template <uint32_t KIND>

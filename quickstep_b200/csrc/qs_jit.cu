@@ -84,8 +84,10 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
       << "," << int(in.arg) << "," << int(in.flags) << "," << int(in.aux) << "}";
   }
   o << "}; return t[pc]; }\n";
+  o << "  static constexpr uint32_t n_lip = " << S.n_lip << ";\n";
   table(o, "uint32_t", "lip_kind", S.n_lip, S.lip, [](const LipDesc &l) { return l.kind; });
   table(o, "uint32_t", "lip_anti", S.n_lip, S.lip, [](const LipDesc &l) { return l.is_anti; });
+  table(o, "uint32_t", "lip_soff", S.n_lip, S.lip, [](const LipDesc &l) { return l.smem_off; });
   // aggregation
   {
     AggDesc Z{};
@@ -246,7 +248,7 @@ static std::string jit_key(const JitSpec &sp) {
     put(in.op, 1); put(in.type, 1); put(in.leaf, 1); put(in.ltype, 1); put(in.arg, 2); put(in.flags, 1); put(in.aux, 1);
   }
   put(S.n_lip, 4);
-  for (uint32_t i = 0; i < S.n_lip; ++i) { put(S.lip[i].kind, 4); put(S.lip[i].is_anti, 4); }
+  for (uint32_t i = 0; i < S.n_lip; ++i) { put(S.lip[i].kind, 4); put(S.lip[i].is_anti, 4); put(S.lip[i].smem_off, 4); }
   if (sp.A) {
     const AggDesc &A = *sp.A;
     put(1, 1); put(A.n_agg, 4); put(A.strategy, 4); put(A.n_key_cols, 4); put(A.key_words, 4);

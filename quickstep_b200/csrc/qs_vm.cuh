@@ -361,13 +361,17 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
       // LIP probes are always AND-ed right after (flags&2), so rows whose
       // current top value is false skip the (random) memory access.
       const LipDesc &f = S.lip[in.arg];
+      // the filter's bit words: the CTA's shared-memory copy when plan_scan made one (small filters), else global
+      const uint64_t *words;
+      if constexpr (Q::lip_soff(in.arg) != 0) words = reinterpret_cast<const uint64_t *>(qs_dyn_smem + Q::lip_soff(in.arg));
+      else words = f.words;
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         bool b = false;
         // pst[0] starts as the row's validity (rows of a ragged first / last tile outside the scanned range) and only
         // ever gets AND-ed: invalid rows are never probed
         if (pst[0][r] && ((in.flags & 2) == 0 || pst[SP - 1][r])) {
-          b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, static_cast<int64_t>(acc[r]));
+          b = lip_contains<Q::lip_kind(in.arg), Q::lip_anti(in.arg)>(f, words, static_cast<int64_t>(acc[r]));
           if constexpr (lip_ops<Q>() >= 2) {
             ++regs.lip_cnt[in.arg];
             regs.lip_miss[in.arg] += b ? 0u : 1u;
@@ -522,6 +526,20 @@ __device__ __forceinline__ void scan_tiles(const ScanDesc &S, char *smem, Body &
       const uint4 *src = reinterpret_cast<const uint4 *>(S.cols[c].dict);
       uint4 *dst = reinterpret_cast<uint4 *>(smem + Q::col_doff(c));
       for (uint32_t i = tid; i < n16; i += kBlock) dst[i] = src[i];
+    }
+  });
+  // ... and of the small LIP filters this scan probes (LIPFilterAdaptiveProber's filters live in the probing
+  // thread's cache in the reference; here the CTA's shared memory).  The filter is complete: its build ran earlier
+  // on the same stream.
+  static_for<0, kMaxLip>([&](auto ff) {
+    constexpr int f = QS_IDX(ff);
+    if constexpr (f < static_cast<int>(Q::n_lip)) {
+      if constexpr (Q::lip_soff(f) != 0) {
+        const uint64_t n = S.lip[f].n_words;
+        const uint64_t *src = S.lip[f].words;
+        uint64_t *dst = reinterpret_cast<uint64_t *>(smem + Q::lip_soff(f));
+        for (uint64_t i = tid; i < n; i += kBlock) dst[i] = src[i];
+      }
     }
   });
   __syncthreads();
