@@ -20,7 +20,8 @@ here is numpy on top of qs_oracle.predicate / qs_oracle.scalar (which see only t
     AggregationHandleMax.hpp:188-200;
     COUNT(x) counts the non-NULL values (AggregationHandleCount.hpp:126-133, nullable_type == true),
     COUNT(*) counts rows;
-  * rows with a NULL key neither enter a join hash table nor match in it: storage/HashTable.hpp:1384,1903.
+  * rows with a NULL key neither enter a join hash table nor match in it: storage/HashTable.hpp:1384,1903;
+    rows with a NULL group-by key belong to no group: storage/PackedPayloadHashTable.hpp:861-866.
 """
 import numpy as np
 
@@ -79,6 +80,8 @@ def aggregate(es, pred_root, aggregates, group_attr, table, nulls: np.ndarray):
     if group_attr is None:
         groups = {None: np.nonzero(keep)[0]}
     else:
+        # a row whose group-by key is NULL belongs to no group (PackedPayloadHashTable.hpp:861-866)
+        keep = keep & ~((nulls >> np.uint64(group_attr)) & np.uint64(1)).astype(bool)
         keys = table.columns[group_attr].data
         groups = {}
         idx = np.nonzero(keep)[0]

@@ -1633,7 +1633,12 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
   scan.n_lip_probe = n_lip_probe;
   scan.lip_probe = lip_probe;
   Lowering L(&state->exprs, input);
-  int st = lower_scan_predicate(L, &scan);
+  // Rows whose group-by key is NULL belong to no group: PackedPayloadHashTable::upsertValueAccessorCompositeKey skips
+  // them (storage/PackedPayloadHashTable.hpp:861-866, GetCompositeKeyFromValueAccessor<..., check_for_null_keys = true>;
+  // the engine prints no NULL group, tests/golden/ref_null_results.json "group_by_nullable")
+  uint64_t group_key_mask = 0;
+  for (uint32_t k = 0; k < state->A.n_key_cols; ++k) if (state->key_attr_ids[k] < 64) group_key_mask |= 1ull << state->key_attr_ids[k];
+  int st = lower_scan_predicate(L, &scan, group_key_mask);
   if (st) return st;
   AggDesc A = state->A;
   for (uint32_t k = 0; k < A.n_key_cols; ++k) {
@@ -1641,9 +1646,6 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     if (attr >= input->attrs.size() || input->attrs[attr].width != A.key_width[k]) { set_error(QSGPU_ERR_INVALID, "group-by attribute does not match the input relation"); return QSGPU_ERR_INVALID; }
     A.key_col[k] = static_cast<uint16_t>(L.stage_attr(attr));
   }
-  if (input->nullable_mask)
-    for (uint32_t k = 0; k < A.n_key_cols; ++k)
-      if (state->key_attr_ids[k] < 64 && ((input->nullable_mask >> state->key_attr_ids[k]) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "GROUP BY a NULL-able attribute"); return QSGPU_ERR_UNSUPPORTED; }
   std::vector<bool> nn_done(A.n_agg + 1, false);
   for (size_t i = 0; i < state->aggregates.size(); ++i) {
     const int w = state->value_word[i];

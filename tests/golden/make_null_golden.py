@@ -45,6 +45,8 @@ QUERIES = {
     "char_eq": "SELECT COUNT(*) FROM {t} WHERE c = 'ab';",
     "char_not_eq": "SELECT COUNT(*) FROM {t} WHERE NOT c = 'ab';",
     "attr_vs_attr": "SELECT COUNT(*), SUM(y) FROM {t} WHERE x < y;",
+    "group_by_nullable": "SELECT y, COUNT(*), SUM(x) FROM {t} WHERE g = 0 AND x < 2 GROUP BY y ORDER BY y;",
+    "group_by_nullable_counts": "SELECT COUNT(*), COUNT(y) FROM {t} WHERE g = 0 AND x < 2;",
 }
 
 
