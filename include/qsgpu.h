@@ -201,13 +201,14 @@ int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t
  *     (NegationPredicate::getAllMatches), arithmetic over a NULL is NULL;
  *   - SUM / AVG / MIN / MAX / COUNT(x) skip NULL arguments (AggregationHandleSum.hpp:117-127) and are NULL (COUNT: 0)
  *     for a group without a non-NULL argument -- declare such aggregates in qs_agg_spec.nullable_arguments;
- *   - rows with a NULL join key neither enter a join table nor match (storage/HashTable.hpp:1384,1903), and are not
- *     inserted into / are rejected by LIP filters;
+ *   - rows with a NULL join key neither enter a join table nor match (storage/HashTable.hpp:1384,1903): inner / semi
+ *     joins drop such a probe row, an anti join emits it and a left outer join emits it NULL-padded (:1999-2003);
+ *     they are not inserted into / are rejected by LIP filters;
  *   - Select and the probe side of an inner join carry the NULL-ness of what they project into the output relation.
  *   - rows whose GROUP BY key is NULL belong to no group (storage/PackedPayloadHashTable.hpp:861-866: the reference
  *     prints no NULL group).
- * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): sort, partitioning, anti / outer join keys and
- * build-side projections on a NULL-able attribute, and NULL-able attributes held as relation-wide dictionary codes.
+ * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): sort and partitioning on a NULL-able attribute, build-side
+ * projections of NULL-able attributes, and NULL-able attributes held as relation-wide dictionary codes.
  * qsgpu_relation_write_nulls sets the masks of rows written through qsgpu_relation_column / qsgpu_relation_wrap
  * (their stored values should be zero bytes); qsgpu_stage_blocks fills them from the block formats' own NULL
  * representations (qs_stage_desc.null_kind).

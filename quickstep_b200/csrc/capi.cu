@@ -2117,6 +2117,7 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
   st = fill_lip_build(n_lip_build, lip_build, L, rel, &K);
   if (st) return st;
   JoinDesc J = table->J;
+  J.null_col = 0xffff;               // (probe side only; NULL build keys are filtered by the scan predicate above)
   J.key_col = static_cast<uint16_t>(L.stage_attr(key_attr));
   J.key_ltype = vtype_of(rel->attrs[key_attr].type);
   if (n_keys == 2) { J.key2_present = 1; J.key2_col = static_cast<uint16_t>(L.stage_attr(key_attrs[1])); }
@@ -2176,13 +2177,10 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
   Lowering L(probe->exprs, rel, table->build_rel);
   uint64_t key_mask = 0;
   for (uint32_t i = 0; i < n_keys; ++i) if (probe_key_attrs[i] < 64) key_mask |= 1ull << probe_key_attrs[i];
-  if ((key_mask & rel->nullable_mask) && (join_type == QS_JOIN_LEFT_ANTI || join_type == QS_JOIN_LEFT_OUTER)) {
-    // such a row counts as "no match found" and IS emitted (HashTable::runOverKeysFromValueAccessor, :1999-2003);
-    // the probe kernel has no "passes but does not search" state yet
-    set_error(QSGPU_ERR_UNSUPPORTED, "anti / outer join probed with a NULL-able key attribute");
-    return QSGPU_ERR_UNSUPPORTED;
-  }
-  int st = lower_scan_predicate(L, probe, key_mask);
+  // a probe row with a NULL key matches nothing: inner / semi joins drop it, an anti join emits it and an outer join
+  // emits it NULL-padded (HashTable::runOverKeysFromValueAccessor, storage/HashTable.hpp:1999-2003) -- the probe
+  // kernel lets such a row pass without searching (JoinDesc::null_col), so the predicate stays what the plan says
+  int st = lower_scan_predicate(L, probe);
   if (st) return st;
   if (residual_root >= 0) { L.lower_pred(residual_root); L.mark_mid_end(); }
   SinkDesc K{};
@@ -2216,6 +2214,9 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
   }
   JoinDesc J = table->J;
   J.join_type = static_cast<uint8_t>(join_type);
+  J.null_col = 0xffff;
+  J.key_null_bits = key_mask & rel->nullable_mask;
+  if (J.key_null_bits) J.null_col = static_cast<uint16_t>(L.stage_null_mask());
   J.key_col = static_cast<uint16_t>(L.stage_attr(probe_key_attr));
   J.key_ltype = klt;
   if (n_keys == 2) { J.key2_present = 1; J.key2_col = static_cast<uint16_t>(L.stage_attr(probe_key_attrs[1])); }

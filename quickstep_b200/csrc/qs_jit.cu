@@ -120,6 +120,7 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
     o << "  static constexpr bool j_dense = " << (J.dense ? "true" : "false") << ";\n";
     o << "  static constexpr bool j_key2 = " << (J.key2_present ? "true" : "false") << ";\n";
     o << "  static constexpr uint32_t j_key2_col = " << J.key2_col << ";\n";
+    o << "  static constexpr uint32_t j_null_col = " << (sp.J ? J.null_col : 0xffffu) << ";\n";
     table(o, "uint32_t", "build_w", J.n_build_cols, J.build_cols, [](const ColDesc &c) { return c.width; });
     table(o, "uint32_t", "build_cw", J.n_build_cols, J.build_cols, [](const ColDesc &c) { return c.cw; });
   }
@@ -263,7 +264,7 @@ static std::string jit_key(const JitSpec &sp) {
   } else put(0, 1);
   if (sp.J) {
     const JoinDesc &J = *sp.J;
-    put(1, 1); put(J.key_col, 2); put(J.join_type, 1); put(J.key_ltype, 1); put(J.dense, 4); put(J.key2_present, 1); put(J.key2_col, 2);
+    put(1, 1); put(J.key_col, 2); put(J.join_type, 1); put(J.key_ltype, 1); put(J.dense, 4); put(J.key2_present, 1); put(J.key2_col, 2); put(J.null_col, 2);
     put(J.n_build_cols, 4);
     for (uint32_t i = 0; i < J.n_build_cols; ++i) { put(J.build_cols[i].width, 4); put(J.build_cols[i].cw, 1); }
   } else put(0, 1);

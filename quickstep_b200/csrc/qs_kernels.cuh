@@ -1021,6 +1021,11 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
     for (int r = 0; r < kRows; ++r) {
       pass[r] = valid[r] && (bits[r] & 1u);
       active[r] = pass[r];
+      if constexpr (Q::j_null_col != 0xffffu) {
+        // a NULL key passes but does not search (see JoinDesc::null_col)
+        const uint64_t m = *reinterpret_cast<const uint64_t *>(stage + Q::col_off(Q::j_null_col) + tile_row(r, tid) * 8u);
+        active[r] = active[r] && (m & J.key_null_bits) == 0ull;
+      }
       matched[r] = false;
       key[r] = join_key<Q>(stage, tile_row(r, tid));
       if constexpr (Q::j_dense) {

@@ -50,6 +50,12 @@ struct JoinDesc {
   uint8_t key2_present;
   uint16_t key2_col;
   uint8_t join_type;                // QS_JOIN_*
+  // Probe side with a NULL-able key: the staged slot of the probe relation's per-row NULL mask (0xffff = the key
+  // cannot be NULL) and the key attributes' bits in it.  A row with a NULL key passes the predicate but does not
+  // search: it matches nothing, so an anti join emits it and an outer join emits it NULL-padded
+  // (HashTable::runOverKeysFromValueAccessor, storage/HashTable.hpp:1999-2003).
+  uint16_t null_col;
+  uint64_t key_null_bits;
   uint32_t n_build_cols;
   ColDesc build_cols[kMaxCols];     // build relation columns for LEAF_BUILD / raw emits
   uint32_t *error_flag;

@@ -219,6 +219,50 @@ def test_predicates_and_projection(engine):
 
 
 @pytest.mark.parametrize("table", ["open", "dense"])
+@pytest.mark.parametrize("join_type", [A.QS_JOIN_LEFT_ANTI, A.QS_JOIN_LEFT_OUTER])
+def test_anti_and_outer_join_emit_null_key_rows(engine, table, join_type):
+    """A probe row with a NULL key matches nothing: the anti join emits it, the outer join emits it NULL-padded
+    (HashTable::runOverKeysFromValueAccessor, storage/HashTable.hpp:1999-2003); NULL build keys never enter the table."""
+    rng = np.random.default_rng(41)
+    nb, npr = 1500, 12000
+    build = HostTable("b", [Column("k", A.QS_INT, rng.integers(0, 600, size=nb).astype(np.int32)),
+                            Column("p", A.QS_LONG, np.arange(nb, dtype=np.int64))])
+    bnull = (rng.random(nb) < 0.2).astype(np.uint64)
+    probe = HostTable("p", [Column("k", A.QS_INT, rng.integers(0, 900, size=npr).astype(np.int32)),
+                            Column("i", A.QS_LONG, np.arange(npr, dtype=np.int64))])
+    pnull = (rng.random(npr) < 0.25).astype(np.uint64)
+    es = ExprSet()
+    pred = es.cmp(A.QS_GE, es.attr(1, A.QS_LONG), es.lit_long(100))          # rows 0..99 fail the probe predicate
+    outer = join_type == A.QS_JOIN_LEFT_OUTER
+    roots = [es.attr(1, A.QS_LONG), es.attr(0, A.QS_INT)] + ([es.attr(1, A.QS_LONG, 8, 2)] if outer else [])
+    schema = [(A.QS_LONG, 8), (A.QS_INT, 4)] + ([(A.QS_LONG, 8)] if outer else [])
+    brel, prel = nullable_relation(engine, build, bnull), nullable_relation(engine, probe, pnull, block_rows=2999)
+    jt = engine.JoinTable(A.QS_INT, nb, dense_range=(0, 599) if table == "dense" else None)
+    out = engine.Relation.create(schema, 200000)
+    try:
+        jt.build(brel, None, -1, 0)
+        jt.probe(prel, es, pred, 0, join_type, -1, roots, out)
+        got, got_nulls = out.read_all(), out.read_nulls()
+    finally:
+        out.destroy(); jt.destroy(); brel.destroy(); prel.destroy()
+    bk, pk = build.columns[0].data, probe.columns[0].data
+    keep = np.arange(npr) >= 100
+    pairs = NO.join_pairs(bk, bnull.astype(bool), pk, pnull.astype(bool), keep)
+    matched = {p for p, _b in pairs}
+    unmatched = [p for p in range(npr) if keep[p] and p not in matched]        # NULL-key rows included
+    assert sum(1 for p in unmatched if pnull[p]) > 1000
+    key_of = lambda p: None if pnull[p] else int(pk[p])
+    if outer:
+        exp = sorted([(p, key_of(p), int(b)) for p, b in pairs] + [(p, key_of(p), None) for p in unmatched], key=repr)
+        gotr = sorted(((int(got[0][i]), None if (int(got_nulls[i]) >> 1) & 1 else int(got[1][i]),
+                        None if (int(got_nulls[i]) >> 2) & 1 else int(got[2][i])) for i in range(len(got_nulls))), key=repr)
+    else:
+        exp = sorted(((p, key_of(p)) for p in unmatched), key=repr)
+        gotr = sorted(((int(got[0][i]), None if (int(got_nulls[i]) >> 1) & 1 else int(got[1][i])) for i in range(len(got_nulls))), key=repr)
+    assert gotr == exp
+
+
+@pytest.mark.parametrize("table", ["open", "dense"])
 @pytest.mark.parametrize("join_type", [A.QS_JOIN_INNER, A.QS_JOIN_LEFT_SEMI])
 def test_join_null_keys(engine, table, join_type):
     """NULL keys neither enter the table nor match; the probe side's NULL-able projections keep their masks."""
@@ -423,12 +467,12 @@ def test_refusals(engine):
                 st.run(rel)
             finally:
                 st.destroy()
-        with pytest.raises(QsGpuError):      # anti join probed with a NULL-able key
+        with pytest.raises(QsGpuError):      # build-side projection of a NULL-able attribute
             jt = engine.JoinTable(A.QS_INT, 16)
-            out = engine.Relation.create([(A.QS_INT, 4)], 2000)
+            out = engine.Relation.create([(A.QS_DOUBLE, 8)], 200000)
             try:
                 jt.build(rel, None, -1, 0)
-                jt.probe(rel, es, -1, 2, A.QS_JOIN_LEFT_ANTI, -1, [es.attr(0, A.QS_INT)], out)
+                jt.probe(rel, es, -1, 0, A.QS_JOIN_INNER, -1, [es.attr(1, A.QS_DOUBLE, 8, 2)], out)
             finally:
                 out.destroy(); jt.destroy()
         with pytest.raises(QsGpuError):      # relation-wide dictionary codes for a NULL-able attribute
