@@ -207,8 +207,10 @@ int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t
  *   - Select and the probe side of an inner join carry the NULL-ness of what they project into the output relation.
  *   - rows whose GROUP BY key is NULL belong to no group (storage/PackedPayloadHashTable.hpp:861-866: the reference
  *     prints no NULL group).
- * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): sort and partitioning on a NULL-able attribute, build-side
- * projections of NULL-able attributes, and NULL-able attributes held as relation-wide dictionary codes.
+ *   - NULL-able attributes of a join's build side are read through the matched build row's mask (projections, scalars
+ *     and the residual predicate alike).
+ * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): sort and partitioning on a NULL-able attribute, and
+ * NULL-able attributes held as relation-wide dictionary codes.
  * qsgpu_relation_write_nulls sets the masks of rows written through qsgpu_relation_column / qsgpu_relation_wrap
  * (their stored values should be zero bytes); qsgpu_stage_blocks fills them from the block formats' own NULL
  * representations (qs_stage_desc.null_kind).

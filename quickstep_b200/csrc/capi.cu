@@ -1340,6 +1340,10 @@ static int lower_projection(Lowering &L, uint32_t n_project, const int32_t *root
       L.lower_emit_null(j, nb);
       null_cols |= 1ull << j;
     }
+    if (const uint64_t nbb = L.build_null_bits(roots[j])) {      // ... or the matched build row's
+      L.lower_emit_null_build(j, nbb);
+      null_cols |= 1ull << j;
+    }
   }
   L.finish();
   if (!L.ok()) { set_error(L.status, L.err); return L.status; }
@@ -2215,6 +2219,7 @@ int qsgpu_join_probe_composite(qsgpu_join_table_t table, const qs_scan *probe, u
   JoinDesc J = table->J;
   J.join_type = static_cast<uint8_t>(join_type);
   J.null_col = 0xffff;
+  J.build_nulls = table->build_rel ? table->build_rel->d_nulls : nullptr;
   J.key_null_bits = key_mask & rel->nullable_mask;
   if (J.key_null_bits) J.null_col = static_cast<uint16_t>(L.stage_null_mask());
   J.key_col = static_cast<uint16_t>(L.stage_attr(probe_key_attr));

@@ -96,16 +96,40 @@ uint64_t Lowering::null_bits(int i) {
   if (!n || !rel) return 0;
   switch (n->kind) {
     case QS_N_ATTRIBUTE:
-      if (n->b == 2) {
-        if (build_rel && static_cast<uint32_t>(n->a) < 64 && ((build_rel->nullable_mask >> n->a) & 1ull))
-          fail(QSGPU_ERR_UNSUPPORTED, "NULL-able build-side attribute read through a join");
-        return 0;
-      }
+      if (n->b == 2) return 0;            // build side: build_null_bits
       return static_cast<uint32_t>(n->a) < 64 ? (rel->nullable_mask & (1ull << n->a)) : 0ull;
     case QS_N_UNARY: case QS_N_SHARED: return null_bits(n->a);
     case QS_N_BINARY: return null_bits(n->a) | null_bits(n->b);
     default: return 0;
   }
+}
+
+uint64_t Lowering::build_null_bits(int i) {
+  const qs_node *n = node(i);
+  if (!n || !build_rel) return 0;
+  switch (n->kind) {
+    case QS_N_ATTRIBUTE:
+      return (n->b == 2 && static_cast<uint32_t>(n->a) < 64) ? (build_rel->nullable_mask & (1ull << n->a)) : 0ull;
+    case QS_N_UNARY: case QS_N_SHARED: return build_null_bits(n->a);
+    case QS_N_BINARY: return build_null_bits(n->a) | build_null_bits(n->b);
+    default: return 0;
+  }
+}
+
+void Lowering::push_notnull_build(uint64_t bits, bool and_it) {
+  Instr in{};
+  in.op = OP_NOTNULL_BUILD;
+  in.aux = static_cast<uint8_t>(add_lit(bits));
+  push(in);
+  if (and_it) { Instr a{}; a.op = OP_AND; push(a); }
+}
+
+void Lowering::lower_emit_null_build(uint32_t out_col, uint64_t bits) {
+  Instr in{};
+  in.op = OP_EMIT_NULL_BUILD;
+  in.arg = static_cast<uint16_t>(out_col);
+  in.aux = static_cast<uint8_t>(add_lit(bits));
+  push(in);
 }
 
 void Lowering::push_notnull(uint64_t bits, bool and_it) {
@@ -138,10 +162,6 @@ void Lowering::lower_emit_null(uint32_t out_col, uint64_t bits) {
 int Lowering::build_attr(uint32_t attr) {
   if (!build_rel || attr >= build_rel->attrs.size()) {
     fail(QSGPU_ERR_INVALID, "build-side attribute without a build relation");
-    return 0;
-  }
-  if (attr < 64 && ((build_rel->nullable_mask >> attr) & 1ull)) {
-    fail(QSGPU_ERR_UNSUPPORTED, "NULL-able build-side attribute read through a join");
     return 0;
   }
   if (bslot_of_attr[attr] >= 0) return bslot_of_attr[attr];
@@ -482,6 +502,7 @@ void Lowering::lower_pred(int i) {
       // itself is well defined and its answer is AND-ed with "no operand is NULL".
       lower_comparison(n, l, r);
       if (const uint64_t nb = null_bits(n->a) | null_bits(n->b)) push_notnull(nb, true);
+      if (const uint64_t nbb = build_null_bits(n->a) | build_null_bits(n->b)) push_notnull_build(nbb, true);
       return;
     }
     default:

@@ -65,6 +65,9 @@ enum Op : uint8_t {
   OP_NULLSEL,     // acc = (col[arg] & lits[aux]) == 0 ? acc : lits[aux+1]: an aggregate skips NULL arguments
                   // (AggregationHandleSum.hpp:117-127); lits[aux+1] is the identity of the aggregate's combine
   OP_EMIT_NULL,   // sink.emit_null(arg, (col[flags] & lits[aux]) != 0): NULL-ness of projected column `arg`
+  // the same two for attributes of a join's BUILD side: the mask is the matched build row's (sink.build_null_mask)
+  OP_NOTNULL_BUILD,
+  OP_EMIT_NULL_BUILD,
 };
 
 enum Leaf : uint8_t { LEAF_COL = 0, LEAF_LIT = 1, LEAF_TMP = 2, LEAF_BUILD = 3 /*join build side*/ };

@@ -986,6 +986,10 @@ struct JoinSink : SinkBase {
     if (brow[r] == kEmptyRow) return 0;
     return load_native(build_value<COL, W>(brow[r]), LTYPE);
   }
+  // NULL mask of the build row matched by row r (only programs over a NULL-able build relation ask)
+  __device__ __forceinline__ uint64_t build_null_mask(int r) {
+    return brow[r] == kEmptyRow ? 0ull : J->build_nulls[brow[r]];
+  }
 };
 
 template <class Q>

@@ -53,6 +53,9 @@ struct Lowering {
   int null_slot = -1;
   int stage_null_mask();
   uint64_t null_bits(int i);                  // NULL-mask bits of the NULL-able scanned attributes scalar i reads
+  uint64_t build_null_bits(int i);            // ... of the NULL-able BUILD-side attributes it reads (joins)
+  void push_notnull_build(uint64_t bits, bool and_it);
+  void lower_emit_null_build(uint32_t out_col, uint64_t bits);
   void push_notnull(uint64_t bits, bool and_it);          // push(no attribute of `bits` is NULL) [and AND it in]
   void lower_null_select(uint64_t bits, uint64_t identity);   // acc = NULL ? identity : acc
   void lower_emit_null(uint32_t out_col, uint64_t bits);

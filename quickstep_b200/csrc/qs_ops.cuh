@@ -56,6 +56,7 @@ struct JoinDesc {
   // (HashTable::runOverKeysFromValueAccessor, storage/HashTable.hpp:1999-2003).
   uint16_t null_col;
   uint64_t key_null_bits;
+  const unsigned long long *build_nulls;   // per-row NULL masks of the build relation (nullptr: it has no NULL-able attribute)
   uint32_t n_build_cols;
   ColDesc build_cols[kMaxCols];     // build relation columns for LEAF_BUILD / raw emits
   uint32_t *error_flag;

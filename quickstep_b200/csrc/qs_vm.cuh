@@ -197,6 +197,7 @@ struct SinkBase {
   template <int J, int COL, int W> __device__ __forceinline__ void emit_raw_build() {}
   template <int COL, int LTYPE, int W> __device__ __forceinline__ uint64_t build_leaf(int) { return 0; }
   template <int J> __device__ __forceinline__ void emit_null(const bool (&)[kRows]) {}
+  __device__ __forceinline__ uint64_t build_null_mask(int) { return 0; }
 };
 
 // Per-thread VM state that survives between the predicate and emit sections.
@@ -224,7 +225,7 @@ __device__ __forceinline__ uint32_t tile_row(int r, int tid) { return r * kBlock
  */
 __host__ __device__ constexpr bool op_pushes(uint8_t op) {
   return op == OP_CMP || op == OP_CMP_CHAR || op == OP_CMP_CODE || op == OP_PUSH_TRUE || op == OP_PUSH_FALSE || op == OP_LIP ||
-         op == OP_NOTNULL;
+         op == OP_NOTNULL || op == OP_NOTNULL_BUILD;
 }
 template <class Q>
 __host__ __device__ constexpr int pred_depth(int pc, int end) {
@@ -251,7 +252,7 @@ __host__ __device__ constexpr int lip_ops() {
 // Does the program record NULL-ness of projected columns (a scan of a relation with NULL-able attributes)?
 template <class Q>
 __host__ __device__ constexpr bool emits_null() {
-  for (int i = 0; i < Q::n_total; ++i) if (Q::code(i).op == OP_EMIT_NULL) return true;
+  for (int i = 0; i < Q::n_total; ++i) if (Q::code(i).op == OP_EMIT_NULL || Q::code(i).op == OP_EMIT_NULL_BUILD) return true;
   return false;
 }
 
@@ -398,6 +399,16 @@ __device__ __forceinline__ void vm_step(const Lits &L, const ScanDesc &S, const 
 #pragma unroll
       for (int r = 0; r < kRows; ++r)
         isnull[r] = (*reinterpret_cast<const uint64_t *>(base + tile_row(r, tid) * 8u) & m) != 0ull;
+      sink.template emit_null<in.arg>(isnull);
+    } else if constexpr (in.op == OP_NOTNULL_BUILD) {
+      const uint64_t m = L.lits[in.aux];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) pst[SP][r] = (sink.build_null_mask(r) & m) == 0ull;
+    } else if constexpr (in.op == OP_EMIT_NULL_BUILD) {
+      const uint64_t m = L.lits[in.aux];
+      bool isnull[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) isnull[r] = (sink.build_null_mask(r) & m) != 0ull;
       sink.template emit_null<in.arg>(isnull);
     } else if constexpr (in.op == OP_EMIT) {
       sink.template emit<in.arg, in.type>(acc);

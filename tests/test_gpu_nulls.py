@@ -262,6 +262,58 @@ def test_anti_and_outer_join_emit_null_key_rows(engine, table, join_type):
     assert gotr == exp
 
 
+@pytest.mark.parametrize("join_type", [A.QS_JOIN_INNER, A.QS_JOIN_LEFT_OUTER])
+def test_join_build_side_nullable_attributes(engine, join_type):
+    """NULL-able attributes of the BUILD side read through the join: projected as they are, inside an expression with a
+    probe attribute, and in the residual predicate (a comparison with a NULL is false).  The NULL-ness comes from the
+    matched build row's mask."""
+    rng = np.random.default_rng(77)
+    nb, npr = 900, 8000
+    build = HostTable("b", [Column("k", A.QS_INT, rng.permutation(1200)[:nb].astype(np.int32)),          # unique keys
+                            Column("q", A.QS_DOUBLE, rng.normal(size=nb)),
+                            Column("w", A.QS_LONG, rng.integers(-5, 5, size=nb))])
+    bnull = ((rng.random(nb) < 0.3).astype(np.uint64) << np.uint64(1)) | ((rng.random(nb) < 0.3).astype(np.uint64) << np.uint64(2))
+    probe = HostTable("p", [Column("k", A.QS_INT, rng.integers(0, 1200, size=npr).astype(np.int32)),
+                            Column("v", A.QS_DOUBLE, rng.normal(size=npr))])
+    pnull = (rng.random(npr) < 0.2).astype(np.uint64) << np.uint64(1)
+    es = ExprSet()
+    inner = join_type == A.QS_JOIN_INNER
+    bq, bw, pv = es.attr(1, A.QS_DOUBLE, 8, 2), es.attr(2, A.QS_LONG, 8, 2), es.attr(1, A.QS_DOUBLE)
+    residual = es.cmp(A.QS_GE, bw, es.lit_long(-2)) if inner else -1           # an outer join takes no residual
+    roots = [es.attr(0, A.QS_INT), bq, es.add(pv, bq), bw]
+    schema = [(A.QS_INT, 4), (A.QS_DOUBLE, 8), (A.QS_DOUBLE, 8), (A.QS_LONG, 8)]
+    brel, prel = nullable_relation(engine, build, bnull), nullable_relation(engine, probe, pnull, block_rows=1999)
+    jt = engine.JoinTable(A.QS_INT, nb)
+    out = engine.Relation.create(schema, 50000)
+    try:
+        jt.build(brel, None, -1, 0)
+        jt.probe(prel, es, -1, 0, join_type, residual, roots, out)
+        got, got_nulls = out.read_all(), out.read_nulls()
+    finally:
+        out.destroy(); jt.destroy(); brel.destroy(); prel.destroy()
+    row_of = {int(k): i for i, k in enumerate(build.columns[0].data)}
+    qn, wn = ((bnull >> np.uint64(1)) & np.uint64(1)).astype(bool), ((bnull >> np.uint64(2)) & np.uint64(1)).astype(bool)
+    vn = ((pnull >> np.uint64(1)) & np.uint64(1)).astype(bool)
+    exp = []
+    for p in range(npr):
+        b = row_of.get(int(probe.columns[0].data[p]))
+        if b is None:
+            if not inner:
+                exp.append((int(probe.columns[0].data[p]), None, None, None))
+            continue
+        if inner and (wn[b] or build.columns[2].data[b] < -2):
+            continue
+        q = None if qn[b] else float(build.columns[1].data[b])
+        s_ = None if (qn[b] or vn[p]) else float(probe.columns[1].data[p]) + float(build.columns[1].data[b])
+        exp.append((int(probe.columns[0].data[p]), q, s_, None if wn[b] else int(build.columns[2].data[b])))
+    gotr = []
+    for i in range(len(got_nulls)):
+        m = int(got_nulls[i])
+        gotr.append((int(got[0][i]), None if (m >> 1) & 1 else float(got[1][i]), None if (m >> 2) & 1 else float(got[2][i]),
+                     None if (m >> 3) & 1 else int(got[3][i])))
+    assert len(exp) > 3000 and sorted(gotr, key=repr) == sorted(exp, key=repr)
+
+
 @pytest.mark.parametrize("table", ["open", "dense"])
 @pytest.mark.parametrize("join_type", [A.QS_JOIN_INNER, A.QS_JOIN_LEFT_SEMI])
 def test_join_null_keys(engine, table, join_type):
@@ -467,14 +519,6 @@ def test_refusals(engine):
                 st.run(rel)
             finally:
                 st.destroy()
-        with pytest.raises(QsGpuError):      # build-side projection of a NULL-able attribute
-            jt = engine.JoinTable(A.QS_INT, 16)
-            out = engine.Relation.create([(A.QS_DOUBLE, 8)], 200000)
-            try:
-                jt.build(rel, None, -1, 0)
-                jt.probe(rel, es, -1, 0, A.QS_JOIN_INNER, -1, [es.attr(1, A.QS_DOUBLE, 8, 2)], out)
-            finally:
-                out.destroy(); jt.destroy()
         with pytest.raises(QsGpuError):      # relation-wide dictionary codes for a NULL-able attribute
             rel.set_dictionary(2, 2, np.arange(-1000, 1000, dtype=np.int32))
     finally:
