@@ -311,7 +311,7 @@ def test_join_build_side_nullable_attributes(engine, join_type):
         m = int(got_nulls[i])
         gotr.append((int(got[0][i]), None if (m >> 1) & 1 else float(got[1][i]), None if (m >> 2) & 1 else float(got[2][i]),
                      None if (m >> 3) & 1 else int(got[3][i])))
-    assert len(exp) > 3000 and sorted(gotr, key=repr) == sorted(exp, key=repr)
+    assert len(exp) > 2000 and sorted(gotr, key=repr) == sorted(exp, key=repr)
 
 
 @pytest.mark.parametrize("table", ["open", "dense"])
