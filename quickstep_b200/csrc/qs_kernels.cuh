@@ -717,6 +717,18 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
 // per CTA tile reserves the output range, and survivors are written straight
 // from the staged tile to their final position (rows of a tile keep their
 // input order).
+// Survivors of a tile -> rows of the output relation.  QS_CTA_COMPACT (a JIT define, QSGPU_CTA_COMPACT=1) keeps the
+// CTA-wide, tile-ordered form for comparison.
+__device__ __forceinline__ void compact_rows(const bool (&flag)[kRows], uint32_t *s, unsigned long long *counter, uint64_t capacity,
+                                             uint32_t *error_flag, uint64_t (&idx)[kRows]) {
+#ifdef QS_CTA_COMPACT
+  cta_compact(flag, s, counter, capacity, error_flag, idx);
+#else
+  (void)s;
+  warp_compact(flag, counter, capacity, error_flag, idx);
+#endif
+}
+
 template <class Q>
 struct SelectSink : SinkBase {
   const SinkDesc *K;
@@ -786,7 +798,7 @@ __device__ __forceinline__ void scan_select_body(char *smem, const ScanDesc &S, 
     // LIPFilterBuilder::insertValueAccessor on the survivors.
     lip_build_rows<Q, SelectSink<Q>>(K, stage, tid, pass);
     if constexpr (Q::n_out > 0) {   // BuildLIPFilter has nothing to materialise
-      cta_compact(pass, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+      compact_rows(pass, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
       if constexpr (emits_null<Q>()) {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
@@ -1104,7 +1116,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         for (int r = 0; r < kRows; ++r) ok[r] = found[r];
       }
       if constexpr (inner) {
-        cta_compact(ok, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+        compact_rows(ok, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
         vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
@@ -1129,7 +1141,7 @@ __device__ __forceinline__ void join_probe_body(char *smem, const ScanDesc &S, c
         flag[r] = pass[r] && (Q::j_type == QS_JOIN_LEFT_SEMI ? matched[r] : !matched[r]);
         sink.brow[r] = kEmptyRow;
       }
-      cta_compact(flag, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
+      compact_rows(flag, s_compact, K.counter, K.capacity, K.error_flag, sink.idx);
 #pragma unroll
       for (int r = 0; r < kRows; ++r) sink.nm[r] = 0ull;
       vm_run<Q, Q::n_mid, Q::n_total>(L, S, stage, tid, regs, bits, sink);
