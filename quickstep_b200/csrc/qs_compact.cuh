@@ -60,14 +60,14 @@ __device__ __forceinline__ void cta_compact(const bool (&flag)[kRows], uint32_t 
   }
 }
 
-// Warp-wide form: every warp reserves the output range of its own survivors with one atomicAdd and places them in
-// (lane-row, lane) order.  No CTA barrier and no shared memory: a warp that waits for its reservation (an L2 atomic
-// round trip, ~1 us) stalls alone while the CTA's other warps go on, where cta_compact parks all eight behind three
-// __syncthreads and the one reservation (ncu of Q3's orders select: `barrier` was the top stall at 5.7 cycles per issued
-// instruction, 64 % of the HBM peak).  A warp without survivors issues no atomic at all.  The price is up to 8x the
-// atomics on the relation's row counter (same address, resolved in L2: ~5 M for the 600 M-row lineitem select, a few
-// microseconds) and an output order that interleaves warps instead of tiles -- which no consumer relies on (the
-// reference's blocks arrive in work-order completion order).
+// Warp-wide form (NOT the default: measured slower).  Every warp reserves the output range of its own survivors with one
+// atomicAdd and places them in (lane-row, lane) order: no CTA barrier, no shared memory, a warp that waits for its
+// reservation stalls alone.  The idea came from ncu of Q3's orders select (`barrier` the top stall, 5.7 cycles per issued
+// instruction, 64 % of the HBM peak).  Measured through the operator layer at SF10 (profiles/README.md, r3a): Q3 0.806 ms
+// with this form against 0.772 ms with cta_compact, Q1 / Q6 unchanged.  What it costs outweighs the barriers it removes:
+// up to 8x the atomics on the relation's row counter, and output runs of a warp's few survivors (3 % of the lineitem rows
+// pass: ~4 per warp) instead of a tile's ~30 -- more partially written sectors in the output relation.  Kept behind
+// QSGPU_WARP_COMPACT=1 so the comparison can be repeated.
 __device__ __forceinline__ void warp_compact(const bool (&flag)[kRows], unsigned long long *counter, uint64_t capacity,
                                              uint32_t *error_flag, uint64_t (&idx)[kRows]) {
   const int lane = threadIdx.x & 31;

@@ -60,10 +60,10 @@ static void table(std::ostringstream &o, const char *type, const char *name, uin
   o << "}; return t[i]; }\n";
 }
 
-// QSGPU_CTA_COMPACT=1: compile the scan kernels with the CTA-wide, tile-ordered compaction instead of the warp-wide one
+// QSGPU_WARP_COMPACT=1: compile the scan kernels with the warp-wide compaction instead of the CTA-wide, tile-ordered one
 // (qs_compact.cuh), for comparison.  Part of the generated source, hence of every cache key.
-static bool cta_compact_requested() {
-  static const bool on = [] { const char *e = std::getenv("QSGPU_CTA_COMPACT"); return e && e[0] == '1'; }();
+static bool warp_compact_requested() {
+  static const bool on = [] { const char *e = std::getenv("QSGPU_WARP_COMPACT"); return e && e[0] == '1'; }();
   return on;
 }
 
@@ -71,7 +71,7 @@ std::string jit_source(const JitSpec &sp, std::string *kernel_name) {
   const ScanDesc &S = *sp.S;
   const Program &P = *sp.P;
   std::ostringstream o;
-  if (cta_compact_requested()) o << "#define QS_CTA_COMPACT 1\n";
+  if (warp_compact_requested()) o << "#define QS_WARP_COMPACT 1\n";
   o << "#include \"qs_kernels.cuh\"\n#define QSC __host__ __device__ static constexpr\nnamespace qs {\nstruct Q {\n";
   o << "  static constexpr uint32_t n_cols = " << S.n_cols << ", n_stages = " << S.n_stages
     << ", stage_bytes = " << S.stage_bytes << ";\n";
@@ -256,7 +256,7 @@ static std::string jit_key(const JitSpec &sp) {
     const Instr &in = P.code[i];
     put(in.op, 1); put(in.type, 1); put(in.leaf, 1); put(in.ltype, 1); put(in.arg, 2); put(in.flags, 1); put(in.aux, 1);
   }
-  put(cta_compact_requested() ? 1 : 0, 1);
+  put(warp_compact_requested() ? 1 : 0, 1);
   put(S.n_lip, 4);
   for (uint32_t i = 0; i < S.n_lip; ++i) { put(S.lip[i].kind, 4); put(S.lip[i].is_anti, 4); put(S.lip[i].smem_off, 4); }
   if (sp.A) {

@@ -717,15 +717,15 @@ __device__ __forceinline__ void scan_groupby_body(char *smem, const ScanDesc &S,
 // per CTA tile reserves the output range, and survivors are written straight
 // from the staged tile to their final position (rows of a tile keep their
 // input order).
-// Survivors of a tile -> rows of the output relation.  QS_CTA_COMPACT (a JIT define, QSGPU_CTA_COMPACT=1) keeps the
-// CTA-wide, tile-ordered form for comparison.
+// Survivors of a tile -> rows of the output relation: CTA-wide and tile-ordered.  QS_WARP_COMPACT (a JIT define,
+// QSGPU_WARP_COMPACT=1) selects the warp-wide form, which measured SLOWER (see qs_compact.cuh).
 __device__ __forceinline__ void compact_rows(const bool (&flag)[kRows], uint32_t *s, unsigned long long *counter, uint64_t capacity,
                                              uint32_t *error_flag, uint64_t (&idx)[kRows]) {
-#ifdef QS_CTA_COMPACT
-  cta_compact(flag, s, counter, capacity, error_flag, idx);
-#else
+#ifdef QS_WARP_COMPACT
   (void)s;
   warp_compact(flag, counter, capacity, error_flag, idx);
+#else
+  cta_compact(flag, s, counter, capacity, error_flag, idx);
 #endif
 }
 
