@@ -467,9 +467,11 @@ int qsgpu_agg_existence_map(qsgpu_agg_state_t state, qsgpu_lip_t *out);
  * aggregate that saw no non-NULL value is NULL (COUNT(x): 0); with GROUP BY only MIN / MAX are, while SUM is 0 and
  * AVG is 0 / 0.0 = NaN for such a group (the hash-table payload of SUM / AVG is the bare running sum,
  * AggregationHandleSum.hpp:176-178, AggregationHandleAvg.hpp:180-189).
- * With null_mask == NULL the call only enqueues for SINGLE_STATE / COMPACT_KEY states (the live group count is
- * read on the device; the output's row count stays device-side until somebody asks), so a query's tail --
- * finalize, the wrapping Select, the sort -- is queued while the scan kernel is still running.
+ * With null_mask == NULL the call only enqueues, for every strategy: the live group count is read on the device (the
+ * state's group counter, or the length of the list of occupied table slots a collect kernel writes), the output is
+ * sized for a bound the host knows (256 groups; the table's slots / the rows a hash table was fed) and its row count
+ * stays device-side until somebody asks -- so a query's tail (finalize, the wrapping Select, the sort) is queued while
+ * the scan kernel is still running.
  */
 int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out,
                        uint64_t *null_mask);

@@ -1735,6 +1735,7 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
       rows = rows > row_begin ? rows - row_begin : 0;
       st = maybe_grow(state, d, rows);
       if (st) return st;
+      state->rows_fed += rows;
       A.tags = state->A.tags; A.keys = state->A.keys; A.states = state->A.states; A.cap = state->A.cap;
     }
     st = plan_scan(d, &S, 0, &plan);
@@ -1749,13 +1750,32 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
   return QSGPU_OK;
 }
 
+// Enqueue-only form for finalization: the slot index list and its length (d_idx_count) stay on the device; *upper_out
+// bounds the number of groups from what the host knows (slots of the table; for a hash table also the rows it was fed).
+static int collect_groups_async(qsgpu_agg_state *s, Device *d, uint64_t *upper_out) {
+  AggDesc &A = s->A;
+  QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
+  if (A.cap == 0) { *upper_out = 0; return QSGPU_OK; }               // no work order ever ran: no groups
+  if (s->idx_cap < A.cap + 1) {
+    if (s->d_idx) dev_free(s->d_idx);
+    QS_CUDA(dev_malloc(&s->d_idx, (A.cap + 1) * 8 + 64));
+    s->idx_cap = A.cap + 1;
+  }
+  const uint64_t table_rows = A.cap + (s->strategy == QS_AGG_SEPARATE_CHAINING ? 1 : 0);
+  QS_CUDA(launch_collect_slots(A.states, A.words, table_rows, s->d_idx, s->d_idx_count,
+                               s->existence ? s->existence->d.words : nullptr, d->stream));
+  count_launch();
+  *upper_out = s->strategy == QS_AGG_SEPARATE_CHAINING ? std::min<uint64_t>(table_rows, s->rows_fed) : table_rows;
+  return QSGPU_OK;
+}
+
 static int collect_groups(qsgpu_agg_state *s, Device *d, uint64_t *n_out) {
   AggDesc &A = s->A;
   if (A.cap == 0) { *n_out = 0; return check_device_error(d); }      // no work order ever ran: no groups
-  if (s->idx_cap < A.cap) {
+  if (s->idx_cap < A.cap + 1) {
     if (s->d_idx) dev_free(s->d_idx);
-    QS_CUDA(dev_malloc(&s->d_idx, A.cap * 8 + 64));
-    s->idx_cap = A.cap;
+    QS_CUDA(dev_malloc(&s->d_idx, (A.cap + 1) * 8 + 64));
+    s->idx_cap = A.cap + 1;
   }
   QS_CUDA(cudaMemsetAsync(s->d_idx_count, 0, 8, d->stream));
   const uint64_t table_rows = A.cap + (s->strategy == QS_AGG_SEPARATE_CHAINING ? 1 : 0);
@@ -1849,6 +1869,7 @@ int qsgpu_agg_merge_partial(qsgpu_agg_state_t state, const void *d_states, const
     if (state->strategy == QS_AGG_SEPARATE_CHAINING) {
       int st = maybe_grow(state, d, n_groups);
       if (st) return st;
+      state->rows_fed += n_groups;
     }
     QS_CUDA(launch_merge_foreign_table(state->A, static_cast<const uint64_t *>(d_states), static_cast<const uint64_t *>(d_keys),
                                        n_groups, d->stream));
@@ -1866,8 +1887,10 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   // Fixed-size states: the output relation is sized for the state's row limit and the kernel reads the live group
   // count on the device, so the call only ENQUEUES (no host wait; a capacity error of the scan surfaces at the
   // next read of the result).  Tables: the groups are collected first and their number sizes the output.
+  // Tables: the occupied slots are collected on the device and their number stays there too (the output is sized for
+  // an upper bound the host knows: the slots, and for a hash table the rows it was fed) -- no host wait here either.
   uint64_t n = dense ? A.partial_rows : 0;
-  int st = dense ? QSGPU_OK : collect_groups(state, d, &n);
+  int st = dense ? QSGPU_OK : collect_groups_async(state, d, &n);
   if (st) return st;
   // output schema: group-by attributes, then one column per aggregate
   std::vector<qs_attr> attrs = state->key_attrs;
@@ -1908,7 +1931,10 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
   for (uint32_t j = 0; j < F.n_out; ++j) F.out[j] = rel->cols[A.n_key_cols + j];
   const uint64_t *keys = dense ? A.gid_keys : A.keys;
   F.rows_out = rel->d_rows;
-  F.d_n_groups = state->strategy == QS_AGG_COMPACT_KEY ? A.n_groups : nullptr;
+  // live group count on the device: the state's dense id counter (COMPACT_KEY), or the length of the collected slot
+  // list (tables; a 64-bit counter whose low word is read)
+  F.d_n_groups = state->strategy == QS_AGG_COMPACT_KEY ? A.n_groups
+               : !dense ? reinterpret_cast<const uint32_t *>(state->d_idx_count) : nullptr;
   if (state->strategy == QS_AGG_SINGLE_STATE || any_nn) {
     // aggregates over zero rows -- or, for a NULL-able argument, over zero non-NULL values -- are SQL NULL:
     // recorded in the output relation's per-row NULL mask
@@ -1941,7 +1967,7 @@ int qsgpu_agg_finalize(qsgpu_agg_state_t state, qsgpu_relation_t *out, uint64_t 
         if (state->aggregates[j].function != QS_AGG_COUNT && row[state->nn_word[j]] == 0) *null_mask |= 1ull << j;
     }
   }
-  if (state->strategy == QS_AGG_COMPACT_KEY) {
+  if (state->strategy != QS_AGG_SINGLE_STATE) {
     rel->dirty = true;                // the kernel stored the live group count in the relation's device counter
   } else {
     rel->host_rows = n;

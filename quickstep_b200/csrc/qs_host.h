@@ -84,6 +84,7 @@ struct qsgpu_agg_state {
   qsgpu_lip *existence = nullptr;
   uint64_t exp_cap = 0;
   uint64_t estimated = 0;
+  uint64_t rows_fed = 0;              // SEPARATE_CHAINING: rows handed to work orders + merged foreign groups (>= groups)
 };
 
 struct qsgpu_join_table {
