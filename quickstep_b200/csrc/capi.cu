@@ -1725,6 +1725,13 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
     QS_CUDA(launch_merge_partials(A, static_cast<uint32_t>(plan.grid), d->stream));
     count_launch(2);
   } else {
+    // everything that does not depend on the table's size first (ring plan, kernel look-up): the host wait below
+    // drains the stream, and what follows it is on the query's critical path
+    st = plan_scan(d, &S, 0, &plan);
+    if (st) return st;
+    JitKernel *kern = nullptr;
+    st = query_kernel(JF_GROUPBY, S, L.P, plan, &A, nullptr, nullptr, 1, &kern);
+    if (st) return st;
     if (state->strategy == QS_AGG_SEPARATE_CHAINING && !t_sc) {
       // Size the table for the rows this work order can really add.  The input's row count may still be
       // device-only (a temporary relation just produced); maybe_grow synchronises anyway, so read it
@@ -1738,11 +1745,6 @@ int qsgpu_agg_run(qsgpu_agg_state_t state, qsgpu_relation_t input, uint64_t row_
       state->rows_fed += rows;
       A.tags = state->A.tags; A.keys = state->A.keys; A.states = state->A.states; A.cap = state->A.cap;
     }
-    st = plan_scan(d, &S, 0, &plan);
-    if (st) return st;
-    JitKernel *kern = nullptr;
-    st = query_kernel(JF_GROUPBY, S, L.P, plan, &A, nullptr, nullptr, 1, &kern);
-    if (st) return st;
     KernelTimer timer(d, QS_K_GROUPBY);
     QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, &A, nullptr, nullptr));
     count_launch();
@@ -2123,14 +2125,6 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
     if (table->build_rel && table->build_rel != rel) { set_error(QSGPU_ERR_UNSUPPORTED, "one build relation per join table"); return QSGPU_ERR_UNSUPPORTED; }
     table->build_rel = rel;
     if (table->J.dense && !table->J.next && !t_sc) QS_CUDA(dev_malloc(&table->J.next, std::max<uint64_t>(rel->capacity, 1) * 8));
-    if (!table->J.dense && !t_sc) {
-      // the rows this work order can insert (the count of a temporary relation may still be device-side)
-      int rs = sync_rows(rel);
-      if (rs) return rs;
-      const uint64_t hi = std::min<uint64_t>(scan->row_end, rel->host_rows);
-      rs = join_reserve(table, d, hi > scan->row_begin ? hi - scan->row_begin : 0);
-      if (rs) return rs;
-    }
   }
   Lowering L(scan->exprs, rel);
   uint64_t key_mask = 0;
@@ -2162,6 +2156,18 @@ int qsgpu_join_build_composite(qsgpu_join_table_t table, const qs_scan *scan, ui
   JitKernel *kern = nullptr;
   st = query_kernel(JF_JOIN_BUILD, S, L.P, plan, nullptr, &K, &J, 1, &kern);
   if (st) return st;
+  if (!table->J.dense && !t_sc) {
+    // Sizing comes last: the rows this work order can insert may only be known on the device (a temporary relation
+    // just produced), reading them drains the stream, and whatever the host does after that -- it used to be the
+    // lowering and the kernel look-up above -- is on the query's critical path.
+    int rs = sync_rows(rel);
+    if (rs) return rs;
+    const uint64_t hi = std::min<uint64_t>(scan->row_end, rel->host_rows);
+    rs = join_reserve(table, d, hi > scan->row_begin ? hi - scan->row_begin : 0);
+    if (rs) return rs;
+    J.slots = table->J.slots;          // the reservation may have chosen the mask / moved the slots
+    J.cap = table->J.cap;
+  }
   KernelTimer timer(d, QS_K_JOIN_BUILD);
   QS_CUDA(launch_query_kernel(d, kern, S, L.P, plan, nullptr, &K, &J));
   count_launch();
