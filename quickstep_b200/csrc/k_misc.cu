@@ -77,18 +77,9 @@ __global__ void __launch_bounds__(kBlock) k_part_hist(const __grid_constant__ Pa
   extern __shared__ unsigned int s_hist[];
   for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x) s_hist[p] = 0;
   __syncthreads();
-  // rows of a warp that fall into the same partition are counted by ONE shared-memory atomic: with 32 partitions a
-  // warp's 32 rows hit ~20 distinct counters instead of issuing 32 atomics, many of them on the same word
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  const uint64_t first = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-  const uint64_t rounds = (D.n_rows + stride - 1) / stride;            // the same for every thread: no divergent exit
-  for (uint64_t it = 0; it < rounds; ++it) {
-    const uint64_t row = first + it * stride;
-    const bool have = row < D.n_rows;
-    const uint32_t p = have ? part_of(D, row) : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, p);
-    if (have && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&s_hist[p], static_cast<unsigned int>(__popc(peers)));
-  }
+  for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < D.n_rows;
+       row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&s_hist[part_of(D, row)], 1u);
   __syncthreads();
   for (uint32_t p = threadIdx.x; p < D.n_parts; p += blockDim.x)
     if (s_hist[p]) atomicAdd(&D.hist[p], static_cast<unsigned long long>(s_hist[p]));
@@ -125,20 +116,9 @@ __global__ void __launch_bounds__(kBlock, 6) k_part_scatter(const __grid_constan
       const uint32_t i = static_cast<uint32_t>(r) * kBlock + threadIdx.x;
       pr[r] = i < n_here ? part_of(D, row0 + i) : 0xffffffffu;
     }
-    // rank inside the step's share of the partition: the lowest lane of each group of equal partitions reserves the
-    // group's ranks with one atomic (__match_any_sync finds the group), the others take base + their position in it
-    // -- the per-row atomicAdd serialised on the few counters (32 partitions: 64 rows of a step per counter)
 #pragma unroll
-    for (int r = 0; r < kPartRows; ++r) {
-      const uint32_t p = pr[r];
-      const uint32_t peers = __match_any_sync(0xffffffffu, p);
-      const uint32_t lane = threadIdx.x & 31;
-      const uint32_t leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (p != 0xffffffffu && lane == leader) base = atomicAdd(&s_count[p], static_cast<unsigned int>(__popc(peers)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (p != 0xffffffffu) pr[r] = (p << 16) | (base + __popc(peers & ((1u << lane) - 1u)));
-    }
+    for (int r = 0; r < kPartRows; ++r)
+      if (pr[r] != 0xffffffffu) pr[r] = (pr[r] << 16) | atomicAdd(&s_count[pr[r]], 1u);
     __syncthreads();
     if (threadIdx.x == 0) {          // exclusive scan of the per-partition counts (n_parts <= 1024)
       unsigned int acc = 0;
