@@ -62,6 +62,25 @@ inline std::vector<qs_attr> SchemaOf(const CatalogRelationSchema &relation) {
   return out;
 }
 
+// NULL-able attributes of a relation, as qsgpu_relation_set_nullable takes them (bit a = attribute a): the reference
+// types every attribute as nullable or not (types/Type.hpp:129) and picks its NULL-checking code paths from that.
+inline std::uint64_t NullableMaskOf(const CatalogRelationSchema &relation) {
+  std::uint64_t mask = 0;
+  for (CatalogRelationSchema::const_iterator it = relation.begin(); it != relation.end(); ++it)
+    if (it->getType().isNullable() && it->getID() < 64) mask |= 1ull << it->getID();
+  return mask;
+}
+
+// qs_agg_spec.nullable_arguments: bit j = aggregate j's argument has a NULL-able type.  `arguments` is what
+// AggregationOperationState's constructor receives (storage/AggregationOperationState.hpp:109-121); the reference hands
+// the same types to AggregateFunction::createHandle, which is where its handles learn whether to check for NULL.
+inline std::uint64_t NullableArgumentsOf(const std::vector<std::vector<std::unique_ptr<const Scalar>>> &arguments) {
+  std::uint64_t mask = 0;
+  for (std::size_t j = 0; j < arguments.size() && j < 64; ++j)
+    if (!arguments[j].empty() && arguments[j].front()->getType().isNullable()) mask |= 1ull << j;
+  return mask;
+}
+
 // The device image of the input relation's blocks this work order scans (the GPU twin of a BlockReference).
 struct DeviceRows {
   qsgpu_relation_t relation = nullptr;
