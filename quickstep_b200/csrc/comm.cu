@@ -131,6 +131,27 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait until a peer has raised `flag` to `epoch`.  A peer that never arrives (its process died, or it took another
+// path through the plan) must not wedge this GPU: after kPeerWaitNs the kernel gives up, raises QSGPU_ERR_CUDA in the
+// device error word (reported at the next read of a result) and goes on with whatever is in the mailbox.
+constexpr unsigned long long kPeerWaitNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ void wait_peer_flag(const unsigned long long *flag, unsigned long long epoch, uint32_t *error_flag) {
+  if (ld_acquire_sys(flag) == epoch) return;
+  const unsigned long long t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_sys(flag) != epoch) {
+    __nanosleep(20);
+    if ((++spins & 0xfffu) == 0 && global_timer_ns() - t0 > kPeerWaitNs) {
+      atomicExch(error_flag, static_cast<uint32_t>(QSGPU_ERR_CUDA));
+      return;
+    }
+  }
+}
 
 // ---- kernels ---------------------------------------------------------------------------------------------
 // Fold the gathered [states | keys] blocks of all ranks, IN RANK ORDER, into this rank's state (the own block
@@ -202,10 +223,8 @@ __global__ void __launch_bounds__(256) k_merge_peer_compact(const __grid_constan
   __syncthreads();
   if (t < n_ranks)
     st_release_sys(reinterpret_cast<unsigned long long *>(peers[t]) + parity * kMaxMergeRanks + rank, epoch);
-  if (t < n_ranks) {
-    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(peers[rank]) + parity * kMaxMergeRanks + t;
-    while (ld_acquire_sys(flag) != epoch) __nanosleep(20);
-  }
+  if (t < n_ranks)
+    wait_peer_flag(reinterpret_cast<const unsigned long long *>(peers[rank]) + parity * kMaxMergeRanks + t, epoch, A.error_flag);
   __syncthreads();
   const uint64_t *gathered = reinterpret_cast<const uint64_t *>(peers[rank] + kMailFlagBytes + static_cast<size_t>(parity) * n_ranks * kMailSlotBytes);
   fold_gathered_compact(A, gathered, kMailSlotBytes / 8, n_ranks, inv);
@@ -251,10 +270,8 @@ __global__ void __launch_bounds__(256) k_allgather_peer(const __grid_constant__ 
   __syncthreads();
   if (t < n_ranks)
     st_release_sys(reinterpret_cast<unsigned long long *>(peers[t]) + parity * kMaxMergeRanks + rank, epoch);
-  if (t < n_ranks) {
-    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(peers[rank]) + parity * kMaxMergeRanks + t;
-    while (ld_acquire_sys(flag) != epoch) __nanosleep(20);
-  }
+  if (t < n_ranks)
+    wait_peer_flag(reinterpret_cast<const unsigned long long *>(peers[rank]) + parity * kMaxMergeRanks + t, epoch, G.error_flag);
   __syncthreads();
   const char *base = peers[rank] + kMailFlagBytes + static_cast<size_t>(parity) * n_ranks * kMailSlotBytes;
   if (t == 0) {
