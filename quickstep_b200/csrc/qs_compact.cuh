@@ -18,7 +18,10 @@ __device__ __forceinline__ void cta_compact(const bool (&flag)[kRows], uint32_t 
   static_assert(kCounts <= 32, "one warp scans the per-warp counts");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t ball[kRows];
-  __syncthreads();                               // previous users of `s` are done
+  // No barrier before `s` is written: every caller has a CTA-wide barrier between two compactions anyway -- the
+  // end-of-tile __syncthreads of scan_tiles, and the __syncthreads_or that opens every round of the join probe -- so the
+  // threads that read `s` in the previous compaction are past it.  (It used to be the first of three barriers here;
+  // ncu had `barrier` as the top stall of Q3's orders select.)
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
     ball[r] = __ballot_sync(0xffffffffu, flag[r]);
