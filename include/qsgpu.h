@@ -209,8 +209,9 @@ int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t
  *     prints no NULL group).
  *   - NULL-able attributes of a join's build side are read through the matched build row's mask (projections, scalars
  *     and the residual predicate alike).
- * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): sort and partitioning on a NULL-able attribute, and
- * NULL-able attributes held as relation-wide dictionary codes.
+ *   - ORDER BY (qsgpu_topk) puts NULLs first or last as qs_sort_key says.
+ * Refused with QSGPU_ERR_UNSUPPORTED (never silently wrong): partitioning on a NULL-able attribute, and NULL-able
+ * attributes held as relation-wide dictionary codes.
  * qsgpu_relation_write_nulls sets the masks of rows written through qsgpu_relation_column / qsgpu_relation_wrap
  * (their stored values should be zero bytes); qsgpu_stage_blocks fills them from the block formats' own NULL
  * representations (qs_stage_desc.null_kind).
@@ -528,6 +529,11 @@ int qsgpu_join_destroy(qsgpu_join_table_t table);
 /* ----------------------------------------------------------------- top-k   */
 /* K9.  SortRunGeneration + SortMergeRun with LIMIT (§8f row 1): order rows of
  * `input` by up to 4 sort attributes and keep the first `limit` rows. */
+/* descending: bit 0 = DESC.  Bits 1-2 order NULLs of a NULL-able sort attribute: QS_SORT_NULLS_FIRST / QS_SORT_NULLS_LAST
+ * as written in the query, 0 = the reference's default (NULLs first iff descending, parser/ParseOrderBy.hpp:53-66). */
+#define QS_SORT_DESCENDING 1u
+#define QS_SORT_NULLS_FIRST 2u
+#define QS_SORT_NULLS_LAST 4u
 typedef struct qs_sort_key { uint32_t attr; uint32_t descending; } qs_sort_key;
 int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
                uint64_t limit, qsgpu_relation_t *out);

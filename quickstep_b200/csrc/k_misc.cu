@@ -212,6 +212,12 @@ struct TopkDesc {
   ColDesc key_col[4];
   uint8_t key_ltype[4];
   uint8_t desc[4];
+  // NULL-able sort keys: the input's per-row NULL masks (nullptr = no sort key can be NULL), key q's bit in them
+  // (0 = not NULL-able) and where a NULL sorts: rank 0 = before every value, 2 = after (values have rank 1).  The
+  // reference's rule (parser/ParseOrderBy.hpp:53-66): NULLS FIRST / LAST as written, else first iff descending.
+  const unsigned long long *nulls;
+  uint64_t key_null_bit[4];
+  uint8_t null_rank[4];
   uint64_t n_rows;
   const unsigned long long *d_n_rows;   // optional device-side row count of the input (min with n_rows)
   uint32_t n_cols;
@@ -221,11 +227,17 @@ struct TopkDesc {
 
 constexpr int kTopkMaxCand = 2048;
 
-struct SortElem { uint64_t k[4]; uint64_t row; };
+// One candidate of the final sort: per key a 2-bit rank (NULL before / value / NULL after; byte q of `ranks`) and the
+// order-preserving key of the value, compared lexicographically as (rank 0, key 0, rank 1, key 1, ...), row id last.
+struct SortElem { uint64_t k[4]; uint64_t row; uint32_t ranks; uint32_t pad; };
 
 __device__ __forceinline__ bool elem_less(const SortElem &a, const SortElem &b) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) if (a.k[i] != b.k[i]) return a.k[i] < b.k[i];
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t ra = (a.ranks >> (8 * i)) & 0xffu, rb = (b.ranks >> (8 * i)) & 0xffu;
+    if (ra != rb) return ra < rb;
+    if (a.k[i] != b.k[i]) return a.k[i] < b.k[i];
+  }
   return a.row < b.row;
 }
 
@@ -245,6 +257,45 @@ __device__ __forceinline__ uint64_t topk_rows(const TopkDesc &D) {
   return D.d_n_rows ? min(D.n_rows, static_cast<uint64_t>(*D.d_n_rows)) : D.n_rows;
 }
 
+// Is sort key q of `row` NULL?
+__device__ __forceinline__ bool topk_key_is_null(const TopkDesc &D, uint32_t q, uint64_t row) {
+  return D.nulls != nullptr && (D.nulls[row] & D.key_null_bit[q]) != 0ull;
+}
+// The key the radix select runs on.  For a NULL-able first sort key it is COARSE: the NULL rank in the two top bits over
+// the value's key shifted down by two -- monotone in (rank, key), so every row at or below the selected threshold is
+// collected (a superset of the answer when low bits tie) and the exact comparator of the final sort decides.
+__device__ __forceinline__ uint64_t topk_primary_key(const TopkDesc &D, uint64_t row) {
+  const uint64_t k = sort_key(D.key_col[0].ptr + row * D.key_col[0].width, D.key_ltype[0], D.desc[0] != 0);
+  if (D.nulls == nullptr || D.key_null_bit[0] == 0ull) return k;
+  const bool isnull = (D.nulls[row] & D.key_null_bit[0]) != 0ull;
+  return (static_cast<uint64_t>(isnull ? D.null_rank[0] : 1u) << 62) | (isnull ? 0ull : (k >> 2));
+}
+__device__ __forceinline__ SortElem topk_elem(const TopkDesc &D, uint64_t row) {
+  SortElem x;
+  x.row = row;
+  x.ranks = 0;
+  x.pad = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    if (q < D.n_keys) {
+      const bool isnull = topk_key_is_null(D, q, row);
+      x.k[q] = isnull ? 0ull : sort_key(D.key_col[q].ptr + row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0);
+      x.ranks |= static_cast<uint32_t>(isnull ? D.null_rank[q] : 1u) << (8 * q);
+    } else {
+      x.k[q] = 0;
+    }
+  }
+  return x;
+}
+__device__ __forceinline__ SortElem topk_pad_elem() {       // sorts behind every row
+  SortElem x;
+  x.row = ~0ull;
+  x.ranks = 0xffffffffu;
+  x.pad = 0;
+  for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
+  return x;
+}
+
 __global__ void k_topk_primary_dev(const __grid_constant__ TopkDesc D, uint64_t *pk, TopkState *S, uint64_t limit) {
   const uint64_t n = topk_rows(D);
   if (blockIdx.x == 0) {
@@ -253,7 +304,7 @@ __global__ void k_topk_primary_dev(const __grid_constant__ TopkDesc D, uint64_t 
   }
   for (uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; row < n;
        row += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    pk[row] = sort_key(D.key_col[0].ptr + row * D.key_col[0].width, D.key_ltype[0], D.desc[0] != 0);
+    pk[row] = topk_primary_key(D, row);
 }
 
 __global__ void __launch_bounds__(256) k_topk_hist_dev(const __grid_constant__ TopkDesc D, const uint64_t *pk, TopkState *S, int shift) {
@@ -328,16 +379,7 @@ __global__ void __launch_bounds__(1024) k_topk_sort_dev(const __grid_constant__ 
   uint32_t N = 1;
   while (N < m) N <<= 1;
   for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-    SortElem x;
-    if (i < m) {
-      x.row = cand[i];
-      for (uint32_t q = 0; q < 4; ++q)
-        x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + x.row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
-    } else {
-      x.row = ~0ull;
-      for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
-    }
-    e[i] = x;
+    e[i] = i < m ? topk_elem(D, cand[i]) : topk_pad_elem();
   }
   __syncthreads();
   for (uint32_t size = 2; size <= N; size <<= 1) {
@@ -401,10 +443,6 @@ __global__ void __launch_bounds__(256) k_topk_coop(const __grid_constant__ TopkD
   unsigned int generation = 0;
   const uint64_t n = topk_rows(D);
   const uint64_t k = min(static_cast<uint64_t>(limit), n);
-  const char *kp = D.key_col[0].ptr;
-  const uint32_t kw = D.key_col[0].width;
-  const uint8_t klt = D.key_ltype[0];
-  const bool kdesc = D.desc[0] != 0;
   const uint64_t first = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
   const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   // (S was zeroed by the host-side memset queued before the launch; remaining starts at k)
@@ -416,7 +454,7 @@ __global__ void __launch_bounds__(256) k_topk_coop(const __grid_constant__ TopkD
     const uint64_t prefix = *reinterpret_cast<volatile unsigned long long *>(&S->prefix);
     const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
     for (uint64_t row = first; row < n; row += step) {
-      const uint64_t key = sort_key(kp + row * kw, klt, kdesc);
+      const uint64_t key = topk_primary_key(D, row);
       if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
     }
     __syncthreads();
@@ -449,7 +487,7 @@ __global__ void __launch_bounds__(256) k_topk_coop(const __grid_constant__ TopkD
   }
   const uint64_t threshold = *reinterpret_cast<volatile unsigned long long *>(&S->prefix);
   for (uint64_t row = first; row < n; row += step) {
-    if (sort_key(kp + row * kw, klt, kdesc) <= threshold) {
+    if (topk_primary_key(D, row) <= threshold) {
       const unsigned long long pos = atomicAdd(&S->n_cand, 1ull);
       if (pos < static_cast<unsigned long long>(kTopkMaxCand)) cand[pos] = row;
     }
@@ -466,16 +504,7 @@ __global__ void __launch_bounds__(256) k_topk_coop(const __grid_constant__ TopkD
   uint32_t N = 1;
   while (N < m) N <<= 1;
   for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-    SortElem x;
-    if (i < m) {
-      x.row = __ldcg(&cand[i]);
-      for (uint32_t q = 0; q < 4; ++q)
-        x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + x.row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
-    } else {
-      x.row = ~0ull;
-      for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
-    }
-    e[i] = x;
+    e[i] = i < m ? topk_elem(D, __ldcg(&cand[i])) : topk_pad_elem();
   }
   __syncthreads();
   for (uint32_t size = 2; size <= N; size <<= 1) {
@@ -520,10 +549,6 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
   __shared__ int s_done;
   const uint64_t n = D.d_n_rows ? min(D.n_rows, static_cast<uint64_t>(*D.d_n_rows)) : D.n_rows;
   const uint64_t k = min(static_cast<uint64_t>(limit), n);
-  const char *kp = D.key_col[0].ptr;
-  const uint32_t kw = D.key_col[0].width;
-  const uint8_t klt = D.key_ltype[0];
-  const bool kdesc = D.desc[0] != 0;
   if (threadIdx.x == 0) { s_prefix = ~0ull; s_remaining = k; s_done = 0; s_m = 0; }
   __syncthreads();
   // every row is a candidate when they all fit the sorting buffer (Q1's 4 groups, a gathered top-10 per GPU):
@@ -535,7 +560,7 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
     const uint64_t hi_mask = shift == 56 ? 0ull : ~0ull << (shift + 8);
     const uint64_t prefix = s_prefix;
     for (uint64_t row = threadIdx.x; row < n; row += blockDim.x) {
-      const uint64_t key = sort_key(kp + row * kw, klt, kdesc);
+      const uint64_t key = topk_primary_key(D, row);
       if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
     }
     __syncthreads();
@@ -561,15 +586,9 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
   }
   const uint64_t threshold = s_prefix;
   for (uint64_t row = threadIdx.x; row < n; row += blockDim.x) {
-    if (sort_key(kp + row * kw, klt, kdesc) <= threshold) {
+    if (topk_primary_key(D, row) <= threshold) {
       const unsigned int pos = atomicAdd(&s_m, 1u);
-      if (pos < static_cast<unsigned int>(kTopkMaxCand)) {
-        SortElem x;
-        x.row = row;
-        for (uint32_t q = 0; q < 4; ++q)
-          x.k[q] = q < D.n_keys ? sort_key(D.key_col[q].ptr + row * D.key_col[q].width, D.key_ltype[q], D.desc[q] != 0) : 0;
-        e[pos] = x;
-      }
+      if (pos < static_cast<unsigned int>(kTopkMaxCand)) e[pos] = topk_elem(D, row);
     }
   }
   __syncthreads();
@@ -580,12 +599,7 @@ __global__ void __launch_bounds__(1024) k_topk_single(const __grid_constant__ To
   }
   uint32_t N = 1;
   while (N < m) N <<= 1;
-  for (uint32_t i = m + threadIdx.x; i < N; i += blockDim.x) {
-    SortElem x;
-    x.row = ~0ull;
-    for (int q = 0; q < 4; ++q) x.k[q] = ~0ull;
-    e[i] = x;
-  }
+  for (uint32_t i = m + threadIdx.x; i < N; i += blockDim.x) e[i] = topk_pad_elem();
   __syncthreads();
   for (uint32_t size = 2; size <= N; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -887,7 +901,6 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
   D.d_n_rows = device_count ? input->d_rows : nullptr;
   for (uint32_t q = 0; q < n_keys; ++q) {
     if (keys[q].attr >= input->attrs.size()) { set_error(QSGPU_ERR_INVALID, "sort attribute out of range"); return QSGPU_ERR_INVALID; }
-    if (keys[q].attr < 64 && ((input->nullable_mask >> keys[q].attr) & 1ull)) { set_error(QSGPU_ERR_UNSUPPORTED, "sorting on a NULL-able attribute (NULLS FIRST / LAST) is not lowered"); return QSGPU_ERR_UNSUPPORTED; }
     const uint8_t lt = vtype_of(input->attrs[keys[q].attr].type);
     uint8_t klt = lt;
     if (lt == 0xff) {
@@ -898,7 +911,16 @@ int qsgpu_topk(qsgpu_relation_t input, uint32_t n_keys, const qs_sort_key *keys,
     D.key_col[q].ptr = input->cols[keys[q].attr];
     D.key_col[q].width = input->attrs[keys[q].attr].width;
     D.key_ltype[q] = klt;
-    D.desc[q] = keys[q].descending ? 1 : 0;
+    D.desc[q] = (keys[q].descending & 1u) ? 1 : 0;
+    // NULL ordering (qs_sort_key.descending bits 1-2): as written, else NULLs first iff descending (ParseOrderBy.hpp:53-66)
+    const uint32_t null_order = (keys[q].descending >> 1) & 3u;
+    if (null_order == 3u) { set_error(QSGPU_ERR_INVALID, "qs_sort_key: NULLS FIRST and NULLS LAST both set"); return QSGPU_ERR_INVALID; }
+    const bool nulls_first = null_order == 1u ? true : null_order == 2u ? false : D.desc[q] != 0;
+    D.null_rank[q] = nulls_first ? 0 : 2;
+    if (keys[q].attr < 64 && ((input->nullable_mask >> keys[q].attr) & 1ull)) {
+      D.key_null_bit[q] = 1ull << keys[q].attr;
+      D.nulls = input->d_nulls;
+    }
   }
   qsgpu_relation *rel = nullptr;
   st = qsgpu_relation_create(input->dev, static_cast<uint32_t>(input->attrs.size()), input->attrs.data(),

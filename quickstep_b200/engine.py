@@ -521,10 +521,14 @@ class JoinTable:
 
 
 def topk(rel: Relation, keys, limit) -> Relation:
-    """keys: [(attr, descending)]."""
+    """keys: [(attr, descending)] or [(attr, descending, nulls_first)] (nulls_first None = the reference's default:
+    NULLs first iff descending)."""
     ks = (A.qs_sort_key * max(1, len(keys)))()
-    for i, (a, d) in enumerate(keys):
-        ks[i].attr, ks[i].descending = a, 1 if d else 0
+    for i, key in enumerate(keys):
+        a, d = key[0], key[1]
+        nf = key[2] if len(key) > 2 else None
+        ks[i].attr = a
+        ks[i].descending = (1 if d else 0) | (0 if nf is None else 2 if nf else 4)
     out = C.c_void_p()
     A.check(A.load().qsgpu_topk(rel.h, len(keys), ks, limit, C.byref(out)))
     return Relation(out, rel.schema, rel.names, rel.dev)
