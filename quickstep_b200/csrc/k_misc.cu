@@ -190,14 +190,17 @@ __device__ __forceinline__ uint64_t sort_key(const char *p, uint8_t ltype, bool 
     return desc ? ~k : k;
   }
   switch (ltype) {
+    // (-0.0 and +0.0 compare equal in the reference's `<`: one key for both, or later sort keys would never decide)
     case V_F32: {
       const double d = static_cast<double>(*reinterpret_cast<const float *>(p));
-      const uint64_t b = d2u(d);
+      uint64_t b = d2u(d);
+      if ((b << 1) == 0ull) b = 0ull;
       k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
       break;
     }
     case V_F64: {
-      const uint64_t b = *reinterpret_cast<const uint64_t *>(p);
+      uint64_t b = *reinterpret_cast<const uint64_t *>(p);
+      if ((b << 1) == 0ull) b = 0ull;
       k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
       break;
     }
