@@ -52,6 +52,25 @@ def workload_name(args, n):
     return f"TPC-H Q1 at {sf} (lineitem {n:,} rows, 42 B/row, 4 groups x 6 states)"
 
 
+def n_host_workers(args, world):
+    """Worker threads per rank: they poll for work while a query is in flight, so never more than this rank's share of
+    the host cores (8 ranks x 4 workers would oversubscribe a 32-core host)."""
+    return max(1, min(args.workers, (os.cpu_count() or 4) // world - 2))
+
+
+def bench_config(args, n, world, rows_rank0, n_workers):
+    """`config` of the JSON line.  Both arms print the SAME object (the reference arm times the CPU path on this very
+    workload): it names the job, not the implementation that ran it."""
+    return {"workload": workload_name(args, n), "total_rows": n, "rows_per_gpu": rows_rank0,
+            "partitioning": f"lineitem block-partitioned on l_orderkey boundaries over {world} GPU(s); orders / customer in shares "
+                            "(orders co-partitioned with lineitem: Q3 joins partition-wise; q3_broadcast_join all-gathers the build side instead)",
+            "path": "libqshost.so (C++ RelationalOperator / WorkOrder layer, Foreman + Workers) -> libqsgpu.so C ABI; "
+                    "cross-GPU merges inside the C ABI (NCCL)",
+            "host_workers_per_rank": n_workers,
+            "l2": f"inputs ({rows_rank0 * 42 / 1e9:.1f} GB per GPU) larger than L2 (126 MB); no flush needed",
+            "timing": "CUDA events on the library stream around K whole queries (kernels + collectives + result read); max over ranks"}
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -183,8 +202,10 @@ def run_reference(args):
     host = S.generate_host(shape, range(shape["n_chunks"]), SEED, dev)       # data generation only (torch); not timed
     tables = S.host_tables(host)
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    if n > 100_000_000:            # ~1.3 s per step at SF100: keep the whole run within a few minutes
-        steps, warmup = min(steps, 20), min(warmup, 3)
+    if n > 100_000_000:            # ~1.1-1.3 s per step at SF100: keep the whole run within a few minutes
+        steps, warmup = min(steps, 60), min(warmup, 10)
+    world = max(1, args.gpus)
+    (_, _), (_, l_hi0), (_, _) = S.chunk_rows(shape, S.rank_chunks(shape, world, 0)[-1])     # rank 0's lineitem partition
     for _ in range(warmup):
         OT.q1(tables["lineitem"])
     t0 = time.perf_counter()
@@ -195,7 +216,9 @@ def run_reference(args):
         "impl": "reference", "metric": "tpch_q1_sf100_query_ms" if n == SF_ROWS[100] else "tpch_q1_query_ms", "value": ms, "unit": "ms",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, n), "total_rows": n},
+        "config": bench_config(args, n, world, l_hi0, n_host_workers(args, world)),      # the job our arm ran
+        "impl_path": "CPU: oracle/libqsoracle.so (C restatement of the reference's aggregation path, pinned to the unmodified "
+                     "engine's answers), all host threads, over the WHOLE relation; no GPU, no partitioning",
         "rows_per_s": n / (ms * 1e-3),
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
                          "sample": f"oracle Q1 over the whole relation ({n:,} rows), {cores} threads, 63k-row work orders; "
@@ -292,9 +315,7 @@ def main():
     my_rows = len(host["lineitem"][0])
     log(f"generated: {n:,} lineitem rows in the database, {my_rows:,} on this rank")
 
-    # Worker threads per rank: they poll for work while a query is in flight, so never more than this rank's share of
-    # the host cores (8 ranks x 4 workers would oversubscribe a 32-core host)
-    n_workers = max(1, min(args.workers, (os.cpu_count() or 4) // world - 2))
+    n_workers = n_host_workers(args, world)
     db = H.Database(local, num_workers=n_workers)
     if comm is not None:
         db.set_comm(comm.h)
@@ -565,14 +586,7 @@ def main():
             "metric": "tpch_q1_sf100_query_ms" if sf100 else "tpch_q1_query_ms", "value": t1[0], "unit": "ms", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t1[1], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, n), "total_rows": n, "rows_per_gpu": my_rows,
-                       "partitioning": f"lineitem block-partitioned on l_orderkey boundaries over {world} GPU(s); orders / customer in shares "
-                                       "(orders co-partitioned with lineitem: Q3 joins partition-wise; q3_broadcast_join all-gathers the build side instead)",
-                       "path": "libqshost.so (C++ RelationalOperator / WorkOrder layer, Foreman + Workers) -> libqsgpu.so C ABI; "
-                               "cross-GPU merges inside the C ABI (NCCL)",
-                       "host_workers_per_rank": n_workers,
-                       "l2": f"inputs ({my_rows * T.Q1_BYTES_PER_ROW / 1e9:.1f} GB per GPU) larger than L2 (126 MB); no flush needed",
-                       "timing": "CUDA events on the library stream around K whole queries (kernels + collectives + result read); max over ranks"},
+            "config": bench_config(args, n, world, my_rows, n_workers),
             "rows_per_s": n / (t1[0] * 1e-3),
             "query_ms": {"q1": t1[0], "q6": t6[0], "q3": t3[0], **({"q3_broadcast_join": t3b[0]} if t3b else {})},
             "query_wall_ms": {"q1": t1[1], "q6": t6[1], "q3": t3[1]},
