@@ -1,0 +1,369 @@
+// TEST INFRASTRUCTURE: generates tests/golden/reference_expressions.json with the UNMODIFIED reference's own classes.
+//
+// Linked against the static libraries of oracle/build_ref.sh's build tree (tests/golden/make_expr_golden.sh is the
+// recipe).  For a fixed relation of random tuples it
+//   * builds predicates and scalars out of the reference's real expression classes (ScalarAttribute, ScalarLiteral,
+//     ScalarUnaryExpression, ScalarBinaryExpression, ScalarSharedExpression, ComparisonPredicate, NegationPredicate,
+//     ConjunctionPredicate, DisjunctionPredicate),
+//   * evaluates them with the reference's own vectorised code paths -- Predicate::getAllMatches
+//     (expressions/predicate/Predicate.hpp:167) and Scalar::getAllValues (expressions/scalar/Scalar.hpp:215) -- over a
+//     ColumnVectorsValueAccessor holding the tuples,
+//   * lowers each through its getProto() with the in-tree binding's LowerPredicate / LowerScalar
+//     (quickstep_b200/host/intree/ProtoLowering.hpp) into the C ABI's qs_node array,
+// and writes tuples, node arrays and the reference's answers.  tests/test_reference_expressions.py evaluates the SAME
+// node arrays with the oracle (CPU) and with the CUDA path (-m gpu) and demands the reference's bits.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "catalog/CatalogAttribute.hpp"
+#include "catalog/CatalogRelation.hpp"
+#include "expressions/predicate/ComparisonPredicate.hpp"
+#include "expressions/predicate/ConjunctionPredicate.hpp"
+#include "expressions/predicate/DisjunctionPredicate.hpp"
+#include "expressions/predicate/NegationPredicate.hpp"
+#include "expressions/predicate/Predicate.hpp"
+#include "expressions/scalar/Scalar.hpp"
+#include "expressions/scalar/ScalarAttribute.hpp"
+#include "expressions/scalar/ScalarBinaryExpression.hpp"
+#include "expressions/scalar/ScalarLiteral.hpp"
+#include "expressions/scalar/ScalarSharedExpression.hpp"
+#include "expressions/scalar/ScalarUnaryExpression.hpp"
+#include "storage/TupleIdSequence.hpp"
+#include "types/DatetimeLit.hpp"
+#include "types/Type.hpp"
+#include "types/TypeFactory.hpp"
+#include "types/TypeID.hpp"
+#include "types/TypedValue.hpp"
+#include "types/containers/ColumnVector.hpp"
+#include "types/containers/ColumnVectorsValueAccessor.hpp"
+#include "types/operations/binary_operations/BinaryOperationFactory.hpp"
+#include "types/operations/binary_operations/BinaryOperationID.hpp"
+#include "types/operations/comparisons/ComparisonFactory.hpp"
+#include "types/operations/comparisons/ComparisonID.hpp"
+#include "types/operations/unary_operations/NumericCastOperation.hpp"
+#include "types/operations/unary_operations/UnaryOperationFactory.hpp"
+#include "types/operations/unary_operations/UnaryOperationID.hpp"
+#include "utility/ColumnVectorCache.hpp"
+
+#include "ProtoLowering.hpp"
+
+using namespace quickstep;  // NOLINT
+
+namespace {
+
+constexpr int kRows = 512;
+constexpr int kRelationId = 7;
+enum Attr { A_I, A_I2, A_L, A_F, A_D, A_DISC, A_TAX, A_DT, A_C1, A_C4, A_C10, kNumAttrs };
+
+std::uint64_t g_state = 0x9E3779B97F4A7C15ull;
+std::uint64_t Next() {      // splitmix64
+  std::uint64_t z = (g_state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+std::string Hex(const void *p, std::size_t n) {
+  static const char *d = "0123456789abcdef";
+  std::string s;
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  for (std::size_t i = 0; i < n; ++i) {
+    s.push_back(d[b[i] >> 4]);
+    s.push_back(d[b[i] & 15]);
+  }
+  return s;
+}
+
+struct Column {
+  const Type *type;
+  std::string name;
+  std::vector<char> bytes;     // kRows * width, canonical (zero padding)
+};
+
+std::vector<Column> g_cols;
+CatalogRelation *g_rel = nullptr;
+
+void PutChar(std::vector<char> *out, std::size_t width, const char *s) {
+  std::vector<char> v(width, '\0');
+  std::memcpy(v.data(), s, std::min(width, std::strlen(s)));
+  out->insert(out->end(), v.begin(), v.end());
+}
+
+template <typename T>
+void Put(std::vector<char> *out, T v) {
+  const char *p = reinterpret_cast<const char *>(&v);
+  out->insert(out->end(), p, p + sizeof(T));
+}
+
+void MakeRelation() {
+  g_rel = new CatalogRelation(nullptr, "t", kRelationId);
+  const char *names[kNumAttrs] = {"i", "i2", "l", "f", "d", "disc", "tax", "dt", "c1", "c4", "c10"};
+  const Type *types[kNumAttrs] = {
+      &TypeFactory::GetType(kInt, false),    &TypeFactory::GetType(kInt, false),    &TypeFactory::GetType(kLong, false),
+      &TypeFactory::GetType(kFloat, false),  &TypeFactory::GetType(kDouble, false), &TypeFactory::GetType(kDouble, false),
+      &TypeFactory::GetType(kDouble, false), &TypeFactory::GetType(kDate, false),   &TypeFactory::GetType(kChar, 1, false),
+      &TypeFactory::GetType(kChar, 4, false), &TypeFactory::GetType(kChar, 10, false)};
+  g_cols.resize(kNumAttrs);
+  for (int a = 0; a < kNumAttrs; ++a) {
+    g_rel->addAttribute(new CatalogAttribute(g_rel, names[a], *types[a]));
+    g_cols[a].type = types[a];
+    g_cols[a].name = names[a];
+  }
+  const char *flags[3] = {"R", "A", "N"};
+  const char *modes[7] = {"AIR", "MAIL", "SHIP", "RAIL", "FOB", "TRUC", "REG"};
+  const char *segs[5] = {"BUILDING", "AUTOMOBILE", "MACHINERY", "HOUSEHOLD", "FURNITURE"};
+  const double special[8] = {0.0, -0.0, std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::infinity(),
+                             -std::numeric_limits<double>::infinity(), 1e-310 /* subnormal */, 1e308, -1.5};
+  for (int r = 0; r < kRows; ++r) {
+    Put<std::int32_t>(&g_cols[A_I].bytes, static_cast<std::int32_t>(Next() % 2001) - 1000);
+    std::int32_t i2 = static_cast<std::int32_t>(Next() % 97) - 48;
+    Put<std::int32_t>(&g_cols[A_I2].bytes, i2 == 0 ? 7 : i2);                            // divisors: never zero
+    Put<std::int64_t>(&g_cols[A_L].bytes, static_cast<std::int64_t>(Next() % 20000000001ull) - 10000000000ll);
+    Put<float>(&g_cols[A_F].bytes, static_cast<float>(static_cast<std::int64_t>(Next() % 200001) - 100000) / 64.0f);
+    double d = 900.0 + static_cast<double>(Next() % 10409500) / 100.0;                   // l_extendedprice-like
+    if (r % 16 == 5) d = special[(r / 16) % 8];
+    Put<double>(&g_cols[A_D].bytes, d);
+    Put<double>(&g_cols[A_DISC].bytes, static_cast<double>(Next() % 11) / 100.0);
+    Put<double>(&g_cols[A_TAX].bytes, static_cast<double>(Next() % 9) / 100.0);
+    DateLit dt;
+    std::memset(&dt, 0, sizeof(dt));
+    dt.year = 1992 + static_cast<std::int32_t>(Next() % 7);
+    dt.month = static_cast<std::uint8_t>(1 + Next() % 12);
+    dt.day = static_cast<std::uint8_t>(1 + Next() % 28);
+    Put<DateLit>(&g_cols[A_DT].bytes, dt);
+    PutChar(&g_cols[A_C1].bytes, 1, flags[Next() % 3]);
+    PutChar(&g_cols[A_C4].bytes, 4, modes[Next() % 7]);
+    PutChar(&g_cols[A_C10].bytes, 10, segs[Next() % 5]);
+  }
+}
+
+ColumnVectorsValueAccessor *MakeAccessor() {
+  ColumnVectorsValueAccessor *acc = new ColumnVectorsValueAccessor();
+  for (const Column &c : g_cols) {
+    NativeColumnVector *cv = new NativeColumnVector(*c.type, kRows);
+    const std::size_t w = c.type->maximumByteLength();
+    for (int r = 0; r < kRows; ++r) cv->appendUntypedValue(c.bytes.data() + r * w);
+    acc->addColumn(cv);
+  }
+  return acc;
+}
+
+// ---- small constructors over the reference's classes
+Scalar *Attr(int a) { return new ScalarAttribute(*g_rel->getAttributeById(a)); }
+Scalar *LitI(int v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kInt, false)); }
+Scalar *LitL(std::int64_t v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kLong, false)); }
+Scalar *LitF(float v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kFloat, false)); }
+Scalar *LitD(double v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kDouble, false)); }
+Scalar *LitDate(int y, int m, int d) {
+  DateLit v;
+  std::memset(&v, 0, sizeof(v));
+  v.year = y;
+  v.month = static_cast<std::uint8_t>(m);
+  v.day = static_cast<std::uint8_t>(d);
+  return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kDate, false));
+}
+Scalar *LitC(const char *s) {      // a CHAR(strlen) literal, as the parser types string literals
+  const std::size_t n = std::strlen(s);
+  TypedValue v(kChar, s, n);
+  return new ScalarLiteral(v, TypeFactory::GetType(kChar, n, false));
+}
+Scalar *Bin(BinaryOperationID op, Scalar *l, Scalar *r) {
+  return new ScalarBinaryExpression(BinaryOperationFactory::GetBinaryOperation(op), l, r);
+}
+Scalar *Neg(Scalar *x) { return new ScalarUnaryExpression(UnaryOperationFactory::GetUnaryOperation(UnaryOperationID::kNegate), x); }
+Scalar *Cast(TypeID to, Scalar *x) {
+  return new ScalarUnaryExpression(NumericCastOperation::Instance(TypeFactory::GetType(to, false)), x);
+}
+Scalar *Shared(int id, Scalar *x) { return new ScalarSharedExpression(id, x); }
+Predicate *Cmp(ComparisonID op, Scalar *l, Scalar *r) {
+  return new ComparisonPredicate(ComparisonFactory::GetComparison(op), l, r);
+}
+Predicate *And(std::vector<Predicate *> ps) {
+  ConjunctionPredicate *c = new ConjunctionPredicate();
+  for (Predicate *p : ps) c->addPredicate(p);
+  return c;
+}
+Predicate *Or(std::vector<Predicate *> ps) {
+  DisjunctionPredicate *c = new DisjunctionPredicate();
+  for (Predicate *p : ps) c->addPredicate(p);
+  return c;
+}
+Predicate *Not(Predicate *p) { return new NegationPredicate(p); }
+
+constexpr BinaryOperationID ADD = BinaryOperationID::kAdd, SUB = BinaryOperationID::kSubtract, MUL = BinaryOperationID::kMultiply,
+                            DIV = BinaryOperationID::kDivide, MOD = BinaryOperationID::kModulo;
+constexpr ComparisonID EQ = ComparisonID::kEqual, NE = ComparisonID::kNotEqual, LT = ComparisonID::kLess,
+                       LE = ComparisonID::kLessOrEqual, GT = ComparisonID::kGreater, GE = ComparisonID::kGreaterOrEqual;
+
+bool g_first_case = true;
+
+void EmitNodes(FILE *out, const gpu::ExprBuilder &b, int root) {
+  const qs_expr_set es = b.view();
+  std::fprintf(out, "\"root\": %d, \"pool\": \"%s\", \"nodes\": [", root, Hex(es.str_pool, es.str_pool_bytes).c_str());
+  for (std::uint32_t i = 0; i < es.n_nodes; ++i) {
+    const qs_node &n = es.nodes[i];
+    std::fprintf(out, "%s[%u, %u, %u, %u, %d, %d, \"%s\"]", i ? ", " : "", n.kind, n.op, n.type, n.width, n.a, n.b,
+                 Hex(&n.lit, sizeof(n.lit)).c_str());
+  }
+  std::fprintf(out, "]");
+}
+
+gpu::AttributeTypes Types() {
+  gpu::AttributeTypes t;
+  std::vector<qs_attr> attrs;
+  for (const Column &c : g_cols) {
+    qs_attr a{};
+    a.type = static_cast<std::uint16_t>(c.type->getTypeID() == kDate ? QS_DATE : static_cast<int>(c.type->getTypeID()));
+    a.width = static_cast<std::uint16_t>(c.type->maximumByteLength());
+    attrs.push_back(a);
+  }
+  t.relations.emplace_back(kRelationId, attrs);
+  return t;
+}
+
+void PredicateCase(FILE *out, const char *name, const char *sql, Predicate *p) {
+  std::unique_ptr<Predicate> owner(p);
+  std::unique_ptr<ColumnVectorsValueAccessor> acc(MakeAccessor());
+  std::unique_ptr<TupleIdSequence> matches(p->getAllMatches(acc.get(), nullptr, nullptr, nullptr));
+  std::string bits;
+  for (int r = 0; r < kRows; ++r) bits.push_back(matches->get(r) ? '1' : '0');
+  gpu::ExprBuilder b;
+  const int root = gpu::LowerPredicate(p->getProto(), Types(), &b);
+  std::fprintf(out, "%s\n  {\"name\": \"%s\", \"sql\": \"%s\", \"kind\": \"predicate\", ", g_first_case ? "" : ",", name, sql);
+  EmitNodes(out, b, root);
+  std::fprintf(out, ", \"matches\": \"%s\", \"n_matches\": %zu}", bits.c_str(), static_cast<std::size_t>(matches->numTuples()));
+  g_first_case = false;
+}
+
+void ScalarCase(FILE *out, const char *name, const char *sql, Scalar *s) {
+  std::unique_ptr<Scalar> owner(s);
+  std::unique_ptr<ColumnVectorsValueAccessor> acc(MakeAccessor());
+  ColumnVectorCache cache;
+  ColumnVectorPtr values = s->getAllValues(acc.get(), nullptr, &cache);
+  const Type &t = s->getType();
+  const std::size_t w = t.maximumByteLength();
+  std::string bytes;
+  CHECK(values->isNative());
+  const NativeColumnVector &ncv = static_cast<const NativeColumnVector &>(*values);
+  CHECK_EQ(static_cast<std::size_t>(kRows), ncv.size());
+  for (int r = 0; r < kRows; ++r) bytes += Hex(ncv.getUntypedValue(r), w);
+  gpu::ExprBuilder b;
+  const int root = gpu::LowerScalar(s->getProto(), Types(), &b);
+  std::fprintf(out, "%s\n  {\"name\": \"%s\", \"sql\": \"%s\", \"kind\": \"scalar\", ", g_first_case ? "" : ",", name, sql);
+  EmitNodes(out, b, root);
+  std::fprintf(out, ", \"result_type\": %d, \"result_width\": %zu, \"values\": \"%s\"}",
+               t.getTypeID() == kDate ? QS_DATE : static_cast<int>(t.getTypeID()), w, bytes.c_str());
+  g_first_case = false;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  FILE *out = argc > 1 ? std::fopen(argv[1], "w") : stdout;
+  MakeRelation();
+  std::fprintf(out, "{\"generator\": \"tests/golden/make_expr_golden.cpp against the unmodified reference (fee4c630)\",\n");
+  std::fprintf(out, " \"relation_id\": %d, \"n_rows\": %d,\n \"columns\": [", kRelationId, kRows);
+  for (int a = 0; a < kNumAttrs; ++a) {
+    const Column &c = g_cols[a];
+    std::fprintf(out, "%s\n  {\"name\": \"%s\", \"type\": %d, \"width\": %zu, \"data\": \"%s\"}", a ? "," : "", c.name.c_str(),
+                 c.type->getTypeID() == kDate ? QS_DATE : static_cast<int>(c.type->getTypeID()), c.type->maximumByteLength(),
+                 Hex(c.bytes.data(), c.bytes.size()).c_str());
+  }
+  std::fprintf(out, "],\n \"cases\": [");
+
+  // ------------------------------------------------------------------ scalars (E1: Scalar::getAllValues)
+  ScalarCase(out, "int_plus_literal", "i + 1", Bin(ADD, Attr(A_I), LitI(1)));
+  ScalarCase(out, "int_times_long", "i * l", Bin(MUL, Attr(A_I), Attr(A_L)));
+  ScalarCase(out, "long_minus_int", "l - i", Bin(SUB, Attr(A_L), Attr(A_I)));
+  ScalarCase(out, "float_times_literal", "f * 2.5", Bin(MUL, Attr(A_F), LitF(2.5f)));
+  ScalarCase(out, "float_plus_double", "f + d", Bin(ADD, Attr(A_F), Attr(A_D)));
+  ScalarCase(out, "int_plus_float", "i + f", Bin(ADD, Attr(A_I), Attr(A_F)));
+  ScalarCase(out, "long_times_double", "l * disc", Bin(MUL, Attr(A_L), Attr(A_DISC)));
+  ScalarCase(out, "q1_disc_price", "d * (1 - disc)", Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC))));
+  ScalarCase(out, "q1_charge", "d * (1 - disc) * (1 + tax)",
+             Bin(MUL, Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC))), Bin(ADD, LitI(1), Attr(A_TAX))));
+  ScalarCase(out, "q1_charge_shared", "SHARED#3(d * (1 - disc)) * (1 + tax)",
+             Bin(MUL, Shared(3, Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC)))), Bin(ADD, LitI(1), Attr(A_TAX))));
+  ScalarCase(out, "shared_nested_right", "(i + 1) * (SHARED#7(i2 + 2) + 3)",
+             Bin(MUL, Bin(ADD, Attr(A_I), LitI(1)), Bin(ADD, Shared(7, Bin(ADD, Attr(A_I2), LitI(2))), LitI(3))));
+  ScalarCase(out, "q6_revenue", "d * disc", Bin(MUL, Attr(A_D), Attr(A_DISC)));
+  ScalarCase(out, "negate_double", "-d", Neg(Attr(A_D)));
+  ScalarCase(out, "negate_int", "-i", Neg(Attr(A_I)));
+  ScalarCase(out, "negate_long_expr", "-(l + i)", Neg(Bin(ADD, Attr(A_L), Attr(A_I))));
+  ScalarCase(out, "int_divide", "i / i2", Bin(DIV, Attr(A_I), Attr(A_I2)));
+  ScalarCase(out, "long_divide_int", "l / i2", Bin(DIV, Attr(A_L), Attr(A_I2)));
+  ScalarCase(out, "double_divide", "d / 7.0", Bin(DIV, Attr(A_D), LitD(7.0)));
+  ScalarCase(out, "double_divide_by_column", "d / disc", Bin(DIV, Attr(A_D), Attr(A_DISC)));       // x / 0.0 -> inf / nan
+  ScalarCase(out, "int_modulo", "i % i2", Bin(MOD, Attr(A_I), Attr(A_I2)));
+  ScalarCase(out, "long_modulo", "l % 1000", Bin(MOD, Attr(A_L), LitL(1000)));
+  ScalarCase(out, "cast_int_to_double", "CAST(i AS DOUBLE) * disc", Bin(MUL, Cast(kDouble, Attr(A_I)), Attr(A_DISC)));
+  ScalarCase(out, "cast_long_to_float", "CAST(l AS FLOAT)", Cast(kFloat, Attr(A_L)));
+  ScalarCase(out, "cast_float_to_int", "CAST(f AS INT)", Cast(kInt, Attr(A_F)));
+  ScalarCase(out, "cast_int_to_long_times_long", "CAST(i AS LONG) * l", Bin(MUL, Cast(kLong, Attr(A_I)), Attr(A_L)));
+  ScalarCase(out, "nested_mixed", "i + l * 2 - 3", Bin(SUB, Bin(ADD, Attr(A_I), Bin(MUL, Attr(A_L), LitI(2))), LitI(3)));
+  ScalarCase(out, "literal_only_arith", "i + (2 + 3)", Bin(ADD, Attr(A_I), Bin(ADD, LitI(2), LitI(3))));
+  ScalarCase(out, "double_sum_three", "d + disc + tax", Bin(ADD, Bin(ADD, Attr(A_D), Attr(A_DISC)), Attr(A_TAX)));
+  ScalarCase(out, "bare_attribute_char", "c4", Attr(A_C4));
+  ScalarCase(out, "bare_attribute_date", "dt", Attr(A_DT));
+
+  // ------------------------------------------------------------------ predicates (P1 / P2: getAllMatches)
+  PredicateCase(out, "int_lt", "i < 100", Cmp(LT, Attr(A_I), LitI(100)));
+  PredicateCase(out, "int_ge_negative", "i >= -250", Cmp(GE, Attr(A_I), LitI(-250)));
+  PredicateCase(out, "long_eq_never", "l = 12345", Cmp(EQ, Attr(A_L), LitL(12345)));
+  PredicateCase(out, "long_gt_int_literal", "l > 0", Cmp(GT, Attr(A_L), LitI(0)));
+  PredicateCase(out, "double_le", "disc <= 0.07", Cmp(LE, Attr(A_DISC), LitD(0.07)));
+  PredicateCase(out, "double_eq_exact_step", "disc = 0.05", Cmp(EQ, Attr(A_DISC), LitD(0.05)));
+  PredicateCase(out, "double_ne_special", "d <> 0.0", Cmp(NE, Attr(A_D), LitD(0.0)));             // NaN <> 0 true, -0.0 <> 0 false
+  PredicateCase(out, "double_lt_special", "d < 1000.0", Cmp(LT, Attr(A_D), LitD(1000.0)));          // NaN false, -inf true
+  PredicateCase(out, "double_ge_special", "d >= 0.0", Cmp(GE, Attr(A_D), LitD(0.0)));               // -0.0 true, NaN false
+  PredicateCase(out, "float_gt", "f > 1.5", Cmp(GT, Attr(A_F), LitF(1.5f)));
+  PredicateCase(out, "float_vs_double_literal", "f <= 0.1", Cmp(LE, Attr(A_F), LitD(0.1)));
+  PredicateCase(out, "int_vs_double_literal", "i < 0.5", Cmp(LT, Attr(A_I), LitD(0.5)));
+  PredicateCase(out, "date_le_q1", "dt <= DATE '1998-09-02'", Cmp(LE, Attr(A_DT), LitDate(1998, 9, 2)));
+  PredicateCase(out, "date_range_q6", "dt >= DATE '1994-01-01' AND dt < DATE '1995-01-01'",
+                And({Cmp(GE, Attr(A_DT), LitDate(1994, 1, 1)), Cmp(LT, Attr(A_DT), LitDate(1995, 1, 1))}));
+  PredicateCase(out, "date_eq_month_boundary", "dt = DATE '1995-03-15'", Cmp(EQ, Attr(A_DT), LitDate(1995, 3, 15)));
+  PredicateCase(out, "date_gt_q3", "dt > DATE '1995-03-15'", Cmp(GT, Attr(A_DT), LitDate(1995, 3, 15)));
+  PredicateCase(out, "char1_eq", "c1 = 'R'", Cmp(EQ, Attr(A_C1), LitC("R")));
+  PredicateCase(out, "char1_ne", "c1 <> 'N'", Cmp(NE, Attr(A_C1), LitC("N")));
+  PredicateCase(out, "char4_lt_same_width", "c4 < 'MAIL'", Cmp(LT, Attr(A_C4), LitC("MAIL")));
+  PredicateCase(out, "char4_eq_shorter_literal", "c4 = 'AIR'", Cmp(EQ, Attr(A_C4), LitC("AIR")));
+  PredicateCase(out, "char4_ge_shorter_literal", "c4 >= 'RA'", Cmp(GE, Attr(A_C4), LitC("RA")));
+  PredicateCase(out, "char10_eq_q3", "c10 = 'BUILDING'", Cmp(EQ, Attr(A_C10), LitC("BUILDING")));
+  PredicateCase(out, "char10_eq_full_width", "c10 = 'AUTOMOBILE'", Cmp(EQ, Attr(A_C10), LitC("AUTOMOBILE")));
+  PredicateCase(out, "char10_gt", "c10 > 'HOUSEHOLD'", Cmp(GT, Attr(A_C10), LitC("HOUSEHOLD")));
+  PredicateCase(out, "literal_on_the_left", "5 < i", Cmp(LT, LitI(5), Attr(A_I)));
+  PredicateCase(out, "attr_vs_attr_int_long", "i < l", Cmp(LT, Attr(A_I), Attr(A_L)));
+  PredicateCase(out, "attr_vs_attr_double_float", "d > f", Cmp(GT, Attr(A_D), Attr(A_F)));
+  PredicateCase(out, "attr_vs_attr_int_int", "i = i2", Cmp(EQ, Attr(A_I), Attr(A_I2)));
+  PredicateCase(out, "attr_vs_attr_double", "disc <= tax", Cmp(LE, Attr(A_DISC), Attr(A_TAX)));
+  PredicateCase(out, "expr_vs_expr", "i + 1 < l * 2", Cmp(LT, Bin(ADD, Attr(A_I), LitI(1)), Bin(MUL, Attr(A_L), LitI(2))));
+  PredicateCase(out, "expr_vs_literal", "d * (1 - disc) > 50000.0",
+                Cmp(GT, Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC))), LitD(50000.0)));
+  PredicateCase(out, "q6_where", "dt >= '1994-01-01' AND dt < '1995-01-01' AND disc >= 0.05 AND disc <= 0.07 AND i2 < 24",
+                And({Cmp(GE, Attr(A_DT), LitDate(1994, 1, 1)), Cmp(LT, Attr(A_DT), LitDate(1995, 1, 1)),
+                     Cmp(GE, Attr(A_DISC), LitD(0.05)), Cmp(LE, Attr(A_DISC), LitD(0.07)), Cmp(LT, Attr(A_I2), LitI(24))}));
+  PredicateCase(out, "or_of_three", "i < -900 OR c1 = 'A' OR disc = 0.1",
+                Or({Cmp(LT, Attr(A_I), LitI(-900)), Cmp(EQ, Attr(A_C1), LitC("A")), Cmp(EQ, Attr(A_DISC), LitD(0.1))}));
+  PredicateCase(out, "not_or_and", "NOT (i < 10 OR d > 50000.0) AND c1 <> 'N'",
+                And({Not(Or({Cmp(LT, Attr(A_I), LitI(10)), Cmp(GT, Attr(A_D), LitD(50000.0))})), Cmp(NE, Attr(A_C1), LitC("N"))}));
+  PredicateCase(out, "not_of_nan_comparison", "NOT (d < 1000.0)", Not(Cmp(LT, Attr(A_D), LitD(1000.0))));   // NaN rows: true
+  PredicateCase(out, "and_inside_or", "(c4 = 'MAIL' AND tax < 0.03) OR (c4 = 'SHIP' AND tax > 0.05)",
+                Or({And({Cmp(EQ, Attr(A_C4), LitC("MAIL")), Cmp(LT, Attr(A_TAX), LitD(0.03))}),
+                    And({Cmp(EQ, Attr(A_C4), LitC("SHIP")), Cmp(GT, Attr(A_TAX), LitD(0.05))})}));
+  PredicateCase(out, "nested_not_not", "NOT (NOT (i2 > 0))", Not(Not(Cmp(GT, Attr(A_I2), LitI(0)))));
+  PredicateCase(out, "always_false_conjunction", "i < 0 AND i > 0", And({Cmp(LT, Attr(A_I), LitI(0)), Cmp(GT, Attr(A_I), LitI(0))}));
+  PredicateCase(out, "cast_in_comparison", "CAST(i AS DOUBLE) / 3.0 >= disc * 100.0",
+                Cmp(GE, Bin(DIV, Cast(kDouble, Attr(A_I)), LitD(3.0)), Bin(MUL, Attr(A_DISC), LitD(100.0))));
+
+  std::fprintf(out, "\n ]}\n");
+  if (out != stdout) std::fclose(out);
+  return 0;
+}

@@ -14,8 +14,9 @@ BUILD = os.environ.get("QS_REF_BUILD", "/tmp/qs_ref_build")
 SHIMS = os.path.join(ROOT, "oracle", "ref_shims")
 
 
-@pytest.mark.timeout(600)
-def test_gpu_work_orders_compile_against_reference_headers():
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("source", ["GpuWorkOrders.cpp", "GpuJoinWorkOrders.cpp"])
+def test_gpu_work_orders_compile_against_reference_headers(source):
     if not os.path.isdir(REF):
         pytest.skip("reference tree absent")
     if not os.path.exists(os.path.join(BUILD, "expressions", "Expressions.pb.h")):
@@ -26,6 +27,6 @@ def test_gpu_work_orders_compile_against_reference_headers():
            os.path.join(SHIMS, "googletest", "googletest", "include"), os.path.join(ROOT, "include"),
            os.path.join(ROOT, "quickstep_b200", "host", "intree")]
     cmd = ["g++", "-std=c++17", "-fsyntax-only", "-DNDEBUG", "-Wall", "-Wno-unused-parameter"] + [f"-I{i}" for i in inc] + \
-          [os.path.join(ROOT, "quickstep_b200", "host", "intree", "GpuWorkOrders.cpp")]
+          [os.path.join(ROOT, "quickstep_b200", "host", "intree", source)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-6000:]
