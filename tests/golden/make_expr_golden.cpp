@@ -90,6 +90,16 @@ struct Column {
 std::vector<Column> g_cols;
 CatalogRelation *g_rel = nullptr;
 
+// The same tuples as a second relation `tn` whose attributes i, l, d, dt, c4 are NULL-able: every fifth value or so is
+// NULL (g_nulls: bit a of row r = attribute a is NULL).  g_nullable_mode selects which of the two the constructors and
+// the accessor below refer to.
+constexpr int kNullableRelationId = 8;
+const int kNullableAttrs[] = {A_I, A_L, A_D, A_DT, A_C4};
+CatalogRelation *g_rel_n = nullptr;
+std::vector<const Type *> g_types_n;
+std::vector<std::uint64_t> g_nulls;
+bool g_nullable_mode = false;
+
 void PutChar(std::vector<char> *out, std::size_t width, const char *s) {
   std::vector<char> v(width, '\0');
   std::memcpy(v.data(), s, std::min(width, std::strlen(s)));
@@ -142,21 +152,43 @@ void MakeRelation() {
     PutChar(&g_cols[A_C4].bytes, 4, modes[Next() % 7]);
     PutChar(&g_cols[A_C10].bytes, 10, segs[Next() % 5]);
   }
+  g_rel_n = new CatalogRelation(nullptr, "tn", kNullableRelationId);
+  for (int a = 0; a < kNumAttrs; ++a) {
+    bool nullable = false;
+    for (int na : kNullableAttrs) nullable |= na == a;
+    const Type &t = *types[a];
+    const Type &tn = !nullable ? t
+                     : t.getTypeID() == kChar ? TypeFactory::GetType(kChar, t.maximumByteLength(), true)
+                                              : TypeFactory::GetType(t.getTypeID(), true);
+    g_types_n.push_back(&tn);
+    g_rel_n->addAttribute(new CatalogAttribute(g_rel_n, names[a], tn));
+  }
+  g_nulls.assign(kRows, 0);
+  for (int r = 0; r < kRows; ++r)
+    for (int na : kNullableAttrs)
+      if (Next() % 5 == 0) g_nulls[r] |= 1ull << na;
 }
 
 ColumnVectorsValueAccessor *MakeAccessor() {
   ColumnVectorsValueAccessor *acc = new ColumnVectorsValueAccessor();
-  for (const Column &c : g_cols) {
-    NativeColumnVector *cv = new NativeColumnVector(*c.type, kRows);
+  for (int a = 0; a < kNumAttrs; ++a) {
+    const Column &c = g_cols[a];
+    const Type &type = g_nullable_mode ? *g_types_n[a] : *c.type;
+    NativeColumnVector *cv = new NativeColumnVector(type, kRows);
     const std::size_t w = c.type->maximumByteLength();
-    for (int r = 0; r < kRows; ++r) cv->appendUntypedValue(c.bytes.data() + r * w);
+    for (int r = 0; r < kRows; ++r) {
+      if (g_nullable_mode && (g_nulls[r] >> a & 1))
+        cv->appendNullValue();
+      else
+        cv->appendUntypedValue(c.bytes.data() + r * w);
+    }
     acc->addColumn(cv);
   }
   return acc;
 }
 
 // ---- small constructors over the reference's classes
-Scalar *Attr(int a) { return new ScalarAttribute(*g_rel->getAttributeById(a)); }
+Scalar *Attr(int a) { return new ScalarAttribute(*(g_nullable_mode ? g_rel_n : g_rel)->getAttributeById(a)); }
 Scalar *LitI(int v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kInt, false)); }
 Scalar *LitL(std::int64_t v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kLong, false)); }
 Scalar *LitF(float v) { return new ScalarLiteral(TypedValue(v), TypeFactory::GetType(kFloat, false)); }
@@ -179,7 +211,9 @@ Scalar *Bin(BinaryOperationID op, Scalar *l, Scalar *r) {
 }
 Scalar *Neg(Scalar *x) { return new ScalarUnaryExpression(UnaryOperationFactory::GetUnaryOperation(UnaryOperationID::kNegate), x); }
 Scalar *Cast(TypeID to, Scalar *x) {
-  return new ScalarUnaryExpression(NumericCastOperation::Instance(TypeFactory::GetType(to, false)), x);
+  // the target type is NULL-able exactly when the operand is (NumericCastOperation::canApplyToType)
+  const bool nullable = x->getType().isNullable();
+  return new ScalarUnaryExpression(NumericCastOperation::Instance(TypeFactory::GetType(to, nullable)), x);
 }
 Scalar *Shared(int id, Scalar *x) { return new ScalarSharedExpression(id, x); }
 Predicate *Cmp(ComparisonID op, Scalar *l, Scalar *r) {
@@ -224,7 +258,7 @@ gpu::AttributeTypes Types() {
     a.width = static_cast<std::uint16_t>(c.type->maximumByteLength());
     attrs.push_back(a);
   }
-  t.relations.emplace_back(kRelationId, attrs);
+  t.relations.emplace_back(g_nullable_mode ? kNullableRelationId : kRelationId, attrs);
   return t;
 }
 
@@ -236,7 +270,8 @@ void PredicateCase(FILE *out, const char *name, const char *sql, Predicate *p) {
   for (int r = 0; r < kRows; ++r) bits.push_back(matches->get(r) ? '1' : '0');
   gpu::ExprBuilder b;
   const int root = gpu::LowerPredicate(p->getProto(), Types(), &b);
-  std::fprintf(out, "%s\n  {\"name\": \"%s\", \"sql\": \"%s\", \"kind\": \"predicate\", ", g_first_case ? "" : ",", name, sql);
+  std::fprintf(out, "%s\n  {\"name\": \"%s%s\", \"sql\": \"%s\", \"kind\": \"predicate\", \"nullable\": %s, ", g_first_case ? "" : ",",
+               g_nullable_mode ? "nullable_" : "", name, sql, g_nullable_mode ? "true" : "false");
   EmitNodes(out, b, root);
   std::fprintf(out, ", \"matches\": \"%s\", \"n_matches\": %zu}", bits.c_str(), static_cast<std::size_t>(matches->numTuples()));
   g_first_case = false;
@@ -249,17 +284,24 @@ void ScalarCase(FILE *out, const char *name, const char *sql, Scalar *s) {
   ColumnVectorPtr values = s->getAllValues(acc.get(), nullptr, &cache);
   const Type &t = s->getType();
   const std::size_t w = t.maximumByteLength();
-  std::string bytes;
+  std::string bytes, value_nulls;
   CHECK(values->isNative());
   const NativeColumnVector &ncv = static_cast<const NativeColumnVector &>(*values);
   CHECK_EQ(static_cast<std::size_t>(kRows), ncv.size());
-  for (int r = 0; r < kRows; ++r) bytes += Hex(ncv.getUntypedValue(r), w);
+  const std::vector<char> zeros(w, '\0');
+  for (int r = 0; r < kRows; ++r) {
+    const void *v = ncv.getUntypedValue(r);           // nullptr: the value is NULL
+    bytes += Hex(v ? v : zeros.data(), w);
+    value_nulls.push_back(v ? '0' : '1');
+  }
   gpu::ExprBuilder b;
   const int root = gpu::LowerScalar(s->getProto(), Types(), &b);
-  std::fprintf(out, "%s\n  {\"name\": \"%s\", \"sql\": \"%s\", \"kind\": \"scalar\", ", g_first_case ? "" : ",", name, sql);
+  std::fprintf(out, "%s\n  {\"name\": \"%s%s\", \"sql\": \"%s\", \"kind\": \"scalar\", \"nullable\": %s, ", g_first_case ? "" : ",",
+               g_nullable_mode ? "nullable_" : "", name, sql, g_nullable_mode ? "true" : "false");
   EmitNodes(out, b, root);
-  std::fprintf(out, ", \"result_type\": %d, \"result_width\": %zu, \"values\": \"%s\"}",
-               t.getTypeID() == kDate ? QS_DATE : static_cast<int>(t.getTypeID()), w, bytes.c_str());
+  std::fprintf(out, ", \"result_type\": %d, \"result_width\": %zu, \"result_nullable\": %s, \"values\": \"%s\", \"value_nulls\": \"%s\"}",
+               t.getTypeID() == kDate ? QS_DATE : static_cast<int>(t.getTypeID()), w, t.isNullable() ? "true" : "false", bytes.c_str(),
+               value_nulls.c_str());
   g_first_case = false;
 }
 
@@ -276,7 +318,9 @@ int main(int argc, char **argv) {
                  c.type->getTypeID() == kDate ? QS_DATE : static_cast<int>(c.type->getTypeID()), c.type->maximumByteLength(),
                  Hex(c.bytes.data(), c.bytes.size()).c_str());
   }
-  std::fprintf(out, "],\n \"cases\": [");
+  std::fprintf(out, "],\n \"nullable_relation_id\": %d, \"nullable_attributes\": [", kNullableRelationId);
+  for (std::size_t k = 0; k < sizeof(kNullableAttrs) / sizeof(kNullableAttrs[0]); ++k) std::fprintf(out, "%s%d", k ? ", " : "", kNullableAttrs[k]);
+  std::fprintf(out, "],\n \"nulls\": \"%s\",\n \"cases\": [", Hex(g_nulls.data(), g_nulls.size() * 8).c_str());
 
   // ------------------------------------------------------------------ scalars (E1: Scalar::getAllValues)
   ScalarCase(out, "int_plus_literal", "i + 1", Bin(ADD, Attr(A_I), LitI(1)));
@@ -362,6 +406,48 @@ int main(int argc, char **argv) {
   PredicateCase(out, "always_false_conjunction", "i < 0 AND i > 0", And({Cmp(LT, Attr(A_I), LitI(0)), Cmp(GT, Attr(A_I), LitI(0))}));
   PredicateCase(out, "cast_in_comparison", "CAST(i AS DOUBLE) / 3.0 >= disc * 100.0",
                 Cmp(GE, Bin(DIV, Cast(kDouble, Attr(A_I)), LitD(3.0)), Bin(MUL, Attr(A_DISC), LitD(100.0))));
+
+  // ------------------------------------------------------------------ the same over NULL-able attributes (relation tn)
+  // comparisons with a NULL operand are false and NOT complements them (LiteralComparators-inl.hpp:168-223,
+  // NegationPredicate.cpp:75-94); arithmetic over a NULL is NULL (ArithmeticBinaryOperators.hpp:178-186)
+  g_nullable_mode = true;
+  ScalarCase(out, "int_plus_literal", "i + 1", Bin(ADD, Attr(A_I), LitI(1)));
+  ScalarCase(out, "int_times_long", "i * l", Bin(MUL, Attr(A_I), Attr(A_L)));
+  ScalarCase(out, "q1_disc_price", "d * (1 - disc)", Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC))));
+  ScalarCase(out, "q1_charge", "d * (1 - disc) * (1 + tax)",
+             Bin(MUL, Bin(MUL, Attr(A_D), Bin(SUB, LitI(1), Attr(A_DISC))), Bin(ADD, LitI(1), Attr(A_TAX))));
+  ScalarCase(out, "negate_double", "-d", Neg(Attr(A_D)));
+  ScalarCase(out, "long_divide_int", "l / i2", Bin(DIV, Attr(A_L), Attr(A_I2)));
+  ScalarCase(out, "cast_int_to_double", "CAST(i AS DOUBLE) * disc", Bin(MUL, Cast(kDouble, Attr(A_I)), Attr(A_DISC)));
+  ScalarCase(out, "nested_mixed", "i + l * 2 - 3", Bin(SUB, Bin(ADD, Attr(A_I), Bin(MUL, Attr(A_L), LitI(2))), LitI(3)));
+  ScalarCase(out, "shared_nullable", "SHARED#2(i + l) * (SHARED#2(i + l) - 1)",
+             Bin(MUL, Shared(2, Bin(ADD, Attr(A_I), Attr(A_L))), Bin(SUB, Shared(2, Bin(ADD, Attr(A_I), Attr(A_L))), LitI(1))));
+  ScalarCase(out, "bare_attribute_int", "i", Attr(A_I));
+  ScalarCase(out, "bare_attribute_char", "c4", Attr(A_C4));
+  ScalarCase(out, "bare_attribute_date", "dt", Attr(A_DT));
+  ScalarCase(out, "not_null_operands_only", "disc + tax", Bin(ADD, Attr(A_DISC), Attr(A_TAX)));
+  PredicateCase(out, "int_lt", "i < 100", Cmp(LT, Attr(A_I), LitI(100)));
+  PredicateCase(out, "not_int_lt", "NOT (i < 100)", Not(Cmp(LT, Attr(A_I), LitI(100))));
+  PredicateCase(out, "double_ge_special", "d >= 0.0", Cmp(GE, Attr(A_D), LitD(0.0)));
+  PredicateCase(out, "double_ne_special", "d <> 0.0", Cmp(NE, Attr(A_D), LitD(0.0)));
+  PredicateCase(out, "char4_eq", "c4 = 'MAIL'", Cmp(EQ, Attr(A_C4), LitC("MAIL")));
+  PredicateCase(out, "char4_ne", "c4 <> 'MAIL'", Cmp(NE, Attr(A_C4), LitC("MAIL")));
+  PredicateCase(out, "not_char4_eq", "NOT (c4 = 'MAIL')", Not(Cmp(EQ, Attr(A_C4), LitC("MAIL"))));
+  PredicateCase(out, "char4_lt_shorter_literal", "c4 < 'RA'", Cmp(LT, Attr(A_C4), LitC("RA")));
+  PredicateCase(out, "date_le", "dt <= DATE '1995-06-17'", Cmp(LE, Attr(A_DT), LitDate(1995, 6, 17)));
+  PredicateCase(out, "attr_vs_attr_both_nullable", "i < l", Cmp(LT, Attr(A_I), Attr(A_L)));
+  PredicateCase(out, "attr_vs_attr_one_nullable", "i = i2", Cmp(EQ, Attr(A_I), Attr(A_I2)));
+  PredicateCase(out, "literal_on_the_left", "5 < i", Cmp(LT, LitI(5), Attr(A_I)));
+  PredicateCase(out, "expr_vs_expr", "i + 1 < l * 2", Cmp(LT, Bin(ADD, Attr(A_I), LitI(1)), Bin(MUL, Attr(A_L), LitI(2))));
+  PredicateCase(out, "or_of_nullables", "i < 0 OR d > 1000.0", Or({Cmp(LT, Attr(A_I), LitI(0)), Cmp(GT, Attr(A_D), LitD(1000.0))}));
+  PredicateCase(out, "not_and_of_nullables", "NOT (i < 0 AND l > 0)", Not(And({Cmp(LT, Attr(A_I), LitI(0)), Cmp(GT, Attr(A_L), LitI(0))})));
+  PredicateCase(out, "not_or_of_nullables", "NOT (i < 0 OR l > 0)", Not(Or({Cmp(LT, Attr(A_I), LitI(0)), Cmp(GT, Attr(A_L), LitI(0))})));
+  PredicateCase(out, "mixed_nullable_and_not", "disc <= 0.05 AND i > 0", And({Cmp(LE, Attr(A_DISC), LitD(0.05)), Cmp(GT, Attr(A_I), LitI(0))}));
+  PredicateCase(out, "not_not", "NOT (NOT (d < 50000.0))", Not(Not(Cmp(LT, Attr(A_D), LitD(50000.0)))));
+  PredicateCase(out, "q6_where", "dt >= '1994-01-01' AND dt < '1995-01-01' AND disc >= 0.05 AND disc <= 0.07 AND i < 240",
+                And({Cmp(GE, Attr(A_DT), LitDate(1994, 1, 1)), Cmp(LT, Attr(A_DT), LitDate(1995, 1, 1)),
+                     Cmp(GE, Attr(A_DISC), LitD(0.05)), Cmp(LE, Attr(A_DISC), LitD(0.07)), Cmp(LT, Attr(A_I), LitI(240))}));
+  g_nullable_mode = false;
 
   std::fprintf(out, "\n ]}\n");
   if (out != stdout) std::fclose(out);
