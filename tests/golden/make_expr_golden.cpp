@@ -24,6 +24,10 @@
 
 #include "catalog/CatalogAttribute.hpp"
 #include "catalog/CatalogRelation.hpp"
+#include "expressions/aggregation/AggregateFunction.hpp"
+#include "expressions/aggregation/AggregateFunctionFactory.hpp"
+#include "expressions/aggregation/AggregationHandle.hpp"
+#include "expressions/aggregation/AggregationID.hpp"
 #include "expressions/predicate/ComparisonPredicate.hpp"
 #include "expressions/predicate/ConjunctionPredicate.hpp"
 #include "expressions/predicate/DisjunctionPredicate.hpp"
@@ -36,6 +40,8 @@
 #include "expressions/scalar/ScalarSharedExpression.hpp"
 #include "expressions/scalar/ScalarUnaryExpression.hpp"
 #include "storage/TupleIdSequence.hpp"
+#include "storage/ValueAccessor.hpp"
+#include "storage/ValueAccessorMultiplexer.hpp"
 #include "types/DatetimeLit.hpp"
 #include "types/Type.hpp"
 #include "types/TypeFactory.hpp"
@@ -51,6 +57,9 @@
 #include "types/operations/unary_operations/UnaryOperationFactory.hpp"
 #include "types/operations/unary_operations/UnaryOperationID.hpp"
 #include "utility/ColumnVectorCache.hpp"
+#include "utility/lip_filter/LIPFilter.hpp"
+#include "utility/lip_filter/LIPFilter.pb.h"
+#include "utility/lip_filter/LIPFilterFactory.hpp"
 
 #include "ProtoLowering.hpp"
 
@@ -60,7 +69,7 @@ namespace {
 
 constexpr int kRows = 512;
 constexpr int kRelationId = 7;
-enum Attr { A_I, A_I2, A_L, A_F, A_D, A_DISC, A_TAX, A_DT, A_C1, A_C4, A_C10, kNumAttrs };
+enum Attr { A_I, A_I2, A_L, A_F, A_D, A_DISC, A_TAX, A_DT, A_C1, A_C4, A_C10, A_L2, kNumAttrs };
 
 std::uint64_t g_state = 0x9E3779B97F4A7C15ull;
 std::uint64_t Next() {      // splitmix64
@@ -114,12 +123,12 @@ void Put(std::vector<char> *out, T v) {
 
 void MakeRelation() {
   g_rel = new CatalogRelation(nullptr, "t", kRelationId);
-  const char *names[kNumAttrs] = {"i", "i2", "l", "f", "d", "disc", "tax", "dt", "c1", "c4", "c10"};
+  const char *names[kNumAttrs] = {"i", "i2", "l", "f", "d", "disc", "tax", "dt", "c1", "c4", "c10", "l2"};
   const Type *types[kNumAttrs] = {
       &TypeFactory::GetType(kInt, false),    &TypeFactory::GetType(kInt, false),    &TypeFactory::GetType(kLong, false),
       &TypeFactory::GetType(kFloat, false),  &TypeFactory::GetType(kDouble, false), &TypeFactory::GetType(kDouble, false),
       &TypeFactory::GetType(kDouble, false), &TypeFactory::GetType(kDate, false),   &TypeFactory::GetType(kChar, 1, false),
-      &TypeFactory::GetType(kChar, 4, false), &TypeFactory::GetType(kChar, 10, false)};
+      &TypeFactory::GetType(kChar, 4, false), &TypeFactory::GetType(kChar, 10, false), &TypeFactory::GetType(kLong, false)};
   g_cols.resize(kNumAttrs);
   for (int a = 0; a < kNumAttrs; ++a) {
     g_rel->addAttribute(new CatalogAttribute(g_rel, names[a], *types[a]));
@@ -151,6 +160,7 @@ void MakeRelation() {
     PutChar(&g_cols[A_C1].bytes, 1, flags[Next() % 3]);
     PutChar(&g_cols[A_C4].bytes, 4, modes[Next() % 7]);
     PutChar(&g_cols[A_C10].bytes, 10, segs[Next() % 5]);
+    Put<std::int64_t>(&g_cols[A_L2].bytes, static_cast<std::int64_t>(Next() % 601) - 300);
   }
   g_rel_n = new CatalogRelation(nullptr, "tn", kNullableRelationId);
   for (int a = 0; a < kNumAttrs; ++a) {
@@ -305,6 +315,130 @@ void ScalarCase(FILE *out, const char *name, const char *sql, Scalar *s) {
   g_first_case = false;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Aggregation handles (A6): AggregateFunction::createHandle -> accumulateValueAccessor over two halves of the relation ->
+// mergeStates -> finalize (expressions/aggregation/AggregationHandle.hpp:140-209), the path of an aggregate without
+// GROUP BY (storage/AggregationOperationState.cpp:476-520, 641-680).
+// ---------------------------------------------------------------------------------------------------------------------
+bool g_first_agg = true;
+
+void AggregateCase(FILE *out, const char *name, const char *sql, AggregationID fn, Scalar *argument /* null: COUNT(*) */) {
+  std::unique_ptr<Scalar> owner(argument);
+  const int half = kRows / 2;
+  std::vector<const Type *> arg_types;
+  if (argument) arg_types.push_back(&argument->getType());
+  std::unique_ptr<AggregationHandle> handle(AggregateFunctionFactory::Get(fn).createHandle(arg_types));
+  std::unique_ptr<AggregationState> total(handle->createInitialState());
+  ColumnVectorPtr values;
+  std::unique_ptr<ColumnVectorsValueAccessor> acc(MakeAccessor());
+  ColumnVectorCache cache;
+  if (argument) values = argument->getAllValues(acc.get(), nullptr, &cache);
+  for (int part = 0; part < 2; ++part) {                 // two "work orders": rows [0, 256) and [256, 512)
+    std::unique_ptr<AggregationState> state;
+    if (!argument) {
+      state.reset(handle->accumulateNullary(half));
+    } else {
+      const NativeColumnVector &all = static_cast<const NativeColumnVector &>(*values);
+      NativeColumnVector *piece = new NativeColumnVector(argument->getType(), half);
+      for (int r = part * half; r < (part + 1) * half; ++r) {
+        const void *v = all.getUntypedValue(r);
+        if (v) piece->appendUntypedValue(v); else piece->appendNullValue();
+      }
+      ColumnVectorsValueAccessor piece_acc;
+      piece_acc.addColumn(piece);
+      state.reset(handle->accumulateValueAccessor({MultiSourceAttributeId(ValueAccessorSource::kBase, 0)},
+                                                  ValueAccessorMultiplexer(&piece_acc)));
+    }
+    handle->mergeStates(*state, total.get());
+  }
+  const TypedValue result = handle->finalize(*total);
+  const Type &rt = *handle->getResultType();
+  char raw[8] = {0};
+  if (!result.isNull()) result.copyInto(raw);
+  gpu::ExprBuilder b;
+  const int root = argument ? gpu::LowerScalar(argument->getProto(), Types(), &b) : -1;
+  std::fprintf(out, "%s\n  {\"name\": \"%s%s\", \"sql\": \"%s\", \"nullable\": %s, \"function\": %d, ", g_first_agg ? "" : ",",
+               g_nullable_mode ? "nullable_" : "", name, sql, g_nullable_mode ? "true" : "false", static_cast<int>(fn));
+  EmitNodes(out, b, root);
+  std::fprintf(out, ", \"result_type\": %d, \"result_null\": %s, \"result\": \"%s\"}", static_cast<int>(rt.getTypeID()),
+               result.isNull() ? "true" : "false", Hex(raw, rt.maximumByteLength()).c_str());
+  g_first_agg = false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LIP filters (L1, L2, L4): LIPFilterFactory::ReconstructFromProto from the proto ExecutionGenerator writes, built with
+// insertValueAccessor over the tuples a build-side predicate keeps, probed with filterBatch over all tuples
+// (utility/lip_filter/BitVectorExactFilter.hpp:76-176, SingleIdentityHashFilter.hpp:62-171).
+// ---------------------------------------------------------------------------------------------------------------------
+bool g_first_lip = true;
+
+void LipCase(FILE *out, const char *name, bool exact, std::int64_t min_value, std::int64_t max_value, std::uint64_t cardinality,
+             bool is_anti, Predicate *build_predicate, int build_attr, int probe_attr) {
+  std::unique_ptr<Predicate> owner(build_predicate);
+  const std::vector<const Type *> &types_n = g_types_n;
+  const Type &build_type = g_nullable_mode ? *types_n[build_attr] : *g_cols[build_attr].type;
+  const Type &probe_type = g_nullable_mode ? *types_n[probe_attr] : *g_cols[probe_attr].type;
+  serialization::LIPFilter proto;
+  if (exact) {
+    proto.set_lip_filter_type(serialization::LIPFilterType::BIT_VECTOR_EXACT_FILTER);
+    proto.SetExtension(serialization::BitVectorExactFilter::min_value, min_value);
+    proto.SetExtension(serialization::BitVectorExactFilter::max_value, max_value);
+    proto.SetExtension(serialization::BitVectorExactFilter::attribute_size, build_type.maximumByteLength());
+    proto.SetExtension(serialization::BitVectorExactFilter::is_anti_filter, is_anti);
+  } else {
+    proto.set_lip_filter_type(serialization::LIPFilterType::SINGLE_IDENTITY_HASH_FILTER);
+    proto.SetExtension(serialization::SingleIdentityHashFilter::filter_cardinality, cardinality);
+    proto.SetExtension(serialization::SingleIdentityHashFilter::attribute_size, build_type.maximumByteLength());
+  }
+  CHECK(LIPFilterFactory::ProtoIsValid(proto));
+  std::unique_ptr<LIPFilter> filter(LIPFilterFactory::ReconstructFromProto(proto));
+  std::unique_ptr<ColumnVectorsValueAccessor> acc(MakeAccessor());
+  std::unique_ptr<TupleIdSequence> keep(build_predicate->getAllMatches(acc.get(), nullptr, nullptr, nullptr));
+  std::unique_ptr<ValueAccessor> build_rows(acc->createSharedTupleIdSequenceAdapterVirtual(*keep));
+  filter->insertValueAccessor(build_rows.get(), build_attr, &build_type);
+  std::vector<tuple_id> batch(kRows);
+  for (int r = 0; r < kRows; ++r) batch[r] = r;
+  const std::size_t kept = filter->filterBatch(acc.get(), probe_attr, probe_type.isNullable(), &batch, kRows);
+  std::string bits(kRows, '0');
+  for (std::size_t k = 0; k < kept; ++k) bits[batch[k]] = '1';
+  gpu::ExprBuilder b;
+  const int root = gpu::LowerPredicate(build_predicate->getProto(), Types(), &b);
+  std::fprintf(out, "%s\n  {\"name\": \"%s%s\", \"nullable\": %s, \"exact\": %s, \"min_value\": %lld, \"max_value\": %lld, "
+               "\"cardinality\": %llu, \"is_anti\": %s, \"attribute_size\": %zu, \"build_attr\": %d, \"probe_attr\": %d, ",
+               g_first_lip ? "" : ",", g_nullable_mode ? "nullable_" : "", name, g_nullable_mode ? "true" : "false",
+               exact ? "true" : "false", static_cast<long long>(min_value), static_cast<long long>(max_value),
+               static_cast<unsigned long long>(cardinality), is_anti ? "true" : "false", build_type.maximumByteLength(), build_attr,
+               probe_attr);
+  EmitNodes(out, b, root);
+  std::fprintf(out, ", \"n_built_from\": %zu, \"passes\": \"%s\", \"n_passes\": %zu}", static_cast<std::size_t>(keep->numTuples()),
+               bits.c_str(), kept);
+  g_first_lip = false;
+}
+
+Predicate *IsR() { return Cmp(EQ, Attr(A_C1), LitC("R")); }
+Predicate *InRange(int a, int lo, int hi) { return And({Cmp(GE, Attr(a), LitI(lo)), Cmp(LE, Attr(a), LitI(hi))}); }
+
+void AllAggregates(FILE *out) {
+  struct Fn { AggregationID id; const char *name; } fns[5] = {{AggregationID::kSum, "sum"}, {AggregationID::kAvg, "avg"},
+      {AggregationID::kMin, "min"}, {AggregationID::kMax, "max"}, {AggregationID::kCount, "count"}};
+  struct Arg { int attr; const char *name; } args[5] = {{A_I, "i"}, {A_L, "l"}, {A_F, "f"}, {A_DISC, "disc"}, {A_L2, "l2"}};
+  for (const Fn &fn : fns)
+    for (const Arg &arg : args) {
+      const std::string name = std::string(fn.name) + "_" + arg.name, sql = std::string(fn.name) + "(" + arg.name + ")";
+      AggregateCase(out, name.c_str(), sql.c_str(), fn.id, Attr(arg.attr));
+    }
+  AggregateCase(out, "count_star", "count(*)", AggregationID::kCount, nullptr);
+  AggregateCase(out, "sum_disc_price", "sum(d2 * (1 - disc))", AggregationID::kSum,
+                Bin(MUL, Attr(A_TAX), Bin(SUB, LitI(1), Attr(A_DISC))));
+  AggregateCase(out, "avg_expr_mixed", "avg(i * disc)", AggregationID::kAvg, Bin(MUL, Attr(A_I), Attr(A_DISC)));
+  AggregateCase(out, "sum_int_expr", "sum(i + i2)", AggregationID::kSum, Bin(ADD, Attr(A_I), Attr(A_I2)));
+  AggregateCase(out, "min_negated", "min(-l)", AggregationID::kMin, Neg(Attr(A_L)));
+  AggregateCase(out, "max_float_expr", "max(f * 2.5)", AggregationID::kMax, Bin(MUL, Attr(A_F), LitF(2.5f)));
+  AggregateCase(out, "sum_with_nan_and_inf", "sum(d)", AggregationID::kSum, Attr(A_D));
+  AggregateCase(out, "count_char", "count(c4)", AggregationID::kCount, Attr(A_C4));
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -447,6 +581,30 @@ int main(int argc, char **argv) {
   PredicateCase(out, "q6_where", "dt >= '1994-01-01' AND dt < '1995-01-01' AND disc >= 0.05 AND disc <= 0.07 AND i < 240",
                 And({Cmp(GE, Attr(A_DT), LitDate(1994, 1, 1)), Cmp(LT, Attr(A_DT), LitDate(1995, 1, 1)),
                      Cmp(GE, Attr(A_DISC), LitD(0.05)), Cmp(LE, Attr(A_DISC), LitD(0.07)), Cmp(LT, Attr(A_I), LitI(240))}));
+  g_nullable_mode = false;
+
+  std::fprintf(out, "\n ],\n \"aggregates\": [");
+  AllAggregates(out);
+  g_nullable_mode = true;
+  AllAggregates(out);
+  g_nullable_mode = false;
+
+  std::fprintf(out, "\n ],\n \"lip_filters\": [");
+  for (int pass = 0; pass < 2; ++pass) {
+    g_nullable_mode = pass == 1;
+    LipCase(out, "exact_int_probe_same_attr", true, -1000, 1000, 0, false, IsR(), A_I, A_I);
+    LipCase(out, "exact_int_probe_other_attr", true, -1000, 1000, 0, false, IsR(), A_I, A_I2);
+    LipCase(out, "exact_int_anti", true, -1000, 1000, 0, true, IsR(), A_I, A_I);
+    LipCase(out, "exact_int_narrow_range", true, -500, 500, 0, false, InRange(A_I, -500, 500), A_I, A_I);
+    LipCase(out, "exact_int_narrow_range_anti", true, -500, 500, 0, true, InRange(A_I, -500, 500), A_I, A_I);
+    LipCase(out, "exact_long", true, -300, 300, 0, false, IsR(), A_L2, A_L2);
+    LipCase(out, "exact_long_probe_out_of_range", true, -300, 300, 0, false, IsR(), A_L2, A_L);
+    LipCase(out, "exact_long_probe_out_of_range_anti", true, -300, 300, 0, true, IsR(), A_L2, A_L);
+    LipCase(out, "identity_hash_int_negative_values", false, 0, 0, 257, false, IsR(), A_I, A_I);
+    LipCase(out, "identity_hash_int_small_cardinality", false, 0, 0, 64, false, IsR(), A_I2, A_I);
+    LipCase(out, "identity_hash_long", false, 0, 0, 1000, false, IsR(), A_L, A_L);
+    LipCase(out, "identity_hash_long_probe_other", false, 0, 0, 1021, false, InRange(A_I, -100, 900), A_L2, A_L);
+  }
   g_nullable_mode = false;
 
   std::fprintf(out, "\n ]}\n");

@@ -12,6 +12,12 @@ Here the SAME node arrays are evaluated by the oracle (CPU, `-m "not gpu"`) and 
 P2, E1), except that two NaNs count as equal whatever their sign / payload bits (x86 SSE produces the negative default NaN
 for 0.0 / 0.0, the GPU the positive one; the reference itself never looks at those bits).
 
+`aggregates` (66 cases): AggregateFunction::createHandle -> accumulateValueAccessor over two halves of the relation ->
+mergeStates -> finalize, for SUM / AVG / MIN / MAX / COUNT over every numeric type, expressions, COUNT(*) and COUNT(CHAR),
+NOT NULL and NULL-able (row A6).  `lip_filters` (24 cases): LIPFilterFactory::ReconstructFromProto, insertValueAccessor
+over the tuples a predicate keeps, filterBatch over all tuples -- exact filters (INT / LONG, anti, probe values outside
+the range) and identity-hash filters (negative values) (rows L1, L2, L4).
+
 The NULL-able cases run over the same tuples with every fifth value or so of five attributes NULL: the reference's answers
 there are "a comparison with a NULL operand is false, NOT complements it, arithmetic over a NULL is NULL" -- the rules
 oracle/qs_null_oracle.py restates and the device path implements with its per-row NULL masks.
@@ -33,6 +39,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_expressions.json")))
 CASES = [c for c in GOLDEN["cases"] if not c["nullable"]]
 NULL_CASES = [c for c in GOLDEN["cases"] if c["nullable"]]
+AGGREGATES = GOLDEN["aggregates"]
+LIP_FILTERS = GOLDEN["lip_filters"]
+RTOL = 1e-9            # double SUM / AVG on the device (summation order differs; BASELINE.json north_star)
 N = GOLDEN["n_rows"]
 NULLS = np.frombuffer(bytes.fromhex(GOLDEN["nulls"]), dtype="<u8").copy()
 RID = len(GOLDEN["columns"])          # attribute id of the row-id column appended below
@@ -109,8 +118,9 @@ def check_scalar(case, ids, vals, val_nulls):
 
 def test_golden_file_is_what_the_generator_writes():
     assert len(CASES) == 69 and len(NULL_CASES) == 32 and N == 512
+    assert len(AGGREGATES) == 66 and len(LIP_FILTERS) == 24
     assert GOLDEN["nullable_attributes"] == [0, 2, 4, 7, 9]
-    assert set(np.nonzero([(NULLS >> np.uint64(a) & np.uint64(1)).any() for a in range(RID)])[0]) == {0, 2, 4, 7, 9}
+    assert set(np.nonzero([(NULLS >> np.uint64(a) & np.uint64(1)).any() for a in range(RID)])[0].tolist()) == {0, 2, 4, 7, 9}
     assert sum(c["kind"] == "predicate" for c in CASES) == 39
     d = the_table().col("d").data
     assert np.isnan(d).any() and np.isinf(d).any() and (np.signbit(d) & (d == 0)).any()      # the special values are there
@@ -181,5 +191,165 @@ def test_cuda_path_gives_the_reference_classes_results(engine, block_rows):
         for case in CASES:
             run_case(G, rel, case)
     finally:
+        G.close()
+        engine.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- aggregation handles
+_RESULT_DTYPE = {A.QS_INT: "<i4", A.QS_LONG: "<i8", A.QS_FLOAT: "<f4", A.QS_DOUBLE: "<f8"}
+
+
+def reference_result(case):
+    if case["result_null"]:
+        return None
+    return np.frombuffer(bytes.fromhex(case["result"]), dtype=_RESULT_DTYPE[case["result_type"]])[0]
+
+
+def check_aggregate(case, got, got_null, exact_doubles):
+    want = reference_result(case)
+    assert got_null == (want is None), (case["name"], got, got_null, want)
+    if want is None:
+        return
+    assert np.asarray(got).dtype == want.dtype, (case["name"], np.asarray(got).dtype, want.dtype)
+    if want.dtype.kind == "f" and case["function"] in (A.QS_AGG_SUM, A.QS_AGG_AVG) and not exact_doubles:
+        g, w = float(got), float(want)
+        assert (g != g and w != w) or g == w or abs(g - w) <= RTOL * max(abs(g), abs(w)), (case["name"], g, w)
+    else:
+        assert got == want or (got != got and want != want), (case["name"], got, want)
+
+
+@pytest.mark.parametrize("case", [c for c in AGGREGATES if not c["nullable"]], ids=[c["name"] for c in AGGREGATES if not c["nullable"]])
+def test_oracle_gives_the_reference_handles_results(oracle, case):
+    """Two 256-row work orders merged in order, like the generator's two accumulate + mergeStates: bit-exact, doubles too."""
+    oracle.set_block_rows(256)
+    try:
+        es, _ = expr_set(case)
+        out = OracleBackend().aggregate(the_table(), es, -1, [(case["function"], case["root"])], [], A.QS_AGG_SINGLE_STATE, [])
+        check_aggregate(case, out.values[0][0], bool(out.null_mask & 1), exact_doubles=True)
+    finally:
+        oracle.set_block_rows(65536)
+
+
+@pytest.mark.parametrize("case", [c for c in AGGREGATES if c["nullable"]], ids=[c["name"] for c in AGGREGATES if c["nullable"]])
+def test_null_oracle_gives_the_reference_handles_results(oracle, case):
+    es, _ = expr_set(case)
+    (value, is_null), = NO.aggregate(es, -1, [(case["function"], case["root"])], None, the_table(), NULLS)[None]
+    want = reference_result(case)
+    assert is_null == (want is None), (case["name"], value, is_null, want)
+    if want is not None:
+        if want.dtype.kind == "f":
+            g, w = float(value), float(want)          # numpy's pairwise sum is not the handle's sequential one
+            assert (g != g and w != w) or g == w or abs(g - w) <= RTOL * max(abs(g), abs(w)), (case["name"], g, w)
+        else:
+            assert int(value) == int(want), (case["name"], value, want)
+
+
+def argument_is_nullable(es, root):
+    """Does the argument read a NULL-able attribute (what AggregateFunction::createHandle learns from the argument type)."""
+    if root < 0:
+        return False
+    n = es.nodes[root]
+    if n.kind == A.QS_N_ATTRIBUTE:
+        return n.a in GOLDEN["nullable_attributes"]
+    if n.kind == A.QS_N_LITERAL:
+        return False
+    return argument_is_nullable(es, n.a) or (n.kind == A.QS_N_BINARY and argument_is_nullable(es, n.b))
+
+
+@pytest.mark.gpu
+def test_cuda_path_gives_the_reference_handles_results(engine):
+    """All 66 aggregate cases as SINGLE_STATE aggregations through qsgpu_agg_create / run (two work orders) / finalize."""
+    from test_gpu_nulls import nullable_relation, run_agg
+    t = the_table()
+    G = GpuBackend(engine)
+    nrel = nullable_relation(engine, the_table(), NULLS)
+    try:
+        rel = G.relation(t)
+        for case in AGGREGATES:
+            es, _ = expr_set(case)
+            aggs = [(case["function"], case["root"])]
+            if not case["nullable"]:
+                out = G.aggregate(rel, es, -1, aggs, [], A.QS_AGG_SINGLE_STATE, [], row_ranges=[(0, 256), (256, 512)])
+                check_aggregate(case, out.values[0][0], bool(out.null_mask & 1), exact_doubles=False)
+            else:
+                cols, out_nulls, mask = run_agg(engine, nrel, A.QS_AGG_SINGLE_STATE, es, -1, aggs, [], [],
+                                                [0] if argument_is_nullable(es, case["root"]) else [], t, work_orders=2)
+                check_aggregate(case, cols[0][0], bool(mask & 1), exact_doubles=False)
+                assert bool(int(out_nulls[0]) & 1) == bool(mask & 1)
+    finally:
+        nrel.destroy()
+        G.close()
+        engine.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- LIP filters
+def run_lip_case(backend, rel, case):
+    es, rid = expr_set(case)
+    attr_type = A.QS_INT if case["attribute_size"] == 4 else A.QS_LONG
+    kind = A.QS_LIP_BITVECTOR_EXACT if case["exact"] else A.QS_LIP_SINGLE_IDENTITY_HASH
+    lip = backend.make_lip(kind, attr_type, case["min_value"], case["max_value"], case["cardinality"], case["is_anti"])
+    backend.build_lip(rel, es, case["root"], None, [(lip, case["build_attr"])])
+    return lip, es, rid
+
+
+def check_passes(case, ids):
+    got = np.zeros(N, dtype=bool)
+    assert len(np.unique(ids)) == len(ids)
+    got[ids] = True
+    want = np.array([ch == "1" for ch in case["passes"]])
+    assert int(want.sum()) == case["n_passes"]
+    assert (got == want).all(), (case["name"], np.nonzero(got != want)[0][:10])
+
+
+@pytest.mark.parametrize("case", [c for c in LIP_FILTERS if not c["nullable"]], ids=[c["name"] for c in LIP_FILTERS if not c["nullable"]])
+def test_oracle_gives_the_reference_filters_results(oracle, case):
+    B = OracleBackend()
+    t = the_table()
+    lip, es, rid = run_lip_case(B, t, case)
+    out = B.select(t, es, -1, [(lip, case["probe_attr"])], [rid], [(A.QS_INT, 4)])
+    check_passes(case, out.columns[0].data)
+
+
+@pytest.mark.parametrize("case", [c for c in LIP_FILTERS if c["nullable"]], ids=[c["name"] for c in LIP_FILTERS if c["nullable"]])
+def test_null_rule_for_filters_gives_the_reference_filters_results(oracle, case):
+    """A NULL value neither enters a filter nor passes one -- not even an anti filter (BitVectorExactFilter.hpp:113-146):
+    the oracle builds from the rows whose build attribute is not NULL and the NULL probe rows are dropped afterwards."""
+    B = OracleBackend()
+    t = the_table()
+    es, rid = expr_set(case)
+    isnull = lambda a: ((NULLS >> np.uint64(a)) & np.uint64(1)).astype(bool)
+    keep = NO.predicate(es, case["root"], t, NULLS) & ~isnull(case["build_attr"])
+    assert int(NO.predicate(es, case["root"], t, NULLS).sum()) == case["n_built_from"]
+    idx = np.nonzero(keep)[0]
+    built_from = HostTable("b", [Column(c.name, c.type, c.data[idx], c.width) for c in t.columns])
+    attr_type = A.QS_INT if case["attribute_size"] == 4 else A.QS_LONG
+    kind = A.QS_LIP_BITVECTOR_EXACT if case["exact"] else A.QS_LIP_SINGLE_IDENTITY_HASH
+    lip = B.make_lip(kind, attr_type, case["min_value"], case["max_value"], case["cardinality"], case["is_anti"])
+    B.build_lip(built_from, None, -1, None, [(lip, case["build_attr"])])
+    out = B.select(t, es, -1, [(lip, case["probe_attr"])], [rid], [(A.QS_INT, 4)])
+    ids = out.columns[0].data
+    check_passes(case, ids[~isnull(case["probe_attr"])[ids]])
+
+
+@pytest.mark.gpu
+def test_cuda_path_gives_the_reference_filters_results(engine):
+    """The 24 LIP cases: qsgpu_lip_create from the proto's fields, qsgpu_build_lip_filter, probe inside qsgpu_select."""
+    from test_gpu_nulls import nullable_relation
+    G = GpuBackend(engine)
+    nrel = nullable_relation(engine, the_table(), NULLS)
+    try:
+        rel = G.relation(the_table())
+        for case in LIP_FILTERS:
+            src = nrel if case["nullable"] else rel
+            lip, es, rid = run_lip_case(G, src, case)
+            out = engine.Relation.create([(A.QS_INT, 4)], N)
+            try:
+                engine.select(src, es, -1, [(lip, case["probe_attr"])], [rid], out)
+                ids = out.read_all()[0]
+            finally:
+                out.destroy()
+            check_passes(case, ids)
+    finally:
+        nrel.destroy()
         G.close()
         engine.synchronize()
