@@ -24,6 +24,7 @@
 
 #include "catalog/CatalogAttribute.hpp"
 #include "catalog/CatalogRelation.hpp"
+#include "catalog/PartitionSchemeHeader.hpp"
 #include "expressions/aggregation/AggregateFunction.hpp"
 #include "expressions/aggregation/AggregateFunctionFactory.hpp"
 #include "expressions/aggregation/AggregationHandle.hpp"
@@ -606,6 +607,24 @@ int main(int argc, char **argv) {
     LipCase(out, "identity_hash_long_probe_other", false, 0, 0, 1021, false, InRange(A_I, -100, 900), A_L2, A_L);
   }
   g_nullable_mode = false;
+
+  // ------------------------------------------------------------------ HashPartitionSchemeHeader::getPartitionId
+  // (catalog/PartitionSchemeHeader.hpp:200-214) for the tuples' i (INT, negative values included), l and l2 (LONG): the
+  // partition PartitionAwareInsertDestination sends a tuple to (storage/InsertDestination.cpp:598-640).
+  std::fprintf(out, "\n ],\n \"hash_partitions\": [");
+  bool first_part = true;
+  for (const int attr : {static_cast<int>(A_I), static_cast<int>(A_L), static_cast<int>(A_L2)})
+    for (const std::size_t n_parts : {2u, 4u, 7u, 8u, 13u}) {
+      HashPartitionSchemeHeader header(n_parts, PartitionSchemeHeader::PartitionAttributeIds(1, attr));
+      const std::size_t w = g_cols[attr].type->maximumByteLength();
+      std::fprintf(out, "%s\n  {\"attr\": %d, \"n_parts\": %zu, \"partition_of_row\": [", first_part ? "" : ",", attr, n_parts);
+      for (int r = 0; r < kRows; ++r) {
+        const TypedValue v = g_cols[attr].type->makeValue(g_cols[attr].bytes.data() + r * w, w);
+        std::fprintf(out, "%s%zu", r ? "," : "", static_cast<std::size_t>(header.getPartitionId({v})));
+      }
+      std::fprintf(out, "]}");
+      first_part = false;
+    }
 
   std::fprintf(out, "\n ]}\n");
   if (out != stdout) std::fclose(out);

@@ -18,6 +18,9 @@ NOT NULL and NULL-able (row A6).  `lip_filters` (24 cases): LIPFilterFactory::Re
 over the tuples a predicate keeps, filterBatch over all tuples -- exact filters (INT / LONG, anti, probe values outside
 the range) and identity-hash filters (negative values) (rows L1, L2, L4).
 
+`hash_partitions` (15 cases): HashPartitionSchemeHeader::getPartitionId for INT (negative values) and LONG keys over 2 / 4 /
+7 / 8 / 13 partitions -- where PartitionAwareInsertDestination sends each tuple (row f4).
+
 The NULL-able cases run over the same tuples with every fifth value or so of five attributes NULL: the reference's answers
 there are "a comparison with a NULL operand is false, NOT complements it, arithmetic over a NULL is NULL" -- the rules
 oracle/qs_null_oracle.py restates and the device path implements with its per-row NULL masks.
@@ -41,6 +44,7 @@ CASES = [c for c in GOLDEN["cases"] if not c["nullable"]]
 NULL_CASES = [c for c in GOLDEN["cases"] if c["nullable"]]
 AGGREGATES = GOLDEN["aggregates"]
 LIP_FILTERS = GOLDEN["lip_filters"]
+HASH_PARTITIONS = GOLDEN["hash_partitions"]
 RTOL = 1e-9            # double SUM / AVG on the device (summation order differs; BASELINE.json north_star)
 N = GOLDEN["n_rows"]
 NULLS = np.frombuffer(bytes.fromhex(GOLDEN["nulls"]), dtype="<u8").copy()
@@ -351,5 +355,46 @@ def test_cuda_path_gives_the_reference_filters_results(engine):
             check_passes(case, ids)
     finally:
         nrel.destroy()
+        G.close()
+        engine.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- hash partitioning
+def partition_function(values: np.ndarray, n_parts: int) -> np.ndarray:
+    """catalog/PartitionSchemeHeader.hpp:200-214 over TypedValue::getHash of one INT / LONG key: the bit pattern of the
+    inline value with the rest of the 8-byte union zeroed (types/TypedValue.hpp:95-100) -- a negative INT is NOT
+    sign-extended -- then `& (n - 1)` for a power of two, `% n` otherwise."""
+    h = values.view(np.uint32).astype(np.uint64) if values.dtype.itemsize == 4 else values.view(np.uint64)
+    n = np.uint64(n_parts)
+    return (h & (n - np.uint64(1))) if n_parts & (n_parts - 1) == 0 else (h % n)
+
+
+@pytest.mark.parametrize("case", HASH_PARTITIONS, ids=[f"attr{c['attr']}_n{c['n_parts']}" for c in HASH_PARTITIONS])
+def test_partition_function_is_the_reference_headers(case):
+    vals = the_table().columns[case["attr"]].data
+    assert (partition_function(vals, case["n_parts"]) == np.array(case["partition_of_row"], dtype=np.uint64)).all()
+
+
+@pytest.mark.gpu
+def test_cuda_path_partitions_like_the_reference_header(engine):
+    """qsgpu_hash_partition (K8 behind PartitionAwareInsertDestination): every tuple lands in the partition
+    HashPartitionSchemeHeader::getPartitionId names, and the output is a permutation of the input."""
+    G = GpuBackend(engine)
+    try:
+        rel = G.relation(the_table())
+        for case in HASH_PARTITIONS:
+            out = engine.Relation.create(rel.schema, N)
+            try:
+                off = engine.hash_partition(rel, case["attr"], case["n_parts"], out)
+                rids = out.read(RID)
+            finally:
+                out.destroy()
+            assert len(off) == case["n_parts"] + 1 and off[0] == 0 and off[-1] == N
+            assert sorted(rids.tolist()) == list(range(N))
+            want = np.array(case["partition_of_row"])
+            for p in range(case["n_parts"]):
+                part = rids[int(off[p]):int(off[p + 1])]
+                assert (want[part] == p).all(), (case["attr"], case["n_parts"], p)
+    finally:
         G.close()
         engine.synchronize()
