@@ -203,7 +203,8 @@ int qsgpu_relation_read_nulls(qsgpu_relation_t rel, uint64_t row_begin, uint64_t
  *     for a group without a non-NULL argument -- declare such aggregates in qs_agg_spec.nullable_arguments;
  *   - rows with a NULL join key neither enter a join table nor match (storage/HashTable.hpp:1384,1903): inner / semi
  *     joins drop such a probe row, an anti join emits it and a left outer join emits it NULL-padded (:1999-2003);
- *     they are not inserted into / are rejected by LIP filters;
+ *     they are not inserted into / are rejected by LIP filters -- anti filters included (filterBatchInternal<true> skips a
+ *     NULL value before it looks at the filter, utility/lip_filter/BitVectorExactFilter.hpp:130-146);
  *   - Select and the probe side of an inner join carry the NULL-ness of what they project into the output relation.
  *   - rows whose GROUP BY key is NULL belong to no group (storage/PackedPayloadHashTable.hpp:861-866: the reference
  *     prints no NULL group).
