@@ -44,6 +44,7 @@
 #include "tmb/id_typedefs.h"
 
 #include "ProtoLowering.hpp"
+#include "QueryContextLowering.hpp"
 #include "qsgpu.h"
 
 namespace tmb { class MessageBus; }
@@ -70,18 +71,6 @@ static_assert(static_cast<int>(HashJoinOperator::JoinType::kInnerJoin) == QS_JOI
                   static_cast<int>(HashJoinOperator::JoinType::kLeftAntiJoin) == QS_JOIN_LEFT_ANTI &&
                   static_cast<int>(HashJoinOperator::JoinType::kLeftOuterJoin) == QS_JOIN_LEFT_OUTER,
               "qsgpu_types.h must keep HashJoinOperator::JoinType's values");
-
-inline std::vector<qs_attr> AttributesOf(const CatalogRelationSchema &relation) {
-  std::vector<qs_attr> out;
-  for (CatalogRelationSchema::const_iterator it = relation.begin(); it != relation.end(); ++it) {
-    const Type &t = it->getType();
-    qs_attr a{};
-    a.type = static_cast<std::uint16_t>(t.getTypeID() == kDate ? QS_DATE : static_cast<int>(t.getTypeID()));
-    a.width = static_cast<std::uint16_t>(t.isVariableLength() ? 0 : t.maximumByteLength());
-    out.push_back(a);
-  }
-  return out;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The device-side twins of what QueryContext owns, created from the SAME serialized entries and addressed by the SAME
@@ -146,55 +135,14 @@ class GpuQueryState {
       if (l) qsgpu_lip_destroy(l);
   }
 
-  // AggregationOperationState::ReconstructFromProto (storage/AggregationOperationState.cpp:186-260) as a qs_agg_spec.
-  // `input` is the relation the proto's relation_id names (the proto's attribute scalars carry ids only).
+  // AggregationOperationState::ReconstructFromProto (storage/AggregationOperationState.cpp:186-260) as a qs_agg_spec
+  // (LowerAggregationState, QueryContextLowering.hpp).  `input` is the relation the proto's relation_id names.
   void addAggregationState(const QueryContext::aggregation_state_id id, const serialization::AggregationOperationState &proto,
                            const CatalogRelationSchema &input, const std::size_t num_partitions) {
-    AttributeTypes types;
-    types.relations.emplace_back(proto.relation_id(), AttributesOf(input));
-    ExprBuilder b;
-    const int pred = proto.has_predicate() ? LowerPredicate(proto.predicate(), types, &b) : -1;
-    std::vector<qs_aggregate> aggregates;
-    std::uint64_t nullable_arguments = 0;
-    for (int j = 0; j < proto.aggregates_size(); ++j) {
-      const serialization::Aggregate &a = proto.aggregates(j);
-      if (a.is_distinct()) LOG(FATAL) << "GPU path: DISTINCT aggregates keep their CPU operators";
-      CHECK_LE(a.argument_size(), 1);
-      qs_aggregate q{};
-      q.function = static_cast<std::uint32_t>(a.function().aggregation_id());
-      q.argument_root = a.argument_size() ? LowerScalar(a.argument(0), types, &b) : -1;
-      if (a.argument_size() && a.argument(0).data_source() == serialization::Scalar::ATTRIBUTE) {
-        const attribute_id arg = a.argument(0).GetExtension(serialization::ScalarAttribute::attribute_id);
-        if (input.getAttributeById(arg)->getType().isNullable() && j < 64) nullable_arguments |= 1ull << j;
-      }
-      aggregates.push_back(q);
-    }
-    std::vector<std::int32_t> group_by;
-    for (int g = 0; g < proto.group_by_expressions_size(); ++g) group_by.push_back(LowerScalar(proto.group_by_expressions(g), types, &b));
-    const qs_expr_set es = b.view();
-    qs_agg_spec spec{};
-    spec.dev = device_;
-    spec.exprs = &es;
-    spec.predicate_root = pred;
-    spec.n_aggregates = static_cast<std::uint32_t>(aggregates.size());
-    spec.aggregates = aggregates.data();
-    spec.n_group_by = static_cast<std::uint32_t>(group_by.size());
-    spec.group_by_roots = group_by.data();
-    spec.estimated_num_entries = proto.estimated_num_entries();
-    spec.nullable_arguments = nullable_arguments;
-    // the strategy the optimizer chose (query_optimizer/ExecutionGenerator.cpp:1924-1965)
-    if (group_by.empty()) {
-      spec.strategy = QS_AGG_SINGLE_STATE;
-    } else {
-      switch (proto.hash_table_impl_type()) {
-        case serialization::HashTableImplType::THREAD_PRIVATE_COMPACT_KEY: spec.strategy = QS_AGG_COMPACT_KEY; break;
-        case serialization::HashTableImplType::COLLISION_FREE_VECTOR:
-          spec.strategy = QS_AGG_COLLISION_FREE;
-          spec.collision_free_max_key = static_cast<std::int64_t>(proto.estimated_num_entries()) - 1;
-          break;
-        default: spec.strategy = QS_AGG_SEPARATE_CHAINING;
-      }
-    }
+    LoweredAggregationState lowered;
+    LowerAggregationState(proto, input, &lowered);
+    const qs_expr_set es = lowered.exprs.view();
+    const qs_agg_spec spec = lowered.spec(device_, &es);
     std::vector<qsgpu_agg_state_t> parts;
     for (std::size_t p = 0; p < num_partitions; ++p) {
       qsgpu_agg_state_t s = nullptr;

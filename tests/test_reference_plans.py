@@ -1,0 +1,243 @@
+"""The reference's OWN plans for TPC-H Q1 / Q6 / Q3, lowered by the in-tree binding, give the engine's answers.
+
+tests/golden/reference_plans.json was written by tests/golden/make_plan_golden.cpp, a program linked against the
+unmodified reference: its parser read benchmarks/tpch/queries/{01,03,06}.sql, its optimizer and ExecutionGenerator planned
+them (catalog statistics of dbgen -s 0.01), and the serialization::QueryContext they produced -- aggregation states,
+predicates, scalar groups, LIP filters and deployments, join hash tables, sort configurations -- was lowered by
+quickstep_b200/host/intree/{ProtoLowering,QueryContextLowering}.hpp into the C ABI's descriptions.  Every operator of the
+DAG also described one work order in the reference's own serialized form (relation ids + QueryContext indices).
+
+This test is the "no plan changes" claim of BASELINE.json's north_star, executed: a small interpreter walks the DAG in
+operator order, gives each operator the lowered objects its work-order proto names, runs it with the oracle over dbgen's
+SF0.01 relations, and compares the final relation with what the unmodified engine printed for the same SQL
+(tests/golden/reference_engine_results.json): keys, counts and dates exact, double sums to 1e-9.
+
+What the real plans contain that hand-written descriptions missed (and the lowering now handles): Q6's
+`date '1994-01-01' + interval '1' year` arrives as an un-folded ScalarBinaryExpression over two literals (folded with
+the reference's own operations, FoldStaticScalar); Q3's 'BUILDING' is a VARCHAR(8) literal compared with a CHAR(10)
+attribute; Q1's AVGs are rewritten into SUM / COUNT with a SelectOperator dividing afterwards (ReuseAggregateExpressions).
+"""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tpch_data as D
+from backends import OracleBackend, agg_out_types
+from quickstep_b200 import capi as A
+from quickstep_b200.expr import ExprSet
+from quickstep_b200.table import Column, HostTable, np_dtype
+from ref_golden import ENGINE, close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLANS = {p["query"]: p for p in json.load(open(os.path.join(ROOT, "tests", "golden", "reference_plans.json")))["plans"]}
+_FIELD = re.compile(r"^\[quickstep\.serialization\.\w+\.(\w+)\]: (\S+)$")
+
+
+def work_order(op):
+    """The operator's serialized work order (protobuf text form) -> {field: value | [values]}."""
+    out = {}
+    for line in op["work_order"].split("\n"):
+        line = line.strip()
+        m = _FIELD.match(line)
+        if m:
+            k, v = m.group(1), m.group(2)
+            v = {"true": True, "false": False}.get(v, v)
+            if isinstance(v, str) and re.fullmatch(r"-?\d+", v):
+                v = int(v)
+            if k in out:
+                out[k] = (out[k] if isinstance(out[k], list) else [out[k]]) + [v]
+            else:
+                out[k] = v
+        elif line.startswith("work_order_type:"):
+            out["type"] = line.split(":")[1].strip()
+    for k in ("simple_selection", "join_key_attributes", "lip_filter_indexes"):
+        if k in out and not isinstance(out[k], list):
+            out[k] = [out[k]]
+    return out
+
+
+def expr_set(obj) -> ExprSet:
+    es = ExprSet()
+    for kind, op, typ, width, a, b, lit in obj["nodes"]:
+        n = A.qs_node()
+        n.kind, n.op, n.type, n.width, n.a, n.b = kind, op, typ, width, a, b
+        n.lit.i64 = int.from_bytes(bytes.fromhex(lit), "little", signed=True)
+        es.nodes.append(n)
+    es.pool = bytearray(bytes.fromhex(obj["pool"]))
+    return es
+
+
+class Interpreter:
+    def __init__(self, plan, tables):
+        self.plan, self.B = plan, OracleBackend()
+        self.schema = {r["id"]: [(t, w) for _n, t, w in r["attributes"]] for r in plan["relations"]}
+        self.rel = {r["id"]: tables[r["name"]] for r in plan["relations"] if not r["temporary"]}
+        self.lips = []
+        for f in plan["lip_filters"]:
+            assert f["kind"] == A.QS_LIP_BITVECTOR_EXACT
+            self.lips.append(self.B.make_lip(f["kind"], A.QS_INT if f["attribute_size"] == 4 else A.QS_LONG, f["min_value"], f["max_value"], 0, f["is_anti"]))
+        self.agg, self.built, self.trace = {}, {}, []
+
+    def destination(self, index):
+        return self.plan["insert_destinations"][index]["relation_id"]
+
+    def store(self, rel_id, cols):
+        schema = self.schema[rel_id]
+        assert len(cols) == len(schema), (rel_id, len(cols), len(schema))
+        self.rel[rel_id] = HostTable(f"r{rel_id}", [Column(f"c{i}", t, np.ascontiguousarray(c), w) for i, ((t, w), c) in enumerate(zip(schema, cols))])
+
+    def lip_refs(self, deployment, action):
+        if deployment < 0:
+            return None
+        return [(self.lips[f], attr) for f, attr in self.plan["lip_filter_deployments"][deployment][action]] or None
+
+    def run(self):
+        for op in self.plan["operators"]:
+            wo = work_order(op)
+            kind = wo.get("type")
+            self.trace.append((op["index"], op["name"], kind))
+            if kind == "SELECT":
+                src = self.rel[wo["relation_id"]]
+                if wo["predicate_index"] >= 0:
+                    pred = self.plan["predicates"][wo["predicate_index"]]
+                    es, root = expr_set(pred), pred["root"]
+                else:
+                    es, root = ExprSet(), -1
+                if wo["simple_projection"]:
+                    roots = [es.attr(a, *self.schema[wo["relation_id"]][a]) for a in wo["simple_selection"]]
+                else:
+                    # predicate and scalar group of one QueryContext go into one expression set (ExprSet::append in
+                    # host/ExprSet.hpp): the group's node indices shift by the predicate's length
+                    grp = self.plan["scalar_groups"][wo["selection_index"]]
+                    ges, base = expr_set(grp), len(es.nodes)
+                    for n in ges.nodes:
+                        if n.kind not in (A.QS_N_LITERAL, A.QS_N_ATTRIBUTE):
+                            n.a += base
+                            if n.kind == A.QS_N_BINARY:
+                                n.b += base
+                        elif n.kind == A.QS_N_LITERAL and n.type == A.QS_CHAR:
+                            n.lit.pool_offset += len(es.pool)
+                        es.nodes.append(n)
+                    es.pool += ges.pool
+                    roots = [r + base for r in grp["roots"]]
+                dest = self.destination(wo["insert_destination_index"])
+                out = self.B.select(src, es, root, self.lip_refs(wo["lip_deployment_index"], "probe"), roots, self.schema[dest])
+                self.store(dest, [c.data for c in out.columns])
+            elif kind == "BUILD_LIP_FILTER":
+                pred = self.plan["predicates"][wo["build_side_predicate_index"]]
+                self.B.build_lip(self.rel[wo["relation_id"]], expr_set(pred), pred["root"], self.lip_refs(wo["lip_deployment_index"], "probe"),
+                                 self.lip_refs(wo["lip_deployment_index"], "build"))
+            elif kind == "BUILD_HASH":
+                assert wo["build_predicate_index"] in (-1, 4294967295)         # kInvalidPredicateId
+                assert len(wo["join_key_attributes"]) == 1
+                self.built[wo["join_hash_table_index"]] = (wo["relation_id"], wo["join_key_attributes"][0])
+            elif kind == "HASH_JOIN":
+                join_type = {"HASH_INNER_JOIN": A.QS_JOIN_INNER, "HASH_SEMI_JOIN": A.QS_JOIN_LEFT_SEMI, "HASH_ANTI_JOIN": A.QS_JOIN_LEFT_ANTI,
+                             "HASH_OUTER_JOIN": A.QS_JOIN_LEFT_OUTER}[wo["hash_join_work_order_type"]]
+                build_rel, build_key = self.built[wo["join_hash_table_index"]]
+                assert build_rel == wo["build_relation_id"] and wo["residual_predicate_index"] == -1
+                grp = self.plan["scalar_groups"][wo["selection_index"]]
+                dest = self.destination(wo["insert_destination_index"])
+                probe = self.rel[wo["probe_relation_id"]]
+                # the build side may carry duplicate keys: size for every pair
+                out = self.B.hash_join(self.rel[build_rel], -1, build_key, probe, expr_set(grp), -1, wo["join_key_attributes"][0], join_type, -1,
+                                       grp["roots"], self.schema[dest], max(1, probe.n_rows * 4))
+                self.store(dest, [c.data for c in out.columns])
+            elif kind == "AGGREGATION":
+                st = self.plan["aggregation_states"][wo["aggr_state_index"]]
+                es = expr_set(st)
+                aggs = [tuple(a) for a in st["aggregates"]]
+                key_schema = [(es.nodes[r].type, es.nodes[r].width) for r in st["group_by_roots"]]
+                out = self.B.aggregate(self.rel[st["relation_id"]], es, st["predicate_root"], aggs, st["group_by_roots"], st["strategy"], key_schema,
+                                       self.lip_refs(wo["lip_deployment_index"], "probe"))
+                self.agg[wo["aggr_state_index"]] = (out, key_schema, agg_out_types(es, aggs))
+            elif kind == "FINALIZE_AGGREGATION":
+                out, key_schema, val_types = self.agg[wo["aggr_state_index"]]
+                dest = self.destination(wo["insert_destination_index"])
+                assert self.schema[dest] == [(t, w or np_dtype(t).itemsize) for t, w in key_schema] + list(val_types), (self.schema[dest], key_schema, val_types)
+                cols, off = [], 0
+                for t, w in key_schema:
+                    dt = np_dtype(t, w)
+                    cols.append(out.keys[:, off:off + dt.itemsize].copy().view(dt).reshape(-1))
+                    off += dt.itemsize
+                assert out.null_mask == 0
+                self.store(dest, cols + list(out.values))
+            elif kind == "SORT_RUN_GENERATION":
+                cfg = self.plan["sort_configs"][wo["sort_config_index"]]
+                src = self.rel[wo["relation_id"]]
+                keys = []
+                for k in cfg["keys"]:
+                    assert k["relation_id"] == wo["relation_id"]
+                    # NOT NULL keys here: null_first has nothing to order
+                    keys.append((k["attribute_id"], not k["ascending"]))
+                top = self.B.topk(src, keys, max(1, src.n_rows))
+                self.store(self.destination(wo["insert_destination_index"]), [c.data for c in top.columns])
+                self.sorted = self.destination(wo["insert_destination_index"])
+            elif op["name"] == "SortMergeRunOperator":
+                # one sorted run: merging it is the identity (the top-k LIMIT is applied when the result is compared)
+                self.store(op["output_relation"], [c.data for c in self.rel[self.sorted].columns])
+            else:
+                assert kind in ("DESTROY_AGGREGATION_STATE", "DESTROY_HASH", None), (op["name"], kind)
+        result = max(i for i in self.rel if self.plan["relations"][[r["id"] for r in self.plan["relations"]].index(i)]["temporary"])
+        return self.rel[result]
+
+
+@pytest.fixture(scope="module")
+def tables(oracle):
+    return D.golden_tables()
+
+
+def test_plans_are_the_optimizers(tables):
+    """Shapes the rest of the repository assumes about the reference's plans, now read off the optimizer."""
+    q1, q6, q3 = PLANS["q1"], PLANS["q6"], PLANS["q3"]
+    names = lambda p: [o["name"] for o in p["operators"] if "DropTable" not in o["name"]]
+    assert names(q6) == ["AggregationOperator", "FinalizeAggregationOperator", "DestroyAggregationStateOperator"]
+    assert names(q1) == ["AggregationOperator", "FinalizeAggregationOperator", "DestroyAggregationStateOperator", "SelectOperator",
+                         "SortRunGenerationOperator", "SortMergeRunOperator"]
+    assert names(q3) == ["SelectOperator", "BuildLIPFilterOperator", "SelectOperator", "BuildHashOperator", "HashJoinOperator", "DestroyHashOperator",
+                         "AggregationOperator", "FinalizeAggregationOperator", "DestroyAggregationStateOperator", "SortRunGenerationOperator",
+                         "SortMergeRunOperator", "SelectOperator"]
+    # Q6: no GROUP BY -> single state; Q1: (CHAR(1), CHAR(1)) keys -> ThreadPrivateCompactKey; Q3: SeparateChaining
+    assert q6["aggregation_states"][0]["strategy"] == A.QS_AGG_SINGLE_STATE
+    assert q1["aggregation_states"][0]["hash_table_impl_type"] == 4 and q1["aggregation_states"][0]["strategy"] == A.QS_AGG_COMPACT_KEY
+    assert q3["aggregation_states"][0]["strategy"] == A.QS_AGG_SEPARATE_CHAINING
+    # Q1's three AVGs became SUM / COUNT(*): five SUMs (the fifth is l_discount's) and one COUNT(*)
+    assert [a[0] for a in q1["aggregation_states"][0]["aggregates"]] == [A.QS_AGG_SUM] * 5 + [A.QS_AGG_COUNT]
+    # Q3: one exact filter over c_custkey's range, built from customer, probed by the orders select on o_custkey
+    assert q3["lip_filters"] == [{"kind": A.QS_LIP_BITVECTOR_EXACT, "min_value": 1, "max_value": 1500, "attribute_size": 4, "is_anti": False}]
+    assert q3["lip_filter_deployments"] == [{"build": [[0, 0]], "probe": []}, {"build": [], "probe": [[0, 1]]}]
+    # Q6's interval arithmetic was folded into one DATE literal by the lowering: no node of an unsupported type is left
+    lits = [n for n in q6["aggregation_states"][0]["nodes"] if n[0] == A.QS_N_LITERAL and n[2] == A.QS_DATE]
+    assert sorted(int.from_bytes(bytes.fromhex(n[6])[:4], "little") for n in lits) == [1994, 1995]
+
+
+def test_q6_plan_gives_the_engines_answer(tables):
+    out = Interpreter(PLANS["q6"], tables).run()
+    want = ENGINE["sf0.01"]["q6"]["rows"]
+    assert out.n_rows == 1 and close(out.columns[0].data[0], float(want[0][0])), (out.columns[0].data, want)
+
+
+def test_q1_plan_gives_the_engines_answer(tables):
+    out = Interpreter(PLANS["q1"], tables).run()
+    want = ENGINE["sf0.01"]["q1"]["rows"]
+    assert out.n_rows == len(want) == 4 and len(out.columns) == 10
+    for i, w in enumerate(want):
+        assert out.columns[0].data[i].decode() == w[0] and out.columns[1].data[i].decode() == w[1]
+        for j in range(2, 9):
+            assert close(out.columns[j].data[i], float(w[j])), (i, j, out.columns[j].data[i], w[j])
+        assert int(out.columns[9].data[i]) == int(w[9])
+
+
+def test_q3_plan_gives_the_engines_answer(tables):
+    it = Interpreter(PLANS["q3"], tables)
+    out = it.run()
+    want = ENGINE["sf0.01"]["q3"]["rows"]
+    assert out.n_rows >= len(want) == 10 and len(out.columns) == 4
+    for i, w in enumerate(want):            # LIMIT 10 of the SortMergeRunOperator
+        d = out.columns[2].data[i]
+        assert int(out.columns[0].data[i]) == int(w[0]) and "%04d-%02d-%02d" % (d["year"], d["month"], d["day"]) == w[2]
+        assert int(out.columns[3].data[i]) == int(w[3])
+        assert close(out.columns[1].data[i], float(w[1])), (i, out.columns[1].data[i], w[1])
