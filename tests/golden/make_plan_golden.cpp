@@ -129,17 +129,21 @@ void EmitRelations(FILE *out, const CatalogDatabase &db) {
   std::fprintf(out, "]");
 }
 
-void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_query) {
+// `sf`: the scale factor whose `\\analyze` statistics the catalog carries (row counts, distinct counts and key ranges grow
+// with it; dbgen's order keys are sparse: 8 of every 32).
+void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_query, double sf = 0.01) {
   // a fresh catalog per query: relation ids of the temporaries start from the same point every time
   CatalogDatabase db(nullptr, "default");
-  AddRelation(&db, "lineitem", 60175,
-              {{"l_orderkey", kInt, 0, 15000, 1, 60000}, {"l_quantity", kDouble, 0, 50, 0, 0}, {"l_extendedprice", kDouble, 0, 35921, 0, 0},
+  const std::int64_t n_orders = static_cast<std::int64_t>(1500000 * sf), n_cust = static_cast<std::int64_t>(150000 * sf);
+  const std::int64_t n_lineitem = sf == 0.01 ? 60175 : static_cast<std::int64_t>(6000000 * sf), max_okey = n_orders * 4;
+  AddRelation(&db, "lineitem", n_lineitem,
+              {{"l_orderkey", kInt, 0, n_orders, 1, max_okey}, {"l_quantity", kDouble, 0, 50, 0, 0}, {"l_extendedprice", kDouble, 0, 35921, 0, 0},
                {"l_discount", kDouble, 0, 11, 0, 0}, {"l_tax", kDouble, 0, 9, 0, 0}, {"l_returnflag", kChar, 1, 3, 0, 0},
                {"l_linestatus", kChar, 1, 2, 0, 0}, {"l_shipdate", kDate, 0, 2518, 0, 0}});
-  AddRelation(&db, "orders", 15000,
-              {{"o_orderkey", kInt, 0, 15000, 1, 60000}, {"o_custkey", kInt, 0, 1000, 1, 1499}, {"o_orderdate", kDate, 0, 2401, 0, 0},
+  AddRelation(&db, "orders", n_orders,
+              {{"o_orderkey", kInt, 0, n_orders, 1, max_okey}, {"o_custkey", kInt, 0, n_cust * 2 / 3, 1, n_cust - 1}, {"o_orderdate", kDate, 0, 2401, 0, 0},
                {"o_shippriority", kInt, 0, 1, 0, 0}});
-  AddRelation(&db, "customer", 1500, {{"c_custkey", kInt, 0, 1500, 1, 1500}, {"c_mktsegment", kChar, 10, 5, 0, 0}});
+  AddRelation(&db, "customer", n_cust, {{"c_custkey", kInt, 0, n_cust, 1, n_cust}, {"c_mktsegment", kChar, 10, 5, 0, 0}});
 
   SqlParserWrapper parser;
   parser.feedNextBuffer(new std::string(sql));
@@ -153,7 +157,7 @@ void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_q
   const serialization::QueryContext &qc = handle.getQueryContextProto();
   const gpu::AttributeTypes types = AllTypes(db);
 
-  std::fprintf(out, "%s\n {\"query\": \"%s\",\n  ", first_query ? "" : ",", name);
+  std::fprintf(out, "%s\n {\"query\": \"%s\", \"statistics_of_sf\": %g,\n  ", first_query ? "" : ",", name, sf);
   EmitRelations(out, db);
 
   // ---- the operator DAG, as the Foreman will see it (query_execution/QueryManagerBase.cpp)
@@ -331,6 +335,12 @@ int main(int argc, char **argv) {
   PlanQuery(out, "q1", ReadFile(ref + "/benchmarks/tpch/queries/01.sql"), true);
   PlanQuery(out, "q6", ReadFile(ref + "/benchmarks/tpch/queries/06.sql"), false);
   PlanQuery(out, "q3", ReadFile(ref + "/benchmarks/tpch/queries/03.sql"), false);
+  // the same SQL planned over the statistics of the benchmarked scale factors: what the hand-built operator DAGs of
+  // quickstep_b200/host/TpchPlans.cpp (bench.py's queries) have to look like
+  PlanQuery(out, "q3_sf10", ReadFile(ref + "/benchmarks/tpch/queries/03.sql"), false, 10.0);
+  PlanQuery(out, "q3_sf100", ReadFile(ref + "/benchmarks/tpch/queries/03.sql"), false, 100.0);
+  PlanQuery(out, "q1_sf100", ReadFile(ref + "/benchmarks/tpch/queries/01.sql"), false, 100.0);
+  PlanQuery(out, "q6_sf100", ReadFile(ref + "/benchmarks/tpch/queries/06.sql"), false, 100.0);
   std::fprintf(out, "\n ]}\n");
   std::fclose(out);
   return 0;

@@ -79,7 +79,7 @@ class Interpreter:
         for f in plan["lip_filters"]:
             assert f["kind"] == A.QS_LIP_BITVECTOR_EXACT
             self.lips.append(self.B.make_lip(f["kind"], A.QS_INT if f["attribute_size"] == 4 else A.QS_LONG, f["min_value"], f["max_value"], 0, f["is_anti"]))
-        self.agg, self.built, self.trace = {}, {}, []
+        self.agg, self.built, self.trace, self.cardinality = {}, {}, [], {}
 
     def destination(self, index):
         return self.plan["insert_destinations"][index]["relation_id"]
@@ -94,8 +94,28 @@ class Interpreter:
             return None
         return [(self.lips[f], attr) for f, attr in self.plan["lip_filter_deployments"][deployment][action]] or None
 
+    def order(self):
+        """The DAG's edges decide who runs first (a LIP filter's builder precedes its probers whatever their indices):
+        Kahn's algorithm, lowest operator index first among the ready ones."""
+        ops = self.plan["operators"]
+        waits = {o["index"]: 0 for o in ops}
+        for o in ops:
+            for consumer, _breaking in o["dependents"]:
+                waits[consumer] += 1
+        ready, out = sorted(i for i, w in waits.items() if w == 0), []
+        while ready:
+            i = ready.pop(0)
+            out.append(ops[i])
+            for consumer, _breaking in ops[i]["dependents"]:
+                waits[consumer] -= 1
+                if waits[consumer] == 0:
+                    ready.append(consumer)
+                    ready.sort()
+        assert len(out) == len(ops)
+        return out
+
     def run(self):
-        for op in self.plan["operators"]:
+        for op in self.order():
             wo = work_order(op)
             kind = wo.get("type")
             self.trace.append((op["index"], op["name"], kind))
@@ -134,6 +154,10 @@ class Interpreter:
                 assert wo["build_predicate_index"] in (-1, 4294967295)         # kInvalidPredicateId
                 assert len(wo["join_key_attributes"]) == 1
                 self.built[wo["join_hash_table_index"]] = (wo["relation_id"], wo["join_key_attributes"][0])
+                build_refs = self.lip_refs(wo["lip_deployment_index"], "build")
+                if build_refs:      # BuildHashWorkOrder::execute also inserts the build keys into its LIP filters (BuildHashOperator.cpp:186-197)
+                    self.B.build_lip(self.rel[wo["relation_id"]], None, -1, None, build_refs)
+                self.cardinality["build_rows"] = self.rel[wo["relation_id"]].n_rows
             elif kind == "HASH_JOIN":
                 join_type = {"HASH_INNER_JOIN": A.QS_JOIN_INNER, "HASH_SEMI_JOIN": A.QS_JOIN_LEFT_SEMI, "HASH_ANTI_JOIN": A.QS_JOIN_LEFT_ANTI,
                              "HASH_OUTER_JOIN": A.QS_JOIN_LEFT_OUTER}[wo["hash_join_work_order_type"]]
@@ -146,6 +170,7 @@ class Interpreter:
                 out = self.B.hash_join(self.rel[build_rel], -1, build_key, probe, expr_set(grp), -1, wo["join_key_attributes"][0], join_type, -1,
                                        grp["roots"], self.schema[dest], max(1, probe.n_rows * 4))
                 self.store(dest, [c.data for c in out.columns])
+                self.cardinality.update(probe_rows=probe.n_rows, join_rows=out.n_rows)
             elif kind == "AGGREGATION":
                 st = self.plan["aggregation_states"][wo["aggr_state_index"]]
                 es = expr_set(st)
@@ -154,6 +179,7 @@ class Interpreter:
                 out = self.B.aggregate(self.rel[st["relation_id"]], es, st["predicate_root"], aggs, st["group_by_roots"], st["strategy"], key_schema,
                                        self.lip_refs(wo["lip_deployment_index"], "probe"))
                 self.agg[wo["aggr_state_index"]] = (out, key_schema, agg_out_types(es, aggs))
+                self.cardinality["groups"] = out.n_groups
             elif kind == "FINALIZE_AGGREGATION":
                 out, key_schema, val_types = self.agg[wo["aggr_state_index"]]
                 dest = self.destination(wo["insert_destination_index"])
@@ -241,3 +267,63 @@ def test_q3_plan_gives_the_engines_answer(tables):
         assert int(out.columns[0].data[i]) == int(w[0]) and "%04d-%02d-%02d" % (d["year"], d["month"], d["day"]) == w[2]
         assert int(out.columns[3].data[i]) == int(w[3])
         assert close(out.columns[1].data[i], float(w[1])), (i, out.columns[1].data[i], w[1])
+
+
+@pytest.mark.parametrize("which", ["q3_sf10", "q3_sf100"])
+def test_q3_plan_of_the_benchmarked_scale_is_the_hand_built_dag(tables, which):
+    """With SF10 / SF100 statistics the optimizer adds the second LIP filter -- o_orderkey's range, built by the
+    BuildHashOperator, probed by the lineitem SelectOperator -- which is the DAG quickstep_b200/tpch.py's Q3Plan and
+    host/TpchPlans.cpp hand-build for bench.py.  The optimizer's plan (its filters sized for the larger key ranges) and the
+    hand-built one run over the same SF0.01 relations: same rows through every operator, same answer, the engine's."""
+    import oracle_tpch as OT
+    plan = PLANS[which]
+    assert [f["max_value"] for f in plan["lip_filters"]] == [{"q3_sf10": 1500000, "q3_sf100": 15000000}[which], {"q3_sf10": 60000000, "q3_sf100": 600000000}[which]]
+    assert plan["lip_filter_deployments"] == [{"build": [[0, 0]], "probe": []}, {"build": [[1, 0]], "probe": []}, {"build": [], "probe": [[1, 0]]},
+                                              {"build": [], "probe": [[0, 1]]}]
+    if which == "q3_sf100":       # a 600 M-bit filter is 75 MB of words on the host: the SF10 plan is the one executed
+        return
+    it = Interpreter(plan, tables)
+    names = [o["name"] for o in it.order() if "DropTable" not in o["name"] and "Destroy" not in o["name"]]
+    assert names == ["BuildLIPFilterOperator", "SelectOperator", "BuildHashOperator", "SelectOperator", "HashJoinOperator", "AggregationOperator",
+                     "FinalizeAggregationOperator", "SortRunGenerationOperator", "SortMergeRunOperator", "SelectOperator"]
+    out = it.run()
+    info = {}
+    hand = OT.q3(tables, D.q3_stats(tables), info=info)
+    assert it.cardinality == dict(build_rows=info["t2_rows"], probe_rows=info["t0_rows"], join_rows=info["t4_rows"], groups=info["groups"])
+    want = ENGINE["sf0.01"]["q3"]["rows"]
+    for i, (h, w) in enumerate(zip(hand, want)):
+        d = out.columns[2].data[i]
+        assert int(out.columns[0].data[i]) == h[0] == int(w[0]) and (int(d["year"]), int(d["month"]), int(d["day"])) == h[2]
+        assert int(out.columns[3].data[i]) == h[3] == int(w[3])
+        assert out.columns[1].data[i] == h[1] and close(h[1], float(w[1]))        # the two plans add the same values in the same order
+
+
+def test_q1_q6_plans_do_not_depend_on_the_scale(tables):
+    for q in ("q1", "q6"):
+        small, big = PLANS[q], PLANS[q + "_sf100"]
+        for key in ("aggregation_states", "predicates", "scalar_groups", "sort_configs"):
+            assert small[key] == big[key], (q, key)
+        assert [o["name"] for o in small["operators"]] == [o["name"] for o in big["operators"]]
+
+
+def test_hand_built_q1_q6_trees_are_the_optimizers(tables):
+    """quickstep_b200/tpch.py's Q1Plan / Q6Plan (what bench.py's operator DAGs evaluate) against the optimizer's lowered
+    aggregation states: same aggregate functions in the same order, same strategy, and -- row by row over dbgen's
+    lineitem -- the same predicate bits and the same argument values."""
+    import qs_oracle as O
+    from quickstep_b200 import tpch as T
+    li = tables["lineitem"]
+    for q, hand in (("q1", T.Q1Plan()), ("q6", T.Q6Plan())):
+        st = PLANS[q]["aggregation_states"][0]
+        es = expr_set(st)
+        assert [a[0] for a in st["aggregates"]] == [f for f, _r in hand.aggregates]
+        assert len(st["group_by_roots"]) == len(getattr(hand, "group_by", []))
+        _n, got = O.predicate(es, st["predicate_root"], li)
+        _n, want = O.predicate(hand.es, hand.pred, li)
+        assert (got == want).all()
+        for (f, r), (_f, hr) in zip(st["aggregates"], hand.aggregates):
+            if r >= 0:
+                a, b = O.scalar(es, r, li), O.scalar(hand.es, hr, li)
+                assert a.dtype == b.dtype and (a.view(np.uint8) == b.view(np.uint8)).all(), (q, f, r)
+        for r, hr in zip(st["group_by_roots"], getattr(hand, "group_by", [])):
+            assert es.nodes[r].a == hand.es.nodes[hr].a
