@@ -113,6 +113,11 @@ class GpuSelectWorkOrder : public WorkOrder {
                      qsgpu_relation_t output)
       : WorkOrder(query_id), input_relation_(input_relation), input_(input), predicate_(predicate), selection_(selection),
         output_(output) {}
+  // simple projection (SelectOperator.hpp:149-187): attribute ids instead of a scalar group
+  GpuSelectWorkOrder(const std::size_t query_id, const CatalogRelationSchema &input_relation, const DeviceRows &input,
+                     const Predicate *predicate, const std::vector<attribute_id> &simple_selection, qsgpu_relation_t output)
+      : WorkOrder(query_id), input_relation_(input_relation), input_(input), predicate_(predicate), selection_(nullptr),
+        simple_selection_(simple_selection), output_(output) {}
   ~GpuSelectWorkOrder() override {}
 
   void execute() override {
@@ -121,7 +126,19 @@ class GpuSelectWorkOrder : public WorkOrder {
     ExprBuilder b;
     const int pred = predicate_ ? LowerPredicate(predicate_->getProto(), types, &b) : -1;
     std::vector<std::int32_t> roots;
-    for (const std::unique_ptr<const Scalar> &s : *selection_) roots.push_back(LowerScalar(s->getProto(), types, &b));
+    if (selection_) {
+      for (const std::unique_ptr<const Scalar> &s : *selection_) roots.push_back(LowerScalar(s->getProto(), types, &b));
+    } else {
+      const std::vector<qs_attr> schema = SchemaOf(input_relation_);
+      for (const attribute_id a : simple_selection_) {      // a bare attribute node is the selectSimple path (StorageBlock.cpp:390-398)
+        qs_node n{};
+        n.kind = QS_N_ATTRIBUTE;
+        n.type = schema[static_cast<std::size_t>(a)].type;
+        n.width = schema[static_cast<std::size_t>(a)].width;
+        n.a = a;
+        roots.push_back(b.add(n));
+      }
+    }
     const qs_expr_set es = b.view();
     qs_scan scan{};
     scan.input = input_.relation;
@@ -137,6 +154,7 @@ class GpuSelectWorkOrder : public WorkOrder {
   const DeviceRows input_;
   const Predicate *predicate_;
   const std::vector<std::unique_ptr<const Scalar>> *selection_;
+  const std::vector<attribute_id> simple_selection_;
   qsgpu_relation_t output_;
 };
 
@@ -167,18 +185,20 @@ class GpuAggregationOperator : public RelationalOperator {
       }
       return true;
     }
-    // streamed input: one work order per batch of blocks fed so far (their rows are contiguous in the device image)
+    // streamed input: one work order per batch of blocks fed so far (their rows are contiguous in the device image of the
+    // temporary relation; noteDeviceRows() is told how many rows that image holds, and the last batch runs to its end)
     if (!fed_.empty()) {
       DeviceRows rows;
       rows.relation = device_input_;
       rows.row_begin = fed_row_begin_;
-      rows.row_end = fed_row_end_;
+      rows.row_end = done_feeding_input_relation_ ? UINT64_MAX : fed_row_end_;
       container->addNormalWorkOrder(new GpuAggregationWorkOrder(query_id_, 0, rows, device_state_), op_index_);
       fed_.clear();
       fed_row_begin_ = fed_row_end_;
     }
     return done_feeding_input_relation_;
   }
+  void noteDeviceRows(const std::uint64_t rows_so_far) { fed_row_end_ = rows_so_far; }
 
   bool getAllWorkOrderProtos(WorkOrderProtosContainer *container) override {
     LOG(FATAL) << "GPU work orders are single-node: -DENABLE_DISTRIBUTED builds keep the CPU operators";
@@ -186,7 +206,7 @@ class GpuAggregationOperator : public RelationalOperator {
   }
 
   void feedInputBlock(const block_id input_block_id, const relation_id input_relation_id, const partition_id part_id) override {
-    fed_.push_back(input_block_id);
+    if (input_relation_id == input_relation_.getID()) fed_.push_back(input_block_id);
   }
 
  private:
@@ -197,6 +217,89 @@ class GpuAggregationOperator : public RelationalOperator {
   qsgpu_relation_t device_input_;
   bool started_;
   std::vector<block_id> fed_;
+  std::uint64_t fed_row_begin_ = 0, fed_row_end_ = 0;
+};
+
+// SelectOperator (relational_operators/SelectOperator.hpp:66-260), both constructors: a scalar group or a simple
+// projection.  Stored input: ONE coarse work order over the relation's device image; streamed input: one per batch of
+// blocks fed since the last call (their rows are contiguous in the device image of the temporary relation).
+class GpuSelectOperator : public RelationalOperator {
+ public:
+  GpuSelectOperator(const std::size_t query_id, const CatalogRelation &input_relation, const bool has_repartition,
+                    const CatalogRelation &output_relation, const QueryContext::insert_destination_id output_destination_index,
+                    const QueryContext::predicate_id predicate_index, const QueryContext::scalar_group_id selection_index,
+                    const bool input_relation_is_stored, qsgpu_relation_t device_input, qsgpu_relation_t device_output)
+      : RelationalOperator(query_id, input_relation.getNumPartitions(), has_repartition, output_relation.getNumPartitions()),
+        input_relation_(input_relation), output_relation_(output_relation), output_destination_index_(output_destination_index),
+        predicate_index_(predicate_index), selection_index_(selection_index), simple_projection_(false),
+        input_relation_is_stored_(input_relation_is_stored), device_input_(device_input), device_output_(device_output),
+        started_(false) {}
+  GpuSelectOperator(const std::size_t query_id, const CatalogRelation &input_relation, const bool has_repartition,
+                    const CatalogRelation &output_relation, const QueryContext::insert_destination_id output_destination_index,
+                    const QueryContext::predicate_id predicate_index, std::vector<attribute_id> &&selection,
+                    const bool input_relation_is_stored, qsgpu_relation_t device_input, qsgpu_relation_t device_output)
+      : RelationalOperator(query_id, input_relation.getNumPartitions(), has_repartition, output_relation.getNumPartitions()),
+        input_relation_(input_relation), output_relation_(output_relation), output_destination_index_(output_destination_index),
+        predicate_index_(predicate_index), selection_index_(QueryContext::kInvalidScalarGroupId),
+        simple_selection_(std::move(selection)), simple_projection_(true), input_relation_is_stored_(input_relation_is_stored),
+        device_input_(device_input), device_output_(device_output), started_(false) {}
+  ~GpuSelectOperator() override {}
+
+  OperatorType getOperatorType() const override { return kSelect; }
+  std::string getName() const override { return "GpuSelectOperator"; }
+
+  bool getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context, StorageManager *storage_manager,
+                        const tmb::client_id scheduler_client_id, tmb::MessageBus *bus) override {
+    const Predicate *predicate = query_context->getPredicate(predicate_index_);
+    DeviceRows rows;
+    rows.relation = device_input_;
+    if (input_relation_is_stored_) {
+      if (started_) return true;
+      started_ = true;
+    } else {
+      if (fed_row_end_ == fed_row_begin_ && !fresh_blocks_) return done_feeding_input_relation_;
+      rows.row_begin = fed_row_begin_;
+      rows.row_end = done_feeding_input_relation_ ? UINT64_MAX : fed_row_end_;
+      fed_row_begin_ = fed_row_end_;
+      fresh_blocks_ = false;
+    }
+    container->addNormalWorkOrder(
+        simple_projection_
+            ? new GpuSelectWorkOrder(query_id_, input_relation_, rows, predicate, simple_selection_, device_output_)
+            : new GpuSelectWorkOrder(query_id_, input_relation_, rows, predicate, &query_context->getScalarGroup(selection_index_),
+                                     device_output_),
+        op_index_);
+    return input_relation_is_stored_ || done_feeding_input_relation_;
+  }
+
+  bool getAllWorkOrderProtos(WorkOrderProtosContainer *container) override {
+    LOG(FATAL) << "GPU work orders are single-node: -DENABLE_DISTRIBUTED builds keep the CPU operators";
+    return true;
+  }
+
+  // The producer's rows of this block are already in the temporary relation's device image; `rows_so_far` of that image
+  // is what the binding's StorageManager hook reports (host/Operators.cpp InputFeed::take is the stand-in's version).
+  void feedInputBlock(const block_id input_block_id, const relation_id input_relation_id, const partition_id part_id) override {
+    if (input_relation_id != input_relation_.getID()) return;
+    fresh_blocks_ = true;
+  }
+  void noteDeviceRows(const std::uint64_t rows_so_far) { fed_row_end_ = rows_so_far; }
+
+  QueryContext::insert_destination_id getInsertDestinationID() const override { return output_destination_index_; }
+  const relation_id getOutputRelationID() const override { return output_relation_.getID(); }
+
+ private:
+  const CatalogRelation &input_relation_;
+  const CatalogRelation &output_relation_;
+  const QueryContext::insert_destination_id output_destination_index_;
+  const QueryContext::predicate_id predicate_index_;
+  const QueryContext::scalar_group_id selection_index_;
+  const std::vector<attribute_id> simple_selection_;
+  const bool simple_projection_;
+  const bool input_relation_is_stored_;
+  qsgpu_relation_t device_input_, device_output_;
+  bool started_;
+  bool fresh_blocks_ = false;
   std::uint64_t fed_row_begin_ = 0, fed_row_end_ = 0;
 };
 
