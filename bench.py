@@ -417,6 +417,12 @@ def main():
             per_row = tj.get("q1_scan_agg_dram_bytes_per_row")
             roof_q1["traffic"] = per_row * my_rows if per_row else None
             roof_q1["traffic_source"] = tj.get("source")
+            per_row6 = tj.get("q6_scan_agg_dram_bytes_per_row")
+            roof_q6["traffic"] = per_row6 * my_rows if per_row6 else None
+            roof_q6["traffic_source"] = tj.get("source")
+            per_row3 = tj.get("q3_lineitem_select_dram_bytes_per_row")
+            roof_q3["traffic"] = per_row3 * my_rows if per_row3 else None
+            roof_q3["traffic_source"] = tj.get("q3_source")
         except Exception:
             pass
 
