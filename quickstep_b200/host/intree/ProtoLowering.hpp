@@ -203,6 +203,7 @@ inline int LowerScalar(const serialization::Scalar &s, const AttributeTypes &typ
     case serialization::Scalar::ATTRIBUTE: {
       const qs_attr a = types.lookup(s.GetExtension(serialization::ScalarAttribute::relation_id),
                                      s.GetExtension(serialization::ScalarAttribute::attribute_id));
+      if (a.type == QS_VARCHAR) LOG(FATAL) << "GPU path: VARCHAR attributes are not staged on the device";
       n.kind = QS_N_ATTRIBUTE;
       n.type = a.type;
       n.width = a.width;

@@ -9,8 +9,10 @@
 // in-tree binding (quickstep_b200/host/intree/ProtoLowering.hpp, QueryContextLowering.hpp) into the C ABI's descriptions.
 // The operator DAG is written next to it.  tests/test_reference_plans.py executes the lowered plans with the oracle over
 // dbgen's SF0.01 relations and must get the answers the engine itself printed for the same SQL.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -324,9 +326,119 @@ std::string ReadFile(const std::string &path) {
   return ss.str();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Coverage mode (tools/tpch_plan_coverage.py): ONE query of benchmarks/tpch/queries planned over the full TPC-H catalog
+// (benchmarks/tpch/create.sql's eight relations, all attributes) with the statistics of scale factor `sf`; prints the
+// operator list, then lowers every entry of the QueryContext.  What the device path does not take (LIKE, CASE, SUBSTRING,
+// EXTRACT, VARCHAR attributes, DISTINCT aggregates, ...) ends in the binding's LOG(FATAL) naming the reason -- such an
+// operator keeps its CPU work orders -- and the driver script records it.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FullAttr {
+  const char *name;
+  TypeID type;
+  std::size_t length;
+  int key_of;        // 0: not an integer key; otherwise index into kRows below of the relation whose key range it has
+};
+
+int Coverage(const std::string &ref, const std::string &query_file, double sf) {
+  // rows at SF1: region, nation, supplier, customer, part, partsupp, orders, lineitem
+  const double kRowsSf1[9] = {0, 5, 25, 10000, 150000, 200000, 800000, 1500000, 6000000};
+  auto rows = [&](int rel) { return rel <= 2 ? static_cast<std::int64_t>(kRowsSf1[rel]) : static_cast<std::int64_t>(kRowsSf1[rel] * sf); };
+  struct Rel { const char *name; int rows_of; std::vector<FullAttr> attrs; };
+  const std::vector<Rel> schema = {
+      {"region", 1, {{"r_regionkey", kInt, 0, 1}, {"r_name", kChar, 25, 0}, {"r_comment", kVarChar, 152, 0}}},
+      {"nation", 2, {{"n_nationkey", kInt, 0, 2}, {"n_name", kChar, 25, 0}, {"n_regionkey", kInt, 0, 1}, {"n_comment", kVarChar, 152, 0}}},
+      {"supplier", 3, {{"s_suppkey", kInt, 0, 3}, {"s_name", kChar, 25, 0}, {"s_address", kVarChar, 40, 0}, {"s_nationkey", kInt, 0, 2},
+                       {"s_phone", kChar, 15, 0}, {"s_acctbal", kDouble, 0, 0}, {"s_comment", kVarChar, 101, 0}}},
+      {"customer", 4, {{"c_custkey", kInt, 0, 4}, {"c_name", kVarChar, 25, 0}, {"c_address", kVarChar, 40, 0}, {"c_nationkey", kInt, 0, 2},
+                       {"c_phone", kChar, 15, 0}, {"c_acctbal", kDouble, 0, 0}, {"c_mktsegment", kChar, 10, 0}, {"c_comment", kVarChar, 117, 0}}},
+      {"part", 5, {{"p_partkey", kInt, 0, 5}, {"p_name", kVarChar, 55, 0}, {"p_mfgr", kChar, 25, 0}, {"p_brand", kChar, 10, 0}, {"p_type", kVarChar, 25, 0},
+                   {"p_size", kInt, 0, 0}, {"p_container", kChar, 10, 0}, {"p_retailprice", kDouble, 0, 0}, {"p_comment", kVarChar, 23, 0}}},
+      {"partsupp", 6, {{"ps_partkey", kInt, 0, 5}, {"ps_suppkey", kInt, 0, 3}, {"ps_availqty", kInt, 0, 0}, {"ps_supplycost", kDouble, 0, 0},
+                       {"ps_comment", kVarChar, 199, 0}}},
+      {"orders", 7, {{"o_orderkey", kInt, 0, 7}, {"o_custkey", kInt, 0, 4}, {"o_orderstatus", kChar, 1, 0}, {"o_totalprice", kDouble, 0, 0},
+                     {"o_orderdate", kDate, 0, 0}, {"o_orderpriority", kChar, 15, 0}, {"o_clerk", kChar, 15, 0}, {"o_shippriority", kInt, 0, 0},
+                     {"o_comment", kVarChar, 79, 0}}},
+      {"lineitem", 8, {{"l_orderkey", kInt, 0, 7}, {"l_partkey", kInt, 0, 5}, {"l_suppkey", kInt, 0, 3}, {"l_linenumber", kInt, 0, 0},
+                       {"l_quantity", kDouble, 0, 0}, {"l_extendedprice", kDouble, 0, 0}, {"l_discount", kDouble, 0, 0}, {"l_tax", kDouble, 0, 0},
+                       {"l_returnflag", kChar, 1, 0}, {"l_linestatus", kChar, 1, 0}, {"l_shipdate", kDate, 0, 0}, {"l_commitdate", kDate, 0, 0},
+                       {"l_receiptdate", kDate, 0, 0}, {"l_shipinstruct", kChar, 25, 0}, {"l_shipmode", kChar, 10, 0}, {"l_comment", kVarChar, 44, 0}}}};
+  CatalogDatabase db(nullptr, "default");
+  for (const Rel &r : schema) {
+    CatalogRelation *rel = new CatalogRelation(&db, r.name);
+    for (const FullAttr &a : r.attrs) {
+      const Type &t = a.length ? TypeFactory::GetType(a.type, a.length, false) : TypeFactory::GetType(a.type, false);
+      rel->addAttribute(new CatalogAttribute(rel, a.name, t));
+    }
+    db.addRelation(rel);
+    rel->addBlock(BlockIdUtil::GetBlockId(1, 1 + rel->getID()));
+    CatalogRelationStatistics *stats = rel->getStatisticsMutable();
+    stats->setExactness(true);
+    stats->setNumTuples(rows(r.rows_of));
+    for (std::size_t i = 0; i < r.attrs.size(); ++i) {
+      if (!r.attrs[i].key_of) continue;
+      const std::int64_t n = rows(r.attrs[i].key_of);
+      const std::int64_t max_key = r.attrs[i].key_of == 7 ? n * 4 : n;            // dbgen's order keys are sparse
+      stats->setNumDistinctValues(static_cast<attribute_id>(i), std::min<std::int64_t>(n, rows(r.rows_of)));
+      stats->setMinValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? 0 : 1)));
+      stats->setMaxValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? n - 1 : max_key)));
+    }
+  }
+  SqlParserWrapper parser;
+  parser.feedNextBuffer(new std::string(ReadFile(ref + "/benchmarks/tpch/queries/" + query_file)));
+  ParseResult result = parser.getNextStatement();
+  CHECK(result.condition == ParseResult::kSuccess) << result.error_message;
+  QueryHandle handle(1, 0);
+  optimizer::OptimizerContext context;
+  optimizer::Optimizer optimizer;
+  optimizer.generateQueryHandle(*result.parsed_statement, &db, &context, &handle);
+  const serialization::QueryContext &qc = handle.getQueryContextProto();
+  const DAG<RelationalOperator, bool> &dag = handle.getQueryPlanMutable()->getQueryPlanDAG();
+  std::printf("operators:");
+  for (std::size_t i = 0; i < dag.size(); ++i) std::printf(" %s", dag.getNodePayload(i).getName().c_str());
+  std::printf("\ncounts: aggregation_states=%d predicates=%d scalar_groups=%d lip_filters=%d join_hash_tables=%d sort_configs=%d\n",
+              qc.aggregation_states_size(), qc.predicates_size(), qc.scalar_groups_size(), qc.lip_filters_size(), qc.join_hash_tables_size(),
+              qc.sort_configs_size());
+  std::fflush(stdout);
+  const gpu::AttributeTypes types = AllTypes(db);
+  for (int i = 0; i < qc.predicates_size(); ++i) {
+    gpu::ExprBuilder b;
+    gpu::LowerPredicate(qc.predicates(i), types, &b);
+  }
+  std::printf("lowered: predicates\n");
+  std::fflush(stdout);
+  for (int i = 0; i < qc.scalar_groups_size(); ++i) {
+    gpu::ExprBuilder b;
+    for (int j = 0; j < qc.scalar_groups(i).scalars_size(); ++j) gpu::LowerScalar(qc.scalar_groups(i).scalars(j), types, &b);
+  }
+  std::printf("lowered: scalar_groups\n");
+  std::fflush(stdout);
+  for (int i = 0; i < qc.aggregation_states_size(); ++i) {
+    const serialization::AggregationOperationState &proto = qc.aggregation_states(i).aggregation_state();
+    gpu::LoweredAggregationState lowered;
+    gpu::LowerAggregationState(proto, db.getRelationSchemaById(proto.relation_id()), &lowered);
+    for (const std::int32_t g : lowered.group_by_roots)
+      CHECK(lowered.exprs.node(g).kind == QS_N_ATTRIBUTE) << "GPU path: GROUP BY expressions other than attributes";
+  }
+  std::printf("lowered: aggregation_states\n");
+  for (int i = 0; i < qc.lip_filters_size(); ++i)
+    CHECK(qc.lip_filters(i).lip_filter_type() != serialization::LIPFilterType::BLOOM_FILTER) << "GPU path: BLOOM_FILTER";
+  for (int i = 0; i < qc.join_hash_tables_size(); ++i) {
+    const serialization::HashTable &h = qc.join_hash_tables(i).join_hash_table();
+    CHECK_LE(h.key_types_size(), 2) << "GPU path: join keys of more than two attributes";
+    for (int k = 0; k < h.key_types_size(); ++k)
+      CHECK(h.key_types(k).type_id() == serialization::Type::INT || (h.key_types_size() == 1 && h.key_types(k).type_id() == serialization::Type::LONG))
+          << "GPU path: join key that is not INT / LONG";
+  }
+  std::printf("lowered: lip_filters join_hash_tables\nok\n");
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
+  if (argc >= 5 && std::string(argv[1]) == "--coverage") return Coverage(argv[2], argv[3], std::atof(argv[4]));
   CHECK_GE(argc, 3) << "usage: make_plan_golden <reference root> <out.json>";
   const std::string ref = argv[1];
   FILE *out = std::fopen(argv[2], "w");

@@ -9,7 +9,7 @@ SRC=${QS_REF_SCRATCH:-/tmp/qs_ref_src}
 BLD=${QS_REF_BUILD:-/tmp/qs_ref_build}
 OUT=${1:-$HERE/reference_plans.json}
 [ -f "$BLD/expressions/Expressions.pb.h" ] || { echo "run oracle/build_ref.sh first"; exit 1; }
-BIN=$(mktemp -d)/make_plan_golden
+BIN=${QS_PLAN_BIN:-$(mktemp -d)/make_plan_golden}
 # the reference's own compile definitions and flags (CMakeFiles/quickstep_cli_shell.dir/flags.make)
 g++ -std=c++17 -O1 -DNDEBUG -Wno-deprecated-declarations -march=x86-64-v3 \
   -DQUICKSTEP_ENABLE_COMPARISON_INLINE_EXPANSION -DQUICKSTEP_ENABLE_VECTOR_COPY_ELISION_SELECTION \
