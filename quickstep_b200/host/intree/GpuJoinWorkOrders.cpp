@@ -271,6 +271,7 @@ class GpuBuildHashWorkOrder : public WorkOrder {
   void execute() override {
     AttributeTypes types;
     types.relations.emplace_back(input_relation_.getID(), AttributesOf(input_relation_));
+    types.single_relation = true;
     LoweredExprs e;
     LowerInto(&e, types, predicate_, nullptr);
     const qs_expr_set es = e.builder.view();
@@ -376,6 +377,7 @@ class GpuBuildLIPFilterWorkOrder : public WorkOrder {
   void execute() override {
     AttributeTypes types;
     types.relations.emplace_back(input_relation_.getID(), AttributesOf(input_relation_));
+    types.single_relation = true;
     LoweredExprs e;
     LowerInto(&e, types, predicate_, nullptr);
     const qs_expr_set es = e.builder.view();

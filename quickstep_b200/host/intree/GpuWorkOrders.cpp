@@ -123,6 +123,7 @@ class GpuSelectWorkOrder : public WorkOrder {
   void execute() override {
     AttributeTypes types;
     types.relations.emplace_back(input_relation_.getID(), SchemaOf(input_relation_));
+    types.single_relation = true;
     ExprBuilder b;
     const int pred = predicate_ ? LowerPredicate(predicate_->getProto(), types, &b) : -1;
     std::vector<std::int32_t> roots;

@@ -82,6 +82,11 @@ inline std::uint16_t LowerTypeID(const serialization::Type &t, std::uint16_t *wi
 struct AttributeTypes {
   // relation_id -> per attribute (type, width); filled by the caller from CatalogRelationSchema
   std::vector<std::pair<int, std::vector<qs_attr>>> relations;
+  // The expression is evaluated over ONE relation (a Select / Aggregation / BuildLIPFilter predicate, a BuildHash
+  // predicate): join sides are dropped.  The optimizer leaves them on, e.g., a BuildHashOperator's build predicate that it
+  // pushed down from a join (TPC-H Q19 / Q21: its attributes still say RIGHT_SIDE), and the reference's single-relation
+  // evaluation (Predicate::getAllMatches over one accessor) never looks at them.
+  bool single_relation = false;
   qs_attr lookup(int relation_id, int attribute_id) const {
     for (const auto &r : relations)
       if (r.first == relation_id) return r.second[static_cast<std::size_t>(attribute_id)];
@@ -208,7 +213,7 @@ inline int LowerScalar(const serialization::Scalar &s, const AttributeTypes &typ
       n.type = a.type;
       n.width = a.width;
       n.a = s.GetExtension(serialization::ScalarAttribute::attribute_id);
-      n.b = static_cast<std::int32_t>(s.GetExtension(serialization::ScalarAttribute::join_side));   // RIGHT_SIDE = 2 = build side
+      n.b = types.single_relation ? 0 : static_cast<std::int32_t>(s.GetExtension(serialization::ScalarAttribute::join_side));   // RIGHT_SIDE = 2 = build side
       return b->add(n);
     }
     case serialization::Scalar::UNARY_EXPRESSION: {

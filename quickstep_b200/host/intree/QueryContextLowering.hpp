@@ -92,6 +92,7 @@ inline void LowerAggregationState(const serialization::AggregationOperationState
                                   LoweredAggregationState *out) {
   AttributeTypes types;
   types.relations.emplace_back(proto.relation_id(), AttributesOf(input));
+  types.single_relation = true;
   out->predicate_root = proto.has_predicate() ? LowerPredicate(proto.predicate(), types, &out->exprs) : -1;
   for (int j = 0; j < proto.aggregates_size(); ++j) {
     const serialization::Aggregate &a = proto.aggregates(j);

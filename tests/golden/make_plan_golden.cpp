@@ -131,13 +131,68 @@ void EmitRelations(FILE *out, const CatalogDatabase &db) {
   std::fprintf(out, "]");
 }
 
+struct FullAttr {
+  const char *name;
+  TypeID type;
+  std::size_t length;
+  int key_of;        // 0: not an integer key; otherwise index into kRowsSf1 below of the relation whose key range it has
+};
+
+// benchmarks/tpch/create.sql's eight relations, all attributes, with the statistics `\\analyze` records at scale factor sf
+void BuildFullCatalog(CatalogDatabase *db, double sf) {
+  // rows at SF1: region, nation, supplier, customer, part, partsupp, orders, lineitem
+  const double kRowsSf1[9] = {0, 5, 25, 10000, 150000, 200000, 800000, 1500000, 6000000};
+  auto rows = [&](int rel) { return rel <= 2 ? static_cast<std::int64_t>(kRowsSf1[rel]) : static_cast<std::int64_t>(kRowsSf1[rel] * sf); };
+  struct Rel { const char *name; int rows_of; std::vector<FullAttr> attrs; };
+  const std::vector<Rel> schema = {
+      {"region", 1, {{"r_regionkey", kInt, 0, 1}, {"r_name", kChar, 25, 0}, {"r_comment", kVarChar, 152, 0}}},
+      {"nation", 2, {{"n_nationkey", kInt, 0, 2}, {"n_name", kChar, 25, 0}, {"n_regionkey", kInt, 0, 1}, {"n_comment", kVarChar, 152, 0}}},
+      {"supplier", 3, {{"s_suppkey", kInt, 0, 3}, {"s_name", kChar, 25, 0}, {"s_address", kVarChar, 40, 0}, {"s_nationkey", kInt, 0, 2},
+                       {"s_phone", kChar, 15, 0}, {"s_acctbal", kDouble, 0, 0}, {"s_comment", kVarChar, 101, 0}}},
+      {"customer", 4, {{"c_custkey", kInt, 0, 4}, {"c_name", kVarChar, 25, 0}, {"c_address", kVarChar, 40, 0}, {"c_nationkey", kInt, 0, 2},
+                       {"c_phone", kChar, 15, 0}, {"c_acctbal", kDouble, 0, 0}, {"c_mktsegment", kChar, 10, 0}, {"c_comment", kVarChar, 117, 0}}},
+      {"part", 5, {{"p_partkey", kInt, 0, 5}, {"p_name", kVarChar, 55, 0}, {"p_mfgr", kChar, 25, 0}, {"p_brand", kChar, 10, 0}, {"p_type", kVarChar, 25, 0},
+                   {"p_size", kInt, 0, 0}, {"p_container", kChar, 10, 0}, {"p_retailprice", kDouble, 0, 0}, {"p_comment", kVarChar, 23, 0}}},
+      {"partsupp", 6, {{"ps_partkey", kInt, 0, 5}, {"ps_suppkey", kInt, 0, 3}, {"ps_availqty", kInt, 0, 0}, {"ps_supplycost", kDouble, 0, 0},
+                       {"ps_comment", kVarChar, 199, 0}}},
+      {"orders", 7, {{"o_orderkey", kInt, 0, 7}, {"o_custkey", kInt, 0, 4}, {"o_orderstatus", kChar, 1, 0}, {"o_totalprice", kDouble, 0, 0},
+                     {"o_orderdate", kDate, 0, 0}, {"o_orderpriority", kChar, 15, 0}, {"o_clerk", kChar, 15, 0}, {"o_shippriority", kInt, 0, 0},
+                     {"o_comment", kVarChar, 79, 0}}},
+      {"lineitem", 8, {{"l_orderkey", kInt, 0, 7}, {"l_partkey", kInt, 0, 5}, {"l_suppkey", kInt, 0, 3}, {"l_linenumber", kInt, 0, 0},
+                       {"l_quantity", kDouble, 0, 0}, {"l_extendedprice", kDouble, 0, 0}, {"l_discount", kDouble, 0, 0}, {"l_tax", kDouble, 0, 0},
+                       {"l_returnflag", kChar, 1, 0}, {"l_linestatus", kChar, 1, 0}, {"l_shipdate", kDate, 0, 0}, {"l_commitdate", kDate, 0, 0},
+                       {"l_receiptdate", kDate, 0, 0}, {"l_shipinstruct", kChar, 25, 0}, {"l_shipmode", kChar, 10, 0}, {"l_comment", kVarChar, 44, 0}}}};
+  for (const Rel &r : schema) {
+    CatalogRelation *rel = new CatalogRelation(db, r.name);
+    for (const FullAttr &a : r.attrs) {
+      const Type &t = a.length ? TypeFactory::GetType(a.type, a.length, false) : TypeFactory::GetType(a.type, false);
+      rel->addAttribute(new CatalogAttribute(rel, a.name, t));
+    }
+    db->addRelation(rel);
+    rel->addBlock(BlockIdUtil::GetBlockId(1, 1 + rel->getID()));
+    CatalogRelationStatistics *stats = rel->getStatisticsMutable();
+    stats->setExactness(true);
+    stats->setNumTuples(rows(r.rows_of));
+    for (std::size_t i = 0; i < r.attrs.size(); ++i) {
+      if (!r.attrs[i].key_of) continue;
+      const std::int64_t n = rows(r.attrs[i].key_of);
+      const std::int64_t max_key = r.attrs[i].key_of == 7 ? n * 4 : n;            // dbgen's order keys are sparse
+      stats->setNumDistinctValues(static_cast<attribute_id>(i), std::min<std::int64_t>(n, rows(r.rows_of)));
+      stats->setMinValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? 0 : 1)));
+      stats->setMaxValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? n - 1 : max_key)));
+    }
+  }
+}
+
 // `sf`: the scale factor whose `\\analyze` statistics the catalog carries (row counts, distinct counts and key ranges grow
 // with it; dbgen's order keys are sparse: 8 of every 32).
-void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_query, double sf = 0.01) {
+void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_query, double sf = 0.01, bool full_catalog = false) {
   // a fresh catalog per query: relation ids of the temporaries start from the same point every time
   CatalogDatabase db(nullptr, "default");
+  if (full_catalog) BuildFullCatalog(&db, sf);
   const std::int64_t n_orders = static_cast<std::int64_t>(1500000 * sf), n_cust = static_cast<std::int64_t>(150000 * sf);
   const std::int64_t n_lineitem = sf == 0.01 ? 60175 : static_cast<std::int64_t>(6000000 * sf), max_okey = n_orders * 4;
+  if (!full_catalog) {
   AddRelation(&db, "lineitem", n_lineitem,
               {{"l_orderkey", kInt, 0, n_orders, 1, max_okey}, {"l_quantity", kDouble, 0, 50, 0, 0}, {"l_extendedprice", kDouble, 0, 35921, 0, 0},
                {"l_discount", kDouble, 0, 11, 0, 0}, {"l_tax", kDouble, 0, 9, 0, 0}, {"l_returnflag", kChar, 1, 3, 0, 0},
@@ -146,6 +201,7 @@ void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_q
               {{"o_orderkey", kInt, 0, n_orders, 1, max_okey}, {"o_custkey", kInt, 0, n_cust * 2 / 3, 1, n_cust - 1}, {"o_orderdate", kDate, 0, 2401, 0, 0},
                {"o_shippriority", kInt, 0, 1, 0, 0}});
   AddRelation(&db, "customer", n_cust, {{"c_custkey", kInt, 0, n_cust, 1, n_cust}, {"c_mktsegment", kChar, 10, 5, 0, 0}});
+  }
 
   SqlParserWrapper parser;
   parser.feedNextBuffer(new std::string(sql));
@@ -334,57 +390,9 @@ std::string ReadFile(const std::string &path) {
 // EXTRACT, VARCHAR attributes, DISTINCT aggregates, ...) ends in the binding's LOG(FATAL) naming the reason -- such an
 // operator keeps its CPU work orders -- and the driver script records it.
 // ---------------------------------------------------------------------------------------------------------------------
-struct FullAttr {
-  const char *name;
-  TypeID type;
-  std::size_t length;
-  int key_of;        // 0: not an integer key; otherwise index into kRows below of the relation whose key range it has
-};
-
 int Coverage(const std::string &ref, const std::string &query_file, double sf) {
-  // rows at SF1: region, nation, supplier, customer, part, partsupp, orders, lineitem
-  const double kRowsSf1[9] = {0, 5, 25, 10000, 150000, 200000, 800000, 1500000, 6000000};
-  auto rows = [&](int rel) { return rel <= 2 ? static_cast<std::int64_t>(kRowsSf1[rel]) : static_cast<std::int64_t>(kRowsSf1[rel] * sf); };
-  struct Rel { const char *name; int rows_of; std::vector<FullAttr> attrs; };
-  const std::vector<Rel> schema = {
-      {"region", 1, {{"r_regionkey", kInt, 0, 1}, {"r_name", kChar, 25, 0}, {"r_comment", kVarChar, 152, 0}}},
-      {"nation", 2, {{"n_nationkey", kInt, 0, 2}, {"n_name", kChar, 25, 0}, {"n_regionkey", kInt, 0, 1}, {"n_comment", kVarChar, 152, 0}}},
-      {"supplier", 3, {{"s_suppkey", kInt, 0, 3}, {"s_name", kChar, 25, 0}, {"s_address", kVarChar, 40, 0}, {"s_nationkey", kInt, 0, 2},
-                       {"s_phone", kChar, 15, 0}, {"s_acctbal", kDouble, 0, 0}, {"s_comment", kVarChar, 101, 0}}},
-      {"customer", 4, {{"c_custkey", kInt, 0, 4}, {"c_name", kVarChar, 25, 0}, {"c_address", kVarChar, 40, 0}, {"c_nationkey", kInt, 0, 2},
-                       {"c_phone", kChar, 15, 0}, {"c_acctbal", kDouble, 0, 0}, {"c_mktsegment", kChar, 10, 0}, {"c_comment", kVarChar, 117, 0}}},
-      {"part", 5, {{"p_partkey", kInt, 0, 5}, {"p_name", kVarChar, 55, 0}, {"p_mfgr", kChar, 25, 0}, {"p_brand", kChar, 10, 0}, {"p_type", kVarChar, 25, 0},
-                   {"p_size", kInt, 0, 0}, {"p_container", kChar, 10, 0}, {"p_retailprice", kDouble, 0, 0}, {"p_comment", kVarChar, 23, 0}}},
-      {"partsupp", 6, {{"ps_partkey", kInt, 0, 5}, {"ps_suppkey", kInt, 0, 3}, {"ps_availqty", kInt, 0, 0}, {"ps_supplycost", kDouble, 0, 0},
-                       {"ps_comment", kVarChar, 199, 0}}},
-      {"orders", 7, {{"o_orderkey", kInt, 0, 7}, {"o_custkey", kInt, 0, 4}, {"o_orderstatus", kChar, 1, 0}, {"o_totalprice", kDouble, 0, 0},
-                     {"o_orderdate", kDate, 0, 0}, {"o_orderpriority", kChar, 15, 0}, {"o_clerk", kChar, 15, 0}, {"o_shippriority", kInt, 0, 0},
-                     {"o_comment", kVarChar, 79, 0}}},
-      {"lineitem", 8, {{"l_orderkey", kInt, 0, 7}, {"l_partkey", kInt, 0, 5}, {"l_suppkey", kInt, 0, 3}, {"l_linenumber", kInt, 0, 0},
-                       {"l_quantity", kDouble, 0, 0}, {"l_extendedprice", kDouble, 0, 0}, {"l_discount", kDouble, 0, 0}, {"l_tax", kDouble, 0, 0},
-                       {"l_returnflag", kChar, 1, 0}, {"l_linestatus", kChar, 1, 0}, {"l_shipdate", kDate, 0, 0}, {"l_commitdate", kDate, 0, 0},
-                       {"l_receiptdate", kDate, 0, 0}, {"l_shipinstruct", kChar, 25, 0}, {"l_shipmode", kChar, 10, 0}, {"l_comment", kVarChar, 44, 0}}}};
   CatalogDatabase db(nullptr, "default");
-  for (const Rel &r : schema) {
-    CatalogRelation *rel = new CatalogRelation(&db, r.name);
-    for (const FullAttr &a : r.attrs) {
-      const Type &t = a.length ? TypeFactory::GetType(a.type, a.length, false) : TypeFactory::GetType(a.type, false);
-      rel->addAttribute(new CatalogAttribute(rel, a.name, t));
-    }
-    db.addRelation(rel);
-    rel->addBlock(BlockIdUtil::GetBlockId(1, 1 + rel->getID()));
-    CatalogRelationStatistics *stats = rel->getStatisticsMutable();
-    stats->setExactness(true);
-    stats->setNumTuples(rows(r.rows_of));
-    for (std::size_t i = 0; i < r.attrs.size(); ++i) {
-      if (!r.attrs[i].key_of) continue;
-      const std::int64_t n = rows(r.attrs[i].key_of);
-      const std::int64_t max_key = r.attrs[i].key_of == 7 ? n * 4 : n;            // dbgen's order keys are sparse
-      stats->setNumDistinctValues(static_cast<attribute_id>(i), std::min<std::int64_t>(n, rows(r.rows_of)));
-      stats->setMinValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? 0 : 1)));
-      stats->setMaxValue(static_cast<attribute_id>(i), TypedValue(static_cast<int>(r.attrs[i].key_of <= 2 ? n - 1 : max_key)));
-    }
-  }
+  BuildFullCatalog(&db, sf);
   SqlParserWrapper parser;
   parser.feedNextBuffer(new std::string(ReadFile(ref + "/benchmarks/tpch/queries/" + query_file)));
   ParseResult result = parser.getNextStatement();
@@ -439,6 +447,18 @@ int Coverage(const std::string &ref, const std::string &query_file, double sf) {
 
 int main(int argc, char **argv) {
   if (argc >= 5 && std::string(argv[1]) == "--coverage") return Coverage(argv[2], argv[3], std::atof(argv[4]));
+  if (argc >= 6 && std::string(argv[1]) == "--plan") {      // --plan <reference root> <out.json> <sf> NN ...: full catalog
+    FILE *out = std::fopen(argv[3], "w");
+    std::fprintf(out, "{\"generator\": \"tests/golden/make_plan_golden.cpp --plan: full TPC-H catalog, statistics of SF%s\",\n \"plans\": [", argv[4]);
+    for (int i = 5; i < argc; ++i) {
+      const std::string q = argv[i];
+      PlanQuery(out, ("q" + std::to_string(std::atoi(q.c_str()))).c_str(), ReadFile(std::string(argv[2]) + "/benchmarks/tpch/queries/" + q + ".sql"), i == 5,
+                std::atof(argv[4]), true);
+    }
+    std::fprintf(out, "\n ]}\n");
+    std::fclose(out);
+    return 0;
+  }
   CHECK_GE(argc, 3) << "usage: make_plan_golden <reference root> <out.json>";
   const std::string ref = argv[1];
   FILE *out = std::fopen(argv[2], "w");

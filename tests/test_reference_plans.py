@@ -70,6 +70,24 @@ def expr_set(obj) -> ExprSet:
     return es
 
 
+def append_exprs(es: ExprSet, obj):
+    """Appends a lowered node array to `es` (ExprSet::append in host/ExprSet.hpp: a work order that evaluates several
+    QueryContext entries passes ONE qs_expr_set); -> index shift of the appended nodes."""
+    ges, base, pool_base = expr_set(obj), len(es.nodes), len(es.pool)
+    for n in ges.nodes:
+        if n.kind == A.QS_N_LITERAL:
+            if n.type == A.QS_CHAR:
+                n.lit.pool_offset += pool_base
+        elif n.kind != A.QS_N_ATTRIBUTE:
+            n.a += base
+            if n.kind in (A.QS_N_BINARY, A.QS_N_COMPARISON, A.QS_N_CONJUNCTION, A.QS_N_DISJUNCTION):
+                n.b += base
+        es.nodes.append(n)
+    es.pool += ges.pool
+    es._c = None
+    return base
+
+
 class Interpreter:
     def __init__(self, plan, tables):
         self.plan, self.B = plan, OracleBackend()
@@ -79,7 +97,7 @@ class Interpreter:
         for f in plan["lip_filters"]:
             assert f["kind"] == A.QS_LIP_BITVECTOR_EXACT
             self.lips.append(self.B.make_lip(f["kind"], A.QS_INT if f["attribute_size"] == 4 else A.QS_LONG, f["min_value"], f["max_value"], 0, f["is_anti"]))
-        self.agg, self.built, self.trace, self.cardinality = {}, {}, [], {}
+        self.agg, self.built, self.trace, self.cardinality, self.nulls = {}, {}, [], {}, {}
 
     def destination(self, index):
         return self.plan["insert_destinations"][index]["relation_id"]
@@ -129,46 +147,71 @@ class Interpreter:
                 if wo["simple_projection"]:
                     roots = [es.attr(a, *self.schema[wo["relation_id"]][a]) for a in wo["simple_selection"]]
                 else:
-                    # predicate and scalar group of one QueryContext go into one expression set (ExprSet::append in
-                    # host/ExprSet.hpp): the group's node indices shift by the predicate's length
                     grp = self.plan["scalar_groups"][wo["selection_index"]]
-                    ges, base = expr_set(grp), len(es.nodes)
-                    for n in ges.nodes:
-                        if n.kind not in (A.QS_N_LITERAL, A.QS_N_ATTRIBUTE):
-                            n.a += base
-                            if n.kind == A.QS_N_BINARY:
-                                n.b += base
-                        elif n.kind == A.QS_N_LITERAL and n.type == A.QS_CHAR:
-                            n.lit.pool_offset += len(es.pool)
-                        es.nodes.append(n)
-                    es.pool += ges.pool
+                    base = append_exprs(es, grp)
                     roots = [r + base for r in grp["roots"]]
                 dest = self.destination(wo["insert_destination_index"])
                 out = self.B.select(src, es, root, self.lip_refs(wo["lip_deployment_index"], "probe"), roots, self.schema[dest])
                 self.store(dest, [c.data for c in out.columns])
+                if wo["relation_id"] in self.nulls:        # a scalar over a NULL is NULL (no predicate in the plans that get here)
+                    import qs_null_oracle as NO
+                    assert root == -1
+                    nl = np.zeros(out.n_rows, dtype=np.uint64)
+                    for j, r in enumerate(roots):
+                        nl |= NO.null_of(es, r, self.nulls[wo["relation_id"]]).astype(np.uint64) << np.uint64(j)
+                    self.nulls[dest] = nl
             elif kind == "BUILD_LIP_FILTER":
                 pred = self.plan["predicates"][wo["build_side_predicate_index"]]
                 self.B.build_lip(self.rel[wo["relation_id"]], expr_set(pred), pred["root"], self.lip_refs(wo["lip_deployment_index"], "probe"),
                                  self.lip_refs(wo["lip_deployment_index"], "build"))
             elif kind == "BUILD_HASH":
-                assert wo["build_predicate_index"] in (-1, 4294967295)         # kInvalidPredicateId
-                assert len(wo["join_key_attributes"]) == 1
-                self.built[wo["join_hash_table_index"]] = (wo["relation_id"], wo["join_key_attributes"][0])
+                pred = wo["build_predicate_index"]
+                self.built[wo["join_hash_table_index"]] = (wo["relation_id"], wo["join_key_attributes"], None if pred in (-1, 4294967295) else pred)
                 build_refs = self.lip_refs(wo["lip_deployment_index"], "build")
                 if build_refs:      # BuildHashWorkOrder::execute also inserts the build keys into its LIP filters (BuildHashOperator.cpp:186-197)
+                    assert pred in (-1, 4294967295)
                     self.B.build_lip(self.rel[wo["relation_id"]], None, -1, None, build_refs)
                 self.cardinality["build_rows"] = self.rel[wo["relation_id"]].n_rows
             elif kind == "HASH_JOIN":
                 join_type = {"HASH_INNER_JOIN": A.QS_JOIN_INNER, "HASH_SEMI_JOIN": A.QS_JOIN_LEFT_SEMI, "HASH_ANTI_JOIN": A.QS_JOIN_LEFT_ANTI,
                              "HASH_OUTER_JOIN": A.QS_JOIN_LEFT_OUTER}[wo["hash_join_work_order_type"]]
-                build_rel, build_key = self.built[wo["join_hash_table_index"]]
-                assert build_rel == wo["build_relation_id"] and wo["residual_predicate_index"] == -1
+                build_rel, build_keys, build_pred = self.built[wo["join_hash_table_index"]]
+                assert build_rel == wo["build_relation_id"]
+                build, probe = self.rel[build_rel], self.rel[wo["probe_relation_id"]]
+                probe_keys = wo["join_key_attributes"]
+                assert len(build_keys) == len(probe_keys)
+                es = ExprSet()
+                bp = rp = -1
+                if build_pred is not None:
+                    # evaluated over the build relation alone (BuildHashWorkOrder::execute): the join sides the optimizer left
+                    # on a pushed-down predicate are dropped (AttributeTypes::single_relation in the in-tree lowering)
+                    bp = append_exprs(es, self.plan["predicates"][build_pred]) + self.plan["predicates"][build_pred]["root"]
+                    for n in es.nodes:
+                        if n.kind == A.QS_N_ATTRIBUTE:
+                            n.b = 0
+                if wo["residual_predicate_index"] >= 0:
+                    res = self.plan["predicates"][wo["residual_predicate_index"]]
+                    rp = append_exprs(es, res) + res["root"]
                 grp = self.plan["scalar_groups"][wo["selection_index"]]
+                base = append_exprs(es, grp)
+                roots = [r + base for r in grp["roots"]]
+                if len(build_keys) == 1:
+                    bk, pk = build_keys[0], probe_keys[0]
+                else:
+                    # composite key (HashTable::putValueAccessorCompositeKey, storage/HashTable.hpp:1469): two INT attributes
+                    # packed into one LONG key column appended to each side -- what qsgpu_join_*_composite does on the device
+                    assert len(build_keys) == 2
+
+                    def with_packed(t, keys):
+                        hi = t.columns[keys[0]].data.astype(np.int64) << np.int64(32)
+                        lo = t.columns[keys[1]].data.astype(np.int64) & np.int64(0xFFFFFFFF)
+                        return HostTable(t.name, list(t.columns) + [Column("packed_key", A.QS_LONG, hi | lo)])
+                    build, probe = with_packed(build, build_keys), with_packed(probe, probe_keys)
+                    bk, pk = len(build.columns) - 1, len(probe.columns) - 1
                 dest = self.destination(wo["insert_destination_index"])
-                probe = self.rel[wo["probe_relation_id"]]
                 # the build side may carry duplicate keys: size for every pair
-                out = self.B.hash_join(self.rel[build_rel], -1, build_key, probe, expr_set(grp), -1, wo["join_key_attributes"][0], join_type, -1,
-                                       grp["roots"], self.schema[dest], max(1, probe.n_rows * 4))
+                out = self.B.hash_join(build, bp, bk, probe, es, -1, pk, join_type, rp, roots, self.schema[dest],
+                                       max(1, probe.n_rows * 8), build_es=es)
                 self.store(dest, [c.data for c in out.columns])
                 self.cardinality.update(probe_rows=probe.n_rows, join_rows=out.n_rows)
             elif kind == "AGGREGATION":
@@ -183,14 +226,16 @@ class Interpreter:
             elif kind == "FINALIZE_AGGREGATION":
                 out, key_schema, val_types = self.agg[wo["aggr_state_index"]]
                 dest = self.destination(wo["insert_destination_index"])
-                assert self.schema[dest] == [(t, w or np_dtype(t).itemsize) for t, w in key_schema] + list(val_types), (self.schema[dest], key_schema, val_types)
+                assert [t for t, _w in self.schema[dest]] == [t for t, _w in key_schema] + [t for t, _w in val_types], (self.schema[dest], key_schema, val_types)
                 cols, off = [], 0
                 for t, w in key_schema:
                     dt = np_dtype(t, w)
                     cols.append(out.keys[:, off:off + dt.itemsize].copy().view(dt).reshape(-1))
                     off += dt.itemsize
-                assert out.null_mask == 0
                 self.store(dest, cols + list(out.values))
+                if out.null_mask:       # an aggregate without GROUP BY that saw no row is NULL (AggregationHandleSum.cpp:134-143)
+                    assert not key_schema and out.n_groups == 1
+                    self.nulls[dest] = np.array([out.null_mask << len(key_schema)], dtype=np.uint64)
             elif kind == "SORT_RUN_GENERATION":
                 cfg = self.plan["sort_configs"][wo["sort_config_index"]]
                 src = self.rel[wo["relation_id"]]
@@ -206,8 +251,9 @@ class Interpreter:
                 # one sorted run: merging it is the identity (the top-k LIMIT is applied when the result is compared)
                 self.store(op["output_relation"], [c.data for c in self.rel[self.sorted].columns])
             else:
-                assert kind in ("DESTROY_AGGREGATION_STATE", "DESTROY_HASH", None), (op["name"], kind)
+                assert kind in ("DESTROY_AGGREGATION_STATE", "DESTROY_HASH", "INITIALIZE_AGGREGATION", None), (op["name"], kind)
         result = max(i for i in self.rel if self.plan["relations"][[r["id"] for r in self.plan["relations"]].index(i)]["temporary"])
+        self.result_nulls = self.nulls.get(result)
         return self.rel[result]
 
 
