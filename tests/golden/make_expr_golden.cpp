@@ -25,6 +25,8 @@
 #include "catalog/CatalogAttribute.hpp"
 #include "catalog/CatalogRelation.hpp"
 #include "catalog/PartitionSchemeHeader.hpp"
+#include "compression/CompressionDictionary.hpp"
+#include "compression/CompressionDictionaryBuilder.hpp"
 #include "expressions/aggregation/AggregateFunction.hpp"
 #include "expressions/aggregation/AggregateFunctionFactory.hpp"
 #include "expressions/aggregation/AggregationHandle.hpp"
@@ -417,6 +419,55 @@ void LipCase(FILE *out, const char *name, bool exact, std::int64_t min_value, st
   g_first_lip = false;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dictionary limit codes (f2): a block's sorted CompressionDictionary built by the reference's own builder from the
+// column's values, and the code range CompressedTupleStorageSubBlock::getMatchesForPredicate evaluates `attribute <cmp>
+// literal` with (compression/CompressionDictionary.hpp:209-236, CompressionDictionary.cpp:201-330) -- literals of the
+// attribute's own type and of other comparable types.
+// ---------------------------------------------------------------------------------------------------------------------
+bool g_first_dict = true;
+
+void DictionaryCase(FILE *out, int attr, const std::vector<std::pair<const char *, Scalar *>> &literals) {
+  const Type &type = *g_cols[attr].type;
+  const std::size_t w = type.maximumByteLength();
+  CompressionDictionaryBuilder builder(type);
+  for (int r = 0; r < kRows; ++r) builder.insertEntry(type.makeValue(g_cols[attr].bytes.data() + r * w, w));
+  std::vector<char> memory(builder.dictionarySizeBytes());
+  builder.buildDictionary(memory.data());
+  CompressionDictionary dict(type, memory.data(), memory.size());
+  std::string entries;
+  for (std::uint32_t c = 0; c < dict.numberOfCodes(); ++c) {
+    std::vector<char> v(w, '\0');
+    const TypedValue tv = dict.getTypedValueForCode(c);
+    if (type.getTypeID() == kChar) std::memcpy(v.data(), tv.getOutOfLineData(), std::min<std::size_t>(w, tv.getAsciiStringLength()));
+    else tv.copyInto(v.data());
+    entries += Hex(v.data(), w);
+  }
+  std::fprintf(out, "%s\n  {\"attr\": %d, \"name\": \"%s\", \"type\": %d, \"width\": %zu, \"n_codes\": %u, \"entries\": \"%s\", \"comparisons\": [",
+               g_first_dict ? "" : ",", attr, g_cols[attr].name.c_str(),
+               type.getTypeID() == kDate ? QS_DATE : static_cast<int>(type.getTypeID()), w, dict.numberOfCodes(), entries.c_str());
+  g_first_dict = false;
+  const ComparisonID cmps[5] = {EQ, LT, LE, GT, GE};          // kNotEqual is the caller's complement of kEqual (:217-219)
+  bool first = true;
+  for (const auto &lit : literals) {
+    std::unique_ptr<Scalar> owner(lit.second);
+    CHECK(lit.second->hasStaticValue());
+    const TypedValue &value = lit.second->getStaticValue();
+    gpu::ExprBuilder b;
+    const int root = gpu::LowerScalar(lit.second->getProto(), Types(), &b);
+    for (const ComparisonID cmp : cmps) {
+      const std::pair<std::uint32_t, std::uint32_t> limits = dict.getLimitCodesForComparisonTyped(cmp, value, lit.second->getType());
+      std::fprintf(out, "%s\n    {\"literal\": \"%s\", \"cmp\": %d, \"first\": %u, \"second\": %u, ", first ? "" : ",", lit.first, static_cast<int>(cmp),
+                   limits.first, limits.second);
+      EmitNodes(out, b, root);
+      std::fprintf(out, "}");
+      first = false;
+    }
+  }
+  std::fprintf(out, "]}");
+}
+
 Predicate *IsR() { return Cmp(EQ, Attr(A_C1), LitC("R")); }
 Predicate *InRange(int a, int lo, int hi) { return And({Cmp(GE, Attr(a), LitI(lo)), Cmp(LE, Attr(a), LitI(hi))}); }
 
@@ -625,6 +676,21 @@ int main(int argc, char **argv) {
       std::fprintf(out, "]}");
       first_part = false;
     }
+
+  // ------------------------------------------------------------------ CompressionDictionary limit codes
+  std::fprintf(out, "\n ],\n \"dictionaries\": [");
+  DictionaryCase(out, A_I2, {{"-49", LitI(-49)}, {"-48", LitI(-48)}, {"0", LitI(0)}, {"7", LitI(7)}, {"48", LitI(48)}, {"49", LitI(49)},
+                             {"6.5", LitD(6.5)}, {"7.0", LitD(7.0)}, {"-100 (LONG)", LitL(-100)}, {"7 (LONG)", LitL(7)}});
+  DictionaryCase(out, A_L2, {{"-301", LitL(-301)}, {"-300", LitL(-300)}, {"12", LitL(12)}, {"300", LitL(300)}, {"301", LitL(301)}, {"12 (INT)", LitI(12)},
+                             {"12.5", LitD(12.5)}});
+  DictionaryCase(out, A_DISC, {{"-0.01", LitD(-0.01)}, {"0.0", LitD(0.0)}, {"0.05", LitD(0.05)}, {"0.055", LitD(0.055)}, {"0.1", LitD(0.1)}, {"0.11", LitD(0.11)},
+                               {"0 (INT)", LitI(0)}, {"1 (INT)", LitI(1)}});
+  DictionaryCase(out, A_DT, {{"1991-12-31", LitDate(1991, 12, 31)}, {"1995-06-17", LitDate(1995, 6, 17)}, {"1998-12-28", LitDate(1998, 12, 28)},
+                             {"1999-01-01", LitDate(1999, 1, 1)}});
+  DictionaryCase(out, A_C4, {{"AIR", LitC("AIR")}, {"MAIL", LitC("MAIL")}, {"MA", LitC("MA")}, {"TRUC", LitC("TRUC")}, {"TRUCKS", LitC("TRUCKS")},
+                             {"ZZZZ", LitC("ZZZZ")}, {"A", LitC("A")}});
+  DictionaryCase(out, A_C10, {{"BUILDING", LitC("BUILDING")}, {"AUTOMOBILE", LitC("AUTOMOBILE")}, {"AUTOMOBILES", LitC("AUTOMOBILES")}, {"B", LitC("B")},
+                              {"HOUSEHOLD", LitC("HOUSEHOLD")}});
 
   std::fprintf(out, "\n ]}\n");
   if (out != stdout) std::fclose(out);

@@ -21,6 +21,12 @@ the range) and identity-hash filters (negative values) (rows L1, L2, L4).
 `hash_partitions` (15 cases): HashPartitionSchemeHeader::getPartitionId for INT (negative values) and LONG keys over 2 / 4 /
 7 / 8 / 13 partitions -- where PartitionAwareInsertDestination sends each tuple (row f4).
 
+`dictionaries` (205 comparisons): the reference's CompressionDictionaryBuilder builds a block dictionary from a column and
+CompressionDictionary::getLimitCodesForComparisonTyped names the code range of `attribute <cmp> literal` (literals of the
+attribute's type and of other types; CHAR literals shorter and longer than the attribute) -- checked against the PRODUCT's
+qsgpu_dictionary_code_range (host arithmetic of libqsgpu.so, no device needed), the function every comparison on a coded
+attribute goes through (row f2).
+
 The NULL-able cases run over the same tuples with every fifth value or so of five attributes NULL: the reference's answers
 there are "a comparison with a NULL operand is false, NOT complements it, arithmetic over a NULL is NULL" -- the rules
 oracle/qs_null_oracle.py restates and the device path implements with its per-row NULL masks.
@@ -45,6 +51,7 @@ NULL_CASES = [c for c in GOLDEN["cases"] if c["nullable"]]
 AGGREGATES = GOLDEN["aggregates"]
 LIP_FILTERS = GOLDEN["lip_filters"]
 HASH_PARTITIONS = GOLDEN["hash_partitions"]
+DICTIONARIES = GOLDEN["dictionaries"]
 RTOL = 1e-9            # double SUM / AVG on the device (summation order differs; BASELINE.json north_star)
 N = GOLDEN["n_rows"]
 NULLS = np.frombuffer(bytes.fromhex(GOLDEN["nulls"]), dtype="<u8").copy()
@@ -402,3 +409,36 @@ def test_cuda_path_partitions_like_the_reference_header(engine):
     finally:
         G.close()
         engine.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- dictionary limit codes
+@pytest.mark.parametrize("d", DICTIONARIES, ids=[d["name"] for d in DICTIONARIES])
+def test_code_range_is_the_reference_dictionarys_limit_codes(d):
+    """qsgpu_dictionary_code_range (libqsgpu.so, host-only) against CompressionDictionary::getLimitCodesForComparisonTyped:
+    the same set of codes for =, <, <=, >, >= -- and for <> as the complement of = (the reference's caller does that:
+    storage/CompressedTupleStorageSubBlock.cpp:213-236)."""
+    import ctypes as C
+    lib = A.load()
+    w, n = d["width"], d["n_codes"]
+    entries = np.frombuffer(bytes.fromhex(d["entries"]), dtype=np.uint8).copy()
+    assert len(entries) == n * w
+    col = the_table().columns[d["attr"]].data
+    assert n == len(np.unique(col))                                   # the builder's dictionary is the column's distinct values
+    checked = 0
+    for c in d["comparisons"]:
+        es, _rid = expr_set(c)
+        view = es.c()
+        want = np.zeros(n, dtype=bool)
+        want[c["first"]:c["second"]] = True
+        for cmp, expect in ((c["cmp"], want),) + (((A.QS_NE, ~want),) if c["cmp"] == A.QS_EQ else ()):
+            first, count, neg = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+            A.check(lib.qsgpu_dictionary_code_range(d["type"], w if d["type"] == A.QS_CHAR else 0, entries.ctypes.data, n, cmp,
+                                                    C.byref(view.nodes[c["root"]]), view.str_pool, view.str_pool_bytes, C.byref(first),
+                                                    C.byref(count), C.byref(neg)))
+            got = np.zeros(n, dtype=bool)
+            got[first.value:first.value + count.value] = True
+            if neg.value:
+                got = ~got
+            assert (got == expect).all(), (d["name"], c["literal"], cmp, first.value, count.value, neg.value, c["first"], c["second"])
+            checked += 1
+    assert checked == len(d["comparisons"]) * 6 // 5
