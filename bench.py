@@ -181,6 +181,50 @@ def check_q3(got, want):
     return {"rows": len(got), "keys": "exact", "first_row": list(got[0]) if got else None, "max_rel_err": worst, "tol": REL_TOL}
 
 
+def time_reference_engine(device):
+    """The UNMODIFIED reference engine (oracle/_ref/quickstep_cli_shell) on this host's cores: dbgen -s 1 -> COPY -> \\analyze ->
+    each query 5x with printing off, mean of the middle 3 (benchmarks/tpch/run-benchmark.sh + process.py), next to the
+    oracle port over an SF1-sized relation -- the pair calibrates the port the SF100 cpu_baseline is measured with.
+    -> dict, {"error": ...} or None when the engine was not built."""
+    try:
+        import shutil
+        import tempfile
+        import ref_engine as R
+        if not R.available():
+            return None
+        cores = os.cpu_count() or 1
+        store = tempfile.mkdtemp(prefix="qs_store_")
+        try:
+            w0 = time.perf_counter()
+            R.load("1", store, workers=cores)
+            load_s = time.perf_counter() - w0
+            tm = R.time_queries(store, workers=cores)
+            q6_rows, _ = R.run_query(store, "06", workers=cores)
+        finally:
+            shutil.rmtree(store, ignore_errors=True)
+        import qs_oracle as O
+        import oracle_tpch as OT
+        from quickstep_b200 import synth as S
+        O.load(); O.set_workers(cores); O.set_block_rows(BLOCK_ROWS)
+        sh1 = S.db_shape(SF_ROWS[1])
+        t1h = S.host_tables(S.generate_host(sh1, range(sh1["n_chunks"]), SEED, device))
+        port = {}
+        for nm, fn in (("q1", lambda: OT.q1(t1h["lineitem"])), ("q6", lambda: OT.q6(t1h["lineitem"]))):
+            fn()
+            w0 = time.perf_counter()
+            for _ in range(5):
+                fn()
+            port[nm] = (time.perf_counter() - w0) * 1e3 / 5
+        return {"binary": "oracle/_ref/quickstep_cli_shell (unmodified reference, Release, built by oracle/build_ref.sh)",
+                "sf": 1, "cores": cores, "load_s": load_s, "query_ms": {"q1": tm["01"]["ms"], "q6": tm["06"]["ms"], "q3": tm["03"]["ms"]},
+                "runs_ms": {k: v["runs_ms"] for k, v in tm.items()}, "q6_revenue_printed": q6_rows[0][0] if q6_rows else None,
+                "procedure": "dbgen -s 1 -> COPY -> \\analyze -> each query 5x, printing off, mean of the middle 3 (benchmarks/tpch/process.py)",
+                "oracle_port_sf1_ms": port,
+                "port_speedup_over_engine": {k: tm[{"q1": "01", "q6": "06"}[k]]["ms"] / port[k] for k in port}}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's CPU algorithm for the path (oracle port, C) on all host cores, over the
@@ -226,6 +270,11 @@ def run_reference(args):
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "result_check": {"q1_groups": len(rows), "q1_count": sum(int(r["count_order"]) for r in rows)},
     }
+    if world == 1 and not args.no_ref_engine:
+        # kind "reference" evidence beside the port: the unmodified engine itself, at the largest scale its loader takes
+        # inside a bench run (SF1; SF100 is 75 GB of .tbl text: "not run")
+        del host, tables
+        line["reference_engine"] = time_reference_engine(dev)
     print(json.dumps(line), flush=True)
 
 
@@ -549,42 +598,10 @@ def main():
     # the SF100 cpu_baseline is measured with.  Nothing is extrapolated.
     ref_engine = None
     if rank == 0 and world == 1 and not args.no_ref_engine:
-        try:
-            import shutil
-            import tempfile
-            import ref_engine as R
-            if R.available():
-                cores = os.cpu_count() or 1
-                store = tempfile.mkdtemp(prefix="qs_store_")
-                try:
-                    w0 = time.perf_counter()
-                    R.load("1", store, workers=cores)
-                    load_s = time.perf_counter() - w0
-                    tm = R.time_queries(store, workers=cores)
-                    q6_rows, _ = R.run_query(store, "06", workers=cores)
-                finally:
-                    shutil.rmtree(store, ignore_errors=True)
-                import qs_oracle as O
-                import oracle_tpch as OT
-                O.load(); O.set_workers(cores); O.set_block_rows(BLOCK_ROWS)
-                sh1 = S.db_shape(SF_ROWS[1])
-                t1h = S.host_tables(S.generate_host(sh1, range(sh1["n_chunks"]), SEED, device))
-                port = {}
-                for nm, fn in (("q1", lambda: OT.q1(t1h["lineitem"])), ("q6", lambda: OT.q6(t1h["lineitem"]))):
-                    fn()
-                    w0 = time.perf_counter()
-                    for _ in range(5):
-                        fn()
-                    port[nm] = (time.perf_counter() - w0) * 1e3 / 5
-                ref_engine = {"binary": "oracle/_ref/quickstep_cli_shell (unmodified reference, Release, built by oracle/build_ref.sh)",
-                              "sf": 1, "cores": cores, "load_s": load_s, "query_ms": {"q1": tm["01"]["ms"], "q6": tm["06"]["ms"], "q3": tm["03"]["ms"]},
-                              "runs_ms": {k: v["runs_ms"] for k, v in tm.items()}, "q6_revenue_printed": q6_rows[0][0] if q6_rows else None,
-                              "procedure": "dbgen -s 1 -> COPY -> \\analyze -> each query 5x, printing off, mean of the middle 3 (benchmarks/tpch/process.py)",
-                              "oracle_port_sf1_ms": port,
-                              "port_speedup_over_engine": {k: tm[{"q1": "01", "q6": "06"}[k]]["ms"] / port[k] for k in port}}
-                log(f"reference engine at SF1 on {cores} cores: q1 {tm['01']['ms']:.1f} ms, q6 {tm['06']['ms']:.1f} ms, q3 {tm['03']['ms']:.1f} ms")
-        except Exception as ex:
-            ref_engine = {"error": repr(ex)}
+        ref_engine = time_reference_engine(device)
+        if ref_engine and "query_ms" in ref_engine:
+            q = ref_engine["query_ms"]
+            log(f"reference engine at SF1 on {ref_engine['cores']} cores: q1 {q['q1']:.1f} ms, q6 {q['q6']:.1f} ms, q3 {q['q3']:.1f} ms")
 
     if rank == 0:
         sf100 = n == SF_ROWS[100]

@@ -14,7 +14,7 @@ def _run(extra_env=None, gpus=1):
     env = dict(os.environ)
     env.update(extra_env or {})
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--rows", "400000",
-                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+                        "--steps", "2", "--warmup", "1", "--no-ref-engine"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     return [l for l in r.stdout.splitlines() if l.startswith("{")]
 
