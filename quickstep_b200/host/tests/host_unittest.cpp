@@ -313,9 +313,59 @@ static void testBlockBuilder() {
   std::printf("block_builder ok\n");
 }
 
-int main() {
+
+// ------------------------------------------------------------------ insertTuples: rows that leave the device
+// StorageManager::insertTuples writes result rows as SplitRowStore blocks in the reference's on-disk layout.  Checked here
+// with the layer's own reader; with a directory as argv[1] the block images are also written out, and
+// tests/test_intree_boundary.py opens them with the REFERENCE's real StorageBlock class (tests/intree/read_blocks.cpp).
+static void testInsertTuples(const char *dump_dir) {
+  const std::uint64_t n = 100000;          // 38-byte tuples: ~55,000 per 2 MB block -> two blocks
+  std::vector<std::int32_t> a(n);
+  std::vector<double> b(n);
+  std::vector<char> c(n * 10, '\0');
+  struct Date { std::int32_t year; std::uint8_t month, day; std::uint8_t pad[2]; };
+  std::vector<Date> d(n);
+  std::vector<std::int64_t> e(n);
+  for (std::uint64_t i = 0; i < n; ++i) {
+    a[i] = static_cast<std::int32_t>(i) - 50000;
+    b[i] = static_cast<double>(i) * 0.25 - 7.5;
+    std::snprintf(&c[i * 10], 10, "row%llu", static_cast<unsigned long long>(i % 1000));
+    d[i] = Date{1992 + static_cast<std::int32_t>(i % 7), static_cast<std::uint8_t>(1 + i % 12), static_cast<std::uint8_t>(1 + i % 28), {0, 0}};
+    e[i] = static_cast<std::int64_t>(i) * 1000003ll - (1ll << 40);
+  }
+  CatalogRelation rel(9, "result", {{"a", qs_attr{QS_INT, 4}}, {"b", qs_attr{QS_DOUBLE, 8}}, {"c", qs_attr{QS_CHAR, 10}},
+                                    {"d", qs_attr{QS_DATE, 8}}, {"e", qs_attr{QS_LONG, 8}}});
+  StorageManager sm(0, /*pinned_blocks=*/false);
+  const std::vector<block_id> ids = sm.insertTuples(rel, {a.data(), b.data(), c.data(), d.data(), e.data()}, n);
+  EXPECT(ids.size() == 2 && sm.hostBlocksOf(rel) == ids);
+  std::uint64_t row = 0;
+  int file_no = 0;
+  for (block_id id : ids) {
+    const StorageBlock &B = sm.getBlock(id);
+    SplitRowStoreReader reader(B.memory, rel.schema());
+    EXPECT(reader.numTuples() == static_cast<std::uint64_t>(B.num_tuples));
+    bool same = true;
+    for (std::uint64_t i = 0; i < reader.numTuples(); ++i)
+      same = same && std::memcmp(reader.value(i, 0), &a[row + i], 4) == 0 && std::memcmp(reader.value(i, 1), &b[row + i], 8) == 0 &&
+             std::memcmp(reader.value(i, 2), &c[(row + i) * 10], 10) == 0 && std::memcmp(reader.value(i, 3), &d[row + i], 6) == 0 &&
+             std::memcmp(reader.value(i, 4), &e[row + i], 8) == 0;
+    EXPECT(same);
+    if (dump_dir) {
+      const std::string path = std::string(dump_dir) + "/block_" + std::to_string(file_no++) + ".bin";
+      std::FILE *f = std::fopen(path.c_str(), "wb");
+      EXPECT(f != nullptr);
+      if (f) { EXPECT(std::fwrite(B.memory, 1, B.size, f) == B.size); std::fclose(f); }
+    }
+    row += reader.numTuples();
+  }
+  EXPECT(row == n);
+  std::printf("insert_tuples_blocks ok\n");
+}
+
+int main(int argc, char **argv) {
   testExprSetAppend();
   testBlockBuilder();
+  testInsertTuples(argc > 1 ? argv[1] : nullptr);
   testBlockingDependency();
   testPipelinedFeed();
   testDiamondAndRepeatedCalls();

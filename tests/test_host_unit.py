@@ -12,5 +12,5 @@ def test_host_unit_binary():
     assert os.path.exists(BIN), "build it: make -C quickstep_b200/host"
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    for case in ("expr_set_append ok", "block_builder ok", "blocking_dependency ok", "pipelined_feed ok", "diamond ok", "all host unit tests passed"):
+    for case in ("expr_set_append ok", "block_builder ok", "insert_tuples_blocks ok", "blocking_dependency ok", "pipelined_feed ok", "diamond ok", "all host unit tests passed"):
         assert case in r.stdout, r.stdout
