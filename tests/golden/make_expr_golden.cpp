@@ -635,6 +635,28 @@ int main(int argc, char **argv) {
                      Cmp(GE, Attr(A_DISC), LitD(0.05)), Cmp(LE, Attr(A_DISC), LitD(0.07)), Cmp(LT, Attr(A_I), LitI(240))}));
   g_nullable_mode = false;
 
+  // ------------------------------------------------------------------ more type mixes (checked against the oracle on the
+  // CPU only: added after the device runs of profiles/r4a-r4d; names start with "extra_")
+  ScalarCase(out, "extra_float_times_long", "f * l", Bin(MUL, Attr(A_F), Attr(A_L)));
+  ScalarCase(out, "extra_float_plus_long_literal", "f + 100 (LONG)", Bin(ADD, Attr(A_F), LitL(100)));
+  ScalarCase(out, "extra_long_minus_float", "l2 - f", Bin(SUB, Attr(A_L2), Attr(A_F)));
+  ScalarCase(out, "extra_int_div_double", "i / disc", Bin(DIV, Attr(A_I), Attr(A_DISC)));
+  ScalarCase(out, "extra_double_mod_free_chain", "(d - tax) * (disc + 1) / (tax + 1)",
+             Bin(DIV, Bin(MUL, Bin(SUB, Attr(A_D), Attr(A_TAX)), Bin(ADD, Attr(A_DISC), LitI(1))), Bin(ADD, Attr(A_TAX), LitI(1))));
+  ScalarCase(out, "extra_cast_double_to_float", "CAST(disc AS FLOAT) * f", Bin(MUL, Cast(kFloat, Attr(A_DISC)), Attr(A_F)));
+  ScalarCase(out, "extra_cast_long_to_double", "CAST(l AS DOUBLE) / 3.0", Bin(DIV, Cast(kDouble, Attr(A_L)), LitD(3.0)));
+  ScalarCase(out, "extra_negate_float", "-f", Neg(Attr(A_F)));
+  PredicateCase(out, "extra_float_vs_long_literal", "f < 3 (LONG)", Cmp(LT, Attr(A_F), LitL(3)));
+  PredicateCase(out, "extra_long_vs_double_literal", "l < 1e9 + 0.5", Cmp(LT, Attr(A_L), LitD(1e9 + 0.5)));
+  PredicateCase(out, "extra_int_vs_long_literal_out_of_int_range", "i < 10000000000", Cmp(LT, Attr(A_I), LitL(10000000000ll)));
+  PredicateCase(out, "extra_int_vs_float_literal", "i >= 2.5 (FLOAT)", Cmp(GE, Attr(A_I), LitF(2.5f)));
+  PredicateCase(out, "extra_long_vs_float_attr", "l2 > f", Cmp(GT, Attr(A_L2), Attr(A_F)));
+  PredicateCase(out, "extra_double_vs_int_attr", "d <= i2", Cmp(LE, Attr(A_D), Attr(A_I2)));
+  PredicateCase(out, "extra_date_vs_date_attr_expr", "dt < DATE '1995-01-01' OR dt >= DATE '1998-01-01'",
+                Or({Cmp(LT, Attr(A_DT), LitDate(1995, 1, 1)), Cmp(GE, Attr(A_DT), LitDate(1998, 1, 1))}));
+  PredicateCase(out, "extra_char1_range", "c1 >= 'N'", Cmp(GE, Attr(A_C1), LitC("N")));
+  PredicateCase(out, "extra_char10_le_prefix", "c10 <= 'FURN'", Cmp(LE, Attr(A_C10), LitC("FURN")));
+
   std::fprintf(out, "\n ],\n \"aggregates\": [");
   AllAggregates(out);
   g_nullable_mode = true;

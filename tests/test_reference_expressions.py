@@ -46,7 +46,10 @@ from quickstep_b200.table import Column, HostTable, np_dtype
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_expressions.json")))
-CASES = [c for c in GOLDEN["cases"] if not c["nullable"]]
+# "extra_" cases were added after the device runs of profiles/r4a-r4d: the oracle is held against them, the -m gpu tests
+# keep the case list that ran on the hardware
+EXTRA_CASES = [c for c in GOLDEN["cases"] if c["name"].startswith("extra_")]
+CASES = [c for c in GOLDEN["cases"] if not c["nullable"] and not c["name"].startswith("extra_")]
 NULL_CASES = [c for c in GOLDEN["cases"] if c["nullable"]]
 AGGREGATES = GOLDEN["aggregates"]
 LIP_FILTERS = GOLDEN["lip_filters"]
@@ -128,7 +131,7 @@ def check_scalar(case, ids, vals, val_nulls):
 
 
 def test_golden_file_is_what_the_generator_writes():
-    assert len(CASES) == 69 and len(NULL_CASES) == 32 and N == 512
+    assert len(CASES) == 69 and len(NULL_CASES) == 32 and len(EXTRA_CASES) == 17 and N == 512
     assert len(AGGREGATES) == 66 and len(LIP_FILTERS) == 24
     assert GOLDEN["nullable_attributes"] == [0, 2, 4, 7, 9]
     assert set(np.nonzero([(NULLS >> np.uint64(a) & np.uint64(1)).any() for a in range(RID)])[0].tolist()) == {0, 2, 4, 7, 9}
@@ -139,6 +142,11 @@ def test_golden_file_is_what_the_generator_writes():
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_oracle_gives_the_reference_classes_results(oracle, case):
+    run_case(OracleBackend(), the_table(), case)
+
+
+@pytest.mark.parametrize("case", EXTRA_CASES, ids=[c["name"] for c in EXTRA_CASES])
+def test_oracle_gives_the_reference_classes_results_on_more_type_mixes(oracle, case):
     run_case(OracleBackend(), the_table(), case)
 
 
