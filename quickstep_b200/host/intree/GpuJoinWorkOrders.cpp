@@ -28,6 +28,7 @@
 #include "query_execution/WorkOrdersContainer.hpp"
 #include "relational_operators/HashJoinOperator.hpp"
 #include "relational_operators/RelationalOperator.hpp"
+#include "relational_operators/SortMergeRunOperator.hpp"
 #include "relational_operators/WorkOrder.hpp"
 #include "storage/AggregationOperationState.pb.h"
 #include "storage/HashTable.pb.h"
@@ -696,6 +697,96 @@ class GpuFinalizeAggregationOperator : public RelationalOperator {
   const QueryContext::insert_destination_id output_destination_index_;
   GpuQueryState *state_;
   const std::uint64_t max_groups_;
+  bool started_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ORDER BY [LIMIT]: the reference plans a SortRunGenerationOperator (sort every block into a run) followed by a
+// SortMergeRunOperator (merge the runs, keep top_k; relational_operators/SortMergeRunOperator.hpp:72-240).  On the device
+// the whole input is one relation: the GPU run generation has nothing to do, and the merge operator sorts it with ONE
+// qsgpu_topk (limit = top_k, or every row when there is no LIMIT).
+// ---------------------------------------------------------------------------------------------------------------------
+class GpuTopKWorkOrder : public WorkOrder {
+ public:
+  GpuTopKWorkOrder(const std::size_t query_id, qsgpu_relation_t input, std::vector<qs_sort_key> keys, const std::uint64_t limit,
+                   const CatalogRelationSchema &output_relation, InsertDestination *output_destination, qsgpu_relation_t *device_output)
+      : WorkOrder(query_id), input_(input), keys_(std::move(keys)), limit_(limit), output_relation_(output_relation),
+        output_destination_(output_destination), device_output_(device_output) {}
+  ~GpuTopKWorkOrder() override {}
+
+  void execute() override {
+    qsgpu_relation_t sorted = nullptr;
+    QS_GPU_CHECK(qsgpu_topk(input_, static_cast<std::uint32_t>(keys_.size()), keys_.data(), limit_, &sorted));
+    if (device_output_) {
+      *device_output_ = sorted;
+      return;
+    }
+    EmitToInsertDestination(sorted, output_relation_, limit_, output_destination_);      // the query's result relation
+    QS_GPU_CHECK(qsgpu_relation_destroy(sorted));
+  }
+
+ private:
+  qsgpu_relation_t input_;
+  const std::vector<qs_sort_key> keys_;
+  const std::uint64_t limit_;
+  const CatalogRelationSchema &output_relation_;
+  InsertDestination *output_destination_;
+  qsgpu_relation_t *device_output_;
+};
+
+// SortMergeRunOperator's constructor arguments (what ExecutionGenerator::convertSort passes, ExecutionGenerator.cpp:
+// 2227-2351) plus the lowered sort keys and the device image of the input.
+class GpuSortMergeRunOperator : public RelationalOperator {
+ public:
+  GpuSortMergeRunOperator(const std::size_t query_id, const CatalogRelation &input_relation, const CatalogRelation &output_relation,
+                          const QueryContext::insert_destination_id output_destination_index, const CatalogRelation &run_relation,
+                          const QueryContext::insert_destination_id run_block_destination_index,
+                          const QueryContext::sort_config_id sort_config_index, const std::size_t merge_factor, const std::size_t top_k,
+                          const bool input_relation_is_stored, std::vector<qs_sort_key> keys, qsgpu_relation_t device_input,
+                          const std::uint64_t max_rows)
+      : RelationalOperator(query_id, 1u, false, 1u), input_relation_(input_relation), output_relation_(output_relation),
+        output_destination_index_(output_destination_index), sort_config_index_(sort_config_index), top_k_(top_k),
+        input_relation_is_stored_(input_relation_is_stored), keys_(std::move(keys)), device_input_(device_input),
+        max_rows_(max_rows), started_(false) {}
+  ~GpuSortMergeRunOperator() override {}
+
+  OperatorType getOperatorType() const override { return kSortMergeRun; }
+  std::string getName() const override { return "GpuSortMergeRunOperator"; }
+
+  bool getAllWorkOrders(WorkOrdersContainer *container, QueryContext *query_context, StorageManager *storage_manager,
+                        const tmb::client_id scheduler_client_id, tmb::MessageBus *bus) override {
+    // a sort consumes its whole input: nothing before the producer has finished
+    if (!input_relation_is_stored_ && !done_feeding_input_relation_) return false;
+    if (!started_) {
+      container->addNormalWorkOrder(
+          new GpuTopKWorkOrder(query_id_, device_input_, keys_, top_k_ ? top_k_ : max_rows_, output_relation_,
+                               query_context->getInsertDestination(output_destination_index_), nullptr),
+          op_index_);
+      started_ = true;
+    }
+    return true;
+  }
+
+  bool getAllWorkOrderProtos(WorkOrderProtosContainer *container) override {
+    LOG(FATAL) << "GPU work orders are single-node: -DENABLE_DISTRIBUTED builds keep the CPU operators";
+    return true;
+  }
+
+  void feedInputBlock(const block_id input_block_id, const relation_id input_relation_id, const partition_id part_id) override {}
+
+  QueryContext::insert_destination_id getInsertDestinationID() const override { return output_destination_index_; }
+  const relation_id getOutputRelationID() const override { return output_relation_.getID(); }
+
+ private:
+  const CatalogRelation &input_relation_;
+  const CatalogRelation &output_relation_;
+  const QueryContext::insert_destination_id output_destination_index_;
+  const QueryContext::sort_config_id sort_config_index_;
+  const std::size_t top_k_;
+  const bool input_relation_is_stored_;
+  const std::vector<qs_sort_key> keys_;
+  qsgpu_relation_t device_input_;
+  const std::uint64_t max_rows_;
   bool started_;
 };
 

@@ -15,6 +15,7 @@
 #include "expressions/aggregation/AggregateFunction.pb.h"
 #include "storage/AggregationOperationState.pb.h"
 #include "storage/HashTable.pb.h"
+#include "utility/SortConfiguration.pb.h"
 #include "types/Type.hpp"
 #include "types/TypeID.hpp"
 
@@ -119,6 +120,25 @@ inline void LowerAggregationState(const serialization::AggregationOperationState
       default: out->strategy = QS_AGG_SEPARATE_CHAINING;
     }
   }
+}
+
+// SortConfiguration (utility/SortConfiguration.proto; reconstructed at query_execution/QueryContext.cpp:128-131) as the
+// qs_sort_key list of qsgpu_topk: ORDER BY expressions are attributes of the sorted relation (the optimizer projects
+// anything else first); `null_first` is always spelled out in the proto -- the parser has already applied the default
+// (NULLs first iff descending, parser/ParseOrderBy.hpp:53-66) -- so it travels as an explicit NULLS FIRST / LAST.
+inline std::vector<qs_sort_key> LowerSortConfiguration(const serialization::SortConfiguration &proto) {
+  std::vector<qs_sort_key> keys;
+  for (int k = 0; k < proto.order_by_list_size(); ++k) {
+    const serialization::SortConfiguration::OrderBy &ob = proto.order_by_list(k);
+    if (ob.expression().data_source() != serialization::Scalar::ATTRIBUTE)
+      LOG(FATAL) << "GPU path: ORDER BY expressions other than attributes keep their CPU operators";
+    qs_sort_key key{};
+    key.attr = static_cast<std::uint32_t>(ob.expression().GetExtension(serialization::ScalarAttribute::attribute_id));
+    key.descending = (ob.is_ascending() ? 0u : QS_SORT_DESCENDING) | (ob.null_first() ? QS_SORT_NULLS_FIRST : QS_SORT_NULLS_LAST);
+    keys.push_back(key);
+  }
+  if (keys.size() > 4) LOG(FATAL) << "GPU path: more than four sort attributes";
+  return keys;
 }
 
 }  // namespace gpu

@@ -369,6 +369,9 @@ void PlanQuery(FILE *out, const char *name, const std::string &sql, bool first_q
                    ob.expression().GetExtension(serialization::ScalarAttribute::attribute_id), ob.is_ascending() ? "true" : "false",
                    ob.null_first() ? "true" : "false");
     }
+    std::fprintf(out, "], \"qs_sort_keys\": [");
+    const std::vector<qs_sort_key> lowered = gpu::LowerSortConfiguration(sc);
+    for (std::size_t k = 0; k < lowered.size(); ++k) std::fprintf(out, "%s[%u, %u]", k ? ", " : "", lowered[k].attr, lowered[k].descending);
     std::fprintf(out, "]}");
   }
   std::fprintf(out, "]}");

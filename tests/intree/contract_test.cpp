@@ -182,7 +182,8 @@ int main(int argc, char **argv) {
         new gpu::GpuHashJoinOperator(1, *t0, *lineitem, true, key, false, 1, false, *t0, 0, 0, QueryContext::kInvalidPredicateId, 0,
                                      HashJoinOperator::JoinType::kLeftSemiJoin, &state, {extent}, nullptr),
         new gpu::GpuBuildLIPFilterOperator(1, *t0, QueryContext::kInvalidPredicateId, false, &state, {extent}),
-        new gpu::GpuFinalizeAggregationOperator(1, 0, 1, false, 1, *t0, 0, &state, 256)};
+        new gpu::GpuFinalizeAggregationOperator(1, 0, 1, false, 1, *t0, 0, &state, 256),
+        new gpu::GpuSortMergeRunOperator(1, *t0, *t0, 0, *t0, 0, 0, 128, 10, false, gpu::LowerSortConfiguration(planned.sort_configs(0)), nullptr, 1000)};
     for (RelationalOperator *o : never_ops) o->getAllWorkOrders(&container, &query_context, nullptr, 0, nullptr);
   }
   std::printf("in-tree contract ok\n");

@@ -240,10 +240,11 @@ class Interpreter:
                 cfg = self.plan["sort_configs"][wo["sort_config_index"]]
                 src = self.rel[wo["relation_id"]]
                 keys = []
-                for k in cfg["keys"]:
-                    assert k["relation_id"] == wo["relation_id"]
-                    # NOT NULL keys here: null_first has nothing to order
-                    keys.append((k["attribute_id"], not k["ascending"]))
+                for k, (attr, flags) in zip(cfg["keys"], cfg["qs_sort_keys"]):       # LowerSortConfiguration's qs_sort_key list
+                    assert k["relation_id"] == wo["relation_id"] and attr == k["attribute_id"]
+                    assert bool(flags & 1) == (not k["ascending"]) and bool(flags & 2) == k["null_first"] and bool(flags & 4) == (not k["null_first"])
+                    # NOT NULL keys here: the NULL placement has nothing to order
+                    keys.append((attr, bool(flags & 1)))
                 top = self.B.topk(src, keys, max(1, src.n_rows))
                 self.store(self.destination(wo["insert_destination_index"]), [c.data for c in top.columns])
                 self.sorted = self.destination(wo["insert_destination_index"])
