@@ -89,8 +89,8 @@ def append_exprs(es: ExprSet, obj):
 
 
 class Interpreter:
-    def __init__(self, plan, tables):
-        self.plan, self.B = plan, OracleBackend()
+    def __init__(self, plan, tables, backend=None):
+        self.plan, self.B = plan, backend or OracleBackend()
         self.schema = {r["id"]: [(t, w) for _n, t, w in r["attributes"]] for r in plan["relations"]}
         self.rel = {r["id"]: tables[r["name"]] for r in plan["relations"] if not r["temporary"]}
         self.lips = []
@@ -258,9 +258,55 @@ class Interpreter:
         return self.rel[result]
 
 
+class StagingBackend:
+    """The Backend interface of tests/backends.py over HOST tables for a backend that works on staged relations: inputs are
+    staged (inner.relation) for every call and outputs come back as host tables, so the interpreter -- which keeps its
+    temporaries on the host -- walks the same code over the oracle and over the device
+    (tests/test_zz_reference_plans_on_device.py wraps GpuBackend; here it wraps OracleBackend to test the plumbing)."""
+
+    def __init__(self, inner):
+        self.G, self.staged = inner, {}
+
+    def up(self, table):
+        if id(table) not in self.staged:
+            self.staged[id(table)] = (table, self.G.relation(table))          # keeps `table` alive: ids stay unique
+        return self.staged[id(table)][1]
+
+    def make_lip(self, *a, **k):
+        return self.G.make_lip(*a, **k)
+
+    def build_lip(self, rel, es, pred, probe, build):
+        self.G.build_lip(self.up(rel), es if es is not None else ExprSet(), pred, probe, build)
+
+    def select(self, rel, es, pred, probe, roots, out_schema, capacity=None):
+        return self.G.select(self.up(rel), es, pred, probe, roots, out_schema, capacity)
+
+    def hash_join(self, build, bes_pred, build_key, probe, es, probe_pred, probe_key, join_type, residual, roots, out_schema, capacity,
+                  build_es=None, probe_lips=None):
+        return self.G.hash_join(self.up(build), bes_pred, build_key, self.up(probe), es, probe_pred, probe_key, join_type, residual, roots,
+                                out_schema, capacity, build_es=build_es, probe_lips=probe_lips)
+
+    def aggregate(self, rel, es, pred, aggregates, group_roots, strategy, key_schema, probe=None):
+        return self.G.aggregate(self.up(rel), es, pred, aggregates, group_roots, strategy, key_schema, probe, estimated=max(16, rel.n_rows))
+
+    def topk(self, rel, keys, limit):
+        return self.G.topk(self.up(rel), keys, limit)
+
+    def close(self):
+        if hasattr(self.G, "close"):
+            self.G.close()
+
+
 @pytest.fixture(scope="module")
 def tables(oracle):
     return D.golden_tables()
+
+
+@pytest.mark.parametrize("query", ["q6", "q1", "q3"])
+def test_staging_backend_plumbing(tables, query):
+    """The adapter the device run uses, over the oracle: same answers as the direct run."""
+    out = Interpreter(PLANS[query], tables, StagingBackend(OracleBackend())).run()
+    {"q6": check_q6, "q1": check_q1, "q3": check_q3}[query](out)
 
 
 def test_plans_are_the_optimizers(tables):
@@ -287,14 +333,12 @@ def test_plans_are_the_optimizers(tables):
     assert sorted(int.from_bytes(bytes.fromhex(n[6])[:4], "little") for n in lits) == [1994, 1995]
 
 
-def test_q6_plan_gives_the_engines_answer(tables):
-    out = Interpreter(PLANS["q6"], tables).run()
+def check_q6(out):
     want = ENGINE["sf0.01"]["q6"]["rows"]
     assert out.n_rows == 1 and close(out.columns[0].data[0], float(want[0][0])), (out.columns[0].data, want)
 
 
-def test_q1_plan_gives_the_engines_answer(tables):
-    out = Interpreter(PLANS["q1"], tables).run()
+def check_q1(out):
     want = ENGINE["sf0.01"]["q1"]["rows"]
     assert out.n_rows == len(want) == 4 and len(out.columns) == 10
     for i, w in enumerate(want):
@@ -304,9 +348,7 @@ def test_q1_plan_gives_the_engines_answer(tables):
         assert int(out.columns[9].data[i]) == int(w[9])
 
 
-def test_q3_plan_gives_the_engines_answer(tables):
-    it = Interpreter(PLANS["q3"], tables)
-    out = it.run()
+def check_q3(out):
     want = ENGINE["sf0.01"]["q3"]["rows"]
     assert out.n_rows >= len(want) == 10 and len(out.columns) == 4
     for i, w in enumerate(want):            # LIMIT 10 of the SortMergeRunOperator
@@ -314,6 +356,18 @@ def test_q3_plan_gives_the_engines_answer(tables):
         assert int(out.columns[0].data[i]) == int(w[0]) and "%04d-%02d-%02d" % (d["year"], d["month"], d["day"]) == w[2]
         assert int(out.columns[3].data[i]) == int(w[3])
         assert close(out.columns[1].data[i], float(w[1])), (i, out.columns[1].data[i], w[1])
+
+
+def test_q6_plan_gives_the_engines_answer(tables):
+    check_q6(Interpreter(PLANS["q6"], tables).run())
+
+
+def test_q1_plan_gives_the_engines_answer(tables):
+    check_q1(Interpreter(PLANS["q1"], tables).run())
+
+
+def test_q3_plan_gives_the_engines_answer(tables):
+    check_q3(Interpreter(PLANS["q3"], tables).run())
 
 
 @pytest.mark.parametrize("which", ["q3_sf10", "q3_sf100"])

@@ -1,0 +1,56 @@
+"""The reference optimizer's own plans, lowered by the in-tree binding, EXECUTED ON THE DEVICE through the C ABI.
+
+Same interpreter as tests/test_reference_plans.py / test_reference_plans_more.py (DAG order, every operator fed exactly the
+lowered objects its serialized work order names), but every operator runs on the GPU: each call stages its input
+relations, runs the C-ABI entry (qsgpu_select / qsgpu_build_lip_filter / qsgpu_join_build + probe / qsgpu_agg_create + run +
+finalize / qsgpu_topk) and reads the output relation back.  The answers must be the ones the unmodified engine printed.
+
+STATUS: written after round 2's GPU budget was spent -- these eight tests have NOT yet run on hardware.  They are therefore
+`xfail(strict=False)`: an XPASS in the driver's log is the first hardware evidence for them, an xfail names what the
+device path still refuses for a plan shape (the oracle-level tests of the same plans are green).  The file sorts last so
+that nothing runs after it.  Q1 / Q3 / Q6 use only operator shapes bench.py and the -m gpu suite already run on the device;
+Q4 / Q5 / Q17 / Q19 / Q21 add CHAR(15) / CHAR(25) group-by and sort keys, build-side predicates, residual predicates on semi /
+anti joins and empty inputs.
+"""
+import pytest
+
+import tpch_data as D
+from backends import GpuBackend
+
+import test_reference_plans as P
+import test_reference_plans_more as M
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="not yet run on hardware (written after the round's GPU budget was spent)")]
+
+
+@pytest.fixture()
+def device(engine):
+    b = P.StagingBackend(GpuBackend(engine))
+    yield b
+    try:                # a plan the device refuses must show up as that test's xfail, not as a teardown error
+        b.close()
+        engine.synchronize()
+    except Exception as ex:          # noqa: BLE001
+        print("teardown after a failed plan:", repr(ex))
+
+
+@pytest.fixture(scope="module")
+def hot_tables(oracle):
+    return D.golden_tables()
+
+
+@pytest.fixture(scope="module")
+def full_tables(oracle):
+    return M.load_full_tables()
+
+
+@pytest.mark.parametrize("query,check", [("q6", P.check_q6), ("q1", P.check_q1), ("q3", P.check_q3)])
+def test_hot_path_plans_on_the_device(device, hot_tables, query, check):
+    check(P.Interpreter(P.PLANS[query], hot_tables, device).run())
+
+
+@pytest.mark.parametrize("query", ["q4", "q5", "q17", "q19", "q21"])
+def test_next_plans_on_the_device(device, full_tables, query):
+    it, out = M.run(query, full_tables, device)
+    M.check(query, it, out)
