@@ -89,8 +89,9 @@ def append_exprs(es: ExprSet, obj):
 
 
 class Interpreter:
-    def __init__(self, plan, tables, backend=None):
-        self.plan, self.B = plan, backend or OracleBackend()
+    def __init__(self, plan, tables, backend=None, limit=None):
+        # limit: the query's LIMIT (SortMergeRunOperator's top_k is not part of any serialized entry); None sorts everything
+        self.plan, self.B, self.limit = plan, backend or OracleBackend(), limit
         self.schema = {r["id"]: [(t, w) for _n, t, w in r["attributes"]] for r in plan["relations"]}
         self.rel = {r["id"]: tables[r["name"]] for r in plan["relations"] if not r["temporary"]}
         self.lips = []
@@ -245,7 +246,7 @@ class Interpreter:
                     assert bool(flags & 1) == (not k["ascending"]) and bool(flags & 2) == k["null_first"] and bool(flags & 4) == (not k["null_first"])
                     # NOT NULL keys here: the NULL placement has nothing to order
                     keys.append((attr, bool(flags & 1)))
-                top = self.B.topk(src, keys, max(1, src.n_rows))
+                top = self.B.topk(src, keys, max(1, min(self.limit or src.n_rows, src.n_rows)))
                 self.store(self.destination(wo["insert_destination_index"]), [c.data for c in top.columns])
                 self.sorted = self.destination(wo["insert_destination_index"])
             elif op["name"] == "SortMergeRunOperator":
