@@ -288,7 +288,10 @@ class StagingBackend:
                                 out_schema, capacity, build_es=build_es, probe_lips=probe_lips)
 
     def aggregate(self, rel, es, pred, aggregates, group_roots, strategy, key_schema, probe=None):
-        return self.G.aggregate(self.up(rel), es, pred, aggregates, group_roots, strategy, key_schema, probe, estimated=max(16, rel.n_rows))
+        # table sizing: a compact-key state keeps the optimizer's small-group estimate (above 256 the library would take
+        # the hash strategy); hash / dense tables are sized for the rows they may hold
+        estimated = 16 if strategy == A.QS_AGG_COMPACT_KEY else max(16, rel.n_rows)
+        return self.G.aggregate(self.up(rel), es, pred, aggregates, group_roots, strategy, key_schema, probe, estimated=estimated)
 
     def topk(self, rel, keys, limit):
         return self.G.topk(self.up(rel), keys, limit)
