@@ -20,7 +20,7 @@ from backends import GpuBackend
 import test_reference_plans as P
 import test_reference_plans_more as M
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
               pytest.mark.xfail(strict=False, reason="not yet run on hardware (written after the round's GPU budget was spent)")]
 
 
