@@ -7,8 +7,9 @@ finalize / qsgpu_topk) and reads the output relation back.  The answers must be 
 
 STATUS (profiles/r4e_reference_plans_on_device.log, one B200, the round's last seconds of GPU budget): Q6, Q1, Q3 and Q17
 ran and gave the engine's answers on the device (XPASS while they were still marked xfail) and are plain `-m gpu` tests
-now; Q19 ran and failed (cause not yet examined: its residual predicate is a 107-node disjunction over both join sides
-next to a build-side predicate); Q4, Q5 and Q21 have NOT run on hardware (Q4 and Q21 sort on CHAR(15) / CHAR(25) keys, which
+now; Q19 ran and failed -- as lower.cu reads, on `p_brand = 'Brand#12'` inside the join's residual predicate: a CHAR
+comparison on a BUILD-side attribute is refused with QSGPU_ERR_UNSUPPORTED ("CHAR comparison other than attribute-vs-literal"),
+and its 19 string literals exceed the VM's 96-byte string pool; Q4, Q5 and Q21 have NOT run on hardware (Q4 and Q21 sort on CHAR(15) / CHAR(25) keys, which
 qsgpu_topk refuses above 8 bytes).  Those four stay `xfail(strict=False)`: an XPASS in a later log is their first hardware
 evidence.  The file sorts last so that nothing runs after it.
 """
